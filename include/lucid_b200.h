@@ -1,0 +1,113 @@
+/* lucid_b200.h -- C ABI of the B200 exact-OIT rasteriser (drop-in for LucidRenderer's hot path).
+ *
+ * Each entry point names the reference interface it stands in for (file:line under the
+ * nadult/lucid tree).  Plain pointers and sizes only; the buffer layouts are in lucid_abi.h.
+ * All calls on one handle must come from one host thread at a time (the reference is single
+ * threaded, single queue); handles are independent, so one handle per GPU scales out.
+ * Every function returns 0 on success or a negative LUCID_E_* code; lucid_last_error() gives text.
+ */
+#ifndef LUCID_B200_H
+#define LUCID_B200_H
+
+#include "lucid_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lucid_renderer lucid_renderer;
+
+enum {
+	LUCID_OK = 0,
+	LUCID_E_INVALID = -1,  /* bad argument */
+	LUCID_E_CUDA = -2,	   /* CUDA runtime error (no device, out of memory, launch failure) */
+	LUCID_E_LIMIT = -3,	   /* a documented limit was exceeded (instances, bin coordinates) */
+	LUCID_E_STATE = -4	   /* call sequence error (e.g. render before set_geometry) */
+};
+
+enum { LUCID_MEM_HOST = 0, LUCID_MEM_DEVICE = 1, LUCID_MEM_NONE = 2 };
+
+enum {
+	LUCID_RENDER_ASYNC = 1,		  /* return after enqueueing; pair with lucid_wait() */
+	LUCID_RENDER_SKIP_INFO = 2,	  /* do not copy LucidInfo back this frame */
+	LUCID_RENDER_FRAG_COUNTS = 4  /* also write the per-pixel fragment-count image (parity tests) */
+};
+
+/* LucidRenderer::exConstruct(device, compiler, opts, view_size), src/lucid_renderer.cpp:186-317.
+ * Zero fields select the reference's defaults. */
+typedef struct LucidCreateInfo {
+	int32_t width, height;		  /* view_size; <= 4096 (7-bit bin coordinates, funcs.glsl:52-59) */
+	uint32_t opts;				  /* LUCID_OPT_* (LucidRenderOpt flags) */
+	int32_t max_visible_quads;	  /* 0 -> 4793490 (= min(2^30/224, VRAM_MB*1024), lucid_renderer.cpp:204) */
+	int32_t max_dispatches;		  /* 0 -> 256 (lucid_renderer.cpp:203) */
+	int32_t device;				  /* CUDA device ordinal */
+	void *stream;				  /* cudaStream_t to run on; NULL -> the renderer creates one */
+	int32_t bin_row_begin, bin_row_end; /* owned bin rows [begin,end) for the multi-GPU split; 0,0 -> all */
+} LucidCreateInfo;
+
+int lucid_create(const LucidCreateInfo *info, lucid_renderer **out);
+void lucid_destroy(lucid_renderer *r);
+const char *lucid_last_error(const lucid_renderer *r); /* r may be NULL: error of the failed create */
+
+/* RenderContext::verts / quads_ib (src/lucid_base.h:62-84): positions float[3*nv] tightly packed,
+ * colors RGBA8, tex coords float[2*nv], normals 10-10-10 (scene.cpp:338-343), quad indices
+ * u32[4*nq].  colors / uvs / normals may be NULL.  LUCID_MEM_HOST: copied now; LUCID_MEM_DEVICE:
+ * borrowed, must stay valid while rendering (as the reference borrows the Scene's buffers). */
+int lucid_set_geometry(lucid_renderer *r, const float *positions, int32_t num_verts,
+					   const uint32_t *colors, const float *uvs, const uint32_t *normals,
+					   const uint32_t *quad_indices, int32_t num_quads, int32_t memory);
+
+/* opaque_tex / trans_tex (lucid_base.h:82, bound at lucid_renderer.cpp:550-552): slot 0 opaque,
+ * slot 1 transparent; tightly packed RGBA8 mip chain, level l is max(1,w>>l) x max(1,h>>l).
+ * Sampler: repeat, bilinear, mip-linear, no anisotropy (DESIGN.md "Texture filter"). */
+int lucid_set_texture(lucid_renderer *r, int32_t slot, const uint8_t *rgba8_mips, int32_t width,
+					  int32_t height, int32_t levels);
+
+/* change the owned bin rows between frames (load balancing of the bin-row split) */
+int lucid_set_bin_rows(lucid_renderer *r, int32_t begin, int32_t end);
+
+/* LucidRenderer::render(const Context&), src/lucid_renderer.cpp:319-350: config as filled by
+ * setupInputData, instances / colours / uv rects as filled by uploadInstances (host pointers).
+ * out_rgba8: RGBA8 image (the reference writes the swap-chain image), row pitch in bytes;
+ * out_memory says where it lives; LUCID_MEM_NONE keeps the image in the renderer's own buffer.
+ * A device pointer may be peer memory: the raster kernels then store across NVLink directly. */
+int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstanceData *instances,
+				 const uint32_t *instance_colors, const float *instance_uv_rects,
+				 int32_t num_instances, void *out_rgba8, size_t pitch_bytes, int32_t out_memory,
+				 uint32_t flags);
+int lucid_wait(lucid_renderer *r);
+
+/* m_last_info (lucid_renderer.cpp:341-346): LucidInfo followed by 10*bin_count ints */
+int lucid_read_info(lucid_renderer *r, uint32_t *dst, size_t num_words);
+int lucid_bin_count(const lucid_renderer *r);
+
+/* per-stage GPU milliseconds of the last frame (PERF_GPU_SCOPE replacement):
+ * [0] setup [1] bin count [2] bin offsets/categories [3] bin dispatch+sort [4] raster low
+ * [5] raster high [6] finish [7] whole frame */
+int lucid_stage_times(lucid_renderer *r, float ms[8]);
+
+/* ---- inspection of intermediate buffers (what tests compare with the CPU checker) ---- */
+/* which: 0 small quads (slot i), 1 large quads (slot MVQ-1-i) */
+int lucid_read_quad_aabbs(lucid_renderer *r, int32_t which, uint32_t *dst, int32_t count);
+/* 21 words per triangle in the reference's field order: bary0 bary1 scan0 scan1 depth normal */
+int lucid_read_tri_records(lucid_renderer *r, int32_t which, uint32_t *dst, int32_t num_quads);
+/* 16 words per quad: colors normals uv0 uv1 */
+int lucid_read_quad_attrs(lucid_renderer *r, int32_t which, uint32_t *dst, int32_t num_quads);
+int lucid_read_bin_lists(lucid_renderer *r, uint32_t *bin_quads, size_t num_bin_quads,
+						 uint32_t *bin_tris, size_t num_bin_tris);
+int lucid_read_frag_counts(lucid_renderer *r, uint32_t *dst);
+int lucid_read_image(lucid_renderer *r, void *dst_rgba8, size_t pitch_bytes);
+
+/* ---- multi-GPU composite over NVLink: share one GPU's image with the other ranks ---- */
+/* device pointer and pitch (bytes) of the renderer-owned image */
+int lucid_image_pointer(lucid_renderer *r, void **device_ptr, size_t *pitch_bytes);
+/* 64-byte cudaIpcMemHandle_t of the renderer-owned image, to be sent to peer processes */
+int lucid_ipc_export_image(lucid_renderer *r, void *handle64);
+/* maps a peer's image into this process; pass the result as out_rgba8 with LUCID_MEM_DEVICE */
+int lucid_ipc_open_image(lucid_renderer *r, const void *handle64, void **device_ptr);
+int lucid_ipc_close_image(lucid_renderer *r, void *device_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

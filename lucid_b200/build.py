@@ -1,0 +1,67 @@
+"""Builds lucid_b200/_lucid_b200.so in-tree: the sm_100a kernels, the C ABI and the C++ host code.
+
+nvcc cross-compiles without a GPU, so this runs on the CPU-only build box; the .so then travels to
+the B200 box with the repository snapshot.  -fmad=false is part of the floating-point contract
+(DESIGN.md): no operation is contracted into an FMA, so coverage and fragment counts are
+reproducible bit for bit against the CPU checker.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO_PATH = os.path.join(HERE, "_lucid_b200.so")
+
+CUDA_SOURCES = ["csrc/setup.cu", "csrc/binning.cu", "csrc/raster.cu", "csrc/capi.cu"]
+HOST_SOURCES = ["host/lucid_host.cpp", "host/lucid_renderer.cpp"]
+HEADERS = ["csrc/common.cuh", "../include/lucid_abi.h", "../include/lucid_b200.h", "../include/lucid_host.h",
+           "../include/lucid_renderer.hpp"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    for rel in CUDA_SOURCES + HOST_SOURCES + HEADERS + ["build.py"]:
+        path = os.path.join(HERE, rel)
+        if os.path.exists(path) and os.path.getmtime(path) > t:
+            return True
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return SO_PATH
+    srcs = [os.path.join(HERE, s) for s in CUDA_SOURCES + HOST_SOURCES if os.path.exists(os.path.join(HERE, s))]
+    cmd = [
+        _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+        "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wall,-Wno-unused-function", "-shared",
+        "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+        "-I", os.path.join(ROOT, "include"), "-o", SO_PATH,
+    ]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        sys.stderr.write(res.stdout + res.stderr)
+    return SO_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,461 @@
+// binning.cu -- bin counting, offsets + categorisation, dispatch and list canonicalisation.
+//
+// Replaces data/shaders/bin_counter.glsl, bin_categorizer.glsl and bin_dispatcher.glsl.
+// The reference keeps a private shared-memory histogram per work group and a batch linked list
+// so the dispatcher can replay "its own" quads; here counting is a warp-aggregated atomic
+// histogram straight into the per-bin counters (large triangles add +1/-1 to a per-row
+// difference array that the scan kernel integrates), one CTA turns the counters into offsets and
+// the LOW/HIGH bin lists, dispatch claims list positions with warp-aggregated atomics, and a
+// final pass sorts every bin's list so the result is independent of atomic ordering.
+#include "common.cuh"
+
+namespace lucid {
+
+constexpr int BIN_THREADS = 256;
+
+__device__ __forceinline__ int *cnt(const Params &p, int which) {
+	return p.counts + (size_t)which * p.bin_count;
+}
+
+// scanline.glsl:28-52 -- edge functions evaluated at each bin's trivial-reject corner
+struct BinScan {
+	float mn[3], mx[3], step[3];
+};
+__device__ __forceinline__ BinScan loadBinScan(const TriScan &t, int &min_by, int &max_by) {
+	BinScan s;
+	const float inf = __int_as_float(0x7f800000);
+	float scan[3] = {__uint_as_float(t.s0.x), __uint_as_float(t.s0.y), __uint_as_float(t.s0.z)};
+	float step[3] = {__uint_as_float(t.s1.x), __uint_as_float(t.s1.y), __uint_as_float(t.s1.z)};
+	min_by = (int)(t.s0.w & 0xffff) >> BIN_SHIFT;
+	max_by = (int)(t.s0.w >> 16) >> BIN_SHIFT;
+	u32 signs = t.s1.w;
+	const float offset = float(BIN_SIZE) - 0.989f;
+	float start_x = 0.99f, start_y = float(min_by * BIN_SIZE) - 0.01f;
+#pragma unroll
+	for(int i = 0; i < 3; i++) {
+		bool xneg = (signs >> i) & 1, yneg = (signs >> (3 + i)) & 1;
+		float yoff = yneg ? 0.0f : offset, xoff = xneg ? 0.0f : offset;
+		float v = scan[i] + (step[i] * (yoff + start_y) - (xoff + start_x));
+		s.mn[i] = xneg ? -inf : v;
+		s.mx[i] = xneg ? v : inf;
+		s.step[i] = step[i] * float(BIN_SIZE);
+	}
+	return s;
+}
+// bin_counter.glsl:53-62
+__device__ __forceinline__ void binScanStep(BinScan &s, int &bmin, int &bmax) {
+	float xmin = fmaxf(fmaxf(s.mn[0], s.mn[1]), s.mn[2]);
+	float xmax = fminf(fminf(s.mx[0], s.mx[1]), s.mx[2]);
+#pragma unroll
+	for(int i = 0; i < 3; i++) {
+		s.mn[i] += s.step[i];
+		s.mx[i] += s.step[i];
+	}
+	bmin = f2i(xmin + 1.0f) >> BIN_SHIFT;
+	bmax = f2i(xmax) >> BIN_SHIFT;
+}
+
+// Adds 1 to counter[bin] for every lane with valid set; lanes that hit the same bin are merged
+// into one atomic.  Returns the lane's position (old value + rank among its peers).
+template <bool NeedResult>
+__device__ __forceinline__ int warpAggregatedAdd(int *counters, int bin, bool valid) {
+	u32 peers = __match_any_sync(0xffffffffu, valid ? bin : -1);
+	int result = 0;
+	if(valid) {
+		int leader = __ffs(peers) - 1;
+		int base = 0;
+		if((int)laneId() == leader) {
+			if(NeedResult)
+				base = atomicAdd(counters + bin, __popc(peers));
+			else
+				atomicAdd(counters + bin, __popc(peers)); // result unused: compiles to RED
+		}
+		if(NeedResult) {
+			base = __shfl_sync(peers, base, leader);
+			result = base + __popc(peers & laneMaskLt());
+		}
+	}
+	return result;
+}
+
+// ------------------------------------------------------------------------------------------------
+// counting (bin_counter.glsl:64-134)
+
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
+	const int n_small = p.info->num_visible_quads[0], n_large = p.info->num_visible_quads[1];
+	int *quad_counts = cnt(p, LUCID_CNT_QUAD_COUNTS);
+	int *tri_diff = cnt(p, LUCID_CNT_TRI_COUNTS); // per-row difference array until the scan kernel
+	const int bcx = p.bin_count_x;
+	const int stride = gridDim.x * blockDim.x;
+	const int first = blockIdx.x * blockDim.x + threadIdx.x;
+
+	// small quads: every bin of the (<= 4 bins) AABB, conservative
+	for(int base = blockIdx.x * blockDim.x; base < n_small; base += stride) {
+		int q = base + threadIdx.x;
+		bool valid = q < n_small;
+		u32 enc = valid ? p.quad_aabbs[q] : 0u;
+		int bsx = enc & 0x7f, bsy = (enc >> 7) & 0x7f, bex = (enc >> 14) & 0x7f, bey = (enc >> 21) & 0x7f;
+		int w = bex - bsx + 1, n = valid ? w * (bey - bsy + 1) : 0;
+#pragma unroll
+		for(int k = 0; k < 4; k++) {
+			int by = bsy + k / max(w, 1), bx = bsx + k % max(w, 1);
+			bool ok = k < n && by >= p.row_begin && by < p.row_end;
+			warpAggregatedAdd<false>(quad_counts, by * bcx + bx, ok);
+		}
+	}
+	// large triangles: one thread per triangle, +1 at the first bin of each row span and -1 just
+	// after the last (bin_counter.glsl:123-133)
+	for(int i = first; i < n_large * 2; i += stride) {
+		int quad_idx = (p.max_visible_quads - 1) - (i >> 1), second = i & 1;
+		u32 enc = p.quad_aabbs[quad_idx];
+		if((enc >> (30 + second)) & 1)
+			continue;
+		int bsx = enc & 0x7f, bex = (enc >> 14) & 0x7f, bsy, bey;
+		TriScan t;
+		const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + ((u32)quad_idx * 2 + second));
+		t.s0 = src[0], t.s1 = src[1];
+		BinScan s = loadBinScan(t, bsy, bey);
+		for(int by = bsy; by <= bey; by++) {
+			int bmin, bmax;
+			binScanStep(s, bmin, bmax);
+			bmin = max(bmin, bsx), bmax = min(bmax, bex);
+			if(bmax >= bmin && by >= p.row_begin && by < p.row_end) {
+				atomicAdd(tri_diff + by * bcx + bmin, 1);
+				if(bmax + 1 < bcx)
+					atomicAdd(tri_diff + by * bcx + bmax + 1, -1);
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// offsets + categories (bin_categorizer.glsl:22-89), one CTA
+
+constexpr int SCAN_THREADS = 1024;
+
+// exclusive prefix sum over the CTA of one int per thread
+__device__ __forceinline__ int blockExclusiveScan(int value, int *s_warp, int &total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int incl = value;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o)
+			incl += t;
+	}
+	if(lane == 31)
+		s_warp[warp] = incl;
+	__syncthreads();
+	if(warp == 0) {
+		int w = s_warp[lane];
+		int wi = w;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			int t = __shfl_up_sync(0xffffffffu, wi, o);
+			if(lane >= o)
+				wi += t;
+		}
+		s_warp[lane] = wi - w;
+		if(lane == 31)
+			s_warp[32] = wi;
+	}
+	__syncthreads();
+	int result = s_warp[warp] + incl - value;
+	total = s_warp[32];
+	__syncthreads();
+	return result;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_bin_scan(const Params p) {
+	__shared__ int s_warp[33];
+	const int bc = p.bin_count, bcx = p.bin_count_x, bcy = p.bin_count_y;
+	int *qc = cnt(p, LUCID_CNT_QUAD_COUNTS), *qo = cnt(p, LUCID_CNT_QUAD_OFFSETS);
+	int *qt = cnt(p, LUCID_CNT_QUAD_OFFSETS_TEMP);
+	int *tc = cnt(p, LUCID_CNT_TRI_COUNTS), *to = cnt(p, LUCID_CNT_TRI_OFFSETS);
+	int *tt = cnt(p, LUCID_CNT_TRI_OFFSETS_TEMP);
+	int *low = cnt(p, LUCID_CNT_LOW_BINS), *high = cnt(p, LUCID_CNT_HIGH_BINS);
+
+	// integrate the large-triangle difference arrays row by row (one warp per bin row)
+	for(int by = threadIdx.x >> 5; by < bcy; by += SCAN_THREADS / 32) {
+		int carry = 0;
+		for(int bx0 = 0; bx0 < bcx; bx0 += 32) {
+			int bx = bx0 + (threadIdx.x & 31);
+			int v = bx < bcx ? tc[by * bcx + bx] : 0;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				int t = __shfl_up_sync(0xffffffffu, v, o);
+				if((threadIdx.x & 31) >= o)
+					v += t;
+			}
+			v += carry;
+			if(bx < bcx)
+				tc[by * bcx + bx] = v;
+			carry = __shfl_sync(0xffffffffu, v, 31);
+		}
+	}
+	__syncthreads();
+
+	// each thread owns a contiguous run of bins so offsets and level lists come out in bin order
+	const int per = (bc + SCAN_THREADS - 1) / SCAN_THREADS;
+	const int b0 = min(threadIdx.x * per, bc), b1 = min(b0 + per, bc);
+	int sum_q = 0, sum_t = 0, n_low = 0, n_high = 0, n_empty = 0;
+	for(int b = b0; b < b1; b++) {
+		int q = qc[b], t = tc[b];
+		sum_q += q, sum_t += t;
+		int num_tris = t + q * 2;
+		if(num_tris == 0)
+			n_empty++;
+		else if(num_tris < 1024)
+			n_low++;
+		else
+			n_high++;
+	}
+	int tot_q, tot_t, tot_low, tot_high, tot_empty;
+	int off_q = blockExclusiveScan(sum_q, s_warp, tot_q);
+	int off_t = blockExclusiveScan(sum_t, s_warp, tot_t);
+	int off_low = blockExclusiveScan(n_low, s_warp, tot_low);
+	int off_high = blockExclusiveScan(n_high, s_warp, tot_high);
+	blockExclusiveScan(n_empty, s_warp, tot_empty);
+	for(int b = b0; b < b1; b++) {
+		int q = qc[b], t = tc[b];
+		qo[b] = off_q, qt[b] = off_q, to[b] = off_t, tt[b] = off_t;
+		off_q += q, off_t += t;
+		int num_tris = t + q * 2;
+		if(num_tris == 0) {
+		} else if(num_tris < 1024)
+			low[off_low++] = b;
+		else
+			high[off_high++] = b;
+		p.bin_flags[b] = 0;
+		p.bin_stats[b * 4 + 0] = p.bin_stats[b * 4 + 1] = 0;
+		p.bin_stats[b * 4 + 2] = p.bin_stats[b * 4 + 3] = 0;
+	}
+	if(threadIdx.x == 0) {
+		LucidInfo *info = p.info;
+		info->bin_level_counts[LUCID_BIN_LEVEL_EMPTY] = tot_empty;
+		info->bin_level_counts[LUCID_BIN_LEVEL_MICRO] = 0;
+		info->bin_level_counts[LUCID_BIN_LEVEL_LOW] = tot_low;
+		info->bin_level_counts[LUCID_BIN_LEVEL_MEDIUM] = 0;
+		info->bin_level_counts[LUCID_BIN_LEVEL_HIGH] = tot_high;
+		for(int l = 0; l < LUCID_BIN_LEVELS_COUNT; l++) {
+			int md = p.max_dispatches >> (l == LUCID_BIN_LEVEL_HIGH ? 1 : 0);
+			info->bin_level_dispatches[l][0] = min(info->bin_level_counts[l], md);
+			info->bin_level_dispatches[l][1] = 1;
+			info->bin_level_dispatches[l][2] = 1;
+		}
+		int n_small = info->num_visible_quads[0], n_large = info->num_visible_quads[1];
+		info->num_counted_quads[0] = n_small, info->num_counted_quads[1] = n_large;
+		// quad_setup.glsl:471-485 (kept for getStats-style consumers; nothing is launched from it)
+		int num_tasks = (n_small + 4095) / 4096 + (n_large + 511) / 512;
+		info->num_binning_dispatches[0] = (u32)min(max(num_tasks, 4), p.max_dispatches);
+		info->num_binning_dispatches[1] = 1, info->num_binning_dispatches[2] = 1;
+		// list capacity check: the reference sizes both lists at 2 * MAX_VISIBLE_QUADS and never checks
+		if((u32)tot_q > p.bin_list_capacity || (u32)tot_t > p.bin_list_capacity)
+			info->temp[1] = 1;
+		p.work_counters[0] = p.work_counters[1] = p.work_counters[2] = p.work_counters[3] = 0;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch (bin_dispatcher.glsl:66-114)
+
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
+	if(p.info->temp[1] != 0)
+		return; // lists would overflow their buffers
+	const int n_small = p.info->num_visible_quads[0], n_large = p.info->num_visible_quads[1];
+	int *quad_cursor = cnt(p, LUCID_CNT_QUAD_OFFSETS_TEMP);
+	int *tri_cursor = cnt(p, LUCID_CNT_TRI_OFFSETS_TEMP);
+	const int bcx = p.bin_count_x;
+	const int stride = gridDim.x * blockDim.x;
+
+	for(int base = blockIdx.x * blockDim.x; base < n_small; base += stride) {
+		int q = base + threadIdx.x;
+		bool valid = q < n_small;
+		u32 enc = valid ? p.quad_aabbs[q] : 0u;
+		u32 word = (u32)q | (enc & 0xf0000000u);
+		int bsx = enc & 0x7f, bsy = (enc >> 7) & 0x7f, bex = (enc >> 14) & 0x7f, bey = (enc >> 21) & 0x7f;
+		int w = bex - bsx + 1, n = valid ? w * (bey - bsy + 1) : 0;
+#pragma unroll
+		for(int k = 0; k < 4; k++) {
+			int by = bsy + k / max(w, 1), bx = bsx + k % max(w, 1);
+			bool ok = k < n && by >= p.row_begin && by < p.row_end;
+			int pos = warpAggregatedAdd<true>(quad_cursor, by * bcx + bx, ok);
+			if(ok)
+				p.bin_quads[pos] = word;
+		}
+	}
+
+	// large triangles.  Narrow spans are written by the owning thread; a triangle whose bin AABB
+	// is wider than 8 bins is handed to the whole warp, which strides across each row span
+	// (the reference balances this with per-row segment scans, bin_dispatcher.glsl:123-196).
+	const int lane = laneId();
+	for(int base = blockIdx.x * blockDim.x; base < n_large * 2; base += stride) {
+		int i = base + threadIdx.x;
+		bool valid = i < n_large * 2;
+		int quad_idx = (p.max_visible_quads - 1) - (i >> 1), second = i & 1;
+		u32 enc = valid ? p.quad_aabbs[quad_idx] : 0u;
+		valid = valid && !((enc >> (30 + second)) & 1);
+		u32 tri_idx = (u32)quad_idx * 2 + second;
+		int bsx = enc & 0x7f, bex = (enc >> 14) & 0x7f, bsy = 0, bey = -1;
+		BinScan s;
+		if(valid) {
+			TriScan t;
+			const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + tri_idx);
+			t.s0 = src[0], t.s1 = src[1];
+			s = loadBinScan(t, bsy, bey);
+		}
+		bool wide = valid && (bex - bsx) >= 8;
+		if(valid && !wide) {
+			for(int by = bsy; by <= bey; by++) {
+				int bmin, bmax;
+				binScanStep(s, bmin, bmax);
+				bmin = max(bmin, bsx), bmax = min(bmax, bex);
+				if(by < p.row_begin || by >= p.row_end)
+					continue;
+				for(int bx = bmin; bx <= bmax; bx++)
+					p.bin_tris[atomicAdd(tri_cursor + by * bcx + bx, 1)] = tri_idx;
+			}
+		}
+		u32 wide_mask = __ballot_sync(0xffffffffu, wide);
+		while(wide_mask) {
+			int src_lane = __ffs(wide_mask) - 1;
+			wide_mask &= wide_mask - 1;
+			int rows = __shfl_sync(0xffffffffu, bey - bsy + 1, src_lane);
+			int row0 = __shfl_sync(0xffffffffu, bsy, src_lane);
+			int cbsx = __shfl_sync(0xffffffffu, bsx, src_lane), cbex = __shfl_sync(0xffffffffu, bex, src_lane);
+			u32 ctri = __shfl_sync(0xffffffffu, tri_idx, src_lane);
+			for(int r = 0; r < rows; r++) {
+				int bmin = 0, bmax = -1;
+				if(lane == src_lane)
+					binScanStep(s, bmin, bmax);
+				bmin = __shfl_sync(0xffffffffu, bmin, src_lane);
+				bmax = __shfl_sync(0xffffffffu, bmax, src_lane);
+				bmin = max(bmin, cbsx), bmax = min(bmax, cbex);
+				int by = row0 + r;
+				if(by < p.row_begin || by >= p.row_end)
+					continue;
+				for(int bx = bmin + lane; bx <= bmax; bx += 32)
+					p.bin_tris[atomicAdd(tri_cursor + by * bcx + bx, 1)] = ctri;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// canonical list order: every bin's quad list and tri list sorted ascending by index.
+// The reference leaves the order to atomic arrival; it only matters for depth-key ties in the
+// raster stage, and sorting makes every frame reproducible.
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_TILE = 4096;
+
+__device__ __forceinline__ u32 sortKey(u32 w) { return w & 0x0fffffffu; }
+
+// bitonic network in the "flip / disperse" form: every compare-exchange puts the smaller key at
+// the lower index, so a virtual tail of +inf padding never has to be touched.
+__device__ void sortTileShared(u32 *s, int n) {
+	int padded = 32;
+	while(padded < n)
+		padded <<= 1;
+	for(int k = 2; k <= padded; k <<= 1) {
+		for(int i = threadIdx.x; i < padded / 2; i += SORT_THREADS) {
+			int lo = (i / (k / 2)) * k + (i % (k / 2));
+			int hi = lo ^ (k - 1);
+			if(hi < n) {
+				u32 a = s[lo], b = s[hi];
+				if(sortKey(a) > sortKey(b))
+					s[lo] = b, s[hi] = a;
+			}
+		}
+		__syncthreads();
+		for(int j = k / 4; j >= 1; j >>= 1) {
+			for(int i = threadIdx.x; i < padded / 2; i += SORT_THREADS) {
+				int lo = (i / j) * (2 * j) + (i % j);
+				int hi = lo + j;
+				if(hi < n) {
+					u32 a = s[lo], b = s[hi];
+					if(sortKey(a) > sortKey(b))
+						s[lo] = b, s[hi] = a;
+				}
+			}
+			__syncthreads();
+		}
+	}
+}
+
+// large segments: the same network run on global memory by one CTA (rare: only bins with more
+// than SORT_TILE entries in one list)
+__device__ void sortSegmentGlobal(u32 *g, int n) {
+	int padded = 32;
+	while(padded < n)
+		padded <<= 1;
+	for(int k = 2; k <= padded; k <<= 1) {
+		for(int i = threadIdx.x; i < padded / 2; i += SORT_THREADS) {
+			int lo = (i / (k / 2)) * k + (i % (k / 2));
+			int hi = lo ^ (k - 1);
+			if(hi < n) {
+				u32 a = g[lo], b = g[hi];
+				if(sortKey(a) > sortKey(b))
+					g[lo] = b, g[hi] = a;
+			}
+		}
+		__syncthreads();
+		for(int j = k / 4; j >= 1; j >>= 1) {
+			for(int i = threadIdx.x; i < padded / 2; i += SORT_THREADS) {
+				int lo = (i / j) * (2 * j) + (i % j);
+				int hi = lo + j;
+				if(hi < n) {
+					u32 a = g[lo], b = g[hi];
+					if(sortKey(a) > sortKey(b))
+						g[lo] = b, g[hi] = a;
+				}
+			}
+			__syncthreads();
+		}
+	}
+}
+
+__device__ void sortSegment(u32 *seg, int n, u32 *s_tile) {
+	if(n <= 1)
+		return;
+	if(n <= SORT_TILE) {
+		for(int i = threadIdx.x; i < n; i += SORT_THREADS)
+			s_tile[i] = seg[i];
+		__syncthreads();
+		sortTileShared(s_tile, n);
+		for(int i = threadIdx.x; i < n; i += SORT_THREADS)
+			seg[i] = s_tile[i];
+		__syncthreads();
+	} else {
+		__syncthreads();
+		sortSegmentGlobal(seg, n);
+	}
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_bin_sort(const Params p) {
+	__shared__ u32 s_tile[SORT_TILE];
+	if(p.info->temp[1] != 0)
+		return;
+	const int *qc = cnt(p, LUCID_CNT_QUAD_COUNTS), *qo = cnt(p, LUCID_CNT_QUAD_OFFSETS);
+	const int *tc = cnt(p, LUCID_CNT_TRI_COUNTS), *to = cnt(p, LUCID_CNT_TRI_OFFSETS);
+	for(int b = blockIdx.x; b < p.bin_count; b += gridDim.x) {
+		sortSegment(p.bin_quads + qo[b], qc[b], s_tile);
+		sortSegment(p.bin_tris + to[b], tc[b], s_tile);
+	}
+}
+
+void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *ev) {
+	int grid = 148 * 4;
+	k_bin_count<<<grid, BIN_THREADS, 0, stream>>>(p);
+	if(ev)
+		cudaEventRecord(ev[0], stream);
+	k_bin_scan<<<1, SCAN_THREADS, 0, stream>>>(p);
+	if(ev)
+		cudaEventRecord(ev[1], stream);
+	k_bin_dispatch<<<grid, BIN_THREADS, 0, stream>>>(p);
+	k_bin_sort<<<min(p.bin_count, 148 * 8), SORT_THREADS, 0, stream>>>(p);
+	if(ev)
+		cudaEventRecord(ev[2], stream);
+}
+
+} // namespace lucid

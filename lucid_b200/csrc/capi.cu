@@ -1,0 +1,574 @@
+// capi.cu -- the C ABI declared in include/lucid_b200.h: device memory, streams, per-frame
+// uploads, kernel sequencing and read-backs.  There is no CPU fallback: every entry point that
+// needs the GPU fails with LUCID_E_CUDA when no device is usable.
+#include "../../include/lucid_b200.h"
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lucid;
+
+static thread_local std::string g_create_error;
+
+struct lucid_renderer {
+	LucidCreateInfo ci;
+	Params p;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	int num_sms = 148;
+	std::string error;
+
+	// owned device allocations
+	std::vector<void *> owned;
+	void *geom_owned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	void *tex_owned[2] = {nullptr, nullptr};
+	u32 *image = nullptr;
+	u32 *frag_counts = nullptr;
+	void *info_dev = nullptr;
+	size_t info_words = 0;
+	LucidInstanceData *d_instances = nullptr;
+	u32 *d_inst_colors = nullptr;
+	float4 *d_inst_uv_rects = nullptr;
+
+	// pinned host staging
+	unsigned char *h_instances = nullptr; // instances + colors + uv rects
+	u32 *h_info = nullptr;
+	bool info_valid = false;
+	bool has_geometry = false;
+	int num_quads = 0, num_verts = 0;
+
+	cudaEvent_t ev[10];
+	bool timing_valid = false;
+	bool pending = false;
+};
+
+namespace {
+
+int fail(lucid_renderer *r, int code, const std::string &msg) {
+	if(r)
+		r->error = msg;
+	else
+		g_create_error = msg;
+	return code;
+}
+int failCuda(lucid_renderer *r, cudaError_t e, const char *what) {
+	return fail(r, LUCID_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                                                   \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if(e_ != cudaSuccess)                                                                      \
+			return failCuda(r, e_, #call);                                                         \
+	} while(0)
+
+template <class T> cudaError_t devAlloc(lucid_renderer *r, T **ptr, size_t count) {
+	void *v = nullptr;
+	cudaError_t e = cudaMalloc(&v, count * sizeof(T));
+	if(e == cudaSuccess) {
+		r->owned.push_back(v);
+		*ptr = (T *)v;
+	}
+	return e;
+}
+
+void freeAll(lucid_renderer *r) {
+	for(void *v : r->owned)
+		cudaFree(v);
+	for(void *v : r->geom_owned)
+		if(v)
+			cudaFree(v);
+	for(void *v : r->tex_owned)
+		if(v)
+			cudaFree(v);
+	if(r->h_instances)
+		cudaFreeHost(r->h_instances);
+	if(r->h_info)
+		cudaFreeHost(r->h_info);
+	for(auto &e : r->ev)
+		if(e)
+			cudaEventDestroy(e);
+	if(r->own_stream && r->stream)
+		cudaStreamDestroy(r->stream);
+}
+
+int rasterHighSmallCtas(int sms) { return sms * 8; }
+int rasterHighLargeCtas(int sms) { return sms * 2; }
+
+} // namespace
+
+extern "C" {
+
+const char *lucid_last_error(const lucid_renderer *r) {
+	return r ? r->error.c_str() : g_create_error.c_str();
+}
+
+int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
+	lucid_renderer *r = nullptr;
+	if(!info || !out)
+		return fail(nullptr, LUCID_E_INVALID, "lucid_create: null argument");
+	*out = nullptr;
+	if(info->width <= 0 || info->height <= 0)
+		return fail(nullptr, LUCID_E_INVALID, "lucid_create: bad view size");
+	// 7-bit bin coordinates (funcs.glsl:52-59): at most 128 bins of 32 pixels per axis
+	if(info->width > 4096 || info->height > 4096)
+		return fail(nullptr, LUCID_E_LIMIT, "lucid_create: view size above 4096 (7-bit bin coordinates)");
+	int dev_count = 0;
+	cudaError_t e = cudaGetDeviceCount(&dev_count);
+	if(e != cudaSuccess || dev_count == 0)
+		return fail(nullptr, LUCID_E_CUDA,
+					std::string("lucid_create: no CUDA device (") + cudaGetErrorString(e) + ")");
+	if(info->device < 0 || info->device >= dev_count)
+		return fail(nullptr, LUCID_E_INVALID, "lucid_create: bad device ordinal");
+
+	r = new lucid_renderer();
+	memset(r->ev, 0, sizeof(r->ev));
+	r->ci = *info;
+	lucid_renderer *keep = r;
+	auto bail = [&](int code) {
+		g_create_error = keep->error;
+		freeAll(keep);
+		delete keep;
+		return code;
+	};
+#define CUC(call)                                                                                  \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if(e_ != cudaSuccess) {                                                                    \
+			failCuda(r, e_, #call);                                                                \
+			return bail(LUCID_E_CUDA);                                                             \
+		}                                                                                          \
+	} while(0)
+	CUC(cudaSetDevice(info->device));
+	cudaDeviceProp prop;
+	CUC(cudaGetDeviceProperties(&prop, info->device));
+	r->num_sms = prop.multiProcessorCount;
+	if(info->stream) {
+		r->stream = (cudaStream_t)info->stream;
+	} else {
+		CUC(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+		r->own_stream = true;
+	}
+	for(auto &ev : r->ev)
+		CUC(cudaEventCreate(&ev));
+
+	Params &p = r->p;
+	memset(&p, 0, sizeof(p));
+	p.width = info->width, p.height = info->height;
+	p.bin_count_x = (info->width + BIN_SIZE - 1) / BIN_SIZE;
+	p.bin_count_y = (info->height + BIN_SIZE - 1) / BIN_SIZE;
+	p.bin_count = p.bin_count_x * p.bin_count_y;
+	p.max_visible_quads = info->max_visible_quads > 0 ? info->max_visible_quads : 4793490;
+	p.max_dispatches = info->max_dispatches > 0 ? info->max_dispatches : 256;
+	if(p.max_dispatches > LUCID_INFO_MAX_DISPATCHES)
+		p.max_dispatches = LUCID_INFO_MAX_DISPATCHES;
+	// 24-bit triangle index in sample words and 28-bit quad index in bin lists
+	if(p.max_visible_quads > (1 << 23)) {
+		fail(r, LUCID_E_LIMIT, "lucid_create: max_visible_quads above 2^23 (24-bit triangle index)");
+		return bail(LUCID_E_LIMIT);
+	}
+	p.opts = info->opts;
+	p.row_begin = 0, p.row_end = p.bin_count_y;
+	if(info->bin_row_end > info->bin_row_begin) {
+		p.row_begin = info->bin_row_begin < 0 ? 0 : info->bin_row_begin;
+		p.row_end = info->bin_row_end > p.bin_count_y ? p.bin_count_y : info->bin_row_end;
+	}
+
+	const size_t mvq = (size_t)p.max_visible_quads;
+	CUC(devAlloc(r, &p.quad_aabbs, mvq));
+	CUC(devAlloc(r, &p.tri_scan, mvq * 2));
+	CUC(devAlloc(r, &p.tri_shade, mvq * 2));
+	CUC(devAlloc(r, &p.quad_colors, mvq));
+	CUC(devAlloc(r, &p.quad_normals, mvq));
+	CUC(devAlloc(r, &p.quad_uv, mvq * 2));
+	p.bin_list_capacity = (u32)(mvq * 2);
+	CUC(devAlloc(r, &p.bin_quads, (size_t)p.bin_list_capacity));
+	CUC(devAlloc(r, &p.bin_tris, (size_t)p.bin_list_capacity));
+	r->info_words = LUCID_INFO_U32_SIZE + (size_t)p.bin_count * LUCID_COUNTS_PER_BIN;
+	u32 *info_dev = nullptr;
+	CUC(devAlloc(r, &info_dev, r->info_words));
+	r->info_dev = info_dev;
+	p.info = reinterpret_cast<LucidInfo *>(info_dev);
+	p.counts = reinterpret_cast<int *>(info_dev + LUCID_INFO_U32_SIZE);
+	CUC(devAlloc(r, &p.setup_lookback, (size_t)LUCID_MAX_INSTANCES * 4));
+	CUC(devAlloc(r, &p.setup_ticket, 4));
+	CUC(devAlloc(r, &p.bin_flags, (size_t)p.bin_count));
+	CUC(devAlloc(r, &p.bin_stats, (size_t)p.bin_count * 4));
+	CUC(devAlloc(r, &p.work_counters, 8));
+	CUC(devAlloc(r, &p.deferred_items, (size_t)p.bin_count * 8));
+	size_t scratch_entries = std::max((size_t)rasterHighSmallCtas(r->num_sms) * 4096,
+									  (size_t)rasterHighLargeCtas(r->num_sms) * 16384);
+	CUC(devAlloc(r, &p.high_scratch, scratch_entries));
+	CUC(devAlloc(r, &r->image, (size_t)p.width * p.height));
+	CUC(devAlloc(r, &r->frag_counts, (size_t)p.width * p.height));
+	CUC(devAlloc(r, &r->d_instances, (size_t)LUCID_MAX_INSTANCES));
+	CUC(devAlloc(r, &r->d_inst_colors, (size_t)LUCID_MAX_INSTANCES));
+	CUC(devAlloc(r, &r->d_inst_uv_rects, (size_t)LUCID_MAX_INSTANCES));
+	p.instances = r->d_instances, p.inst_colors = r->d_inst_colors, p.inst_uv_rects = r->d_inst_uv_rects;
+	CUC(cudaMallocHost((void **)&r->h_instances, (size_t)LUCID_MAX_INSTANCES * (16 + 4 + 16)));
+	CUC(cudaMallocHost((void **)&r->h_info, r->info_words * 4));
+	CUC(cudaMemsetAsync(r->info_dev, 0, r->info_words * 4, r->stream));
+	CUC(cudaMemsetAsync(r->image, 0, (size_t)p.width * p.height * 4, r->stream));
+	CUC(cudaStreamSynchronize(r->stream));
+#undef CUC
+	*out = r;
+	return LUCID_OK;
+}
+
+void lucid_destroy(lucid_renderer *r) {
+	if(!r)
+		return;
+	cudaSetDevice(r->ci.device);
+	cudaStreamSynchronize(r->stream);
+	freeAll(r);
+	delete r;
+}
+
+int lucid_bin_count(const lucid_renderer *r) { return r ? r->p.bin_count : LUCID_E_INVALID; }
+
+int lucid_set_bin_rows(lucid_renderer *r, int32_t begin, int32_t end) {
+	if(!r)
+		return LUCID_E_INVALID;
+	if(begin < 0 || end > r->p.bin_count_y || begin >= end)
+		return fail(r, LUCID_E_INVALID, "lucid_set_bin_rows: bad range");
+	r->p.row_begin = begin, r->p.row_end = end;
+	return LUCID_OK;
+}
+
+int lucid_set_geometry(lucid_renderer *r, const float *positions, int32_t num_verts,
+					   const uint32_t *colors, const float *uvs, const uint32_t *normals,
+					   const uint32_t *quad_indices, int32_t num_quads, int32_t memory) {
+	if(!r)
+		return LUCID_E_INVALID;
+	if(!positions || !quad_indices || num_verts <= 0 || num_quads < 0)
+		return fail(r, LUCID_E_INVALID, "lucid_set_geometry: positions and quad indices are required");
+	CU(cudaSetDevice(r->ci.device));
+	CU(cudaStreamSynchronize(r->stream));
+	for(auto &v : r->geom_owned)
+		if(v) {
+			cudaFree(v);
+			v = nullptr;
+		}
+	Params &p = r->p;
+	if(memory == LUCID_MEM_DEVICE) {
+		p.positions = positions, p.quad_indices = (const uint4 *)quad_indices;
+		p.vertex_colors = colors, p.vertex_uvs = (const float2 *)uvs, p.vertex_normals = normals;
+	} else if(memory == LUCID_MEM_HOST) {
+		const void *src[5] = {positions, quad_indices, colors, uvs, normals};
+		size_t bytes[5] = {(size_t)num_verts * 12, (size_t)num_quads * 16, (size_t)num_verts * 4,
+						   (size_t)num_verts * 8, (size_t)num_verts * 4};
+		for(int i = 0; i < 5; i++) {
+			if(!src[i] || bytes[i] == 0)
+				continue;
+			CU(cudaMalloc(&r->geom_owned[i], bytes[i]));
+			CU(cudaMemcpyAsync(r->geom_owned[i], src[i], bytes[i], cudaMemcpyHostToDevice, r->stream));
+		}
+		CU(cudaStreamSynchronize(r->stream));
+		p.positions = (const float *)r->geom_owned[0];
+		p.quad_indices = (const uint4 *)r->geom_owned[1];
+		p.vertex_colors = (const u32 *)r->geom_owned[2];
+		p.vertex_uvs = (const float2 *)r->geom_owned[3];
+		p.vertex_normals = (const u32 *)r->geom_owned[4];
+	} else {
+		return fail(r, LUCID_E_INVALID, "lucid_set_geometry: bad memory kind");
+	}
+	if(((uintptr_t)p.quad_indices & 15) != 0)
+		return fail(r, LUCID_E_INVALID, "lucid_set_geometry: quad indices must be 16-byte aligned");
+	r->num_quads = num_quads, r->num_verts = num_verts;
+	r->has_geometry = true;
+	return LUCID_OK;
+}
+
+int lucid_set_texture(lucid_renderer *r, int32_t slot, const uint8_t *data, int32_t width,
+					  int32_t height, int32_t levels) {
+	if(!r)
+		return LUCID_E_INVALID;
+	if(slot < 0 || slot > 1 || !data || width <= 0 || height <= 0 || levels <= 0 || levels > 16)
+		return fail(r, LUCID_E_INVALID, "lucid_set_texture: bad argument");
+	CU(cudaSetDevice(r->ci.device));
+	CU(cudaStreamSynchronize(r->stream));
+	if(r->tex_owned[slot]) {
+		cudaFree(r->tex_owned[slot]);
+		r->tex_owned[slot] = nullptr;
+	}
+	size_t texels = 0;
+	for(int l = 0; l < levels; l++) {
+		r->p.tex_level_offset[slot][l] = (u32)texels;
+		texels += (size_t)std::max(1, width >> l) * std::max(1, height >> l);
+	}
+	CU(cudaMalloc(&r->tex_owned[slot], texels * 4));
+	CU(cudaMemcpy(r->tex_owned[slot], data, texels * 4, cudaMemcpyHostToDevice));
+	r->p.tex_data[slot] = (const uchar4 *)r->tex_owned[slot];
+	r->p.tex_width[slot] = width, r->p.tex_height[slot] = height, r->p.tex_levels[slot] = levels;
+	return LUCID_OK;
+}
+
+int lucid_wait(lucid_renderer *r) {
+	if(!r)
+		return LUCID_E_INVALID;
+	CU(cudaSetDevice(r->ci.device));
+	CU(cudaStreamSynchronize(r->stream));
+	r->pending = false;
+	CU(cudaGetLastError());
+	return LUCID_OK;
+}
+
+int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstanceData *instances,
+				 const uint32_t *instance_colors, const float *instance_uv_rects,
+				 int32_t num_instances, void *out_rgba8, size_t pitch_bytes, int32_t out_memory,
+				 uint32_t flags) {
+	if(!r)
+		return LUCID_E_INVALID;
+	if(!config || num_instances < 0 || (num_instances > 0 && (!instances || !instance_colors)))
+		return fail(r, LUCID_E_INVALID, "lucid_render: null argument");
+	if(!r->has_geometry)
+		return fail(r, LUCID_E_STATE, "lucid_render: lucid_set_geometry has not been called");
+	if(num_instances > LUCID_MAX_INSTANCES)
+		num_instances = LUCID_MAX_INSTANCES; // lucid_renderer.cpp:403-410 truncates the same way
+	Params &p = r->p;
+	for(int i = 0; i < num_instances; i++) {
+		const LucidInstanceData &in = instances[i];
+		if(in.num_quads < 0 || in.num_quads > LUCID_MAX_INSTANCE_QUADS || (in.index_offset & 3) != 0 ||
+		   in.index_offset < 0 || (int64_t)in.index_offset / 4 + in.num_quads > r->num_quads)
+			return fail(r, LUCID_E_INVALID, "lucid_render: instance " + std::to_string(i) + " out of range");
+	}
+	if(out_memory != LUCID_MEM_NONE && (!out_rgba8 || pitch_bytes < (size_t)p.width * 4 || (pitch_bytes & 3)))
+		return fail(r, LUCID_E_INVALID, "lucid_render: bad output image");
+	CU(cudaSetDevice(r->ci.device));
+	if(r->pending)
+		CU(cudaStreamSynchronize(r->stream));
+	cudaStream_t st = r->stream;
+
+	// per-frame uploads (uploadInstances / setupInputData): one pinned staging block
+	unsigned char *h = r->h_instances;
+	size_t n = (size_t)num_instances;
+	memcpy(h, instances, n * 16);
+	memcpy(h + (size_t)LUCID_MAX_INSTANCES * 16, instance_colors, n * 4);
+	float *h_uv = reinterpret_cast<float *>(h + (size_t)LUCID_MAX_INSTANCES * 20);
+	if(instance_uv_rects) {
+		memcpy(h_uv, instance_uv_rects, n * 16);
+	} else {
+		for(size_t i = 0; i < n; i++)
+			h_uv[i * 4] = 0.0f, h_uv[i * 4 + 1] = 0.0f, h_uv[i * 4 + 2] = 1.0f, h_uv[i * 4 + 3] = 1.0f;
+	}
+	if(n) {
+		CU(cudaMemcpyAsync(r->d_instances, h, n * 16, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(r->d_inst_colors, h + (size_t)LUCID_MAX_INSTANCES * 16, n * 4,
+						   cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(r->d_inst_uv_rects, h_uv, n * 16, cudaMemcpyHostToDevice, st));
+	}
+	// LucidInfo and the first 6 per-bin counter arrays are cleared every frame (lucid_renderer.cpp:437)
+	CU(cudaMemsetAsync(r->info_dev, 0, (LUCID_INFO_U32_SIZE + (size_t)p.bin_count * 6) * 4, st));
+
+	LucidConfig cfg = *config;
+	cfg.num_instances = num_instances; // taken from this call, not the previous frame
+	p.num_instances = num_instances;
+	p.num_setup_ctas = num_instances * (LUCID_MAX_INSTANCE_QUADS / 256);
+	if(out_memory == LUCID_MEM_DEVICE) {
+		p.image = (u32 *)out_rgba8;
+		p.image_pitch = (int)(pitch_bytes / 4);
+	} else {
+		p.image = r->image;
+		p.image_pitch = p.width;
+	}
+	p.frag_counts = (flags & LUCID_RENDER_FRAG_COUNTS) ? r->frag_counts : nullptr;
+
+	CU(cudaEventRecord(r->ev[0], st));
+	launchQuadSetup(p, cfg, st);
+	CU(cudaEventRecord(r->ev[1], st));
+	launchBinning(p, st, &r->ev[2]); // ev[2] count, ev[3] scan, ev[4] dispatch+sort
+	launchRaster(p, cfg, st, &r->ev[5], r->num_sms); // ev[5] low, ev[6] high, ev[7] finish
+	CU(cudaGetLastError());
+	r->timing_valid = true;
+
+	if(!(flags & LUCID_RENDER_SKIP_INFO)) {
+		CU(cudaMemcpyAsync(r->h_info, r->info_dev, r->info_words * 4, cudaMemcpyDeviceToHost, st));
+		r->info_valid = true;
+	}
+	if(out_memory == LUCID_MEM_HOST)
+		CU(cudaMemcpy2DAsync(out_rgba8, pitch_bytes, r->image, (size_t)p.width * 4, (size_t)p.width * 4,
+							 p.height, cudaMemcpyDeviceToHost, st));
+	r->pending = true;
+	if(!(flags & LUCID_RENDER_ASYNC))
+		return lucid_wait(r);
+	return LUCID_OK;
+}
+
+int lucid_read_info(lucid_renderer *r, uint32_t *dst, size_t num_words) {
+	if(!r || !dst)
+		return LUCID_E_INVALID;
+	if(!r->info_valid)
+		return fail(r, LUCID_E_STATE, "lucid_read_info: no frame has copied its info back");
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	memcpy(dst, r->h_info, std::min(num_words, r->info_words) * 4);
+	return LUCID_OK;
+}
+
+int lucid_stage_times(lucid_renderer *r, float ms[8]) {
+	if(!r || !ms)
+		return LUCID_E_INVALID;
+	if(!r->timing_valid)
+		return fail(r, LUCID_E_STATE, "lucid_stage_times: nothing rendered yet");
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	for(int i = 0; i < 7; i++)
+		CU(cudaEventElapsedTime(&ms[i], r->ev[i], r->ev[i + 1]));
+	CU(cudaEventElapsedTime(&ms[7], r->ev[0], r->ev[7]));
+	return LUCID_OK;
+}
+
+static int slotRange(lucid_renderer *r, int which, int count, size_t &first_slot) {
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	if(which < 0 || which > 1 || count < 0 || count > r->p.max_visible_quads)
+		return fail(r, LUCID_E_INVALID, "bad slot range");
+	first_slot = which == 0 ? 0 : (size_t)r->p.max_visible_quads - count;
+	return LUCID_OK;
+}
+
+int lucid_read_quad_aabbs(lucid_renderer *r, int32_t which, uint32_t *dst, int32_t count) {
+	if(!r || !dst)
+		return LUCID_E_INVALID;
+	size_t first;
+	int rc = slotRange(r, which, count, first);
+	if(rc)
+		return rc;
+	std::vector<u32> tmp(count);
+	CU(cudaMemcpy(tmp.data(), r->p.quad_aabbs + first, (size_t)count * 4, cudaMemcpyDeviceToHost));
+	for(int i = 0; i < count; i++)
+		dst[i] = which == 0 ? tmp[i] : tmp[count - 1 - i];
+	return LUCID_OK;
+}
+
+int lucid_read_tri_records(lucid_renderer *r, int32_t which, uint32_t *dst, int32_t num_quads) {
+	if(!r || !dst)
+		return LUCID_E_INVALID;
+	size_t first;
+	int rc = slotRange(r, which, num_quads, first);
+	if(rc)
+		return rc;
+	size_t nt = (size_t)num_quads * 2;
+	std::vector<TriScan> scan(nt);
+	std::vector<TriShade> shade(nt);
+	std::vector<u32> aabbs(num_quads);
+	CU(cudaMemcpy(scan.data(), r->p.tri_scan + first * 2, nt * sizeof(TriScan), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(shade.data(), r->p.tri_shade + first * 2, nt * sizeof(TriShade), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(aabbs.data(), r->p.quad_aabbs + first, (size_t)num_quads * 4, cudaMemcpyDeviceToHost));
+	for(int q = 0; q < num_quads; q++) {
+		int src_q = which == 0 ? q : num_quads - 1 - q;
+		for(int s = 0; s < 2; s++) {
+			u32 *o = dst + ((size_t)q * 2 + s) * 21;
+			if((aabbs[src_q] >> (30 + s)) & 1) { // culled triangles have no record
+				memset(o, 0, 21 * 4);
+				continue;
+			}
+			const TriScan &sc = scan[(size_t)src_q * 2 + s];
+			const TriShade &sh = shade[(size_t)src_q * 2 + s];
+			memcpy(o + 0, &sh.bary0, 16), memcpy(o + 4, &sh.bary1, 16);
+			memcpy(o + 8, &sc.s0, 16), memcpy(o + 12, &sc.s1, 16);
+			memcpy(o + 16, &sh.depth, 16);
+			o[20] = sh.misc.x;
+		}
+	}
+	return LUCID_OK;
+}
+
+int lucid_read_quad_attrs(lucid_renderer *r, int32_t which, uint32_t *dst, int32_t num_quads) {
+	if(!r || !dst)
+		return LUCID_E_INVALID;
+	size_t first;
+	int rc = slotRange(r, which, num_quads, first);
+	if(rc)
+		return rc;
+	std::vector<uint4> col(num_quads), nrm(num_quads), uv((size_t)num_quads * 2);
+	CU(cudaMemcpy(col.data(), r->p.quad_colors + first, (size_t)num_quads * 16, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(nrm.data(), r->p.quad_normals + first, (size_t)num_quads * 16, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(uv.data(), r->p.quad_uv + first * 2, (size_t)num_quads * 32, cudaMemcpyDeviceToHost));
+	for(int q = 0; q < num_quads; q++) {
+		int s = which == 0 ? q : num_quads - 1 - q;
+		memcpy(dst + (size_t)q * 16 + 0, &col[s], 16);
+		memcpy(dst + (size_t)q * 16 + 4, &nrm[s], 16);
+		memcpy(dst + (size_t)q * 16 + 8, &uv[(size_t)s * 2], 32);
+	}
+	return LUCID_OK;
+}
+
+int lucid_read_bin_lists(lucid_renderer *r, uint32_t *bin_quads, size_t nq, uint32_t *bin_tris, size_t nt) {
+	if(!r)
+		return LUCID_E_INVALID;
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	if(nq > r->p.bin_list_capacity || nt > r->p.bin_list_capacity)
+		return fail(r, LUCID_E_INVALID, "lucid_read_bin_lists: count above capacity");
+	if(bin_quads && nq)
+		CU(cudaMemcpy(bin_quads, r->p.bin_quads, nq * 4, cudaMemcpyDeviceToHost));
+	if(bin_tris && nt)
+		CU(cudaMemcpy(bin_tris, r->p.bin_tris, nt * 4, cudaMemcpyDeviceToHost));
+	return LUCID_OK;
+}
+
+int lucid_read_frag_counts(lucid_renderer *r, uint32_t *dst) {
+	if(!r || !dst)
+		return LUCID_E_INVALID;
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	CU(cudaMemcpy(dst, r->frag_counts, (size_t)r->p.width * r->p.height * 4, cudaMemcpyDeviceToHost));
+	return LUCID_OK;
+}
+
+int lucid_read_image(lucid_renderer *r, void *dst, size_t pitch_bytes) {
+	if(!r || !dst || pitch_bytes < (size_t)r->p.width * 4)
+		return LUCID_E_INVALID;
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	CU(cudaMemcpy2D(dst, pitch_bytes, r->image, (size_t)r->p.width * 4, (size_t)r->p.width * 4,
+					r->p.height, cudaMemcpyDeviceToHost));
+	return LUCID_OK;
+}
+
+int lucid_image_pointer(lucid_renderer *r, void **device_ptr, size_t *pitch_bytes) {
+	if(!r || !device_ptr || !pitch_bytes)
+		return LUCID_E_INVALID;
+	*device_ptr = r->image;
+	*pitch_bytes = (size_t)r->p.width * 4;
+	return LUCID_OK;
+}
+
+int lucid_ipc_export_image(lucid_renderer *r, void *handle64) {
+	if(!r || !handle64)
+		return LUCID_E_INVALID;
+	CU(cudaSetDevice(r->ci.device));
+	cudaIpcMemHandle_t h;
+	CU(cudaIpcGetMemHandle(&h, r->image));
+	static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t");
+	memcpy(handle64, &h, 64);
+	return LUCID_OK;
+}
+
+int lucid_ipc_open_image(lucid_renderer *r, const void *handle64, void **device_ptr) {
+	if(!r || !handle64 || !device_ptr)
+		return LUCID_E_INVALID;
+	CU(cudaSetDevice(r->ci.device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	CU(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return LUCID_OK;
+}
+
+int lucid_ipc_close_image(lucid_renderer *r, void *device_ptr) {
+	if(!r || !device_ptr)
+		return LUCID_E_INVALID;
+	CU(cudaSetDevice(r->ci.device));
+	CU(cudaIpcCloseMemHandle(device_ptr));
+	return LUCID_OK;
+}
+}

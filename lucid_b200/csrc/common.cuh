@@ -1,0 +1,195 @@
+// common.cuh -- parameter block, storage layout and the floating-point contract of the sm_100a
+// kernels.  Everything is compiled with -fmad=false: each binary32 operation is rounded on its
+// own, in the association written in the source, so the kernels and the CPU checker agree bit for
+// bit on coverage, bin lists and fragment counts (DESIGN.md "Floating-point contract").
+#pragma once
+
+#include "../../include/lucid_abi.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lucid {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+constexpr int BIN_SIZE = LUCID_BIN_SIZE;
+constexpr int BIN_SHIFT = LUCID_BIN_SHIFT;
+
+// ---- storage layout in HBM -----------------------------------------------------------------
+// Visible quads occupy slots [0, n_small) (small: bin AABB area <= 4) and (MVQ - n_large, MVQ)
+// (large, allocated downwards), as in quad_setup.glsl:437-444; tri_idx = slot * 2 + second_tri.
+//   quad_aabbs[slot]   u32      28-bit bin AABB + 2 cull bits (quad_setup.glsl:241-242)
+//   tri_scan[tri]      2x16 B   scanline record (scan.xyz, ymin|ymax<<16) (step.xyz, sign bits)
+//   tri_shade[tri]     4x16 B   depth plane (xyz, flags|instance<<16), bary edge 0, bary edge 1,
+//                               (flat normal 10-10-10, instance RGBA8, 0, 0)
+//   quad_colors/normals[slot] 16 B, quad_uv[slot] 2x16 B   optional vertex attributes
+// The reference keeps the same fields in uvec4_storage / normals_storage
+// (definitions.glsl:132-137); here the per-sample fields of one triangle share one 64-byte line
+// and the instance colour is folded in, which removes a dependent load from the shading loop.
+struct TriScan {
+	uint4 s0, s1;
+};
+struct TriShade {
+	uint4 depth, bary0, bary1, misc;
+};
+
+struct Params {
+	int width, height;
+	int bin_count_x, bin_count_y, bin_count;
+	int max_visible_quads;
+	int row_begin, row_end; // bin rows owned by this device (multi-GPU bin-row split)
+	u32 opts;
+	int max_dispatches;
+	int num_instances;
+	int num_setup_ctas;
+
+	// caller geometry (device pointers)
+	const float *positions;
+	const uint4 *quad_indices;
+	const u32 *vertex_colors;
+	const float2 *vertex_uvs;
+	const u32 *vertex_normals;
+	// per-frame instance data
+	const LucidInstanceData *instances;
+	const u32 *inst_colors;
+	const float4 *inst_uv_rects;
+
+	// renderer-owned storage
+	u32 *quad_aabbs;
+	TriScan *tri_scan;
+	TriShade *tri_shade;
+	uint4 *quad_colors;
+	uint4 *quad_normals;
+	uint4 *quad_uv;
+	u32 *bin_quads;
+	u32 *bin_tris;
+	u32 bin_list_capacity;
+	LucidInfo *info;
+	int *counts; // 10 * bin_count, directly after info in the same allocation
+	u64 *setup_lookback;
+	u32 *setup_ticket;
+	u32 *sort_scratch;
+
+	// raster state
+	u32 *image;			  // RGBA8, pitch in pixels
+	int image_pitch;
+	u32 *frag_counts;	  // optional per-pixel fragment counts (debug / parity), may be null
+	u32 *bin_flags;		  // per bin: bit 0 promoted LOW->HIGH, bit 1 HIGH error
+	u32 *bin_stats;		  // per bin: [0] LOW frags [1] LOW hbtris [2] HIGH frags [3] HIGH hbtris
+	u32 *work_counters;	  // [0] low items [1] high items [2] high-big items [3] deferred count
+	int *deferred_items;  // HIGH items that need the large-capacity kernel
+	uint4 *high_scratch;  // per persistent CTA: half-block-row records
+	// textures: level offsets into one RGBA8 array per slot
+	const uchar4 *tex_data[2];
+	int tex_width[2], tex_height[2], tex_levels[2];
+	u32 tex_level_offset[2][16];
+};
+
+// ---- floating-point contract ------------------------------------------------------------------
+__device__ __forceinline__ int f2i(float x) { return __float2int_rz(x); }	  // saturating, NaN -> 0
+__device__ __forceinline__ u32 f2u(float x) { return __float2uint_rz(x); } // saturating, NaN -> 0
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+	return fminf(fmaxf(x, lo), hi);
+}
+__device__ __forceinline__ float saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+__device__ __forceinline__ float rcp(float x) { return __fdiv_rn(1.0f, x); }
+__device__ __forceinline__ float rsqrt_rn(float x) { return __fdiv_rn(1.0f, __fsqrt_rn(x)); }
+
+// log2 / exp2 / pow: polynomial evaluation in plain binary32 operations, identical on host and
+// device (atanh series on [sqrt(1/2), sqrt(2)), degree-6 Taylor for 2^r).
+__device__ __forceinline__ float log2_poly(float x) {
+	u32 ix = __float_as_uint(x);
+	int e = (int)(ix - 0x3f3504f3u) >> 23;
+	float m = __uint_as_float(ix - ((u32)e << 23));
+	float f = m - 1.0f;
+	float s = __fdiv_rn(f, 2.0f + f);
+	float z = s * s;
+	float p = 0.2222222222f;
+	p = p * z + 0.2857142857f;
+	p = p * z + 0.4f;
+	p = p * z + 0.6666666667f;
+	p = p * z + 2.0f;
+	float ln = s * p;
+	return ln * 1.4426950408889634f + (float)e;
+}
+__device__ __forceinline__ float exp2_poly(float t) {
+	float n = floorf(t + 0.5f);
+	float r = (t - n) * 0.6931471805599453f;
+	float p = 1.0f / 720.0f;
+	p = p * r + 1.0f / 120.0f;
+	p = p * r + 1.0f / 24.0f;
+	p = p * r + 1.0f / 6.0f;
+	p = p * r + 0.5f;
+	p = p * r + 1.0f;
+	p = p * r + 1.0f;
+	int ni = f2i(n);
+	if(ni < -126)
+		return 0.0f;
+	if(ni > 127)
+		ni = 127;
+	return p * __uint_as_float((u32)(ni + 127) << 23);
+}
+__device__ __forceinline__ float pow_poly(float x, float y) {
+	if(!(x > 0.0f))
+		return 0.0f;
+	return exp2_poly(y * log2_poly(x));
+}
+
+struct F3 {
+	float x, y, z;
+};
+__device__ __forceinline__ F3 mk3(float x, float y, float z) { return F3{x, y, z}; }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ F3 operator-(F3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ bool same3(F3 a, F3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+__device__ __forceinline__ float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 cross3(F3 a, F3 b) {
+	return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ F3 xyz(const LucidVec4 &v) { return mk3(v.x, v.y, v.z); }
+
+__device__ __forceinline__ u32 encodeNormalUint(F3 n) {
+	u32 x = f2u(512.0f + n.x * 511.0f) & 0x3ffu;
+	u32 y = f2u(512.0f + n.y * 511.0f) & 0x3ffu;
+	u32 z = f2u(512.0f + n.z * 511.0f) & 0x3ffu;
+	return x | (y << 10) | (z << 20);
+}
+__device__ __forceinline__ F3 decodeNormalUint(u32 n) {
+	const float s = 1.0f / 511.0f;
+	return mk3((float((n >> 0) & 0x3ffu) - 512.0f) * s, (float((n >> 10) & 0x3ffu) - 512.0f) * s,
+			   (float((n >> 20) & 0x3ffu) - 512.0f) * s);
+}
+__device__ __forceinline__ float4 decodeRGBA8(u32 c) {
+	const float s = 1.0f / 255.0f;
+	return make_float4(float(c & 0xffu) * s, float((c >> 8) & 0xffu) * s,
+					   float((c >> 16) & 0xffu) * s, float((c >> 24) & 0xffu) * s);
+}
+__device__ __forceinline__ u32 encodeRGBA8(float4 c) {
+	return f2u(c.x * 255.0f) | (f2u(c.y * 255.0f) << 8) | (f2u(c.z * 255.0f) << 16) |
+		   (f2u(c.w * 255.0f) << 24);
+}
+__device__ __forceinline__ float linearToSRGB1(float c) {
+	return c < 0.0031308f ? 12.92f * c : 1.055f * pow_poly(c, 1.0f / 2.4f) - 0.055f;
+}
+__device__ __forceinline__ float SRGBToLinear1(float c) {
+	return c < 0.04045f ? (1.0f / 12.92f) * c : pow_poly((c + 0.055f) * (1.0f / 1.055f), 2.4f);
+}
+
+__device__ __forceinline__ u32 laneId() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 laneMaskLt() {
+	u32 m;
+	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
+}
+
+// kernel launchers (each in its own translation unit)
+void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream);
+void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *stage_events);
+void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream,
+				  cudaEvent_t *stage_events, int num_sms);
+
+} // namespace lucid

@@ -1,0 +1,462 @@
+// setup.cu -- quad/triangle setup for sm_100a.
+//
+// Replaces data/shaders/quad_setup.glsl (reference file:line cited per function).  What changes
+// against the reference's structure: one 256-thread CTA per quarter instance instead of a
+// 1024-thread work group per instance packet; the two global atomicAdd compactions
+// (quad_setup.glsl:415-421) become a single-pass decoupled look-back scan over CTAs taken in
+// ticket order, so visible-quad slots are a pure function of the input order (deterministic);
+// per-sample triangle fields are written as one 64-byte record.
+#include "common.cuh"
+
+namespace lucid {
+
+constexpr int SETUP_THREADS = 256;
+constexpr int SETUP_PARTS = LUCID_MAX_INSTANCE_QUADS / SETUP_THREADS;
+
+__device__ __forceinline__ F3 vertexLoad(const Params &p, u32 vi) {
+	const float *v = p.positions + (size_t)vi * 3;
+	return mk3(__ldg(v), __ldg(v + 1), __ldg(v + 2));
+}
+
+__device__ __forceinline__ u32 vertexClipMask(float4 v) {
+	return (v.x < -v.w ? 0x01u : 0u) | (v.x > v.w ? 0x02u : 0u) | (v.y < -v.w ? 0x04u : 0u) |
+		   (v.y > v.w ? 0x08u : 0u) | (v.z < -v.w ? 0x10u : 0u) | (v.z > v.w ? 0x20u : 0u);
+}
+
+__device__ __forceinline__ float &comp(float4 &v, int i) { return (&v.x)[i]; }
+
+// quad_setup.glsl:77-128 -- screen AABB of a triangle that crosses the near plane (Blinn 1996)
+__device__ float4 clippedAABB(float4 v0, float4 v1, float4 v2, float w0, float w1, float w2,
+							  u32 clipmask) {
+	float4 aabb = make_float4(1.0f, 1.0f, -1.0f, -1.0f);
+	float4 v[3] = {v0, v1, v2};
+	float iw[3] = {w0, w1, w2};
+	int any_vis = 0;
+	u32 or_mask = clipmask | (clipmask >> 8) | (clipmask >> 16);
+#pragma unroll
+	for(int i = 0; i < 3; i++) {
+		u32 cm = clipmask >> (i * 8);
+		if((cm & 0x3) == 0) {
+			any_vis |= 0x1;
+			if(v[i].x - aabb.x * v[i].w < 0.0f)
+				aabb.x = v[i].x * iw[i];
+			if(v[i].x - aabb.z * v[i].w > 0.0f)
+				aabb.z = v[i].x * iw[i];
+		}
+		if((cm & 0xc) == 0) {
+			any_vis |= 0x10;
+			if(v[i].y - aabb.y * v[i].w < 0.0f)
+				aabb.y = v[i].y * iw[i];
+			if(v[i].y - aabb.w * v[i].w > 0.0f)
+				aabb.w = v[i].y * iw[i];
+		}
+	}
+	if((any_vis & 0x0f) == 0) {
+		aabb.x = -1.0f, aabb.z = 1.0f;
+	} else if((or_mask & 0x3) != 0) {
+#pragma unroll
+		for(int i = 0; i < 3; i++) {
+			u32 cm = clipmask >> (i * 8);
+			if((cm & 0x1) != 0 && v[i].x - aabb.x * v[i].w < 0.0f)
+				aabb.x = -1.0f;
+			if((cm & 0x2) != 0 && v[i].x - aabb.z * v[i].w > 0.0f)
+				aabb.z = 1.0f;
+		}
+	}
+	if((any_vis & 0xf0) == 0) {
+		aabb.y = -1.0f, aabb.w = 1.0f;
+	} else if((or_mask & 0xc) != 0) {
+#pragma unroll
+		for(int i = 0; i < 3; i++) {
+			u32 cm = clipmask >> (i * 8);
+			if((cm & 0x4) != 0 && v[i].y - aabb.y * v[i].w < 0.0f)
+				aabb.y = -1.0f;
+			if((cm & 0x8) != 0 && v[i].y - aabb.w * v[i].w > 0.0f)
+				aabb.w = 1.0f;
+		}
+	}
+	return aabb;
+}
+
+__device__ __forceinline__ float4 plainAABB(float4 a, float4 b, float4 c) {
+	return make_float4(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y),
+					   fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y));
+}
+
+struct QuadResult {
+	int status;	   // -1 visible, -2 visible but outside the owned bin rows, else rejection type
+	int size_type; // 0 small, 1 large
+	u32 enc_aabb, y_aabb0, y_aabb1;
+};
+
+// quad_setup.glsl:136-254
+__device__ QuadResult processInputQuad(const Params &p, const LucidConfig &cfg, uint4 vi) {
+	QuadResult out;
+	out.status = -1, out.size_type = 0, out.enc_aabb = 0, out.y_aabb0 = 0, out.y_aabb1 = 0;
+	u32 v0 = vi.x, v1 = vi.y, v2 = vi.z, v3 = vi.w;
+	bool cull0 = v0 == v1 || v1 == v2 || v2 == v0;
+	bool cull1 = v0 == v2 || v2 == v3 || v3 == v0;
+	if(cull0 && cull1) {
+		out.status = LUCID_REJECTION_OTHER;
+		return out;
+	}
+	F3 vws[4] = {vertexLoad(p, v0), vertexLoad(p, v1), vertexLoad(p, v2), vertexLoad(p, v3)};
+	cull0 = cull0 || same3(vws[0], vws[1]) || same3(vws[1], vws[2]) || same3(vws[2], vws[0]);
+	cull1 = cull1 || same3(vws[0], vws[2]) || same3(vws[2], vws[3]) || same3(vws[3], vws[0]);
+
+	if(cfg.enable_backface_culling != 0) {
+		F3 org = xyz(cfg.frustum.ws_origin0);
+		F3 p0 = vws[0] - org, p1 = vws[1] - org, p2 = vws[2] - org, p3 = vws[3] - org;
+		F3 nrm0 = cross3(p2, p1 - p2);
+		F3 nrm1 = cross3(p3, p2 - p3);
+		float volume0 = dot3(p0, nrm0), volume1 = dot3(p0, nrm1);
+		cull0 = cull0 || volume0 <= 0.0f;
+		cull1 = cull1 || volume1 <= 0.0f;
+		if(cull0 && cull1) {
+			out.status = LUCID_REJECTION_BACKFACE;
+			return out;
+		}
+	}
+	u32 cull_flags = (cull0 ? 1u : 0u) | (cull1 ? 2u : 0u);
+
+	float4 vndc[4];
+	const LucidVec4 *m = cfg.view_proj_matrix;
+#pragma unroll
+	for(int i = 0; i < 4; i++) {
+		F3 q = vws[i];
+		vndc[i].x = m[0].x * q.x + m[1].x * q.y + m[2].x * q.z + m[3].x;
+		vndc[i].y = m[0].y * q.x + m[1].y * q.y + m[2].y * q.z + m[3].y;
+		vndc[i].z = m[0].z * q.x + m[1].z * q.y + m[2].z * q.z + m[3].z;
+		vndc[i].w = m[0].w * q.x + m[1].w * q.y + m[2].w * q.z + m[3].w;
+	}
+	u32 clipmask = vertexClipMask(vndc[0]) | (vertexClipMask(vndc[1]) << 8) |
+				   (vertexClipMask(vndc[2]) << 16) | (vertexClipMask(vndc[3]) << 24);
+	u32 and_mask = clipmask & (clipmask >> 8) & (clipmask >> 16) & (clipmask >> 24) & 0xffu;
+	u32 or_mask = clipmask | (clipmask >> 8) | (clipmask >> 16) | (clipmask >> 24);
+	if(and_mask != 0) {
+		out.status = LUCID_REJECTION_FRUSTUM;
+		return out;
+	}
+
+	float4 aabb0 = make_float4(0, 0, 0, 0), aabb1 = aabb0;
+	float iw[4] = {rcp(vndc[0].w), rcp(vndc[1].w), rcp(vndc[2].w), rcp(vndc[3].w)};
+	bool near_far = (or_mask & 0x30) != 0;
+	if(near_far) {
+		aabb0 = clippedAABB(vndc[0], vndc[1], vndc[2], iw[0], iw[1], iw[2], clipmask);
+		aabb1 = clippedAABB(vndc[0], vndc[2], vndc[3], iw[0], iw[2], iw[3],
+							(clipmask & 0xffu) | ((clipmask & 0xffff0000u) >> 8));
+	}
+#pragma unroll
+	for(int i = 0; i < 4; i++) {
+		vndc[i].x *= iw[i];
+		vndc[i].y *= iw[i];
+		vndc[i].z *= iw[i];
+	}
+	if(!near_far) {
+		aabb0 = plainAABB(vndc[0], vndc[1], vndc[2]);
+		aabb1 = plainAABB(vndc[0], vndc[2], vndc[3]);
+	}
+
+	float sx = float(p.width) * 0.5f, sy = float(p.height) * 0.5f;
+	float mx = float(p.width - 1), my = float(p.height - 1);
+	aabb0 = make_float4((aabb0.x + 1.0f) * sx, (aabb0.y + 1.0f) * sy, (aabb0.z + 1.0f) * sx,
+						(aabb0.w + 1.0f) * sy);
+	aabb1 = make_float4((aabb1.x + 1.0f) * sx, (aabb1.y + 1.0f) * sy, (aabb1.z + 1.0f) * sx,
+						(aabb1.w + 1.0f) * sy);
+	float4 aabb = make_float4(fminf(aabb0.x, aabb1.x), fminf(aabb0.y, aabb1.y),
+							  fmaxf(aabb0.z, aabb1.z), fmaxf(aabb0.w, aabb1.w));
+
+	if(ceilf(aabb.x - 0.5001f) == floorf(aabb.z + 0.5001f) ||
+	   ceilf(aabb.y - 0.5001f) == floorf(aabb.w + 0.5001f)) {
+		out.status = LUCID_REJECTION_BETWEEN_SAMPLES;
+		return out;
+	}
+#define ADJ(a)                                                                                     \
+	a = make_float4(clampf(a.x + 0.49f, 0.0f, mx), clampf(a.y + 0.49f, 0.0f, my),                  \
+					clampf(a.z - 0.49f, 0.0f, mx), clampf(a.w - 0.49f, 0.0f, my))
+	ADJ(aabb0);
+	ADJ(aabb1);
+	ADJ(aabb);
+#undef ADJ
+	u32 b0 = f2u(aabb.x) >> BIN_SHIFT, b1 = f2u(aabb.y) >> BIN_SHIFT;
+	u32 b2 = f2u(aabb.z) >> BIN_SHIFT, b3 = f2u(aabb.w) >> BIN_SHIFT;
+	out.enc_aabb = (b0 & 0x7fu) | ((b1 & 0x7fu) << 7) | ((b2 & 0x7fu) << 14) |
+				   ((b3 & 0x7fu) << 21) | (cull_flags << 30);
+	u32 bsx = b2 - b0 + 1u, bsy = b3 - b1 + 1u;
+	out.size_type = bsx * bsy <= 4u ? 0 : 1;
+	out.y_aabb0 = f2u(aabb0.y) | (f2u(aabb0.w) << 16);
+	out.y_aabb1 = f2u(aabb1.y) | (f2u(aabb1.w) << 16);
+	// bin-row split across devices: a quad is kept only where its bin rows intersect the owned
+	// range; the small/large decision above used the unclamped AABB
+	if((int)b3 < p.row_begin || (int)b1 >= p.row_end)
+		out.status = -2;
+	return out;
+}
+
+// quad_setup.glsl:274-340
+__device__ void storeTri(const Params &p, const LucidConfig &cfg, u32 tri_idx, u32 flags_id,
+						 u32 inst_color, F3 tri0, F3 tri1, F3 tri2, u32 y_aabb, F3 ray_dir0) {
+	F3 normal = cross3(tri0 - tri2, tri1 - tri0);
+	float multiplier = rcp(__fsqrt_rn(dot3(normal, normal)));
+	normal = normal * multiplier;
+	u32 enc_normal = (flags_id & LUCID_INST_HAS_VERTEX_NORMALS) ? 0u : encodeNormalUint(normal);
+
+	F3 edge0 = (tri0 - tri2) * multiplier;
+	F3 edge1 = (tri1 - tri0) * multiplier;
+	float plane_dist = dot3(normal, tri0);
+	F3 nrm_tri0 = cross3(tri0, normal);
+	float param0 = dot3(edge0, nrm_tri0);
+	float param1 = dot3(edge1, nrm_tri0);
+	edge0 = cross3(normal, edge0);
+	edge1 = cross3(normal, edge1);
+
+	F3 dirx = xyz(cfg.frustum.ws_dirx), diry = xyz(cfg.frustum.ws_diry);
+	F3 dir0 = xyz(cfg.frustum.ws_dir0);
+	edge0 = mk3(dot3(edge0, dirx), dot3(edge0, diry), dot3(edge0, ray_dir0));
+	edge1 = mk3(dot3(edge1, dirx), dot3(edge1, diry), dot3(edge1, ray_dir0));
+	F3 pnormal = normal * rcp(plane_dist);
+	F3 depth_eq = mk3(dot3(pnormal, dirx), dot3(pnormal, diry), dot3(pnormal, ray_dir0));
+
+	TriShade sh;
+	sh.depth = make_uint4(__float_as_uint(depth_eq.x), __float_as_uint(depth_eq.y),
+						  __float_as_uint(depth_eq.z), flags_id);
+	sh.bary0 = make_uint4(__float_as_uint(edge0.x), __float_as_uint(edge0.y),
+						  __float_as_uint(edge0.z), __float_as_uint(param0));
+	sh.bary1 = make_uint4(__float_as_uint(edge1.x), __float_as_uint(edge1.y),
+						  __float_as_uint(edge1.z), __float_as_uint(param1));
+	sh.misc = make_uint4(enc_normal, inst_color, 0u, 0u);
+	uint4 *dst = reinterpret_cast<uint4 *>(p.tri_shade + tri_idx);
+	dst[0] = sh.depth, dst[1] = sh.bary0, dst[2] = sh.bary1, dst[3] = sh.misc;
+
+	F3 nrm0 = cross3(tri2, tri1 - tri2);
+	F3 nrm1 = cross3(tri0, tri2 - tri0);
+	F3 nrm2 = cross3(tri1, tri0 - tri1);
+	float volume = dot3(tri0, nrm0);
+	if(volume < 0.0f)
+		nrm0 = -nrm0, nrm1 = -nrm1, nrm2 = -nrm2;
+	F3 e0 = mk3(dot3(nrm0, dirx), dot3(nrm0, diry), dot3(nrm0, dir0));
+	F3 e1 = mk3(dot3(nrm1, dirx), dot3(nrm1, diry), dot3(nrm1, dir0));
+	F3 e2 = mk3(dot3(nrm2, dirx), dot3(nrm2, diry), dot3(nrm2, dir0));
+	float ix0 = rcp(e0.x), ix1 = rcp(e1.x), ix2 = rcp(e2.x);
+	F3 scan_base = -mk3(e0.z * ix0, e1.z * ix1, e2.z * ix2);
+	F3 scan_step = -mk3(e0.y * ix0, e1.y * ix1, e2.y * ix2);
+	u32 x_signs = (e0.x < 0.0f ? 1u : 0u) | (e1.x < 0.0f ? 2u : 0u) | (e2.x < 0.0f ? 4u : 0u);
+	u32 y_signs = (e0.y < 0.0f ? 8u : 0u) | (e1.y < 0.0f ? 16u : 0u) | (e2.y < 0.0f ? 32u : 0u);
+	F3 scan = mk3(scan_step.x * 0.5f + scan_base.x - (-0.5f), scan_step.y * 0.5f + scan_base.y - (-0.5f),
+				  scan_step.z * 0.5f + scan_base.z - (-0.5f));
+	uint4 *sdst = reinterpret_cast<uint4 *>(p.tri_scan + tri_idx);
+	sdst[0] = make_uint4(__float_as_uint(scan.x), __float_as_uint(scan.y), __float_as_uint(scan.z),
+						 y_aabb);
+	sdst[1] = make_uint4(__float_as_uint(scan_step.x), __float_as_uint(scan_step.y),
+						 __float_as_uint(scan_step.z), x_signs | y_signs);
+}
+
+// look-back word: [63:62] status, [61:31] small count, [30:0] large count
+constexpr u64 LB_AGGREGATE = 1ull << 62, LB_PREFIX = 2ull << 62, LB_STATUS = 3ull << 62;
+__device__ __forceinline__ u64 lbPack(u64 status, u32 small, u32 large) {
+	return status | ((u64)small << 31) | (u64)large;
+}
+__device__ __forceinline__ u64 lbLoad(const u64 *ptr) {
+	return *reinterpret_cast<const volatile u64 *>(ptr);
+}
+__device__ __forceinline__ void lbStore(u64 *ptr, u64 v) {
+	*reinterpret_cast<volatile u64 *>(ptr) = v;
+}
+
+struct KeptQuad {
+	uint4 verts;
+	u32 enc_aabb, y_aabb0, y_aabb1;
+	int slot;
+};
+
+__global__ void __launch_bounds__(SETUP_THREADS)
+	k_quad_setup(const Params p, const __grid_constant__ LucidConfig cfg) {
+	__shared__ KeptQuad s_kept[SETUP_THREADS];
+	__shared__ u32 s_vid;
+	__shared__ int s_warp_counts[SETUP_THREADS / 32][2];
+	__shared__ int s_base[2], s_total[2];
+	__shared__ u32 s_rejected[LUCID_REJECTION_TYPE_COUNT];
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	// CTAs are ordered by ticket, not by blockIdx, so every predecessor in the look-back chain is
+	// guaranteed to be running or finished.
+	if(tid == 0)
+		s_vid = atomicAdd(p.setup_ticket, 1u);
+	if(tid < LUCID_REJECTION_TYPE_COUNT)
+		s_rejected[tid] = 0;
+	__syncthreads();
+	const u32 vid = s_vid;
+	const int inst_id = vid / SETUP_PARTS, part = vid % SETUP_PARTS;
+	const LucidInstanceData inst = p.instances[inst_id];
+	const int local_quad = part * SETUP_THREADS + tid;
+	const bool has_quad = local_quad < inst.num_quads;
+	if(part == 0 && tid == 0)
+		atomicAdd(&p.info->num_input_quads, inst.num_quads);
+
+	uint4 vi = make_uint4(0, 0, 0, 0);
+	QuadResult res;
+	res.status = -3, res.size_type = 0, res.enc_aabb = 0, res.y_aabb0 = res.y_aabb1 = 0;
+	if(has_quad) {
+		// one 128-bit load per quad: the index buffer is 4 x u32 per quad (quad_setup.glsl:405-409)
+		const uint4 *ib = reinterpret_cast<const uint4 *>(
+			reinterpret_cast<const u32 *>(p.quad_indices) + inst.index_offset);
+		vi = __ldg(ib + local_quad);
+		vi.x += inst.vertex_offset, vi.y += inst.vertex_offset;
+		vi.z += inst.vertex_offset, vi.w += inst.vertex_offset;
+		res = processInputQuad(p, cfg, vi);
+	}
+
+	// ordered ranks of small / large visible quads inside the CTA
+	const bool vis = res.status == -1;
+	const bool is_small = vis && res.size_type == 0, is_large = vis && res.size_type == 1;
+	const u32 bs = __ballot_sync(0xffffffffu, is_small), bl = __ballot_sync(0xffffffffu, is_large);
+	{
+		// warp-aggregated rejection counters
+		int key = res.status >= 0 ? res.status : LUCID_REJECTION_TYPE_COUNT;
+		u32 peers = __match_any_sync(0xffffffffu, key);
+		if(res.status >= 0 && lane == __ffs(peers) - 1)
+			atomicAdd(&s_rejected[res.status], __popc(peers));
+	}
+	if(lane == 0)
+		s_warp_counts[warp][0] = __popc(bs), s_warp_counts[warp][1] = __popc(bl);
+	__syncthreads();
+	int before_small = __popc(bs & laneMaskLt()), before_large = __popc(bl & laneMaskLt());
+	int total_small = 0, total_large = 0;
+#pragma unroll
+	for(int w = 0; w < SETUP_THREADS / 32; w++) {
+		int cs = s_warp_counts[w][0], cl = s_warp_counts[w][1];
+		if(w < warp)
+			before_small += cs, before_large += cl;
+		total_small += cs, total_large += cl;
+	}
+
+	// decoupled look-back over (small, large) counts
+	if(warp == 0) {
+		u64 *lb = p.setup_lookback;
+		u32 ex_small = 0, ex_large = 0;
+		if(vid == 0) {
+			if(lane == 0)
+				lbStore(lb, lbPack(LB_PREFIX, total_small, total_large));
+		} else {
+			if(lane == 0)
+				lbStore(lb + vid, lbPack(LB_AGGREGATE, total_small, total_large));
+			int base = (int)vid - 1;
+			while(true) {
+				int idx = base - lane;
+				u64 st = idx >= 0 ? lbLoad(lb + idx) : lbPack(LB_PREFIX, 0, 0);
+				while(__any_sync(0xffffffffu, (st & LB_STATUS) == 0)) {
+					if((st & LB_STATUS) == 0)
+						st = lbLoad(lb + idx);
+				}
+				u32 pm = __ballot_sync(0xffffffffu, (st & LB_STATUS) == LB_PREFIX);
+				int first = pm ? __ffs(pm) - 1 : 32;
+				u32 cs = lane <= first ? (u32)((st >> 31) & 0x7fffffffu) : 0u;
+				u32 cl = lane <= first ? (u32)(st & 0x7fffffffu) : 0u;
+#pragma unroll
+				for(int o = 16; o > 0; o >>= 1) {
+					cs += __shfl_xor_sync(0xffffffffu, cs, o);
+					cl += __shfl_xor_sync(0xffffffffu, cl, o);
+				}
+				ex_small += cs, ex_large += cl;
+				if(pm)
+					break;
+				base -= 32;
+			}
+			if(lane == 0)
+				lbStore(lb + vid, lbPack(LB_PREFIX, ex_small + total_small, ex_large + total_large));
+		}
+		if(lane == 0) {
+			s_base[0] = ex_small, s_base[1] = ex_large;
+			s_total[0] = total_small, s_total[1] = total_large;
+		}
+	}
+	__syncthreads();
+
+	// slot assignment; quads past MAX_VISIBLE_QUADS (in input order) are dropped and counted
+	const int mvq = p.max_visible_quads;
+	int slot = -1;
+	if(vis) {
+		int gs = s_base[0] + before_small, gl = s_base[1] + before_large;
+		if(gs + gl < mvq)
+			slot = is_small ? gs : (mvq - 1) - gl;
+	}
+	{
+		u32 ks = __ballot_sync(0xffffffffu, slot >= 0 && is_small);
+		u32 kl = __ballot_sync(0xffffffffu, slot >= 0 && is_large);
+		u32 dr = __ballot_sync(0xffffffffu, vis && slot < 0);
+		if(lane == 0) {
+			if(ks)
+				atomicAdd(&p.info->num_visible_quads[0], __popc(ks));
+			if(kl)
+				atomicAdd(&p.info->num_visible_quads[1], __popc(kl));
+			if(dr)
+				atomicAdd(&p.info->temp[0], __popc(dr));
+		}
+	}
+	const int n_entries = s_total[0] + s_total[1];
+	if(vis) {
+		int e = is_small ? before_small : s_total[0] + before_large;
+		KeptQuad k;
+		k.verts = vi, k.enc_aabb = res.enc_aabb, k.y_aabb0 = res.y_aabb0, k.y_aabb1 = res.y_aabb1;
+		k.slot = slot;
+		s_kept[e] = k;
+	}
+	if(tid < LUCID_REJECTION_TYPE_COUNT && s_rejected[tid] != 0)
+		atomicAdd(&p.info->num_rejected_quads[tid], s_rejected[tid]);
+	__syncthreads();
+
+	// triangle records: all threads share the visible triangles evenly (two per kept quad)
+	const F3 dir0 = xyz(cfg.frustum.ws_dir0), dirx = xyz(cfg.frustum.ws_dirx);
+	const F3 diry = xyz(cfg.frustum.ws_diry), origin = xyz(cfg.frustum.ws_origin0);
+	const F3 ray_dir0 = dir0 + (dirx + diry) * 0.5f;
+	const u32 flags_id = inst.flags | ((u32)inst_id << 16);
+	const u32 inst_color = p.inst_colors[inst_id];
+	for(int j = tid; j < n_entries * 2; j += SETUP_THREADS) {
+		const KeptQuad &k = s_kept[j >> 1];
+		int second = j & 1;
+		if(k.slot < 0 || ((k.enc_aabb >> (30 + second)) & 1))
+			continue;
+		u32 i1 = second ? k.verts.z : k.verts.y, i2 = second ? k.verts.w : k.verts.z;
+		F3 t0 = vertexLoad(p, k.verts.x) - origin;
+		F3 t1 = vertexLoad(p, i1) - origin;
+		F3 t2 = vertexLoad(p, i2) - origin;
+		storeTri(p, cfg, (u32)k.slot * 2 + second, flags_id, inst_color, t0, t1, t2,
+				 second ? k.y_aabb1 : k.y_aabb0, ray_dir0);
+	}
+	// quad records (quad_setup.glsl:256-272, 342-354)
+	for(int e = tid; e < n_entries; e += SETUP_THREADS) {
+		const KeptQuad &k = s_kept[e];
+		if(k.slot < 0)
+			continue;
+		p.quad_aabbs[k.slot] = k.enc_aabb;
+		uint4 v = k.verts;
+		if((inst.flags & LUCID_INST_HAS_VERTEX_COLORS) && p.vertex_colors)
+			p.quad_colors[k.slot] =
+				make_uint4(__ldg(p.vertex_colors + v.x), __ldg(p.vertex_colors + v.y),
+						   __ldg(p.vertex_colors + v.z), __ldg(p.vertex_colors + v.w));
+		if((inst.flags & LUCID_INST_HAS_VERTEX_NORMALS) && p.vertex_normals)
+			p.quad_normals[k.slot] =
+				make_uint4(__ldg(p.vertex_normals + v.x), __ldg(p.vertex_normals + v.y),
+						   __ldg(p.vertex_normals + v.z), __ldg(p.vertex_normals + v.w));
+		if((inst.flags & LUCID_INST_HAS_ALBEDO_TEXTURE) && p.vertex_uvs) {
+			float2 t0 = __ldg(p.vertex_uvs + v.x), t1 = __ldg(p.vertex_uvs + v.y);
+			float2 t2 = __ldg(p.vertex_uvs + v.z), t3 = __ldg(p.vertex_uvs + v.w);
+			p.quad_uv[(size_t)k.slot * 2 + 0] =
+				make_uint4(__float_as_uint(t0.x), __float_as_uint(t0.y),
+						   __float_as_uint(t1.x - t0.x), __float_as_uint(t1.y - t0.y));
+			p.quad_uv[(size_t)k.slot * 2 + 1] =
+				make_uint4(__float_as_uint(t2.x - t0.x), __float_as_uint(t2.y - t0.y),
+						   __float_as_uint(t3.x - t0.x), __float_as_uint(t3.y - t0.y));
+		}
+	}
+}
+
+void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream) {
+	if(p.num_setup_ctas == 0)
+		return;
+	cudaMemsetAsync(p.setup_lookback, 0, (size_t)p.num_setup_ctas * sizeof(u64), stream);
+	cudaMemsetAsync(p.setup_ticket, 0, sizeof(u32), stream);
+	k_quad_setup<<<p.num_setup_ctas, SETUP_THREADS, 0, stream>>>(p, cfg);
+}
+
+} // namespace lucid

@@ -1,0 +1,1486 @@
+// lucid_oracle.cpp -- CPU restatement of the LucidRaster exact-OIT pipeline.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product path (lucid_b200/) may include, link or call
+// this file; it exists so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can
+// check the CUDA path and time a CPU baseline.
+//
+// PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or fixtures for the
+// renderer and its own implementation (GLSL compute on Vulkan) cannot run in
+// this image (no Vulkan ICD, no shaderc).  The pins we do have are the reference's runtime
+// invariants (verifyInfo, sortedness, stats[2]), closed-form scenes, an independent brute-force
+// rasteriser in tests/, and -- for the host-side camera/frustum math only -- the reference's own
+// libfwk sources compiled into oracle/_ref (see oracle/Makefile).
+//
+// What is restated (file:line under /root/reference):
+//   quad setup      data/shaders/quad_setup.glsl:64-489
+//   bin counting    data/shaders/bin_counter.glsl:53-134, shared/scanline.glsl:28-52
+//   categorising    data/shaders/bin_categorizer.glsl:22-89
+//   bin dispatch    data/shaders/bin_dispatcher.glsl:55-114 (the "simple" large-tri path)
+//   raster LOW      data/shaders/raster_low.glsl:39-281, shared/raster.glsl:116-176,272-396
+//   raster HIGH     data/shaders/raster_high.glsl:54-348
+//   shading/reduce  data/shaders/shared/shading.glsl:64-314, shared/funcs.glsl:28-33,100-121,153-164,261-271
+//
+// Determinism / canonical order (the reference's orders come from racing atomics and are
+// arbitrary; SURVEY.md section 7 "Hard parts"):
+//   * visible small quads take slots 0.. in input order, large quads MVQ-1.. downwards in input order;
+//   * every per-bin list is sorted ascending by its stored word's index;
+//   * inside a bin the triangle sequence T is: quads list (tri 0, tri 1 per quad) then tris list;
+//   * the block sort tie-break ("row slot") is the rank of the triangle in T restricted to its
+//     block row (LOW) / half-block row (HIGH).
+//
+// Floating-point contract shared with the CUDA kernels: IEEE binary32, round-to-nearest, every
+// operation individually rounded in the association written below (no FMA contraction: build with
+// -ffp-contract=off), 1/x and sqrt correctly rounded, inversesqrt(x) := 1/sqrt(x),
+// min/max := fminf/fmaxf (NaN loses), float->int conversions saturate (NaN -> 0),
+// pow(x, y) := the polynomial exp2/log2 of orc_pow() below.
+
+#include "../include/lucid_abi.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers (the fp contract)
+
+inline float bitsToFloat(u32 v) {
+	float f;
+	memcpy(&f, &v, 4);
+	return f;
+}
+inline u32 floatBits(float f) {
+	u32 v;
+	memcpy(&v, &f, 4);
+	return v;
+}
+inline int f2i(float x) {
+	if(x != x)
+		return 0;
+	if(x >= 2147483648.0f)
+		return std::numeric_limits<int>::max();
+	if(x <= -2147483648.0f)
+		return std::numeric_limits<int>::min();
+	return (int)x;
+}
+inline u32 f2u(float x) {
+	if(x != x || x <= 0.0f)
+		return 0;
+	if(x >= 4294967296.0f)
+		return 0xffffffffu;
+	return (u32)x;
+}
+inline float fmin2(float a, float b) { return fminf(a, b); }
+inline float fmax2(float a, float b) { return fmaxf(a, b); }
+inline float clampf(float x, float lo, float hi) { return fmin2(fmax2(x, lo), hi); }
+inline float saturate(float x) { return clampf(x, 0.0f, 1.0f); }
+inline float rcp(float x) { return 1.0f / x; }
+inline float rsqrt(float x) { return 1.0f / sqrtf(x); }
+inline int findLSB(u32 v) { return v == 0 ? -1 : __builtin_ctz(v); }
+inline int findMSB(u32 v) { return v == 0 ? -1 : 31 - __builtin_clz(v); }
+inline int popcount(u32 v) { return __builtin_popcount(v); }
+
+// log2 on the mantissa interval [sqrt(1/2), sqrt(2)) with the classic atanh series, exp2 with a
+// degree-6 Taylor polynomial; every operation is a plain binary32 op so the CUDA side can repeat
+// it bit for bit.  |relative error| < 2e-6 on the sRGB ranges (checked in tests/).
+inline float orc_log2(float x) {
+	u32 ix = floatBits(x);
+	int e = (int)(ix - 0x3f3504f3u) >> 23;
+	float m = bitsToFloat(ix - ((u32)e << 23));
+	float f = m - 1.0f;
+	float s = f / (2.0f + f);
+	float z = s * s;
+	float p = 0.2222222222f;				// 2/9
+	p = p * z + 0.2857142857f;				// 2/7
+	p = p * z + 0.4f;						// 2/5
+	p = p * z + 0.6666666667f;				// 2/3
+	p = p * z + 2.0f;
+	float ln = s * p;
+	return ln * 1.4426950408889634f + (float)e;
+}
+inline float orc_exp2(float t) {
+	float n = floorf(t + 0.5f);
+	float r = (t - n) * 0.6931471805599453f;
+	float p = 1.0f / 720.0f;
+	p = p * r + 1.0f / 120.0f;
+	p = p * r + 1.0f / 24.0f;
+	p = p * r + 1.0f / 6.0f;
+	p = p * r + 0.5f;
+	p = p * r + 1.0f;
+	p = p * r + 1.0f;
+	int ni = f2i(n);
+	if(ni < -126)
+		return 0.0f;
+	if(ni > 127)
+		ni = 127;
+	return p * bitsToFloat((u32)(ni + 127) << 23);
+}
+inline float orc_pow(float x, float y) {
+	if(!(x > 0.0f))
+		return 0.0f;
+	return orc_exp2(y * orc_log2(x));
+}
+
+struct V3 {
+	float x, y, z;
+};
+inline V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+inline V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+inline bool operator==(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) {
+	return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+inline float length(V3 a) { return sqrtf(dot(a, a)); }
+inline V3 xyz(const LucidVec4 &v) { return v3(v.x, v.y, v.z); }
+
+struct V4 {
+	float x, y, z, w;
+	float &operator[](int i) { return (&x)[i]; }
+	float operator[](int i) const { return (&x)[i]; }
+};
+
+struct UV4 {
+	u32 x, y, z, w;
+};
+
+// ------------------------------------------------------------------------------------------------
+// colour / normal codecs (shared/funcs.glsl:28-33,61-66,100-121,153-164)
+
+inline u32 encodeNormalUint(V3 n) {
+	u32 x = f2u(512.0f + n.x * 511.0f) & 0x3ffu;
+	u32 y = f2u(512.0f + n.y * 511.0f) & 0x3ffu;
+	u32 z = f2u(512.0f + n.z * 511.0f) & 0x3ffu;
+	return x | (y << 10) | (z << 20);
+}
+inline V3 decodeNormalUint(u32 n) {
+	const float s = 1.0f / 511.0f;
+	return v3((float((n >> 0) & 0x3ffu) - 512.0f) * s, (float((n >> 10) & 0x3ffu) - 512.0f) * s,
+			  (float((n >> 20) & 0x3ffu) - 512.0f) * s);
+}
+inline V4 decodeRGBA8(u32 c) {
+	const float s = 1.0f / 255.0f;
+	return V4{float(c & 0xffu) * s, float((c >> 8) & 0xffu) * s, float((c >> 16) & 0xffu) * s,
+			  float((c >> 24) & 0xffu) * s};
+}
+inline u32 encodeRGBA8(V4 c) {
+	return f2u(c.x * 255.0f) | (f2u(c.y * 255.0f) << 8) | (f2u(c.z * 255.0f) << 16) |
+		   (f2u(c.w * 255.0f) << 24);
+}
+inline float linearToSRGB1(float c) {
+	return c < 0.0031308f ? 12.92f * c : 1.055f * orc_pow(c, 1.0f / 2.4f) - 0.055f;
+}
+inline float SRGBToLinear1(float c) {
+	return c < 0.04045f ? (1.0f / 12.92f) * c : orc_pow((c + 0.055f) * (1.0f / 1.055f), 2.4f);
+}
+
+inline u32 encodeAABB28(u32 x0, u32 y0, u32 x1, u32 y1) {
+	return (x0 & 0x7fu) | ((y0 & 0x7fu) << 7) | ((x1 & 0x7fu) << 14) | ((y1 & 0x7fu) << 21);
+}
+
+// ------------------------------------------------------------------------------------------------
+
+struct Texture {
+	std::vector<std::vector<uint8_t>> mips; // RGBA8, tightly packed
+	std::vector<int> w, h;
+	bool valid() const { return !mips.empty(); }
+};
+
+struct TriRecord {
+	UV4 bary0, bary1, scan0, scan1, depth;
+	u32 normal;
+};
+
+struct QuadAttrs {
+	UV4 colors, normals, uv0, uv1;
+};
+
+struct Oracle {
+	// configuration
+	int width = 0, height = 0;
+	int bin_count_x = 0, bin_count_y = 0, bin_count = 0;
+	int max_visible_quads = 0;
+	u32 opts = 0;
+	int row_begin = 0, row_end = 0; // owned bin rows [begin, end)
+	int num_threads = 1;
+
+	// borrowed geometry
+	const float *positions = nullptr;
+	const u32 *colors = nullptr;
+	const float *uvs = nullptr;
+	const u32 *normals = nullptr;
+	const u32 *indices = nullptr;
+	int num_verts = 0, num_quads = 0;
+	Texture tex[2]; // 0 opaque, 1 transparent
+
+	// per-frame inputs
+	LucidConfig cfg;
+	std::vector<LucidInstanceData> instances;
+	std::vector<u32> inst_colors;
+	std::vector<V4> inst_uv_rects;
+
+	// outputs
+	LucidInfo info;
+	std::vector<int> counts; // 10 * bin_count
+	// visible quad storage: [0] small (slot = i), [1] large (slot = MVQ-1-i)
+	std::vector<u32> quad_aabbs[2];
+	std::vector<u32> quad_input_id[2];
+	std::vector<TriRecord> tris[2]; // 2 per quad
+	std::vector<QuadAttrs> qattrs[2];
+	std::vector<u32> bin_quads, bin_tris;
+	std::vector<u32> image;		  // RGBA8, width*height
+	std::vector<float> image_f;	  // RGB float pre-quantisation
+	std::vector<u32> frag_counts; // per pixel
+	std::vector<u32> exact_image; // per-pixel exact sort blend (cross-check of the window)
+	std::vector<uint8_t> bin_level; // final level each bin was rasterised at (0/2/4), 5 = error
+	double stage_ms[8] = {0};
+
+	const TriRecord &tri(u32 tri_idx) const {
+		u32 q = tri_idx >> 1;
+		if((int)q < (int)quad_aabbs[0].size())
+			return tris[0][tri_idx];
+		u32 k = (u32)(max_visible_quads - 1) - q;
+		return tris[1][k * 2 + (tri_idx & 1)];
+	}
+	const QuadAttrs &quadAttrs(u32 q) const {
+		if((int)q < (int)quad_aabbs[0].size())
+			return qattrs[0][q];
+		return qattrs[1][(u32)(max_visible_quads - 1) - q];
+	}
+	u32 quadAABB(u32 q) const {
+		if((int)q < (int)quad_aabbs[0].size())
+			return quad_aabbs[0][q];
+		return quad_aabbs[1][(u32)(max_visible_quads - 1) - q];
+	}
+	int *cnt(int which) { return counts.data() + (size_t)which * bin_count; }
+
+	void setup();
+	void binning();
+	void raster();
+	void rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]);
+	u32 shadeSample(int px, int py, u32 tri_idx, float &out_depth) const;
+	V4 sampleTexture(const Texture &, float u, float v, float dudx, float dvdx, float dudy,
+					 float dvdy) const;
+	void run();
+};
+
+V3 vertexLoad(const Oracle &o, u32 vi) {
+	return v3(o.positions[(size_t)vi * 3 + 0], o.positions[(size_t)vi * 3 + 1],
+			  o.positions[(size_t)vi * 3 + 2]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// quad setup (quad_setup.glsl)
+
+u32 vertexClipMask(V4 p) {
+	return (p.x < -p.w ? 0x01u : 0u) | (p.x > p.w ? 0x02u : 0u) | (p.y < -p.w ? 0x04u : 0u) |
+		   (p.y > p.w ? 0x08u : 0u) | (p.z < -p.w ? 0x10u : 0u) | (p.z > p.w ? 0x20u : 0u);
+}
+
+// quad_setup.glsl:77-128 (Blinn, "Calculating Screen Coverage")
+V4 clippedAABB(const V4 v[3], const float inv_w[3], u32 clipmask) {
+	V4 aabb{1.0f, 1.0f, -1.0f, -1.0f};
+	int any_vis = 0;
+	u32 or_mask = clipmask | (clipmask >> 8) | (clipmask >> 16);
+	for(int i = 0; i < 3; i++) {
+		u32 cm = clipmask >> (i * 8);
+		if((cm & 0x3) == 0) {
+			any_vis |= 0x1;
+			if(v[i].x - aabb[0] * v[i].w < 0.0f)
+				aabb[0] = v[i].x * inv_w[i];
+			if(v[i].x - aabb[2] * v[i].w > 0.0f)
+				aabb[2] = v[i].x * inv_w[i];
+		}
+		if((cm & 0xc) == 0) {
+			any_vis |= 0x10;
+			if(v[i].y - aabb[1] * v[i].w < 0.0f)
+				aabb[1] = v[i].y * inv_w[i];
+			if(v[i].y - aabb[3] * v[i].w > 0.0f)
+				aabb[3] = v[i].y * inv_w[i];
+		}
+	}
+	if((any_vis & 0x0f) == 0) {
+		aabb[0] = -1.0f, aabb[2] = 1.0f;
+	} else if((or_mask & 0x3) != 0) {
+		for(int i = 0; i < 3; i++) {
+			u32 cm = clipmask >> (i * 8);
+			if((cm & 0x1) != 0 && v[i].x - aabb[0] * v[i].w < 0.0f)
+				aabb[0] = -1.0f;
+			if((cm & 0x2) != 0 && v[i].x - aabb[2] * v[i].w > 0.0f)
+				aabb[2] = 1.0f;
+		}
+	}
+	if((any_vis & 0xf0) == 0) {
+		aabb[1] = -1.0f, aabb[3] = 1.0f;
+	} else if((or_mask & 0xc) != 0) {
+		for(int i = 0; i < 3; i++) {
+			u32 cm = clipmask >> (i * 8);
+			if((cm & 0x4) != 0 && v[i].y - aabb[1] * v[i].w < 0.0f)
+				aabb[1] = -1.0f;
+			if((cm & 0x8) != 0 && v[i].y - aabb[3] * v[i].w > 0.0f)
+				aabb[3] = 1.0f;
+		}
+	}
+	return aabb;
+}
+
+V4 plainAABB(V4 a, V4 b, V4 c) {
+	return V4{fmin2(fmin2(a.x, b.x), c.x), fmin2(fmin2(a.y, b.y), c.y), fmax2(fmax2(a.x, b.x), c.x),
+			  fmax2(fmax2(a.y, b.y), c.y)};
+}
+
+struct SetupQuad {
+	int status; // -1 visible, else rejection type
+	int size_type;
+	u32 enc_aabb;
+	u32 y_aabb[2];
+	u32 v[4];
+	bool owned;
+};
+
+// quad_setup.glsl:136-254
+SetupQuad processInputQuad(const Oracle &o, u32 v0, u32 v1, u32 v2, u32 v3) {
+	SetupQuad out;
+	out.status = -1;
+	out.owned = true;
+	out.v[0] = v0, out.v[1] = v1, out.v[2] = v2, out.v[3] = v3;
+	const LucidConfig &cfg = o.cfg;
+
+	bool cull0 = v0 == v1 || v1 == v2 || v2 == v0;
+	bool cull1 = v0 == v2 || v2 == v3 || v3 == v0;
+	if(cull0 && cull1) {
+		out.status = LUCID_REJECTION_OTHER;
+		return out;
+	}
+	V3 vws[4] = {vertexLoad(o, v0), vertexLoad(o, v1), vertexLoad(o, v2), vertexLoad(o, v3)};
+	cull0 = cull0 || vws[0] == vws[1] || vws[1] == vws[2] || vws[2] == vws[0];
+	cull1 = cull1 || vws[0] == vws[2] || vws[2] == vws[3] || vws[3] == vws[0];
+
+	if(cfg.enable_backface_culling != 0) {
+		V3 org = xyz(cfg.frustum.ws_origin0);
+		V3 p0 = vws[0] - org, p1 = vws[1] - org, p2 = vws[2] - org, p3 = vws[3] - org;
+		V3 nrm0 = cross(p2, p1 - p2);
+		V3 nrm1 = cross(p3, p2 - p3);
+		float volume0 = dot(p0, nrm0), volume1 = dot(p0, nrm1);
+		cull0 = cull0 || volume0 <= 0.0f;
+		cull1 = cull1 || volume1 <= 0.0f;
+		if(cull0 && cull1) {
+			out.status = LUCID_REJECTION_BACKFACE;
+			return out;
+		}
+	}
+	u32 cull_flags = (cull0 ? 1u : 0u) | (cull1 ? 2u : 0u);
+
+	V4 vndc[4];
+	const LucidVec4 *m = cfg.view_proj_matrix;
+	for(int i = 0; i < 4; i++) {
+		V3 p = vws[i];
+		vndc[i].x = m[0].x * p.x + m[1].x * p.y + m[2].x * p.z + m[3].x;
+		vndc[i].y = m[0].y * p.x + m[1].y * p.y + m[2].y * p.z + m[3].y;
+		vndc[i].z = m[0].z * p.x + m[1].z * p.y + m[2].z * p.z + m[3].z;
+		vndc[i].w = m[0].w * p.x + m[1].w * p.y + m[2].w * p.z + m[3].w;
+	}
+	u32 clipmask = vertexClipMask(vndc[0]) | (vertexClipMask(vndc[1]) << 8) |
+				   (vertexClipMask(vndc[2]) << 16) | (vertexClipMask(vndc[3]) << 24);
+	u32 and_mask = clipmask & (clipmask >> 8) & (clipmask >> 16) & (clipmask >> 24) & 0xffu;
+	u32 or_mask = clipmask | (clipmask >> 8) | (clipmask >> 16) | (clipmask >> 24);
+	if(and_mask != 0) {
+		out.status = LUCID_REJECTION_FRUSTUM;
+		return out;
+	}
+
+	V4 aabb0{0, 0, 0, 0}, aabb1{0, 0, 0, 0};
+	float inv_w[4] = {rcp(vndc[0].w), rcp(vndc[1].w), rcp(vndc[2].w), rcp(vndc[3].w)};
+	bool near_far = (or_mask & 0x30) != 0;
+	if(near_far) {
+		V4 t0[3] = {vndc[0], vndc[1], vndc[2]};
+		float w0[3] = {inv_w[0], inv_w[1], inv_w[2]};
+		aabb0 = clippedAABB(t0, w0, clipmask);
+		V4 t1[3] = {vndc[0], vndc[2], vndc[3]};
+		float w1[3] = {inv_w[0], inv_w[2], inv_w[3]};
+		aabb1 = clippedAABB(t1, w1, (clipmask & 0xffu) | ((clipmask & 0xffff0000u) >> 8));
+	}
+	for(int i = 0; i < 4; i++) {
+		vndc[i].x *= inv_w[i];
+		vndc[i].y *= inv_w[i];
+		vndc[i].z *= inv_w[i];
+	}
+	if(!near_far) {
+		aabb0 = plainAABB(vndc[0], vndc[1], vndc[2]);
+		aabb1 = plainAABB(vndc[0], vndc[2], vndc[3]);
+	}
+
+	float sx = float(o.width) * 0.5f, sy = float(o.height) * 0.5f;
+	float mx = float(o.width - 1), my = float(o.height - 1);
+	V4 scale{sx, sy, sx, sy};
+	for(int i = 0; i < 4; i++) {
+		aabb0[i] = (aabb0[i] + 1.0f) * scale[i];
+		aabb1[i] = (aabb1[i] + 1.0f) * scale[i];
+	}
+	V4 aabb{fmin2(aabb0[0], aabb1[0]), fmin2(aabb0[1], aabb1[1]), fmax2(aabb0[2], aabb1[2]),
+			fmax2(aabb0[3], aabb1[3])};
+
+	if(ceilf(aabb[0] - 0.5001f) == floorf(aabb[2] + 0.5001f) ||
+	   ceilf(aabb[1] - 0.5001f) == floorf(aabb[3] + 0.5001f)) {
+		out.status = LUCID_REJECTION_BETWEEN_SAMPLES;
+		return out;
+	}
+
+	const float off[4] = {0.49f, 0.49f, -0.49f, -0.49f};
+	const float hi[4] = {mx, my, mx, my};
+	for(int i = 0; i < 4; i++) {
+		aabb0[i] = clampf(aabb0[i] + off[i], 0.0f, hi[i]);
+		aabb1[i] = clampf(aabb1[i] + off[i], 0.0f, hi[i]);
+		aabb[i] = clampf(aabb[i] + off[i], 0.0f, hi[i]);
+	}
+	u32 b[4];
+	for(int i = 0; i < 4; i++)
+		b[i] = f2u(aabb[i]) >> LUCID_BIN_SHIFT;
+	out.enc_aabb = encodeAABB28(b[0], b[1], b[2], b[3]) | (cull_flags << 30);
+	u32 bsx = b[2] - b[0] + 1u, bsy = b[3] - b[1] + 1u;
+	out.size_type = bsx * bsy <= 4u ? 0 : 1;
+	out.y_aabb[0] = f2u(aabb0[1]) | (f2u(aabb0[3]) << 16);
+	out.y_aabb[1] = f2u(aabb1[1]) | (f2u(aabb1[3]) << 16);
+	// multi-GPU shard: quads whose bin rows miss [row_begin,row_end) are not kept;
+	// the small/large split above used the unclamped AABB.
+	out.owned = !((int)b[3] < o.row_begin || (int)b[1] >= o.row_end);
+	return out;
+}
+
+// quad_setup.glsl:274-340
+TriRecord storeTri(const Oracle &o, u32 instance_flags_id, V3 tri0, V3 tri1, V3 tri2, u32 y_aabb,
+				   V3 ray_dir0) {
+	TriRecord r;
+	V3 normal = cross(tri0 - tri2, tri1 - tri0);
+	float multiplier = rcp(length(normal));
+	normal = normal * multiplier;
+	r.normal = encodeNormalUint(normal);
+
+	V3 edge0 = (tri0 - tri2) * multiplier;
+	V3 edge1 = (tri1 - tri0) * multiplier;
+	float plane_dist = dot(normal, tri0);
+	V3 nrm_tri0 = cross(tri0, normal);
+	float param0 = dot(edge0, nrm_tri0);
+	float param1 = dot(edge1, nrm_tri0);
+	edge0 = cross(normal, edge0);
+	edge1 = cross(normal, edge1);
+
+	V3 dirx = xyz(o.cfg.frustum.ws_dirx), diry = xyz(o.cfg.frustum.ws_diry);
+	V3 dir0 = xyz(o.cfg.frustum.ws_dir0);
+	edge0 = v3(dot(edge0, dirx), dot(edge0, diry), dot(edge0, ray_dir0));
+	edge1 = v3(dot(edge1, dirx), dot(edge1, diry), dot(edge1, ray_dir0));
+
+	V3 pnormal = normal * rcp(plane_dist);
+	V3 depth_eq = v3(dot(pnormal, dirx), dot(pnormal, diry), dot(pnormal, ray_dir0));
+	r.depth = UV4{floatBits(depth_eq.x), floatBits(depth_eq.y), floatBits(depth_eq.z),
+				  instance_flags_id};
+	r.bary0 = UV4{floatBits(edge0.x), floatBits(edge0.y), floatBits(edge0.z), floatBits(param0)};
+	r.bary1 = UV4{floatBits(edge1.x), floatBits(edge1.y), floatBits(edge1.z), floatBits(param1)};
+
+	V3 nrm0 = cross(tri2, tri1 - tri2);
+	V3 nrm1 = cross(tri0, tri2 - tri0);
+	V3 nrm2 = cross(tri1, tri0 - tri1);
+	float volume = dot(tri0, nrm0);
+	if(volume < 0.0f)
+		nrm0 = -nrm0, nrm1 = -nrm1, nrm2 = -nrm2;
+	V3 e[3] = {v3(dot(nrm0, dirx), dot(nrm0, diry), dot(nrm0, dir0)),
+			   v3(dot(nrm1, dirx), dot(nrm1, diry), dot(nrm1, dir0)),
+			   v3(dot(nrm2, dirx), dot(nrm2, diry), dot(nrm2, dir0))};
+	float inv_ex[3] = {rcp(e[0].x), rcp(e[1].x), rcp(e[2].x)};
+	V3 scan_base = -v3(e[0].z * inv_ex[0], e[1].z * inv_ex[1], e[2].z * inv_ex[2]);
+	V3 scan_step = -v3(e[0].y * inv_ex[0], e[1].y * inv_ex[1], e[2].y * inv_ex[2]);
+	u32 x_signs = (e[0].x < 0.0f ? 1u : 0u) | (e[1].x < 0.0f ? 2u : 0u) | (e[2].x < 0.0f ? 4u : 0u);
+	u32 y_signs =
+		(e[0].y < 0.0f ? 8u : 0u) | (e[1].y < 0.0f ? 16u : 0u) | (e[2].y < 0.0f ? 32u : 0u);
+	// start = (-0.5, 0.5): scan = scan_step * start.y + scan_base - start.x
+	V3 scan = v3(scan_step.x * 0.5f + scan_base.x - (-0.5f), scan_step.y * 0.5f + scan_base.y - (-0.5f),
+				 scan_step.z * 0.5f + scan_base.z - (-0.5f));
+	r.scan0 = UV4{floatBits(scan.x), floatBits(scan.y), floatBits(scan.z), y_aabb};
+	r.scan1 = UV4{floatBits(scan_step.x), floatBits(scan_step.y), floatBits(scan_step.z),
+				  x_signs | y_signs};
+	return r;
+}
+
+// quad_setup.glsl:256-272
+QuadAttrs storeQuad(const Oracle &o, u32 flags, const u32 v[4]) {
+	QuadAttrs a;
+	memset(&a, 0, sizeof(a));
+	if((flags & LUCID_INST_HAS_VERTEX_COLORS) && o.colors)
+		a.colors = UV4{o.colors[v[0]], o.colors[v[1]], o.colors[v[2]], o.colors[v[3]]};
+	if((flags & LUCID_INST_HAS_VERTEX_NORMALS) && o.normals)
+		a.normals = UV4{o.normals[v[0]], o.normals[v[1]], o.normals[v[2]], o.normals[v[3]]};
+	if((flags & LUCID_INST_HAS_ALBEDO_TEXTURE) && o.uvs) {
+		float t0x = o.uvs[v[0] * 2], t0y = o.uvs[v[0] * 2 + 1];
+		float t1x = o.uvs[v[1] * 2] - t0x, t1y = o.uvs[v[1] * 2 + 1] - t0y;
+		float t2x = o.uvs[v[2] * 2] - t0x, t2y = o.uvs[v[2] * 2 + 1] - t0y;
+		float t3x = o.uvs[v[3] * 2] - t0x, t3y = o.uvs[v[3] * 2 + 1] - t0y;
+		a.uv0 = UV4{floatBits(t0x), floatBits(t0y), floatBits(t1x), floatBits(t1y)};
+		a.uv1 = UV4{floatBits(t2x), floatBits(t2y), floatBits(t3x), floatBits(t3y)};
+	}
+	return a;
+}
+
+void Oracle::setup() {
+	memset(&info, 0, sizeof(info));
+	counts.assign((size_t)bin_count * LUCID_COUNTS_PER_BIN, 0);
+	for(int s = 0; s < 2; s++) {
+		quad_aabbs[s].clear();
+		quad_input_id[s].clear();
+		tris[s].clear();
+		qattrs[s].clear();
+	}
+	int n_inst = (int)instances.size();
+	std::vector<int> inst_first_quad(n_inst + 1, 0);
+	for(int i = 0; i < n_inst; i++)
+		inst_first_quad[i + 1] = inst_first_quad[i] + instances[i].num_quads;
+	int total = inst_first_quad[n_inst];
+	info.num_input_quads = total;
+
+	V3 dir0 = xyz(cfg.frustum.ws_dir0), dirx = xyz(cfg.frustum.ws_dirx);
+	V3 diry = xyz(cfg.frustum.ws_diry);
+	V3 ray_dir0 = dir0 + (dirx + diry) * 0.5f;
+	V3 origin = xyz(cfg.frustum.ws_origin0);
+
+	std::vector<SetupQuad> sq((size_t)total);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(num_threads)
+	for(int i = 0; i < n_inst; i++) {
+		const LucidInstanceData &inst = instances[i];
+		for(int l = 0; l < inst.num_quads; l++) {
+			size_t io = (size_t)inst.index_offset + (size_t)l * 4;
+			u32 v0 = indices[io + 0] + (u32)inst.vertex_offset;
+			u32 v1 = indices[io + 1] + (u32)inst.vertex_offset;
+			u32 v2 = indices[io + 2] + (u32)inst.vertex_offset;
+			u32 v3_ = indices[io + 3] + (u32)inst.vertex_offset;
+			sq[(size_t)inst_first_quad[i] + l] = processInputQuad(*this, v0, v1, v2, v3_);
+		}
+	}
+
+	// sequential slot assignment in input order (canonical form of quad_setup.glsl:415-444)
+	std::vector<int> slot_of((size_t)total, -1);
+	int n_vis[2] = {0, 0};
+	for(int q = 0; q < total; q++) {
+		const SetupQuad &s = sq[q];
+		if(s.status >= 0) {
+			info.num_rejected_quads[s.status]++;
+			continue;
+		}
+		if(!s.owned)
+			continue;
+		if(n_vis[0] + n_vis[1] >= max_visible_quads) {
+			info.temp[0]++; // overflow: dropped (the reference has no defined behaviour here)
+			continue;
+		}
+		slot_of[q] = n_vis[s.size_type]++;
+	}
+	info.num_visible_quads[0] = n_vis[0];
+	info.num_visible_quads[1] = n_vis[1];
+	for(int s = 0; s < 2; s++) {
+		quad_aabbs[s].resize(n_vis[s]);
+		quad_input_id[s].resize(n_vis[s]);
+		tris[s].resize((size_t)n_vis[s] * 2);
+		qattrs[s].resize(n_vis[s]);
+	}
+
+#pragma omp parallel for schedule(dynamic, 4) num_threads(num_threads)
+	for(int i = 0; i < n_inst; i++) {
+		const LucidInstanceData &inst = instances[i];
+		u32 flags_id = inst.flags | ((u32)i << 16);
+		for(int l = 0; l < inst.num_quads; l++) {
+			int q = inst_first_quad[i] + l;
+			int k = slot_of[q];
+			if(k < 0)
+				continue;
+			const SetupQuad &s = sq[q];
+			int st = s.size_type;
+			quad_aabbs[st][k] = s.enc_aabb;
+			quad_input_id[st][k] = (u32)q;
+			qattrs[st][k] = storeQuad(*this, inst.flags, s.v);
+			for(int second = 0; second < 2; second++) {
+				TriRecord rec;
+				memset(&rec, 0, sizeof(rec));
+				if(((s.enc_aabb >> (30 + second)) & 1) == 0) {
+					V3 t0 = vertexLoad(*this, s.v[0]) - origin;
+					V3 t1 = vertexLoad(*this, s.v[1 + second]) - origin;
+					V3 t2 = vertexLoad(*this, s.v[2 + second]) - origin;
+					rec = storeTri(*this, flags_id, t0, t1, t2, s.y_aabb[second], ray_dir0);
+					if(inst.flags & LUCID_INST_HAS_VERTEX_NORMALS)
+						rec.normal = 0;
+				}
+				tris[st][(size_t)k * 2 + second] = rec;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// binning (bin_counter / bin_categorizer / bin_dispatcher)
+
+struct ScanParams {
+	float mn[3], mx[3], step[3];
+};
+
+const float INF = std::numeric_limits<float>::infinity();
+
+// scanline.glsl:28-52
+ScanParams loadScanBin(const TriRecord &t, int &min_by, int &max_by) {
+	ScanParams p;
+	float scan[3] = {bitsToFloat(t.scan0.x), bitsToFloat(t.scan0.y), bitsToFloat(t.scan0.z)};
+	p.step[0] = bitsToFloat(t.scan1.x), p.step[1] = bitsToFloat(t.scan1.y);
+	p.step[2] = bitsToFloat(t.scan1.z);
+	min_by = (int)(t.scan0.w & 0xffff) >> LUCID_BIN_SHIFT;
+	max_by = (int)(t.scan0.w >> 16) >> LUCID_BIN_SHIFT;
+	u32 signs = t.scan1.w;
+	const float offset = float(LUCID_BIN_SIZE) - 0.989f;
+	float start_x = 0.99f, start_y = float(min_by * LUCID_BIN_SIZE) - 0.01f;
+	for(int i = 0; i < 3; i++) {
+		bool xneg = (signs >> i) & 1, yneg = (signs >> (3 + i)) & 1;
+		float yoff = yneg ? 0.0f : offset, xoff = xneg ? 0.0f : offset;
+		float s = scan[i] + (p.step[i] * (yoff + start_y) - (xoff + start_x));
+		p.mn[i] = xneg ? -INF : s;
+		p.mx[i] = xneg ? s : INF;
+		p.step[i] = p.step[i] * float(LUCID_BIN_SIZE);
+	}
+	return p;
+}
+
+// bin_counter.glsl:53-62
+void scanlineStepBin(ScanParams &p, int &bmin, int &bmax) {
+	float xmin = fmax2(fmax2(p.mn[0], p.mn[1]), p.mn[2]);
+	float xmax = fmin2(fmin2(p.mx[0], p.mx[1]), p.mx[2]);
+	for(int i = 0; i < 3; i++) {
+		p.mn[i] += p.step[i];
+		p.mx[i] += p.step[i];
+	}
+	bmin = f2i(xmin + 1.0f) >> LUCID_BIN_SHIFT;
+	bmax = f2i(xmax) >> LUCID_BIN_SHIFT;
+}
+
+void Oracle::binning() {
+	int n_small = info.num_visible_quads[0], n_large = info.num_visible_quads[1];
+	int *qc = cnt(LUCID_CNT_QUAD_COUNTS), *tc = cnt(LUCID_CNT_TRI_COUNTS);
+	std::vector<std::vector<u32>> bq(bin_count), bt(bin_count);
+
+	// small quads: every bin of the (<= 4 bin) AABB, no edge test (bin_counter.glsl:64-72)
+	for(int q = 0; q < n_small; q++) {
+		u32 enc = quad_aabbs[0][q];
+		int bsx = enc & 0x7f, bsy = (enc >> 7) & 0x7f, bex = (enc >> 14) & 0x7f;
+		int bey = (enc >> 21) & 0x7f;
+		u32 word = (u32)q | (enc & 0xf0000000u);
+		for(int by = std::max(bsy, row_begin); by <= std::min(bey, row_end - 1); by++)
+			for(int bx = bsx; bx <= bex; bx++)
+				bq[by * bin_count_x + bx].push_back(word);
+	}
+	// large tris: per bin-row scanline at the trivial-reject corner (bin_counter.glsl:112-134,
+	// bin_dispatcher.glsl:89-114)
+	for(int k = 0; k < n_large; k++) {
+		u32 enc = quad_aabbs[1][k];
+		u32 quad_idx = (u32)(max_visible_quads - 1 - k);
+		int bsx = enc & 0x7f, bex = (enc >> 14) & 0x7f;
+		for(int second = 0; second < 2; second++) {
+			if((enc >> (30 + second)) & 1)
+				continue;
+			u32 tri_idx = quad_idx * 2 + second;
+			int bsy, bey;
+			ScanParams p = loadScanBin(tris[1][(size_t)k * 2 + second], bsy, bey);
+			for(int by = bsy; by <= bey; by++) {
+				int bmin, bmax;
+				scanlineStepBin(p, bmin, bmax);
+				bmin = std::max(bmin, bsx), bmax = std::min(bmax, bex);
+				if(by < row_begin || by >= row_end)
+					continue;
+				for(int bx = bmin; bx <= bmax; bx++)
+					bt[by * bin_count_x + bx].push_back(tri_idx);
+			}
+		}
+	}
+	info.num_counted_quads[0] = n_small;
+	info.num_counted_quads[1] = n_large;
+
+	// offsets + categories (bin_categorizer.glsl:22-89); level lists in ascending bin order
+	int qoff = 0, toff = 0;
+	int *qo = cnt(LUCID_CNT_QUAD_OFFSETS), *qt = cnt(LUCID_CNT_QUAD_OFFSETS_TEMP);
+	int *to = cnt(LUCID_CNT_TRI_OFFSETS), *tt = cnt(LUCID_CNT_TRI_OFFSETS_TEMP);
+	int *low = cnt(LUCID_CNT_LOW_BINS), *high = cnt(LUCID_CNT_HIGH_BINS);
+	for(int b = 0; b < bin_count; b++) {
+		std::sort(bq[b].begin(), bq[b].end(),
+				  [](u32 a, u32 c) { return (a & 0x0fffffffu) < (c & 0x0fffffffu); });
+		std::sort(bt[b].begin(), bt[b].end());
+		qc[b] = (int)bq[b].size(), tc[b] = (int)bt[b].size();
+		qo[b] = qoff, to[b] = toff;
+		qoff += qc[b], toff += tc[b];
+		qt[b] = qoff, tt[b] = toff;
+		int num_tris = tc[b] + qc[b] * 2;
+		if(num_tris == 0)
+			info.bin_level_counts[LUCID_BIN_LEVEL_EMPTY]++;
+		else if(num_tris < 1024)
+			low[info.bin_level_counts[LUCID_BIN_LEVEL_LOW]++] = b;
+		else
+			high[info.bin_level_counts[LUCID_BIN_LEVEL_HIGH]++] = b;
+	}
+	bin_quads.clear(), bin_tris.clear();
+	bin_quads.reserve(qoff), bin_tris.reserve(toff);
+	for(int b = 0; b < bin_count; b++) {
+		bin_quads.insert(bin_quads.end(), bq[b].begin(), bq[b].end());
+		bin_tris.insert(bin_tris.end(), bt[b].begin(), bt[b].end());
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading (shared/shading.glsl:64-184)
+
+inline float fractf(float x) { return x - floorf(x); }
+
+// Texture filter definition (the reference delegates to the Vulkan sampler, which is
+// implementation defined): repeat addressing, bilinear inside a level, linear
+// between the two nearest levels, lod = log2(max(|d/dx|, |d/dy|) in texels), no anisotropy.
+V4 texel(const Texture &t, int level, int x, int y) {
+	int w = t.w[level], h = t.h[level];
+	x = ((x % w) + w) % w;
+	y = ((y % h) + h) % h;
+	const uint8_t *p = &t.mips[level][((size_t)y * w + x) * 4];
+	const float s = 1.0f / 255.0f;
+	return V4{float(p[0]) * s, float(p[1]) * s, float(p[2]) * s, float(p[3]) * s};
+}
+V4 bilinear(const Texture &t, int level, float u, float v) {
+	float fx = u * float(t.w[level]) - 0.5f, fy = v * float(t.h[level]) - 0.5f;
+	float x0f = floorf(fx), y0f = floorf(fy);
+	float ax = fx - x0f, ay = fy - y0f;
+	int x0 = f2i(x0f), y0 = f2i(y0f);
+	V4 c00 = texel(t, level, x0, y0), c10 = texel(t, level, x0 + 1, y0);
+	V4 c01 = texel(t, level, x0, y0 + 1), c11 = texel(t, level, x0 + 1, y0 + 1);
+	V4 out;
+	for(int i = 0; i < 4; i++) {
+		float top = c00[i] + (c10[i] - c00[i]) * ax;
+		float bot = c01[i] + (c11[i] - c01[i]) * ax;
+		out[i] = top + (bot - top) * ay;
+	}
+	return out;
+}
+V4 Oracle::sampleTexture(const Texture &t, float u, float v, float dudx, float dvdx, float dudy,
+						 float dvdy) const {
+	if(!t.valid())
+		return V4{1.0f, 1.0f, 1.0f, 1.0f};
+	float w0 = float(t.w[0]), h0 = float(t.h[0]);
+	float ax = dudx * w0, ay = dvdx * h0, bx = dudy * w0, by = dvdy * h0;
+	float rho2 = fmax2(ax * ax + ay * ay, bx * bx + by * by);
+	int levels = (int)t.mips.size();
+	float lod = 0.0f;
+	if(rho2 > 1.0f)
+		lod = 0.5f * orc_log2(rho2);
+	lod = clampf(lod, 0.0f, float(levels - 1));
+	float l0f = floorf(lod);
+	int l0 = f2i(l0f), l1 = std::min(l0 + 1, levels - 1);
+	float a = lod - l0f;
+	V4 c0 = bilinear(t, l0, u, v);
+	if(a == 0.0f || l1 == l0)
+		return c0;
+	V4 c1 = bilinear(t, l1, u, v);
+	V4 out;
+	for(int i = 0; i < 4; i++)
+		out[i] = c0[i] + (c1[i] - c0[i]) * a;
+	return out;
+}
+
+u32 Oracle::shadeSample(int ipx, int ipy, u32 tri_idx, float &out_depth) const {
+	float px = float(ipx), py = float(ipy);
+	const TriRecord &t = tri(tri_idx);
+	float dx = bitsToFloat(t.depth.x), dy = bitsToFloat(t.depth.y), dz = bitsToFloat(t.depth.z);
+	u32 flags = t.depth.w & 0xffff, instance_id = t.depth.w >> 16;
+	float e0x = bitsToFloat(t.bary0.x), e0y = bitsToFloat(t.bary0.y), e0z = bitsToFloat(t.bary0.z);
+	float e1x = bitsToFloat(t.bary1.x), e1y = bitsToFloat(t.bary1.y), e1z = bitsToFloat(t.bary1.z);
+	float param0 = bitsToFloat(t.bary0.w), param1 = bitsToFloat(t.bary1.w);
+
+	float inv_ray_pos = dx * px + (dy * py + dz);
+	out_depth = inv_ray_pos;
+	float ray_pos = rcp(inv_ray_pos);
+	float e0 = e0x * px + (e0y * py + e0z);
+	float e1 = e1x * px + (e1y * py + e1z);
+	float b0 = e0 * ray_pos, b1 = e1 * ray_pos;
+
+	float bdx0 = 0, bdx1 = 0, bdy0 = 0, bdy1 = 0;
+	bool textured = (flags & LUCID_INST_HAS_ALBEDO_TEXTURE) != 0;
+	if(textured) {
+		float ray_posx = rcp(inv_ray_pos + dx);
+		float ray_posy = rcp(inv_ray_pos + dy);
+		bdx0 = (e0 + e0x) * ray_posx - b0, bdx1 = (e1 + e1x) * ray_posx - b1;
+		bdy0 = (e0 + e0y) * ray_posy - b0, bdy1 = (e1 + e1y) * ray_posy - b1;
+	}
+	b0 -= param0, b1 -= param1;
+
+	V4 color{1.0f, 1.0f, 1.0f, 1.0f};
+	if(flags & LUCID_INST_HAS_COLOR)
+		color = decodeRGBA8(inst_colors[instance_id]);
+
+	u32 second = tri_idx & 1;
+	if(textured) {
+		const QuadAttrs &qa = quadAttrs(tri_idx >> 1);
+		float t0x = bitsToFloat(qa.uv0.x), t0y = bitsToFloat(qa.uv0.y);
+		float t1x = bitsToFloat(second == 0 ? qa.uv0.z : qa.uv1.x);
+		float t1y = bitsToFloat(second == 0 ? qa.uv0.w : qa.uv1.y);
+		float t2x = bitsToFloat(second == 0 ? qa.uv1.x : qa.uv1.z);
+		float t2y = bitsToFloat(second == 0 ? qa.uv1.y : qa.uv1.w);
+		float u = b0 * t1x + (b1 * t2x + t0x), v = b0 * t1y + (b1 * t2y + t0y);
+		float dudx = bdx0 * t1x + bdx1 * t2x, dvdx = bdx0 * t1y + bdx1 * t2y;
+		float dudy = bdy0 * t1x + bdy1 * t2x, dvdy = bdy0 * t1y + bdy1 * t2y;
+		if(flags & LUCID_INST_HAS_UV_RECT) {
+			V4 r = inst_uv_rects[instance_id];
+			u = r.z * fractf(u) + r.x, v = r.w * fractf(v) + r.y;
+			dudx *= r.z, dvdx *= r.w, dudy *= r.z, dvdy *= r.w;
+		}
+		V4 tc;
+		if(flags & LUCID_INST_TEX_OPAQUE) {
+			tc = sampleTexture(tex[0], u, v, dudx, dvdx, dudy, dvdy);
+			tc.w = 1.0f;
+		} else {
+			tc = sampleTexture(tex[1], u, v, dudx, dvdx, dudy, dvdy);
+		}
+		for(int i = 0; i < 4; i++)
+			color[i] *= tc[i];
+	}
+	if(flags & LUCID_INST_HAS_VERTEX_COLORS) {
+		const QuadAttrs &qa = quadAttrs(tri_idx >> 1);
+		const u32 *c = &qa.colors.x;
+		V4 c0 = decodeRGBA8(c[0]), c1 = decodeRGBA8(c[1 + second]), c2 = decodeRGBA8(c[2 + second]);
+		float w0 = 1.0f - b0 - b1;
+		for(int i = 0; i < 4; i++)
+			color[i] *= w0 * c0[i] + (b0 * c1[i] + b1 * c2[i]);
+	}
+	if(color.w == 0.0f)
+		return 0;
+
+	V3 normal;
+	if(flags & LUCID_INST_HAS_VERTEX_NORMALS) {
+		const QuadAttrs &qa = quadAttrs(tri_idx >> 1);
+		const u32 *n = &qa.normals.x;
+		V3 n0 = decodeNormalUint(n[0]);
+		V3 n1 = decodeNormalUint(n[1 + second]) - n0, n2 = decodeNormalUint(n[2 + second]) - n0;
+		normal = v3(b0 * n1.x + (b1 * n2.x + n0.x), b0 * n1.y + (b1 * n2.y + n0.y),
+					b0 * n1.z + (b1 * n2.z + n0.z));
+	} else {
+		normal = decodeNormalUint(t.normal);
+	}
+	const LucidLighting &L = cfg.lighting;
+	V3 msun = v3(-L.sun_dir.x, -L.sun_dir.y, -L.sun_dir.z);
+	float light_value = fmax2(0.0f, dot(msun, normal) * 0.7f + 0.3f);
+	// finalShading, funcs.glsl:261-271
+	float amb[3] = {L.ambient_color.x * L.ambient_power, L.ambient_color.y * L.ambient_power,
+					L.ambient_color.z * L.ambient_power};
+	float dif[3] = {L.sun_color.x * L.sun_power * light_value,
+					L.sun_color.y * L.sun_power * light_value,
+					L.sun_color.z * L.sun_power * light_value};
+	for(int i = 0; i < 3; i++) {
+		float lin = SRGBToLinear1(color[i]);
+		color[i] = saturate(linearToSRGB1(lin * (amb[i] + dif[i])));
+	}
+	return encodeRGBA8(color);
+}
+
+// shared/shading.glsl:186-314; window of 3 (+1 depth when counting invalid pixels)
+struct Reducer {
+	float prev_depths[4];
+	u32 prev_colors[3];
+	float out_trans;
+	float out_color[3];
+	bool additive;
+	u32 invalid;
+	void init(bool additive_) {
+		for(int i = 0; i < 4; i++)
+			prev_depths[i] = 999999999.0f;
+		for(int i = 0; i < 3; i++)
+			prev_colors[i] = 0, out_color[i] = 0.0f;
+		out_trans = 1.0f;
+		additive = additive_;
+		invalid = 0;
+	}
+	void blend(u32 c) {
+		V4 cc = decodeRGBA8(c);
+		if(additive) {
+			for(int i = 0; i < 3; i++)
+				out_color[i] += cc[i] * cc.w;
+		} else {
+			for(int i = 0; i < 3; i++)
+				out_color[i] += cc[i] * cc.w * out_trans;
+			out_trans *= 1.0f - cc.w;
+		}
+	}
+	void push(u32 color, float depth, bool vis_errors) {
+		if(depth > prev_depths[0]) {
+			std::swap(color, prev_colors[0]);
+			std::swap(depth, prev_depths[0]);
+			if(prev_depths[0] > prev_depths[1]) {
+				std::swap(prev_colors[0], prev_colors[1]);
+				std::swap(prev_depths[0], prev_depths[1]);
+				if(prev_depths[1] > prev_depths[2]) {
+					std::swap(prev_colors[1], prev_colors[2]);
+					std::swap(prev_depths[1], prev_depths[2]);
+					// the 4th depth exists only in VISUALIZE_ERRORS builds; it is tracked here
+					// unconditionally so stats[2] is always available, but it only changes the
+					// image when vis_errors is set (shading.glsl:258-265)
+					if(prev_depths[2] > prev_depths[3]) {
+						invalid++;
+						if(vis_errors) {
+							out_color[0] = 1.0f, out_color[1] = 0.0f, out_color[2] = 0.0f;
+							out_trans = 0.0f;
+							return;
+						}
+					}
+				}
+			}
+		}
+		prev_depths[3] = prev_depths[2];
+		prev_depths[2] = prev_depths[1];
+		prev_depths[1] = prev_depths[0];
+		prev_depths[0] = depth;
+		if(prev_colors[2] != 0)
+			blend(prev_colors[2]);
+		prev_colors[2] = prev_colors[1];
+		prev_colors[1] = prev_colors[0];
+		prev_colors[0] = color;
+	}
+	void finish(const LucidVec4 &bg, float rgb[3]) {
+		for(int i = 2; i >= 0; i--)
+			if(prev_colors[i] != 0)
+				blend(prev_colors[i]);
+		rgb[0] = saturate(out_color[0] + out_trans * bg.x);
+		rgb[1] = saturate(out_color[1] + out_trans * bg.y);
+		rgb[2] = saturate(out_color[2] + out_trans * bg.z);
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// rasterisation of one bin
+
+// scanline.glsl:13-26 + raster.glsl:116-140: four rows of [xmin,xmax] spans, 5 bits each
+struct RowScan {
+	float scan[3], step[3];
+	bool xneg[3];
+};
+RowScan loadScanRow(const TriRecord &t, float start_x, float start_y) {
+	RowScan r;
+	float scan[3] = {bitsToFloat(t.scan0.x), bitsToFloat(t.scan0.y), bitsToFloat(t.scan0.z)};
+	r.step[0] = bitsToFloat(t.scan1.x), r.step[1] = bitsToFloat(t.scan1.y);
+	r.step[2] = bitsToFloat(t.scan1.z);
+	for(int i = 0; i < 3; i++) {
+		r.xneg[i] = (t.scan1.w >> i) & 1;
+		r.scan[i] = scan[i] + (r.step[i] * start_y - start_x);
+	}
+	return r;
+}
+void rasterBinStep(RowScan &r, u32 &min_bits, u32 &max_bits, u32 &bx_mask) {
+	min_bits = max_bits = bx_mask = 0;
+	for(int row = 0; row < 4; row++) {
+		float mn[3], mx[3];
+		for(int i = 0; i < 3; i++) {
+			mn[i] = r.xneg[i] ? -INF : r.scan[i];
+			mx[i] = r.xneg[i] ? r.scan[i] : INF;
+		}
+		int imin = f2i(fmax2(fmax2(mn[0], mn[1]), fmax2(mn[2], 0.0f)));
+		int imax = f2i(fmin2(fmin2(mx[0], mx[1]), fmin2(mx[2], float(LUCID_BIN_SIZE)))) - 1;
+		if(imin > imax)
+			imin = LUCID_BIN_SIZE - 1, imax = 0;
+		for(int i = 0; i < 3; i++)
+			r.scan[i] += r.step[i];
+		min_bits |= (u32)imin << (5 * row);
+		max_bits |= (u32)imax << (5 * row);
+		bx_mask |= (0xfu << (imin >> 3)) & (0xfu >> (3 - (imax >> 3)));
+	}
+	bx_mask &= 0xf;
+}
+
+// raster.glsl:142-168: spans of one 8x4 half-block column
+struct HalfSpans {
+	int xmin[4], count[4];
+	u32 num_frags;
+};
+HalfSpans halfSpans(u32 mins, u32 maxs, int startx) {
+	HalfSpans h;
+	h.num_frags = 0;
+	for(int r = 0; r < 4; r++) {
+		int mn = std::max((int)((mins >> (5 * r)) & 31) - startx, 0);
+		int mx = std::min((int)((maxs >> (5 * r)) & 31) - startx, 7);
+		h.xmin[r] = mn;
+		h.count[r] = std::max(mx - mn + 1, 0);
+		h.num_frags += h.count[r];
+	}
+	return h;
+}
+void halfCentroid(const HalfSpans &h, float &cx, float &cy) {
+	float cpx[4], cpy[4];
+	const float ys[4] = {1.0f, 3.0f, 5.0f, 7.0f};
+	for(int r = 0; r < 4; r++) {
+		cpx[r] = float(h.xmin[r] * 2 + h.count[r]) * float(h.count[r]);
+		cpy[r] = ys[r] * float(h.count[r]);
+	}
+	cx = cpx[0] + cpx[1] + cpx[2] + cpx[3];
+	cy = cpy[0] + cpy[1] + cpy[2] + cpy[3];
+}
+u32 halfPixelMask(const HalfSpans &h) {
+	u32 bits = 0;
+	for(int r = 0; r < 4; r++)
+		if(h.count[r] > 0)
+			bits |= ((1u << h.count[r]) - 1u) << (h.xmin[r] + 8 * r);
+	return bits;
+}
+
+// raster.glsl:170-176
+u32 blockDepth(const TriRecord &t, float cx, float cy, float range) {
+	float dx = bitsToFloat(t.depth.x), dy = bitsToFloat(t.depth.y), dz = bitsToFloat(t.depth.z);
+	float ray_pos = dx * cx + (dy * cy + dz);
+	float depth = range * saturate(rsqrt(ray_pos + 1.0f));
+	return f2u(depth);
+}
+
+struct RowTri {
+	u32 mins[2], maxs[2]; // LOW uses both 4-row groups, HIGH only [0]
+	u32 bx_mask;
+	u32 tri_idx;
+};
+
+void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
+	promote = false;
+	const int *qc = counts.data() + (size_t)LUCID_CNT_QUAD_COUNTS * bin_count;
+	const int *qo = counts.data() + (size_t)LUCID_CNT_QUAD_OFFSETS * bin_count;
+	const int *tc = counts.data() + (size_t)LUCID_CNT_TRI_COUNTS * bin_count;
+	const int *to = counts.data() + (size_t)LUCID_CNT_TRI_OFFSETS * bin_count;
+	int bin_y = bin_id / bin_count_x, bin_x = bin_id - bin_y * bin_count_x;
+	int pos_x = bin_x * LUCID_BIN_SIZE, pos_y = bin_y * LUCID_BIN_SIZE;
+
+	// triangle sequence T (raster_low.glsl:66-79)
+	std::vector<u32> T;
+	T.reserve((size_t)qc[bin_id] * 2 + tc[bin_id]);
+	for(int i = 0; i < qc[bin_id]; i++) {
+		u32 w = bin_quads[(size_t)qo[bin_id] + i];
+		u32 quad_idx = w & 0xfffffffu;
+		for(u32 second = 0; second < 2; second++)
+			if(((w >> (30 + second)) & 1) == 0)
+				T.push_back(quad_idx * 2 + second);
+	}
+	for(int i = 0; i < tc[bin_id]; i++)
+		T.push_back(bin_tris[(size_t)to[bin_id] + i]);
+
+	const int rows_per_group = high ? 4 : 8; // half-block rows vs block rows
+	const int num_groups = LUCID_BIN_SIZE / rows_per_group;
+	const int shift = high ? 2 : 3;
+	std::vector<std::vector<RowTri>> rows(num_groups);
+	bool error = false;
+
+	// generateRowTris (raster_low.glsl:39-64, raster_high.glsl:54-90)
+	for(u32 tri_idx : T) {
+		const TriRecord &t = tri(tri_idx);
+		int ymin = (int)(t.scan0.w & 0xffff) - pos_y, ymax = (int)(t.scan0.w >> 16) - pos_y;
+		int min_g = std::min(std::max(ymin, 0), LUCID_BIN_SIZE - 1) >> shift;
+		int max_g = std::min(std::max(ymax, 0), LUCID_BIN_SIZE - 1) >> shift;
+		RowScan rs = loadScanRow(t, float(pos_x), float(pos_y + min_g * rows_per_group));
+		for(int g = min_g; g <= max_g; g++) {
+			RowTri rt;
+			rt.tri_idx = tri_idx;
+			rt.mins[1] = rt.maxs[1] = 0;
+			u32 bx0, bx1 = 0;
+			rasterBinStep(rs, rt.mins[0], rt.maxs[0], bx0);
+			if(!high)
+				rasterBinStep(rs, rt.mins[1], rt.maxs[1], bx1);
+			rt.bx_mask = bx0 | bx1;
+			if(rt.bx_mask == 0)
+				continue;
+			if(high && rows[g].size() >= 16384) { // MAX_HBLOCK_ROW_TRIS, raster_high.glsl:80-83
+				error = true;
+				continue;
+			}
+			rows[g].push_back(rt);
+		}
+	}
+
+	if(high) {
+		// computeRBlockGroups (raster_high.glsl:108-144): estimate = tris whose [first,last]
+		// column range covers the half-block; more than 16 * 256 is an error
+		for(int g = 0; g < num_groups && !error; g++) {
+			int est[4] = {0, 0, 0, 0};
+			for(const RowTri &rt : rows[g])
+				for(int c = findLSB(rt.bx_mask); c <= findMSB(rt.bx_mask); c++)
+					est[c]++;
+			for(int c = 0; c < 4; c++)
+				if(est[c] > 256 * 16)
+					error = true;
+		}
+	} else {
+		// generateBlocks overflow check (raster_low.glsl:92-105): > 256 tris in an 8x8 block
+		for(int g = 0; g < num_groups; g++) {
+			int bc[4] = {0, 0, 0, 0};
+			for(const RowTri &rt : rows[g])
+				for(int c = 0; c < 4; c++)
+					if(rt.bx_mask & (1u << c))
+						bc[c]++;
+			for(int c = 0; c < 4; c++)
+				if(bc[c] > 256)
+					promote = true;
+		}
+		if(promote)
+			return;
+	}
+
+	bool additive = (opts & LUCID_OPT_ADDITIVE_BLENDING) != 0;
+	bool vis_errors = (opts & LUCID_OPT_VISUALIZE_ERRORS) != 0;
+	bool alpha_thr = (opts & LUCID_OPT_ALPHA_THRESHOLD) != 0 && !additive && !vis_errors;
+	const float alpha_threshold = 1.0f / 128.0f;
+
+	if(error) {
+		// raster_high.glsl:313-317: the bin is painted red with alpha 0.  (The reference adds
+		// stale shared-memory counters to the stats here; we add nothing.)
+		for(int y = 0; y < LUCID_BIN_SIZE; y++)
+			for(int x = 0; x < LUCID_BIN_SIZE; x++) {
+				int gx = pos_x + x, gy = pos_y + y;
+				if(gx < width && gy < height) {
+					size_t p = (size_t)gy * width + gx;
+					image[p] = 0x000000ffu;
+					image_f[p * 3 + 0] = 1.0f, image_f[p * 3 + 1] = 0.0f, image_f[p * 3 + 2] = 0.0f;
+					exact_image[p] = 0x000000ffu;
+				}
+			}
+		bin_level[bin_id] = 5;
+		return;
+	}
+
+	struct Entry {
+		u32 key;
+		u32 slot;
+	};
+	for(int g = 0; g < num_groups; g++) {
+		for(int bx = 0; bx < 4; bx++) {
+			// block list in row-slot order, then depth keys
+			std::vector<Entry> list;
+			int startx = bx * 8;
+			for(u32 slot = 0; slot < rows[g].size(); slot++) {
+				const RowTri &rt = rows[g][slot];
+				if(!(rt.bx_mask & (1u << bx)))
+					continue;
+				HalfSpans h0 = halfSpans(rt.mins[0], rt.maxs[0], startx);
+				float cx, cy;
+				halfCentroid(h0, cx, cy);
+				u32 nf = h0.num_frags;
+				if(!high) {
+					HalfSpans h1 = halfSpans(rt.mins[1], rt.maxs[1], startx);
+					float cx1, cy1;
+					halfCentroid(h1, cx1, cy1);
+					cx = cx + cx1, cy = cy + cy1;
+					nf += h1.num_frags;
+				}
+				float scale = 0.5f / float(nf);
+				float bpx = float(pos_x + bx * 8), bpy = float(pos_y + g * rows_per_group);
+				float cpx = cx * scale + bpx, cpy = cy * scale + bpy;
+				u32 depth = blockDepth(tri(rt.tri_idx), cpx, cpy, high ? float(0x7fffe) : float(0x3ffffe));
+				Entry e;
+				e.slot = slot;
+				e.key = high ? (slot | (depth << 14)) : (slot | (depth << 10));
+				list.push_back(e);
+			}
+			if(list.empty() && !high) {
+				// still need to write background below
+			}
+			// LOW skips the sort for <= 3 tris (raster_low.glsl:144)
+			if(high || list.size() > 3)
+				std::sort(list.begin(), list.end(),
+						  [](const Entry &a, const Entry &b) { return a.key < b.key; });
+
+			int halves = high ? 1 : 2;
+			for(int half = 0; half < halves; half++) {
+				int hb_y = pos_y + g * rows_per_group + half * 4; // top row of the half-block
+				int hb_x = pos_x + bx * 8;
+				Reducer red[32];
+				std::vector<std::pair<float, u32>> exact[32];
+				u32 px_frags[32];
+				for(int p = 0; p < 32; p++)
+					red[p].init(additive), px_frags[p] = 0;
+
+				u32 frag_total = 0, tri_count = (u32)list.size();
+				u32 processed = 0; // samples consumed so far (segment boundaries every 256)
+				bool stop = false;
+				for(const Entry &e : list) {
+					const RowTri &rt = rows[g][e.slot];
+					HalfSpans h = halfSpans(rt.mins[half], rt.maxs[half], startx);
+					frag_total += h.num_frags;
+					u32 bits = halfPixelMask(h);
+					while(bits != 0) {
+						int pid = findLSB(bits);
+						bits &= bits - 1;
+						int ipx = hb_x + (pid & 7), ipy = hb_y + (pid >> 3);
+						px_frags[pid]++;
+						if(!stop) {
+							float depth;
+							u32 color = shadeSample(ipx, ipy, rt.tri_idx, depth);
+							red[pid].push(color, depth, vis_errors);
+							exact[pid].push_back(std::make_pair(depth, color));
+						}
+						processed++;
+						if((processed & 255) == 0) {
+							// end of a 256-sample segment (raster.glsl:394-395): saturate and,
+							// in ALPHA_THRESHOLD builds, stop once every pixel is opaque enough
+							bool all_opaque = true;
+							for(int p = 0; p < 32; p++) {
+								for(int i = 0; i < 3; i++)
+									red[p].out_color[i] = saturate(red[p].out_color[i]);
+								all_opaque = all_opaque && red[p].out_trans < alpha_threshold;
+							}
+							if(alpha_thr && all_opaque)
+								stop = true;
+						}
+					}
+				}
+				if((processed & 255) != 0)
+					for(int p = 0; p < 32; p++)
+						for(int i = 0; i < 3; i++)
+							red[p].out_color[i] = saturate(red[p].out_color[i]);
+
+				stats[0] += frag_total;
+				stats[1] += tri_count;
+				for(int p = 0; p < 32; p++) {
+					int gx = hb_x + (p & 7), gy = hb_y + (p >> 3);
+					if(vis_errors)
+						stats[2] += red[p].invalid; // only VISUALIZE_ERRORS builds count these
+					if(gx >= width || gy >= height)
+						continue;
+					size_t pi = (size_t)gy * width + gx;
+					float rgb[3];
+					red[p].finish(cfg.background_color, rgb);
+					image_f[pi * 3 + 0] = rgb[0], image_f[pi * 3 + 1] = rgb[1];
+					image_f[pi * 3 + 2] = rgb[2];
+					// imageStore to rgba8 unorm: round to nearest
+					u32 r8 = f2u(rgb[0] * 255.0f + 0.5f), g8 = f2u(rgb[1] * 255.0f + 0.5f);
+					u32 b8 = f2u(rgb[2] * 255.0f + 0.5f);
+					image[pi] = r8 | (g8 << 8) | (b8 << 16) | 0xff000000u;
+					frag_counts[pi] = px_frags[p];
+
+					// exact per-pixel sort (near to far = descending inverse depth), stable
+					std::stable_sort(exact[p].begin(), exact[p].end(),
+									 [](const std::pair<float, u32> &a,
+										const std::pair<float, u32> &b) { return a.first > b.first; });
+					Reducer ex;
+					ex.init(additive);
+					for(auto &s : exact[p])
+						if(s.second != 0)
+							ex.blend(s.second);
+					float ergb[3];
+					ex.finish(cfg.background_color, ergb);
+					exact_image[pi] = f2u(ergb[0] * 255.0f + 0.5f) |
+									  (f2u(ergb[1] * 255.0f + 0.5f) << 8) |
+									  (f2u(ergb[2] * 255.0f + 0.5f) << 16) | 0xff000000u;
+				}
+			}
+		}
+	}
+	bin_level[bin_id] = high ? LUCID_BIN_LEVEL_HIGH : LUCID_BIN_LEVEL_LOW;
+}
+
+void Oracle::raster() {
+	size_t npix = (size_t)width * height;
+	// the reference never writes empty bins; the application's clear provides their colour
+	// (src/lucid_app.cpp:606-619): exact u8 background
+	const LucidVec4 &bg = cfg.background_color;
+	u32 bg8 = f2u(saturate(bg.x) * 255.0f + 0.5f) | (f2u(saturate(bg.y) * 255.0f + 0.5f) << 8) |
+			  (f2u(saturate(bg.z) * 255.0f + 0.5f) << 16) | 0xff000000u;
+	image.assign(npix, bg8);
+	exact_image.assign(npix, bg8);
+	image_f.resize(npix * 3);
+	for(size_t i = 0; i < npix; i++)
+		image_f[i * 3 + 0] = saturate(bg.x), image_f[i * 3 + 1] = saturate(bg.y),
+					   image_f[i * 3 + 2] = saturate(bg.z);
+	frag_counts.assign(npix, 0);
+	bin_level.assign(bin_count, 0);
+
+	int *low = cnt(LUCID_CNT_LOW_BINS), *high = cnt(LUCID_CNT_HIGH_BINS);
+	int n_low = info.bin_level_counts[LUCID_BIN_LEVEL_LOW];
+	int n_high = info.bin_level_counts[LUCID_BIN_LEVEL_HIGH];
+	std::vector<uint8_t> promoted(n_low, 0);
+	u32 s0 = 0, s1 = 0, s2 = 0;
+
+#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads) reduction(+ : s0, s1, s2)
+	for(int i = 0; i < n_low; i++) {
+		u32 st[4] = {0, 0, 0, 0};
+		bool promote;
+		rasterBin(low[i], false, promote, st);
+		promoted[i] = promote;
+		s0 += st[0], s1 += st[1], s2 += st[2];
+	}
+	// promoted bins are appended to the HIGH list in ascending bin order (raster_low.glsl:230-237)
+	for(int i = 0; i < n_low; i++)
+		if(promoted[i])
+			high[n_high++] = low[i];
+	info.bin_level_counts[LUCID_BIN_LEVEL_HIGH] = n_high;
+
+#pragma omp parallel for schedule(dynamic, 1) num_threads(num_threads) reduction(+ : s0, s1, s2)
+	for(int i = 0; i < n_high; i++) {
+		u32 st[4] = {0, 0, 0, 0};
+		bool promote;
+		rasterBin(high[i], true, promote, st);
+		s0 += st[0], s1 += st[1], s2 += st[2];
+	}
+	info.stats[0] = s0, info.stats[1] = s1, info.stats[2] = s2;
+}
+
+double nowMs() {
+	using namespace std::chrono;
+	return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+void Oracle::run() {
+	double t0 = nowMs();
+	setup();
+	double t1 = nowMs();
+	binning();
+	double t2 = nowMs();
+	raster();
+	double t3 = nowMs();
+	stage_ms[0] = t1 - t0, stage_ms[1] = t2 - t1, stage_ms[2] = t3 - t2, stage_ms[3] = t3 - t0;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C interface for ctypes (tests/, bench.py cpu_baseline)
+
+extern "C" {
+
+void *oracle_create(int width, int height, uint32_t opts, int max_visible_quads) {
+	Oracle *o = new Oracle();
+	o->width = width, o->height = height, o->opts = opts;
+	o->bin_count_x = (width + LUCID_BIN_SIZE - 1) / LUCID_BIN_SIZE;
+	o->bin_count_y = (height + LUCID_BIN_SIZE - 1) / LUCID_BIN_SIZE;
+	o->bin_count = o->bin_count_x * o->bin_count_y;
+	o->max_visible_quads = max_visible_quads;
+	o->row_begin = 0, o->row_end = o->bin_count_y;
+	return o;
+}
+void oracle_destroy(void *h) { delete(Oracle *)h; }
+void oracle_set_threads(void *h, int n) { ((Oracle *)h)->num_threads = n < 1 ? 1 : n; }
+void oracle_set_bin_rows(void *h, int begin, int end) {
+	Oracle *o = (Oracle *)h;
+	o->row_begin = std::max(0, begin), o->row_end = std::min(o->bin_count_y, end);
+}
+void oracle_set_geometry(void *h, const float *positions, int num_verts, const uint32_t *colors,
+						 const float *uvs, const uint32_t *normals, const uint32_t *quad_indices,
+						 int num_quads) {
+	Oracle *o = (Oracle *)h;
+	o->positions = positions, o->num_verts = num_verts, o->colors = colors, o->uvs = uvs;
+	o->normals = normals, o->indices = quad_indices, o->num_quads = num_quads;
+}
+// mip chain: tightly packed RGBA8 levels, level l has max(1, w>>l) x max(1, h>>l) texels
+void oracle_set_texture(void *h, int slot, const uint8_t *data, int w, int hgt, int levels) {
+	Oracle *o = (Oracle *)h;
+	Texture &t = o->tex[slot];
+	t.mips.clear(), t.w.clear(), t.h.clear();
+	size_t off = 0;
+	for(int l = 0; l < levels; l++) {
+		int lw = std::max(1, w >> l), lh = std::max(1, hgt >> l);
+		t.mips.emplace_back(data + off, data + off + (size_t)lw * lh * 4);
+		t.w.push_back(lw), t.h.push_back(lh);
+		off += (size_t)lw * lh * 4;
+	}
+}
+// stages: bit 0 setup, bit 1 binning, bit 2 raster
+int oracle_render(void *h, const LucidConfig *cfg, const LucidInstanceData *instances,
+				  const uint32_t *inst_colors, const float *inst_uv_rects, int num_instances,
+				  int stages) {
+	Oracle *o = (Oracle *)h;
+	o->cfg = *cfg;
+	o->instances.assign(instances, instances + num_instances);
+	o->inst_colors.assign(inst_colors, inst_colors + num_instances);
+	o->inst_uv_rects.resize(num_instances);
+	for(int i = 0; i < num_instances; i++)
+		o->inst_uv_rects[i] = inst_uv_rects ? V4{inst_uv_rects[i * 4], inst_uv_rects[i * 4 + 1],
+												 inst_uv_rects[i * 4 + 2], inst_uv_rects[i * 4 + 3]} :
+											  V4{0, 0, 1, 1};
+	double t0 = nowMs();
+	if(stages & 1)
+		o->setup();
+	double t1 = nowMs();
+	if(stages & 2)
+		o->binning();
+	double t2 = nowMs();
+	if(stages & 4)
+		o->raster();
+	double t3 = nowMs();
+	o->stage_ms[0] = t1 - t0, o->stage_ms[1] = t2 - t1, o->stage_ms[2] = t3 - t2;
+	o->stage_ms[3] = t3 - t0;
+	return 0;
+}
+void oracle_stage_ms(void *h, double *dst) { memcpy(dst, ((Oracle *)h)->stage_ms, 4 * sizeof(double)); }
+int oracle_bin_count(void *h) { return ((Oracle *)h)->bin_count; }
+// LucidInfo followed by 10 * bin_count ints
+void oracle_read_info(void *h, uint32_t *dst) {
+	Oracle *o = (Oracle *)h;
+	memcpy(dst, &o->info, sizeof(LucidInfo));
+	memcpy(dst + LUCID_INFO_U32_SIZE, o->counts.data(), o->counts.size() * 4);
+}
+// which: 0 small (slot i), 1 large (slot MVQ-1-i)
+void oracle_read_quad_aabbs(void *h, int which, uint32_t *dst) {
+	Oracle *o = (Oracle *)h;
+	memcpy(dst, o->quad_aabbs[which].data(), o->quad_aabbs[which].size() * 4);
+}
+void oracle_read_quad_input_ids(void *h, int which, uint32_t *dst) {
+	Oracle *o = (Oracle *)h;
+	memcpy(dst, o->quad_input_id[which].data(), o->quad_input_id[which].size() * 4);
+}
+// 21 words per tri: bary0 bary1 scan0 scan1 depth normal; 2 tris per visible quad
+void oracle_read_tri_records(void *h, int which, uint32_t *dst) {
+	Oracle *o = (Oracle *)h;
+	for(size_t i = 0; i < o->tris[which].size(); i++) {
+		const TriRecord &t = o->tris[which][i];
+		memcpy(dst + i * 21 + 0, &t.bary0, 16);
+		memcpy(dst + i * 21 + 4, &t.bary1, 16);
+		memcpy(dst + i * 21 + 8, &t.scan0, 16);
+		memcpy(dst + i * 21 + 12, &t.scan1, 16);
+		memcpy(dst + i * 21 + 16, &t.depth, 16);
+		dst[i * 21 + 20] = t.normal;
+	}
+}
+// 16 words per quad: colors normals uv0 uv1
+void oracle_read_quad_attrs(void *h, int which, uint32_t *dst) {
+	Oracle *o = (Oracle *)h;
+	memcpy(dst, o->qattrs[which].data(), o->qattrs[which].size() * sizeof(QuadAttrs));
+}
+void oracle_read_bin_lists(void *h, uint32_t *bin_quads, uint32_t *bin_tris) {
+	Oracle *o = (Oracle *)h;
+	memcpy(bin_quads, o->bin_quads.data(), o->bin_quads.size() * 4);
+	memcpy(bin_tris, o->bin_tris.data(), o->bin_tris.size() * 4);
+}
+void oracle_read_image(void *h, uint32_t *rgba8) {
+	Oracle *o = (Oracle *)h;
+	memcpy(rgba8, o->image.data(), o->image.size() * 4);
+}
+void oracle_read_exact_image(void *h, uint32_t *rgba8) {
+	Oracle *o = (Oracle *)h;
+	memcpy(rgba8, o->exact_image.data(), o->exact_image.size() * 4);
+}
+void oracle_read_image_float(void *h, float *rgb) {
+	Oracle *o = (Oracle *)h;
+	memcpy(rgb, o->image_f.data(), o->image_f.size() * 4);
+}
+void oracle_read_frag_counts(void *h, uint32_t *dst) {
+	Oracle *o = (Oracle *)h;
+	memcpy(dst, o->frag_counts.data(), o->frag_counts.size() * 4);
+}
+void oracle_read_bin_levels(void *h, uint8_t *dst) {
+	Oracle *o = (Oracle *)h;
+	memcpy(dst, o->bin_level.data(), o->bin_level.size());
+}
+float oracle_pow(float x, float y) { return orc_pow(x, y); }
+float oracle_log2(float x) { return orc_log2(x); }
+uint32_t oracle_shade_probe(void *h, int px, int py, uint32_t tri_idx, float *depth) {
+	return ((Oracle *)h)->shadeSample(px, py, tri_idx, *depth);
+}
+}
