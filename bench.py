@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- exact-OIT frames/s of the B200 rasteriser on BASELINE.json's synthetic configs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config I] [--impl ours|reference]
+
+A "step" is one frame: quad setup -> binning -> raster low/high -> image, for one view of the
+workload scene.  At N=1 the workload is BASELINE.json configs[1] (1M-triangle meshlet scene,
+1920x1080).  With N>1 every rank renders its own view of an orbit around the same scene per step
+(views sharded per GPU, no data-path collective: "scaling": "weak"); `--mode split` instead splits
+the bin rows of ONE frame over the ranks and stores every strip straight into rank 0's image over
+NVLink (strong scaling, reported for config 3 in DESIGN.md).
+
+`value` is frames/s with geometry resident in HBM (per-frame config + instance upload included);
+`e2e` is the same frame through lucid_render() with host buffers in and the RGBA8 image plus
+LucidInfo copied back to the host inside the timed region.  `--impl reference` times the CPU
+restatement of the reference shaders (oracle/) with all host threads: the reference's own Vulkan
+path cannot run on this image (no ICD, no shaderc).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    0: "config0: 100k-triangle quad soup, 50% alpha=0.5, 1280x720",
+    1: "config1: 1M-triangle meshlet scene (489 patches of 32x32 quads), mixed opaque/transparent, 1920x1080",
+    2: "config2: hairball-like dense overlap, 5M triangles, 3840x2160",
+    3: "config3: 10M-triangle architecture scene, textured atlas shading, 3840x2160",
+    4: "config4: 64-view orbit of the 1M-triangle scene, 1920x1080",
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(config: int, scale: float):
+    from lucid_b200 import scenes
+    return scenes.get_config(config, scale)
+
+
+def view_camera(scene, view: int, num_views: int = 64):
+    cam = dict(scene["camera"])
+    if cam["kind"] == "orbit" and view:
+        cam["rot_h"] = cam["rot_h"] + 2.0 * np.pi * view / num_views
+    return cam
+
+
+def algorithmic_bytes(stats: dict, scene, width, height):
+    """SURVEY.md 8(d) byte formulas with this implementation's record sizes."""
+    n_in = stats["input_quads"]
+    n_vis = stats["visible_small"] + stats["visible_large"]
+    n_bq, n_bt = stats["bin_quads"], stats["bin_tris"]
+    t_bin = 2 * n_bq + n_bt
+    attr = (16 if scene.get("colors") is not None else 0) + (16 if scene.get("normals") is not None else 0) + \
+           (32 if scene.get("uvs") is not None else 0)
+    n_px = (stats["low_bins"] + stats["high_bins"]) * 1024
+    setup = 64 * n_in + (4 + 2 * 96 + attr) * n_vis
+    count = 4 * n_vis + 32 * 2 * stats["visible_large"]
+    dispatch = count + 4 * (n_bq + n_bt) * 2  # scatter + the canonicalising sort's read/write
+    raster = 4 * (n_bq + n_bt) + (96 + attr / 2) * t_bin + 4 * n_px
+    return {"setup": setup, "bin_count": count, "bin_dispatch": dispatch, "raster": raster}
+
+
+def run_ours(args):
+    import torch
+    from lucid_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene = make_scene(args.config, args.scale)
+    width, height = scene["width"], scene["height"]
+    stream = torch.cuda.current_stream()
+    split = args.mode == "split" and world > 1
+    nby = (height + 31) // 32
+    rows = None
+    if split:
+        bounds = [round(i * nby / world) for i in range(world + 1)]
+        rows = (bounds[rank], bounds[rank + 1])
+    r = api.LucidRenderer(width, height, 0, args.mvq, device=local_rank, stream=stream.cuda_stream, bin_rows=rows)
+    r.set_scene(scene)
+    inst, cols, rects = api.build_instances(scene["draw_calls"], scene["materials"])
+
+    def config_for(step):
+        view = 0 if split else (step * world + rank) % 64
+        cam = api.make_camera(view_camera(scene, view), width, height)
+        return api.make_config(cam, len(inst), scene["background"])
+
+    # composite target for the bin-row split: every rank stores into rank 0's image over NVLink
+    peer_ptr = None
+    if split:
+        handle = [r.ipc_export_image() if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            peer_ptr = r.ipc_open_image(handle[0])
+
+    def render(step, **kw):
+        if peer_ptr is not None:
+            r.render(config_for(step), inst, cols, rects, out_device_ptr=peer_ptr, out_pitch=width * 4, **kw)
+        else:
+            r.render(config_for(step), inst, cols, rects, **kw)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        render(w, flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stage_acc = np.zeros(8, np.float64)
+    t_wall = time.time()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (untimed)
+        starts[k].record(stream)
+        render(args.warmup + k, flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
+        stops[k].record(stream)
+        if args.stage_times:
+            stage_acc += r.stage_times()
+    barrier()
+    wall = time.time() - t_wall
+    clocks = sampler.stop()
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)], np.float64)
+    total_ms = torch.tensor([float(step_ms.sum())], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+
+    # end to end through the C ABI: host instance arrays in, RGBA8 image + LucidInfo back to host
+    host_img = np.zeros((height, width), np.uint32)
+    e2e_steps = max(3, min(args.steps, 10))
+    for w in range(2):
+        render(w) if split and rank != 0 else r.render(config_for(w), inst, cols, rects, out=host_img)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        if split and rank != 0:
+            render(k)
+        else:
+            r.render(config_for(k), inst, cols, rects, out=host_img)
+        if split:
+            barrier()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    # counters of one frame for the roofline arithmetic
+    r.render(config_for(0), inst, cols, rects)
+    info = r.read_info()
+    stats = api.decode_stats(info, r.bin_count, width, height)
+    stage = r.stage_times().astype(np.float64)
+    if args.stage_times and args.steps:
+        stage = stage_acc / args.steps
+
+    frames_per_step = 1 if split else world
+    tris_per_frame = 2 * stats["input_quads"]
+    ms_per_step = total_ms / args.steps
+    value = frames_per_step * 1000.0 / ms_per_step
+    e2e_value = frames_per_step * e2e_steps / e2e_s
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ab = algorithmic_bytes(stats, scene, width, height)
+        stage_names = ["setup", "bin_count", "bin_scan", "bin_dispatch", "raster_low", "raster_high", "finish"]
+        stage_ms = {n: round(float(stage[i]), 4) for i, n in enumerate(stage_names)}
+        raster_ms = float(stage[4] + stage[5])
+        fracs = {
+            "setup": ab["setup"] / (stage[0] * 1e-3) / 1e9 / peak if stage[0] > 0 else None,
+            "bin_count": ab["bin_count"] / (stage[1] * 1e-3) / 1e9 / peak if stage[1] > 0 else None,
+            "bin_dispatch": ab["bin_dispatch"] / (stage[3] * 1e-3) / 1e9 / peak if stage[3] > 0 else None,
+            "raster": ab["raster"] / (raster_ms * 1e-3) / 1e9 / peak if raster_ms > 0 else None,
+        }
+        dominant = "raster" if raster_ms >= max(stage[0], stage[1], stage[3]) else \
+            max(("setup", stage[0]), ("bin_count", stage[1]), ("bin_dispatch", stage[3]), key=lambda t: t[1])[0]
+        dom_ms = {"raster": raster_ms, "setup": stage[0], "bin_count": stage[1], "bin_dispatch": stage[3]}[dominant]
+        achieved = ab[dominant] / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"config{args.config}", {}).get(dominant)
+        line = {
+            "metric": "exact_oit_frames_per_sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "strong" if split else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "resolution": [width, height],
+                       "input_triangles": tris_per_frame, "scale": args.scale,
+                       "parallelism": ("bin-row split x%d, P2P composite" % world) if split else
+                       ("views sharded x%d" % world if world > 1 else "single GPU"),
+                       "l2": "256 MiB device memset between timed frames (untimed)"},
+            "mtris_per_sec": round(value * tris_per_frame / 1e6, 2),
+            "stage_ms": stage_ms,
+            "counters": {k: stats[k] for k in ("visible_small", "visible_large", "bin_quads", "bin_tris", "low_bins",
+                                               "high_bins", "promoted_bins", "fragments", "half_block_tris")},
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 2), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes": int(ab[dominant]),
+                         "per_stage_frac": {k: (round(v, 4) if v is not None else None) for k, v in fracs.items()}},
+            "e2e": {"value": round(e2e_value, 3), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(len(inst) * 36 + 352),
+                    "d2h_bytes_per_step": int(width * height * 4 + info.size * 4)},
+            "gpu_launches": int(10 * args.steps),
+            "clocks": clocks,
+            "wall_s": round(wall, 3),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(scene, args)
+        print(json.dumps(line), flush=True)
+    if peer_ptr is not None:
+        r.ipc_close_image(peer_ptr)
+    r.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(scene, args, frames: int = 1):
+    """The oracle (CPU restatement of the reference shaders) timed on the host cores."""
+    from lucid_b200 import api
+    from oracle.binding import Oracle
+    threads = os.cpu_count() or 1
+    o = Oracle(scene["width"], scene["height"], 0, args.mvq or 4793490, threads=threads)
+    o.set_scene(scene)
+    cfg, inst, cols, rects = api.prepare_frame(scene)
+    times = []
+    for _ in range(frames):
+        t0 = time.perf_counter()
+        o.render(cfg, inst, cols, rects)
+        times.append(time.perf_counter() - t0)
+    o.close()
+    return {"value": round(1.0 / float(np.mean(times)), 4), "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{frames} full frame(s) of the same workload and camera",
+            "note": "CPU restatement of the reference shaders (OpenMP); Vulkan/lavapipe unavailable on this image"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from lucid_b200 import api
+    from oracle.binding import Oracle
+    scene = make_scene(args.config, args.scale)
+    threads = os.cpu_count() or 1
+    o = Oracle(scene["width"], scene["height"], 0, args.mvq or 4793490, threads=threads)
+    o.set_scene(scene)
+    inst, cols, rects = api.build_instances(scene["draw_calls"], scene["materials"])
+
+    def frame(step):
+        cam = api.make_camera(view_camera(scene, step % 64), scene["width"], scene["height"])
+        cfg = api.make_config(cam, len(inst), scene["background"])
+        o.render(cfg, inst, cols, rects)
+
+    for w in range(args.warmup):
+        frame(w)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        frame(args.warmup + k)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    stats = api.decode_stats(o.info, o.bin_count, o.width, o.height)
+    line = {
+        "impl": "reference", "metric": "exact_oit_frames_per_sec", "value": round(value, 4), "unit": "frames/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1000.0 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.config], "resolution": [scene["width"], scene["height"]],
+                   "input_triangles": 2 * stats["input_quads"], "scale": args.scale},
+        "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "every step is one full frame of the workload (one orbit view per step)"},
+        "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--mode", default="views", choices=["views", "split"])
+    ap.add_argument("--mvq", type=int, default=0)
+    ap.add_argument("--stage-times", action="store_true", help="average per-stage ms over the timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""Host-side logic of the multi-GPU modes: bin-row partitioning of one frame with
+replicated geometry, strip composite, and per-view sharding of multi-view batches.
+
+One process per GPU (torch.distributed).  The fast composite needs no collective at all: rank 0
+exports its image with CUDA IPC and every other rank's raster kernels store their strip straight
+into it over NVLink (LucidRenderer.render(out_device_ptr=...)).  composite_gather() is the portable
+path (NCCL on GPUs, gloo in the CPU tests): strips are disjoint, so it is a plain gather.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BIN_SIZE = 32
+
+
+def split_bin_rows(bin_count_y: int, world_size: int, weights=None) -> list[tuple[int, int]]:
+    """Contiguous bin-row ranges [begin, end) per rank.  With weights (e.g. last frame's fragments
+    per bin row) the boundaries equalise the summed weight; every rank gets at least one row when
+    bin_count_y >= world_size."""
+    if world_size <= 0:
+        raise ValueError("world_size")
+    if weights is None:
+        bounds = [round(i * bin_count_y / world_size) for i in range(world_size + 1)]
+    else:
+        w = np.asarray(weights, np.float64)
+        if w.shape != (bin_count_y,):
+            raise ValueError("weights must have one entry per bin row")
+        c = np.concatenate([[0.0], np.cumsum(w + 1e-9)])
+        targets = c[-1] * np.arange(1, world_size) / world_size
+        inner = np.searchsorted(c, targets, side="left")
+        bounds = [0] + [int(b) for b in inner] + [bin_count_y]
+    # monotone, non-empty where possible
+    for i in range(1, world_size):
+        lo = bounds[i - 1] + (1 if bin_count_y >= world_size else 0)
+        hi = bin_count_y - ((world_size - i) if bin_count_y >= world_size else 0)
+        bounds[i] = min(max(bounds[i], lo), hi)
+    return [(bounds[i], bounds[i + 1]) for i in range(world_size)]
+
+
+def strip_pixel_rows(rows: tuple[int, int], height: int) -> tuple[int, int]:
+    return min(rows[0] * BIN_SIZE, height), min(rows[1] * BIN_SIZE, height)
+
+
+def views_for_rank(num_views: int, rank: int, world_size: int) -> list[int]:
+    """Multi-view batches shard per view (north star): view v goes to rank v % world_size."""
+    return list(range(rank, num_views, world_size))
+
+
+def composite_gather(dist, strip, rows, all_rows, height, width, dst: int = 0):
+    """Gathers disjoint image strips on rank dst.  strip: torch int32 tensor [strip_h, width] holding
+    this rank's pixel rows; returns the full [height, width] tensor on dst (None elsewhere)."""
+    import torch
+
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    max_h = max(strip_pixel_rows(r, height)[1] - strip_pixel_rows(r, height)[0] for r in all_rows)
+    padded = torch.zeros((max_h, width), dtype=strip.dtype, device=strip.device)
+    padded[: strip.shape[0]] = strip
+    if rank == dst:
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.gather(padded, parts, dst=dst)
+        full = torch.empty((height, width), dtype=strip.dtype, device=strip.device)
+        for r, part in zip(all_rows, parts):
+            y0, y1 = strip_pixel_rows(r, height)
+            full[y0:y1] = part[: y1 - y0]
+        return full
+    dist.gather(padded, None, dst=dst)
+    return None
+
+
+def reduce_info(dist, info):
+    """LucidInfo counters of the bin-row split: statistics sum over ranks, per-bin arrays are
+    disjoint (owned rows only) so they also sum."""
+    import torch
+
+    t = torch.as_tensor(np.asarray(info).astype(np.int64))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.numpy()
