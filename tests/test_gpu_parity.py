@@ -106,7 +106,14 @@ def test_deterministic_and_idempotent(small):
         info1 = r.read_info()
         bq1, _ = r.read_bin_lists(bq0.size, 0)
         assert np.array_equal(img0, img1)
-        assert np.array_equal(info0[:64], info1[:64]) and np.array_equal(info0[1152:], info1[1152:])
+        assert np.array_equal(info0[:64], info1[:64])
+        # the six per-bin counter arrays are cleared every frame; the level lists are only
+        # overwritten up to their counts (lucid_renderer.cpp:437)
+        _, c0 = api.split_info(info0, r.bin_count)
+        _, c1 = api.split_info(info1, r.bin_count)
+        assert np.array_equal(c0[:6], c1[:6])
+        n_low, n_high = int(info0[7]), int(info0[9])
+        assert np.array_equal(c0[7][:n_low], c1[7][:n_low]) and np.array_equal(c0[9][:n_high], c1[9][:n_high])
         assert np.array_equal(bq0, bq1)
     finally:
         r.close()
@@ -193,7 +200,9 @@ def test_bin_row_split_matches_full_frame(small):
             part.render(cfg, inst, cols, rects, out_device_ptr=ptr, out_pitch=pitch)
             frags += part.getStats()["fragments"]
             o = pu.run_oracle(sc, bin_rows=rows)
-            assert np.array_equal(part.read_info()[:64], o.info[:64])
+            pi = part.read_info()
+            for lo, hi in ((0, 10), (32, 36), (60, 63)):  # counts, rejections, statistics
+                assert np.array_equal(pi[lo:hi], o.info[lo:hi])
             part.close()
         assert np.array_equal(target.read_image(), full_img)
     finally:
