@@ -5,8 +5,9 @@
 // so the dispatcher can replay "its own" quads; here counting is a warp-aggregated atomic
 // histogram straight into the per-bin counters (large triangles add +1/-1 to a per-row
 // difference array that the scan kernel integrates), one CTA turns the counters into offsets and
-// the LOW/HIGH bin lists, dispatch claims list positions with warp-aggregated atomics, and a
-// final pass sorts every bin's list so the result is independent of atomic ordering.
+// the LOW/HIGH bin lists, and dispatch claims list positions with warp-aggregated atomics.
+// The order inside a bin's list is therefore arbitrary (as in the reference); the raster stage
+// breaks depth-key ties by triangle index, so the image does not depend on it.
 #include "common.cuh"
 
 namespace lucid {
@@ -341,109 +342,6 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 	}
 }
 
-// ------------------------------------------------------------------------------------------------
-// canonical list order: every bin's quad list and tri list sorted ascending by index.
-// The reference leaves the order to atomic arrival; it only matters for depth-key ties in the
-// raster stage, and sorting makes every frame reproducible.
-
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_TILE = 4096;
-
-__device__ __forceinline__ u32 sortKey(u32 w) { return w & 0x0fffffffu; }
-
-// bitonic network in the "flip / disperse" form: every compare-exchange puts the smaller key at
-// the lower index, so a virtual tail of +inf padding never has to be touched.
-__device__ void sortTileShared(u32 *s, int n) {
-	int padded = 32;
-	while(padded < n)
-		padded <<= 1;
-	for(int k = 2; k <= padded; k <<= 1) {
-		for(int i = threadIdx.x; i < padded / 2; i += SORT_THREADS) {
-			int lo = (i / (k / 2)) * k + (i % (k / 2));
-			int hi = lo ^ (k - 1);
-			if(hi < n) {
-				u32 a = s[lo], b = s[hi];
-				if(sortKey(a) > sortKey(b))
-					s[lo] = b, s[hi] = a;
-			}
-		}
-		__syncthreads();
-		for(int j = k / 4; j >= 1; j >>= 1) {
-			for(int i = threadIdx.x; i < padded / 2; i += SORT_THREADS) {
-				int lo = (i / j) * (2 * j) + (i % j);
-				int hi = lo + j;
-				if(hi < n) {
-					u32 a = s[lo], b = s[hi];
-					if(sortKey(a) > sortKey(b))
-						s[lo] = b, s[hi] = a;
-				}
-			}
-			__syncthreads();
-		}
-	}
-}
-
-// large segments: the same network run on global memory by one CTA (rare: only bins with more
-// than SORT_TILE entries in one list)
-__device__ void sortSegmentGlobal(u32 *g, int n) {
-	int padded = 32;
-	while(padded < n)
-		padded <<= 1;
-	for(int k = 2; k <= padded; k <<= 1) {
-		for(int i = threadIdx.x; i < padded / 2; i += SORT_THREADS) {
-			int lo = (i / (k / 2)) * k + (i % (k / 2));
-			int hi = lo ^ (k - 1);
-			if(hi < n) {
-				u32 a = g[lo], b = g[hi];
-				if(sortKey(a) > sortKey(b))
-					g[lo] = b, g[hi] = a;
-			}
-		}
-		__syncthreads();
-		for(int j = k / 4; j >= 1; j >>= 1) {
-			for(int i = threadIdx.x; i < padded / 2; i += SORT_THREADS) {
-				int lo = (i / j) * (2 * j) + (i % j);
-				int hi = lo + j;
-				if(hi < n) {
-					u32 a = g[lo], b = g[hi];
-					if(sortKey(a) > sortKey(b))
-						g[lo] = b, g[hi] = a;
-				}
-			}
-			__syncthreads();
-		}
-	}
-}
-
-__device__ void sortSegment(u32 *seg, int n, u32 *s_tile) {
-	if(n <= 1)
-		return;
-	if(n <= SORT_TILE) {
-		for(int i = threadIdx.x; i < n; i += SORT_THREADS)
-			s_tile[i] = seg[i];
-		__syncthreads();
-		sortTileShared(s_tile, n);
-		for(int i = threadIdx.x; i < n; i += SORT_THREADS)
-			seg[i] = s_tile[i];
-		__syncthreads();
-	} else {
-		__syncthreads();
-		sortSegmentGlobal(seg, n);
-	}
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) k_bin_sort(const Params p) {
-	__shared__ u32 s_tile[SORT_TILE];
-	if(p.info->temp[1] != 0)
-		return;
-	const int *qc = cnt(p, LUCID_CNT_QUAD_COUNTS), *qo = cnt(p, LUCID_CNT_QUAD_OFFSETS);
-	const int *tc = cnt(p, LUCID_CNT_TRI_COUNTS), *to = cnt(p, LUCID_CNT_TRI_OFFSETS);
-	for(int b = blockIdx.x; b < p.bin_count; b += gridDim.x) {
-		sortSegment(p.bin_quads + qo[b], qc[b], s_tile);
-		sortSegment(p.bin_tris + to[b], tc[b], s_tile);
-	}
-}
-
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *ev) {
 	int grid = 148 * 4;
 	k_bin_count<<<grid, BIN_THREADS, 0, stream>>>(p);
@@ -453,7 +351,6 @@ void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *ev) {
 	if(ev)
 		cudaEventRecord(ev[1], stream);
 	k_bin_dispatch<<<grid, BIN_THREADS, 0, stream>>>(p);
-	k_bin_sort<<<min(p.bin_count, 148 * 8), SORT_THREADS, 0, stream>>>(p);
 	if(ev)
 		cudaEventRecord(ev[2], stream);
 }

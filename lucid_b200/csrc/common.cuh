@@ -23,7 +23,8 @@ constexpr int BIN_SHIFT = LUCID_BIN_SHIFT;
 //   quad_aabbs[slot]   u32      28-bit bin AABB + 2 cull bits (quad_setup.glsl:241-242)
 //   tri_scan[tri]      2x16 B   scanline record (scan.xyz, ymin|ymax<<16) (step.xyz, sign bits)
 //   tri_shade[tri]     4x16 B   depth plane (xyz, flags|instance<<16), bary edge 0, bary edge 1,
-//                               (flat normal 10-10-10, instance RGBA8, 0, 0)
+//                               (flat normal 10-10-10, instance RGBA8, constant shaded RGBA8,
+//                                1 if the constant is valid)
 //   quad_colors/normals[slot] 16 B, quad_uv[slot] 2x16 B   optional vertex attributes
 // The reference keeps the same fields in uvec4_storage / normals_storage
 // (definitions.glsl:132-137); here the per-sample fields of one triangle share one 64-byte line
@@ -97,8 +98,10 @@ __device__ __forceinline__ float saturatef(float x) { return fminf(fmaxf(x, 0.0f
 __device__ __forceinline__ float rcp(float x) { return __fdiv_rn(1.0f, x); }
 __device__ __forceinline__ float rsqrt_rn(float x) { return __fdiv_rn(1.0f, __fsqrt_rn(x)); }
 
-// log2 / exp2 / pow: polynomial evaluation in plain binary32 operations, identical on host and
-// device (atanh series on [sqrt(1/2), sqrt(2)), degree-6 Taylor for 2^r).
+// log2 / exp2 / pow: polynomial evaluation shared with the CPU checker (atanh series on
+// [sqrt(1/2), sqrt(2)), degree-6 Taylor for 2^r).  The Horner steps are explicit fused
+// multiply-adds (fmaf on the host, FFMA here): single rounding on both sides, so the result is
+// still bit-identical while costing half the instructions of separate mul + add.
 __device__ __forceinline__ float log2_poly(float x) {
 	u32 ix = __float_as_uint(x);
 	int e = (int)(ix - 0x3f3504f3u) >> 23;
@@ -107,23 +110,23 @@ __device__ __forceinline__ float log2_poly(float x) {
 	float s = __fdiv_rn(f, 2.0f + f);
 	float z = s * s;
 	float p = 0.2222222222f;
-	p = p * z + 0.2857142857f;
-	p = p * z + 0.4f;
-	p = p * z + 0.6666666667f;
-	p = p * z + 2.0f;
+	p = __fmaf_rn(p, z, 0.2857142857f);
+	p = __fmaf_rn(p, z, 0.4f);
+	p = __fmaf_rn(p, z, 0.6666666667f);
+	p = __fmaf_rn(p, z, 2.0f);
 	float ln = s * p;
-	return ln * 1.4426950408889634f + (float)e;
+	return __fmaf_rn(ln, 1.4426950408889634f, (float)e);
 }
 __device__ __forceinline__ float exp2_poly(float t) {
 	float n = floorf(t + 0.5f);
 	float r = (t - n) * 0.6931471805599453f;
 	float p = 1.0f / 720.0f;
-	p = p * r + 1.0f / 120.0f;
-	p = p * r + 1.0f / 24.0f;
-	p = p * r + 1.0f / 6.0f;
-	p = p * r + 0.5f;
-	p = p * r + 1.0f;
-	p = p * r + 1.0f;
+	p = __fmaf_rn(p, r, 1.0f / 120.0f);
+	p = __fmaf_rn(p, r, 1.0f / 24.0f);
+	p = __fmaf_rn(p, r, 1.0f / 6.0f);
+	p = __fmaf_rn(p, r, 0.5f);
+	p = __fmaf_rn(p, r, 1.0f);
+	p = __fmaf_rn(p, r, 1.0f);
 	int ni = f2i(n);
 	if(ni < -126)
 		return 0.0f;
@@ -177,6 +180,33 @@ __device__ __forceinline__ float linearToSRGB1(float c) {
 }
 __device__ __forceinline__ float SRGBToLinear1(float c) {
 	return c < 0.04045f ? (1.0f / 12.92f) * c : pow_poly((c + 0.055f) * (1.0f / 1.055f), 2.4f);
+}
+
+// finalShading (funcs.glsl:261-271) + Lambert term of shadeSample (shading.glsl:181-183)
+__device__ __forceinline__ u32 shadeFinal(const LucidLighting &L, float4 color, F3 normal) {
+	F3 msun = mk3(-L.sun_dir.x, -L.sun_dir.y, -L.sun_dir.z);
+	float light_value = fmaxf(0.0f, dot3(msun, normal) * 0.7f + 0.3f);
+	float ambx = L.ambient_color.x * L.ambient_power, amby = L.ambient_color.y * L.ambient_power;
+	float ambz = L.ambient_color.z * L.ambient_power;
+	float difx = L.sun_color.x * L.sun_power * light_value, dify = L.sun_color.y * L.sun_power * light_value;
+	float difz = L.sun_color.z * L.sun_power * light_value;
+	color.x = saturatef(linearToSRGB1(SRGBToLinear1(color.x) * (ambx + difx)));
+	color.y = saturatef(linearToSRGB1(SRGBToLinear1(color.y) * (amby + dify)));
+	color.z = saturatef(linearToSRGB1(SRGBToLinear1(color.z) * (ambz + difz)));
+	return encodeRGBA8(color);
+}
+// A triangle without vertex colours, vertex normals or a texture shades to the same RGBA8 value
+// at every sample (instance colour x flat-normal lighting), so setup evaluates shadeSample's
+// colour once per triangle and the raster loop only computes depth for it.
+constexpr u32 INST_VARYING_MASK =
+	LUCID_INST_HAS_VERTEX_COLORS | LUCID_INST_HAS_VERTEX_NORMALS | LUCID_INST_HAS_ALBEDO_TEXTURE;
+__device__ __forceinline__ u32 shadeConstant(const LucidLighting &L, u32 flags, u32 inst_color, u32 enc_normal) {
+	float4 color = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+	if(flags & LUCID_INST_HAS_COLOR)
+		color = decodeRGBA8(inst_color);
+	if(color.w == 0.0f)
+		return 0;
+	return shadeFinal(L, color, decodeNormalUint(enc_normal));
 }
 
 __device__ __forceinline__ u32 laneId() { return threadIdx.x & 31; }

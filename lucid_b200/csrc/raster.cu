@@ -153,6 +153,8 @@ __device__ u32 shadeSample(const Params &p, const LucidConfig &cfg, int ipx, int
 
 	float inv_ray_pos = dx * px + (dy * py + dz);
 	out_depth = inv_ray_pos;
+	if(misc.w != 0)
+		return misc.z; // attribute-free triangle: colour was evaluated once in quad setup
 	float ray_pos = rcp(inv_ray_pos);
 	float e0 = e0x * px + (e0y * py + e0z);
 	float e1 = e1x * px + (e1y * py + e1z);
@@ -217,18 +219,7 @@ __device__ u32 shadeSample(const Params &p, const LucidConfig &cfg, int ipx, int
 	} else {
 		normal = decodeNormalUint(misc.x);
 	}
-	const LucidLighting &L = cfg.lighting;
-	F3 msun = mk3(-L.sun_dir.x, -L.sun_dir.y, -L.sun_dir.z);
-	float light_value = fmaxf(0.0f, dot3(msun, normal) * 0.7f + 0.3f);
-	// finalShading, funcs.glsl:261-271
-	float ambx = L.ambient_color.x * L.ambient_power, amby = L.ambient_color.y * L.ambient_power;
-	float ambz = L.ambient_color.z * L.ambient_power;
-	float difx = L.sun_color.x * L.sun_power * light_value, dify = L.sun_color.y * L.sun_power * light_value;
-	float difz = L.sun_color.z * L.sun_power * light_value;
-	color.x = saturatef(linearToSRGB1(SRGBToLinear1(color.x) * (ambx + difx)));
-	color.y = saturatef(linearToSRGB1(SRGBToLinear1(color.y) * (amby + dify)));
-	color.z = saturatef(linearToSRGB1(SRGBToLinear1(color.z) * (ambz + difz)));
-	return encodeRGBA8(color);
+	return shadeFinal(cfg.lighting, color, normal);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -303,6 +294,19 @@ __device__ __forceinline__ u32 bitonic32(u32 v) {
 	return v;
 }
 
+// the last five steps of a bitonic merge (partner distance 16..1) stay in registers
+__device__ __forceinline__ u32 bitonicMerge32(u32 v, bool ascending) {
+	const u32 lane = laneId();
+#pragma unroll
+	for(int j = 16; j > 0; j >>= 1) {
+		u32 o = __shfl_xor_sync(0xffffffffu, v, j);
+		bool lower = (lane & j) == 0;
+		v = (lower == ascending) ? min(v, o) : max(v, o);
+	}
+	return v;
+}
+
+// keys[0..n) ascending; the array must have room for n rounded up to a power of two (>= 64)
 __device__ void warpSortShared(u32 *keys, int n) {
 	const int lane = laneId();
 	if(n <= 32) {
@@ -316,29 +320,61 @@ __device__ void warpSortShared(u32 *keys, int n) {
 	int padded = 64;
 	while(padded < n)
 		padded <<= 1;
-	for(int k = 2; k <= padded; k <<= 1) {
-		for(int i = lane; i < padded / 2; i += 32) {
-			int lo = (i / (k / 2)) * k + (i % (k / 2));
-			int hi = lo ^ (k - 1);
-			if(hi < n) {
+	for(int i = n + lane; i < padded; i += 32)
+		keys[i] = 0xffffffffu;
+	__syncwarp();
+	// runs of 32 sorted in registers, alternating direction
+	for(int base = 0; base < padded; base += 32) {
+		u32 v = bitonic32(keys[base + lane]);
+		if(base & 32)
+			v = __shfl_sync(0xffffffffu, v, 31 - lane);
+		keys[base + lane] = v;
+	}
+	__syncwarp();
+	for(int k = 64; k <= padded; k <<= 1) {
+		for(int j = k >> 1; j >= 32; j >>= 1) {
+			for(int i = lane; i < (padded >> 1); i += 32) {
+				int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+				bool ascending = (lo & k) == 0;
 				u32 a = keys[lo], b = keys[hi];
-				if(a > b)
+				if((a > b) == ascending)
 					keys[lo] = b, keys[hi] = a;
 			}
+			__syncwarp();
 		}
+		for(int base = 0; base < padded; base += 32)
+			keys[base + lane] = bitonicMerge32(keys[base + lane], (base & k) == 0);
 		__syncwarp();
-		for(int j = k / 4; j >= 1; j >>= 1) {
-			for(int i = lane; i < padded / 2; i += 32) {
-				int lo = (i / j) * (2 * j) + (i % j);
-				int hi = lo + j;
-				if(hi < n) {
-					u32 a = keys[lo], b = keys[hi];
-					if(a > b)
-						keys[lo] = b, keys[hi] = a;
+	}
+}
+
+// Entries with equal quantised depth are ordered by triangle index.  The low key bits only make
+// keys unique (they are list positions that depend on atomic arrival order); this pass makes the
+// final order -- and therefore the image -- independent of them.  Ties are rare and short.
+template <typename TriOf>
+__device__ void warpFixDepthTies(u32 *keys, int n, int slot_bits, TriOf triOf) {
+	const int lane = laneId();
+	const u32 slot_mask = (1u << slot_bits) - 1u;
+	bool tie = false;
+	for(int i = lane; i + 1 < n; i += 32)
+		tie = tie || (keys[i] >> slot_bits) == (keys[i + 1] >> slot_bits);
+	if(!__any_sync(0xffffffffu, tie))
+		return;
+	while(true) {
+		bool swapped = false;
+#pragma unroll
+		for(int parity = 0; parity < 2; parity++) {
+			for(int i = 2 * lane + parity; i + 1 < n; i += 64) {
+				u32 a = keys[i], b = keys[i + 1];
+				if((a >> slot_bits) == (b >> slot_bits) && triOf(a & slot_mask) > triOf(b & slot_mask)) {
+					keys[i] = b, keys[i + 1] = a;
+					swapped = true;
 				}
 			}
 			__syncwarp();
 		}
+		if(!__any_sync(0xffffffffu, swapped))
+			break;
 	}
 }
 
@@ -500,12 +536,56 @@ __device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const Wa
 	out_frags = total_frags;
 }
 
+// triangle of entry t of the bin's sequence T: quads list (two triangles per quad) then tris list
+__device__ __forceinline__ bool binTriangle(const Params &p, int t, int n_q, int q_off, int t_off, u32 &tri_idx) {
+	if(t < n_q * 2) {
+		u32 w = __ldg(p.bin_quads + q_off + (t >> 1));
+		tri_idx = (w & 0x0fffffffu) * 2 + (t & 1);
+		return ((w >> (30 + (t & 1))) & 1) == 0;
+	}
+	tri_idx = __ldg(p.bin_tris + t_off + (t - n_q * 2));
+	return true;
+}
+
+// scanline state of a triangle at the first pixel row of group `g` of the bin (groups of
+// 8 rows for LOW, 4 for HIGH).  The walk starts at the triangle's first group inside the bin and
+// adds the step row by row, exactly like the reference's incremental loop, so the values -- and
+// the spans truncated from them -- are bit-identical.
+template <int ROWS_PER_GROUP>
+__device__ __forceinline__ bool rowScanAt(const Params &p, u32 tri_idx, int pos_x, int pos_y, int g, RowScan &rs) {
+	constexpr int shift = ROWS_PER_GROUP == 8 ? 3 : 2;
+	const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + tri_idx);
+	uint4 s0 = __ldg(src);
+	int ymin = (int)(s0.w & 0xffff) - pos_y, ymax = (int)(s0.w >> 16) - pos_y;
+	int min_g = min(max(ymin, 0), BIN_SIZE - 1) >> shift, max_g = min(max(ymax, 0), BIN_SIZE - 1) >> shift;
+	if(g < min_g || g > max_g)
+		return false;
+	uint4 s1 = __ldg(src + 1);
+	rs.step[0] = __uint_as_float(s1.x), rs.step[1] = __uint_as_float(s1.y), rs.step[2] = __uint_as_float(s1.z);
+	rs.xneg = s1.w & 7u;
+	float start_x = float(pos_x), start_y = float(pos_y + min_g * ROWS_PER_GROUP);
+	rs.scan[0] = __uint_as_float(s0.x) + (rs.step[0] * start_y - start_x);
+	rs.scan[1] = __uint_as_float(s0.y) + (rs.step[1] * start_y - start_x);
+	rs.scan[2] = __uint_as_float(s0.z) + (rs.step[2] * start_y - start_x);
+	for(int k = (g - min_g) * ROWS_PER_GROUP; k > 0; k--)
+		rs.scan[0] += rs.step[0], rs.scan[1] += rs.step[1], rs.scan[2] += rs.step[2];
+	return true;
+}
+__device__ __forceinline__ bool touchesGroup(const Params &p, u32 tri_idx, int pos_y, int g, int shift) {
+	u32 y_aabb = __ldg(reinterpret_cast<const u32 *>(p.tri_scan + tri_idx) + 3);
+	int ymin = (int)(y_aabb & 0xffff) - pos_y, ymax = (int)(y_aabb >> 16) - pos_y;
+	int min_g = min(max(ymin, 0), BIN_SIZE - 1) >> shift, max_g = min(max(ymax, 0), BIN_SIZE - 1) >> shift;
+	return g >= min_g && g <= max_g;
+}
+
 // LOW: one block row of a bin with fewer than 1024 triangles (raster_low.glsl)
 __device__ void rasterLowItem(const Params &p, const LucidConfig &cfg, int bin_id, int by,
 							  unsigned char *smem) {
-	uint4 *s_rows = reinterpret_cast<uint4 *>(smem);					   // LOW_MAX_TRIS
+	uint4 *s_rows = reinterpret_cast<uint4 *>(smem);					   // LOW_MAX_TRIS, indexed by t
 	u32 *s_tri = reinterpret_cast<u32 *>(smem + LOW_MAX_TRIS * 16);		   // LOW_MAX_TRIS
-	u32 *s_warp = reinterpret_cast<u32 *>(smem + LOW_MAX_TRIS * 20);
+	unsigned short *s_queue = reinterpret_cast<unsigned short *>(smem + LOW_MAX_TRIS * 20); // LOW_MAX_TRIS
+	u32 *s_warp = reinterpret_cast<u32 *>(smem + LOW_MAX_TRIS * 22);
+	__shared__ int s_qcount;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	WarpScratch ws;
 	ws.keys = s_warp + warp * (MAX_BLOCK_TRIS + SAMPLE_BUF + 32);
@@ -517,55 +597,52 @@ __device__ void rasterLowItem(const Params &p, const LucidConfig &cfg, int bin_i
 	const int n_T = n_q * 2 + n_t; // < 1024
 	const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
 	const int pos_x = bin_x * BIN_SIZE, pos_y = bin_y * BIN_SIZE;
+	if(tid == 0)
+		s_qcount = 0;
+	__syncthreads();
 
-	// phase A: spans of every triangle of the bin on this block row (raster_low.glsl:39-79)
-	for(int t = tid; t < n_T; t += RASTER_THREADS) {
-		u32 tri_idx;
-		bool valid = true;
-		if(t < n_q * 2) {
-			u32 w = __ldg(p.bin_quads + q_off + (t >> 1));
-			valid = ((w >> (30 + (t & 1))) & 1) == 0;
-			tri_idx = (w & 0x0fffffffu) * 2 + (t & 1);
-		} else {
-			tri_idx = __ldg(p.bin_tris + t_off + (t - n_q * 2));
-		}
+	// phase A1: which triangles of the bin reach this block row (y range only)
+	for(int t0 = 0; t0 < n_T; t0 += RASTER_THREADS) {
+		int t = t0 + tid;
+		u32 tri_idx = 0;
+		bool pass = t < n_T && binTriangle(p, t, n_q, q_off, t_off, tri_idx);
+		pass = pass && touchesGroup(p, tri_idx, pos_y, by, 3);
+		if(t < n_T)
+			s_tri[t] = tri_idx;
+		u32 m = __ballot_sync(0xffffffffu, pass);
+		int base = 0;
+		if(lane == 0 && m)
+			base = atomicAdd(&s_qcount, __popc(m));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if(pass)
+			s_queue[base + __popc(m & laneMaskLt())] = (unsigned short)t;
+	}
+	__syncthreads();
+	// phase A2: spans of the queued triangles, all lanes busy (raster_low.glsl:39-64)
+	const int n_queue = s_qcount;
+	for(int q = tid; q < n_queue; q += RASTER_THREADS) {
+		int t = s_queue[q];
+		RowScan rs;
 		uint4 rec = make_uint4(0, 0, 0, 0);
-		if(valid) {
-			const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + tri_idx);
-			uint4 s0 = __ldg(src);
-			int ymin = (int)(s0.w & 0xffff) - pos_y, ymax = (int)(s0.w >> 16) - pos_y;
-			int min_by = min(max(ymin, 0), BIN_SIZE - 1) >> 3, max_by = min(max(ymax, 0), BIN_SIZE - 1) >> 3;
-			if(by >= min_by && by <= max_by) {
-				uint4 s1 = __ldg(src + 1);
-				RowScan rs;
-				rs.step[0] = __uint_as_float(s1.x), rs.step[1] = __uint_as_float(s1.y);
-				rs.step[2] = __uint_as_float(s1.z);
-				rs.xneg = s1.w & 7u;
-				float start_x = float(pos_x), start_y = float(pos_y + min_by * 8);
-				rs.scan[0] = __uint_as_float(s0.x) + (rs.step[0] * start_y - start_x);
-				rs.scan[1] = __uint_as_float(s0.y) + (rs.step[1] * start_y - start_x);
-				rs.scan[2] = __uint_as_float(s0.z) + (rs.step[2] * start_y - start_x);
-				for(int k = (by - min_by) * 8; k > 0; k--)
-					rs.scan[0] += rs.step[0], rs.scan[1] += rs.step[1], rs.scan[2] += rs.step[2];
-				u32 mn0, mx0, bx0, mn1, mx1, bx1;
-				rasterBinStep(rs, mn0, mx0, bx0);
-				rasterBinStep(rs, mn1, mx1, bx1);
-				u32 bx = bx0 | bx1;
-				if(bx != 0)
-					rec = make_uint4(mn0 | (bx << 24), mn1, mx0, mx1);
-			}
+		if(rowScanAt<8>(p, s_tri[t], pos_x, pos_y, by, rs)) {
+			u32 mn0, mx0, bx0, mn1, mx1, bx1;
+			rasterBinStep(rs, mn0, mx0, bx0);
+			rasterBinStep(rs, mn1, mx1, bx1);
+			u32 bx = bx0 | bx1;
+			if(bx != 0)
+				rec = make_uint4(mn0 | (bx << 24), mn1, mx0, mx1);
 		}
 		s_rows[t] = rec;
-		s_tri[t] = tri_idx;
 	}
 	__syncthreads();
 
 	// phase B: warp = block column (raster_low.glsl:81-194)
 	const int bx = warp;
 	int count = 0;
-	for(int t0 = 0; t0 < n_T; t0 += 32) {
-		int t = t0 + lane;
-		bool has = t < n_T && ((s_rows[t].x >> (24 + bx)) & 1);
+	for(int q0 = 0; q0 < n_queue; q0 += 32) {
+		int q = q0 + lane;
+		int t = q < n_queue ? s_queue[q] : 0;
+		bool has = q < n_queue && ((s_rows[t].x >> (24 + bx)) & 1);
 		u32 m = __ballot_sync(0xffffffffu, has);
 		int pos = count + __popc(m & laneMaskLt());
 		if(has && pos < MAX_BLOCK_TRIS)
@@ -597,8 +674,10 @@ __device__ void rasterLowItem(const Params &p, const LucidConfig &cfg, int bin_i
 		frag_acc += (u32)nf0 | ((u32)nf1 << 16);
 	}
 	__syncwarp();
-	if(count > 3) // blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
+	if(count > 3) { // blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
 		warpSortShared(ws.keys, count);
+		warpFixDepthTies(ws.keys, count, 10, [&](u32 t) { return s_tri[t]; });
+	}
 	__syncwarp();
 
 	auto getRow0 = [&](u32 slot, u32 &mins, u32 &maxs, u32 &tri) {
@@ -686,9 +765,11 @@ template <int CAP>
 __device__ void rasterHighItem(const Params &p, const LucidConfig &cfg, int item, uint4 *scratch,
 							   unsigned char *smem) {
 	constexpr int ROW_CAP = CAP * 4 < MAX_HBLOCK_ROW_TRIS ? CAP * 4 : MAX_HBLOCK_ROW_TRIS;
+	constexpr int QUEUE = RASTER_THREADS * 2;
 	unsigned char *s_bx = smem;									  // ROW_CAP bytes
 	u32 *s_warp = reinterpret_cast<u32 *>(smem + ROW_CAP);
-	__shared__ int s_counts[RASTER_WARPS][2];
+	__shared__ u32 s_queue[QUEUE];
+	__shared__ int s_qtail, s_row_count;
 	__shared__ int s_est[4], s_exact[4], s_status;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	WarpScratch ws;
@@ -705,56 +786,40 @@ __device__ void rasterHighItem(const Params &p, const LucidConfig &cfg, int item
 
 	if(tid < 4)
 		s_est[tid] = 0, s_exact[tid] = 0;
-	if(tid == 0)
+	if(tid == 0) {
 		s_status = (p.bin_flags[bin_id] & 2u) ? 2 : 0;
+		s_qtail = 0, s_row_count = 0;
+	}
 	__syncthreads();
 	if(s_status != 0)
 		return; // another item already found the bin over a limit
 
-	// phase A: spans on this half-block row, appended in list order (raster_high.glsl:54-106)
-	int row_count = 0;
+	// phase A (raster_high.glsl:54-106).  A1 queues the triangles whose y range reaches this
+	// half-block row; A2 evaluates 128 queued triangles at a time with every lane busy and appends
+	// the non-empty ones to the row list.  List order does not matter (see warpFixDepthTies).
 	int est[4] = {0, 0, 0, 0}, exact[4] = {0, 0, 0, 0};
-	for(int t0 = 0; t0 < n_T; t0 += RASTER_THREADS) {
-		int t = t0 + tid;
-		u32 tri_idx = 0;
-		bool valid = t < n_T;
-		if(valid) {
-			if(t < n_q * 2) {
-				u32 w = __ldg(p.bin_quads + q_off + (t >> 1));
-				valid = ((w >> (30 + (t & 1))) & 1) == 0;
-				tri_idx = (w & 0x0fffffffu) * 2 + (t & 1);
-			} else {
-				tri_idx = __ldg(p.bin_tris + t_off + (t - n_q * 2));
-			}
-		}
-		u32 mn = 0, mx = 0, bx = 0;
-		if(valid) {
-			const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + tri_idx);
-			uint4 s0 = __ldg(src);
-			int ymin = (int)(s0.w & 0xffff) - pos_y, ymax = (int)(s0.w >> 16) - pos_y;
-			int min_g = min(max(ymin, 0), BIN_SIZE - 1) >> 2, max_g = min(max(ymax, 0), BIN_SIZE - 1) >> 2;
-			if(rby >= min_g && rby <= max_g) {
-				uint4 s1 = __ldg(src + 1);
-				RowScan rs;
-				rs.step[0] = __uint_as_float(s1.x), rs.step[1] = __uint_as_float(s1.y);
-				rs.step[2] = __uint_as_float(s1.z);
-				rs.xneg = s1.w & 7u;
-				float start_x = float(pos_x), start_y = float(pos_y + min_g * 4);
-				rs.scan[0] = __uint_as_float(s0.x) + (rs.step[0] * start_y - start_x);
-				rs.scan[1] = __uint_as_float(s0.y) + (rs.step[1] * start_y - start_x);
-				rs.scan[2] = __uint_as_float(s0.z) + (rs.step[2] * start_y - start_x);
-				for(int k = (rby - min_g) * 4; k > 0; k--)
-					rs.scan[0] += rs.step[0], rs.scan[1] += rs.step[1], rs.scan[2] += rs.step[2];
+	int qhead = 0;
+	auto evaluate = [&](int qi, bool active) {
+		u32 mn = 0, mx = 0, bx = 0, tri_idx = 0;
+		if(active) {
+			tri_idx = s_queue[qi & (QUEUE - 1)];
+			RowScan rs;
+			if(rowScanAt<4>(p, tri_idx, pos_x, pos_y, rby, rs))
 				rasterBinStep(rs, mn, mx, bx);
-			}
 		}
 		bool has = bx != 0;
 		u32 m = __ballot_sync(0xffffffffu, has);
-		const int buf = (t0 / RASTER_THREADS) & 1;
-		if(lane == 0)
-			s_counts[warp][buf] = __popc(m);
-		// estimated (first..last column, holes included) and exact per-half-block counts
+		int base = 0;
+		if(lane == 0 && m)
+			base = atomicAdd(&s_row_count, __popc(m));
+		base = __shfl_sync(0xffffffffu, base, 0);
 		if(has) {
+			int slot = base + __popc(m & laneMaskLt());
+			if(slot < ROW_CAP) {
+				scratch[slot] = make_uint4(mn, mx, tri_idx, bx);
+				s_bx[slot] = (unsigned char)bx;
+			}
+			// estimated (first..last column, holes included) and exact per-half-block counts
 			int lo = __ffs(bx) - 1, hi = 31 - __clz(bx);
 #pragma unroll
 			for(int c = 0; c < 4; c++) {
@@ -762,23 +827,29 @@ __device__ void rasterHighItem(const Params &p, const LucidConfig &cfg, int item
 				exact[c] += (bx >> c) & 1;
 			}
 		}
+	};
+	for(int t0 = 0; t0 < n_T; t0 += RASTER_THREADS) {
+		int t = t0 + tid;
+		u32 tri_idx = 0;
+		bool pass = t < n_T && binTriangle(p, t, n_q, q_off, t_off, tri_idx);
+		pass = pass && touchesGroup(p, tri_idx, pos_y, rby, 2);
+		u32 m = __ballot_sync(0xffffffffu, pass);
+		int base = 0;
+		if(lane == 0 && m)
+			base = atomicAdd(&s_qtail, __popc(m));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if(pass)
+			s_queue[(base + __popc(m & laneMaskLt())) & (QUEUE - 1)] = tri_idx;
 		__syncthreads();
-		int before = 0, chunk_total = 0;
-#pragma unroll
-		for(int w = 0; w < RASTER_WARPS; w++) {
-			int c = s_counts[w][buf];
-			if(w < warp)
-				before += c;
-			chunk_total += c;
+		if(s_qtail - qhead >= RASTER_THREADS) {
+			evaluate(qhead + tid, true);
+			qhead += RASTER_THREADS;
 		}
-		if(has) {
-			int slot = row_count + before + __popc(m & laneMaskLt());
-			if(slot < ROW_CAP) {
-				scratch[slot] = make_uint4(mn, mx, tri_idx, bx);
-				s_bx[slot] = (unsigned char)bx;
-			}
-		}
-		row_count += chunk_total;
+		__syncthreads();
+	}
+	{
+		int rest = s_qtail - qhead;
+		evaluate(qhead + tid, tid < rest);
 	}
 #pragma unroll
 	for(int c = 0; c < 4; c++) {
@@ -794,6 +865,7 @@ __device__ void rasterHighItem(const Params &p, const LucidConfig &cfg, int item
 		}
 	}
 	__syncthreads();
+	const int row_count = s_row_count;
 	if(tid == 0) {
 		int max_est = max(max(s_est[0], s_est[1]), max(s_est[2], s_est[3]));
 		int max_exact = max(max(s_exact[0], s_exact[1]), max(s_exact[2], s_exact[3]));
@@ -811,21 +883,21 @@ __device__ void rasterHighItem(const Params &p, const LucidConfig &cfg, int item
 	__syncthreads();
 	if(s_status != 0)
 		return;
-	__threadfence_block();
 
 	// phase B: warp = half-block column (raster_high.glsl:146-273)
 	const int hbx = warp;
 	int count = 0;
 	for(int s0 = 0; s0 < row_count; s0 += 32) {
-		int s = s0 + lane;
-		bool has = s < row_count && ((s_bx[s] >> hbx) & 1);
+		int sl = s0 + lane;
+		bool has = sl < row_count && ((s_bx[sl] >> hbx) & 1);
 		u32 m = __ballot_sync(0xffffffffu, has);
 		if(has)
-			ws.keys[count + __popc(m & laneMaskLt())] = (u32)s;
+			ws.keys[count + __popc(m & laneMaskLt())] = (u32)sl;
 		count += __popc(m);
 	}
 	__syncwarp();
 	const int startx = hbx * 8;
+	u32 fsum = 0;
 	for(int i = lane; i < count; i += 32) {
 		u32 slot = ws.keys[i];
 		uint4 rec = scratch[slot];
@@ -836,9 +908,11 @@ __device__ void rasterHighItem(const Params &p, const LucidConfig &cfg, int item
 		float cpy = float(cy) * scale + (float(rby * 4) + float(pos_y));
 		u32 depth = blockDepth(p, rec.z, cpx, cpy, float(0x7fffe));
 		ws.keys[i] = slot | (depth << 14);
+		fsum += (u32)nf;
 	}
 	__syncwarp();
 	warpSortShared(ws.keys, count);
+	warpFixDepthTies(ws.keys, count, 14, [&](u32 slot) { return scratch[slot].z; });
 	__syncwarp();
 	auto getRow = [&](u32 slot, u32 &mins, u32 &maxs, u32 &tri) {
 		uint4 r = scratch[slot];
@@ -846,24 +920,14 @@ __device__ void rasterHighItem(const Params &p, const LucidConfig &cfg, int item
 	};
 	u32 frags;
 	shadeHalfBlock(p, cfg, ws, count, 0x3fff, startx, pos_x + hbx * 8, pos_y + rby * 4, getRow, frags);
-	if(lane == 0) {
-		// exact per-half-block counts (raster_high.glsl:309-310)
-		// note: fragments of the whole list, including segments skipped by the alpha threshold
-		atomicAdd(&p.bin_stats[bin_id * 4 + 3], (u32)count);
-	}
-	// fragment total of the list (independent of early-out)
-	u32 fsum = 0;
-	for(int i = lane; i < count; i += 32) {
-		uint4 rec = scratch[ws.keys[i] & 0x3fff];
-		int nf, cx, cy;
-		halfPixelMask(rec.x, rec.y, startx, nf, cx, cy);
-		fsum += (u32)nf;
-	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1)
 		fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
-	if(lane == 0)
+	if(lane == 0) {
+		// exact per-half-block counts (raster_high.glsl:309-310)
 		atomicAdd(&p.bin_stats[bin_id * 4 + 2], fsum);
+		atomicAdd(&p.bin_stats[bin_id * 4 + 3], (u32)count);
+	}
 }
 
 template <int CAP, bool DEFERRED>
@@ -890,10 +954,6 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_high(const Params p,
 // background for bins no kernel writes, red for bins over the reference's limits, and the
 // statistics (shading.glsl:38-53); LOW results of promoted bins are not counted
 __global__ void __launch_bounds__(256) k_raster_finish(const Params p, u32 background, int fill_empty) {
-	__shared__ u32 s_sum[2];
-	if(threadIdx.x < 2)
-		s_sum[threadIdx.x] = 0;
-	__syncthreads();
 	const int *qc = cntc(p, LUCID_CNT_QUAD_COUNTS), *tc = cntc(p, LUCID_CNT_TRI_COUNTS);
 	u32 frags = 0, hbt = 0;
 	for(int b = blockIdx.x; b < p.bin_count; b += gridDim.x) {
@@ -929,7 +989,7 @@ __global__ void __launch_bounds__(256) k_raster_finish(const Params p, u32 backg
 	}
 }
 
-constexpr int lowSmemBytes() { return LOW_MAX_TRIS * 20 + RASTER_WARPS * (MAX_BLOCK_TRIS + SAMPLE_BUF + 32) * 4; }
+constexpr int lowSmemBytes() { return LOW_MAX_TRIS * 22 + RASTER_WARPS * (MAX_BLOCK_TRIS + SAMPLE_BUF + 32) * 4; }
 template <int CAP> constexpr int highSmemBytes() {
 	return (CAP * 4 < MAX_HBLOCK_ROW_TRIS ? CAP * 4 : MAX_HBLOCK_ROW_TRIS) + RASTER_WARPS * (CAP + SAMPLE_BUF + 32) * 4;
 }

@@ -224,7 +224,10 @@ __device__ void storeTri(const Params &p, const LucidConfig &cfg, u32 tri_idx, u
 						  __float_as_uint(edge0.z), __float_as_uint(param0));
 	sh.bary1 = make_uint4(__float_as_uint(edge1.x), __float_as_uint(edge1.y),
 						  __float_as_uint(edge1.z), __float_as_uint(param1));
-	sh.misc = make_uint4(enc_normal, inst_color, 0u, 0u);
+	const bool constant = (flags_id & INST_VARYING_MASK) == 0;
+	sh.misc = make_uint4(enc_normal, inst_color,
+						 constant ? shadeConstant(cfg.lighting, flags_id, inst_color, enc_normal) : 0u,
+						 constant ? 1u : 0u);
 	uint4 *dst = reinterpret_cast<uint4 *>(p.tri_shade + tri_idx);
 	dst[0] = sh.depth, dst[1] = sh.bary0, dst[2] = sh.bary1, dst[3] = sh.misc;
 

@@ -32,7 +32,8 @@
 // operation individually rounded in the association written below (no FMA contraction: build with
 // -ffp-contract=off), 1/x and sqrt correctly rounded, inversesqrt(x) := 1/sqrt(x),
 // min/max := fminf/fmaxf (NaN loses), float->int conversions saturate (NaN -> 0),
-// pow(x, y) := the polynomial exp2/log2 of orc_pow() below.
+// pow(x, y) := the polynomial exp2/log2 of orc_pow() below, whose Horner steps are the only fused
+// multiply-adds of the contract (explicit fmaf, single rounding on both sides).
 
 #include "../include/lucid_abi.h"
 
@@ -94,8 +95,8 @@ inline int findMSB(u32 v) { return v == 0 ? -1 : 31 - __builtin_clz(v); }
 inline int popcount(u32 v) { return __builtin_popcount(v); }
 
 // log2 on the mantissa interval [sqrt(1/2), sqrt(2)) with the classic atanh series, exp2 with a
-// degree-6 Taylor polynomial; every operation is a plain binary32 op so the CUDA side can repeat
-// it bit for bit.  |relative error| < 2e-6 on the sRGB ranges (checked in tests/).
+// degree-6 Taylor polynomial; Horner steps are explicit fmaf so the CUDA side (FFMA) repeats them
+// bit for bit.  |relative error| < 2e-6 on the sRGB ranges (checked in tests/).
 inline float orc_log2(float x) {
 	u32 ix = floatBits(x);
 	int e = (int)(ix - 0x3f3504f3u) >> 23;
@@ -104,23 +105,23 @@ inline float orc_log2(float x) {
 	float s = f / (2.0f + f);
 	float z = s * s;
 	float p = 0.2222222222f;				// 2/9
-	p = p * z + 0.2857142857f;				// 2/7
-	p = p * z + 0.4f;						// 2/5
-	p = p * z + 0.6666666667f;				// 2/3
-	p = p * z + 2.0f;
+	p = fmaf(p, z, 0.2857142857f);			// 2/7
+	p = fmaf(p, z, 0.4f);					// 2/5
+	p = fmaf(p, z, 0.6666666667f);			// 2/3
+	p = fmaf(p, z, 2.0f);
 	float ln = s * p;
-	return ln * 1.4426950408889634f + (float)e;
+	return fmaf(ln, 1.4426950408889634f, (float)e);
 }
 inline float orc_exp2(float t) {
 	float n = floorf(t + 0.5f);
 	float r = (t - n) * 0.6931471805599453f;
 	float p = 1.0f / 720.0f;
-	p = p * r + 1.0f / 120.0f;
-	p = p * r + 1.0f / 24.0f;
-	p = p * r + 1.0f / 6.0f;
-	p = p * r + 0.5f;
-	p = p * r + 1.0f;
-	p = p * r + 1.0f;
+	p = fmaf(p, r, 1.0f / 120.0f);
+	p = fmaf(p, r, 1.0f / 24.0f);
+	p = fmaf(p, r, 1.0f / 6.0f);
+	p = fmaf(p, r, 0.5f);
+	p = fmaf(p, r, 1.0f);
+	p = fmaf(p, r, 1.0f);
 	int ni = f2i(n);
 	if(ni < -126)
 		return 0.0f;

@@ -44,6 +44,14 @@ def run_cuda(scene, opts=0, camera=None, bin_rows=None, mvq=1 << 20, renderer=No
     return r, img
 
 
+def canonical_lists(values, counts):
+    """Sorts the entries of every bin's segment (segments are laid out in bin order)."""
+    values = np.asarray(values)
+    bins = np.repeat(np.arange(len(counts)), np.asarray(counts, np.int64))
+    order = np.lexsort((values & 0x0FFFFFFF, bins))
+    return values[order]
+
+
 def compare(r, img, o, check_image=True):
     """Returns a dict of mismatch descriptions (empty = parity)."""
     bad = {}
@@ -77,10 +85,12 @@ def compare(r, img, o, check_image=True):
     words("low_bins", cc[7][:n_low], co[7][:n_low])
     words("high_bins", cc[9][:n_high], co[9][:n_high])
     if "bin_quad_counts" not in bad and "bin_tri_counts" not in bad:
+        # canonical form: every bin's list as a sorted set -- the order inside a
+        # list comes from atomic arrival in the reference and in the CUDA path alike
         bq_o, bt_o = o.read_bin_lists()
         bq_c, bt_c = r.read_bin_lists(bq_o.size, bt_o.size)
-        words("bin_quads", bq_c, bq_o)
-        words("bin_tris", bt_c, bt_o)
+        words("bin_quads", canonical_lists(bq_c, co[0]), canonical_lists(bq_o, co[0]))
+        words("bin_tris", canonical_lists(bt_c, co[3]), canonical_lists(bt_o, co[3]))
     words("stats", hc[60:63], ho[60:63])
     words("frag_counts", r.read_frag_counts(), o.read_frag_counts())
     if check_image:

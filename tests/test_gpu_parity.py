@@ -49,6 +49,7 @@ def test_matches_committed_golden(name, small):
         _, counts = api.split_info(info, r.bin_count)
         assert digest(counts[:6]) == g["bin_counts"]
         bq, bt = r.read_bin_lists(st["bin_quads"], st["bin_tris"])
+        bq, bt = pu.canonical_lists(bq, counts[0]), pu.canonical_lists(bt, counts[3])
         assert digest(bq) == g["bin_quads"] and digest(bt) == g["bin_tris"]
         assert digest(r.read_frag_counts()) == g["frag_counts"]
         ns, nl = st["visible_small"], st["visible_large"]
@@ -99,12 +100,15 @@ def test_deterministic_and_idempotent(small):
     r, img0 = pu.run_cuda(sc)
     try:
         info0 = r.read_info().copy()
+        _, cnt0 = api.split_info(info0, r.bin_count)
         bq0, bt0 = r.read_bin_lists(int(api.decode_stats(info0, r.bin_count, r.width, r.height)["bin_quads"]), 0)
+        bq0 = pu.canonical_lists(bq0, cnt0[0])
         other = dict(sc["camera"], rot_h=1.7)
         pu.run_cuda(sc, camera=other, renderer=r)
         _, img1 = pu.run_cuda(sc, renderer=r)
         info1 = r.read_info()
         bq1, _ = r.read_bin_lists(bq0.size, 0)
+        bq1 = pu.canonical_lists(bq1, cnt0[0])
         assert np.array_equal(img0, img1)
         assert np.array_equal(info0[:64], info1[:64])
         # the six per-bin counter arrays are cleared every frame; the level lists are only
@@ -239,9 +243,9 @@ def test_full_size_hairball_properties():
         _, counts = api.split_info(info, r.bin_count)
         bq, _ = r.read_bin_lists(st["bin_quads"], 0)
         offs, cnts = counts[1], counts[0]
-        for b in np.argsort(cnts)[-20:]:
-            seg = bq[offs[b]:offs[b] + cnts[b]] & 0x0FFFFFFF
-            assert (np.diff(seg.astype(np.int64)) > 0).all()
+        for b in np.argsort(cnts)[-20:]:  # list entries are unique visible small-quad slots
+            seg = np.sort(bq[offs[b]:offs[b] + cnts[b]] & 0x0FFFFFFF)
+            assert (np.diff(seg.astype(np.int64)) > 0).all() and seg[-1] < st["visible_small"]
         _, img2 = pu.run_cuda(sc, renderer=r)
         assert np.array_equal(img, img2)
     finally:
