@@ -15,7 +15,13 @@ def funcs_of(fpath):
         return func_cache[fpath]
     out = []
     try:
-        lines = open(fpath).read().splitlines()
+        local = fpath
+        if not os.path.exists(local):
+            for sub in ("lucid_b200/csrc", "lucid_b200/host", "include"):
+                cand = os.path.join(root, sub, os.path.basename(fpath))
+                if os.path.exists(cand):
+                    local = cand
+        lines = open(local).read().splitlines()
     except OSError:
         lines = []
     for i, ln in enumerate(lines, 1):
