@@ -94,9 +94,6 @@ void freeAll(lucid_renderer *r) {
 		cudaStreamDestroy(r->stream);
 }
 
-int rasterHighSmallCtas(int sms) { return sms * 8; }
-int rasterHighLargeCtas(int sms) { return sms * 2; }
-
 } // namespace
 
 extern "C" {
@@ -198,9 +195,7 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.bin_stats, (size_t)p.bin_count * 4));
 	CUC(devAlloc(r, &p.work_counters, 8));
 	CUC(devAlloc(r, &p.deferred_items, (size_t)p.bin_count * 8));
-	size_t scratch_entries = std::max((size_t)rasterHighSmallCtas(r->num_sms) * 4096,
-									  (size_t)rasterHighLargeCtas(r->num_sms) * 16384);
-	CUC(devAlloc(r, &p.high_scratch, scratch_entries));
+	CUC(devAlloc(r, &p.high_scratch, rasterScratchBytes(r->num_sms) / sizeof(uint4)));
 	CUC(devAlloc(r, &r->image, (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->frag_counts, (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->d_instances, (size_t)LUCID_MAX_INSTANCES));

@@ -80,8 +80,8 @@ struct Params {
 	u32 *bin_flags;		  // per bin: bit 0 promoted LOW->HIGH, bit 1 HIGH error
 	u32 *bin_stats;		  // per bin: [0] LOW frags [1] LOW hbtris [2] HIGH frags [3] HIGH hbtris
 	u32 *work_counters;	  // [0] low items [1] high items [2] high-big items [3] deferred count
-	int *deferred_items;  // HIGH items that need the large-capacity kernel
-	uint4 *high_scratch;  // per persistent CTA: half-block-row records
+	int *deferred_items;  // HIGH bins that need the large-capacity kernel
+	uint4 *high_scratch;  // per persistent raster CTA: the half-block / block lists of its current bin
 	// textures: level offsets into one RGBA8 array per slot
 	const uchar4 *tex_data[2];
 	int tex_width[2], tex_height[2], tex_levels[2];
@@ -221,5 +221,6 @@ void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t strea
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *stage_events);
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream,
 				  cudaEvent_t *stage_events, int num_sms);
+size_t rasterScratchBytes(int num_sms);
 
 } // namespace lucid

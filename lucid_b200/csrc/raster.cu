@@ -2,28 +2,29 @@
 //
 // Replaces data/shaders/raster_low.glsl, raster_high.glsl, shared/raster.glsl and
 // shared/shading.glsl.  Same results, different decomposition:
-//   * a work item is one block row of a LOW bin (8 pixel rows, four 8x8 blocks) or one half-block
-//     row of a HIGH bin (4 pixel rows, four 8x4 half-blocks); a 128-thread CTA takes one item and
-//     each of its four warps owns one block column.  The reference runs a whole bin per work
-//     group and bounces row lists and half-block lists through global scratch
-//     (raster_low.glsl:22-32,58-63); here LOW keeps everything in shared memory and HIGH keeps
-//     only its row records in an L2-resident scratch slice.
-//   * sort keys break depth ties by the triangle's position in the bin's (sorted) list instead
-//     of an atomic arrival slot, so the output is deterministic.
-//   * samples are expanded and consumed as a stream with the reference's 256-sample segments
-//     (raster.glsl:71-72,292-396), which keeps the per-segment saturation points identical.
+//   * a persistent 256-thread CTA takes one bin at a time.  Phase A walks the bin's triangles
+//     once and appends a record to the list of every 8x4 half-block (HIGH) or 8x8 block (LOW) the
+//     triangle covers; the lists live in an L2-resident scratch slice owned by the CTA.  The
+//     reference builds per-row lists first and filters them per block column
+//     (raster_low.glsl:22-32,58-63,81-106; raster_high.glsl:54-144).
+//   * phase B hands half-blocks / blocks to warps dynamically: depth keys, a register-tile
+//     bitonic sort, then shading with lane = pixel.
+//   * depth ties are broken by triangle index instead of an atomic arrival slot, so the output is
+//     deterministic.
+//   * instead of regrouping 32 shaded samples per round through shared-memory atomics and
+//     shuffles (raster.glsl:358-396), a 32x32 bit transpose of the triangles' pixel masks gives
+//     every pixel lane its own sample list for up to 256 samples at a time.
 #include "common.cuh"
 
 namespace lucid {
 
-constexpr int RASTER_THREADS = 128;
+constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int SEGMENT_SIZE = 256;
 constexpr int SAMPLE_BUF = SEGMENT_SIZE + 32;
 constexpr int MAX_BLOCK_TRIS = 256;		 // raster_low.glsl:17
 constexpr int MAX_HBLOCK_TRIS = 4096;	 // raster_high.glsl:27
 constexpr int MAX_HBLOCK_ROW_TRIS = 16384; // raster_high.glsl:30
-constexpr int LOW_MAX_TRIS = 1024;
 
 __device__ __forceinline__ const int *cntc(const Params &p, int which) {
 	return p.counts + (size_t)which * p.bin_count;
@@ -56,24 +57,6 @@ __device__ __forceinline__ void rasterBinStep(RowScan &r, u32 &min_bits, u32 &ma
 		bx_mask |= (0xfu << (imin >> 3)) & (0xfu >> (3 - (imax >> 3)));
 	}
 	bx_mask &= 0xfu;
-}
-
-// raster.glsl:142-168 -- one 8-wide column of four rows: pixel mask, fragment count, centroid sums
-__device__ __forceinline__ u32 halfPixelMask(u32 mins, u32 maxs, int startx, int &num_frags,
-											 int &csum_x, int &csum_y) {
-	u32 bits = 0;
-	num_frags = 0, csum_x = 0, csum_y = 0;
-#pragma unroll
-	for(int r = 0; r < 4; r++) {
-		int mn = max((int)((mins >> (5 * r)) & 31) - startx, 0);
-		int mx = min((int)((maxs >> (5 * r)) & 31) - startx, 7);
-		int c = max(mx - mn + 1, 0);
-		num_frags += c;
-		csum_x += (mn * 2 + c) * c;
-		csum_y += (2 * r + 1) * c;
-		bits |= ((1u << c) - 1u) << (mn + 8 * r);
-	}
-	return bits;
 }
 
 // raster.glsl:170-176
@@ -141,7 +124,7 @@ __device__ float4 sampleTexture(const Params &p, int slot, float u, float v, flo
 					   c0.w + (c1.w - c0.w) * a);
 }
 
-__device__ u32 shadeSample(const Params &p, const LucidConfig &cfg, int ipx, int ipy, u32 tri_idx,
+__device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg, int ipx, int ipy, u32 tri_idx,
 						   float &out_depth) {
 	float px = float(ipx), py = float(ipy);
 	const uint4 *rec = reinterpret_cast<const uint4 *>(p.tri_shade + tri_idx);
@@ -278,74 +261,138 @@ __device__ __forceinline__ void reducerPush(Reducer &s, u32 color, float depth, 
 
 // ------------------------------------------------------------------------------------------------
 // warp-level sort of u32 keys in shared memory (ascending)
+//
+// Bitonic network in its "mirrored" form: the first step of every merge level pairs element e with
+// e ^ (k - 1), the remaining steps pair e with e ^ j, and every compare-exchange moves the smaller
+// key to the lower index -- no per-run direction.  A lane holds K consecutive keys in registers
+// (element e = lane * K + r): steps with a partner distance below K are register-to-register
+// min/max pairs, the others one shuffle per key.  Tiles of 256 keys (K = 8) are sorted entirely in
+// registers; only the steps with distance >= 256 of larger lists go through shared memory.
 
-__device__ __forceinline__ u32 bitonic32(u32 v) {
-	const u32 lane = laneId();
+template <int K> __device__ __forceinline__ void sortRegsMergeSteps(u32 (&v)[K], int first_j, u32 lane) {
 #pragma unroll
-	for(int k = 2; k <= 32; k <<= 1) {
+	for(int j = first_j; j >= 1; j >>= 1) {
+		if(j < K) {
 #pragma unroll
-		for(int j = k >> 1; j > 0; j >>= 1) {
-			u32 o = __shfl_xor_sync(0xffffffffu, v, j);
-			bool up = (lane & k) == 0 || k == 32;
-			bool lower = (lane & j) == 0;
-			v = (lower == up) ? min(v, o) : max(v, o);
+			for(int r = 0; r < K; r++)
+				if((r & j) == 0) {
+					u32 lo = min(v[r], v[r | j]), hi = max(v[r], v[r | j]);
+					v[r] = lo, v[r | j] = hi;
+				}
+		} else {
+			const int lm = j / K;
+			const bool lower = (lane & lm) == 0;
+#pragma unroll
+			for(int r = 0; r < K; r++) {
+				u32 o = __shfl_xor_sync(0xffffffffu, v[r], lm);
+				v[r] = lower ? min(v[r], o) : max(v[r], o);
+			}
 		}
 	}
-	return v;
 }
 
-// the last five steps of a bitonic merge (partner distance 16..1) stay in registers
-__device__ __forceinline__ u32 bitonicMerge32(u32 v, bool ascending) {
-	const u32 lane = laneId();
+// full sort of the 32 * K keys held by the warp
+template <int K> __device__ __forceinline__ void sortRegs(u32 (&v)[K], u32 lane) {
 #pragma unroll
-	for(int j = 16; j > 0; j >>= 1) {
-		u32 o = __shfl_xor_sync(0xffffffffu, v, j);
-		bool lower = (lane & j) == 0;
-		v = (lower == ascending) ? min(v, o) : max(v, o);
+	for(int k = 2; k <= 32 * K; k <<= 1) {
+		if(k <= K) {
+#pragma unroll
+			for(int r = 0; r < K; r++)
+				if((r & (k >> 1)) == 0) {
+					const int q = r ^ (k - 1);
+					u32 lo = min(v[r], v[q]), hi = max(v[r], v[q]);
+					v[r] = lo, v[q] = hi;
+				}
+		} else {
+			const int lm = k / K - 1;
+			const bool lower = (lane & (k / (2 * K))) == 0;
+			u32 o[K];
+#pragma unroll
+			for(int r = 0; r < K; r++)
+				o[r] = __shfl_xor_sync(0xffffffffu, v[r ^ (K - 1)], lm);
+#pragma unroll
+			for(int r = 0; r < K; r++)
+				v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
+		}
+		sortRegsMergeSteps<K>(v, k >> 2, lane);
 	}
-	return v;
 }
 
-// keys[0..n) ascending; the array must have room for n rounded up to a power of two (>= 64)
-__device__ void warpSortShared(u32 *keys, int n) {
-	const int lane = laneId();
-	if(n <= 32) {
-		u32 v = lane < n ? keys[lane] : 0xffffffffu;
-		v = bitonic32(v);
-		if(lane < n)
-			keys[lane] = v;
-		__syncwarp();
+template <int K> __device__ __forceinline__ void sortSingleTile(u32 *keys, int n, u32 lane) {
+	u32 v[K];
+#pragma unroll
+	for(int r = 0; r < K; r++) {
+		int e = lane * K + r;
+		v[r] = e < n ? keys[e] : 0xffffffffu;
+	}
+	sortRegs<K>(v, lane);
+#pragma unroll
+	for(int r = 0; r < K; r++) {
+		int e = lane * K + r;
+		if(e < n)
+			keys[e] = v[r];
+	}
+}
+
+// keys[0..n) ascending; the array has room for n rounded up to a power of two
+template <int CAP> __device__ void warpSortShared(u32 *keys, int n) {
+	const u32 lane = laneId();
+	if(n <= 1)
 		return;
-	}
-	int padded = 64;
-	while(padded < n)
-		padded <<= 1;
-	for(int i = n + lane; i < padded; i += 32)
-		keys[i] = 0xffffffffu;
-	__syncwarp();
-	// runs of 32 sorted in registers, alternating direction
-	for(int base = 0; base < padded; base += 32) {
-		u32 v = bitonic32(keys[base + lane]);
-		if(base & 32)
-			v = __shfl_sync(0xffffffffu, v, 31 - lane);
-		keys[base + lane] = v;
-	}
-	__syncwarp();
-	for(int k = 64; k <= padded; k <<= 1) {
-		for(int j = k >> 1; j >= 32; j >>= 1) {
+	if(n <= 32)
+		sortSingleTile<1>(keys, n, lane);
+	else if(n <= 64)
+		sortSingleTile<2>(keys, n, lane);
+	else if(n <= 128)
+		sortSingleTile<4>(keys, n, lane);
+	else if(n <= 256)
+		sortSingleTile<8>(keys, n, lane);
+	else if(CAP > 256) {
+		int padded = 512;
+		while(padded < n)
+			padded <<= 1;
+		for(int i = n + lane; i < padded; i += 32)
+			keys[i] = 0xffffffffu;
+		__syncwarp();
+		uint4 *tiles = reinterpret_cast<uint4 *>(keys);
+		for(int base = 0; base < padded; base += 256) {
+			uint4 a = tiles[(base >> 2) + lane * 2], b = tiles[(base >> 2) + lane * 2 + 1];
+			u32 v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+			sortRegs<8>(v, lane);
+			tiles[(base >> 2) + lane * 2] = make_uint4(v[0], v[1], v[2], v[3]);
+			tiles[(base >> 2) + lane * 2 + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+		}
+		__syncwarp();
+		for(int k = 512; k <= padded; k <<= 1) {
+			const int half = k >> 1;
 			for(int i = lane; i < (padded >> 1); i += 32) {
-				int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
-				bool ascending = (lo & k) == 0;
+				int blk = i / half, idx = i - blk * half;
+				int lo = blk * k + idx, hi = blk * k + (k - 1 - idx);
 				u32 a = keys[lo], b = keys[hi];
-				if((a > b) == ascending)
+				if(a > b)
 					keys[lo] = b, keys[hi] = a;
 			}
 			__syncwarp();
+			for(int j = k >> 2; j >= 256; j >>= 1) {
+				for(int i = lane; i < (padded >> 1); i += 32) {
+					int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+					u32 a = keys[lo], b = keys[hi];
+					if(a > b)
+						keys[lo] = b, keys[hi] = a;
+				}
+				__syncwarp();
+			}
+			for(int base = 0; base < padded; base += 256) {
+				uint4 a = tiles[(base >> 2) + lane * 2], b = tiles[(base >> 2) + lane * 2 + 1];
+				u32 v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+				sortRegsMergeSteps<8>(v, 128, lane);
+				tiles[(base >> 2) + lane * 2] = make_uint4(v[0], v[1], v[2], v[3]);
+				tiles[(base >> 2) + lane * 2 + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+			}
+			__syncwarp();
 		}
-		for(int base = 0; base < padded; base += 32)
-			keys[base + lane] = bitonicMerge32(keys[base + lane], (base & k) == 0);
-		__syncwarp();
 	}
+	__syncwarp();
 }
 
 // Entries with equal quantised depth are ordered by triangle index.  The low key bits only make
@@ -379,133 +426,91 @@ __device__ void warpFixDepthTies(u32 *keys, int n, int slot_bits, TriOf triOf) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// the work item
+// half-block records
+//
+// Phase A of a bin turns every (triangle, 4-row group, 8-pixel column) with coverage into one
+// record appended to that half-block's list: the triangle index and, for each of the 4 pixel rows,
+// the first covered x (3 bits) and the number of covered pixels (4 bits) -- the same content as the
+// reference's half-block tri record (raster.glsl:152-161), kept per half-block from the start so
+// that phase B never filters a row list.
 
-template <bool HIGH> struct Geo {
-	static constexpr int rows_per_group = HIGH ? 4 : 8;
-	static constexpr int group_shift = HIGH ? 2 : 3;
-	static constexpr int halves = HIGH ? 1 : 2;
-	static constexpr int slot_bits = HIGH ? 14 : 10;
-};
+// (xmin, count) x 4 rows of column `startx / 8` from the bin-wide 5-bit spans
+__device__ __forceinline__ u32 packHalfRows(u32 mins, u32 maxs, int startx) {
+	u32 rows = 0;
+#pragma unroll
+	for(int r = 0; r < 4; r++) {
+		int mn = max((int)((mins >> (5 * r)) & 31) - startx, 0);
+		int mx = min((int)((maxs >> (5 * r)) & 31) - startx, 7);
+		int c = max(mx - mn + 1, 0);
+		if(c == 0)
+			mn = 0;
+		rows |= (u32)(mn | (c << 3)) << (7 * r);
+	}
+	return rows;
+}
+// raster.glsl:142-168: pixel mask (bit y * 8 + x), fragment count and centroid sums of a record
+__device__ __forceinline__ u32 rowsToBits(u32 rows, int &num_frags) {
+	u32 bits = 0;
+	num_frags = 0;
+#pragma unroll
+	for(int r = 0; r < 4; r++) {
+		u32 mn = (rows >> (7 * r)) & 7u, c = (rows >> (7 * r + 3)) & 15u;
+		bits |= ((1u << c) - 1u) << (mn + 8 * r);
+		num_frags += (int)c;
+	}
+	return bits;
+}
+__device__ __forceinline__ void rowsCentroid(u32 rows, int &num_frags, int &csum_x, int &csum_y) {
+	num_frags = 0, csum_x = 0, csum_y = 0;
+#pragma unroll
+	for(int r = 0; r < 4; r++) {
+		int mn = (rows >> (7 * r)) & 7, c = (rows >> (7 * r + 3)) & 15;
+		num_frags += c;
+		csum_x += (mn * 2 + c) * c;
+		csum_y += (2 * r + 1) * c;
+	}
+}
+
+// 32 x 32 bit-matrix transpose across the warp: lane j gives row j, lane p receives column p
+__device__ __forceinline__ u32 transpose32(u32 x) {
+	const u32 lane = laneId();
+#pragma unroll
+	for(int j = 16; j >= 1; j >>= 1) {
+		const u32 m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+		u32 y = __shfl_xor_sync(0xffffffffu, x, j);
+		x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+	}
+	return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading of one 8x4 half-block from its depth-sorted list
+
+constexpr int CHUNK_SAMPLES = 256;
 
 struct WarpScratch {
-	u32 *keys;	  // CAP entries
-	u32 *samples; // SAMPLE_BUF entries
-	u32 *mask;	  // 32 entries
+	float4 *stage;	 // 32: depth plane + constant colour of the chunk's triangles
+	uint2 *results;	 // CHUNK_SAMPLES: (colour, depth) per sample
+	uint2 *chunk;	 // 32: (pixel mask, first sample) of the chunk's triangles
+	u32 *samples;	 // SAMPLE_BUF: pixel | tri << 8
+	u32 *mask;		 // 32 (segment path)
+	u32 *keys;		 // CAP
 };
+constexpr int WARP_SCRATCH_FIXED = 32 * 16 + CHUNK_SAMPLES * 8 + 32 * 8 + SAMPLE_BUF * 4 + 32 * 4;
+__device__ __forceinline__ WarpScratch warpScratch(unsigned char *base) {
+	WarpScratch ws;
+	ws.stage = reinterpret_cast<float4 *>(base);
+	ws.results = reinterpret_cast<uint2 *>(base + 32 * 16);
+	ws.chunk = ws.results + CHUNK_SAMPLES;
+	ws.samples = reinterpret_cast<u32 *>(ws.chunk + 32);
+	ws.mask = ws.samples + SAMPLE_BUF;
+	ws.keys = ws.mask + 32;
+	return ws;
+}
 
-// Streams the sorted triangle list of one 8x4 half-block: expands triangles into samples in
-// 256-sample segments, shades 32 samples per round and feeds every pixel's samples to its lane.
-// getRow(slot) returns (mins, maxs, tri_idx) of the list entry for this half.
-template <typename GetRow>
-__device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const WarpScratch &ws,
-							   int count, int slot_mask, int startx, int hb_x, int hb_y,
-							   GetRow getRow, u32 &out_frags) {
+__device__ __forceinline__ void writePixel(const Params &p, const LucidConfig &cfg, Reducer &red, int hb_x, int hb_y,
+										   u32 px_frags, bool additive, bool vis_errors) {
 	const int lane = laneId();
-	const bool additive = (p.opts & LUCID_OPT_ADDITIVE_BLENDING) != 0;
-	const bool vis_errors = (p.opts & LUCID_OPT_VISUALIZE_ERRORS) != 0;
-	const bool alpha_thr = (p.opts & LUCID_OPT_ALPHA_THRESHOLD) != 0 && !additive && !vis_errors;
-	Reducer red;
-	reducerInit(red);
-	u32 px_frags = 0, total_frags = 0;
-
-	int next = 0;		 // next list entry to expand
-	u32 seg_start = 0;	 // sample offset of the current segment
-	u32 off = 0;		 // sample offset of entry `next`
-	int carried = 0;	 // samples spilled past the previous segment (< 32)
-	bool stop = false;
-
-	while(next < count || carried > 0) {
-		// move the spill of the previous segment to the front (raster.glsl:302-304)
-		if(carried > 0) {
-			u32 v = ws.samples[SEGMENT_SIZE + lane];
-			__syncwarp();
-			ws.samples[lane] = v;
-		}
-		__syncwarp();
-		// expand entries whose first sample lies inside this segment
-		const u32 seg_end = seg_start + SEGMENT_SIZE;
-		while(next < count && off < seg_end) {
-			int i = next + lane;
-			u32 mins = 0, maxs = 0, tri_idx = 0;
-			u32 bits = 0;
-			int nf = 0;
-			if(i < count) {
-				u32 slot = ws.keys[i] & slot_mask;
-				getRow(slot, mins, maxs, tri_idx);
-				int cx, cy;
-				bits = halfPixelMask(mins, maxs, startx, nf, cx, cy);
-			}
-			int incl = nf;
-#pragma unroll
-			for(int o = 1; o < 32; o <<= 1) {
-				int t = __shfl_up_sync(0xffffffffu, incl, o);
-				if(lane >= o)
-					incl += t;
-			}
-			u32 my_off = off + (u32)(incl - nf);
-			bool in_seg = i < count && my_off < seg_end;
-			u32 in_mask = __ballot_sync(0xffffffffu, in_seg);
-			int taken = __popc(in_mask); // a prefix of the lanes
-			if(in_seg) {
-				u32 dst = my_off - seg_start;
-				u32 word = tri_idx << 8;
-				while(bits) {
-					u32 pid = __ffs(bits) - 1;
-					bits &= bits - 1;
-					ws.samples[dst++] = pid | word;
-				}
-			}
-			u32 consumed = __shfl_sync(0xffffffffu, (u32)incl, max(taken - 1, 0));
-			if(taken > 0)
-				off += consumed;
-			next += taken;
-			if(taken < 32)
-				break;
-		}
-		__syncwarp();
-		u32 avail = off - seg_start; // samples buffered for this segment (may exceed 256 by < 32)
-		int nseg = (int)min(avail, (u32)SEGMENT_SIZE);
-		carried = (int)(avail - (u32)nseg);
-		total_frags += (u32)nseg;
-
-		for(int r0 = 0; r0 < nseg; r0 += 32) {
-			int idx = r0 + lane;
-			bool active = idx < nseg;
-			u32 val = active ? ws.samples[idx] : 0u;
-			ws.mask[lane] = 0;
-			__syncwarp();
-			u32 color = 0;
-			float depth = 0.0f;
-			if(active && !stop) {
-				u32 pid = val & 31u;
-				color = shadeSample(p, cfg, hb_x + (int)(pid & 7), hb_y + (int)(pid >> 3), val >> 8, depth);
-			}
-			if(active)
-				atomicOr(&ws.mask[val & 31u], 1u << lane);
-			__syncwarp();
-			u32 pm = ws.mask[lane];
-			px_frags += __popc(pm);
-			if(stop)
-				pm = 0;
-			while(__any_sync(0xffffffffu, pm != 0)) {
-				int bit = pm ? __ffs(pm) - 1 : 0;
-				u32 c = __shfl_sync(0xffffffffu, color, bit);
-				float d = __shfl_sync(0xffffffffu, depth, bit);
-				if(pm) {
-					pm &= pm - 1;
-					reducerPush(red, c, d, additive, vis_errors);
-				}
-			}
-			__syncwarp();
-		}
-		// end of segment: saturate (raster.glsl:394-395), optional early out
-		red.r = saturatef(red.r), red.g = saturatef(red.g), red.b = saturatef(red.b);
-		if(alpha_thr && nseg == SEGMENT_SIZE && __all_sync(0xffffffffu, red.trans < (1.0f / 128.0f)))
-			stop = true;
-		seg_start += SEGMENT_SIZE;
-	}
-
 	// finishReduceSamples (shading.glsl:297-314)
 	if(red.c2 != 0)
 		reducerBlend(red, red.c2, additive);
@@ -533,8 +538,226 @@ __device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const Wa
 		if(lane == 0 && inv)
 			atomicAdd(&p.info->stats[2], inv);
 	}
-	out_frags = total_frags;
 }
+
+// Lane = pixel.  The sorted list is consumed in chunks of up to 32 triangles (at most 256
+// samples).  A 32x32 bit transpose of the chunk's pixel masks tells every pixel lane which of the
+// chunk's triangles cover it, in list order; the lane then walks its own samples through the
+// 3-entry window.  Triangles with a per-triangle constant colour are shaded by the pixel lane
+// itself (depth plane from shared memory); other chunks shade all samples first, one sample per
+// lane, and the pixel lanes pick the results up.  The reference's per-segment saturate
+// (raster.glsl:394-395) cannot change the stored pixel -- the accumulators never decrease and the
+// final value is saturated -- so segments only matter for the alpha-threshold early out, which
+// keeps the segment-accurate path below.  Once every pixel of the half-block has zero
+// transmittance, later samples add exactly +0 and are skipped.
+template <typename GetRec>
+__device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const WarpScratch &ws, int count,
+							   u32 pos_mask, int hb_x, int hb_y, GetRec getRec) {
+	const int lane = laneId();
+	const bool additive = (p.opts & LUCID_OPT_ADDITIVE_BLENDING) != 0;
+	const bool vis_errors = (p.opts & LUCID_OPT_VISUALIZE_ERRORS) != 0;
+	const float fpx = float(hb_x + (lane & 7)), fpy = float(hb_y + (lane >> 3));
+	Reducer red;
+	reducerInit(red);
+	u32 px_frags = 0;
+	bool dead = false;
+
+	for(int next = 0; next < count;) {
+		const int i = next + lane;
+		u32 rows = 0, tri_idx = 0, bits = 0;
+		int nf = 0;
+		if(i < count) {
+			getRec(ws.keys[i] & pos_mask, rows, tri_idx);
+			bits = rowsToBits(rows, nf);
+		}
+		int incl = nf;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			int t = __shfl_up_sync(0xffffffffu, incl, o);
+			if(lane >= o)
+				incl += t;
+		}
+		const bool in_chunk = i < count && incl <= CHUNK_SAMPLES;
+		const int taken = __popc(__ballot_sync(0xffffffffu, in_chunk)); // a prefix, never empty
+		const int total = __shfl_sync(0xffffffffu, incl, taken - 1);
+		const int off = incl - nf;
+		if(!in_chunk)
+			bits = 0;
+		next += taken;
+		u32 tm = transpose32(bits);
+		px_frags += __popc(tm);
+		if(dead)
+			continue;
+
+		uint4 dq = make_uint4(0, 0, 0, 0), misc = make_uint4(0, 0, 0, 1);
+		if(in_chunk) {
+			const uint4 *rec = reinterpret_cast<const uint4 *>(p.tri_shade + tri_idx);
+			dq = __ldg(rec), misc = __ldg(rec + 3);
+		}
+		if(__all_sync(0xffffffffu, misc.w != 0)) {
+			ws.stage[lane] = make_float4(__uint_as_float(dq.x), __uint_as_float(dq.y), __uint_as_float(dq.z),
+										 __uint_as_float(misc.z));
+			__syncwarp();
+			while(tm) {
+				int j = __ffs(tm) - 1;
+				tm &= tm - 1;
+				float4 s = ws.stage[j];
+				float depth = s.x * fpx + (s.y * fpy + s.z);
+				reducerPush(red, __float_as_uint(s.w), depth, additive, vis_errors);
+			}
+		} else {
+			if(in_chunk) {
+				ws.chunk[lane] = make_uint2(bits, (u32)off);
+				u32 dst = (u32)off, word = tri_idx << 8, b = bits;
+				while(b) {
+					u32 pid = __ffs(b) - 1;
+					b &= b - 1;
+					ws.samples[dst++] = pid | word;
+				}
+			}
+			__syncwarp();
+			for(int r0 = 0; r0 < total; r0 += 32) {
+				int idx = r0 + lane;
+				if(idx < total) {
+					u32 val = ws.samples[idx], pid = val & 31u;
+					float depth;
+					u32 color = shadeSample(p, cfg, hb_x + (int)(pid & 7), hb_y + (int)(pid >> 3), val >> 8, depth);
+					ws.results[idx] = make_uint2(color, __float_as_uint(depth));
+				}
+			}
+			__syncwarp();
+			while(tm) {
+				int j = __ffs(tm) - 1;
+				tm &= tm - 1;
+				uint2 c = ws.chunk[j];
+				uint2 res = ws.results[c.y + __popc(c.x & laneMaskLt())];
+				reducerPush(red, res.x, __uint_as_float(res.y), additive, vis_errors);
+			}
+		}
+		__syncwarp();
+		if(!vis_errors && __all_sync(0xffffffffu, red.trans == 0.0f)) {
+			dead = true;
+			if(!p.frag_counts)
+				break;
+		}
+	}
+	writePixel(p, cfg, red, hb_x, hb_y, px_frags, additive, vis_errors);
+}
+
+// Segment-accurate variant (raster.glsl:292-396) for ALPHA_THRESHOLD: samples are expanded and
+// consumed in the reference's 256-sample segments, so the early-out decisions fall on the same
+// sample boundaries.
+template <typename GetRec>
+__device__ __noinline__ void shadeHalfBlockSegments(const Params &p, const LucidConfig &cfg, const WarpScratch &ws,
+													int count, u32 pos_mask, int hb_x, int hb_y, GetRec getRec) {
+	const int lane = laneId();
+	Reducer red;
+	reducerInit(red);
+	u32 px_frags = 0;
+	int next = 0;		// next list entry to expand
+	u32 seg_start = 0;	// sample offset of the current segment
+	u32 off = 0;		// sample offset of entry `next`
+	int carried = 0;	// samples spilled past the previous segment (< 32)
+	bool stop = false;
+
+	while(next < count || carried > 0) {
+		// move the spill of the previous segment to the front (raster.glsl:302-304)
+		if(carried > 0) {
+			u32 v = ws.samples[SEGMENT_SIZE + lane];
+			__syncwarp();
+			ws.samples[lane] = v;
+		}
+		__syncwarp();
+		const u32 seg_end = seg_start + SEGMENT_SIZE;
+		while(next < count && off < seg_end) {
+			int i = next + lane;
+			u32 rows = 0, tri_idx = 0, bits = 0;
+			int nf = 0;
+			if(i < count) {
+				getRec(ws.keys[i] & pos_mask, rows, tri_idx);
+				bits = rowsToBits(rows, nf);
+			}
+			int incl = nf;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				int t = __shfl_up_sync(0xffffffffu, incl, o);
+				if(lane >= o)
+					incl += t;
+			}
+			u32 my_off = off + (u32)(incl - nf);
+			bool in_seg = i < count && my_off < seg_end;
+			int taken = __popc(__ballot_sync(0xffffffffu, in_seg)); // a prefix of the lanes
+			if(in_seg) {
+				u32 dst = my_off - seg_start, word = tri_idx << 8;
+				while(bits) {
+					u32 pid = __ffs(bits) - 1;
+					bits &= bits - 1;
+					ws.samples[dst++] = pid | word;
+				}
+			}
+			u32 consumed = __shfl_sync(0xffffffffu, (u32)incl, max(taken - 1, 0));
+			if(taken > 0)
+				off += consumed;
+			next += taken;
+			if(taken < 32)
+				break;
+		}
+		__syncwarp();
+		u32 avail = off - seg_start; // samples buffered for this segment (may exceed 256 by < 32)
+		int nseg = (int)min(avail, (u32)SEGMENT_SIZE);
+		carried = (int)(avail - (u32)nseg);
+
+		for(int r0 = 0; r0 < nseg; r0 += 32) {
+			int idx = r0 + lane;
+			bool active = idx < nseg;
+			u32 val = active ? ws.samples[idx] : 0u;
+			ws.mask[lane] = 0;
+			__syncwarp();
+			u32 color = 0;
+			float depth = 0.0f;
+			if(active && !stop) {
+				u32 pid = val & 31u;
+				color = shadeSample(p, cfg, hb_x + (int)(pid & 7), hb_y + (int)(pid >> 3), val >> 8, depth);
+			}
+			if(active)
+				atomicOr(&ws.mask[val & 31u], 1u << lane);
+			__syncwarp();
+			u32 pm = ws.mask[lane];
+			px_frags += __popc(pm);
+			if(stop)
+				pm = 0;
+			while(__any_sync(0xffffffffu, pm != 0)) {
+				int bit = pm ? __ffs(pm) - 1 : 0;
+				u32 c = __shfl_sync(0xffffffffu, color, bit);
+				float d = __shfl_sync(0xffffffffu, depth, bit);
+				if(pm) {
+					pm &= pm - 1;
+					reducerPush(red, c, d, false, false);
+				}
+			}
+			__syncwarp();
+		}
+		red.r = saturatef(red.r), red.g = saturatef(red.g), red.b = saturatef(red.b);
+		if(nseg == SEGMENT_SIZE && __all_sync(0xffffffffu, red.trans < (1.0f / 128.0f)))
+			stop = true;
+		seg_start += SEGMENT_SIZE;
+	}
+	writePixel(p, cfg, red, hb_x, hb_y, px_frags, false, false);
+}
+
+template <typename GetRec>
+__device__ __forceinline__ void shadeHalfBlockAny(const Params &p, const LucidConfig &cfg, const WarpScratch &ws,
+												 int count, u32 pos_mask, int hb_x, int hb_y, GetRec getRec) {
+	const bool alpha_thr = (p.opts & (LUCID_OPT_ALPHA_THRESHOLD | LUCID_OPT_ADDITIVE_BLENDING |
+									   LUCID_OPT_VISUALIZE_ERRORS)) == LUCID_OPT_ALPHA_THRESHOLD;
+	if(alpha_thr)
+		shadeHalfBlockSegments(p, cfg, ws, count, pos_mask, hb_x, hb_y, getRec);
+	else
+		shadeHalfBlock(p, cfg, ws, count, pos_mask, hb_x, hb_y, getRec);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bins
 
 // triangle of entry t of the bin's sequence T: quads list (two triangles per quad) then tris list
 __device__ __forceinline__ bool binTriangle(const Params &p, int t, int n_q, int q_off, int t_off, u32 &tri_idx) {
@@ -547,169 +770,210 @@ __device__ __forceinline__ bool binTriangle(const Params &p, int t, int n_q, int
 	return true;
 }
 
-// scanline state of a triangle at the first pixel row of group `g` of the bin (groups of
-// 8 rows for LOW, 4 for HIGH).  The walk starts at the triangle's first group inside the bin and
-// adds the step row by row, exactly like the reference's incremental loop, so the values -- and
-// the spans truncated from them -- are bit-identical.
-template <int ROWS_PER_GROUP>
-__device__ __forceinline__ bool rowScanAt(const Params &p, u32 tri_idx, int pos_x, int pos_y, int g, RowScan &rs) {
-	constexpr int shift = ROWS_PER_GROUP == 8 ? 3 : 2;
-	const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + tri_idx);
-	uint4 s0 = __ldg(src);
-	int ymin = (int)(s0.w & 0xffff) - pos_y, ymax = (int)(s0.w >> 16) - pos_y;
-	int min_g = min(max(ymin, 0), BIN_SIZE - 1) >> shift, max_g = min(max(ymax, 0), BIN_SIZE - 1) >> shift;
-	if(g < min_g || g > max_g)
-		return false;
-	uint4 s1 = __ldg(src + 1);
-	rs.step[0] = __uint_as_float(s1.x), rs.step[1] = __uint_as_float(s1.y), rs.step[2] = __uint_as_float(s1.z);
-	rs.xneg = s1.w & 7u;
-	float start_x = float(pos_x), start_y = float(pos_y + min_g * ROWS_PER_GROUP);
-	rs.scan[0] = __uint_as_float(s0.x) + (rs.step[0] * start_y - start_x);
-	rs.scan[1] = __uint_as_float(s0.y) + (rs.step[1] * start_y - start_x);
-	rs.scan[2] = __uint_as_float(s0.z) + (rs.step[2] * start_y - start_x);
-	for(int k = (g - min_g) * ROWS_PER_GROUP; k > 0; k--)
-		rs.scan[0] += rs.step[0], rs.scan[1] += rs.step[1], rs.scan[2] += rs.step[2];
-	return true;
-}
-__device__ __forceinline__ bool touchesGroup(const Params &p, u32 tri_idx, int pos_y, int g, int shift) {
-	u32 y_aabb = __ldg(reinterpret_cast<const u32 *>(p.tri_scan + tri_idx) + 3);
-	int ymin = (int)(y_aabb & 0xffff) - pos_y, ymax = (int)(y_aabb >> 16) - pos_y;
-	int min_g = min(max(ymin, 0), BIN_SIZE - 1) >> shift, max_g = min(max(ymax, 0), BIN_SIZE - 1) >> shift;
-	return g >= min_g && g <= max_g;
+struct BinInfo {
+	int bin_id, n_q, q_off, n_t, t_off, n_T, pos_x, pos_y;
+};
+__device__ __forceinline__ BinInfo loadBin(const Params &p, int bin_id) {
+	BinInfo b;
+	b.bin_id = bin_id;
+	b.n_q = cntc(p, LUCID_CNT_QUAD_COUNTS)[bin_id], b.q_off = cntc(p, LUCID_CNT_QUAD_OFFSETS)[bin_id];
+	b.n_t = cntc(p, LUCID_CNT_TRI_COUNTS)[bin_id], b.t_off = cntc(p, LUCID_CNT_TRI_OFFSETS)[bin_id];
+	b.n_T = b.n_q * 2 + b.n_t;
+	int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
+	b.pos_x = bin_x * BIN_SIZE, b.pos_y = bin_y * BIN_SIZE;
+	return b;
 }
 
-// LOW: one block row of a bin with fewer than 1024 triangles (raster_low.glsl)
-__device__ void rasterLowItem(const Params &p, const LucidConfig &cfg, int bin_id, int by,
-							  unsigned char *smem) {
-	uint4 *s_rows = reinterpret_cast<uint4 *>(smem);					   // LOW_MAX_TRIS, indexed by t
-	u32 *s_tri = reinterpret_cast<u32 *>(smem + LOW_MAX_TRIS * 16);		   // LOW_MAX_TRIS
-	unsigned short *s_queue = reinterpret_cast<unsigned short *>(smem + LOW_MAX_TRIS * 20); // LOW_MAX_TRIS
-	u32 *s_warp = reinterpret_cast<u32 *>(smem + LOW_MAX_TRIS * 22);
-	__shared__ int s_qcount;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	WarpScratch ws;
-	ws.keys = s_warp + warp * (MAX_BLOCK_TRIS + SAMPLE_BUF + 32);
-	ws.samples = ws.keys + MAX_BLOCK_TRIS;
-	ws.mask = ws.samples + SAMPLE_BUF;
+// Phase A: every triangle of the bin is walked once over the 4-row (HIGH) or 8-row (LOW) groups
+// its y range touches.  The scanline state is advanced row by row from the triangle's first group,
+// exactly like the reference's incremental loop (raster_low.glsl:39-64, raster_high.glsl:54-90), so
+// the spans truncated from it are bit-identical.  Walking is cheap but its trip count differs per
+// triangle, so each warp only *queues* (triangle, group, scan state) items while walking and
+// evaluates the spans (rasterBinStep, the expensive part) 32 queued items at a time with every
+// lane busy.  emit(active, tri, group, mins0, maxs0, mins1, maxs1, bx) is called by all lanes.
+constexpr int PHASE_A_RING = 64; // items; 32 bytes each, in the warp's (idle) phase-B scratch
 
-	const int n_q = cntc(p, LUCID_CNT_QUAD_COUNTS)[bin_id], q_off = cntc(p, LUCID_CNT_QUAD_OFFSETS)[bin_id];
-	const int n_t = cntc(p, LUCID_CNT_TRI_COUNTS)[bin_id], t_off = cntc(p, LUCID_CNT_TRI_OFFSETS)[bin_id];
-	const int n_T = n_q * 2 + n_t; // < 1024
-	const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
-	const int pos_x = bin_x * BIN_SIZE, pos_y = bin_y * BIN_SIZE;
-	if(tid == 0)
-		s_qcount = 0;
-	__syncthreads();
-
-	// phase A1: which triangles of the bin reach this block row (y range only)
-	for(int t0 = 0; t0 < n_T; t0 += RASTER_THREADS) {
-		int t = t0 + tid;
-		u32 tri_idx = 0;
-		bool pass = t < n_T && binTriangle(p, t, n_q, q_off, t_off, tri_idx);
-		pass = pass && touchesGroup(p, tri_idx, pos_y, by, 3);
-		if(t < n_T)
-			s_tri[t] = tri_idx;
-		u32 m = __ballot_sync(0xffffffffu, pass);
-		int base = 0;
-		if(lane == 0 && m)
-			base = atomicAdd(&s_qcount, __popc(m));
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if(pass)
-			s_queue[base + __popc(m & laneMaskLt())] = (unsigned short)t;
-	}
-	__syncthreads();
-	// phase A2: spans of the queued triangles, all lanes busy (raster_low.glsl:39-64)
-	const int n_queue = s_qcount;
-	for(int q = tid; q < n_queue; q += RASTER_THREADS) {
-		int t = s_queue[q];
+template <bool HIGH, typename Emit>
+__device__ __forceinline__ void binPhaseA(const Params &p, const BinInfo &b, uint4 *ring, Emit emit) {
+	constexpr int shift = HIGH ? 2 : 3, rows_per_group = HIGH ? 4 : 8;
+	const int lane = laneId(), warp = threadIdx.x >> 5;
+	int q_head = 0, q_tail = 0; // warp-uniform
+	auto drain = [&](int index, bool active) {
+		uint4 a = ring[(index & (PHASE_A_RING - 1)) * 2], s = ring[(index & (PHASE_A_RING - 1)) * 2 + 1];
 		RowScan rs;
-		uint4 rec = make_uint4(0, 0, 0, 0);
-		if(rowScanAt<8>(p, s_tri[t], pos_x, pos_y, by, rs)) {
-			u32 mn0, mx0, bx0, mn1, mx1, bx1;
-			rasterBinStep(rs, mn0, mx0, bx0);
+		rs.scan[0] = __uint_as_float(a.x), rs.scan[1] = __uint_as_float(a.y), rs.scan[2] = __uint_as_float(a.z);
+		rs.step[0] = __uint_as_float(s.x), rs.step[1] = __uint_as_float(s.y), rs.step[2] = __uint_as_float(s.z);
+		rs.xneg = (a.w >> 27) & 7u;
+		u32 mn0, mx0, bx0, mn1 = 0, mx1 = 0, bx1 = 0;
+		rasterBinStep(rs, mn0, mx0, bx0);
+		if(!HIGH)
 			rasterBinStep(rs, mn1, mx1, bx1);
-			u32 bx = bx0 | bx1;
-			if(bx != 0)
-				rec = make_uint4(mn0 | (bx << 24), mn1, mx0, mx1);
+		emit(active, a.w & 0xffffffu, (int)((a.w >> 24) & 7u), mn0, mx0, mn1, mx1, active ? (bx0 | bx1) : 0u);
+	};
+	for(int base = warp * 32; base < b.n_T; base += RASTER_THREADS) {
+		const int t = base + lane;
+		u32 tri_idx = 0;
+		const bool ok = t < b.n_T && binTriangle(p, t, b.n_q, b.q_off, b.t_off, tri_idx);
+		int n_g = 0, min_g = 0;
+		float scan0 = 0, scan1 = 0, scan2 = 0, step0 = 0, step1 = 0, step2 = 0;
+		u32 xneg = 0;
+		if(ok) {
+			const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + tri_idx);
+			uint4 s0 = __ldg(src), s1 = __ldg(src + 1);
+			int ymin = (int)(s0.w & 0xffff) - b.pos_y, ymax = (int)(s0.w >> 16) - b.pos_y;
+			min_g = min(max(ymin, 0), BIN_SIZE - 1) >> shift;
+			n_g = (min(max(ymax, 0), BIN_SIZE - 1) >> shift) - min_g + 1;
+			step0 = __uint_as_float(s1.x), step1 = __uint_as_float(s1.y), step2 = __uint_as_float(s1.z);
+			xneg = s1.w & 7u;
+			float start_x = float(b.pos_x), start_y = float(b.pos_y + min_g * rows_per_group);
+			scan0 = __uint_as_float(s0.x) + (step0 * start_y - start_x);
+			scan1 = __uint_as_float(s0.y) + (step1 * start_y - start_x);
+			scan2 = __uint_as_float(s0.z) + (step2 * start_y - start_x);
 		}
-		s_rows[t] = rec;
+		const int max_ng = __reduce_max_sync(0xffffffffu, n_g);
+		for(int k = 0; k < max_ng; k++) {
+			const bool has = k < n_g;
+			const u32 m = __ballot_sync(0xffffffffu, has);
+			if(has) {
+				int pos = (q_tail + __popc(m & laneMaskLt())) & (PHASE_A_RING - 1);
+				ring[pos * 2] = make_uint4(__float_as_uint(scan0), __float_as_uint(scan1), __float_as_uint(scan2),
+										   tri_idx | ((u32)(min_g + k) << 24) | (xneg << 27));
+				ring[pos * 2 + 1] = make_uint4(__float_as_uint(step0), __float_as_uint(step1), __float_as_uint(step2), 0u);
+#pragma unroll
+				for(int r = 0; r < rows_per_group; r++)
+					scan0 += step0, scan1 += step1, scan2 += step2;
+			}
+			q_tail += __popc(m);
+			__syncwarp();
+			if(q_tail - q_head >= 32) {
+				drain(q_head + lane, true);
+				q_head += 32;
+				__syncwarp();
+			}
+		}
 	}
+	if(q_tail > q_head)
+		drain(q_head + lane, lane < q_tail - q_head);
+	__syncwarp();
+}
+
+constexpr int HB_LIST_CAP = MAX_HBLOCK_TRIS;			  // per half-block list (HIGH), 8-byte records
+constexpr size_t HIGH_SCRATCH_BYTES = (size_t)32 * HB_LIST_CAP * 8;
+constexpr size_t LOW_SCRATCH_BYTES = (size_t)16 * MAX_BLOCK_TRIS * 16;
+
+struct BinShared {
+	int count[32]; // entries per half-block (HIGH) / block (LOW)
+	int holes[32]; // HIGH: columns inside a record's [first, last] range without coverage
+	int next_item, status, bin_index;
+	u32 frags, hbtris;
+};
+
+// LOW: a bin with fewer than 1024 triangles (raster_low.glsl); one warp per 8x8 block
+__device__ void rasterLowBin(const Params &p, const LucidConfig &cfg, int bin_id, uint4 *lists, BinShared &sh,
+							 unsigned char *smem) {
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const WarpScratch ws = warpScratch(smem + (size_t)warp * (WARP_SCRATCH_FIXED + MAX_BLOCK_TRIS * 4));
+	const BinInfo b = loadBin(p, bin_id);
+	if(tid < 32)
+		sh.count[tid] = 0;
+	if(tid == 0)
+		sh.next_item = 0, sh.status = 0, sh.frags = 0, sh.hbtris = 0;
 	__syncthreads();
 
-	// phase B: warp = block column (raster_low.glsl:81-194)
-	const int bx = warp;
-	int count = 0;
-	for(int q0 = 0; q0 < n_queue; q0 += 32) {
-		int q = q0 + lane;
-		int t = q < n_queue ? s_queue[q] : 0;
-		bool has = q < n_queue && ((s_rows[t].x >> (24 + bx)) & 1);
-		u32 m = __ballot_sync(0xffffffffu, has);
-		int pos = count + __popc(m & laneMaskLt());
-		if(has && pos < MAX_BLOCK_TRIS)
-			ws.keys[pos] = (u32)t;
-		count += __popc(m);
-	}
-	__syncwarp();
-	if(count > MAX_BLOCK_TRIS) {
+	binPhaseA<false>(p, b, reinterpret_cast<uint4 *>(ws.stage),
+					 [&](bool, u32 tri_idx, int g, u32 mn0, u32 mx0, u32 mn1, u32 mx1, u32 bx) {
+						 while(bx) {
+							 int c = __ffs(bx) - 1;
+							 bx &= bx - 1;
+							 int slot = atomicAdd(&sh.count[g * 4 + c], 1);
+							 if(slot < MAX_BLOCK_TRIS)
+								 lists[(g * 4 + c) * MAX_BLOCK_TRIS + slot] = make_uint4(
+									 tri_idx, packHalfRows(mn0, mx0, c * 8), packHalfRows(mn1, mx1, c * 8), 0u);
+						 }
+					 });
+	__syncthreads();
+	if(tid < 16 && sh.count[tid] > MAX_BLOCK_TRIS)
+		sh.status = 1;
+	__syncthreads();
+	if(sh.status != 0) {
 		// too many triangles for one block: the whole bin is redone by the HIGH path
 		// (raster_low.glsl:101-105,230-237)
-		if(lane == 0)
+		if(tid == 0)
 			atomicOr(&p.bin_flags[bin_id], 1u);
 		return;
 	}
-	const int startx = bx * 8;
-	u32 frag_acc = 0;
-	for(int i = lane; i < count; i += 32) {
-		u32 t = ws.keys[i];
-		uint4 rec = s_rows[t];
-		int nf0, cx0, cy0, nf1, cx1, cy1;
-		halfPixelMask(rec.x, rec.z, startx, nf0, cx0, cy0);
-		halfPixelMask(rec.y, rec.w, startx, nf1, cx1, cy1);
-		// both halves use row offsets 1,3,5,7 for the centroid, exactly as the reference does
-		float cx = float(cx0) + float(cx1), cy = float(cy0) + float(cy1);
-		float scale = __fdiv_rn(0.5f, float(nf0 + nf1));
-		float cpx = cx * scale + float(pos_x + bx * 8), cpy = cy * scale + float(pos_y + by * 8);
-		u32 depth = blockDepth(p, s_tri[t], cpx, cpy, float(0x3ffffe));
-		ws.keys[i] = t | (depth << 10);
-		frag_acc += (u32)nf0 | ((u32)nf1 << 16);
-	}
-	__syncwarp();
-	if(count > 3) { // blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
-		warpSortShared(ws.keys, count);
-		warpFixDepthTies(ws.keys, count, 10, [&](u32 t) { return s_tri[t]; });
-	}
-	__syncwarp();
 
-	auto getRow0 = [&](u32 slot, u32 &mins, u32 &maxs, u32 &tri) {
-		uint4 r = s_rows[slot];
-		mins = r.x, maxs = r.z, tri = s_tri[slot];
-	};
-	auto getRow1 = [&](u32 slot, u32 &mins, u32 &maxs, u32 &tri) {
-		uint4 r = s_rows[slot];
-		mins = r.y, maxs = r.w, tri = s_tri[slot];
-	};
-	u32 f0, f1;
-	shadeHalfBlock(p, cfg, ws, count, 0x3ff, startx, pos_x + bx * 8, pos_y + by * 8, getRow0, f0);
-	shadeHalfBlock(p, cfg, ws, count, 0x3ff, startx, pos_x + bx * 8, pos_y + by * 8 + 4, getRow1, f1);
-#pragma unroll
-	for(int o = 16; o > 0; o >>= 1)
-		frag_acc += __shfl_xor_sync(0xffffffffu, frag_acc, o);
-	if(lane == 0) {
-		// stats: fragments, and the block's triangle count once per half-block (raster_low.glsl:272-275)
-		atomicAdd(&p.bin_stats[bin_id * 4 + 0], (frag_acc & 0xffffu) + (frag_acc >> 16));
-		atomicAdd(&p.bin_stats[bin_id * 4 + 1], (u32)count * 2u);
+	// phase B (raster_low.glsl:81-194): blocks are handed to warps dynamically
+	u32 frag_acc = 0, hbt_acc = 0;
+	while(true) {
+		int blk = 0;
+		if(lane == 0)
+			blk = atomicAdd(&sh.next_item, 1);
+		blk = __shfl_sync(0xffffffffu, blk, 0);
+		if(blk >= 16)
+			break;
+		const int by = blk >> 2, bx = blk & 3;
+		const int count = sh.count[blk];
+		const uint4 *list = lists + blk * MAX_BLOCK_TRIS;
+		for(int i = lane; i < count; i += 32) {
+			uint4 rec = list[i];
+			int nf0, cx0, cy0, nf1, cx1, cy1;
+			rowsCentroid(rec.y, nf0, cx0, cy0);
+			rowsCentroid(rec.z, nf1, cx1, cy1);
+			// both halves use row offsets 1,3,5,7 for the centroid, exactly as the reference does
+			float cx = float(cx0) + float(cx1), cy = float(cy0) + float(cy1);
+			float scale = __fdiv_rn(0.5f, float(nf0 + nf1));
+			float cpx = cx * scale + float(b.pos_x + bx * 8), cpy = cy * scale + float(b.pos_y + by * 8);
+			u32 depth = blockDepth(p, rec.x, cpx, cpy, float(0x3ffffe));
+			ws.keys[i] = (u32)i | (depth << 10);
+			frag_acc += (u32)(nf0 + nf1);
+		}
+		hbt_acc += lane == 0 ? (u32)count * 2u : 0u; // the block's count once per half-block (raster_low.glsl:272-275)
+		__syncwarp();
+		if(count > 3) { // blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
+			warpSortShared<MAX_BLOCK_TRIS>(ws.keys, count);
+			warpFixDepthTies(ws.keys, count, 10, [&](u32 pos) { return list[pos].x; });
+		}
+		__syncwarp();
+		for(int half = 0; half < 2; half++) {
+			auto rec = [&](u32 pos, u32 &rows, u32 &tri) {
+				uint4 r = list[pos];
+				rows = half ? r.z : r.y, tri = r.x;
+			};
+			shadeHalfBlockAny(p, cfg, ws, count, 0x3ffu, b.pos_x + bx * 8, b.pos_y + by * 8 + half * 4, rec);
+			__syncwarp();
+		}
 	}
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) {
+		frag_acc += __shfl_xor_sync(0xffffffffu, frag_acc, o);
+		hbt_acc += __shfl_xor_sync(0xffffffffu, hbt_acc, o);
+	}
+	if(lane == 0) {
+		atomicAdd(&sh.frags, frag_acc);
+		atomicAdd(&sh.hbtris, hbt_acc);
+	}
+	__syncthreads();
+	if(tid == 0)
+		p.bin_stats[bin_id * 4 + 0] = sh.frags, p.bin_stats[bin_id * 4 + 1] = sh.hbtris;
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS) k_raster_low(const Params p,
-															   const __grid_constant__ LucidConfig cfg) {
+__global__ void __launch_bounds__(RASTER_THREADS, 3) k_raster_low(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
 	extern __shared__ __align__(16) unsigned char smem[];
+	__shared__ BinShared sh;
+	uint4 *lists = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.high_scratch) +
+											 (size_t)blockIdx.x * LOW_SCRATCH_BYTES);
 	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
-	const int item = blockIdx.x;
-	if(item >= n_low * 4)
-		return;
-	const int bin_id = cntc(p, LUCID_CNT_LOW_BINS)[item >> 2];
-	rasterLowItem(p, cfg, bin_id, item & 3, smem);
+	while(true) {
+		__syncthreads();
+		if(threadIdx.x == 0)
+			sh.bin_index = (int)atomicAdd(&p.work_counters[0], 1u);
+		__syncthreads();
+		const int idx = sh.bin_index;
+		if(idx >= n_low)
+			break;
+		rasterLowBin(p, cfg, cntc(p, LUCID_CNT_LOW_BINS)[idx], lists, sh, smem);
+	}
 }
 
 // appends promoted LOW bins to the HIGH list in bin order (raster_low.glsl:230-237,294-298)
@@ -760,194 +1024,130 @@ __global__ void __launch_bounds__(1024) k_promote(const Params p) {
 	}
 }
 
-// HIGH: one half-block row (4 pixel rows) of a dense bin (raster_high.glsl)
+// HIGH: a dense bin (raster_high.glsl); one warp per 8x4 half-block.  CAP is the longest
+// half-block list this instantiation sorts in shared memory; bins that need more are handed to
+// the CAP = 4096 instantiation (the reference's limit, raster_high.glsl:27).
 template <int CAP>
-__device__ void rasterHighItem(const Params &p, const LucidConfig &cfg, int item, uint4 *scratch,
-							   unsigned char *smem) {
-	constexpr int ROW_CAP = CAP * 4 < MAX_HBLOCK_ROW_TRIS ? CAP * 4 : MAX_HBLOCK_ROW_TRIS;
-	constexpr int QUEUE = RASTER_THREADS * 2;
-	unsigned char *s_bx = smem;									  // ROW_CAP bytes
-	u32 *s_warp = reinterpret_cast<u32 *>(smem + ROW_CAP);
-	__shared__ u32 s_queue[QUEUE];
-	__shared__ int s_qtail, s_row_count;
-	__shared__ int s_est[4], s_exact[4], s_status;
+__device__ void rasterHighBin(const Params &p, const LucidConfig &cfg, int bin_id, uint2 *lists, BinShared &sh,
+							  unsigned char *smem) {
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	WarpScratch ws;
-	ws.keys = s_warp + warp * (CAP + SAMPLE_BUF + 32);
-	ws.samples = ws.keys + CAP;
-	ws.mask = ws.samples + SAMPLE_BUF;
-
-	const int bin_id = cntc(p, LUCID_CNT_HIGH_BINS)[item >> 3], rby = item & 7;
-	const int n_q = cntc(p, LUCID_CNT_QUAD_COUNTS)[bin_id], q_off = cntc(p, LUCID_CNT_QUAD_OFFSETS)[bin_id];
-	const int n_t = cntc(p, LUCID_CNT_TRI_COUNTS)[bin_id], t_off = cntc(p, LUCID_CNT_TRI_OFFSETS)[bin_id];
-	const int n_T = n_q * 2 + n_t;
-	const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
-	const int pos_x = bin_x * BIN_SIZE, pos_y = bin_y * BIN_SIZE;
-
-	if(tid < 4)
-		s_est[tid] = 0, s_exact[tid] = 0;
-	if(tid == 0) {
-		s_status = (p.bin_flags[bin_id] & 2u) ? 2 : 0;
-		s_qtail = 0, s_row_count = 0;
-	}
+	const WarpScratch ws = warpScratch(smem + (size_t)warp * (WARP_SCRATCH_FIXED + CAP * 4));
+	const BinInfo b = loadBin(p, bin_id);
+	if(tid < 32)
+		sh.count[tid] = 0, sh.holes[tid] = 0;
+	if(tid == 0)
+		sh.next_item = 0, sh.status = (p.bin_flags[bin_id] & 2u) ? 2 : 0, sh.frags = 0, sh.hbtris = 0;
 	__syncthreads();
-	if(s_status != 0)
-		return; // another item already found the bin over a limit
 
-	// phase A (raster_high.glsl:54-106).  A1 queues the triangles whose y range reaches this
-	// half-block row; A2 evaluates 128 queued triangles at a time with every lane busy and appends
-	// the non-empty ones to the row list.  List order does not matter (see warpFixDepthTies).
-	int est[4] = {0, 0, 0, 0}, exact[4] = {0, 0, 0, 0};
-	int qhead = 0;
-	auto evaluate = [&](int qi, bool active) {
-		u32 mn = 0, mx = 0, bx = 0, tri_idx = 0;
-		if(active) {
-			tri_idx = s_queue[qi & (QUEUE - 1)];
-			RowScan rs;
-			if(rowScanAt<4>(p, tri_idx, pos_x, pos_y, rby, rs))
-				rasterBinStep(rs, mn, mx, bx);
-		}
-		bool has = bx != 0;
-		u32 m = __ballot_sync(0xffffffffu, has);
-		int base = 0;
-		if(lane == 0 && m)
-			base = atomicAdd(&s_row_count, __popc(m));
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if(has) {
-			int slot = base + __popc(m & laneMaskLt());
-			if(slot < ROW_CAP) {
-				scratch[slot] = make_uint4(mn, mx, tri_idx, bx);
-				s_bx[slot] = (unsigned char)bx;
-			}
-			// estimated (first..last column, holes included) and exact per-half-block counts
-			int lo = __ffs(bx) - 1, hi = 31 - __clz(bx);
-#pragma unroll
-			for(int c = 0; c < 4; c++) {
-				est[c] += (c >= lo && c <= hi) ? 1 : 0;
-				exact[c] += (bx >> c) & 1;
+	// phase A (raster_high.glsl:54-144)
+	binPhaseA<true>(p, b, reinterpret_cast<uint4 *>(ws.stage),
+					[&](bool, u32 tri_idx, int g, u32 mn, u32 mx, u32, u32, u32 bx) {
+						if(bx == 0)
+							return;
+						const int lo = __ffs(bx) - 1, hi = 31 - __clz(bx);
+						u32 holes = ((2u << hi) - (1u << lo)) & ~bx;
+						while(bx) {
+							int c = __ffs(bx) - 1;
+							bx &= bx - 1;
+							int slot = atomicAdd(&sh.count[g * 4 + c], 1);
+							if(slot < HB_LIST_CAP)
+								lists[(g * 4 + c) * HB_LIST_CAP + slot] = make_uint2(tri_idx, packHalfRows(mn, mx, c * 8));
+						}
+						while(holes) {
+							int c = __ffs(holes) - 1;
+							holes &= holes - 1;
+							atomicAdd(&sh.holes[g * 4 + c], 1);
+						}
+					});
+	__syncthreads();
+	if(tid < 32) {
+		// the reference's limit is on the estimated count (first..last column, holes included):
+		// more than 4096 paints the bin red (raster_high.glsl:80-83,140-141).  16384 records in one
+		// half-block row imply more than 4096 in one of its half-blocks, so that limit is covered.
+		int exact = sh.count[tid], est = exact + sh.holes[tid];
+		bool over = __any_sync(0xffffffffu, est > MAX_HBLOCK_TRIS);
+		bool big = __any_sync(0xffffffffu, exact > CAP);
+		if(tid == 0) {
+			if(over) {
+				atomicOr(&p.bin_flags[bin_id], 2u);
+				sh.status = 2;
+			} else if(big) {
+				int idx = atomicAdd(&p.work_counters[3], 1u);
+				p.deferred_items[idx] = bin_id;
+				sh.status = 1;
 			}
 		}
-	};
-	for(int t0 = 0; t0 < n_T; t0 += RASTER_THREADS) {
-		int t = t0 + tid;
-		u32 tri_idx = 0;
-		bool pass = t < n_T && binTriangle(p, t, n_q, q_off, t_off, tri_idx);
-		pass = pass && touchesGroup(p, tri_idx, pos_y, rby, 2);
-		u32 m = __ballot_sync(0xffffffffu, pass);
-		int base = 0;
-		if(lane == 0 && m)
-			base = atomicAdd(&s_qtail, __popc(m));
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if(pass)
-			s_queue[(base + __popc(m & laneMaskLt())) & (QUEUE - 1)] = tri_idx;
-		__syncthreads();
-		if(s_qtail - qhead >= RASTER_THREADS) {
-			evaluate(qhead + tid, true);
-			qhead += RASTER_THREADS;
-		}
-		__syncthreads();
-	}
-	{
-		int rest = s_qtail - qhead;
-		evaluate(qhead + tid, tid < rest);
-	}
-#pragma unroll
-	for(int c = 0; c < 4; c++) {
-		int e = est[c], x = exact[c];
-#pragma unroll
-		for(int o = 16; o > 0; o >>= 1) {
-			e += __shfl_xor_sync(0xffffffffu, e, o);
-			x += __shfl_xor_sync(0xffffffffu, x, o);
-		}
-		if(lane == 0) {
-			atomicAdd(&s_est[c], e);
-			atomicAdd(&s_exact[c], x);
-		}
 	}
 	__syncthreads();
-	const int row_count = s_row_count;
-	if(tid == 0) {
-		int max_est = max(max(s_est[0], s_est[1]), max(s_est[2], s_est[3]));
-		int max_exact = max(max(s_exact[0], s_exact[1]), max(s_exact[2], s_exact[3]));
-		if(row_count > MAX_HBLOCK_ROW_TRIS || max_est > MAX_HBLOCK_TRIS) {
-			// over the reference's limits: the bin is painted red (raster_high.glsl:80-83,140-141)
-			atomicOr(&p.bin_flags[bin_id], 2u);
-			s_status = 2;
-		} else if(row_count > ROW_CAP || max_exact > CAP) {
-			// does not fit this kernel's shared memory: hand the item to the large variant
-			int idx = atomicAdd(&p.work_counters[3], 1u);
-			p.deferred_items[idx] = item;
-			s_status = 1;
-		}
-	}
-	__syncthreads();
-	if(s_status != 0)
+	if(sh.status != 0)
 		return;
 
-	// phase B: warp = half-block column (raster_high.glsl:146-273)
-	const int hbx = warp;
-	int count = 0;
-	for(int s0 = 0; s0 < row_count; s0 += 32) {
-		int sl = s0 + lane;
-		bool has = sl < row_count && ((s_bx[sl] >> hbx) & 1);
-		u32 m = __ballot_sync(0xffffffffu, has);
-		if(has)
-			ws.keys[count + __popc(m & laneMaskLt())] = (u32)sl;
-		count += __popc(m);
+	// phase B (raster_high.glsl:146-273): half-blocks are handed to warps dynamically
+	u32 frag_acc = 0, hbt_acc = 0;
+	while(true) {
+		int hb = 0;
+		if(lane == 0)
+			hb = atomicAdd(&sh.next_item, 1);
+		hb = __shfl_sync(0xffffffffu, hb, 0);
+		if(hb >= 32)
+			break;
+		const int rby = hb >> 2, hbx = hb & 3;
+		const int count = sh.count[hb];
+		const uint2 *list = lists + hb * HB_LIST_CAP;
+		for(int i = lane; i < count; i += 32) {
+			uint2 rec = list[i];
+			int nf, cx, cy;
+			rowsCentroid(rec.y, nf, cx, cy);
+			float scale = __fdiv_rn(0.5f, float(nf));
+			float cpx = float(cx) * scale + (float(hbx * 8) + float(b.pos_x));
+			float cpy = float(cy) * scale + (float(rby * 4) + float(b.pos_y));
+			u32 depth = blockDepth(p, rec.x, cpx, cpy, float(0x7fffe));
+			ws.keys[i] = (u32)i | (depth << 14);
+			frag_acc += (u32)nf;
+		}
+		hbt_acc += lane == 0 ? (u32)count : 0u; // exact per-half-block counts (raster_high.glsl:309-310)
+		__syncwarp();
+		warpSortShared<CAP>(ws.keys, count);
+		warpFixDepthTies(ws.keys, count, 14, [&](u32 pos) { return list[pos].x; });
+		__syncwarp();
+		auto rec = [&](u32 pos, u32 &rows, u32 &tri) {
+			uint2 r = list[pos];
+			rows = r.y, tri = r.x;
+		};
+		shadeHalfBlockAny(p, cfg, ws, count, 0x3fffu, b.pos_x + hbx * 8, b.pos_y + rby * 4, rec);
+		__syncwarp();
 	}
-	__syncwarp();
-	const int startx = hbx * 8;
-	u32 fsum = 0;
-	for(int i = lane; i < count; i += 32) {
-		u32 slot = ws.keys[i];
-		uint4 rec = scratch[slot];
-		int nf, cx, cy;
-		halfPixelMask(rec.x, rec.y, startx, nf, cx, cy);
-		float scale = __fdiv_rn(0.5f, float(nf));
-		float cpx = float(cx) * scale + (float(hbx * 8) + float(pos_x));
-		float cpy = float(cy) * scale + (float(rby * 4) + float(pos_y));
-		u32 depth = blockDepth(p, rec.z, cpx, cpy, float(0x7fffe));
-		ws.keys[i] = slot | (depth << 14);
-		fsum += (u32)nf;
-	}
-	__syncwarp();
-	warpSortShared(ws.keys, count);
-	warpFixDepthTies(ws.keys, count, 14, [&](u32 slot) { return scratch[slot].z; });
-	__syncwarp();
-	auto getRow = [&](u32 slot, u32 &mins, u32 &maxs, u32 &tri) {
-		uint4 r = scratch[slot];
-		mins = r.x, maxs = r.y, tri = r.z;
-	};
-	u32 frags;
-	shadeHalfBlock(p, cfg, ws, count, 0x3fff, startx, pos_x + hbx * 8, pos_y + rby * 4, getRow, frags);
 #pragma unroll
-	for(int o = 16; o > 0; o >>= 1)
-		fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
-	if(lane == 0) {
-		// exact per-half-block counts (raster_high.glsl:309-310)
-		atomicAdd(&p.bin_stats[bin_id * 4 + 2], fsum);
-		atomicAdd(&p.bin_stats[bin_id * 4 + 3], (u32)count);
+	for(int o = 16; o > 0; o >>= 1) {
+		frag_acc += __shfl_xor_sync(0xffffffffu, frag_acc, o);
+		hbt_acc += __shfl_xor_sync(0xffffffffu, hbt_acc, o);
 	}
+	if(lane == 0) {
+		atomicAdd(&sh.frags, frag_acc);
+		atomicAdd(&sh.hbtris, hbt_acc);
+	}
+	__syncthreads();
+	if(tid == 0)
+		p.bin_stats[bin_id * 4 + 2] = sh.frags, p.bin_stats[bin_id * 4 + 3] = sh.hbtris;
 }
 
-template <int CAP, bool DEFERRED>
-__global__ void __launch_bounds__(RASTER_THREADS) k_raster_high(const Params p,
-																const __grid_constant__ LucidConfig cfg) {
+template <int CAP, bool DEFERRED, int MIN_CTAS>
+__global__ void __launch_bounds__(RASTER_THREADS, MIN_CTAS) k_raster_high(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
 	extern __shared__ __align__(16) unsigned char smem[];
-	__shared__ int s_item;
-	constexpr int ROW_CAP = CAP * 4 < MAX_HBLOCK_ROW_TRIS ? CAP * 4 : MAX_HBLOCK_ROW_TRIS;
-	uint4 *scratch = p.high_scratch + (size_t)blockIdx.x * ROW_CAP;
-	const int n_items = DEFERRED ? (int)p.work_counters[3] : p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH] * 8;
+	__shared__ BinShared sh;
+	uint2 *lists = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(p.high_scratch) +
+											 (size_t)blockIdx.x * HIGH_SCRATCH_BYTES);
+	const int n_items = DEFERRED ? (int)p.work_counters[3] : p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH];
 	while(true) {
 		__syncthreads();
 		if(threadIdx.x == 0)
-			s_item = (int)atomicAdd(&p.work_counters[DEFERRED ? 2 : 1], 1u);
+			sh.bin_index = (int)atomicAdd(&p.work_counters[DEFERRED ? 2 : 1], 1u);
 		__syncthreads();
-		int idx = s_item;
+		const int idx = sh.bin_index;
 		if(idx >= n_items)
 			break;
-		int item = DEFERRED ? p.deferred_items[idx] : idx;
-		rasterHighItem<CAP>(p, cfg, item, scratch, smem);
+		const int bin_id = DEFERRED ? p.deferred_items[idx] : cntc(p, LUCID_CNT_HIGH_BINS)[idx];
+		rasterHighBin<CAP>(p, cfg, bin_id, lists, sh, smem);
 	}
 }
 
@@ -989,31 +1189,40 @@ __global__ void __launch_bounds__(256) k_raster_finish(const Params p, u32 backg
 	}
 }
 
-constexpr int lowSmemBytes() { return LOW_MAX_TRIS * 22 + RASTER_WARPS * (MAX_BLOCK_TRIS + SAMPLE_BUF + 32) * 4; }
-template <int CAP> constexpr int highSmemBytes() {
-	return (CAP * 4 < MAX_HBLOCK_ROW_TRIS ? CAP * 4 : MAX_HBLOCK_ROW_TRIS) + RASTER_WARPS * (CAP + SAMPLE_BUF + 32) * 4;
-}
+constexpr int HIGH_SMALL_CAP = 1024;
+constexpr int lowSmemBytes() { return RASTER_WARPS * (WARP_SCRATCH_FIXED + MAX_BLOCK_TRIS * 4); }
+template <int CAP> constexpr int highSmemBytes() { return RASTER_WARPS * (WARP_SCRATCH_FIXED + CAP * 4); }
 
-int rasterHighGridSmall(int num_sms) { return num_sms * 8; }
-int rasterHighGridLarge(int num_sms) { return num_sms * 2; }
+static int rasterLowGrid(int num_sms) { return num_sms * 4; }
+static int rasterHighGridSmall(int num_sms) { return num_sms * 3; }
+static int rasterHighGridLarge(int num_sms) { return num_sms; }
+
+size_t rasterScratchBytes(int num_sms) {
+	size_t low = (size_t)rasterLowGrid(num_sms) * LOW_SCRATCH_BYTES;
+	size_t high = (size_t)rasterHighGridSmall(num_sms) * HIGH_SCRATCH_BYTES;
+	size_t large = (size_t)rasterHighGridLarge(num_sms) * HIGH_SCRATCH_BYTES;
+	return low > high ? (low > large ? low : large) : (high > large ? high : large);
+}
 
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, cudaEvent_t *ev,
 				  int num_sms) {
 	static bool configured = false;
 	if(!configured) {
 		cudaFuncSetAttribute(k_raster_low, cudaFuncAttributeMaxDynamicSharedMemorySize, lowSmemBytes());
-		cudaFuncSetAttribute(k_raster_high<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-							 highSmemBytes<1024>());
-		cudaFuncSetAttribute(k_raster_high<4096, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-							 highSmemBytes<4096>());
+		cudaFuncSetAttribute(k_raster_high<HIGH_SMALL_CAP, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+							 highSmemBytes<HIGH_SMALL_CAP>());
+		cudaFuncSetAttribute(k_raster_high<MAX_HBLOCK_TRIS, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+							 highSmemBytes<MAX_HBLOCK_TRIS>());
 		configured = true;
 	}
-	k_raster_low<<<p.bin_count * 4, RASTER_THREADS, lowSmemBytes(), stream>>>(p, cfg);
+	k_raster_low<<<rasterLowGrid(num_sms), RASTER_THREADS, lowSmemBytes(), stream>>>(p, cfg);
 	k_promote<<<1, 1024, 0, stream>>>(p);
 	if(ev)
 		cudaEventRecord(ev[0], stream);
-	k_raster_high<1024, false><<<rasterHighGridSmall(num_sms), RASTER_THREADS, highSmemBytes<1024>(), stream>>>(p, cfg);
-	k_raster_high<4096, true><<<rasterHighGridLarge(num_sms), RASTER_THREADS, highSmemBytes<4096>(), stream>>>(p, cfg);
+	k_raster_high<HIGH_SMALL_CAP, false, 3>
+		<<<rasterHighGridSmall(num_sms), RASTER_THREADS, highSmemBytes<HIGH_SMALL_CAP>(), stream>>>(p, cfg);
+	k_raster_high<MAX_HBLOCK_TRIS, true, 1>
+		<<<rasterHighGridLarge(num_sms), RASTER_THREADS, highSmemBytes<MAX_HBLOCK_TRIS>(), stream>>>(p, cfg);
 	if(ev)
 		cudaEventRecord(ev[1], stream);
 	const LucidVec4 &bg = cfg.background_color;
