@@ -228,8 +228,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_bin_scan(const Params p) {
 		else
 			high[off_high++] = b;
 		p.bin_flags[b] = 0;
-		p.bin_stats[b * 4 + 0] = p.bin_stats[b * 4 + 1] = 0;
-		p.bin_stats[b * 4 + 2] = p.bin_stats[b * 4 + 3] = 0;
 	}
 	if(threadIdx.x == 0) {
 		LucidInfo *info = p.info;
@@ -253,7 +251,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_bin_scan(const Params p) {
 		// list capacity check: the reference sizes both lists at 2 * MAX_VISIBLE_QUADS and never checks
 		if((u32)tot_q > p.bin_list_capacity || (u32)tot_t > p.bin_list_capacity)
 			info->temp[1] = 1;
-		p.work_counters[0] = p.work_counters[1] = p.work_counters[2] = p.work_counters[3] = 0;
+		for(int i = 0; i < 8; i++)
+			p.work_counters[i] = 0;
 	}
 }
 

@@ -192,10 +192,12 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.setup_lookback, (size_t)LUCID_MAX_INSTANCES * 4));
 	CUC(devAlloc(r, &p.setup_ticket, 4));
 	CUC(devAlloc(r, &p.bin_flags, (size_t)p.bin_count));
-	CUC(devAlloc(r, &p.bin_stats, (size_t)p.bin_count * 4));
 	CUC(devAlloc(r, &p.work_counters, 8));
-	CUC(devAlloc(r, &p.deferred_items, (size_t)p.bin_count * 8));
-	CUC(devAlloc(r, &p.high_scratch, rasterScratchBytes(r->num_sms) / sizeof(uint4)));
+	CUC(devAlloc(r, &p.block_lists, (size_t)p.bin_count * (BIN_LIST_BYTES / sizeof(uint4))));
+	CUC(devAlloc(r, &p.block_counts, (size_t)p.bin_count * 32));
+	p.block_items_cap = (u32)p.bin_count * 32u;
+	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 2));
+	CUC(devAlloc(r, &p.large_keys, rasterLargeKeysCount(r->num_sms)));
 	CUC(devAlloc(r, &r->image, (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->frag_counts, (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->d_instances, (size_t)LUCID_MAX_INSTANCES));

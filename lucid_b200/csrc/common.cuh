@@ -77,11 +77,13 @@ struct Params {
 	u32 *image;			  // RGBA8, pitch in pixels
 	int image_pitch;
 	u32 *frag_counts;	  // optional per-pixel fragment counts (debug / parity), may be null
-	u32 *bin_flags;		  // per bin: bit 0 promoted LOW->HIGH, bit 1 HIGH error
-	u32 *bin_stats;		  // per bin: [0] LOW frags [1] LOW hbtris [2] HIGH frags [3] HIGH hbtris
-	u32 *work_counters;	  // [0] low items [1] high items [2] high-big items [3] deferred count
-	int *deferred_items;  // HIGH bins that need the large-capacity kernel
-	uint4 *high_scratch;  // per persistent raster CTA: the half-block / block lists of its current bin
+	u32 *bin_flags;		  // per bin: bit 0 promoted LOW->HIGH, bit 1 over the reference's HIGH limits (red)
+	u32 *work_counters;	  // [0] bins taken [1] heavy items taken [2] light items taken [3] heavy items [4] light items
+	uint4 *block_lists;	  // per bin BIN_LIST_BYTES: 32 half-block lists (HIGH) or 16 block lists (LOW)
+	int *block_counts;	  // 32 per bin: entries of each list
+	u32 *block_items;	  // work items of k_raster_blocks: heavy at [0, cap), light at [cap, 2 cap)
+	u32 block_items_cap;
+	u32 *large_keys;	  // per k_raster_blocks warp: sort keys of lists too long for shared memory
 	// textures: level offsets into one RGBA8 array per slot
 	const uchar4 *tex_data[2];
 	int tex_width[2], tex_height[2], tex_levels[2];
@@ -221,6 +223,10 @@ void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t strea
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *stage_events);
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream,
 				  cudaEvent_t *stage_events, int num_sms);
-size_t rasterScratchBytes(int num_sms);
+size_t rasterLargeKeysCount(int num_sms);
+
+// 32 half-block lists of up to 4096 8-byte records (raster_high.glsl:27); a LOW bin uses the first
+// 16 x 256 16-byte records
+constexpr size_t BIN_LIST_BYTES = (size_t)32 * 4096 * 8;
 
 } // namespace lucid

@@ -24,7 +24,6 @@ constexpr int SEGMENT_SIZE = 256;
 constexpr int SAMPLE_BUF = SEGMENT_SIZE + 32;
 constexpr int MAX_BLOCK_TRIS = 256;		 // raster_low.glsl:17
 constexpr int MAX_HBLOCK_TRIS = 4096;	 // raster_high.glsl:27
-constexpr int MAX_HBLOCK_ROW_TRIS = 16384; // raster_high.glsl:30
 
 __device__ __forceinline__ const int *cntc(const Params &p, int which) {
 	return p.counts + (size_t)which * p.bin_count;
@@ -334,8 +333,45 @@ template <int K> __device__ __forceinline__ void sortSingleTile(u32 *keys, int n
 	}
 }
 
-// keys[0..n) ascending; the array has room for n rounded up to a power of two
-template <int CAP> __device__ void warpSortShared(u32 *keys, int n) {
+// compare-exchange steps of a merge level whose partner distance is at least one tile (256 keys)
+__device__ __forceinline__ void mirrorStep(u32 *keys, int padded, int k, u32 lane) {
+	const int half = k >> 1;
+	for(int i = lane; i < (padded >> 1); i += 32) {
+		int blk = i / half, idx = i - blk * half;
+		int lo = blk * k + idx, hi = blk * k + (k - 1 - idx);
+		u32 a = keys[lo], b = keys[hi];
+		if(a > b)
+			keys[lo] = b, keys[hi] = a;
+	}
+	__syncwarp();
+}
+__device__ __forceinline__ void distanceStep(u32 *keys, int padded, int j, u32 lane) {
+	for(int i = lane; i < (padded >> 1); i += 32) {
+		int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+		u32 a = keys[lo], b = keys[hi];
+		if(a > b)
+			keys[lo] = b, keys[hi] = a;
+	}
+	__syncwarp();
+}
+// the remaining steps (distance 128..1) of every 256-key tile, or a full sort of every tile
+template <bool FULL_SORT> __device__ __forceinline__ void tileSteps(u32 *keys, int padded, u32 lane) {
+	uint4 *tiles = reinterpret_cast<uint4 *>(keys);
+	for(int base = 0; base < padded; base += 256) {
+		uint4 a = tiles[(base >> 2) + lane * 2], b = tiles[(base >> 2) + lane * 2 + 1];
+		u32 v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+		if(FULL_SORT)
+			sortRegs<8>(v, lane);
+		else
+			sortRegsMergeSteps<8>(v, 128, lane);
+		tiles[(base >> 2) + lane * 2] = make_uint4(v[0], v[1], v[2], v[3]);
+		tiles[(base >> 2) + lane * 2 + 1] = make_uint4(v[4], v[5], v[6], v[7]);
+	}
+	__syncwarp();
+}
+
+// keys[0..n) ascending in shared memory; the array has room for n rounded up to a power of two
+__device__ void warpSortShared(u32 *keys, int n) {
 	const u32 lane = laneId();
 	if(n <= 1)
 		return;
@@ -347,82 +383,110 @@ template <int CAP> __device__ void warpSortShared(u32 *keys, int n) {
 		sortSingleTile<4>(keys, n, lane);
 	else if(n <= 256)
 		sortSingleTile<8>(keys, n, lane);
-	else if(CAP > 256) {
+	else {
 		int padded = 512;
 		while(padded < n)
 			padded <<= 1;
 		for(int i = n + lane; i < padded; i += 32)
 			keys[i] = 0xffffffffu;
 		__syncwarp();
-		uint4 *tiles = reinterpret_cast<uint4 *>(keys);
-		for(int base = 0; base < padded; base += 256) {
-			uint4 a = tiles[(base >> 2) + lane * 2], b = tiles[(base >> 2) + lane * 2 + 1];
-			u32 v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-			sortRegs<8>(v, lane);
-			tiles[(base >> 2) + lane * 2] = make_uint4(v[0], v[1], v[2], v[3]);
-			tiles[(base >> 2) + lane * 2 + 1] = make_uint4(v[4], v[5], v[6], v[7]);
-		}
-		__syncwarp();
+		tileSteps<true>(keys, padded, lane);
 		for(int k = 512; k <= padded; k <<= 1) {
-			const int half = k >> 1;
-			for(int i = lane; i < (padded >> 1); i += 32) {
-				int blk = i / half, idx = i - blk * half;
-				int lo = blk * k + idx, hi = blk * k + (k - 1 - idx);
-				u32 a = keys[lo], b = keys[hi];
-				if(a > b)
-					keys[lo] = b, keys[hi] = a;
-			}
-			__syncwarp();
-			for(int j = k >> 2; j >= 256; j >>= 1) {
-				for(int i = lane; i < (padded >> 1); i += 32) {
-					int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
-					u32 a = keys[lo], b = keys[hi];
-					if(a > b)
-						keys[lo] = b, keys[hi] = a;
-				}
-				__syncwarp();
-			}
-			for(int base = 0; base < padded; base += 256) {
-				uint4 a = tiles[(base >> 2) + lane * 2], b = tiles[(base >> 2) + lane * 2 + 1];
-				u32 v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-				sortRegsMergeSteps<8>(v, 128, lane);
-				tiles[(base >> 2) + lane * 2] = make_uint4(v[0], v[1], v[2], v[3]);
-				tiles[(base >> 2) + lane * 2 + 1] = make_uint4(v[4], v[5], v[6], v[7]);
-			}
-			__syncwarp();
+			mirrorStep(keys, padded, k, lane);
+			for(int j = k >> 2; j >= 256; j >>= 1)
+				distanceStep(keys, padded, j, lane);
+			tileSteps<false>(keys, padded, lane);
 		}
 	}
 	__syncwarp();
 }
 
-// Entries with equal quantised depth are ordered by triangle index.  The low key bits only make
-// keys unique (they are list positions that depend on atomic arrival order); this pass makes the
-// final order -- and therefore the image -- independent of them.  Ties are rare and short.
-template <typename TriOf>
-__device__ void warpFixDepthTies(u32 *keys, int n, int slot_bits, TriOf triOf) {
-	const int lane = laneId();
-	const u32 slot_mask = (1u << slot_bits) - 1u;
-	bool tie = false;
-	for(int i = lane; i + 1 < n; i += 32)
-		tie = tie || (keys[i] >> slot_bits) == (keys[i + 1] >> slot_bits);
-	if(!__any_sync(0xffffffffu, tie))
-		return;
-	while(true) {
-		bool swapped = false;
-#pragma unroll
-		for(int parity = 0; parity < 2; parity++) {
-			for(int i = 2 * lane + parity; i + 1 < n; i += 64) {
-				u32 a = keys[i], b = keys[i + 1];
-				if((a >> slot_bits) == (b >> slot_bits) && triOf(a & slot_mask) > triOf(b & slot_mask)) {
-					keys[i] = b, keys[i + 1] = a;
-					swapped = true;
-				}
+// Lists longer than the shared-memory key array (up to the reference's 4096 per half-block) are
+// sorted in an L2-resident global array: 1024-key blocks are staged through shared memory, only
+// the steps with a partner distance of 1024 or more touch global memory directly.
+constexpr int SMEM_KEYS = 1024;
+__device__ __noinline__ void warpSortLarge(u32 *gkeys, int n, u32 *skeys) {
+	const u32 lane = laneId();
+	int padded = 2 * SMEM_KEYS;
+	while(padded < n)
+		padded <<= 1;
+	for(int i = n + lane; i < padded; i += 32)
+		gkeys[i] = 0xffffffffu;
+	__syncwarp();
+	auto stage = [&](int base, bool load) {
+		for(int i = lane; i < SMEM_KEYS; i += 32) {
+			if(load)
+				skeys[i] = __ldcg(gkeys + base + i);
+			else
+				__stcg(gkeys + base + i, skeys[i]);
+		}
+		__syncwarp();
+	};
+	for(int base = 0; base < padded; base += SMEM_KEYS) {
+		stage(base, true);
+		warpSortShared(skeys, SMEM_KEYS);
+		stage(base, false);
+	}
+	for(int k = 2 * SMEM_KEYS; k <= padded; k <<= 1) {
+		const int half = k >> 1;
+		for(int i = lane; i < (padded >> 1); i += 32) {
+			int blk = i / half, idx = i - blk * half;
+			int lo = blk * k + idx, hi = blk * k + (k - 1 - idx);
+			u32 a = __ldcg(gkeys + lo), b = __ldcg(gkeys + hi);
+			if(a > b)
+				__stcg(gkeys + lo, b), __stcg(gkeys + hi, a);
+		}
+		__syncwarp();
+		for(int j = k >> 2; j >= SMEM_KEYS; j >>= 1) {
+			for(int i = lane; i < (padded >> 1); i += 32) {
+				int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+				u32 a = __ldcg(gkeys + lo), b = __ldcg(gkeys + hi);
+				if(a > b)
+					__stcg(gkeys + lo, b), __stcg(gkeys + hi, a);
 			}
 			__syncwarp();
 		}
-		if(!__any_sync(0xffffffffu, swapped))
-			break;
+		for(int base = 0; base < padded; base += SMEM_KEYS) {
+			stage(base, true);
+			distanceStep(skeys, SMEM_KEYS, 512, lane);
+			distanceStep(skeys, SMEM_KEYS, 256, lane);
+			tileSteps<false>(skeys, SMEM_KEYS, lane);
+			stage(base, false);
+		}
 	}
+}
+
+// Entries with equal quantised depth are ordered by triangle index.  The low key bits only make
+// keys unique (they are list positions that depend on atomic arrival order); this pass makes the
+// final order -- and therefore the image -- independent of them.  Runs of equal depth are rare and
+// short: the lane that finds the start of a run sorts it by insertion.
+template <typename TriOf> __device__ void warpFixDepthTies(u32 *keys, int n, int slot_bits, TriOf triOf) {
+	const int lane = laneId();
+	const u32 slot_mask = (1u << slot_bits) - 1u;
+	for(int i0 = 0; i0 + 1 < n; i0 += 32) {
+		const int i = i0 + lane;
+		bool start = false;
+		if(i + 1 < n) {
+			u32 d = keys[i] >> slot_bits;
+			start = d == (keys[i + 1] >> slot_bits) && (i == 0 || d != (keys[i - 1] >> slot_bits));
+		}
+		if(start) {
+			const u32 d = keys[i] >> slot_bits;
+			for(int e = i + 1; e < n && (keys[e] >> slot_bits) == d; e++) {
+				u32 ke = keys[e], te = triOf(ke & slot_mask);
+				int q = e;
+				while(q > i) {
+					u32 kq = keys[q - 1];
+					if(triOf(kq & slot_mask) <= te)
+						break;
+					keys[q] = kq;
+					q--;
+				}
+				keys[q] = ke;
+			}
+		}
+	}
+	__syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -481,6 +545,23 @@ __device__ __forceinline__ u32 transpose32(u32 x) {
 		x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
 	}
 	return x;
+}
+
+// a block's record list: HIGH 8-byte records (tri, rows), LOW 16-byte records (tri, rows of the
+// upper half, rows of the lower half, 0)
+struct RecList {
+	const unsigned char *base;
+	bool wide;	// 16-byte records
+	bool lower; // take the lower half's rows
+};
+__device__ __forceinline__ void recAt(const RecList &l, u32 pos, u32 &rows, u32 &tri) {
+	if(l.wide) {
+		uint4 r = __ldg(reinterpret_cast<const uint4 *>(l.base) + pos);
+		tri = r.x, rows = l.lower ? r.z : r.y;
+	} else {
+		uint2 r = __ldg(reinterpret_cast<const uint2 *>(l.base) + pos);
+		tri = r.x, rows = r.y;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -550,9 +631,8 @@ __device__ __forceinline__ void writePixel(const Params &p, const LucidConfig &c
 // final value is saturated -- so segments only matter for the alpha-threshold early out, which
 // keeps the segment-accurate path below.  Once every pixel of the half-block has zero
 // transmittance, later samples add exactly +0 and are skipped.
-template <typename GetRec>
-__device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const WarpScratch &ws, int count,
-							   u32 pos_mask, int hb_x, int hb_y, GetRec getRec) {
+__device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const WarpScratch &ws, const u32 *keys,
+							   int count, u32 pos_mask, int hb_x, int hb_y, const RecList &list) {
 	const int lane = laneId();
 	const bool additive = (p.opts & LUCID_OPT_ADDITIVE_BLENDING) != 0;
 	const bool vis_errors = (p.opts & LUCID_OPT_VISUALIZE_ERRORS) != 0;
@@ -567,7 +647,7 @@ __device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const Wa
 		u32 rows = 0, tri_idx = 0, bits = 0;
 		int nf = 0;
 		if(i < count) {
-			getRec(ws.keys[i] & pos_mask, rows, tri_idx);
+			recAt(list, keys[i] & pos_mask, rows, tri_idx);
 			bits = rowsToBits(rows, nf);
 		}
 		int incl = nf;
@@ -647,9 +727,9 @@ __device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const Wa
 // Segment-accurate variant (raster.glsl:292-396) for ALPHA_THRESHOLD: samples are expanded and
 // consumed in the reference's 256-sample segments, so the early-out decisions fall on the same
 // sample boundaries.
-template <typename GetRec>
 __device__ __noinline__ void shadeHalfBlockSegments(const Params &p, const LucidConfig &cfg, const WarpScratch &ws,
-													int count, u32 pos_mask, int hb_x, int hb_y, GetRec getRec) {
+													const u32 *keys, int count, u32 pos_mask, int hb_x, int hb_y,
+													const RecList &list) {
 	const int lane = laneId();
 	Reducer red;
 	reducerInit(red);
@@ -674,7 +754,7 @@ __device__ __noinline__ void shadeHalfBlockSegments(const Params &p, const Lucid
 			u32 rows = 0, tri_idx = 0, bits = 0;
 			int nf = 0;
 			if(i < count) {
-				getRec(ws.keys[i] & pos_mask, rows, tri_idx);
+				recAt(list, keys[i] & pos_mask, rows, tri_idx);
 				bits = rowsToBits(rows, nf);
 			}
 			int incl = nf;
@@ -745,15 +825,15 @@ __device__ __noinline__ void shadeHalfBlockSegments(const Params &p, const Lucid
 	writePixel(p, cfg, red, hb_x, hb_y, px_frags, false, false);
 }
 
-template <typename GetRec>
 __device__ __forceinline__ void shadeHalfBlockAny(const Params &p, const LucidConfig &cfg, const WarpScratch &ws,
-												 int count, u32 pos_mask, int hb_x, int hb_y, GetRec getRec) {
+												 const u32 *keys, int count, u32 pos_mask, int hb_x, int hb_y,
+												 const RecList &list) {
 	const bool alpha_thr = (p.opts & (LUCID_OPT_ALPHA_THRESHOLD | LUCID_OPT_ADDITIVE_BLENDING |
 									   LUCID_OPT_VISUALIZE_ERRORS)) == LUCID_OPT_ALPHA_THRESHOLD;
 	if(alpha_thr)
-		shadeHalfBlockSegments(p, cfg, ws, count, pos_mask, hb_x, hb_y, getRec);
+		shadeHalfBlockSegments(p, cfg, ws, keys, count, pos_mask, hb_x, hb_y, list);
 	else
-		shadeHalfBlock(p, cfg, ws, count, pos_mask, hb_x, hb_y, getRec);
+		shadeHalfBlock(p, cfg, ws, keys, count, pos_mask, hb_x, hb_y, list);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -857,92 +937,246 @@ __device__ __forceinline__ void binPhaseA(const Params &p, const BinInfo &b, uin
 	__syncwarp();
 }
 
-constexpr int HB_LIST_CAP = MAX_HBLOCK_TRIS;			  // per half-block list (HIGH), 8-byte records
-constexpr size_t HIGH_SCRATCH_BYTES = (size_t)32 * HB_LIST_CAP * 8;
-constexpr size_t LOW_SCRATCH_BYTES = (size_t)16 * MAX_BLOCK_TRIS * 16;
+// ------------------------------------------------------------------------------------------------
+// stage 1: k_raster_bins -- block lists of every non-empty bin (generateRowTris + generateBlocks /
+// computeRBlockGroups of the reference, raster_low.glsl:39-106, raster_high.glsl:54-144)
+
+constexpr int HB_LIST_CAP = MAX_HBLOCK_TRIS; // records per half-block list (HIGH)
+constexpr int HEAVY_BLOCK = 192;			 // blocks with more entries are shaded first
+
+__device__ __forceinline__ unsigned char *binLists(const Params &p, int bin_id) {
+	return reinterpret_cast<unsigned char *>(p.block_lists) + (size_t)bin_id * BIN_LIST_BYTES;
+}
 
 struct BinShared {
 	int count[32]; // entries per half-block (HIGH) / block (LOW)
 	int holes[32]; // HIGH: columns inside a record's [first, last] range without coverage
-	int next_item, status, bin_index;
-	u32 frags, hbtris;
+	int bin_index, status;
 };
 
-// LOW: a bin with fewer than 1024 triangles (raster_low.glsl); one warp per 8x8 block
-__device__ void rasterLowBin(const Params &p, const LucidConfig &cfg, int bin_id, uint4 *lists, BinShared &sh,
-							 unsigned char *smem) {
+// a persistent 256-thread CTA takes one bin at a time: HIGH bins first (they take longest)
+__global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_constant__ Params p, u32 background) {
+	__shared__ BinShared sh;
+	__shared__ __align__(16) uint4 s_ring[RASTER_WARPS][PHASE_A_RING * 2];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const WarpScratch ws = warpScratch(smem + (size_t)warp * (WARP_SCRATCH_FIXED + MAX_BLOCK_TRIS * 4));
-	const BinInfo b = loadBin(p, bin_id);
-	if(tid < 32)
-		sh.count[tid] = 0;
-	if(tid == 0)
-		sh.next_item = 0, sh.status = 0, sh.frags = 0, sh.hbtris = 0;
-	__syncthreads();
-
-	binPhaseA<false>(p, b, reinterpret_cast<uint4 *>(ws.stage),
-					 [&](bool, u32 tri_idx, int g, u32 mn0, u32 mx0, u32 mn1, u32 mx1, u32 bx) {
-						 while(bx) {
-							 int c = __ffs(bx) - 1;
-							 bx &= bx - 1;
-							 int slot = atomicAdd(&sh.count[g * 4 + c], 1);
-							 if(slot < MAX_BLOCK_TRIS)
-								 lists[(g * 4 + c) * MAX_BLOCK_TRIS + slot] = make_uint4(
-									 tri_idx, packHalfRows(mn0, mx0, c * 8), packHalfRows(mn1, mx1, c * 8), 0u);
-						 }
-					 });
-	__syncthreads();
-	if(tid < 16 && sh.count[tid] > MAX_BLOCK_TRIS)
-		sh.status = 1;
-	__syncthreads();
-	if(sh.status != 0) {
-		// too many triangles for one block: the whole bin is redone by the HIGH path
-		// (raster_low.glsl:101-105,230-237)
+	const int n_high = p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH];
+	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
+	while(true) {
+		__syncthreads();
 		if(tid == 0)
-			atomicOr(&p.bin_flags[bin_id], 1u);
-		return;
-	}
+			sh.bin_index = (int)atomicAdd(&p.work_counters[0], 1u);
+		__syncthreads();
+		const int idx = sh.bin_index;
+		if(idx >= n_high + n_low)
+			break;
+		bool high = idx < n_high;
+		const int bin_id = high ? cntc(p, LUCID_CNT_HIGH_BINS)[idx] : cntc(p, LUCID_CNT_LOW_BINS)[idx - n_high];
+		const BinInfo b = loadBin(p, bin_id);
+		unsigned char *lists = binLists(p, bin_id);
 
-	// phase B (raster_low.glsl:81-194): blocks are handed to warps dynamically
+		if(!high) {
+			if(tid < 32)
+				sh.count[tid] = 0;
+			if(tid == 0)
+				sh.status = 0;
+			__syncthreads();
+			uint4 *recs = reinterpret_cast<uint4 *>(lists);
+			binPhaseA<false>(p, b, s_ring[warp], [&](bool, u32 tri_idx, int g, u32 mn0, u32 mx0, u32 mn1, u32 mx1, u32 bx) {
+				while(bx) {
+					int c = __ffs(bx) - 1;
+					bx &= bx - 1;
+					int slot = atomicAdd(&sh.count[g * 4 + c], 1);
+					if(slot < MAX_BLOCK_TRIS)
+						recs[(g * 4 + c) * MAX_BLOCK_TRIS + slot] =
+							make_uint4(tri_idx, packHalfRows(mn0, mx0, c * 8), packHalfRows(mn1, mx1, c * 8), 0u);
+				}
+			});
+			__syncthreads();
+			if(tid < 16 && sh.count[tid] > MAX_BLOCK_TRIS)
+				sh.status = 1;
+			__syncthreads();
+			if(sh.status != 0) {
+				// too many triangles for one block: the bin is redone by the HIGH path
+				// (raster_low.glsl:101-105,230-237); k_promote appends it to the HIGH list
+				if(tid == 0)
+					p.bin_flags[bin_id] |= 1u;
+				high = true;
+			}
+			__syncthreads();
+		}
+		if(high) {
+			if(tid < 32)
+				sh.count[tid] = 0, sh.holes[tid] = 0;
+			if(tid == 0)
+				sh.status = 0;
+			__syncthreads();
+			uint2 *recs = reinterpret_cast<uint2 *>(lists);
+			binPhaseA<true>(p, b, s_ring[warp], [&](bool, u32 tri_idx, int g, u32 mn, u32 mx, u32, u32, u32 bx) {
+				if(bx == 0)
+					return;
+				const int lo = __ffs(bx) - 1, hi = 31 - __clz(bx);
+				u32 holes = ((2u << hi) - (1u << lo)) & ~bx;
+				while(bx) {
+					int c = __ffs(bx) - 1;
+					bx &= bx - 1;
+					int slot = atomicAdd(&sh.count[g * 4 + c], 1);
+					if(slot < HB_LIST_CAP)
+						recs[(g * 4 + c) * HB_LIST_CAP + slot] = make_uint2(tri_idx, packHalfRows(mn, mx, c * 8));
+				}
+				while(holes) {
+					int c = __ffs(holes) - 1;
+					holes &= holes - 1;
+					atomicAdd(&sh.holes[g * 4 + c], 1);
+				}
+			});
+			__syncthreads();
+			if(tid < 32) {
+				// the reference's limit is on the estimated count (first..last column, holes
+				// included): more than 4096 paints the bin red (raster_high.glsl:80-83,140-141).
+				// 16384 records in one half-block row imply more than 4096 in one of its
+				// half-blocks, so that limit is covered too.
+				bool over = __any_sync(0xffffffffu, sh.count[tid] + sh.holes[tid] > MAX_HBLOCK_TRIS);
+				if(tid == 0 && over) {
+					p.bin_flags[bin_id] |= 2u;
+					sh.status = 2;
+				}
+			}
+			__syncthreads();
+			if(sh.status != 0)
+				continue; // k_raster_finish paints the bin
+		}
+
+		// publish the non-empty blocks as work items of stage 2; empty ones only get the background
+		const int n_blocks = high ? 32 : 16;
+		if(tid < 32) {
+			const int c = tid < n_blocks ? sh.count[tid] : 0;
+			if(tid < n_blocks)
+				p.block_counts[bin_id * 32 + tid] = c;
+			const u32 item = ((u32)bin_id << 6) | (high ? 32u : 0u) | (u32)tid;
+			const u32 heavy = __ballot_sync(0xffffffffu, c > HEAVY_BLOCK), light = __ballot_sync(0xffffffffu, c > 0) & ~heavy;
+			u32 base_h = 0, base_l = 0;
+			if(tid == 0) {
+				if(heavy)
+					base_h = atomicAdd(&p.work_counters[3], (u32)__popc(heavy));
+				if(light)
+					base_l = atomicAdd(&p.work_counters[4], (u32)__popc(light));
+			}
+			base_h = __shfl_sync(0xffffffffu, base_h, 0), base_l = __shfl_sync(0xffffffffu, base_l, 0);
+			if((heavy >> tid) & 1)
+				p.block_items[base_h + __popc(heavy & laneMaskLt())] = item;
+			if((light >> tid) & 1)
+				p.block_items[p.block_items_cap + base_l + __popc(light & laneMaskLt())] = item;
+		}
+		const int rows = high ? 4 : 8;
+		for(int blk = warp; blk < n_blocks; blk += RASTER_WARPS) {
+			if(sh.count[blk] != 0)
+				continue;
+			const int bx0 = b.pos_x + (blk & 3) * 8, by0 = b.pos_y + (blk >> 2) * rows;
+			for(int i = lane; i < 8 * rows; i += 32) {
+				int gx = bx0 + (i & 7), gy = by0 + (i >> 3);
+				if(gx < p.width && gy < p.height) {
+					p.image[(size_t)gy * p.image_pitch + gx] = background;
+					if(p.frag_counts)
+						p.frag_counts[(size_t)gy * p.width + gx] = 0;
+				}
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 2: k_raster_blocks -- depth sort and shading; a work item is one 8x8 block of a LOW bin or
+// one 8x4 half-block of a HIGH bin and belongs to one warp (generateBlocks / generateRBlocks sort +
+// unpackSamples + shadeAndReduceSamples, raster_low.glsl:107-281, raster_high.glsl:146-348)
+
+constexpr int BLOCK_WARPS = 4;
+constexpr int WARP_SCRATCH_BYTES = WARP_SCRATCH_FIXED + SMEM_KEYS * 4;
+
+__global__ void __launch_bounds__(BLOCK_WARPS * 32, 7)
+	k_raster_blocks(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = laneId(), warp = threadIdx.x >> 5;
+	const WarpScratch ws = warpScratch(smem + (size_t)warp * WARP_SCRATCH_BYTES);
+	u32 *large_keys = p.large_keys + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
+	const u32 n_heavy = p.work_counters[3], n_light = p.work_counters[4];
 	u32 frag_acc = 0, hbt_acc = 0;
 	while(true) {
-		int blk = 0;
-		if(lane == 0)
-			blk = atomicAdd(&sh.next_item, 1);
-		blk = __shfl_sync(0xffffffffu, blk, 0);
-		if(blk >= 16)
+		u32 item = 0;
+		if(lane == 0) {
+			u32 i = atomicAdd(&p.work_counters[1], 1u);
+			if(i < n_heavy)
+				item = p.block_items[i] | 0x80000000u;
+			else {
+				i = atomicAdd(&p.work_counters[2], 1u);
+				if(i < n_light)
+					item = p.block_items[p.block_items_cap + i] | 0x80000000u;
+			}
+		}
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if(item == 0)
 			break;
-		const int by = blk >> 2, bx = blk & 3;
-		const int count = sh.count[blk];
-		const uint4 *list = lists + blk * MAX_BLOCK_TRIS;
+		const int bin_id = (int)((item & 0x7fffffffu) >> 6), sub = (int)(item & 31u);
+		const bool high = (item & 32u) != 0;
+		const int count = p.block_counts[bin_id * 32 + sub];
+		const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
+		const int pos_x = bin_x * BIN_SIZE, pos_y = bin_y * BIN_SIZE;
+		const int cx8 = (sub & 3) * 8, ry = sub >> 2;
+		RecList list;
+		list.wide = !high, list.lower = false;
+		list.base = binLists(p, bin_id) + (high ? (size_t)sub * HB_LIST_CAP * 8 : (size_t)sub * MAX_BLOCK_TRIS * 16);
+		u32 *keys = count > SMEM_KEYS ? large_keys : ws.keys;
+
+		// depth keys from the centroid of the covered pixels (raster.glsl:142-176)
 		for(int i = lane; i < count; i += 32) {
-			uint4 rec = list[i];
-			int nf0, cx0, cy0, nf1, cx1, cy1;
-			rowsCentroid(rec.y, nf0, cx0, cy0);
-			rowsCentroid(rec.z, nf1, cx1, cy1);
-			// both halves use row offsets 1,3,5,7 for the centroid, exactly as the reference does
-			float cx = float(cx0) + float(cx1), cy = float(cy0) + float(cy1);
-			float scale = __fdiv_rn(0.5f, float(nf0 + nf1));
-			float cpx = cx * scale + float(b.pos_x + bx * 8), cpy = cy * scale + float(b.pos_y + by * 8);
-			u32 depth = blockDepth(p, rec.x, cpx, cpy, float(0x3ffffe));
-			ws.keys[i] = (u32)i | (depth << 10);
-			frag_acc += (u32)(nf0 + nf1);
+			u32 depth;
+			if(high) {
+				uint2 rec = __ldg(reinterpret_cast<const uint2 *>(list.base) + i);
+				int nf, cx, cy;
+				rowsCentroid(rec.y, nf, cx, cy);
+				float scale = __fdiv_rn(0.5f, float(nf));
+				float cpx = float(cx) * scale + (float(cx8) + float(pos_x));
+				float cpy = float(cy) * scale + (float(ry * 4) + float(pos_y));
+				depth = blockDepth(p, rec.x, cpx, cpy, float(0x7fffe)) << 14;
+				frag_acc += (u32)nf;
+			} else {
+				uint4 rec = __ldg(reinterpret_cast<const uint4 *>(list.base) + i);
+				int nf0, cx0, cy0, nf1, cx1, cy1;
+				rowsCentroid(rec.y, nf0, cx0, cy0);
+				rowsCentroid(rec.z, nf1, cx1, cy1);
+				// both halves use row offsets 1,3,5,7 for the centroid, exactly as the reference does
+				float cx = float(cx0) + float(cx1), cy = float(cy0) + float(cy1);
+				float scale = __fdiv_rn(0.5f, float(nf0 + nf1));
+				float cpx = cx * scale + float(pos_x + cx8), cpy = cy * scale + float(pos_y + ry * 8);
+				depth = blockDepth(p, rec.x, cpx, cpy, float(0x3ffffe)) << 10;
+				frag_acc += (u32)(nf0 + nf1);
+			}
+			keys[i] = (u32)i | depth;
 		}
-		hbt_acc += lane == 0 ? (u32)count * 2u : 0u; // the block's count once per half-block (raster_low.glsl:272-275)
 		__syncwarp();
-		if(count > 3) { // blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
-			warpSortShared<MAX_BLOCK_TRIS>(ws.keys, count);
-			warpFixDepthTies(ws.keys, count, 10, [&](u32 pos) { return list[pos].x; });
+		// stats: LOW counts the block's triangles once per half-block (raster_low.glsl:272-275),
+		// HIGH the exact half-block list (raster_high.glsl:309-310)
+		hbt_acc += lane == 0 ? (u32)count * (high ? 1u : 2u) : 0u;
+		const int slot_bits = high ? 14 : 10;
+		if(high || count > 3) { // LOW blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
+			if(count > SMEM_KEYS)
+				warpSortLarge(keys, count, ws.keys);
+			else
+				warpSortShared(keys, count);
+			warpFixDepthTies(keys, count, slot_bits, [&](u32 pos) {
+				return high ? __ldg(reinterpret_cast<const uint2 *>(list.base) + pos).x
+							: __ldg(reinterpret_cast<const uint4 *>(list.base) + pos).x;
+			});
 		}
-		__syncwarp();
-		for(int half = 0; half < 2; half++) {
-			auto rec = [&](u32 pos, u32 &rows, u32 &tri) {
-				uint4 r = list[pos];
-				rows = half ? r.z : r.y, tri = r.x;
-			};
-			shadeHalfBlockAny(p, cfg, ws, count, 0x3ffu, b.pos_x + bx * 8, b.pos_y + by * 8 + half * 4, rec);
+		const u32 pos_mask = (1u << slot_bits) - 1u;
+		if(high) {
+			shadeHalfBlockAny(p, cfg, ws, keys, count, pos_mask, pos_x + cx8, pos_y + ry * 4, list);
+		} else {
+			shadeHalfBlockAny(p, cfg, ws, keys, count, pos_mask, pos_x + cx8, pos_y + ry * 8, list);
 			__syncwarp();
+			list.lower = true;
+			shadeHalfBlockAny(p, cfg, ws, keys, count, pos_mask, pos_x + cx8, pos_y + ry * 8 + 4, list);
 		}
+		__syncwarp();
 	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1) {
@@ -950,33 +1184,38 @@ __device__ void rasterLowBin(const Params &p, const LucidConfig &cfg, int bin_id
 		hbt_acc += __shfl_xor_sync(0xffffffffu, hbt_acc, o);
 	}
 	if(lane == 0) {
-		atomicAdd(&sh.frags, frag_acc);
-		atomicAdd(&sh.hbtris, hbt_acc);
-	}
-	__syncthreads();
-	if(tid == 0)
-		p.bin_stats[bin_id * 4 + 0] = sh.frags, p.bin_stats[bin_id * 4 + 1] = sh.hbtris;
-}
-
-__global__ void __launch_bounds__(RASTER_THREADS, 3) k_raster_low(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
-	extern __shared__ __align__(16) unsigned char smem[];
-	__shared__ BinShared sh;
-	uint4 *lists = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(p.high_scratch) +
-											 (size_t)blockIdx.x * LOW_SCRATCH_BYTES);
-	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
-	while(true) {
-		__syncthreads();
-		if(threadIdx.x == 0)
-			sh.bin_index = (int)atomicAdd(&p.work_counters[0], 1u);
-		__syncthreads();
-		const int idx = sh.bin_index;
-		if(idx >= n_low)
-			break;
-		rasterLowBin(p, cfg, cntc(p, LUCID_CNT_LOW_BINS)[idx], lists, sh, smem);
+		if(frag_acc)
+			atomicAdd(&p.info->stats[0], frag_acc);
+		if(hbt_acc)
+			atomicAdd(&p.info->stats[1], hbt_acc);
 	}
 }
 
-// appends promoted LOW bins to the HIGH list in bin order (raster_low.glsl:230-237,294-298)
+// ------------------------------------------------------------------------------------------------
+// stage 3: k_raster_finish -- background for empty bins (the reference leaves them to the
+// application's clear), red for bins over the reference's limits, and the level bookkeeping of
+// promoted bins: appended to the HIGH list in bin order (raster_low.glsl:230-237,294-298)
+__global__ void __launch_bounds__(256) k_raster_finish(const Params p, u32 background) {
+	const int *qc = cntc(p, LUCID_CNT_QUAD_COUNTS), *tc = cntc(p, LUCID_CNT_TRI_COUNTS);
+	for(int b = blockIdx.x; b < p.bin_count; b += gridDim.x) {
+		int by = b / p.bin_count_x, bx = b - by * p.bin_count_x;
+		if(by < p.row_begin || by >= p.row_end)
+			continue;
+		const bool empty = tc[b] + qc[b] * 2 == 0, error = (p.bin_flags[b] & 2u) != 0;
+		if(!empty && !error)
+			continue;
+		const u32 value = error ? 0x000000ffu : background;
+		for(int i = threadIdx.x; i < BIN_SIZE * BIN_SIZE; i += blockDim.x) {
+			int gx = bx * BIN_SIZE + (i & 31), gy = by * BIN_SIZE + (i >> 5);
+			if(gx < p.width && gy < p.height) {
+				p.image[(size_t)gy * p.image_pitch + gx] = value;
+				if(p.frag_counts)
+					p.frag_counts[(size_t)gy * p.width + gx] = 0;
+			}
+		}
+	}
+}
+
 __global__ void __launch_bounds__(1024) k_promote(const Params p) {
 	__shared__ int s_warp[33];
 	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
@@ -988,7 +1227,6 @@ __global__ void __launch_bounds__(1024) k_promote(const Params p) {
 	int mine = 0;
 	for(int i = i0; i < i1; i++)
 		mine += (p.bin_flags[low[i]] & 1u) ? 1 : 0;
-	// exclusive scan over threads
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int incl = mine;
 	for(int o = 1; o < 32; o <<= 1) {
@@ -1024,211 +1262,28 @@ __global__ void __launch_bounds__(1024) k_promote(const Params p) {
 	}
 }
 
-// HIGH: a dense bin (raster_high.glsl); one warp per 8x4 half-block.  CAP is the longest
-// half-block list this instantiation sorts in shared memory; bins that need more are handed to
-// the CAP = 4096 instantiation (the reference's limit, raster_high.glsl:27).
-template <int CAP>
-__device__ void rasterHighBin(const Params &p, const LucidConfig &cfg, int bin_id, uint2 *lists, BinShared &sh,
-							  unsigned char *smem) {
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const WarpScratch ws = warpScratch(smem + (size_t)warp * (WARP_SCRATCH_FIXED + CAP * 4));
-	const BinInfo b = loadBin(p, bin_id);
-	if(tid < 32)
-		sh.count[tid] = 0, sh.holes[tid] = 0;
-	if(tid == 0)
-		sh.next_item = 0, sh.status = (p.bin_flags[bin_id] & 2u) ? 2 : 0, sh.frags = 0, sh.hbtris = 0;
-	__syncthreads();
+static int rasterBinsGrid(int num_sms) { return num_sms * 4; }
+static int rasterBlocksGrid(int num_sms) { return num_sms * 7; }
+size_t rasterLargeKeysCount(int num_sms) { return (size_t)rasterBlocksGrid(num_sms) * BLOCK_WARPS * MAX_HBLOCK_TRIS; }
 
-	// phase A (raster_high.glsl:54-144)
-	binPhaseA<true>(p, b, reinterpret_cast<uint4 *>(ws.stage),
-					[&](bool, u32 tri_idx, int g, u32 mn, u32 mx, u32, u32, u32 bx) {
-						if(bx == 0)
-							return;
-						const int lo = __ffs(bx) - 1, hi = 31 - __clz(bx);
-						u32 holes = ((2u << hi) - (1u << lo)) & ~bx;
-						while(bx) {
-							int c = __ffs(bx) - 1;
-							bx &= bx - 1;
-							int slot = atomicAdd(&sh.count[g * 4 + c], 1);
-							if(slot < HB_LIST_CAP)
-								lists[(g * 4 + c) * HB_LIST_CAP + slot] = make_uint2(tri_idx, packHalfRows(mn, mx, c * 8));
-						}
-						while(holes) {
-							int c = __ffs(holes) - 1;
-							holes &= holes - 1;
-							atomicAdd(&sh.holes[g * 4 + c], 1);
-						}
-					});
-	__syncthreads();
-	if(tid < 32) {
-		// the reference's limit is on the estimated count (first..last column, holes included):
-		// more than 4096 paints the bin red (raster_high.glsl:80-83,140-141).  16384 records in one
-		// half-block row imply more than 4096 in one of its half-blocks, so that limit is covered.
-		int exact = sh.count[tid], est = exact + sh.holes[tid];
-		bool over = __any_sync(0xffffffffu, est > MAX_HBLOCK_TRIS);
-		bool big = __any_sync(0xffffffffu, exact > CAP);
-		if(tid == 0) {
-			if(over) {
-				atomicOr(&p.bin_flags[bin_id], 2u);
-				sh.status = 2;
-			} else if(big) {
-				int idx = atomicAdd(&p.work_counters[3], 1u);
-				p.deferred_items[idx] = bin_id;
-				sh.status = 1;
-			}
-		}
-	}
-	__syncthreads();
-	if(sh.status != 0)
-		return;
-
-	// phase B (raster_high.glsl:146-273): half-blocks are handed to warps dynamically
-	u32 frag_acc = 0, hbt_acc = 0;
-	while(true) {
-		int hb = 0;
-		if(lane == 0)
-			hb = atomicAdd(&sh.next_item, 1);
-		hb = __shfl_sync(0xffffffffu, hb, 0);
-		if(hb >= 32)
-			break;
-		const int rby = hb >> 2, hbx = hb & 3;
-		const int count = sh.count[hb];
-		const uint2 *list = lists + hb * HB_LIST_CAP;
-		for(int i = lane; i < count; i += 32) {
-			uint2 rec = list[i];
-			int nf, cx, cy;
-			rowsCentroid(rec.y, nf, cx, cy);
-			float scale = __fdiv_rn(0.5f, float(nf));
-			float cpx = float(cx) * scale + (float(hbx * 8) + float(b.pos_x));
-			float cpy = float(cy) * scale + (float(rby * 4) + float(b.pos_y));
-			u32 depth = blockDepth(p, rec.x, cpx, cpy, float(0x7fffe));
-			ws.keys[i] = (u32)i | (depth << 14);
-			frag_acc += (u32)nf;
-		}
-		hbt_acc += lane == 0 ? (u32)count : 0u; // exact per-half-block counts (raster_high.glsl:309-310)
-		__syncwarp();
-		warpSortShared<CAP>(ws.keys, count);
-		warpFixDepthTies(ws.keys, count, 14, [&](u32 pos) { return list[pos].x; });
-		__syncwarp();
-		auto rec = [&](u32 pos, u32 &rows, u32 &tri) {
-			uint2 r = list[pos];
-			rows = r.y, tri = r.x;
-		};
-		shadeHalfBlockAny(p, cfg, ws, count, 0x3fffu, b.pos_x + hbx * 8, b.pos_y + rby * 4, rec);
-		__syncwarp();
-	}
-#pragma unroll
-	for(int o = 16; o > 0; o >>= 1) {
-		frag_acc += __shfl_xor_sync(0xffffffffu, frag_acc, o);
-		hbt_acc += __shfl_xor_sync(0xffffffffu, hbt_acc, o);
-	}
-	if(lane == 0) {
-		atomicAdd(&sh.frags, frag_acc);
-		atomicAdd(&sh.hbtris, hbt_acc);
-	}
-	__syncthreads();
-	if(tid == 0)
-		p.bin_stats[bin_id * 4 + 2] = sh.frags, p.bin_stats[bin_id * 4 + 3] = sh.hbtris;
-}
-
-template <int CAP, bool DEFERRED, int MIN_CTAS>
-__global__ void __launch_bounds__(RASTER_THREADS, MIN_CTAS) k_raster_high(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
-	extern __shared__ __align__(16) unsigned char smem[];
-	__shared__ BinShared sh;
-	uint2 *lists = reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(p.high_scratch) +
-											 (size_t)blockIdx.x * HIGH_SCRATCH_BYTES);
-	const int n_items = DEFERRED ? (int)p.work_counters[3] : p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH];
-	while(true) {
-		__syncthreads();
-		if(threadIdx.x == 0)
-			sh.bin_index = (int)atomicAdd(&p.work_counters[DEFERRED ? 2 : 1], 1u);
-		__syncthreads();
-		const int idx = sh.bin_index;
-		if(idx >= n_items)
-			break;
-		const int bin_id = DEFERRED ? p.deferred_items[idx] : cntc(p, LUCID_CNT_HIGH_BINS)[idx];
-		rasterHighBin<CAP>(p, cfg, bin_id, lists, sh, smem);
-	}
-}
-
-// background for bins no kernel writes, red for bins over the reference's limits, and the
-// statistics (shading.glsl:38-53); LOW results of promoted bins are not counted
-__global__ void __launch_bounds__(256) k_raster_finish(const Params p, u32 background, int fill_empty) {
-	const int *qc = cntc(p, LUCID_CNT_QUAD_COUNTS), *tc = cntc(p, LUCID_CNT_TRI_COUNTS);
-	u32 frags = 0, hbt = 0;
-	for(int b = blockIdx.x; b < p.bin_count; b += gridDim.x) {
-		int by = b / p.bin_count_x, bx = b - by * p.bin_count_x;
-		u32 flags = p.bin_flags[b];
-		int num_tris = tc[b] + qc[b] * 2;
-		bool empty = num_tris == 0;
-		bool error = (flags & 2u) != 0;
-		if(by < p.row_begin || by >= p.row_end)
-			continue;
-		if((empty && fill_empty) || error) {
-			u32 value = error ? 0x000000ffu : background;
-			for(int i = threadIdx.x; i < BIN_SIZE * BIN_SIZE; i += blockDim.x) {
-				int gx = bx * BIN_SIZE + (i & 31), gy = by * BIN_SIZE + (i >> 5);
-				if(gx < p.width && gy < p.height) {
-					p.image[(size_t)gy * p.image_pitch + gx] = value;
-					if(p.frag_counts)
-						p.frag_counts[(size_t)gy * p.width + gx] = 0;
-				}
-			}
-		}
-		if(threadIdx.x == 0 && !empty && !error) {
-			bool high = num_tris >= 1024 || (flags & 1u);
-			frags += p.bin_stats[b * 4 + (high ? 2 : 0)];
-			hbt += p.bin_stats[b * 4 + (high ? 3 : 1)];
-		}
-	}
-	if(threadIdx.x == 0) {
-		if(frags)
-			atomicAdd(&p.info->stats[0], frags);
-		if(hbt)
-			atomicAdd(&p.info->stats[1], hbt);
-	}
-}
-
-constexpr int HIGH_SMALL_CAP = 1024;
-constexpr int lowSmemBytes() { return RASTER_WARPS * (WARP_SCRATCH_FIXED + MAX_BLOCK_TRIS * 4); }
-template <int CAP> constexpr int highSmemBytes() { return RASTER_WARPS * (WARP_SCRATCH_FIXED + CAP * 4); }
-
-static int rasterLowGrid(int num_sms) { return num_sms * 4; }
-static int rasterHighGridSmall(int num_sms) { return num_sms * 3; }
-static int rasterHighGridLarge(int num_sms) { return num_sms; }
-
-size_t rasterScratchBytes(int num_sms) {
-	size_t low = (size_t)rasterLowGrid(num_sms) * LOW_SCRATCH_BYTES;
-	size_t high = (size_t)rasterHighGridSmall(num_sms) * HIGH_SCRATCH_BYTES;
-	size_t large = (size_t)rasterHighGridLarge(num_sms) * HIGH_SCRATCH_BYTES;
-	return low > high ? (low > large ? low : large) : (high > large ? high : large);
-}
-
-void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, cudaEvent_t *ev,
-				  int num_sms) {
+void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, cudaEvent_t *ev, int num_sms) {
 	static bool configured = false;
+	const int blocks_smem = BLOCK_WARPS * WARP_SCRATCH_BYTES;
 	if(!configured) {
-		cudaFuncSetAttribute(k_raster_low, cudaFuncAttributeMaxDynamicSharedMemorySize, lowSmemBytes());
-		cudaFuncSetAttribute(k_raster_high<HIGH_SMALL_CAP, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-							 highSmemBytes<HIGH_SMALL_CAP>());
-		cudaFuncSetAttribute(k_raster_high<MAX_HBLOCK_TRIS, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-							 highSmemBytes<MAX_HBLOCK_TRIS>());
+		cudaFuncSetAttribute(k_raster_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, blocks_smem);
 		configured = true;
 	}
-	k_raster_low<<<rasterLowGrid(num_sms), RASTER_THREADS, lowSmemBytes(), stream>>>(p, cfg);
-	k_promote<<<1, 1024, 0, stream>>>(p);
-	if(ev)
-		cudaEventRecord(ev[0], stream);
-	k_raster_high<HIGH_SMALL_CAP, false, 3>
-		<<<rasterHighGridSmall(num_sms), RASTER_THREADS, highSmemBytes<HIGH_SMALL_CAP>(), stream>>>(p, cfg);
-	k_raster_high<MAX_HBLOCK_TRIS, true, 1>
-		<<<rasterHighGridLarge(num_sms), RASTER_THREADS, highSmemBytes<MAX_HBLOCK_TRIS>(), stream>>>(p, cfg);
-	if(ev)
-		cudaEventRecord(ev[1], stream);
 	const LucidVec4 &bg = cfg.background_color;
 	auto q = [](float v) { return (u32)(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f + 0.5f); };
-	u32 bg8 = q(bg.x) | (q(bg.y) << 8) | (q(bg.z) << 16) | 0xff000000u;
-	k_raster_finish<<<num_sms * 2, 256, 0, stream>>>(p, bg8, 1);
+	const u32 bg8 = q(bg.x) | (q(bg.y) << 8) | (q(bg.z) << 16) | 0xff000000u;
+	k_raster_bins<<<rasterBinsGrid(num_sms), RASTER_THREADS, 0, stream>>>(p, bg8);
+	if(ev)
+		cudaEventRecord(ev[0], stream);
+	k_raster_blocks<<<rasterBlocksGrid(num_sms), BLOCK_WARPS * 32, blocks_smem, stream>>>(p, cfg);
+	if(ev)
+		cudaEventRecord(ev[1], stream);
+	k_raster_finish<<<num_sms * 2, 256, 0, stream>>>(p, bg8);
+	k_promote<<<1, 1024, 0, stream>>>(p);
 	if(ev)
 		cudaEventRecord(ev[2], stream);
 }
