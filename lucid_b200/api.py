@@ -93,8 +93,8 @@ def load_library(build_if_needed: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.SO_PATH
-    if build_if_needed and _build.needs_build():
+    path = os.environ.get("LUCID_B200_SO") or _build.SO_PATH  # override: experiment builds only
+    if build_if_needed and path == _build.SO_PATH and _build.needs_build():
         try:
             _build.build()
         except Exception:

@@ -40,8 +40,9 @@ def needs_build() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines / out: experiment builds (tools/variants.py); the product build uses neither."""
+    if not force and not needs_build() and out is None:
         return SO_PATH
     srcs = [os.path.join(HERE, s) for s in CUDA_SOURCES + HOST_SOURCES if os.path.exists(os.path.join(HERE, s))]
     cmd = [
@@ -49,8 +50,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
         "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wall,-Wno-unused-function", "-shared",
         "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-        "-I", os.path.join(ROOT, "include"), "-o", SO_PATH,
+        "-I", os.path.join(ROOT, "include"), "-o", out or SO_PATH,
     ]
+    cmd += [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += srcs
@@ -60,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return SO_PATH
+    return out or SO_PATH
 
 
 if __name__ == "__main__":

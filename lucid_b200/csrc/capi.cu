@@ -198,6 +198,7 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	p.block_items_cap = (u32)p.bin_count * 32u;
 	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 2));
 	CUC(devAlloc(r, &p.large_keys, rasterLargeKeysCount(r->num_sms)));
+	CUC(devAlloc(r, &p.block_aux, rasterLargeKeysCount(r->num_sms)));
 	CUC(devAlloc(r, &r->image, (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->frag_counts, (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->d_instances, (size_t)LUCID_MAX_INSTANCES));

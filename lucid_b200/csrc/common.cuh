@@ -22,9 +22,10 @@ constexpr int BIN_SHIFT = LUCID_BIN_SHIFT;
 // (large, allocated downwards), as in quad_setup.glsl:437-444; tri_idx = slot * 2 + second_tri.
 //   quad_aabbs[slot]   u32      28-bit bin AABB + 2 cull bits (quad_setup.glsl:241-242)
 //   tri_scan[tri]      2x16 B   scanline record (scan.xyz, ymin|ymax<<16) (step.xyz, sign bits)
-//   tri_shade[tri]     4x16 B   depth plane (xyz, flags|instance<<16), bary edge 0, bary edge 1,
-//                               (flat normal 10-10-10, instance RGBA8, constant shaded RGBA8,
-//                                1 if the constant is valid)
+//   tri_shade[tri]     4x16 B   depth plane (xyz, flags|instance<<16), (flat normal 10-10-10,
+//                               instance RGBA8, constant shaded RGBA8, 1 if the constant is valid),
+//                               bary edge 0, bary edge 1 -- the first 32-byte sector is all the
+//                               block sort and constant-colour triangles ever read
 //   quad_colors/normals[slot] 16 B, quad_uv[slot] 2x16 B   optional vertex attributes
 // The reference keeps the same fields in uvec4_storage / normals_storage
 // (definitions.glsl:132-137); here the per-sample fields of one triangle share one 64-byte line
@@ -33,7 +34,7 @@ struct TriScan {
 	uint4 s0, s1;
 };
 struct TriShade {
-	uint4 depth, bary0, bary1, misc;
+	uint4 depth, misc, bary0, bary1;
 };
 
 struct Params {
@@ -84,6 +85,7 @@ struct Params {
 	u32 *block_items;	  // work items of k_raster_blocks: heavy at [0, cap), light at [cap, 2 cap)
 	u32 block_items_cap;
 	u32 *large_keys;	  // per k_raster_blocks warp: sort keys of lists too long for shared memory
+	uint4 *block_aux;	  // per k_raster_blocks warp: (depth plane, constant colour) per list entry
 	// textures: level offsets into one RGBA8 array per slot
 	const uchar4 *tex_data[2];
 	int tex_width[2], tex_height[2], tex_levels[2];

@@ -59,8 +59,7 @@ __device__ __forceinline__ void rasterBinStep(RowScan &r, u32 &min_bits, u32 &ma
 }
 
 // raster.glsl:170-176
-__device__ __forceinline__ u32 blockDepth(const Params &p, u32 tri_idx, float cx, float cy, float range) {
-	uint4 d = __ldg(reinterpret_cast<const uint4 *>(p.tri_shade + tri_idx));
+__device__ __forceinline__ u32 blockDepth(uint4 d, float cx, float cy, float range) {
 	float ray_pos = __uint_as_float(d.x) * cx + (__uint_as_float(d.y) * cy + __uint_as_float(d.z));
 	float depth = range * saturatef(rsqrt_rn(ray_pos + 1.0f));
 	return f2u(depth);
@@ -127,7 +126,15 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 						   float &out_depth) {
 	float px = float(ipx), py = float(ipy);
 	const uint4 *rec = reinterpret_cast<const uint4 *>(p.tri_shade + tri_idx);
-	uint4 dq = __ldg(rec), b0q = __ldg(rec + 1), b1q = __ldg(rec + 2), misc = __ldg(rec + 3);
+	uint4 dq = __ldg(rec), misc = __ldg(rec + 1), b0q = __ldg(rec + 2), b1q = __ldg(rec + 3);
+	// the attribute loads are issued together with the record (their addresses depend on tri_idx
+	// only); whether they are used is decided by the instance flags once the record has arrived
+	const u32 second = tri_idx & 1, quad_idx = tri_idx >> 1;
+	uint4 attr_c = make_uint4(0, 0, 0, 0), attr_n = attr_c;
+	if(p.vertex_colors)
+		attr_c = __ldg(p.quad_colors + quad_idx);
+	if(p.vertex_normals)
+		attr_n = __ldg(p.quad_normals + quad_idx);
 	float dx = __uint_as_float(dq.x), dy = __uint_as_float(dq.y), dz = __uint_as_float(dq.z);
 	u32 flags = dq.w & 0xffffu, instance_id = dq.w >> 16;
 	float e0x = __uint_as_float(b0q.x), e0y = __uint_as_float(b0q.y), e0z = __uint_as_float(b0q.z);
@@ -156,7 +163,6 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 	if(flags & LUCID_INST_HAS_COLOR)
 		color = decodeRGBA8(misc.y);
 
-	const u32 second = tri_idx & 1, quad_idx = tri_idx >> 1;
 	if(textured) {
 		uint4 q0 = __ldg(p.quad_uv + (size_t)quad_idx * 2), q1 = __ldg(p.quad_uv + (size_t)quad_idx * 2 + 1);
 		float t0x = __uint_as_float(q0.x), t0y = __uint_as_float(q0.y);
@@ -180,7 +186,7 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 		color.x *= tc.x, color.y *= tc.y, color.z *= tc.z, color.w *= tc.w;
 	}
 	if(flags & LUCID_INST_HAS_VERTEX_COLORS) {
-		uint4 c = __ldg(p.quad_colors + quad_idx);
+		uint4 c = attr_c;
 		float4 c0 = decodeRGBA8(c.x), c1 = decodeRGBA8(second ? c.z : c.y), c2 = decodeRGBA8(second ? c.w : c.z);
 		float w0 = 1.0f - b0 - b1;
 		color.x *= w0 * c0.x + (b0 * c1.x + b1 * c2.x);
@@ -193,7 +199,7 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 
 	F3 normal;
 	if(flags & LUCID_INST_HAS_VERTEX_NORMALS) {
-		uint4 n = __ldg(p.quad_normals + quad_idx);
+		uint4 n = attr_n;
 		F3 n0 = decodeNormalUint(n.x);
 		F3 n1 = decodeNormalUint(second ? n.z : n.y) - n0, n2 = decodeNormalUint(second ? n.w : n.z) - n0;
 		normal = mk3(b0 * n1.x + (b1 * n2.x + n0.x), b0 * n1.y + (b1 * n2.y + n0.y),
@@ -371,7 +377,7 @@ template <bool FULL_SORT> __device__ __forceinline__ void tileSteps(u32 *keys, i
 }
 
 // keys[0..n) ascending in shared memory; the array has room for n rounded up to a power of two
-__device__ void warpSortShared(u32 *keys, int n) {
+__device__ __noinline__ void warpSortShared(u32 *keys, int n) {
 	const u32 lane = laneId();
 	if(n <= 1)
 		return;
@@ -498,37 +504,39 @@ template <typename TriOf> __device__ void warpFixDepthTies(u32 *keys, int n, int
 // reference's half-block tri record (raster.glsl:152-161), kept per half-block from the start so
 // that phase B never filters a row list.
 
-// (xmin, count) x 4 rows of column `startx / 8` from the bin-wide 5-bit spans
-__device__ __forceinline__ u32 packHalfRows(u32 mins, u32 maxs, int startx) {
-	u32 rows = 0;
+// HIGH record (8 bytes): x = tri_idx | (mins & 0xff) << 24, y = mins >> 8 | maxs << 12, where
+// mins / maxs are the bin-wide 5-bit spans of the group's four rows (raster.glsl:116-140).
+// LOW record (16 bytes): x = tri_idx, y = mins of rows 0-3 | (maxs 0-3) << 20 (low 12 bits),
+// z = mins of rows 4-7 | (maxs 4-7) << 20 (low 12 bits), w = the two maxs' high 8 bits.
+__device__ __forceinline__ uint2 packHighRecord(u32 tri_idx, u32 mins, u32 maxs) {
+	return make_uint2(tri_idx | (mins << 24), (mins >> 8) | (maxs << 12));
+}
+__device__ __forceinline__ uint4 packLowRecord(u32 tri_idx, u32 mn0, u32 mx0, u32 mn1, u32 mx1) {
+	return make_uint4(tri_idx, mn0 | (mx0 << 20), mn1 | (mx1 << 20), (mx0 >> 12) | ((mx1 >> 12) << 8));
+}
+
+// raster.glsl:142-168: the spans clipped to the 8-pixel column starting at startx, as
+// (first x, count) per row; then the pixel mask (bit y * 8 + x), fragment count, centroid sums
+__device__ __forceinline__ u32 rowsToBits(u32 mins, u32 maxs, int startx, int &num_frags) {
+	u32 bits = 0;
+	num_frags = 0;
 #pragma unroll
 	for(int r = 0; r < 4; r++) {
 		int mn = max((int)((mins >> (5 * r)) & 31) - startx, 0);
 		int mx = min((int)((maxs >> (5 * r)) & 31) - startx, 7);
 		int c = max(mx - mn + 1, 0);
-		if(c == 0)
-			mn = 0;
-		rows |= (u32)(mn | (c << 3)) << (7 * r);
-	}
-	return rows;
-}
-// raster.glsl:142-168: pixel mask (bit y * 8 + x), fragment count and centroid sums of a record
-__device__ __forceinline__ u32 rowsToBits(u32 rows, int &num_frags) {
-	u32 bits = 0;
-	num_frags = 0;
-#pragma unroll
-	for(int r = 0; r < 4; r++) {
-		u32 mn = (rows >> (7 * r)) & 7u, c = (rows >> (7 * r + 3)) & 15u;
-		bits |= ((1u << c) - 1u) << (mn + 8 * r);
-		num_frags += (int)c;
+		bits |= ((1u << c) - 1u) << ((mn & 7) + 8 * r);
+		num_frags += c;
 	}
 	return bits;
 }
-__device__ __forceinline__ void rowsCentroid(u32 rows, int &num_frags, int &csum_x, int &csum_y) {
+__device__ __forceinline__ void rowsCentroid(u32 mins, u32 maxs, int startx, int &num_frags, int &csum_x, int &csum_y) {
 	num_frags = 0, csum_x = 0, csum_y = 0;
 #pragma unroll
 	for(int r = 0; r < 4; r++) {
-		int mn = (rows >> (7 * r)) & 7, c = (rows >> (7 * r + 3)) & 15;
+		int mn = max((int)((mins >> (5 * r)) & 31) - startx, 0);
+		int mx = min((int)((maxs >> (5 * r)) & 31) - startx, 7);
+		int c = max(mx - mn + 1, 0);
 		num_frags += c;
 		csum_x += (mn * 2 + c) * c;
 		csum_y += (2 * r + 1) * c;
@@ -547,21 +555,28 @@ __device__ __forceinline__ u32 transpose32(u32 x) {
 	return x;
 }
 
-// a block's record list: HIGH 8-byte records (tri, rows), LOW 16-byte records (tri, rows of the
-// upper half, rows of the lower half, 0)
+__device__ __forceinline__ void unpackHighRecord(uint2 r, u32 &tri, u32 &mins, u32 &maxs) {
+	tri = r.x & 0xffffffu;
+	mins = (r.x >> 24) | ((r.y & 0xfffu) << 8), maxs = r.y >> 12;
+}
+__device__ __forceinline__ void unpackLowRecord(uint4 r, bool lower, u32 &tri, u32 &mins, u32 &maxs) {
+	tri = r.x;
+	u32 w = lower ? r.z : r.y, hi = lower ? (r.w >> 8) : r.w;
+	mins = w & 0xfffffu, maxs = (w >> 20) | ((hi & 0xffu) << 12);
+}
+
+// a block's record list
 struct RecList {
 	const unsigned char *base;
-	bool wide;	// 16-byte records
-	bool lower; // take the lower half's rows
+	int startx; // first x of the block's column inside the bin
+	bool wide;	// LOW: 16-byte records
+	bool lower; // LOW: take the lower half's spans
 };
-__device__ __forceinline__ void recAt(const RecList &l, u32 pos, u32 &rows, u32 &tri) {
-	if(l.wide) {
-		uint4 r = __ldg(reinterpret_cast<const uint4 *>(l.base) + pos);
-		tri = r.x, rows = l.lower ? r.z : r.y;
-	} else {
-		uint2 r = __ldg(reinterpret_cast<const uint2 *>(l.base) + pos);
-		tri = r.x, rows = r.y;
-	}
+__device__ __forceinline__ void recAt(const RecList &l, u32 pos, u32 &mins, u32 &maxs, u32 &tri) {
+	if(l.wide)
+		unpackLowRecord(__ldg(reinterpret_cast<const uint4 *>(l.base) + pos), l.lower, tri, mins, maxs);
+	else
+		unpackHighRecord(__ldg(reinterpret_cast<const uint2 *>(l.base) + pos), tri, mins, maxs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -631,8 +646,32 @@ __device__ __forceinline__ void writePixel(const Params &p, const LucidConfig &c
 // final value is saturated -- so segments only matter for the alpha-threshold early out, which
 // keeps the segment-accurate path below.  Once every pixel of the half-block has zero
 // transmittance, later samples add exactly +0 and are skipped.
-__device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const WarpScratch &ws, const u32 *keys,
-							   int count, u32 pos_mask, int hb_x, int hb_y, const RecList &list) {
+// Per entry the loop needs the record (spans, triangle) and the aux word the key pass left behind
+// (depth plane, constant colour): both addresses come from the sorted key alone, so the loads of
+// the next chunk are issued before the current one is shaded.
+struct ChunkEntry {
+	u32 mins, maxs, tri;
+	uint4 aux; // depth plane xyz, w = constant colour or AUX_VARYING
+};
+constexpr u32 AUX_VARYING = 0x00ffffffu; // alpha 0 with colour bits set: never produced by shadeConstant
+
+__device__ __forceinline__ ChunkEntry loadEntry(const RecList &list, const uint4 *aux, const u32 *keys, int i, int count,
+												u32 pos_mask) {
+	ChunkEntry e;
+	e.mins = 0xfffffu, e.maxs = 0, e.tri = 0; // empty spans (31 > 0 in every row)
+	e.aux = make_uint4(0, 0, 0, 0);
+	if(i < count) {
+		u32 pos = keys[i] & pos_mask;
+		recAt(list, pos, e.mins, e.maxs, e.tri);
+		if(aux)
+			e.aux = __ldcg(aux + pos);
+	}
+	return e;
+}
+
+__device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const WarpScratch &ws,
+											   const u32 *keys, const uint4 *aux, int count, u32 pos_mask, int hb_x,
+											   int hb_y, const RecList &list) {
 	const int lane = laneId();
 	const bool additive = (p.opts & LUCID_OPT_ADDITIVE_BLENDING) != 0;
 	const bool vis_errors = (p.opts & LUCID_OPT_VISUALIZE_ERRORS) != 0;
@@ -642,14 +681,15 @@ __device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const Wa
 	u32 px_frags = 0;
 	bool dead = false;
 
+	ChunkEntry ahead = loadEntry(list, aux, keys, lane, count, pos_mask);
+	int ahead_at = 0; // list index the `ahead` entries were loaded for
 	for(int next = 0; next < count;) {
+		if(ahead_at != next)
+			ahead = loadEntry(list, aux, keys, next + lane, count, pos_mask);
+		const ChunkEntry cur = ahead;
 		const int i = next + lane;
-		u32 rows = 0, tri_idx = 0, bits = 0;
-		int nf = 0;
-		if(i < count) {
-			recAt(list, keys[i] & pos_mask, rows, tri_idx);
-			bits = rowsToBits(rows, nf);
-		}
+		int nf;
+		u32 bits = rowsToBits(cur.mins, cur.maxs, list.startx, nf);
 		int incl = nf;
 #pragma unroll
 		for(int o = 1; o < 32; o <<= 1) {
@@ -664,19 +704,17 @@ __device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const Wa
 		if(!in_chunk)
 			bits = 0;
 		next += taken;
+		ahead_at = next;
+		ahead = loadEntry(list, aux, keys, next + lane, count, pos_mask);
+
 		u32 tm = transpose32(bits);
 		px_frags += __popc(tm);
 		if(dead)
 			continue;
 
-		uint4 dq = make_uint4(0, 0, 0, 0), misc = make_uint4(0, 0, 0, 1);
-		if(in_chunk) {
-			const uint4 *rec = reinterpret_cast<const uint4 *>(p.tri_shade + tri_idx);
-			dq = __ldg(rec), misc = __ldg(rec + 3);
-		}
-		if(__all_sync(0xffffffffu, misc.w != 0)) {
-			ws.stage[lane] = make_float4(__uint_as_float(dq.x), __uint_as_float(dq.y), __uint_as_float(dq.z),
-										 __uint_as_float(misc.z));
+		if(__all_sync(0xffffffffu, !in_chunk || cur.aux.w != AUX_VARYING)) {
+			ws.stage[lane] = make_float4(__uint_as_float(cur.aux.x), __uint_as_float(cur.aux.y),
+										 __uint_as_float(cur.aux.z), __uint_as_float(cur.aux.w));
 			__syncwarp();
 			while(tm) {
 				int j = __ffs(tm) - 1;
@@ -688,7 +726,7 @@ __device__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const Wa
 		} else {
 			if(in_chunk) {
 				ws.chunk[lane] = make_uint2(bits, (u32)off);
-				u32 dst = (u32)off, word = tri_idx << 8, b = bits;
+				u32 dst = (u32)off, word = cur.tri << 8, b = bits;
 				while(b) {
 					u32 pid = __ffs(b) - 1;
 					b &= b - 1;
@@ -751,12 +789,10 @@ __device__ __noinline__ void shadeHalfBlockSegments(const Params &p, const Lucid
 		const u32 seg_end = seg_start + SEGMENT_SIZE;
 		while(next < count && off < seg_end) {
 			int i = next + lane;
-			u32 rows = 0, tri_idx = 0, bits = 0;
-			int nf = 0;
-			if(i < count) {
-				recAt(list, keys[i] & pos_mask, rows, tri_idx);
-				bits = rowsToBits(rows, nf);
-			}
+			ChunkEntry e = loadEntry(list, nullptr, keys, i, count, pos_mask);
+			const u32 tri_idx = e.tri;
+			int nf;
+			u32 bits = rowsToBits(e.mins, e.maxs, list.startx, nf);
 			int incl = nf;
 #pragma unroll
 			for(int o = 1; o < 32; o <<= 1) {
@@ -826,14 +862,14 @@ __device__ __noinline__ void shadeHalfBlockSegments(const Params &p, const Lucid
 }
 
 __device__ __forceinline__ void shadeHalfBlockAny(const Params &p, const LucidConfig &cfg, const WarpScratch &ws,
-												 const u32 *keys, int count, u32 pos_mask, int hb_x, int hb_y,
-												 const RecList &list) {
+												 const u32 *keys, const uint4 *aux, int count, u32 pos_mask, int hb_x,
+												 int hb_y, const RecList &list) {
 	const bool alpha_thr = (p.opts & (LUCID_OPT_ALPHA_THRESHOLD | LUCID_OPT_ADDITIVE_BLENDING |
 									   LUCID_OPT_VISUALIZE_ERRORS)) == LUCID_OPT_ALPHA_THRESHOLD;
 	if(alpha_thr)
 		shadeHalfBlockSegments(p, cfg, ws, keys, count, pos_mask, hb_x, hb_y, list);
 	else
-		shadeHalfBlock(p, cfg, ws, keys, count, pos_mask, hb_x, hb_y, list);
+		shadeHalfBlock(p, cfg, ws, keys, aux, count, pos_mask, hb_x, hb_y, list);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -988,7 +1024,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 					int slot = atomicAdd(&sh.count[g * 4 + c], 1);
 					if(slot < MAX_BLOCK_TRIS)
 						recs[(g * 4 + c) * MAX_BLOCK_TRIS + slot] =
-							make_uint4(tri_idx, packHalfRows(mn0, mx0, c * 8), packHalfRows(mn1, mx1, c * 8), 0u);
+							packLowRecord(tri_idx, mn0, mx0, mn1, mx1);
 				}
 			});
 			__syncthreads();
@@ -1021,7 +1057,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 					bx &= bx - 1;
 					int slot = atomicAdd(&sh.count[g * 4 + c], 1);
 					if(slot < HB_LIST_CAP)
-						recs[(g * 4 + c) * HB_LIST_CAP + slot] = make_uint2(tri_idx, packHalfRows(mn, mx, c * 8));
+						recs[(g * 4 + c) * HB_LIST_CAP + slot] = packHighRecord(tri_idx, mn, mx);
 				}
 				while(holes) {
 					int c = __ffs(holes) - 1;
@@ -1089,15 +1125,23 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 // one 8x4 half-block of a HIGH bin and belongs to one warp (generateBlocks / generateRBlocks sort +
 // unpackSamples + shadeAndReduceSamples, raster_low.glsl:107-281, raster_high.glsl:146-348)
 
+#ifndef RB_MIN_CTAS
+#define RB_MIN_CTAS 5
+#endif
+#ifndef RB_KEY_UNROLL
+#define RB_KEY_UNROLL 2
+#endif
 constexpr int BLOCK_WARPS = 4;
+constexpr int KEY_UNROLL = RB_KEY_UNROLL;
 constexpr int WARP_SCRATCH_BYTES = WARP_SCRATCH_FIXED + SMEM_KEYS * 4;
 
-__global__ void __launch_bounds__(BLOCK_WARPS * 32, 7)
+__global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 	k_raster_blocks(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const int lane = laneId(), warp = threadIdx.x >> 5;
 	const WarpScratch ws = warpScratch(smem + (size_t)warp * WARP_SCRATCH_BYTES);
 	u32 *large_keys = p.large_keys + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
+	uint4 *aux = p.block_aux + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
 	const u32 n_heavy = p.work_counters[3], n_light = p.work_counters[4];
 	u32 frag_acc = 0, hbt_acc = 0;
 	while(true) {
@@ -1122,35 +1166,68 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, 7)
 		const int pos_x = bin_x * BIN_SIZE, pos_y = bin_y * BIN_SIZE;
 		const int cx8 = (sub & 3) * 8, ry = sub >> 2;
 		RecList list;
-		list.wide = !high, list.lower = false;
+		list.wide = !high, list.lower = false, list.startx = cx8;
 		list.base = binLists(p, bin_id) + (high ? (size_t)sub * HB_LIST_CAP * 8 : (size_t)sub * MAX_BLOCK_TRIS * 16);
-		u32 *keys = count > SMEM_KEYS ? large_keys : ws.keys;
+		const bool large = count > SMEM_KEYS;
+		u32 *keys = large ? large_keys : ws.keys;
+		u32 *tie_tris = reinterpret_cast<u32 *>(ws.stage); // SMEM_KEYS words, idle until shading starts
 
-		// depth keys from the centroid of the covered pixels (raster.glsl:142-176)
-		for(int i = lane; i < count; i += 32) {
-			u32 depth;
-			if(high) {
-				uint2 rec = __ldg(reinterpret_cast<const uint2 *>(list.base) + i);
-				int nf, cx, cy;
-				rowsCentroid(rec.y, nf, cx, cy);
-				float scale = __fdiv_rn(0.5f, float(nf));
-				float cpx = float(cx) * scale + (float(cx8) + float(pos_x));
-				float cpy = float(cy) * scale + (float(ry * 4) + float(pos_y));
-				depth = blockDepth(p, rec.x, cpx, cpy, float(0x7fffe)) << 14;
-				frag_acc += (u32)nf;
-			} else {
-				uint4 rec = __ldg(reinterpret_cast<const uint4 *>(list.base) + i);
-				int nf0, cx0, cy0, nf1, cx1, cy1;
-				rowsCentroid(rec.y, nf0, cx0, cy0);
-				rowsCentroid(rec.z, nf1, cx1, cy1);
-				// both halves use row offsets 1,3,5,7 for the centroid, exactly as the reference does
-				float cx = float(cx0) + float(cx1), cy = float(cy0) + float(cy1);
-				float scale = __fdiv_rn(0.5f, float(nf0 + nf1));
-				float cpx = cx * scale + float(pos_x + cx8), cpy = cy * scale + float(pos_y + ry * 8);
-				depth = blockDepth(p, rec.x, cpx, cpy, float(0x3ffffe)) << 10;
-				frag_acc += (u32)(nf0 + nf1);
+		// depth keys from the centroid of the covered pixels (raster.glsl:142-176); four entries
+		// per lane are in flight.  The pass leaves (depth plane, constant colour) per entry in the
+		// warp's aux array for the shading loop.
+		for(int i0 = 0; i0 < count; i0 += 32 * KEY_UNROLL) {
+			uint4 rec[KEY_UNROLL], dq[KEY_UNROLL], misc[KEY_UNROLL];
+#pragma unroll
+			for(int u = 0; u < KEY_UNROLL; u++) {
+				const int i = i0 + u * 32 + lane;
+				rec[u] = make_uint4(0, 0, 0, 0);
+				if(i < count) {
+					if(high) {
+						uint2 r = __ldg(reinterpret_cast<const uint2 *>(list.base) + i);
+						rec[u].x = r.x, rec[u].y = r.y;
+					} else {
+						rec[u] = __ldg(reinterpret_cast<const uint4 *>(list.base) + i);
+					}
+				}
 			}
-			keys[i] = (u32)i | depth;
+#pragma unroll
+			for(int u = 0; u < KEY_UNROLL; u++) {
+				const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_shade + (rec[u].x & 0xffffffu));
+				dq[u] = __ldg(src), misc[u] = __ldg(src + 1);
+			}
+#pragma unroll
+			for(int u = 0; u < KEY_UNROLL; u++) {
+				const int i = i0 + u * 32 + lane;
+				if(i >= count)
+					continue;
+				u32 tri_idx, mins, maxs, depth;
+				if(high) {
+					unpackHighRecord(make_uint2(rec[u].x, rec[u].y), tri_idx, mins, maxs);
+					int nf, cx, cy;
+					rowsCentroid(mins, maxs, cx8, nf, cx, cy);
+					float scale = __fdiv_rn(0.5f, float(nf));
+					float cpx = float(cx) * scale + (float(cx8) + float(pos_x));
+					float cpy = float(cy) * scale + (float(ry * 4) + float(pos_y));
+					depth = blockDepth(dq[u], cpx, cpy, float(0x7fffe)) << 14;
+					frag_acc += (u32)nf;
+				} else {
+					int nf0, cx0, cy0, nf1, cx1, cy1;
+					unpackLowRecord(rec[u], false, tri_idx, mins, maxs);
+					rowsCentroid(mins, maxs, cx8, nf0, cx0, cy0);
+					unpackLowRecord(rec[u], true, tri_idx, mins, maxs);
+					rowsCentroid(mins, maxs, cx8, nf1, cx1, cy1);
+					// both halves use row offsets 1,3,5,7 for the centroid, exactly as the reference does
+					float cx = float(cx0) + float(cx1), cy = float(cy0) + float(cy1);
+					float scale = __fdiv_rn(0.5f, float(nf0 + nf1));
+					float cpx = cx * scale + float(pos_x + cx8), cpy = cy * scale + float(pos_y + ry * 8);
+					depth = blockDepth(dq[u], cpx, cpy, float(0x3ffffe)) << 10;
+					frag_acc += (u32)(nf0 + nf1);
+				}
+				keys[i] = (u32)i | depth;
+				if(!large)
+					tie_tris[i] = tri_idx;
+				__stcg(aux + i, make_uint4(dq[u].x, dq[u].y, dq[u].z, misc[u].w != 0 ? misc[u].z : AUX_VARYING));
+			}
 		}
 		__syncwarp();
 		// stats: LOW counts the block's triangles once per half-block (raster_low.glsl:272-275),
@@ -1158,25 +1235,23 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, 7)
 		hbt_acc += lane == 0 ? (u32)count * (high ? 1u : 2u) : 0u;
 		const int slot_bits = high ? 14 : 10;
 		if(high || count > 3) { // LOW blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
-			if(count > SMEM_KEYS)
+			if(large) {
 				warpSortLarge(keys, count, ws.keys);
-			else
+				warpFixDepthTies(keys, count, slot_bits, [&](u32 pos) {
+					return __ldg(reinterpret_cast<const uint2 *>(list.base) + pos).x & 0xffffffu;
+				});
+			} else {
 				warpSortShared(keys, count);
-			warpFixDepthTies(keys, count, slot_bits, [&](u32 pos) {
-				return high ? __ldg(reinterpret_cast<const uint2 *>(list.base) + pos).x
-							: __ldg(reinterpret_cast<const uint4 *>(list.base) + pos).x;
-			});
+				warpFixDepthTies(keys, count, slot_bits, [&](u32 pos) { return tie_tris[pos]; });
+			}
 		}
 		const u32 pos_mask = (1u << slot_bits) - 1u;
-		if(high) {
-			shadeHalfBlockAny(p, cfg, ws, keys, count, pos_mask, pos_x + cx8, pos_y + ry * 4, list);
-		} else {
-			shadeHalfBlockAny(p, cfg, ws, keys, count, pos_mask, pos_x + cx8, pos_y + ry * 8, list);
+		const int halves = high ? 1 : 2, hb_y = pos_y + ry * (high ? 4 : 8);
+		for(int half = 0; half < halves; half++) {
+			list.lower = half != 0;
+			shadeHalfBlockAny(p, cfg, ws, keys, aux, count, pos_mask, pos_x + cx8, hb_y + half * 4, list);
 			__syncwarp();
-			list.lower = true;
-			shadeHalfBlockAny(p, cfg, ws, keys, count, pos_mask, pos_x + cx8, pos_y + ry * 8 + 4, list);
 		}
-		__syncwarp();
 	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1) {
@@ -1263,7 +1338,7 @@ __global__ void __launch_bounds__(1024) k_promote(const Params p) {
 }
 
 static int rasterBinsGrid(int num_sms) { return num_sms * 4; }
-static int rasterBlocksGrid(int num_sms) { return num_sms * 7; }
+static int rasterBlocksGrid(int num_sms) { return num_sms * RB_MIN_CTAS; }
 size_t rasterLargeKeysCount(int num_sms) { return (size_t)rasterBlocksGrid(num_sms) * BLOCK_WARPS * MAX_HBLOCK_TRIS; }
 
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, cudaEvent_t *ev, int num_sms) {

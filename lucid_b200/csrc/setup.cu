@@ -229,7 +229,7 @@ __device__ void storeTri(const Params &p, const LucidConfig &cfg, u32 tri_idx, u
 						 constant ? shadeConstant(cfg.lighting, flags_id, inst_color, enc_normal) : 0u,
 						 constant ? 1u : 0u);
 	uint4 *dst = reinterpret_cast<uint4 *>(p.tri_shade + tri_idx);
-	dst[0] = sh.depth, dst[1] = sh.bary0, dst[2] = sh.bary1, dst[3] = sh.misc;
+	dst[0] = sh.depth, dst[1] = sh.misc, dst[2] = sh.bary0, dst[3] = sh.bary1;
 
 	F3 nrm0 = cross3(tri2, tri1 - tri2);
 	F3 nrm1 = cross3(tri0, tri2 - tri0);
