@@ -118,7 +118,7 @@ def algorithmic_bytes(stats: dict, scene, width, height):
     n_px = (stats["low_bins"] + stats["high_bins"]) * 1024
     setup = 64 * n_in + (4 + 2 * 96 + attr) * n_vis
     count = 4 * n_vis + 32 * 2 * stats["visible_large"]
-    dispatch = count + 4 * (n_bq + n_bt) * 2  # scatter + the canonicalising sort's read/write
+    dispatch = count + 4 * (n_bq + n_bt)
     raster = 4 * (n_bq + n_bt) + (96 + attr / 2) * t_bin + 4 * n_px
     return {"setup": setup, "bin_count": count, "bin_dispatch": dispatch, "raster": raster}
 
@@ -172,6 +172,7 @@ def run_ours(args):
             r.render(config_for(step), inst, cols, rects, **kw)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    frame_token = torch.zeros(1, device="cuda")
 
     def barrier():
         if dist is not None:
@@ -186,51 +187,62 @@ def run_ours(args):
     sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stage_acc = np.zeros(8, np.float64)
     t_wall = time.time()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)  # L2 flush between timed iterations (untimed)
         starts[k].record(stream)
         render(args.warmup + k, flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
+        if split:  # the frame is complete when every rank's strip has landed in rank 0's image
+            dist.all_reduce(frame_token)
         stops[k].record(stream)
-        if args.stage_times:
-            stage_acc += r.stage_times()
     barrier()
     wall = time.time() - t_wall
-    clocks = sampler.stop()
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)], np.float64)
     total_ms = torch.tensor([float(step_ms.sum())], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
+    # per-stage CUDA-event times of the frames of the timed region (the library keeps the events of
+    # its last 64 frames, recorded on the stream the kernels were launched on)
+    kept = min(args.steps, 64)
+    stage = np.mean([r.stage_times(i).astype(np.float64) for i in range(kept)], axis=0)
 
-    # end to end through the C ABI: host instance arrays in, RGBA8 image + LucidInfo back to host
-    host_img = np.zeros((height, width), np.uint32)
-    e2e_steps = max(3, min(args.steps, 10))
-    for w in range(2):
-        render(w) if split and rank != 0 else r.render(config_for(w), inst, cols, rects, out=host_img)
+    # end to end through the C ABI: host instance arrays in (the library stages them through pinned
+    # memory), RGBA8 image + LucidInfo read back into pinned host memory every frame.  Frames are
+    # submitted asynchronously: the copy-out of frame n overlaps the rendering of frame n+1.
+    host_imgs = [torch.empty((height, width), dtype=torch.int32).pin_memory() for _ in range(2)]
+    e2e_steps = max(args.steps, 3)
+
+    def e2e_frame(k):
+        if split:
+            # every rank rasterises its bin rows into rank 0's image, then rank 0 reads it back
+            render(k, flags=api.RENDER_ASYNC)
+            dist.all_reduce(frame_token)
+            if rank == 0:
+                torch.cuda.current_stream().synchronize()
+                r.read_image_into(host_imgs[k & 1].data_ptr())
+        else:
+            r.render(config_for(k), inst, cols, rects, out=host_imgs[k & 1].data_ptr(), flags=api.RENDER_ASYNC)
+
+    for w in range(3):
+        e2e_frame(w)
+    r.wait()
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        if split and rank != 0:
-            render(k)
-        else:
-            r.render(config_for(k), inst, cols, rects, out=host_img)
-        if split:
-            barrier()
+        e2e_frame(k)
+    r.wait()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+    clocks = sampler.stop()
 
     # counters of one frame for the roofline arithmetic
     r.render(config_for(0), inst, cols, rects)
     info = r.read_info()
     stats = api.decode_stats(info, r.bin_count, width, height)
-    stage = r.stage_times().astype(np.float64)
-    if args.stage_times and args.steps:
-        stage = stage_acc / args.steps
 
     frames_per_step = 1 if split else world
     tris_per_frame = 2 * stats["input_quads"]
@@ -241,7 +253,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         ab = algorithmic_bytes(stats, scene, width, height)
-        stage_names = ["setup", "bin_count", "bin_scan", "bin_dispatch", "raster_low", "raster_high", "finish"]
+        # LOW and HIGH bins share the two raster kernels (block lists, then block sort + shading)
+        stage_names = ["setup", "bin_count", "bin_scan", "bin_dispatch", "raster_lists", "raster_shade", "finish"]
         stage_ms = {n: round(float(stage[i]), 4) for i, n in enumerate(stage_names)}
         raster_ms = float(stage[4] + stage[5])
         fracs = {
@@ -280,7 +293,9 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(len(inst) * 36 + 352),
                     "d2h_bytes_per_step": int(width * height * 4 + info.size * 4)},
-            "gpu_launches": int(10 * args.steps),
+            # k_quad_setup, k_bin_count, k_bin_scan, k_bin_dispatch, k_raster_bins, k_raster_blocks,
+            # k_raster_finish, k_promote
+            "gpu_launches": int(8 * args.steps),
             "clocks": clocks,
             "wall_s": round(wall, 3),
         }
@@ -362,7 +377,6 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--mode", default="views", choices=["views", "split"])
     ap.add_argument("--mvq", type=int, default=0)
-    ap.add_argument("--stage-times", action="store_true", help="average per-stage ms over the timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

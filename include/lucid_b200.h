@@ -28,7 +28,9 @@ enum {
 enum { LUCID_MEM_HOST = 0, LUCID_MEM_DEVICE = 1, LUCID_MEM_NONE = 2 };
 
 enum {
-	LUCID_RENDER_ASYNC = 1,		  /* return after enqueueing; pair with lucid_wait() */
+	LUCID_RENDER_ASYNC = 1,		  /* return after enqueueing; pair with lucid_wait().  A host image is then
+									 copied out on a second stream while the next frame renders, so its
+									 buffer should be pinned and must not be reused before lucid_wait() */
 	LUCID_RENDER_SKIP_INFO = 2,	  /* do not copy LucidInfo back this frame */
 	LUCID_RENDER_FRAG_COUNTS = 4  /* also write the per-pixel fragment-count image (parity tests) */
 };
@@ -81,10 +83,14 @@ int lucid_wait(lucid_renderer *r);
 int lucid_read_info(lucid_renderer *r, uint32_t *dst, size_t num_words);
 int lucid_bin_count(const lucid_renderer *r);
 
-/* per-stage GPU milliseconds of the last frame (PERF_GPU_SCOPE replacement):
- * [0] setup [1] bin count [2] bin offsets/categories [3] bin dispatch+sort [4] raster low
- * [5] raster high [6] finish [7] whole frame */
+/* per-stage GPU milliseconds of the last frame (PERF_GPU_SCOPE replacement, lucid_renderer.cpp:323,
+ * 433,459,486,557,571): [0] quad setup [1] bin count [2] bin offsets + categories [3] bin dispatch
+ * [4] raster: block lists of all LOW and HIGH bins (generate rows / generate blocks)
+ * [5] raster: block sort + shading of all LOW and HIGH blocks [6] finish [7] whole frame.
+ * LOW and HIGH bins run in the same two kernels, so their time is not reported separately.
+ * lucid_stage_times_at: the frame `frames_back` frames ago (0 = last; 64 frames are kept). */
 int lucid_stage_times(lucid_renderer *r, float ms[8]);
+int lucid_stage_times_at(lucid_renderer *r, int32_t frames_back, float ms[8]);
 
 /* ---- inspection of intermediate buffers (what tests compare with the CPU checker) ---- */
 /* which: 0 small quads (slot i), 1 large quads (slot MVQ-1-i) */

@@ -80,7 +80,7 @@ _lib = None
 C_ABI_SYMBOLS = [
     "lucid_create", "lucid_destroy", "lucid_last_error", "lucid_set_geometry", "lucid_set_texture",
     "lucid_set_bin_rows", "lucid_render", "lucid_wait", "lucid_read_info", "lucid_bin_count",
-    "lucid_stage_times", "lucid_read_quad_aabbs", "lucid_read_tri_records", "lucid_read_quad_attrs",
+    "lucid_stage_times", "lucid_stage_times_at", "lucid_read_quad_aabbs", "lucid_read_tri_records", "lucid_read_quad_attrs",
     "lucid_read_bin_lists", "lucid_read_frag_counts", "lucid_read_image", "lucid_image_pointer",
     "lucid_ipc_export_image", "lucid_ipc_open_image", "lucid_ipc_close_image",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
@@ -118,6 +118,7 @@ def load_library(build_if_needed: bool = True):
     lib.lucid_read_info.argtypes = [vp, vp, C.c_size_t]
     lib.lucid_bin_count.argtypes = [vp]
     lib.lucid_stage_times.argtypes = [vp, C.POINTER(C.c_float * 8)]
+    lib.lucid_stage_times_at.argtypes = [vp, C.c_int32, C.POINTER(C.c_float * 8)]
     lib.lucid_read_quad_aabbs.argtypes = [vp, C.c_int32, vp, C.c_int32]
     lib.lucid_read_tri_records.argtypes = [vp, C.c_int32, vp, C.c_int32]
     lib.lucid_read_quad_attrs.argtypes = [vp, C.c_int32, vp, C.c_int32]
@@ -300,6 +301,8 @@ class LucidRenderer:
         uv_rects = None if uv_rects is None else np.ascontiguousarray(uv_rects, np.float32)
         if out_device_ptr is not None:
             mem, ptr, pitch = MEM_DEVICE, C.c_void_p(out_device_ptr), out_pitch or self.width * 4
+        elif isinstance(out, int):  # address of a (pinned) host image, e.g. torch tensor.data_ptr()
+            mem, ptr, pitch = MEM_HOST, C.c_void_p(out), out_pitch or self.width * 4
         elif out is not None:
             assert out.dtype == np.uint32 and out.shape == (self.height, self.width) and out.flags.c_contiguous
             mem, ptr, pitch = MEM_HOST, _ptr(out), self.width * 4
@@ -318,15 +321,19 @@ class LucidRenderer:
         self._check(self._lib.lucid_read_info(self._h, _ptr(out), out.size), "lucid_read_info")
         return out
 
-    def stage_times(self) -> np.ndarray:
+    def stage_times(self, frames_back: int = 0) -> np.ndarray:
         ms = (C.c_float * 8)()
-        self._check(self._lib.lucid_stage_times(self._h, C.byref(ms)), "lucid_stage_times")
+        self._check(self._lib.lucid_stage_times_at(self._h, frames_back, C.byref(ms)), "lucid_stage_times")
         return np.array(ms[:], np.float32)
 
     def read_image(self) -> np.ndarray:
         out = np.zeros((self.height, self.width), np.uint32)
         self._check(self._lib.lucid_read_image(self._h, _ptr(out), self.width * 4), "lucid_read_image")
         return out
+
+    def read_image_into(self, host_ptr: int, pitch: int | None = None):
+        self._check(self._lib.lucid_read_image(self._h, C.c_void_p(host_ptr), pitch or self.width * 4),
+                    "lucid_read_image")
 
     def read_frag_counts(self) -> np.ndarray:
         out = np.zeros((self.height, self.width), np.uint32)

@@ -4,7 +4,9 @@
 #include "../../include/lucid_b200.h"
 #include "common.cuh"
 
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -25,7 +27,17 @@ struct lucid_renderer {
 	std::vector<void *> owned;
 	void *geom_owned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	void *tex_owned[2] = {nullptr, nullptr};
-	u32 *image = nullptr;
+	// two renderer-owned images: while frame n is copied to the host on copy_stream, frame n+1
+	// renders into the other one (the reference double-buffers its per-frame data the same way,
+	// lucid_renderer.h:78-81)
+	u32 *images[2] = {nullptr, nullptr};
+	u32 *image = nullptr; // the one the last frame rendered into
+	int image_index = 0;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t render_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+	bool copy_pending[2] = {false, false};
+	cudaEvent_t upload_done[2] = {nullptr, nullptr};
+	bool upload_pending[2] = {false, false};
 	u32 *frag_counts = nullptr;
 	void *info_dev = nullptr;
 	size_t info_words = 0;
@@ -40,12 +52,16 @@ struct lucid_renderer {
 	bool has_geometry = false;
 	int num_quads = 0, num_verts = 0;
 
-	cudaEvent_t ev[10];
-	bool timing_valid = false;
+	// per-stage events of the last TIMING_RING frames
+	static constexpr int TIMING_RING = 64;
+	cudaEvent_t ev[TIMING_RING][8];
+	long long frame_counter = 0;
 	bool pending = false;
 };
 
 namespace {
+
+constexpr size_t STAGING_BYTES = (size_t)LUCID_MAX_INSTANCES * (16 + 4 + 16);
 
 int fail(lucid_renderer *r, int code, const std::string &msg) {
 	if(r)
@@ -87,9 +103,20 @@ void freeAll(lucid_renderer *r) {
 		cudaFreeHost(r->h_instances);
 	if(r->h_info)
 		cudaFreeHost(r->h_info);
-	for(auto &e : r->ev)
-		if(e)
-			cudaEventDestroy(e);
+	for(auto &set : r->ev)
+		for(auto &e : set)
+			if(e)
+				cudaEventDestroy(e);
+	for(int i = 0; i < 2; i++) {
+		if(r->render_done[i])
+			cudaEventDestroy(r->render_done[i]);
+		if(r->copy_done[i])
+			cudaEventDestroy(r->copy_done[i]);
+		if(r->upload_done[i])
+			cudaEventDestroy(r->upload_done[i]);
+	}
+	if(r->copy_stream)
+		cudaStreamDestroy(r->copy_stream);
 	if(r->own_stream && r->stream)
 		cudaStreamDestroy(r->stream);
 }
@@ -148,8 +175,14 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 		CUC(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
 		r->own_stream = true;
 	}
-	for(auto &ev : r->ev)
-		CUC(cudaEventCreate(&ev));
+	for(auto &set : r->ev)
+		for(auto &ev : set)
+			CUC(cudaEventCreate(&ev));
+	CUC(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+	for(int i = 0; i < 2; i++) {
+		CUC(cudaEventCreateWithFlags(&r->render_done[i], cudaEventDisableTiming));
+		CUC(cudaEventCreateWithFlags(&r->copy_done[i], cudaEventDisableTiming));
+	}
 
 	Params &p = r->p;
 	memset(&p, 0, sizeof(p));
@@ -199,16 +232,21 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 2));
 	CUC(devAlloc(r, &p.large_keys, rasterLargeKeysCount(r->num_sms)));
 	CUC(devAlloc(r, &p.block_aux, rasterLargeKeysCount(r->num_sms)));
-	CUC(devAlloc(r, &r->image, (size_t)p.width * p.height));
+	CUC(devAlloc(r, &r->images[0], (size_t)p.width * p.height));
+	CUC(devAlloc(r, &r->images[1], (size_t)p.width * p.height));
+	r->image = r->images[0];
 	CUC(devAlloc(r, &r->frag_counts, (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->d_instances, (size_t)LUCID_MAX_INSTANCES));
 	CUC(devAlloc(r, &r->d_inst_colors, (size_t)LUCID_MAX_INSTANCES));
 	CUC(devAlloc(r, &r->d_inst_uv_rects, (size_t)LUCID_MAX_INSTANCES));
 	p.instances = r->d_instances, p.inst_colors = r->d_inst_colors, p.inst_uv_rects = r->d_inst_uv_rects;
-	CUC(cudaMallocHost((void **)&r->h_instances, (size_t)LUCID_MAX_INSTANCES * (16 + 4 + 16)));
+	CUC(cudaMallocHost((void **)&r->h_instances, 2 * STAGING_BYTES));
+	for(int i = 0; i < 2; i++)
+		CUC(cudaEventCreateWithFlags(&r->upload_done[i], cudaEventDisableTiming));
 	CUC(cudaMallocHost((void **)&r->h_info, r->info_words * 4));
 	CUC(cudaMemsetAsync(r->info_dev, 0, r->info_words * 4, r->stream));
-	CUC(cudaMemsetAsync(r->image, 0, (size_t)p.width * p.height * 4, r->stream));
+	CUC(cudaMemsetAsync(r->images[0], 0, (size_t)p.width * p.height * 4, r->stream));
+	CUC(cudaMemsetAsync(r->images[1], 0, (size_t)p.width * p.height * 4, r->stream));
 	CUC(cudaStreamSynchronize(r->stream));
 #undef CUC
 	*out = r;
@@ -308,7 +346,10 @@ int lucid_wait(lucid_renderer *r) {
 		return LUCID_E_INVALID;
 	CU(cudaSetDevice(r->ci.device));
 	CU(cudaStreamSynchronize(r->stream));
+	CU(cudaStreamSynchronize(r->copy_stream));
 	r->pending = false;
+	r->copy_pending[0] = r->copy_pending[1] = false;
+	r->upload_pending[0] = r->upload_pending[1] = false;
 	CU(cudaGetLastError());
 	return LUCID_OK;
 }
@@ -334,13 +375,23 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	}
 	if(out_memory != LUCID_MEM_NONE && (!out_rgba8 || pitch_bytes < (size_t)p.width * 4 || (pitch_bytes & 3)))
 		return fail(r, LUCID_E_INVALID, "lucid_render: bad output image");
+	static const bool host_profile = getenv("LUCID_PROFILE_HOST") != nullptr;
+	static double t_acc[6] = {0, 0, 0, 0, 0, 0};
+	static long t_frames = 0;
+	auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t0 = host_profile ? now() : 0.0;
 	CU(cudaSetDevice(r->ci.device));
-	if(r->pending)
-		CU(cudaStreamSynchronize(r->stream));
 	cudaStream_t st = r->stream;
+	// two pinned staging blocks: the host fills one while the upload of the previous frame may
+	// still be queued behind that frame's kernels
+	const int sb = (int)(r->frame_counter & 1);
+	if(r->upload_pending[sb]) {
+		CU(cudaEventSynchronize(r->upload_done[sb]));
+		r->upload_pending[sb] = false;
+	}
 
 	// per-frame uploads (uploadInstances / setupInputData): one pinned staging block
-	unsigned char *h = r->h_instances;
+	unsigned char *h = r->h_instances + (size_t)sb * STAGING_BYTES;
 	size_t n = (size_t)num_instances;
 	memcpy(h, instances, n * 16);
 	memcpy(h + (size_t)LUCID_MAX_INSTANCES * 16, instance_colors, n * 4);
@@ -351,15 +402,6 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 		for(size_t i = 0; i < n; i++)
 			h_uv[i * 4] = 0.0f, h_uv[i * 4 + 1] = 0.0f, h_uv[i * 4 + 2] = 1.0f, h_uv[i * 4 + 3] = 1.0f;
 	}
-	if(n) {
-		CU(cudaMemcpyAsync(r->d_instances, h, n * 16, cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(r->d_inst_colors, h + (size_t)LUCID_MAX_INSTANCES * 16, n * 4,
-						   cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(r->d_inst_uv_rects, h_uv, n * 16, cudaMemcpyHostToDevice, st));
-	}
-	// LucidInfo and the first 6 per-bin counter arrays are cleared every frame (lucid_renderer.cpp:437)
-	CU(cudaMemsetAsync(r->info_dev, 0, (LUCID_INFO_U32_SIZE + (size_t)p.bin_count * 6) * 4, st));
-
 	LucidConfig cfg = *config;
 	cfg.num_instances = num_instances; // taken from this call, not the previous frame
 	p.num_instances = num_instances;
@@ -368,27 +410,63 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 		p.image = (u32 *)out_rgba8;
 		p.image_pitch = (int)(pitch_bytes / 4);
 	} else {
+		// frames that stay on the device always use image 0 (the one lucid_image_pointer and the
+		// IPC export name); frames copied to the host alternate
+		const int b = out_memory == LUCID_MEM_HOST ? (r->image_index ^ 1) : 0;
+		if(r->copy_pending[b]) // the image is still being copied out by an earlier frame
+			CU(cudaStreamWaitEvent(st, r->copy_done[b], 0));
+		r->image_index = b;
+		r->image = r->images[b];
 		p.image = r->image;
 		p.image_pitch = p.width;
 	}
 	p.frag_counts = (flags & LUCID_RENDER_FRAG_COUNTS) ? r->frag_counts : nullptr;
 
-	CU(cudaEventRecord(r->ev[0], st));
+	double t1 = host_profile ? now() : 0.0;
+	cudaEvent_t *ev = r->ev[r->frame_counter % lucid_renderer::TIMING_RING];
+	CU(cudaEventRecord(ev[0], st));
+	// per-frame uploads and clears (uploadInstances / setupInputData): one kernel reading the
+	// pinned staging block; LucidInfo and the first 6 per-bin arrays are cleared (lucid_renderer.cpp:437)
+	launchFrameBegin(p, h, h + (size_t)LUCID_MAX_INSTANCES * 16, h_uv, st);
+	CU(cudaEventRecord(r->upload_done[sb], st));
+	r->upload_pending[sb] = true;
 	launchQuadSetup(p, cfg, st);
-	CU(cudaEventRecord(r->ev[1], st));
-	launchBinning(p, st, &r->ev[2]); // ev[2] count, ev[3] scan, ev[4] dispatch+sort
-	launchRaster(p, cfg, st, &r->ev[5], r->num_sms); // ev[5] low, ev[6] high, ev[7] finish
+	CU(cudaEventRecord(ev[1], st));
+	double t2 = host_profile ? now() : 0.0;
+	launchBinning(p, st, &ev[2]);					// ev[2] count, ev[3] scan, ev[4] dispatch
+	double t3 = host_profile ? now() : 0.0;
+	launchRaster(p, cfg, st, &ev[5], r->num_sms); // ev[5] block lists, ev[6] sort + shade, ev[7] finish
 	CU(cudaGetLastError());
-	r->timing_valid = true;
+	r->frame_counter++;
+	double t4 = host_profile ? now() : 0.0;
 
 	if(!(flags & LUCID_RENDER_SKIP_INFO)) {
-		CU(cudaMemcpyAsync(r->h_info, r->info_dev, r->info_words * 4, cudaMemcpyDeviceToHost, st));
+		launchInfoOut(p, r->h_info, (int)r->info_words, st);
 		r->info_valid = true;
 	}
-	if(out_memory == LUCID_MEM_HOST)
-		CU(cudaMemcpy2DAsync(out_rgba8, pitch_bytes, r->image, (size_t)p.width * 4, (size_t)p.width * 4,
-							 p.height, cudaMemcpyDeviceToHost, st));
+	if(out_memory == LUCID_MEM_HOST) {
+		const int b = r->image_index;
+		CU(cudaEventRecord(r->render_done[b], st));
+		CU(cudaStreamWaitEvent(r->copy_stream, r->render_done[b], 0));
+		if(pitch_bytes == (size_t)p.width * 4)
+			CU(cudaMemcpyAsync(out_rgba8, r->image, pitch_bytes * p.height, cudaMemcpyDeviceToHost, r->copy_stream));
+		else
+			CU(cudaMemcpy2DAsync(out_rgba8, pitch_bytes, r->image, (size_t)p.width * 4, (size_t)p.width * 4,
+								 p.height, cudaMemcpyDeviceToHost, r->copy_stream));
+		CU(cudaEventRecord(r->copy_done[b], r->copy_stream));
+		r->copy_pending[b] = true;
+	}
 	r->pending = true;
+	if(host_profile) {
+		double t5 = now();
+		t_acc[0] += t1 - t0, t_acc[1] += t2 - t1, t_acc[2] += t3 - t2, t_acc[3] += t4 - t3, t_acc[4] += t5 - t4;
+		if(++t_frames % 100 == 0) {
+			fprintf(stderr, "lucid_render host us/frame: uploads %.1f setup %.1f binning %.1f raster %.1f readback %.1f\n",
+					t_acc[0] / 100, t_acc[1] / 100, t_acc[2] / 100, t_acc[3] / 100, t_acc[4] / 100);
+			for(double &t : t_acc)
+				t = 0;
+		}
+	}
 	if(!(flags & LUCID_RENDER_ASYNC))
 		return lucid_wait(r);
 	return LUCID_OK;
@@ -406,19 +484,22 @@ int lucid_read_info(lucid_renderer *r, uint32_t *dst, size_t num_words) {
 	return LUCID_OK;
 }
 
-int lucid_stage_times(lucid_renderer *r, float ms[8]) {
+int lucid_stage_times_at(lucid_renderer *r, int32_t frames_back, float ms[8]) {
 	if(!r || !ms)
 		return LUCID_E_INVALID;
-	if(!r->timing_valid)
-		return fail(r, LUCID_E_STATE, "lucid_stage_times: nothing rendered yet");
+	if(frames_back < 0 || frames_back >= lucid_renderer::TIMING_RING || frames_back >= r->frame_counter)
+		return fail(r, LUCID_E_STATE, "lucid_stage_times: no such frame in the timing history");
 	int rc = lucid_wait(r);
 	if(rc)
 		return rc;
+	cudaEvent_t *ev = r->ev[(r->frame_counter - 1 - frames_back) % lucid_renderer::TIMING_RING];
 	for(int i = 0; i < 7; i++)
-		CU(cudaEventElapsedTime(&ms[i], r->ev[i], r->ev[i + 1]));
-	CU(cudaEventElapsedTime(&ms[7], r->ev[0], r->ev[7]));
+		CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+	CU(cudaEventElapsedTime(&ms[7], ev[0], ev[7]));
 	return LUCID_OK;
 }
+
+int lucid_stage_times(lucid_renderer *r, float ms[8]) { return lucid_stage_times_at(r, 0, ms); }
 
 static int slotRange(lucid_renderer *r, int which, int count, size_t &first_slot) {
 	int rc = lucid_wait(r);

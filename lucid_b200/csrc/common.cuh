@@ -221,6 +221,9 @@ __device__ __forceinline__ u32 laneMaskLt() {
 }
 
 // kernel launchers (each in its own translation unit)
+void launchFrameBegin(const Params &p, const void *staged_instances, const void *staged_colors,
+					  const void *staged_uv_rects, cudaStream_t stream);
+void launchInfoOut(const Params &p, u32 *host_info, int num_words, cudaStream_t stream);
 void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream);
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *stage_events);
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream,

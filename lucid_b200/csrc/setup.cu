@@ -454,11 +454,49 @@ __global__ void __launch_bounds__(SETUP_THREADS)
 	}
 }
 
+// Start of a frame (uploadInstances + the clears of setupInputData, lucid_renderer.cpp:352-451):
+// pulls the instance arrays out of the pinned staging block over PCIe and zeroes LucidInfo, the
+// first six per-bin counter arrays and the setup look-back state.  A kernel instead of
+// cudaMemcpyAsync / cudaMemsetAsync keeps the copy engines free for the image read-back of the
+// previous frame, which runs concurrently on another stream.
+__global__ void __launch_bounds__(256) k_frame_begin(const Params p, const uint4 *staged_instances,
+													  const u32 *staged_colors, const uint4 *staged_uv_rects) {
+	const int stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+	for(int i = first; i < p.num_instances; i += stride) {
+		reinterpret_cast<uint4 *>(const_cast<LucidInstanceData *>(p.instances))[i] = staged_instances[i];
+		const_cast<u32 *>(p.inst_colors)[i] = staged_colors[i];
+		reinterpret_cast<uint4 *>(const_cast<float4 *>(p.inst_uv_rects))[i] = staged_uv_rects[i];
+	}
+	u32 *info = reinterpret_cast<u32 *>(p.info);
+	const int n_clear = (int)LUCID_INFO_U32_SIZE + p.bin_count * 6; // lucid_renderer.cpp:437
+	for(int i = first; i < n_clear; i += stride)
+		info[i] = 0;
+	for(int i = first; i < p.num_setup_ctas; i += stride)
+		p.setup_lookback[i] = 0;
+	if(first == 0)
+		*p.setup_ticket = 0;
+}
+
+// End of a frame: LucidInfo and the per-bin arrays go to the pinned read-back buffer
+// (m_info download, lucid_renderer.cpp:341-346) as posted PCIe writes
+__global__ void __launch_bounds__(256) k_info_out(const Params p, u32 *host_info, int num_words) {
+	const u32 *info = reinterpret_cast<const u32 *>(p.info);
+	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_words; i += gridDim.x * blockDim.x)
+		host_info[i] = info[i];
+}
+
+void launchFrameBegin(const Params &p, const void *staged_instances, const void *staged_colors,
+					  const void *staged_uv_rects, cudaStream_t stream) {
+	k_frame_begin<<<64, 256, 0, stream>>>(p, (const uint4 *)staged_instances, (const u32 *)staged_colors,
+										   (const uint4 *)staged_uv_rects);
+}
+void launchInfoOut(const Params &p, u32 *host_info, int num_words, cudaStream_t stream) {
+	k_info_out<<<32, 256, 0, stream>>>(p, host_info, num_words);
+}
+
 void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream) {
 	if(p.num_setup_ctas == 0)
 		return;
-	cudaMemsetAsync(p.setup_lookback, 0, (size_t)p.num_setup_ctas * sizeof(u64), stream);
-	cudaMemsetAsync(p.setup_ticket, 0, sizeof(u32), stream);
 	k_quad_setup<<<p.num_setup_ctas, SETUP_THREADS, 0, stream>>>(p, cfg);
 }
 

@@ -1,0 +1,145 @@
+// Exercises the C++ LucidRenderer facade (include/lucid_renderer.hpp) the way the reference's
+// application drives its renderer (src/lucid_app.cpp:621-665): construct, fill a RenderContext,
+// render, verifyInfo, getStats.  Scene: the reference's "#planes" known-answer fixture
+// (src/scene_setup.cpp:101-102: N stacked quads, one opacity) -- every covered pixel must hold the
+// analytic N-layer front-to-back blend of the truncated RGBA8 sample colour.
+//
+//   test_renderer              full check on cuda:0, exit code 0 on success
+//   test_renderer --no-device  expects exConstruct to fail cleanly (no CUDA device, no fallback)
+#include "lucid_renderer.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+using namespace lucid_b200;
+
+static int fail(const char *what) {
+	printf("FAIL: %s\n", what);
+	return 1;
+}
+
+int main(int argc, char **argv) {
+	const bool expect_no_device = argc > 1 && strcmp(argv[1], "--no-device") == 0;
+	LucidRenderer renderer;
+	const int width = 256, height = 192;
+	Ex ex = renderer.exConstruct(LucidRenderOpt::visualize_errors, int2{width, height}, 0, 1 << 16);
+	if(expect_no_device) {
+		if(ex)
+			return fail("exConstruct succeeded although no device was expected");
+		printf("exConstruct failed as expected: %s\n", ex.message.c_str());
+		Ex again = renderer.render(RenderContext());
+		return again ? fail("render succeeded without a renderer") : 0;
+	}
+	if(!ex)
+		return fail(ex.message.c_str());
+
+	// N planes facing the camera, z = 0 .. -(N-1) * dist, half size 2
+	const int num_planes = 32;
+	const float opacity = 0.25f, dist = 0.05f, hs = 2.0f;
+	std::vector<float> positions;
+	std::vector<uint32_t> quads;
+	for(int i = 0; i < num_planes; i++) {
+		float z = -dist * i;
+		const float corners[4][2] = {{-hs, -hs}, {hs, -hs}, {hs, hs}, {-hs, hs}};
+		for(auto &c : corners) {
+			positions.push_back(c[0]), positions.push_back(c[1]), positions.push_back(z);
+		}
+		for(uint32_t k = 0; k < 4; k++)
+			quads.push_back(uint32_t(i) * 4 + k);
+	}
+
+	RenderContext ctx;
+	ctx.verts.positions = positions.data();
+	ctx.verts.num_verts = (int)positions.size() / 3;
+	ctx.quads_ib = quads.data();
+	ctx.num_quads = num_planes;
+	ctx.memory = LUCID_MEM_HOST;
+	SceneMaterial mat;
+	mat.diffuse[0] = 0.9f, mat.diffuse[1] = 0.5f, mat.diffuse[2] = 0.2f;
+	mat.opacity = opacity;
+	ctx.materials.push_back(mat);
+	SceneDrawCall dc;
+	dc.material_id = 0, dc.num_quads = num_planes, dc.quad_offset = 0, dc.opts = 0;
+	ctx.dcs.push_back(dc);
+	lucid_host_default_lighting(&ctx.lighting);
+	const float center[3] = {0.0f, 0.0f, 0.0f};
+	lucid_host_orbit_camera(center, 6.0f, 0.0f, 0.0f, 60.0f * 3.14159265f / 180.0f, 1.0f / 16.0f, 1024.0f, width,
+							height, &ctx.camera);
+	std::vector<uint32_t> image((size_t)width * height, 0u);
+	ctx.out_image = image.data();
+	ctx.out_pitch_bytes = (size_t)width * 4;
+	ctx.out_memory = LUCID_MEM_HOST;
+
+	ex = renderer.render(ctx);
+	if(!ex)
+		return fail(ex.message.c_str());
+	if(renderer.verifyInfo() != 0)
+		return fail("verifyInfo reported invalid offsets");
+	const LucidInfo &info = renderer.lastInfo();
+	printf("input quads %d, visible %d + %d, fragments %u, half-block-tris %u, invalid pixels %u\n",
+		   info.num_input_quads, info.num_visible_quads[0], info.num_visible_quads[1], info.stats[0], info.stats[1],
+		   info.stats[2]);
+	if(info.num_input_quads != num_planes)
+		return fail("num_input_quads");
+	if(info.stats[2] != 0)
+		return fail("window overflow on a depth-sorted stack of planes");
+
+	// per pixel: count layers by unblending is fragile; instead use the closed form.  Every sample of
+	// every plane has the same RGBA8 colour c (flat normal, instance colour), so a pixel covered by
+	// k planes holds  c * (1 - (1-a)^k) + bg * (1-a)^k  with a = alpha8 / 255.
+	const uint32_t bg = 0xff1e1e00u;
+	uint32_t center_px = image[(size_t)(height / 2) * width + width / 2];
+	if(center_px == bg)
+		return fail("centre pixel not covered");
+	// recover the sample colour from a pixel covered by exactly one... all planes overlap at the
+	// centre, so solve for c there and check every other covered pixel against k in [1, N]
+	const float a = float((uint32_t)(opacity * 255.0f)) / 255.0f;
+	const float tN = std::pow(1.0f - a, (float)num_planes);
+	float c[3];
+	for(int ch = 0; ch < 3; ch++) {
+		float px = float((center_px >> (8 * ch)) & 0xff) / 255.0f, b = float((bg >> (8 * ch)) & 0xff) / 255.0f;
+		c[ch] = (px - b * tN) / (1.0f - tN);
+	}
+	long long covered = 0, mismatched = 0, frag_sum = 0;
+	for(size_t i = 0; i < image.size(); i++) {
+		if(image[i] == bg)
+			continue;
+		covered++;
+		int best_err = 1000, best_k = 0;
+		for(int k = 1; k <= num_planes; k++) {
+			float t = std::pow(1.0f - a, (float)k);
+			int err = 0;
+			for(int ch = 0; ch < 3; ch++) {
+				float b = float((bg >> (8 * ch)) & 0xff) / 255.0f;
+				int expect = (int)std::lround((c[ch] * (1.0f - t) + b * t) * 255.0f);
+				int got = (int)((image[i] >> (8 * ch)) & 0xff);
+				err = std::max(err, std::abs(expect - got));
+			}
+			if(err < best_err)
+				best_err = err, best_k = k;
+		}
+		if(best_err > 2) // 1/255 for the solved colour + 1/255 rounding
+			mismatched++;
+		frag_sum += best_k;
+	}
+	printf("covered pixels %lld, mismatched %lld, layers summed %lld\n", covered, mismatched, frag_sum);
+	if(covered == 0 || mismatched != 0)
+		return fail("covered pixels do not follow the N-layer blend");
+	// the layer count is only identifiable while (1-a)^k still changes the 8-bit value
+	if(frag_sum > (long long)info.stats[0])
+		return fail("more layers seen in the image than fragments counted");
+
+	for(const StatsGroup &g : renderer.getStats()) {
+		printf("[%s]\n", g.title.c_str());
+		for(const StatsRow &row : g.rows)
+			printf("  %-28s %s\n", row.label.c_str(), row.value.c_str());
+	}
+	float ms[8];
+	if(!renderer.stageTimes(ms))
+		return fail("stageTimes");
+	printf("frame %.3f ms\n", ms[7]);
+	printf("OK\n");
+	return 0;
+}
