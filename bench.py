@@ -295,9 +295,9 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(len(inst) * 36 + 352),
                     "d2h_bytes_per_step": int(width * height * 4 + info.size * 4)},
-            # k_quad_setup, k_bin_count, k_bin_scan, k_bin_dispatch, k_raster_bins, k_raster_blocks,
-            # k_raster_finish, k_promote
-            "gpu_launches": int(8 * args.steps),
+            # k_frame_begin, k_quad_cull, k_tri_setup, k_bin_count, k_bin_scan, k_bin_dispatch, k_raster_bins,
+            # k_raster_blocks, k_raster_finish, k_promote (+ k_info_out when LucidInfo is read back)
+            "gpu_launches": int(10 * args.steps),
             "clocks": clocks,
             "wall_s": round(wall, 3),
         }

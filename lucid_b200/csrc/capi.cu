@@ -25,7 +25,7 @@ struct lucid_renderer {
 
 	// owned device allocations
 	std::vector<void *> owned;
-	void *geom_owned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	void *geom_owned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [5] padded positions
 	void *tex_owned[2] = {nullptr, nullptr};
 	// two renderer-owned images: while frame n is copied to the host on copy_stream, frame n+1
 	// renders into the other one (the reference double-buffers its per-frame data the same way,
@@ -208,6 +208,8 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 
 	const size_t mvq = (size_t)p.max_visible_quads;
 	CUC(devAlloc(r, &p.quad_aabbs, mvq));
+	CUC(devAlloc(r, &p.quad_verts, mvq));
+	CUC(devAlloc(r, &p.quad_setup_info, mvq));
 	CUC(devAlloc(r, &p.tri_scan, mvq * 2));
 	CUC(devAlloc(r, &p.tri_shade, mvq * 2));
 	CUC(devAlloc(r, &p.quad_colors, mvq));
@@ -312,6 +314,10 @@ int lucid_set_geometry(lucid_renderer *r, const float *positions, int32_t num_ve
 	}
 	if(((uintptr_t)p.quad_indices & 15) != 0)
 		return fail(r, LUCID_E_INVALID, "lucid_set_geometry: quad indices must be 16-byte aligned");
+	CU(cudaMalloc(&r->geom_owned[5], (size_t)num_verts * 16));
+	p.positions4 = (const float4 *)r->geom_owned[5];
+	launchPadPositions(p.positions, (float4 *)r->geom_owned[5], num_verts, r->stream);
+	CU(cudaStreamSynchronize(r->stream));
 	r->num_quads = num_quads, r->num_verts = num_verts;
 	r->has_geometry = true;
 	return LUCID_OK;
@@ -405,7 +411,7 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	LucidConfig cfg = *config;
 	cfg.num_instances = num_instances; // taken from this call, not the previous frame
 	p.num_instances = num_instances;
-	p.num_setup_ctas = num_instances * (LUCID_MAX_INSTANCE_QUADS / 256);
+	p.num_setup_ctas = num_instances; // one k_quad_cull CTA per instance
 	if(out_memory == LUCID_MEM_DEVICE) {
 		p.image = (u32 *)out_rgba8;
 		p.image_pitch = (int)(pitch_bytes / 4);

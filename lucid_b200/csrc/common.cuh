@@ -49,6 +49,7 @@ struct Params {
 
 	// caller geometry (device pointers)
 	const float *positions;
+	const float4 *positions4; // 16-byte padded copy of positions (renderer-owned)
 	const uint4 *quad_indices;
 	const u32 *vertex_colors;
 	const float2 *vertex_uvs;
@@ -60,6 +61,8 @@ struct Params {
 
 	// renderer-owned storage
 	u32 *quad_aabbs;
+	uint4 *quad_verts;		// per visible slot: the quad's vertex indices (k_quad_cull -> k_tri_setup)
+	uint4 *quad_setup_info; // per visible slot: y range of both triangles, instance id
 	TriScan *tri_scan;
 	TriShade *tri_shade;
 	uint4 *quad_colors;
@@ -225,6 +228,7 @@ void launchFrameBegin(const Params &p, const void *staged_instances, const void 
 					  const void *staged_uv_rects, cudaStream_t stream);
 void launchInfoOut(const Params &p, u32 *host_info, int num_words, cudaStream_t stream);
 void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream);
+void launchPadPositions(const float *positions, float4 *positions4, int num_verts, cudaStream_t stream);
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *stage_events);
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream,
 				  cudaEvent_t *stage_events, int num_sms);

@@ -1,11 +1,12 @@
 // setup.cu -- quad/triangle setup for sm_100a.
 //
 // Replaces data/shaders/quad_setup.glsl (reference file:line cited per function).  What changes
-// against the reference's structure: one 256-thread CTA per quarter instance instead of a
-// 1024-thread work group per instance packet; the two global atomicAdd compactions
-// (quad_setup.glsl:415-421) become a single-pass decoupled look-back scan over CTAs taken in
-// ticket order, so visible-quad slots are a pure function of the input order (deterministic);
-// per-sample triangle fields are written as one 64-byte record.
+// against the reference's structure: the work is split into k_quad_cull (one thread per input
+// quad: culling, bin AABB, compaction) and k_tri_setup (one thread per visible triangle: the
+// equations), so the expensive part runs barrier-free at full occupancy over compacted slots; the
+// two global atomicAdd compactions (quad_setup.glsl:415-421) become a single-pass decoupled
+// look-back scan over CTAs taken in ticket order, so visible-quad slots are a pure function of the
+// input order (deterministic); per-sample triangle fields are written as one 64-byte record.
 #include "common.cuh"
 
 namespace lucid {
@@ -13,9 +14,18 @@ namespace lucid {
 constexpr int SETUP_THREADS = 256;
 constexpr int SETUP_PARTS = LUCID_MAX_INSTANCE_QUADS / SETUP_THREADS;
 
+// positions are read from a 16-byte padded copy made once per lucid_set_geometry: one 128-bit load
+// per vertex instead of three scalar ones on the tightly packed float3 array (quad_setup.glsl:64-66)
 __device__ __forceinline__ F3 vertexLoad(const Params &p, u32 vi) {
-	const float *v = p.positions + (size_t)vi * 3;
-	return mk3(__ldg(v), __ldg(v + 1), __ldg(v + 2));
+	float4 v = __ldg(p.positions4 + vi);
+	return mk3(v.x, v.y, v.z);
+}
+__global__ void __launch_bounds__(256) k_pad_positions(const float *positions, float4 *positions4, int num_verts) {
+	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_verts; i += gridDim.x * blockDim.x)
+		positions4[i] = make_float4(positions[(size_t)i * 3], positions[(size_t)i * 3 + 1], positions[(size_t)i * 3 + 2], 1.0f);
+}
+void launchPadPositions(const float *positions, float4 *positions4, int num_verts, cudaStream_t stream) {
+	k_pad_positions<<<148 * 4, 256, 0, stream>>>(positions, positions4, num_verts);
 }
 
 __device__ __forceinline__ u32 vertexClipMask(float4 v) {
@@ -266,18 +276,16 @@ __device__ __forceinline__ void lbStore(u64 *ptr, u64 v) {
 	*reinterpret_cast<volatile u64 *>(ptr) = v;
 }
 
-struct KeptQuad {
-	uint4 verts;
-	u32 enc_aabb, y_aabb0, y_aabb1;
-	int slot;
-};
-
-__global__ void __launch_bounds__(SETUP_THREADS)
-	k_quad_setup(const Params p, const __grid_constant__ LucidConfig cfg) {
-	__shared__ KeptQuad s_kept[SETUP_THREADS];
+// k_quad_cull: culling, bin AABB, small/large split and the ordered compaction into visible-quad
+// slots (quad_setup.glsl:136-254,374-489).  One 256-thread CTA per instance; a thread handles the
+// quads tid, tid + 256, ... of the instance, so the loads of up to four quads are in flight
+// together and one look-back step covers 1024 quads.  The per-triangle records are left to
+// k_tri_setup, which runs over the compacted slots without any barrier.
+__global__ void __launch_bounds__(SETUP_THREADS, 3)
+	k_quad_cull(const Params p, const __grid_constant__ LucidConfig cfg) {
 	__shared__ u32 s_vid;
-	__shared__ int s_warp_counts[SETUP_THREADS / 32][2];
-	__shared__ int s_base[2], s_total[2];
+	__shared__ int s_counts[SETUP_PARTS * (SETUP_THREADS / 32)][2]; // per (part, warp): small, large
+	__shared__ int s_base[2];
 	__shared__ u32 s_rejected[LUCID_REJECTION_TYPE_COUNT];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -288,55 +296,64 @@ __global__ void __launch_bounds__(SETUP_THREADS)
 	if(tid < LUCID_REJECTION_TYPE_COUNT)
 		s_rejected[tid] = 0;
 	__syncthreads();
-	const u32 vid = s_vid;
-	const int inst_id = vid / SETUP_PARTS, part = vid % SETUP_PARTS;
+	const u32 inst_id = s_vid;
 	const LucidInstanceData inst = p.instances[inst_id];
-	const int local_quad = part * SETUP_THREADS + tid;
-	const bool has_quad = local_quad < inst.num_quads;
-	if(part == 0 && tid == 0)
+	if(tid == 0)
 		atomicAdd(&p.info->num_input_quads, inst.num_quads);
 
-	uint4 vi = make_uint4(0, 0, 0, 0);
-	QuadResult res;
-	res.status = -3, res.size_type = 0, res.enc_aabb = 0, res.y_aabb0 = res.y_aabb1 = 0;
-	if(has_quad) {
-		// one 128-bit load per quad: the index buffer is 4 x u32 per quad (quad_setup.glsl:405-409)
-		const uint4 *ib = reinterpret_cast<const uint4 *>(
-			reinterpret_cast<const u32 *>(p.quad_indices) + inst.index_offset);
-		vi = __ldg(ib + local_quad);
-		vi.x += inst.vertex_offset, vi.y += inst.vertex_offset;
-		vi.z += inst.vertex_offset, vi.w += inst.vertex_offset;
-		res = processInputQuad(p, cfg, vi);
-	}
-
-	// ordered ranks of small / large visible quads inside the CTA
-	const bool vis = res.status == -1;
-	const bool is_small = vis && res.size_type == 0, is_large = vis && res.size_type == 1;
-	const u32 bs = __ballot_sync(0xffffffffu, is_small), bl = __ballot_sync(0xffffffffu, is_large);
-	{
-		// warp-aggregated rejection counters
-		int key = res.status >= 0 ? res.status : LUCID_REJECTION_TYPE_COUNT;
-		u32 peers = __match_any_sync(0xffffffffu, key);
-		if(res.status >= 0 && lane == __ffs(peers) - 1)
-			atomicAdd(&s_rejected[res.status], __popc(peers));
-	}
-	if(lane == 0)
-		s_warp_counts[warp][0] = __popc(bs), s_warp_counts[warp][1] = __popc(bl);
-	__syncthreads();
-	int before_small = __popc(bs & laneMaskLt()), before_large = __popc(bl & laneMaskLt());
-	int total_small = 0, total_large = 0;
+	uint4 vi[SETUP_PARTS];
+	QuadResult res[SETUP_PARTS];
+	// one 128-bit load per quad: the index buffer is 4 x u32 per quad (quad_setup.glsl:405-409)
+	const uint4 *ib = reinterpret_cast<const uint4 *>(reinterpret_cast<const u32 *>(p.quad_indices) + inst.index_offset);
 #pragma unroll
-	for(int w = 0; w < SETUP_THREADS / 32; w++) {
-		int cs = s_warp_counts[w][0], cl = s_warp_counts[w][1];
-		if(w < warp)
-			before_small += cs, before_large += cl;
-		total_small += cs, total_large += cl;
+	for(int k = 0; k < SETUP_PARTS; k++) {
+		const int local_quad = k * SETUP_THREADS + tid;
+		vi[k] = make_uint4(0, 0, 0, 0);
+		if(local_quad < inst.num_quads) {
+			vi[k] = __ldg(ib + local_quad);
+			vi[k].x += inst.vertex_offset, vi[k].y += inst.vertex_offset;
+			vi[k].z += inst.vertex_offset, vi[k].w += inst.vertex_offset;
+		}
 	}
+	int before_small[SETUP_PARTS], before_large[SETUP_PARTS];
+#pragma unroll
+	for(int k = 0; k < SETUP_PARTS; k++) {
+		const int local_quad = k * SETUP_THREADS + tid;
+		res[k].status = -3, res[k].size_type = 0, res[k].enc_aabb = 0, res[k].y_aabb0 = res[k].y_aabb1 = 0;
+		if(local_quad < inst.num_quads)
+			res[k] = processInputQuad(p, cfg, vi[k]);
+		const bool vis = res[k].status == -1;
+		const u32 bs = __ballot_sync(0xffffffffu, vis && res[k].size_type == 0);
+		const u32 bl = __ballot_sync(0xffffffffu, vis && res[k].size_type == 1);
+		// warp-aggregated rejection counters
+		int key = res[k].status >= 0 ? res[k].status : LUCID_REJECTION_TYPE_COUNT;
+		u32 peers = __match_any_sync(0xffffffffu, key);
+		if(res[k].status >= 0 && lane == __ffs(peers) - 1)
+			atomicAdd(&s_rejected[res[k].status], __popc(peers));
+		if(lane == 0)
+			s_counts[k * (SETUP_THREADS / 32) + warp][0] = __popc(bs), s_counts[k * (SETUP_THREADS / 32) + warp][1] = __popc(bl);
+		before_small[k] = __popc(bs & laneMaskLt()), before_large[k] = __popc(bl & laneMaskLt());
+	}
+	__syncthreads();
 
-	// decoupled look-back over (small, large) counts
+	// warp 0: exclusive scan of the 32 (part, warp) counts in input order, then the decoupled
+	// look-back over the CTAs' (small, large) totals
 	if(warp == 0) {
+		static_assert(SETUP_PARTS * (SETUP_THREADS / 32) == 32, "one count pair per lane");
+		int cs = s_counts[lane][0], cl = s_counts[lane][1];
+		int is = cs, il = cl;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			int ts = __shfl_up_sync(0xffffffffu, is, o), tl = __shfl_up_sync(0xffffffffu, il, o);
+			if(lane >= o)
+				is += ts, il += tl;
+		}
+		s_counts[lane][0] = is - cs, s_counts[lane][1] = il - cl;
+		const u32 total_small = __shfl_sync(0xffffffffu, is, 31), total_large = __shfl_sync(0xffffffffu, il, 31);
+
 		u64 *lb = p.setup_lookback;
 		u32 ex_small = 0, ex_large = 0;
+		const u32 vid = inst_id;
 		if(vid == 0) {
 			if(lane == 0)
 				lbStore(lb, lbPack(LB_PREFIX, total_small, total_large));
@@ -353,14 +370,14 @@ __global__ void __launch_bounds__(SETUP_THREADS)
 				}
 				u32 pm = __ballot_sync(0xffffffffu, (st & LB_STATUS) == LB_PREFIX);
 				int first = pm ? __ffs(pm) - 1 : 32;
-				u32 cs = lane <= first ? (u32)((st >> 31) & 0x7fffffffu) : 0u;
-				u32 cl = lane <= first ? (u32)(st & 0x7fffffffu) : 0u;
+				u32 ps = lane <= first ? (u32)((st >> 31) & 0x7fffffffu) : 0u;
+				u32 pl = lane <= first ? (u32)(st & 0x7fffffffu) : 0u;
 #pragma unroll
 				for(int o = 16; o > 0; o >>= 1) {
-					cs += __shfl_xor_sync(0xffffffffu, cs, o);
-					cl += __shfl_xor_sync(0xffffffffu, cl, o);
+					ps += __shfl_xor_sync(0xffffffffu, ps, o);
+					pl += __shfl_xor_sync(0xffffffffu, pl, o);
 				}
-				ex_small += cs, ex_large += cl;
+				ex_small += ps, ex_large += pl;
 				if(pm)
 					break;
 				base -= 32;
@@ -368,88 +385,91 @@ __global__ void __launch_bounds__(SETUP_THREADS)
 			if(lane == 0)
 				lbStore(lb + vid, lbPack(LB_PREFIX, ex_small + total_small, ex_large + total_large));
 		}
-		if(lane == 0) {
+		if(lane == 0)
 			s_base[0] = ex_small, s_base[1] = ex_large;
-			s_total[0] = total_small, s_total[1] = total_large;
-		}
 	}
 	__syncthreads();
 
 	// slot assignment; quads past MAX_VISIBLE_QUADS (in input order) are dropped and counted
 	const int mvq = p.max_visible_quads;
-	int slot = -1;
-	if(vis) {
-		int gs = s_base[0] + before_small, gl = s_base[1] + before_large;
-		if(gs + gl < mvq)
-			slot = is_small ? gs : (mvq - 1) - gl;
-	}
-	{
-		u32 ks = __ballot_sync(0xffffffffu, slot >= 0 && is_small);
-		u32 kl = __ballot_sync(0xffffffffu, slot >= 0 && is_large);
-		u32 dr = __ballot_sync(0xffffffffu, vis && slot < 0);
-		if(lane == 0) {
-			if(ks)
-				atomicAdd(&p.info->num_visible_quads[0], __popc(ks));
-			if(kl)
-				atomicAdd(&p.info->num_visible_quads[1], __popc(kl));
-			if(dr)
-				atomicAdd(&p.info->temp[0], __popc(dr));
+	int n_small = 0, n_large = 0, n_dropped = 0;
+#pragma unroll
+	for(int k = 0; k < SETUP_PARTS; k++) {
+		const bool vis = res[k].status == -1;
+		if(!vis)
+			continue;
+		const bool is_small = res[k].size_type == 0;
+		const int w = k * (SETUP_THREADS / 32) + warp;
+		int gs = s_base[0] + s_counts[w][0] + before_small[k], gl = s_base[1] + s_counts[w][1] + before_large[k];
+		if(gs + gl < mvq) {
+			const int slot = is_small ? gs : (mvq - 1) - gl;
+			p.quad_aabbs[slot] = res[k].enc_aabb;
+			p.quad_verts[slot] = vi[k];
+			p.quad_setup_info[slot] = make_uint4(res[k].y_aabb0, res[k].y_aabb1, inst_id, 0u);
+			n_small += is_small ? 1 : 0, n_large += is_small ? 0 : 1;
+		} else {
+			n_dropped++;
 		}
 	}
-	const int n_entries = s_total[0] + s_total[1];
-	if(vis) {
-		int e = is_small ? before_small : s_total[0] + before_large;
-		KeptQuad k;
-		k.verts = vi, k.enc_aabb = res.enc_aabb, k.y_aabb0 = res.y_aabb0, k.y_aabb1 = res.y_aabb1;
-		k.slot = slot;
-		s_kept[e] = k;
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) {
+		n_small += __shfl_xor_sync(0xffffffffu, n_small, o);
+		n_large += __shfl_xor_sync(0xffffffffu, n_large, o);
+		n_dropped += __shfl_xor_sync(0xffffffffu, n_dropped, o);
+	}
+	if(lane == 0) {
+		if(n_small)
+			atomicAdd(&p.info->num_visible_quads[0], n_small);
+		if(n_large)
+			atomicAdd(&p.info->num_visible_quads[1], n_large);
+		if(n_dropped)
+			atomicAdd(&p.info->temp[0], n_dropped);
 	}
 	if(tid < LUCID_REJECTION_TYPE_COUNT && s_rejected[tid] != 0)
 		atomicAdd(&p.info->num_rejected_quads[tid], s_rejected[tid]);
-	__syncthreads();
+}
 
-	// triangle records: all threads share the visible triangles evenly (two per kept quad)
+// k_tri_setup: one thread per triangle of a visible quad (storeTri / storeQuad,
+// quad_setup.glsl:256-340): plane, barycentric and scanline equations, attribute repack
+__global__ void __launch_bounds__(SETUP_THREADS) k_tri_setup(const Params p, const __grid_constant__ LucidConfig cfg) {
+	const int n_small = p.info->num_visible_quads[0], n_large = p.info->num_visible_quads[1];
+	const int n_tris = (n_small + n_large) * 2;
 	const F3 dir0 = xyz(cfg.frustum.ws_dir0), dirx = xyz(cfg.frustum.ws_dirx);
 	const F3 diry = xyz(cfg.frustum.ws_diry), origin = xyz(cfg.frustum.ws_origin0);
 	const F3 ray_dir0 = dir0 + (dirx + diry) * 0.5f;
-	const u32 flags_id = inst.flags | ((u32)inst_id << 16);
-	const u32 inst_color = p.inst_colors[inst_id];
-	for(int j = tid; j < n_entries * 2; j += SETUP_THREADS) {
-		const KeptQuad &k = s_kept[j >> 1];
-		int second = j & 1;
-		if(k.slot < 0 || ((k.enc_aabb >> (30 + second)) & 1))
+	for(int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tris; t += gridDim.x * blockDim.x) {
+		const int q = t >> 1, second = t & 1;
+		const int slot = q < n_small ? q : (p.max_visible_quads - 1) - (q - n_small);
+		const u32 enc_aabb = p.quad_aabbs[slot];
+		const uint4 v = p.quad_verts[slot];
+		const uint4 qi = p.quad_setup_info[slot];
+		const u32 inst_id = qi.z;
+		const u32 flags = __ldg(&p.instances[inst_id].flags);
+		if(((enc_aabb >> (30 + second)) & 1) == 0) {
+			u32 i1 = second ? v.z : v.y, i2 = second ? v.w : v.z;
+			F3 t0 = vertexLoad(p, v.x) - origin;
+			F3 t1 = vertexLoad(p, i1) - origin;
+			F3 t2 = vertexLoad(p, i2) - origin;
+			storeTri(p, cfg, (u32)slot * 2 + second, flags | (inst_id << 16), __ldg(p.inst_colors + inst_id), t0, t1,
+					 t2, second ? qi.y : qi.x, ray_dir0);
+		}
+		if(second)
 			continue;
-		u32 i1 = second ? k.verts.z : k.verts.y, i2 = second ? k.verts.w : k.verts.z;
-		F3 t0 = vertexLoad(p, k.verts.x) - origin;
-		F3 t1 = vertexLoad(p, i1) - origin;
-		F3 t2 = vertexLoad(p, i2) - origin;
-		storeTri(p, cfg, (u32)k.slot * 2 + second, flags_id, inst_color, t0, t1, t2,
-				 second ? k.y_aabb1 : k.y_aabb0, ray_dir0);
-	}
-	// quad records (quad_setup.glsl:256-272, 342-354)
-	for(int e = tid; e < n_entries; e += SETUP_THREADS) {
-		const KeptQuad &k = s_kept[e];
-		if(k.slot < 0)
-			continue;
-		p.quad_aabbs[k.slot] = k.enc_aabb;
-		uint4 v = k.verts;
-		if((inst.flags & LUCID_INST_HAS_VERTEX_COLORS) && p.vertex_colors)
-			p.quad_colors[k.slot] =
-				make_uint4(__ldg(p.vertex_colors + v.x), __ldg(p.vertex_colors + v.y),
-						   __ldg(p.vertex_colors + v.z), __ldg(p.vertex_colors + v.w));
-		if((inst.flags & LUCID_INST_HAS_VERTEX_NORMALS) && p.vertex_normals)
-			p.quad_normals[k.slot] =
-				make_uint4(__ldg(p.vertex_normals + v.x), __ldg(p.vertex_normals + v.y),
-						   __ldg(p.vertex_normals + v.z), __ldg(p.vertex_normals + v.w));
-		if((inst.flags & LUCID_INST_HAS_ALBEDO_TEXTURE) && p.vertex_uvs) {
+		// quad records (quad_setup.glsl:256-272, 342-354)
+		if((flags & LUCID_INST_HAS_VERTEX_COLORS) && p.vertex_colors)
+			p.quad_colors[slot] = make_uint4(__ldg(p.vertex_colors + v.x), __ldg(p.vertex_colors + v.y),
+											 __ldg(p.vertex_colors + v.z), __ldg(p.vertex_colors + v.w));
+		if((flags & LUCID_INST_HAS_VERTEX_NORMALS) && p.vertex_normals)
+			p.quad_normals[slot] = make_uint4(__ldg(p.vertex_normals + v.x), __ldg(p.vertex_normals + v.y),
+											  __ldg(p.vertex_normals + v.z), __ldg(p.vertex_normals + v.w));
+		if((flags & LUCID_INST_HAS_ALBEDO_TEXTURE) && p.vertex_uvs) {
 			float2 t0 = __ldg(p.vertex_uvs + v.x), t1 = __ldg(p.vertex_uvs + v.y);
 			float2 t2 = __ldg(p.vertex_uvs + v.z), t3 = __ldg(p.vertex_uvs + v.w);
-			p.quad_uv[(size_t)k.slot * 2 + 0] =
-				make_uint4(__float_as_uint(t0.x), __float_as_uint(t0.y),
-						   __float_as_uint(t1.x - t0.x), __float_as_uint(t1.y - t0.y));
-			p.quad_uv[(size_t)k.slot * 2 + 1] =
-				make_uint4(__float_as_uint(t2.x - t0.x), __float_as_uint(t2.y - t0.y),
-						   __float_as_uint(t3.x - t0.x), __float_as_uint(t3.y - t0.y));
+			p.quad_uv[(size_t)slot * 2 + 0] = make_uint4(__float_as_uint(t0.x), __float_as_uint(t0.y),
+														 __float_as_uint(t1.x - t0.x), __float_as_uint(t1.y - t0.y));
+			p.quad_uv[(size_t)slot * 2 + 1] =
+				make_uint4(__float_as_uint(t2.x - t0.x), __float_as_uint(t2.y - t0.y), __float_as_uint(t3.x - t0.x),
+						   __float_as_uint(t3.y - t0.y));
 		}
 	}
 }
@@ -497,7 +517,8 @@ void launchInfoOut(const Params &p, u32 *host_info, int num_words, cudaStream_t 
 void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream) {
 	if(p.num_setup_ctas == 0)
 		return;
-	k_quad_setup<<<p.num_setup_ctas, SETUP_THREADS, 0, stream>>>(p, cfg);
+	k_quad_cull<<<p.num_setup_ctas, SETUP_THREADS, 0, stream>>>(p, cfg);
+	k_tri_setup<<<148 * 8, SETUP_THREADS, 0, stream>>>(p, cfg);
 }
 
 } // namespace lucid
