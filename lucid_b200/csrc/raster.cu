@@ -1088,6 +1088,8 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 			const int c = tid < n_blocks ? sh.count[tid] : 0;
 			if(tid < n_blocks)
 				p.block_counts[bin_id * 32 + tid] = c;
+			// one queue, consumed from index 0: heavy items fill it from the front, light items from
+			// the back (so heavy blocks start first and the tail of the kernel is made of light ones)
 			const u32 item = ((u32)bin_id << 6) | (high ? 32u : 0u) | (u32)tid;
 			const u32 heavy = __ballot_sync(0xffffffffu, c > HEAVY_BLOCK), light = __ballot_sync(0xffffffffu, c > 0) & ~heavy;
 			u32 base_h = 0, base_l = 0;
@@ -1099,9 +1101,9 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 			}
 			base_h = __shfl_sync(0xffffffffu, base_h, 0), base_l = __shfl_sync(0xffffffffu, base_l, 0);
 			if((heavy >> tid) & 1)
-				p.block_items[base_h + __popc(heavy & laneMaskLt())] = item;
+				p.block_items[base_h + __popc(heavy & laneMaskLt())] = make_uint2(item, (u32)c);
 			if((light >> tid) & 1)
-				p.block_items[p.block_items_cap + base_l + __popc(light & laneMaskLt())] = item;
+				p.block_items[p.block_items_cap - 1 - (base_l + __popc(light & laneMaskLt()))] = make_uint2(item, (u32)c);
 		}
 		const int rows = high ? 4 : 8;
 		for(int blk = warp; blk < n_blocks; blk += RASTER_WARPS) {
@@ -1128,6 +1130,9 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 #ifndef RB_MIN_CTAS
 #define RB_MIN_CTAS 5
 #endif
+#ifndef RB_PREFETCH_MAX
+#define RB_PREFETCH_MAX 0 // items up to this many entries request their successor early
+#endif
 #ifndef RB_KEY_UNROLL
 #define RB_KEY_UNROLL 2
 #endif
@@ -1142,26 +1147,28 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 	const WarpScratch ws = warpScratch(smem + (size_t)warp * WARP_SCRATCH_BYTES);
 	u32 *large_keys = p.large_keys + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
 	uint4 *aux = p.block_aux + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
-	const u32 n_heavy = p.work_counters[3], n_light = p.work_counters[4];
+	const u32 n_heavy = p.work_counters[3], n_items = n_heavy + p.work_counters[4];
 	u32 frag_acc = 0, hbt_acc = 0;
+	// Work fetch: the queue index of the next item is requested when the current item's keys are
+	// built and its entry when they are sorted, so both round trips overlap the sort and the
+	// shading instead of being waited for; a warp never holds more than one item ahead, which keeps
+	// the dynamic balance.
+	auto fetchIndex = [&]() { return lane == 0 ? atomicAdd(&p.work_counters[1], 1u) : 0u; };
+	auto fetchEntry = [&](u32 i) {
+		uint2 e = make_uint2(0, 0);
+		if(lane == 0 && i < n_items)
+			e = __ldcg(p.block_items + (i < n_heavy ? i : p.block_items_cap - 1 - (i - n_heavy)));
+		return e;
+	};
+	uint2 next_entry = fetchEntry(fetchIndex());
 	while(true) {
-		u32 item = 0;
-		if(lane == 0) {
-			u32 i = atomicAdd(&p.work_counters[1], 1u);
-			if(i < n_heavy)
-				item = p.block_items[i] | 0x80000000u;
-			else {
-				i = atomicAdd(&p.work_counters[2], 1u);
-				if(i < n_light)
-					item = p.block_items[p.block_items_cap + i] | 0x80000000u;
-			}
-		}
-		item = __shfl_sync(0xffffffffu, item, 0);
-		if(item == 0)
+		const uint2 entry = next_entry;
+		const u32 item = __shfl_sync(0xffffffffu, entry.x, 0);
+		const int count = (int)__shfl_sync(0xffffffffu, entry.y, 0);
+		if(count == 0)
 			break;
-		const int bin_id = (int)((item & 0x7fffffffu) >> 6), sub = (int)(item & 31u);
+		const int bin_id = (int)(item >> 6), sub = (int)(item & 31u);
 		const bool high = (item & 32u) != 0;
-		const int count = p.block_counts[bin_id * 32 + sub];
 		const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
 		const int pos_x = bin_x * BIN_SIZE, pos_y = bin_y * BIN_SIZE;
 		const int cx8 = (sub & 3) * 8, ry = sub >> 2;
@@ -1230,6 +1237,10 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 			}
 		}
 		__syncwarp();
+		const bool light_item = count <= RB_PREFETCH_MAX;
+		u32 next_index = 0;
+		if(light_item)
+			next_index = fetchIndex();
 		// stats: LOW counts the block's triangles once per half-block (raster_low.glsl:272-275),
 		// HIGH the exact half-block list (raster_high.glsl:309-310)
 		hbt_acc += lane == 0 ? (u32)count * (high ? 1u : 2u) : 0u;
@@ -1245,6 +1256,8 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 				warpFixDepthTies(keys, count, slot_bits, [&](u32 pos) { return tie_tris[pos]; });
 			}
 		}
+		if(light_item)
+			next_entry = fetchEntry(next_index);
 		const u32 pos_mask = (1u << slot_bits) - 1u;
 		const int halves = high ? 1 : 2, hb_y = pos_y + ry * (high ? 4 : 8);
 		for(int half = 0; half < halves; half++) {
@@ -1252,6 +1265,8 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 			shadeHalfBlockAny(p, cfg, ws, keys, aux, count, pos_mask, pos_x + cx8, hb_y + half * 4, list);
 			__syncwarp();
 		}
+		if(!light_item) // a long item takes its successor only when it is done (dynamic balance)
+			next_entry = fetchEntry(fetchIndex());
 	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1) {
