@@ -1,0 +1,34 @@
+#!/bin/bash
+# One measurement pass on a B200 box (run under gpurun): parity suite, bench lines, stage probe,
+# ncu launch list of bench.py and --set full captures of one frame.  Everything lands in gpurun_out/.
+#   bash tools/gpu_round.sh <tag> [full-capture configs, default "1 3"]
+tag=${1:-r1}
+full=${2:-"1 3"}
+out=gpurun_out
+mkdir -p $out
+nproc > $out/${tag}_nproc.txt
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $out/${tag}_gpu.txt 2>&1
+
+timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1
+echo "pytest exit $?" >> $out/${tag}_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1
+
+timeout 600 python bench.py > $out/${tag}_bench_config1.json 2> $out/${tag}_bench_config1.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2>&1
+for c in 0 2 3; do
+  timeout 600 python bench.py --config $c --steps 10 > $out/${tag}_bench_config$c.json 2> $out/${tag}_bench_config$c.err
+done
+timeout 900 python tools/gpu_probe.py 0 1 2 3 > $out/${tag}_probe_stage_times.txt 2>&1
+
+# launch list of the bench command itself (per-launch times are cold-cache and serialised)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+  --log-file $out/${tag}_launches_config1.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
+  > $out/${tag}_launches_bench.log 2>&1
+
+# full captures: second frame of profile_frame.py (frame 1 is warm-up: k_pad_positions + 11 launches per frame)
+for c in $full; do
+  timeout 1200 ncu --set full --clock-control none --import-source on --launch-skip 12 -c 11 \
+    -o $out/${tag}_full_config$c -f python tools/profile_frame.py $c 2 > $out/${tag}_full_config$c.log 2>&1
+  python tools/ncu_summary.py $out/${tag}_full_config$c.ncu-rep > $out/${tag}_ncu_full_config$c.txt 2>&1
+done
+ls -la $out | tail -40
