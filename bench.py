@@ -143,7 +143,12 @@ def run_ours(args):
 
     scene = make_scene(args.config, args.scale)
     width, height = scene["width"], scene["height"]
-    stream = torch.cuda.current_stream()
+    # a stream of our own, made torch's current stream: the library launches every kernel on the stream it
+    # is handed (handle 0 would make it create a private one, invisible to torch.cuda.Event), so the
+    # flush, the timing events and the kernels are all ordered on this one stream
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     split = args.mode == "split" and world > 1
     nby = (height + 31) // 32
     rows = None
@@ -258,6 +263,9 @@ def run_ours(args):
         # LOW and HIGH bins share the two raster kernels (block lists, then block sort + shading)
         stage_names = ["setup", "bin_count", "bin_scan", "bin_dispatch", "raster_lists", "raster_shade", "finish"]
         stage_ms = {n: round(float(stage[i]), 4) for i, n in enumerate(stage_names)}
+        stage_ms["frame"] = round(float(stage[7]), 4)  # first launch -> last kernel done, the library's own events
+        # the library's events and ours are on one stream: our bracket can only be the wider one
+        assert ms_per_step >= 0.98 * float(stage[7]), (ms_per_step, float(stage[7]))
         raster_ms = float(stage[4] + stage[5])
         fracs = {
             "setup": ab["setup"] / (stage[0] * 1e-3) / 1e9 / peak if stage[0] > 0 else None,
