@@ -102,44 +102,49 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) {
 	return fminf(fmaxf(x, lo), hi);
 }
 __device__ __forceinline__ float saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
-__device__ __forceinline__ float rcp(float x) { return __fdiv_rn(1.0f, x); }
-__device__ __forceinline__ float rsqrt_rn(float x) { return __fdiv_rn(1.0f, __fsqrt_rn(x)); }
+// 1/x: __frcp_rn is correctly rounded, i.e. the same binary32 value as the IEEE quotient 1.0f / x
+__device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float rsqrt_rn(float x) { return __frcp_rn(__fsqrt_rn(x)); }
+// small unsigned integer (< 2^23) to float without the conversion pipe: OR it into the mantissa of
+// 2^23 and subtract 2^23 -- exact, so identical to float(v)
+__device__ __forceinline__ float smallUintToFloat(u32 v, float bias = 0.0f) {
+	return __uint_as_float(v | 0x4b000000u) - (8388608.0f + bias);
+}
 
-// log2 / exp2 / pow: polynomial evaluation shared with the CPU checker (atanh series on
-// [sqrt(1/2), sqrt(2)), degree-6 Taylor for 2^r).  The Horner steps are explicit fused
-// multiply-adds (fmaf on the host, FFMA here): single rounding on both sides, so the result is
-// still bit-identical while costing half the instructions of separate mul + add.
+// log2 / exp2 / pow: the polynomial contract shared with the CPU checker (oracle/lucid_oracle.cpp
+// orc_log2 / orc_exp2): log2 of the mantissa on [sqrt(1/2), sqrt(2)) as f * P7(f), 2^r on
+// [-1/2, 1/2] as P5(r), no division.  The Horner steps are explicit fused multiply-adds (fmaf on
+// the host, FFMA here): single rounding on both sides, so the result is bit-identical.
 __device__ __forceinline__ float log2_poly(float x) {
 	u32 ix = __float_as_uint(x);
 	int e = (int)(ix - 0x3f3504f3u) >> 23;
 	float m = __uint_as_float(ix - ((u32)e << 23));
 	float f = m - 1.0f;
-	float s = __fdiv_rn(f, 2.0f + f);
-	float z = s * s;
-	float p = 0.2222222222f;
-	p = __fmaf_rn(p, z, 0.2857142857f);
-	p = __fmaf_rn(p, z, 0.4f);
-	p = __fmaf_rn(p, z, 0.6666666667f);
-	p = __fmaf_rn(p, z, 2.0f);
-	float ln = s * p;
-	return __fmaf_rn(ln, 1.4426950408889634f, (float)e);
+	float p = -0.146203533f;
+	p = __fmaf_rn(p, f, 0.23420985f);
+	p = __fmaf_rn(p, f, -0.24882181f);
+	p = __fmaf_rn(p, f, 0.287075609f);
+	p = __fmaf_rn(p, f, -0.360241979f);
+	p = __fmaf_rn(p, f, 0.48092404f);
+	p = __fmaf_rn(p, f, -0.721352756f);
+	p = __fmaf_rn(p, f, 1.4426949f);
+	return __fmaf_rn(p, f, (float)e);
 }
 __device__ __forceinline__ float exp2_poly(float t) {
 	float n = floorf(t + 0.5f);
-	float r = (t - n) * 0.6931471805599453f;
-	float p = 1.0f / 720.0f;
-	p = __fmaf_rn(p, r, 1.0f / 120.0f);
-	p = __fmaf_rn(p, r, 1.0f / 24.0f);
-	p = __fmaf_rn(p, r, 1.0f / 6.0f);
-	p = __fmaf_rn(p, r, 0.5f);
-	p = __fmaf_rn(p, r, 1.0f);
+	float r = t - n;
+	float p = 0.00134004327f;
+	p = __fmaf_rn(p, r, 0.00967603736f);
+	p = __fmaf_rn(p, r, 0.0555032715f);
+	p = __fmaf_rn(p, r, 0.240221068f);
+	p = __fmaf_rn(p, r, 0.693147182f);
 	p = __fmaf_rn(p, r, 1.0f);
 	int ni = f2i(n);
 	if(ni < -126)
 		return 0.0f;
 	if(ni > 127)
 		ni = 127;
-	return p * __uint_as_float((u32)(ni + 127) << 23);
+	return __uint_as_float(__float_as_uint(p) + ((u32)ni << 23));
 }
 __device__ __forceinline__ float pow_poly(float x, float y) {
 	if(!(x > 0.0f))
@@ -170,13 +175,15 @@ __device__ __forceinline__ u32 encodeNormalUint(F3 n) {
 }
 __device__ __forceinline__ F3 decodeNormalUint(u32 n) {
 	const float s = 1.0f / 511.0f;
-	return mk3((float((n >> 0) & 0x3ffu) - 512.0f) * s, (float((n >> 10) & 0x3ffu) - 512.0f) * s,
-			   (float((n >> 20) & 0x3ffu) - 512.0f) * s);
+	return mk3(smallUintToFloat((n >> 0) & 0x3ffu, 512.0f) * s, smallUintToFloat((n >> 10) & 0x3ffu, 512.0f) * s,
+			   smallUintToFloat((n >> 20) & 0x3ffu, 512.0f) * s);
 }
 __device__ __forceinline__ float4 decodeRGBA8(u32 c) {
-	const float s = 1.0f / 255.0f;
-	return make_float4(float(c & 0xffu) * s, float((c >> 8) & 0xffu) * s,
-					   float((c >> 16) & 0xffu) * s, float((c >> 24) & 0xffu) * s);
+	const float s = 1.0f / 255.0f, magic = 8388608.0f;
+	return make_float4((__uint_as_float(__byte_perm(c, 0x4b000000u, 0x7650)) - magic) * s,
+					   (__uint_as_float(__byte_perm(c, 0x4b000000u, 0x7651)) - magic) * s,
+					   (__uint_as_float(__byte_perm(c, 0x4b000000u, 0x7652)) - magic) * s,
+					   (__uint_as_float(__byte_perm(c, 0x4b000000u, 0x7653)) - magic) * s);
 }
 __device__ __forceinline__ u32 encodeRGBA8(float4 c) {
 	return f2u(c.x * 255.0f) | (f2u(c.y * 255.0f) << 8) | (f2u(c.z * 255.0f) << 16) |

@@ -70,22 +70,37 @@ __device__ __forceinline__ u32 blockDepth(uint4 d, float cx, float cy, float ran
 
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
 
-__device__ __forceinline__ float4 texelFetch(const Params &p, int slot, int level, int x, int y) {
-	int w = max(1, p.tex_width[slot] >> level), h = max(1, p.tex_height[slot] >> level);
-	x = ((x % w) + w) % w;
-	y = ((y % h) + h) % h;
-	uchar4 t = __ldg(p.tex_data[slot] + p.tex_level_offset[slot][level] + (size_t)y * w + x);
-	const float s = 1.0f / 255.0f;
-	return make_float4(float(t.x) * s, float(t.y) * s, float(t.z) * s, float(t.w) * s);
+// Filter definition (the reference leaves this to the Vulkan sampler; same arithmetic as
+// oracle/lucid_oracle.cpp sampleTexture): repeat addressing, bilinear within a level, linear between
+// the two nearest levels, isotropic lod.  Coordinates are wrapped once in floating point, so the
+// 2x2 footprint leaves the level by at most one texel (compares, no integer remainder); lod takes
+// log2 piecewise linearly from the exponent / mantissa bits; texels are filtered on the 0..255
+// scale (byte -> float by a permute into the mantissa of 2^23) and scaled by 1/255 once.
+__device__ __forceinline__ float4 texelBytes(u32 t) {
+	const float magic = 8388608.0f; // 0x4b000000: float(2^23 + b) - 2^23 == float(b), exactly
+	return make_float4(__uint_as_float(__byte_perm(t, 0x4b000000u, 0x7650)) - magic,
+					   __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7651)) - magic,
+					   __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7652)) - magic,
+					   __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7653)) - magic);
 }
-__device__ float4 bilinear(const Params &p, int slot, int level, float u, float v) {
-	int w = max(1, p.tex_width[slot] >> level), h = max(1, p.tex_height[slot] >> level);
-	float fx = u * float(w) - 0.5f, fy = v * float(h) - 0.5f;
+// uf, vf in [0, 1]; result on the 0..255 scale
+__device__ __forceinline__ float4 bilinear(const u32 *level_base, int w, int h, float uf, float vf) {
+	float fx = uf * float(w) - 0.5f, fy = vf * float(h) - 0.5f;
 	float x0f = floorf(fx), y0f = floorf(fy);
 	float ax = fx - x0f, ay = fy - y0f;
-	int x0 = f2i(x0f), y0 = f2i(y0f);
-	float4 c00 = texelFetch(p, slot, level, x0, y0), c10 = texelFetch(p, slot, level, x0 + 1, y0);
-	float4 c01 = texelFetch(p, slot, level, x0, y0 + 1), c11 = texelFetch(p, slot, level, x0 + 1, y0 + 1);
+	int x0 = f2i(x0f), y0 = f2i(y0f); // in [-1, size - 1]
+	int x1 = x0 + 1, y1 = y0 + 1;
+	if(x0 < 0)
+		x0 += w;
+	if(x1 >= w)
+		x1 -= w;
+	if(y0 < 0)
+		y0 += h;
+	if(y1 >= h)
+		y1 -= h;
+	const u32 *row0 = level_base + y0 * w, *row1 = level_base + y1 * w;
+	u32 t00 = __ldg(row0 + x0), t10 = __ldg(row0 + x1), t01 = __ldg(row1 + x0), t11 = __ldg(row1 + x1);
+	float4 c00 = texelBytes(t00), c10 = texelBytes(t10), c01 = texelBytes(t01), c11 = texelBytes(t11);
 	float4 o;
 #define LERP2(c)                                                                                   \
 	{                                                                                              \
@@ -97,29 +112,31 @@ __device__ float4 bilinear(const Params &p, int slot, int level, float u, float 
 #undef LERP2
 	return o;
 }
-// Filter definition (the reference leaves this to the Vulkan sampler): repeat addressing,
-// bilinear within a level, linear between the two nearest levels, isotropic lod.
-__device__ float4 sampleTexture(const Params &p, int slot, float u, float v, float dudx, float dvdx,
-								float dudy, float dvdy) {
-	if(p.tex_data[slot] == nullptr)
+__device__ __forceinline__ float4 sampleTexture(const Params &p, int slot, float u, float v, float dudx, float dvdx,
+												float dudy, float dvdy) {
+	const u32 *data = reinterpret_cast<const u32 *>(p.tex_data[slot]);
+	if(data == nullptr)
 		return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-	float w0 = float(p.tex_width[slot]), h0 = float(p.tex_height[slot]);
+	const int wi = p.tex_width[slot], hi = p.tex_height[slot];
+	float w0 = float(wi), h0 = float(hi);
 	float ax = dudx * w0, ay = dvdx * h0, bx = dudy * w0, by = dvdy * h0;
 	float rho2 = fmaxf(ax * ax + ay * ay, bx * bx + by * by);
 	int levels = p.tex_levels[slot];
 	float lod = 0.0f;
 	if(rho2 > 1.0f)
-		lod = 0.5f * log2_poly(rho2);
+		lod = float((int)(__float_as_uint(rho2) - 0x3f800000u)) * (0.5f / 8388608.0f);
 	lod = clampf(lod, 0.0f, float(levels - 1));
 	float l0f = floorf(lod);
 	int l0 = f2i(l0f), l1 = min(l0 + 1, levels - 1);
 	float a = lod - l0f;
-	float4 c0 = bilinear(p, slot, l0, u, v);
+	const float uf = u - floorf(u), vf = v - floorf(v);
+	const float s = 1.0f / 255.0f;
+	float4 c0 = bilinear(data + p.tex_level_offset[slot][l0], max(1, wi >> l0), max(1, hi >> l0), uf, vf);
 	if(a == 0.0f || l1 == l0)
-		return c0;
-	float4 c1 = bilinear(p, slot, l1, u, v);
-	return make_float4(c0.x + (c1.x - c0.x) * a, c0.y + (c1.y - c0.y) * a, c0.z + (c1.z - c0.z) * a,
-					   c0.w + (c1.w - c0.w) * a);
+		return make_float4(c0.x * s, c0.y * s, c0.z * s, c0.w * s);
+	float4 c1 = bilinear(data + p.tex_level_offset[slot][l1], max(1, wi >> l1), max(1, hi >> l1), uf, vf);
+	return make_float4((c0.x + (c1.x - c0.x) * a) * s, (c0.y + (c1.y - c0.y) * a) * s,
+					   (c0.z + (c1.z - c0.z) * a) * s, (c0.w + (c1.w - c0.w) * a) * s);
 }
 
 __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg, int ipx, int ipy, u32 tri_idx,
@@ -176,13 +193,10 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 			u = r.z * fractf(u) + r.x, v = r.w * fractf(v) + r.y;
 			dudx *= r.z, dvdx *= r.w, dudy *= r.z, dvdy *= r.w;
 		}
-		float4 tc;
-		if(flags & LUCID_INST_TEX_OPAQUE) {
-			tc = sampleTexture(p, 0, u, v, dudx, dvdx, dudy, dvdy);
+		const bool tex_opaque = (flags & LUCID_INST_TEX_OPAQUE) != 0;
+		float4 tc = sampleTexture(p, tex_opaque ? 0 : 1, u, v, dudx, dvdx, dudy, dvdy);
+		if(tex_opaque)
 			tc.w = 1.0f;
-		} else {
-			tc = sampleTexture(p, 1, u, v, dudx, dvdx, dudy, dvdy);
-		}
 		color.x *= tc.x, color.y *= tc.y, color.z *= tc.z, color.w *= tc.w;
 	}
 	if(flags & LUCID_INST_HAS_VERTEX_COLORS) {
@@ -274,52 +288,72 @@ __device__ __forceinline__ void reducerPush(Reducer &s, u32 color, float depth, 
 // min/max pairs, the others one shuffle per key.  Tiles of 256 keys (K = 8) are sorted entirely in
 // registers; only the steps with distance >= 256 of larger lists go through shared memory.
 
-template <int K> __device__ __forceinline__ void sortRegsMergeSteps(u32 (&v)[K], int first_j, u32 lane) {
+// The steps between registers of one lane are unrolled (static register indices); the steps across
+// lanes run as loops over the lane distance, which keeps the code of the four tile sizes small
+// enough to stay in the instruction cache next to the shading loop.
+template <int K> __device__ __forceinline__ void sortRegsInLane(u32 (&v)[K]) { // distances K/2 .. 1
 #pragma unroll
-	for(int j = first_j; j >= 1; j >>= 1) {
-		if(j < K) {
+	for(int j = K / 2; j >= 1; j >>= 1) {
+#pragma unroll
+		for(int r = 0; r < K; r++)
+			if((r & j) == 0) {
+				u32 lo = min(v[r], v[r | j]), hi = max(v[r], v[r | j]);
+				v[r] = lo, v[r | j] = hi;
+			}
+	}
+}
+template <int K> __device__ __forceinline__ void sortRegsAcrossLanes(u32 (&v)[K], int first_lm, u32 lane) {
+#pragma unroll 1
+	for(int lm = first_lm; lm >= 1; lm >>= 1) {
+		const bool lower = (lane & lm) == 0;
+#pragma unroll
+		for(int r = 0; r < K; r++) {
+			u32 o = __shfl_xor_sync(0xffffffffu, v[r], lm);
+			v[r] = lower ? min(v[r], o) : max(v[r], o);
+		}
+	}
+}
+// merge steps with partner distances first_j, first_j / 2, ... 1 (first_j >= K)
+template <int K> __device__ __forceinline__ void sortRegsMergeSteps(u32 (&v)[K], int first_j, u32 lane) {
+	sortRegsAcrossLanes<K>(v, first_j / K, lane);
+	sortRegsInLane<K>(v);
+}
+
+// full sort of the 32 * K keys held by the warp
+template <int K> __device__ __forceinline__ void sortRegs(u32 (&v)[K], u32 lane) {
+	// merge levels inside a lane (k <= K)
+#pragma unroll
+	for(int k = 2; k <= K; k <<= 1) {
+#pragma unroll
+		for(int r = 0; r < K; r++)
+			if((r & (k >> 1)) == 0) {
+				const int q = r ^ (k - 1);
+				u32 lo = min(v[r], v[q]), hi = max(v[r], v[q]);
+				v[r] = lo, v[q] = hi;
+			}
+#pragma unroll
+		for(int j = k >> 2; j >= 1; j >>= 1) {
 #pragma unroll
 			for(int r = 0; r < K; r++)
 				if((r & j) == 0) {
 					u32 lo = min(v[r], v[r | j]), hi = max(v[r], v[r | j]);
 					v[r] = lo, v[r | j] = hi;
 				}
-		} else {
-			const int lm = j / K;
-			const bool lower = (lane & lm) == 0;
-#pragma unroll
-			for(int r = 0; r < K; r++) {
-				u32 o = __shfl_xor_sync(0xffffffffu, v[r], lm);
-				v[r] = lower ? min(v[r], o) : max(v[r], o);
-			}
 		}
 	}
-}
-
-// full sort of the 32 * K keys held by the warp
-template <int K> __device__ __forceinline__ void sortRegs(u32 (&v)[K], u32 lane) {
+	// merge levels k = 2 K top: element e pairs with e ^ (k - 1), i.e. lane ^ (2 top - 1), register r ^ (K - 1)
+#pragma unroll 1
+	for(int top = 1; top < 32; top <<= 1) {
+		const bool lower = (lane & top) == 0;
+		u32 o[K];
 #pragma unroll
-	for(int k = 2; k <= 32 * K; k <<= 1) {
-		if(k <= K) {
+		for(int r = 0; r < K; r++)
+			o[r] = __shfl_xor_sync(0xffffffffu, v[r ^ (K - 1)], 2 * top - 1);
 #pragma unroll
-			for(int r = 0; r < K; r++)
-				if((r & (k >> 1)) == 0) {
-					const int q = r ^ (k - 1);
-					u32 lo = min(v[r], v[q]), hi = max(v[r], v[q]);
-					v[r] = lo, v[q] = hi;
-				}
-		} else {
-			const int lm = k / K - 1;
-			const bool lower = (lane & (k / (2 * K))) == 0;
-			u32 o[K];
-#pragma unroll
-			for(int r = 0; r < K; r++)
-				o[r] = __shfl_xor_sync(0xffffffffu, v[r ^ (K - 1)], lm);
-#pragma unroll
-			for(int r = 0; r < K; r++)
-				v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
-		}
-		sortRegsMergeSteps<K>(v, k >> 2, lane);
+		for(int r = 0; r < K; r++)
+			v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
+		sortRegsAcrossLanes<K>(v, top >> 1, lane);
+		sortRegsInLane<K>(v);
 	}
 }
 

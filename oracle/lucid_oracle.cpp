@@ -94,40 +94,42 @@ inline int findLSB(u32 v) { return v == 0 ? -1 : __builtin_ctz(v); }
 inline int findMSB(u32 v) { return v == 0 ? -1 : 31 - __builtin_clz(v); }
 inline int popcount(u32 v) { return __builtin_popcount(v); }
 
-// log2 on the mantissa interval [sqrt(1/2), sqrt(2)) with the classic atanh series, exp2 with a
-// degree-6 Taylor polynomial; Horner steps are explicit fmaf so the CUDA side (FFMA) repeats them
-// bit for bit.  |relative error| < 2e-6 on the sRGB ranges (checked in tests/).
+// log2 / exp2 / pow (the reference leaves pow() to the GLSL driver; this is the contract shared with
+// the CUDA kernels): log2 of the mantissa on [sqrt(1/2), sqrt(2)) as f * P7(f), f = m - 1, and 2^r on
+// [-1/2, 1/2] as P5(r); near-minimax coefficients (Chebyshev interpolation), no division.  Horner
+// steps are explicit fmaf so the CUDA side (FFMA) repeats them bit for bit.  |relative error| of
+// pow < 2e-6 on the sRGB ranges (checked in tests/test_oracle.py).
 inline float orc_log2(float x) {
 	u32 ix = floatBits(x);
 	int e = (int)(ix - 0x3f3504f3u) >> 23;
 	float m = bitsToFloat(ix - ((u32)e << 23));
 	float f = m - 1.0f;
-	float s = f / (2.0f + f);
-	float z = s * s;
-	float p = 0.2222222222f;				// 2/9
-	p = fmaf(p, z, 0.2857142857f);			// 2/7
-	p = fmaf(p, z, 0.4f);					// 2/5
-	p = fmaf(p, z, 0.6666666667f);			// 2/3
-	p = fmaf(p, z, 2.0f);
-	float ln = s * p;
-	return fmaf(ln, 1.4426950408889634f, (float)e);
+	float p = -0.146203533f;
+	p = fmaf(p, f, 0.23420985f);
+	p = fmaf(p, f, -0.24882181f);
+	p = fmaf(p, f, 0.287075609f);
+	p = fmaf(p, f, -0.360241979f);
+	p = fmaf(p, f, 0.48092404f);
+	p = fmaf(p, f, -0.721352756f);
+	p = fmaf(p, f, 1.4426949f);
+	return fmaf(p, f, (float)e);
 }
 inline float orc_exp2(float t) {
 	float n = floorf(t + 0.5f);
-	float r = (t - n) * 0.6931471805599453f;
-	float p = 1.0f / 720.0f;
-	p = fmaf(p, r, 1.0f / 120.0f);
-	p = fmaf(p, r, 1.0f / 24.0f);
-	p = fmaf(p, r, 1.0f / 6.0f);
-	p = fmaf(p, r, 0.5f);
-	p = fmaf(p, r, 1.0f);
+	float r = t - n;
+	float p = 0.00134004327f;
+	p = fmaf(p, r, 0.00967603736f);
+	p = fmaf(p, r, 0.0555032715f);
+	p = fmaf(p, r, 0.240221068f);
+	p = fmaf(p, r, 0.693147182f);
 	p = fmaf(p, r, 1.0f);
 	int ni = f2i(n);
 	if(ni < -126)
 		return 0.0f;
 	if(ni > 127)
 		ni = 127;
-	return p * bitsToFloat((u32)(ni + 127) << 23);
+	// p in [0.70, 1.42]: scaling by 2^ni is an add on the exponent field
+	return bitsToFloat(floatBits(p) + ((u32)ni << 23));
 }
 inline float orc_pow(float x, float y) {
 	if(!(x > 0.0f))
@@ -749,27 +751,46 @@ inline float fractf(float x) { return x - floorf(x); }
 
 // Texture filter definition (the reference delegates to the Vulkan sampler, which is
 // implementation defined): repeat addressing, bilinear inside a level, linear
-// between the two nearest levels, lod = log2(max(|d/dx|, |d/dy|) in texels), no anisotropy.
-V4 texel(const Texture &t, int level, int x, int y) {
-	int w = t.w[level], h = t.h[level];
-	x = ((x % w) + w) % w;
-	y = ((y % h) + h) % h;
-	const uint8_t *p = &t.mips[level][((size_t)y * w + x) * 4];
-	const float s = 1.0f / 255.0f;
-	return V4{float(p[0]) * s, float(p[1]) * s, float(p[2]) * s, float(p[3]) * s};
-}
-V4 bilinear(const Texture &t, int level, float u, float v) {
-	float fx = u * float(t.w[level]) - 0.5f, fy = v * float(t.h[level]) - 0.5f;
+// between the two nearest levels, no anisotropy.  Chosen so that a sample costs few instructions:
+//   * coordinates are wrapped once in floating point (u - floor(u)), after which the 2x2 footprint
+//     can only step outside the level by one texel: two compares instead of integer remainders;
+//   * lod = log2(max(|d/dx|, |d/dy|) in texels) with log2 taken piecewise linearly between powers
+//     of two, straight from the exponent and mantissa bits (what hardware samplers do);
+//   * texels are filtered on the 0..255 scale and the result is scaled by 1/255 once.
+struct Footprint {
+	int x0, x1, y0, y1;
+	float ax, ay;
+};
+inline Footprint footprint(int w, int h, float uf, float vf) {
+	Footprint f;
+	float fx = uf * float(w) - 0.5f, fy = vf * float(h) - 0.5f;
 	float x0f = floorf(fx), y0f = floorf(fy);
-	float ax = fx - x0f, ay = fy - y0f;
-	int x0 = f2i(x0f), y0 = f2i(y0f);
-	V4 c00 = texel(t, level, x0, y0), c10 = texel(t, level, x0 + 1, y0);
-	V4 c01 = texel(t, level, x0, y0 + 1), c11 = texel(t, level, x0 + 1, y0 + 1);
+	f.ax = fx - x0f, f.ay = fy - y0f;
+	f.x0 = f2i(x0f), f.y0 = f2i(y0f); // in [-1, size - 1]
+	f.x1 = f.x0 + 1, f.y1 = f.y0 + 1;
+	if(f.x0 < 0)
+		f.x0 += w;
+	if(f.x1 >= w)
+		f.x1 -= w;
+	if(f.y0 < 0)
+		f.y0 += h;
+	if(f.y1 >= h)
+		f.y1 -= h;
+	return f;
+}
+// uf, vf in [0, 1]; result on the 0..255 scale
+V4 bilinear(const Texture &t, int level, float uf, float vf) {
+	const int w = t.w[level], h = t.h[level];
+	const Footprint f = footprint(w, h, uf, vf);
+	const uint8_t *base = t.mips[level].data();
+	const uint8_t *p00 = base + ((size_t)f.y0 * w + f.x0) * 4, *p10 = base + ((size_t)f.y0 * w + f.x1) * 4;
+	const uint8_t *p01 = base + ((size_t)f.y1 * w + f.x0) * 4, *p11 = base + ((size_t)f.y1 * w + f.x1) * 4;
 	V4 out;
 	for(int i = 0; i < 4; i++) {
-		float top = c00[i] + (c10[i] - c00[i]) * ax;
-		float bot = c01[i] + (c11[i] - c01[i]) * ax;
-		out[i] = top + (bot - top) * ay;
+		float c00 = float(p00[i]), c10 = float(p10[i]), c01 = float(p01[i]), c11 = float(p11[i]);
+		float top = c00 + (c10 - c00) * f.ax;
+		float bot = c01 + (c11 - c01) * f.ax;
+		out[i] = top + (bot - top) * f.ay;
 	}
 	return out;
 }
@@ -782,19 +803,24 @@ V4 Oracle::sampleTexture(const Texture &t, float u, float v, float dudx, float d
 	float rho2 = fmax2(ax * ax + ay * ay, bx * bx + by * by);
 	int levels = (int)t.mips.size();
 	float lod = 0.0f;
-	if(rho2 > 1.0f)
-		lod = 0.5f * orc_log2(rho2);
+	if(rho2 > 1.0f) // 0.5 * (exponent + mantissa fraction) of rho2
+		lod = float((int)(floatBits(rho2) - 0x3f800000u)) * (0.5f / 8388608.0f);
 	lod = clampf(lod, 0.0f, float(levels - 1));
 	float l0f = floorf(lod);
 	int l0 = f2i(l0f), l1 = std::min(l0 + 1, levels - 1);
 	float a = lod - l0f;
-	V4 c0 = bilinear(t, l0, u, v);
-	if(a == 0.0f || l1 == l0)
-		return c0;
-	V4 c1 = bilinear(t, l1, u, v);
+	const float uf = u - floorf(u), vf = v - floorf(v);
+	const float s = 1.0f / 255.0f;
+	V4 c0 = bilinear(t, l0, uf, vf);
 	V4 out;
+	if(a == 0.0f || l1 == l0) {
+		for(int i = 0; i < 4; i++)
+			out[i] = c0[i] * s;
+		return out;
+	}
+	V4 c1 = bilinear(t, l1, uf, vf);
 	for(int i = 0; i < 4; i++)
-		out[i] = c0[i] + (c1[i] - c0[i]) * a;
+		out[i] = (c0[i] + (c1[i] - c0[i]) * a) * s;
 	return out;
 }
 
