@@ -745,6 +745,11 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 		px_frags += __popc(tm);
 		if(dead)
 			continue;
+		// a pixel whose transmittance has reached zero takes exactly +0 from every later sample:
+		// its samples are neither shaded nor reduced (the opaque cull of shading.glsl:31-32, exact part)
+		const u32 dead_px = vis_errors ? 0u : __ballot_sync(0xffffffffu, red.trans == 0.0f);
+		if((dead_px >> lane) & 1u)
+			tm = 0;
 
 		if(__all_sync(0xffffffffu, !in_chunk || cur.aux.w != AUX_VARYING)) {
 			ws.stage[lane] = make_float4(__uint_as_float(cur.aux.x), __uint_as_float(cur.aux.y),
@@ -758,9 +763,24 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 				reducerPush(red, __float_as_uint(s.w), depth, additive, vis_errors);
 			}
 		} else {
+			// samples of live pixels only: offsets are recomputed over the masked pixel sets
+			u32 live = bits & ~dead_px;
+			int live_off = off, live_total = total;
+			if(dead_px != 0) {
+				const int nl = __popc(live);
+				int li = nl;
+#pragma unroll
+				for(int o = 1; o < 32; o <<= 1) {
+					int t = __shfl_up_sync(0xffffffffu, li, o);
+					if(lane >= o)
+						li += t;
+				}
+				live_off = li - nl;
+				live_total = __shfl_sync(0xffffffffu, li, 31);
+			}
 			if(in_chunk) {
-				ws.chunk[lane] = make_uint2(bits, (u32)off);
-				u32 dst = (u32)off, word = cur.tri << 8, b = bits;
+				ws.chunk[lane] = make_uint2(live, (u32)live_off);
+				u32 dst = (u32)live_off, word = cur.tri << 8, b = live;
 				while(b) {
 					u32 pid = __ffs(b) - 1;
 					b &= b - 1;
@@ -768,9 +788,9 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 				}
 			}
 			__syncwarp();
-			for(int r0 = 0; r0 < total; r0 += 32) {
+			for(int r0 = 0; r0 < live_total; r0 += 32) {
 				int idx = r0 + lane;
-				if(idx < total) {
+				if(idx < live_total) {
 					u32 val = ws.samples[idx], pid = val & 31u;
 					float depth;
 					u32 color = shadeSample(p, cfg, hb_x + (int)(pid & 7), hb_y + (int)(pid >> 3), val >> 8, depth);
