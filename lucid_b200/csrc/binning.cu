@@ -83,6 +83,7 @@ __device__ __forceinline__ int warpAggregatedAdd(int *counters, int bin, bool va
 // counting (bin_counter.glsl:64-134)
 
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
+	pdlEntry();
 	const int n_small = p.info->num_visible_quads[0], n_large = p.info->num_visible_quads[1];
 	int *quad_counts = cnt(p, LUCID_CNT_QUAD_COUNTS);
 	int *tri_diff = cnt(p, LUCID_CNT_TRI_COUNTS); // per-row difference array until the scan kernel
@@ -169,6 +170,7 @@ __device__ __forceinline__ int blockExclusiveScan(int value, int *s_warp, int &t
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_bin_scan(const Params p) {
 	__shared__ int s_warp[33];
+	pdlEntry();
 	const int bc = p.bin_count, bcx = p.bin_count_x, bcy = p.bin_count_y;
 	int *qc = cnt(p, LUCID_CNT_QUAD_COUNTS), *qo = cnt(p, LUCID_CNT_QUAD_OFFSETS);
 	int *qt = cnt(p, LUCID_CNT_QUAD_OFFSETS_TEMP);
@@ -259,7 +261,33 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_bin_scan(const Params p) {
 // ------------------------------------------------------------------------------------------------
 // dispatch (bin_dispatcher.glsl:66-114)
 
+// Large triangles are dispatched through a per-warp queue of span segments: every lane walks the
+// bin rows of its own triangle (the incremental scan of bin_counter.glsl:53-62 is serial per
+// triangle) but only *queues* (triangle, first bin, up to 8 bins) segments; 32 queued segments are
+// then written by 32 lanes, each issuing all of its position claims before the first dependent
+// store.  A thread that claimed and stored bin by bin spent one atomic round trip per (triangle,
+// bin) on the critical path, and a tall or wide triangle held its warp for hundreds of them.  The
+// reference balances the same work with per-row segment scans (bin_dispatcher.glsl:123-196).
+constexpr int DISPATCH_RING = 64;  // segments per warp
+constexpr int SEGMENT_BINS = 8;
+
+__device__ __forceinline__ void drainSegments(const Params &p, int *tri_cursor, const uint2 *ring, int index, bool active) {
+	const uint2 seg = ring[index & (DISPATCH_RING - 1)];
+	const int cell = (int)(seg.y & 0xffffu), n = active ? (int)(seg.y >> 16) : 0;
+	int pos[SEGMENT_BINS];
+#pragma unroll
+	for(int k = 0; k < SEGMENT_BINS; k++)
+		if(k < n)
+			pos[k] = atomicAdd(tri_cursor + cell + k, 1);
+#pragma unroll
+	for(int k = 0; k < SEGMENT_BINS; k++)
+		if(k < n)
+			p.bin_tris[pos[k]] = seg.x;
+}
+
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
+	__shared__ uint2 s_ring[BIN_THREADS / 32][DISPATCH_RING];
+	pdlEntry();
 	if(p.info->temp[1] != 0)
 		return; // lists would overflow their buffers
 	const int n_small = p.info->num_visible_quads[0], n_large = p.info->num_visible_quads[1];
@@ -267,7 +295,10 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 	int *tri_cursor = cnt(p, LUCID_CNT_TRI_OFFSETS_TEMP);
 	const int bcx = p.bin_count_x;
 	const int stride = gridDim.x * blockDim.x;
+	const int lane = laneId();
 
+	// small quads: the position claims of the (up to four) bins are all issued before the first
+	// result is needed
 	for(int base = blockIdx.x * blockDim.x; base < n_small; base += stride) {
 		int q = base + threadIdx.x;
 		bool valid = q < n_small;
@@ -275,20 +306,30 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 		u32 word = (u32)q | (enc & 0xf0000000u);
 		int bsx = enc & 0x7f, bsy = (enc >> 7) & 0x7f, bex = (enc >> 14) & 0x7f, bey = (enc >> 21) & 0x7f;
 		int w = bex - bsx + 1, n = valid ? w * (bey - bsy + 1) : 0;
+		u32 peers[4];
+		int claimed[4], bin[4];
+		bool ok[4];
 #pragma unroll
 		for(int k = 0; k < 4; k++) {
 			int by = bsy + k / max(w, 1), bx = bsx + k % max(w, 1);
-			bool ok = k < n && by >= p.row_begin && by < p.row_end;
-			int pos = warpAggregatedAdd<true>(quad_cursor, by * bcx + bx, ok);
-			if(ok)
-				p.bin_quads[pos] = word;
+			ok[k] = k < n && by >= p.row_begin && by < p.row_end;
+			bin[k] = by * bcx + bx;
+			peers[k] = __match_any_sync(0xffffffffu, ok[k] ? bin[k] : -1);
+			claimed[k] = 0;
+			if(ok[k] && lane == __ffs(peers[k]) - 1)
+				claimed[k] = atomicAdd(quad_cursor + bin[k], __popc(peers[k]));
+		}
+#pragma unroll
+		for(int k = 0; k < 4; k++) {
+			// lanes without a bin form the peer group of key -1: their shuffle result is unused
+			int first = __shfl_sync(0xffffffffu, claimed[k], __ffs(peers[k]) - 1);
+			if(ok[k])
+				p.bin_quads[first + __popc(peers[k] & laneMaskLt())] = word;
 		}
 	}
 
-	// large triangles.  Narrow spans are written by the owning thread; a triangle whose bin AABB
-	// is wider than 8 bins is handed to the whole warp, which strides across each row span
-	// (the reference balances this with per-row segment scans, bin_dispatcher.glsl:123-196).
-	const int lane = laneId();
+	uint2 *ring = s_ring[threadIdx.x >> 5];
+	int q_head = 0, q_tail = 0; // warp-uniform
 	for(int base = blockIdx.x * blockDim.x; base < n_large * 2; base += stride) {
 		int i = base + threadIdx.x;
 		bool valid = i < n_large * 2;
@@ -304,52 +345,52 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 			t.s0 = src[0], t.s1 = src[1];
 			s = loadBinScan(t, bsy, bey);
 		}
-		bool wide = valid && (bex - bsx) >= 8;
-		if(valid && !wide) {
-			for(int by = bsy; by <= bey; by++) {
-				int bmin, bmax;
+		const int rows = valid ? bey - bsy + 1 : 0;
+		const int max_rows = __reduce_max_sync(0xffffffffu, rows);
+		for(int r = 0; r < max_rows; r++) {
+			int bmin = 0, bmax = -1;
+			if(r < rows) {
 				binScanStep(s, bmin, bmax);
 				bmin = max(bmin, bsx), bmax = min(bmax, bex);
+				const int by = bsy + r;
 				if(by < p.row_begin || by >= p.row_end)
-					continue;
-				for(int bx = bmin; bx <= bmax; bx++)
-					p.bin_tris[atomicAdd(tri_cursor + by * bcx + bx, 1)] = tri_idx;
+					bmax = bmin - 1;
 			}
-		}
-		u32 wide_mask = __ballot_sync(0xffffffffu, wide);
-		while(wide_mask) {
-			int src_lane = __ffs(wide_mask) - 1;
-			wide_mask &= wide_mask - 1;
-			int rows = __shfl_sync(0xffffffffu, bey - bsy + 1, src_lane);
-			int row0 = __shfl_sync(0xffffffffu, bsy, src_lane);
-			int cbsx = __shfl_sync(0xffffffffu, bsx, src_lane), cbex = __shfl_sync(0xffffffffu, bex, src_lane);
-			u32 ctri = __shfl_sync(0xffffffffu, tri_idx, src_lane);
-			for(int r = 0; r < rows; r++) {
-				int bmin = 0, bmax = -1;
-				if(lane == src_lane)
-					binScanStep(s, bmin, bmax);
-				bmin = __shfl_sync(0xffffffffu, bmin, src_lane);
-				bmax = __shfl_sync(0xffffffffu, bmax, src_lane);
-				bmin = max(bmin, cbsx), bmax = min(bmax, cbex);
-				int by = row0 + r;
-				if(by < p.row_begin || by >= p.row_end)
-					continue;
-				for(int bx = bmin + lane; bx <= bmax; bx += 32)
-					p.bin_tris[atomicAdd(tri_cursor + by * bcx + bx, 1)] = ctri;
+			const int row_cell = (bsy + r) * bcx;
+			while(true) {
+				const bool has = bmin <= bmax;
+				const u32 m = __ballot_sync(0xffffffffu, has);
+				if(m == 0)
+					break;
+				if(has) {
+					const int n = min(bmax - bmin + 1, SEGMENT_BINS);
+					ring[(q_tail + __popc(m & laneMaskLt())) & (DISPATCH_RING - 1)] =
+						make_uint2(tri_idx, (u32)(row_cell + bmin) | ((u32)n << 16));
+					bmin += n;
+				}
+				q_tail += __popc(m);
+				__syncwarp();
+				if(q_tail - q_head >= 32) {
+					drainSegments(p, tri_cursor, ring, q_head + lane, true);
+					q_head += 32;
+					__syncwarp();
+				}
 			}
 		}
 	}
+	if(q_tail > q_head)
+		drainSegments(p, tri_cursor, ring, q_head + lane, lane < q_tail - q_head);
 }
 
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *ev) {
 	int grid = 148 * 4;
-	k_bin_count<<<grid, BIN_THREADS, 0, stream>>>(p);
+	launchPDL(k_bin_count, grid, BIN_THREADS, 0, stream, p);
 	if(ev)
 		cudaEventRecord(ev[0], stream);
-	k_bin_scan<<<1, SCAN_THREADS, 0, stream>>>(p);
+	launchPDL(k_bin_scan, 1, SCAN_THREADS, 0, stream, p);
 	if(ev)
 		cudaEventRecord(ev[1], stream);
-	k_bin_dispatch<<<grid, BIN_THREADS, 0, stream>>>(p);
+	launchPDL(k_bin_dispatch, grid, BIN_THREADS, 0, stream, p);
 	if(ev)
 		cudaEventRecord(ev[2], stream);
 }

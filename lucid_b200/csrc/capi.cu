@@ -15,6 +15,11 @@ using namespace lucid;
 
 static thread_local std::string g_create_error;
 
+bool lucid::pdlEnabled() {
+	static const bool on = getenv("LUCID_NO_PDL") == nullptr;
+	return on;
+}
+
 struct lucid_renderer {
 	LucidCreateInfo ci;
 	Params p;

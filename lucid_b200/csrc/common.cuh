@@ -230,6 +230,29 @@ __device__ __forceinline__ u32 laneMaskLt() {
 	return m;
 }
 
+// ---- programmatic dependent launch -----------------------------------------------------------
+// The frame is a chain of short kernels (tens of microseconds at 1080p), so the gap between two
+// launches matters.  Every kernel is launched with programmatic stream serialisation and starts
+// with pdlEntry(): it lets its own successor be scheduled as soon as all of this grid's CTAs are
+// running, then waits until the predecessor grid has completed and its writes are visible.  The
+// launch latency and CTA ramp-up of kernel n+1 overlap the tail of kernel n.
+__device__ __forceinline__ void pdlEntry() {
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdlEnabled(); // capi.cu: off with LUCID_NO_PDL=1 (A/B timing)
+template <typename... KArgs, typename... Args>
+inline void launchPDL(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args &&...args) {
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((unsigned)block);
+	cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr, cfg.numAttrs = pdlEnabled() ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // kernel launchers (each in its own translation unit)
 void launchFrameBegin(const Params &p, const void *staged_instances, const void *staged_colors,
 					  const void *staged_uv_rects, cudaStream_t stream);

@@ -1194,6 +1194,25 @@ constexpr int BLOCK_WARPS = 4;
 constexpr int KEY_UNROLL = RB_KEY_UNROLL;
 constexpr int WARP_SCRATCH_BYTES = WARP_SCRATCH_FIXED + SMEM_KEYS * 4;
 
+#ifdef RB_PHASE_CLOCKS
+// experiment builds only (tools/variants.py): per-phase clock sums and per-warp finish times
+__device__ unsigned long long g_phase[16];
+__device__ unsigned long long g_warp_end[148 * RB_MIN_CTAS * 4];
+__device__ __forceinline__ unsigned long long gtimer() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#define PHASE_MARK(k)                                                                              \
+	{                                                                                              \
+		long long now_ = clock64();                                                                \
+		ph[k] += (unsigned long long)(now_ - t_mark);                                              \
+		t_mark = now_;                                                                             \
+	}
+#else
+#define PHASE_MARK(k)
+#endif
+
 __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 	k_raster_blocks(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -1214,13 +1233,22 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 			e = __ldcg(p.block_items + (i < n_heavy ? i : p.block_items_cap - 1 - (i - n_heavy)));
 		return e;
 	};
+#ifdef RB_PHASE_CLOCKS
+	unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	long long t_mark = clock64();
+	const unsigned long long t_begin = gtimer();
+#endif
 	uint2 next_entry = fetchEntry(fetchIndex());
 	while(true) {
 		const uint2 entry = next_entry;
 		const u32 item = __shfl_sync(0xffffffffu, entry.x, 0);
 		const int count = (int)__shfl_sync(0xffffffffu, entry.y, 0);
+		PHASE_MARK(0) // work fetch
 		if(count == 0)
 			break;
+#ifdef RB_PHASE_CLOCKS
+		ph[5] += 1, ph[6] += (unsigned long long)count;
+#endif
 		const int bin_id = (int)(item >> 6), sub = (int)(item & 31u);
 		const bool high = (item & 32u) != 0;
 		const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
@@ -1291,6 +1319,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 			}
 		}
 		__syncwarp();
+		PHASE_MARK(1) // key pass
 		const bool light_item = count <= RB_PREFETCH_MAX;
 		u32 next_index = 0;
 		if(light_item)
@@ -1312,6 +1341,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 		}
 		if(light_item)
 			next_entry = fetchEntry(next_index);
+		PHASE_MARK(2) // sort + ties
 		const u32 pos_mask = (1u << slot_bits) - 1u;
 		const int halves = high ? 1 : 2, hb_y = pos_y + ry * (high ? 4 : 8);
 		for(int half = 0; half < halves; half++) {
@@ -1319,9 +1349,19 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 			shadeHalfBlockAny(p, cfg, ws, keys, aux, count, pos_mask, pos_x + cx8, hb_y + half * 4, list);
 			__syncwarp();
 		}
+		PHASE_MARK(3) // shading
 		if(!light_item) // a long item takes its successor only when it is done (dynamic balance)
 			next_entry = fetchEntry(fetchIndex());
 	}
+#ifdef RB_PHASE_CLOCKS
+	if(lane == 0) {
+		for(int k = 0; k < 8; k++)
+			atomicAdd(&g_phase[k], ph[k]);
+		g_warp_end[blockIdx.x * BLOCK_WARPS + warp] = gtimer() - t_begin;
+		atomicMin(&g_phase[8], t_begin);
+		atomicMax(&g_phase[9], gtimer());
+	}
+#endif
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1) {
 		frag_acc += __shfl_xor_sync(0xffffffffu, frag_acc, o);
@@ -1405,6 +1445,18 @@ __global__ void __launch_bounds__(1024) k_promote(const Params p) {
 			p.info->bin_level_dispatches[LUCID_BIN_LEVEL_HIGH][0] = nd;
 	}
 }
+
+#ifdef RB_PHASE_CLOCKS
+extern "C" int lucid_debug_phase_clocks(unsigned long long *dst, unsigned long long *warp_end, int reset) {
+	if(reset) {
+		unsigned long long z[16] = {0};
+		z[8] = ~0ull;
+		return (int)cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+	}
+	cudaMemcpyFromSymbol(dst, g_phase, sizeof(g_phase));
+	return (int)cudaMemcpyFromSymbol(warp_end, g_warp_end, sizeof(g_warp_end));
+}
+#endif
 
 static int rasterBinsGrid(int num_sms) { return num_sms * 4; }
 static int rasterBlocksGrid(int num_sms) { return num_sms * RB_MIN_CTAS; }

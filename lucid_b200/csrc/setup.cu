@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3)
 	__shared__ u32 s_rejected[LUCID_REJECTION_TYPE_COUNT];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	pdlEntry();
 	// CTAs are ordered by ticket, not by blockIdx, so every predecessor in the look-back chain is
 	// guaranteed to be running or finished.
 	if(tid == 0)
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3)
 // k_tri_setup: one thread per triangle of a visible quad (storeTri / storeQuad,
 // quad_setup.glsl:256-340): plane, barycentric and scanline equations, attribute repack
 __global__ void __launch_bounds__(SETUP_THREADS) k_tri_setup(const Params p, const __grid_constant__ LucidConfig cfg) {
+	pdlEntry();
 	const int n_small = p.info->num_visible_quads[0], n_large = p.info->num_visible_quads[1];
 	const int n_tris = (n_small + n_large) * 2;
 	const F3 dir0 = xyz(cfg.frustum.ws_dir0), dirx = xyz(cfg.frustum.ws_dirx);
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_tri_setup(const Params p, con
 __global__ void __launch_bounds__(256) k_frame_begin(const Params p, const uint4 *staged_instances,
 													  const u32 *staged_colors, const uint4 *staged_uv_rects) {
 	const int stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+	pdlEntry();
 	for(int i = first; i < p.num_instances; i += stride) {
 		reinterpret_cast<uint4 *>(const_cast<LucidInstanceData *>(p.instances))[i] = staged_instances[i];
 		const_cast<u32 *>(p.inst_colors)[i] = staged_colors[i];
@@ -501,24 +504,25 @@ __global__ void __launch_bounds__(256) k_frame_begin(const Params p, const uint4
 // (m_info download, lucid_renderer.cpp:341-346) as posted PCIe writes
 __global__ void __launch_bounds__(256) k_info_out(const Params p, u32 *host_info, int num_words) {
 	const u32 *info = reinterpret_cast<const u32 *>(p.info);
+	pdlEntry();
 	for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_words; i += gridDim.x * blockDim.x)
 		host_info[i] = info[i];
 }
 
 void launchFrameBegin(const Params &p, const void *staged_instances, const void *staged_colors,
 					  const void *staged_uv_rects, cudaStream_t stream) {
-	k_frame_begin<<<64, 256, 0, stream>>>(p, (const uint4 *)staged_instances, (const u32 *)staged_colors,
-										   (const uint4 *)staged_uv_rects);
+	launchPDL(k_frame_begin, 64, 256, 0, stream, p, (const uint4 *)staged_instances, (const u32 *)staged_colors,
+			  (const uint4 *)staged_uv_rects);
 }
 void launchInfoOut(const Params &p, u32 *host_info, int num_words, cudaStream_t stream) {
-	k_info_out<<<32, 256, 0, stream>>>(p, host_info, num_words);
+	launchPDL(k_info_out, 32, 256, 0, stream, p, host_info, num_words);
 }
 
 void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream) {
 	if(p.num_setup_ctas == 0)
 		return;
-	k_quad_cull<<<p.num_setup_ctas, SETUP_THREADS, 0, stream>>>(p, cfg);
-	k_tri_setup<<<148 * 8, SETUP_THREADS, 0, stream>>>(p, cfg);
+	launchPDL(k_quad_cull, p.num_setup_ctas, SETUP_THREADS, 0, stream, p, cfg);
+	launchPDL(k_tri_setup, 148 * 8, SETUP_THREADS, 0, stream, p, cfg);
 }
 
 } // namespace lucid
