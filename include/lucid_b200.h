@@ -32,7 +32,10 @@ enum {
 									 copied out on a second stream while the next frame renders, so its
 									 buffer should be pinned and must not be reused before lucid_wait() */
 	LUCID_RENDER_SKIP_INFO = 2,	  /* do not copy LucidInfo back this frame */
-	LUCID_RENDER_FRAG_COUNTS = 4  /* also write the per-pixel fragment-count image (parity tests) */
+	LUCID_RENDER_FRAG_COUNTS = 4, /* also write the per-pixel fragment-count image (parity tests) */
+	LUCID_RENDER_NO_STAGE_TIMES = 8 /* record only the frame's first and last timing event: without events
+									 between them the kernels of a frame overlap their launches
+									 (lucid_stage_times then reports the frame time only) */
 };
 
 /* LucidRenderer::exConstruct(device, compiler, opts, view_size), src/lucid_renderer.cpp:186-317.

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LUCID_INFO_U32_SIZE = 1152
 COUNTS_PER_BIN = 10
 MEM_HOST, MEM_DEVICE, MEM_NONE = 0, 1, 2
-RENDER_ASYNC, RENDER_SKIP_INFO, RENDER_FRAG_COUNTS = 1, 2, 4
+RENDER_ASYNC, RENDER_SKIP_INFO, RENDER_FRAG_COUNTS, RENDER_NO_STAGE_TIMES = 1, 2, 4, 8
 
 OPT_TIMERS = 1 << 4
 OPT_ADDITIVE_BLENDING = 1 << 5

@@ -41,8 +41,9 @@ struct lucid_renderer {
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t render_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
 	bool copy_pending[2] = {false, false};
-	cudaEvent_t upload_done[2] = {nullptr, nullptr};
-	bool upload_pending[2] = {false, false};
+	static constexpr int NUM_STAGING = 3;
+	cudaEvent_t upload_done[NUM_STAGING] = {nullptr, nullptr, nullptr};
+	bool upload_pending[NUM_STAGING] = {false, false, false};
 	u32 *frag_counts = nullptr;
 	void *info_dev = nullptr;
 	size_t info_words = 0;
@@ -60,6 +61,7 @@ struct lucid_renderer {
 	// per-stage events of the last TIMING_RING frames
 	static constexpr int TIMING_RING = 64;
 	cudaEvent_t ev[TIMING_RING][8];
+	bool ev_staged[TIMING_RING] = {};
 	long long frame_counter = 0;
 	bool pending = false;
 };
@@ -117,9 +119,10 @@ void freeAll(lucid_renderer *r) {
 			cudaEventDestroy(r->render_done[i]);
 		if(r->copy_done[i])
 			cudaEventDestroy(r->copy_done[i]);
-		if(r->upload_done[i])
-			cudaEventDestroy(r->upload_done[i]);
 	}
+	for(cudaEvent_t e : r->upload_done)
+		if(e)
+			cudaEventDestroy(e);
 	if(r->copy_stream)
 		cudaStreamDestroy(r->copy_stream);
 	if(r->own_stream && r->stream)
@@ -247,8 +250,8 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &r->d_inst_colors, (size_t)LUCID_MAX_INSTANCES));
 	CUC(devAlloc(r, &r->d_inst_uv_rects, (size_t)LUCID_MAX_INSTANCES));
 	p.instances = r->d_instances, p.inst_colors = r->d_inst_colors, p.inst_uv_rects = r->d_inst_uv_rects;
-	CUC(cudaMallocHost((void **)&r->h_instances, 2 * STAGING_BYTES));
-	for(int i = 0; i < 2; i++)
+	CUC(cudaMallocHost((void **)&r->h_instances, lucid_renderer::NUM_STAGING * STAGING_BYTES));
+	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++)
 		CUC(cudaEventCreateWithFlags(&r->upload_done[i], cudaEventDisableTiming));
 	CUC(cudaMallocHost((void **)&r->h_info, r->info_words * 4));
 	CUC(cudaMemsetAsync(r->info_dev, 0, r->info_words * 4, r->stream));
@@ -360,7 +363,8 @@ int lucid_wait(lucid_renderer *r) {
 	CU(cudaStreamSynchronize(r->copy_stream));
 	r->pending = false;
 	r->copy_pending[0] = r->copy_pending[1] = false;
-	r->upload_pending[0] = r->upload_pending[1] = false;
+	for(bool &b : r->upload_pending)
+		b = false;
 	CU(cudaGetLastError());
 	return LUCID_OK;
 }
@@ -393,9 +397,10 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	double t0 = host_profile ? now() : 0.0;
 	CU(cudaSetDevice(r->ci.device));
 	cudaStream_t st = r->stream;
-	// two pinned staging blocks: the host fills one while the upload of the previous frame may
-	// still be queued behind that frame's kernels
-	const int sb = (int)(r->frame_counter & 1);
+	// three pinned staging blocks: the host fills one while the frames that read the other two may
+	// still be queued (a block is free again when the frame that read it has completed: its event
+	// is recorded at the end of the frame, so no event sits between two kernels of a frame)
+	const int sb = (int)(r->frame_counter % lucid_renderer::NUM_STAGING);
 	if(r->upload_pending[sb]) {
 		CU(cudaEventSynchronize(r->upload_done[sb]));
 		r->upload_pending[sb] = false;
@@ -434,19 +439,29 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	p.frag_counts = (flags & LUCID_RENDER_FRAG_COUNTS) ? r->frag_counts : nullptr;
 
 	double t1 = host_profile ? now() : 0.0;
-	cudaEvent_t *ev = r->ev[r->frame_counter % lucid_renderer::TIMING_RING];
+	const int ring = (int)(r->frame_counter % lucid_renderer::TIMING_RING);
+	cudaEvent_t *ev = r->ev[ring];
+	// per-stage events sit between the kernels and keep each launch from overlapping the tail of
+	// its predecessor (programmatic dependent launch): frames that do not ask for them only get
+	// the frame's first and last event
+	const bool stage_events = !(flags & LUCID_RENDER_NO_STAGE_TIMES);
+	r->ev_staged[ring] = stage_events;
 	CU(cudaEventRecord(ev[0], st));
 	// per-frame uploads and clears (uploadInstances / setupInputData): one kernel reading the
 	// pinned staging block; LucidInfo and the first 6 per-bin arrays are cleared (lucid_renderer.cpp:437)
 	launchFrameBegin(p, h, h + (size_t)LUCID_MAX_INSTANCES * 16, h_uv, st);
+	launchQuadSetup(p, cfg, st);
+	if(stage_events)
+		CU(cudaEventRecord(ev[1], st));
+	double t2 = host_profile ? now() : 0.0;
+	launchBinning(p, st, stage_events ? &ev[2] : nullptr); // ev[2] count, ev[3] scan, ev[4] dispatch
+	double t3 = host_profile ? now() : 0.0;
+	// ev[5] block lists, ev[6] sort + shade (+ frame bookkeeping), ev[7] end of frame
+	launchRaster(p, cfg, st, stage_events ? &ev[5] : nullptr, r->num_sms);
+	if(!stage_events)
+		CU(cudaEventRecord(ev[7], st));
 	CU(cudaEventRecord(r->upload_done[sb], st));
 	r->upload_pending[sb] = true;
-	launchQuadSetup(p, cfg, st);
-	CU(cudaEventRecord(ev[1], st));
-	double t2 = host_profile ? now() : 0.0;
-	launchBinning(p, st, &ev[2]);					// ev[2] count, ev[3] scan, ev[4] dispatch
-	double t3 = host_profile ? now() : 0.0;
-	launchRaster(p, cfg, st, &ev[5], r->num_sms); // ev[5] block lists, ev[6] sort + shade, ev[7] finish
 	CU(cudaGetLastError());
 	r->frame_counter++;
 	double t4 = host_profile ? now() : 0.0;
@@ -503,9 +518,13 @@ int lucid_stage_times_at(lucid_renderer *r, int32_t frames_back, float ms[8]) {
 	int rc = lucid_wait(r);
 	if(rc)
 		return rc;
-	cudaEvent_t *ev = r->ev[(r->frame_counter - 1 - frames_back) % lucid_renderer::TIMING_RING];
-	for(int i = 0; i < 7; i++)
-		CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+	const int ring = (int)((r->frame_counter - 1 - frames_back) % lucid_renderer::TIMING_RING);
+	cudaEvent_t *ev = r->ev[ring];
+	for(int i = 0; i < 7; i++) {
+		ms[i] = 0.0f; // frames rendered with LUCID_RENDER_NO_STAGE_TIMES only have the frame time
+		if(r->ev_staged[ring])
+			CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+	}
 	CU(cudaEventElapsedTime(&ms[7], ev[0], ev[7]));
 	return LUCID_OK;
 }

@@ -1049,6 +1049,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 	__shared__ BinShared sh;
 	__shared__ __align__(16) uint4 s_ring[RASTER_WARPS][PHASE_A_RING * 2];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	pdlEntry();
 	const int n_high = p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH];
 	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
 	while(true) {
@@ -1194,6 +1195,96 @@ constexpr int BLOCK_WARPS = 4;
 constexpr int KEY_UNROLL = RB_KEY_UNROLL;
 constexpr int WARP_SCRATCH_BYTES = WARP_SCRATCH_FIXED + SMEM_KEYS * 4;
 
+// ------------------------------------------------------------------------------------------------
+// frame bookkeeping done by the first CTAs of k_raster_blocks before they take work items (two
+// more launches on a frame of a few hundred microseconds would cost more than the work itself):
+// background for empty bins (the reference leaves them to the application's clear,
+// lucid_app.cpp:606-619), red for bins over the reference's limits (raster_high.glsl:313-317), and
+// the level bookkeeping of promoted bins: appended to the HIGH list in bin order
+// (raster_low.glsl:230-237,294-298).  Everything read here was written by k_raster_bins.
+__device__ __forceinline__ void finishBins(const Params &p, u32 background, u32 *s_mask) {
+	const int lane = laneId(), warp = threadIdx.x >> 5;
+	const int first = blockIdx.x * 32;
+	if(first >= p.bin_count)
+		return;
+	if(warp == 0) {
+		const int b = first + lane;
+		u32 kind = 0; // 1 background, 2 red
+		if(b < p.bin_count) {
+			const int by = b / p.bin_count_x;
+			if(by >= p.row_begin && by < p.row_end) {
+				const bool empty = cntc(p, LUCID_CNT_TRI_COUNTS)[b] + cntc(p, LUCID_CNT_QUAD_COUNTS)[b] * 2 == 0;
+				kind = (p.bin_flags[b] & 2u) ? 2u : empty ? 1u : 0u;
+			}
+		}
+		const u32 fill = __ballot_sync(0xffffffffu, kind != 0), red = __ballot_sync(0xffffffffu, kind == 2);
+		if(lane == 0)
+			s_mask[0] = fill, s_mask[1] = red;
+	}
+	__syncthreads();
+	const u32 red = s_mask[1];
+	u32 fill = s_mask[0];
+	for(int n = 0; fill; n++) {
+		const int j = __ffs(fill) - 1;
+		fill &= fill - 1;
+		if((n & (BLOCK_WARPS - 1)) != warp)
+			continue;
+		const int b = first + j, by = b / p.bin_count_x, bx = b - by * p.bin_count_x;
+		const u32 value = ((red >> j) & 1u) ? 0x000000ffu : background;
+		const int gx = bx * BIN_SIZE + lane;
+		if(gx < p.width)
+			for(int y = 0; y < BIN_SIZE; y++) {
+				const int gy = by * BIN_SIZE + y;
+				if(gy >= p.height)
+					break;
+				p.image[(size_t)gy * p.image_pitch + gx] = value;
+				if(p.frag_counts)
+					p.frag_counts[(size_t)gy * p.width + gx] = 0;
+			}
+	}
+}
+
+__device__ __forceinline__ void promoteBins(const Params &p, int *s_warp) {
+	const int threads = BLOCK_WARPS * 32;
+	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
+	const int *low = cntc(p, LUCID_CNT_LOW_BINS);
+	int *high = p.counts + (size_t)LUCID_CNT_HIGH_BINS * p.bin_count;
+	const int n_high = p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH];
+	const int per = (n_low + threads - 1) / threads;
+	const int i0 = min((int)threadIdx.x * per, n_low), i1 = min(i0 + per, n_low);
+	int mine = 0;
+	for(int i = i0; i < i1; i++)
+		mine += (p.bin_flags[low[i]] & 1u) ? 1 : 0;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int incl = mine;
+	for(int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o)
+			incl += t;
+	}
+	if(lane == 31)
+		s_warp[warp] = incl;
+	__syncthreads();
+	int before = 0, total = 0;
+	for(int w = 0; w < BLOCK_WARPS; w++) {
+		before += w < warp ? s_warp[w] : 0;
+		total += s_warp[w];
+	}
+	if(total == 0)
+		return;
+	int pos = n_high + before + incl - mine;
+	for(int i = i0; i < i1; i++)
+		if(p.bin_flags[low[i]] & 1u)
+			high[pos++] = low[i];
+	if(threadIdx.x == 0) {
+		const int all = n_high + total;
+		p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH] = all;
+		u32 nd = (u32)min(all, p.max_dispatches / 2);
+		if(nd > p.info->bin_level_dispatches[LUCID_BIN_LEVEL_HIGH][0])
+			p.info->bin_level_dispatches[LUCID_BIN_LEVEL_HIGH][0] = nd;
+	}
+}
+
 #ifdef RB_PHASE_CLOCKS
 // experiment builds only (tools/variants.py): per-phase clock sums and per-warp finish times
 __device__ unsigned long long g_phase[16];
@@ -1214,9 +1305,16 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #endif
 
 __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
-	k_raster_blocks(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
+	k_raster_blocks(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg, u32 background) {
 	extern __shared__ __align__(16) unsigned char smem[];
+	__shared__ int s_misc[BLOCK_WARPS];
 	const int lane = laneId(), warp = threadIdx.x >> 5;
+	pdlEntry();
+	finishBins(p, background, reinterpret_cast<u32 *>(s_misc));
+	if(blockIdx.x == gridDim.x - 1) {
+		__syncthreads();
+		promoteBins(p, s_misc);
+	}
 	const WarpScratch ws = warpScratch(smem + (size_t)warp * WARP_SCRATCH_BYTES);
 	u32 *large_keys = p.large_keys + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
 	uint4 *aux = p.block_aux + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
@@ -1375,77 +1473,6 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 	}
 }
 
-// ------------------------------------------------------------------------------------------------
-// stage 3: k_raster_finish -- background for empty bins (the reference leaves them to the
-// application's clear), red for bins over the reference's limits, and the level bookkeeping of
-// promoted bins: appended to the HIGH list in bin order (raster_low.glsl:230-237,294-298)
-__global__ void __launch_bounds__(256) k_raster_finish(const Params p, u32 background) {
-	const int *qc = cntc(p, LUCID_CNT_QUAD_COUNTS), *tc = cntc(p, LUCID_CNT_TRI_COUNTS);
-	for(int b = blockIdx.x; b < p.bin_count; b += gridDim.x) {
-		int by = b / p.bin_count_x, bx = b - by * p.bin_count_x;
-		if(by < p.row_begin || by >= p.row_end)
-			continue;
-		const bool empty = tc[b] + qc[b] * 2 == 0, error = (p.bin_flags[b] & 2u) != 0;
-		if(!empty && !error)
-			continue;
-		const u32 value = error ? 0x000000ffu : background;
-		for(int i = threadIdx.x; i < BIN_SIZE * BIN_SIZE; i += blockDim.x) {
-			int gx = bx * BIN_SIZE + (i & 31), gy = by * BIN_SIZE + (i >> 5);
-			if(gx < p.width && gy < p.height) {
-				p.image[(size_t)gy * p.image_pitch + gx] = value;
-				if(p.frag_counts)
-					p.frag_counts[(size_t)gy * p.width + gx] = 0;
-			}
-		}
-	}
-}
-
-__global__ void __launch_bounds__(1024) k_promote(const Params p) {
-	__shared__ int s_warp[33];
-	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
-	const int *low = cntc(p, LUCID_CNT_LOW_BINS);
-	int *high = p.counts + (size_t)LUCID_CNT_HIGH_BINS * p.bin_count;
-	const int n_high = p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH];
-	const int per = (n_low + 1023) / 1024;
-	const int i0 = min((int)threadIdx.x * per, n_low), i1 = min(i0 + per, n_low);
-	int mine = 0;
-	for(int i = i0; i < i1; i++)
-		mine += (p.bin_flags[low[i]] & 1u) ? 1 : 0;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int incl = mine;
-	for(int o = 1; o < 32; o <<= 1) {
-		int t = __shfl_up_sync(0xffffffffu, incl, o);
-		if(lane >= o)
-			incl += t;
-	}
-	if(lane == 31)
-		s_warp[warp] = incl;
-	__syncthreads();
-	if(warp == 0) {
-		int w = s_warp[lane], wi = w;
-		for(int o = 1; o < 32; o <<= 1) {
-			int t = __shfl_up_sync(0xffffffffu, wi, o);
-			if(lane >= o)
-				wi += t;
-		}
-		s_warp[lane] = wi - w;
-		if(lane == 31)
-			s_warp[32] = wi;
-	}
-	__syncthreads();
-	int pos = n_high + s_warp[warp] + incl - mine;
-	for(int i = i0; i < i1; i++)
-		if(p.bin_flags[low[i]] & 1u)
-			high[pos++] = low[i];
-	if(threadIdx.x == 0 && s_warp[32] > 0) {
-		int total = n_high + s_warp[32];
-		p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH] = total;
-		u32 nd = (u32)min(total, p.max_dispatches / 2);
-		if(nd > p.info->bin_level_dispatches[LUCID_BIN_LEVEL_HIGH][0])
-			p.info->bin_level_dispatches[LUCID_BIN_LEVEL_HIGH][0] = nd;
-	}
-}
-
 #ifdef RB_PHASE_CLOCKS
 extern "C" int lucid_debug_phase_clocks(unsigned long long *dst, unsigned long long *warp_end, int reset) {
 	if(reset) {
@@ -1472,16 +1499,14 @@ void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, 
 	const LucidVec4 &bg = cfg.background_color;
 	auto q = [](float v) { return (u32)(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f + 0.5f); };
 	const u32 bg8 = q(bg.x) | (q(bg.y) << 8) | (q(bg.z) << 16) | 0xff000000u;
-	k_raster_bins<<<rasterBinsGrid(num_sms), RASTER_THREADS, 0, stream>>>(p, bg8);
+	launchPDL(k_raster_bins, rasterBinsGrid(num_sms), RASTER_THREADS, 0, stream, p, bg8);
 	if(ev)
 		cudaEventRecord(ev[0], stream);
-	k_raster_blocks<<<rasterBlocksGrid(num_sms), BLOCK_WARPS * 32, blocks_smem, stream>>>(p, cfg);
-	if(ev)
+	launchPDL(k_raster_blocks, rasterBlocksGrid(num_sms), BLOCK_WARPS * 32, (size_t)blocks_smem, stream, p, cfg, bg8);
+	if(ev) {
 		cudaEventRecord(ev[1], stream);
-	k_raster_finish<<<num_sms * 2, 256, 0, stream>>>(p, bg8);
-	k_promote<<<1, 1024, 0, stream>>>(p);
-	if(ev)
-		cudaEventRecord(ev[2], stream);
+		cudaEventRecord(ev[2], stream); // the finish stage is part of k_raster_blocks now
+	}
 }
 
 } // namespace lucid

@@ -25,9 +25,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   --log-file $out/${tag}_launches_config1.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
   > $out/${tag}_launches_bench.log 2>&1
 
-# full captures: second frame of profile_frame.py (frame 1 is warm-up: k_pad_positions + 11 launches per frame)
+# full captures: second frame of profile_frame.py (frame 1 is warm-up: k_pad_positions + 9 launches per frame)
 for c in $full; do
-  timeout 1200 ncu --set full --clock-control none --import-source on --launch-skip 12 -c 11 \
+  timeout 1200 ncu --set full --clock-control none --import-source on --launch-skip 10 -c 9 \
     -o $out/${tag}_full_config$c -f python tools/profile_frame.py $c 2 > $out/${tag}_full_config$c.log 2>&1
   python tools/ncu_summary.py $out/${tag}_full_config$c.ncu-rep > $out/${tag}_ncu_full_config$c.txt 2>&1
 done
