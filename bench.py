@@ -162,13 +162,22 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     split = args.mode == "split" and world > 1
     nby = (height + 31) // 32
-    rows = None
-    if split:
-        bounds = [round(i * nby / world) for i in range(world + 1)]
-        rows = (bounds[rank], bounds[rank + 1])
-    r = api.LucidRenderer(width, height, 0, args.mvq, device=local_rank, stream=stream.cuda_stream, bin_rows=rows)
+    r = api.LucidRenderer(width, height, 0, args.mvq, device=local_rank, stream=stream.cuda_stream)
     r.set_scene(scene)
     inst, cols, rects = api.build_instances(scene["draw_calls"], scene["materials"])
+    rows = None
+    if split:
+        # row boundaries from the measured per-row raster cost of a full calibration frame (what an
+        # application takes from the previous frame); rank 0's measurement is used by every rank
+        from lucid_b200 import multigpu
+        cam0 = api.make_camera(view_camera(scene, 0), width, height)
+        for _ in range(2):
+            r.render(api.make_config(cam0, len(inst), scene["background"]), inst, cols, rects)
+        cost = torch.from_numpy(r.read_row_costs().astype(np.float64)).cuda()
+        dist.broadcast(cost, src=0)
+        weights = None if args.equal_rows else cost.cpu().numpy()
+        rows = multigpu.split_bin_rows(nby, world, weights)[rank]
+        r.set_bin_rows(*rows)
 
     def config_for(step):
         view = 0 if split else (step * world + rank) % 64
@@ -310,7 +319,9 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.config], "resolution": [width, height],
                        "input_triangles": tris_per_frame, "scale": args.scale,
-                       "parallelism": ("bin-row split x%d, P2P composite" % world) if split else
+                       "parallelism": ("bin-row split x%d (%s), P2P composite; rank 0 rows %s" %
+                                       (world, "equal rows" if args.equal_rows else "balanced on measured row cost",
+                                        list(rows))) if split else
                        ("views sharded x%d" % world if world > 1 else "single GPU"),
                        "l2": "256 MiB device memset between timed frames (untimed)"},
             "mtris_per_sec": round(value * tris_per_frame / 1e6, 2),
@@ -412,6 +423,7 @@ def main():
     ap.add_argument("--mode", default="views", choices=["views", "split"])
     ap.add_argument("--mvq", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--equal-rows", action="store_true", help="--mode split: equal row counts instead of cost-balanced")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -70,6 +70,10 @@ int lucid_set_texture(lucid_renderer *r, int32_t slot, const uint8_t *rgba8_mips
 
 /* change the owned bin rows between frames (load balancing of the bin-row split) */
 int lucid_set_bin_rows(lucid_renderer *r, int32_t begin, int32_t end);
+/* per bin row, the warp cycles the raster kernels spent on it in the last frame: the weights from which
+ * the caller picks the next frame's row boundaries ("choose boundaries from the previous
+ * frame's per-row fragment counts"; measured cycles also cover list building and sorting) */
+int lucid_read_row_costs(lucid_renderer *r, uint64_t *dst, int32_t num_rows);
 
 /* LucidRenderer::render(const Context&), src/lucid_renderer.cpp:319-350: config as filled by
  * setupInputData, instances / colours / uv rects as filled by uploadInstances (host pointers).

@@ -236,6 +236,7 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.setup_ticket, 4));
 	CUC(devAlloc(r, &p.bin_flags, (size_t)p.bin_count));
 	CUC(devAlloc(r, &p.work_counters, 8));
+	CUC(devAlloc(r, &p.row_cost, (size_t)p.bin_count_y));
 	CUC(devAlloc(r, &p.block_lists, (size_t)p.bin_count * (BIN_LIST_BYTES / sizeof(uint4))));
 	CUC(devAlloc(r, &p.block_counts, (size_t)p.bin_count * 32));
 	p.block_items_cap = (u32)p.bin_count * 32u;
@@ -280,6 +281,17 @@ int lucid_set_bin_rows(lucid_renderer *r, int32_t begin, int32_t end) {
 	if(begin < 0 || end > r->p.bin_count_y || begin >= end)
 		return fail(r, LUCID_E_INVALID, "lucid_set_bin_rows: bad range");
 	r->p.row_begin = begin, r->p.row_end = end;
+	return LUCID_OK;
+}
+
+int lucid_read_row_costs(lucid_renderer *r, uint64_t *dst, int32_t num_rows) {
+	if(!r || !dst || num_rows < 0)
+		return LUCID_E_INVALID;
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	const size_t n = (size_t)std::min(num_rows, r->p.bin_count_y);
+	CU(cudaMemcpy(dst, r->p.row_cost, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
 	return LUCID_OK;
 }
 

@@ -980,16 +980,37 @@ __device__ __forceinline__ void binPhaseA(const Params &p, const BinInfo &b, uin
 			rasterBinStep(rs, mn1, mx1, bx1);
 		emit(active, a.w & 0xffffffu, (int)((a.w >> 24) & 7u), mn0, mx0, mn1, mx1, active ? (bx0 | bx1) : 0u);
 	};
-	for(int base = warp * 32; base < b.n_T; base += RASTER_THREADS) {
+	// the triangle's list word and scanline record are two dependent loads: those of the warp's next
+	// 32 triangles are issued before the current ones are walked
+	struct Fetched {
+		u32 tri_idx;
+		bool ok;
+		uint4 s0, s1;
+	};
+	auto fetch = [&](int base) {
+		Fetched f;
 		const int t = base + lane;
-		u32 tri_idx = 0;
-		const bool ok = t < b.n_T && binTriangle(p, t, b.n_q, b.q_off, b.t_off, tri_idx);
+		f.tri_idx = 0;
+		f.ok = t < b.n_T && binTriangle(p, t, b.n_q, b.q_off, b.t_off, f.tri_idx);
+		f.s0 = f.s1 = make_uint4(0, 0, 0, 0);
+		if(f.ok) {
+			const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + f.tri_idx);
+			f.s0 = __ldg(src), f.s1 = __ldg(src + 1);
+		}
+		return f;
+	};
+	Fetched ahead = fetch(warp * 32);
+	for(int base = warp * 32; base < b.n_T; base += RASTER_THREADS) {
+		const Fetched cur = ahead;
+		if(base + RASTER_THREADS < b.n_T)
+			ahead = fetch(base + RASTER_THREADS);
+		const u32 tri_idx = cur.tri_idx;
+		const bool ok = cur.ok;
 		int n_g = 0, min_g = 0;
 		float scan0 = 0, scan1 = 0, scan2 = 0, step0 = 0, step1 = 0, step2 = 0;
 		u32 xneg = 0;
 		if(ok) {
-			const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + tri_idx);
-			uint4 s0 = __ldg(src), s1 = __ldg(src + 1);
+			const uint4 s0 = cur.s0, s1 = cur.s1;
 			int ymin = (int)(s0.w & 0xffff) - b.pos_y, ymax = (int)(s0.w >> 16) - b.pos_y;
 			min_g = min(max(ymin, 0), BIN_SIZE - 1) >> shift;
 			n_g = (min(max(ymax, 0), BIN_SIZE - 1) >> shift) - min_g + 1;
@@ -1060,6 +1081,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 		const int idx = sh.bin_index;
 		if(idx >= n_high + n_low)
 			break;
+		const long long t_bin = clock64();
 		bool high = idx < n_high;
 		const int bin_id = high ? cntc(p, LUCID_CNT_HIGH_BINS)[idx] : cntc(p, LUCID_CNT_LOW_BINS)[idx - n_high];
 		const BinInfo b = loadBin(p, bin_id);
@@ -1160,6 +1182,9 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 			if((light >> tid) & 1)
 				p.block_items[p.block_items_cap - 1 - (base_l + __popc(light & laneMaskLt()))] = make_uint2(item, (u32)c);
 		}
+		if(tid == 0)
+			atomicAdd(reinterpret_cast<unsigned long long *>(p.row_cost) + b.pos_y / BIN_SIZE,
+					  (unsigned long long)(clock64() - t_bin) * RASTER_WARPS);
 		const int rows = high ? 4 : 8;
 		for(int blk = warp; blk < n_blocks; blk += RASTER_WARPS) {
 			if(sh.count[blk] != 0)
@@ -1233,6 +1258,7 @@ __device__ __forceinline__ void finishBins(const Params &p, u32 background, u32 
 		const u32 value = ((red >> j) & 1u) ? 0x000000ffu : background;
 		const int gx = bx * BIN_SIZE + lane;
 		if(gx < p.width)
+#pragma unroll 4
 			for(int y = 0; y < BIN_SIZE; y++) {
 				const int gy = by * BIN_SIZE + y;
 				if(gy >= p.height)
@@ -1344,6 +1370,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 		PHASE_MARK(0) // work fetch
 		if(count == 0)
 			break;
+		const long long t_item = clock64();
 #ifdef RB_PHASE_CLOCKS
 		ph[5] += 1, ph[6] += (unsigned long long)count;
 #endif
@@ -1362,25 +1389,36 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 		// depth keys from the centroid of the covered pixels (raster.glsl:142-176); four entries
 		// per lane are in flight.  The pass leaves (depth plane, constant colour) per entry in the
 		// warp's aux array for the shading loop.
+		auto loadRec = [&](int i) {
+			uint4 r4 = make_uint4(0, 0, 0, 0);
+			if(i < count) {
+				if(high) {
+					uint2 r = __ldg(reinterpret_cast<const uint2 *>(list.base) + i);
+					r4.x = r.x, r4.y = r.y;
+				} else {
+					r4 = __ldg(reinterpret_cast<const uint4 *>(list.base) + i);
+				}
+			}
+			return r4;
+		};
+		uint4 rec_next[KEY_UNROLL];
+#pragma unroll
+		for(int u = 0; u < KEY_UNROLL; u++)
+			rec_next[u] = loadRec(u * 32 + lane);
 		for(int i0 = 0; i0 < count; i0 += 32 * KEY_UNROLL) {
+			// records are one round trip, the triangles' sectors a second, dependent one: the records of
+			// the next iteration are requested together with this iteration's sectors
 			uint4 rec[KEY_UNROLL], dq[KEY_UNROLL], misc[KEY_UNROLL];
 #pragma unroll
 			for(int u = 0; u < KEY_UNROLL; u++) {
-				const int i = i0 + u * 32 + lane;
-				rec[u] = make_uint4(0, 0, 0, 0);
-				if(i < count) {
-					if(high) {
-						uint2 r = __ldg(reinterpret_cast<const uint2 *>(list.base) + i);
-						rec[u].x = r.x, rec[u].y = r.y;
-					} else {
-						rec[u] = __ldg(reinterpret_cast<const uint4 *>(list.base) + i);
-					}
-				}
-			}
-#pragma unroll
-			for(int u = 0; u < KEY_UNROLL; u++) {
+				rec[u] = rec_next[u];
 				const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_shade + (rec[u].x & 0xffffffu));
 				dq[u] = __ldg(src), misc[u] = __ldg(src + 1);
+			}
+			if(i0 + 32 * KEY_UNROLL < count) {
+#pragma unroll
+				for(int u = 0; u < KEY_UNROLL; u++)
+					rec_next[u] = loadRec(i0 + 32 * KEY_UNROLL + u * 32 + lane);
 			}
 #pragma unroll
 			for(int u = 0; u < KEY_UNROLL; u++) {
@@ -1448,6 +1486,8 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 			__syncwarp();
 		}
 		PHASE_MARK(3) // shading
+		if(lane == 0)
+			atomicAdd(reinterpret_cast<unsigned long long *>(p.row_cost) + bin_y, (unsigned long long)(clock64() - t_item));
 		if(!light_item) // a long item takes its successor only when it is done (dynamic balance)
 			next_entry = fetchEntry(fetchIndex());
 	}
