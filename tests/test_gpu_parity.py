@@ -250,3 +250,85 @@ def test_full_size_hairball_properties():
         assert np.array_equal(img, img2)
     finally:
         r.close()
+
+
+def test_full_size_architecture_properties():
+    """configs[3] (10M triangles, textured, large wall/floor triangles, 4K): verifyInfo offsets, unique
+    list entries, the fragment statistic against the per-pixel fragment image, no overflow, a deterministic
+    image, and a bin-row strip rendered on its own reproducing exactly its rows of the full frame."""
+    sc = scenes.get_config(3)
+    r, img = pu.run_cuda(sc, mvq=4793490)
+    try:
+        info = r.read_info()
+        st = api.decode_stats(info, r.bin_count, r.width, r.height)
+        assert r.verifyInfo(info) == []
+        assert st["visible_large"] > 1000 and st["bin_tris"] > 100000
+        assert st["dropped_quads"] == 0 and st["list_overflow"] == 0 and st["invalid_pixels"] == 0
+        assert (img != 0x000000FF).all()
+        fc = r.read_frag_counts()
+        assert int(fc.sum()) <= st["fragments"] <= int(fc.sum()) * 1.02
+        _, counts = api.split_info(info, r.bin_count)
+        bq, bt = r.read_bin_lists(st["bin_quads"], st["bin_tris"])
+        mvq = 4793490
+        for b in np.argsort(counts[3])[-20:]:  # large-triangle lists: unique triangles of large-quad slots
+            seg = np.sort(bt[counts[4][b]:counts[4][b] + counts[3][b]])
+            assert (np.diff(seg.astype(np.int64)) > 0).all()
+            assert (seg >> 1).min() >= mvq - st["visible_large"] and (seg >> 1).max() < mvq
+        assert int(counts[3].sum()) == st["bin_tris"] and int(counts[0].sum()) == st["bin_quads"]
+        _, img2 = pu.run_cuda(sc, renderer=r)
+        assert np.array_equal(img, img2)
+        # rows [20, 41) on their own: same pixels, same per-bin counts
+        rows = (20, 41)
+        cfg, inst, cols, rects = api.prepare_frame(sc)
+        r.set_bin_rows(*rows)
+        strip = np.zeros_like(img)
+        r.render(cfg, inst, cols, rects, out=strip)
+        _, pc = api.split_info(r.read_info(), r.bin_count)
+        y0, y1 = rows[0] * 32, rows[1] * 32
+        assert np.array_equal(strip[y0:y1], img[y0:y1])
+        bcx = (sc["width"] + 31) // 32
+        for which in (0, 3):
+            assert np.array_equal(pc[which][rows[0] * bcx:rows[1] * bcx], counts[which][rows[0] * bcx:rows[1] * bcx])
+            assert pc[which][:rows[0] * bcx].sum() == 0 and pc[which][rows[1] * bcx:].sum() == 0
+    finally:
+        r.close()
+
+
+def test_frames_without_stage_events_and_row_costs(small):
+    """LUCID_RENDER_NO_STAGE_TIMES changes timing bookkeeping only; lucid_read_row_costs reports raster
+    cost exactly for the bin rows that hold work."""
+    sc = small["arch"]
+    r, img = pu.run_cuda(sc)
+    try:
+        cfg, inst, cols, rects = api.prepare_frame(sc)
+        img2 = np.zeros_like(img)
+        r.render(cfg, inst, cols, rects, out=img2, flags=api.RENDER_NO_STAGE_TIMES)
+        assert np.array_equal(img, img2)
+        ms = r.stage_times()
+        assert ms[7] > 0 and (ms[:7] == 0).all()
+        r.render(cfg, inst, cols, rects, out=img2)
+        ms = r.stage_times()
+        assert ms[7] > 0 and ms[0] > 0 and ms[5] > 0
+        cost = r.read_row_costs()
+        _, counts = api.split_info(r.read_info(), r.bin_count)
+        bcx, bcy = (sc["width"] + 31) // 32, (sc["height"] + 31) // 32
+        work = (counts[0] + counts[3]).reshape(bcy, bcx).sum(axis=1)
+        assert cost.shape == (bcy,) and ((cost > 0) == (work > 0)).all()
+        # balanced boundaries from these costs cover every row exactly once
+        parts = multigpu.split_bin_rows(bcy, 3, cost.astype(np.float64))
+        assert parts[0][0] == 0 and parts[-1][1] == bcy and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    finally:
+        r.close()
+
+
+@pytest.mark.parametrize("view", [21, 42])
+def test_orbit_views_against_oracle(view):
+    """configs[4]: other views of the 64-view orbit of the 1M-triangle scene, full size, against the oracle."""
+    sc = scenes.get_config(1)
+    cam = dict(sc["camera"], rot_h=sc["camera"]["rot_h"] + 2.0 * np.pi * view / 64)
+    o = pu.run_oracle(sc, mvq=4793490, threads=os.cpu_count(), camera=cam)
+    r, img = pu.run_cuda(sc, mvq=4793490, camera=cam)
+    try:
+        assert _clean(pu.compare(r, img, o)) == {}
+    finally:
+        r.close()

@@ -30,5 +30,7 @@ for c in $full; do
   timeout 1200 ncu --set full --clock-control none --import-source on --launch-skip 10 -c 9 \
     -o $out/${tag}_full_config$c -f python tools/profile_frame.py $c 2 > $out/${tag}_full_config$c.log 2>&1
   python tools/ncu_summary.py $out/${tag}_full_config$c.ncu-rep > $out/${tag}_ncu_full_config$c.txt 2>&1
+  traffic="$traffic config$c=$out/${tag}_full_config$c.ncu-rep"
 done
+python tools/ncu_traffic.py $traffic > $out/${tag}_dram_traffic.json 2>$out/${tag}_dram_traffic.err
 ls -la $out | tail -40

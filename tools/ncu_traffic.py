@@ -1,0 +1,32 @@
+"""DRAM bytes (read + write) per stage of one captured frame, from `ncu --set full` reports:
+   python tools/ncu_traffic.py config1=a.ncu-rep config3=b.ncu-rep > profiles/dram_traffic.json
+Stages follow bench.py's roofline keys; a stage's traffic is summed over its kernels."""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+STAGE = {"k_quad_cull": "setup", "k_tri_setup": "setup", "k_bin_count": "bin_count", "k_bin_dispatch": "bin_dispatch",
+         "k_raster_bins": "raster", "k_raster_blocks": "raster"}
+out = {}
+for spec in sys.argv[1:]:
+    name, _, path = spec.partition("=")
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    stages, kernels = {}, {}
+    for r in rows[2:]:
+        kname = r[idx["Kernel Name"]].split("(")[0].split("::")[-1]
+        total = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]]
+        kernels[kname] = kernels.get(kname, 0) + int(total)
+        if kname in STAGE:
+            stages[STAGE[kname]] = stages.get(STAGE[kname], 0) + int(total)
+    stages["per_kernel"] = kernels
+    stages["source"] = path.split("/")[-1] + " (ncu --set full, one frame, cold-cache serialised replays)"
+    out[name] = stages
+print(json.dumps(out, indent=1))
