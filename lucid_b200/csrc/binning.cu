@@ -1,11 +1,13 @@
 // binning.cu -- bin counting, offsets + categorisation, dispatch and list canonicalisation.
 //
 // Replaces data/shaders/bin_counter.glsl, bin_categorizer.glsl and bin_dispatcher.glsl.
-// The reference keeps a private shared-memory histogram per work group and a batch linked list
-// so the dispatcher can replay "its own" quads; here counting is a warp-aggregated atomic
-// histogram straight into the per-bin counters (large triangles add +1/-1 to a per-row
-// difference array that the scan kernel integrates), one CTA turns the counters into offsets and
-// the LOW/HIGH bin lists, and dispatch claims list positions with warp-aggregated atomics.
+// Like the reference, a work group (CTA) counts its share of the small quads into a private
+// shared-memory histogram and later claims one slice of every bin it touches
+// (bin_counter.glsl:185-190, bin_dispatcher.glsl:205-209); unlike it, the share is a fixed
+// contiguous chunk of the visible quads, so no batch list has to be kept for the replay: the
+// dispatcher simply recounts its chunk.  Large triangles add +1/-1 to a per-row difference array
+// that the scan kernel integrates; one CTA turns the counters into offsets and the LOW/HIGH bin
+// lists.
 // The order inside a bin's list is therefore arbitrary (as in the reference); the raster stage
 // breaks depth-key ties by triangle index, so the image does not depend on it.
 #include "common.cuh"
@@ -56,33 +58,22 @@ __device__ __forceinline__ void binScanStep(BinScan &s, int &bmin, int &bmax) {
 	bmax = f2i(xmax) >> BIN_SHIFT;
 }
 
-// Adds 1 to counter[bin] for every lane with valid set; lanes that hit the same bin are merged
-// into one atomic.  Returns the lane's position (old value + rank among its peers).
-template <bool NeedResult>
-__device__ __forceinline__ int warpAggregatedAdd(int *counters, int bin, bool valid) {
-	u32 peers = __match_any_sync(0xffffffffu, valid ? bin : -1);
-	int result = 0;
-	if(valid) {
-		int leader = __ffs(peers) - 1;
-		int base = 0;
-		if((int)laneId() == leader) {
-			if(NeedResult)
-				base = atomicAdd(counters + bin, __popc(peers));
-			else
-				atomicAdd(counters + bin, __popc(peers)); // result unused: compiles to RED
-		}
-		if(NeedResult) {
-			base = __shfl_sync(peers, base, leader);
-			result = base + __popc(peers & laneMaskLt());
-		}
-	}
-	return result;
-}
-
 // ------------------------------------------------------------------------------------------------
 // counting (bin_counter.glsl:64-134)
 
+// contiguous chunk of the visible small quads owned by this CTA (same split in count and dispatch)
+struct SmallChunk {
+	int begin, end;
+};
+__device__ __forceinline__ SmallChunk smallChunk(int n_small) {
+	const int per = ((n_small + (int)gridDim.x - 1) / (int)gridDim.x + BIN_THREADS - 1) / BIN_THREADS * BIN_THREADS;
+	SmallChunk c;
+	c.begin = min((int)blockIdx.x * per, n_small), c.end = min(c.begin + per, n_small);
+	return c;
+}
+
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
+	extern __shared__ int s_hist[]; // one counter per bin
 	pdlEntry();
 	const int n_small = p.info->num_visible_quads[0], n_large = p.info->num_visible_quads[1];
 	int *quad_counts = cnt(p, LUCID_CNT_QUAD_COUNTS);
@@ -91,10 +82,18 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
 	const int stride = gridDim.x * blockDim.x;
 	const int first = blockIdx.x * blockDim.x + threadIdx.x;
 
-	// small quads: every bin of the (<= 4 bins) AABB, conservative
-	for(int base = blockIdx.x * blockDim.x; base < n_small; base += stride) {
+	// small quads: every bin of the (<= 4 bins) AABB, conservative.  A CTA counts a contiguous chunk
+	// of the visible quads into a private shared-memory histogram and adds its non-zero bins to the
+	// global counters once: visible quads keep their input order, so a chunk is spatially coherent
+	// and touches few bins, while quad-by-quad global atomics pile up on the scene's hot bins (the
+	// reference keeps per-work-group histograms for the same reason, bin_counter.glsl:185-190)
+	for(int b = threadIdx.x; b < p.bin_count; b += BIN_THREADS)
+		s_hist[b] = 0;
+	__syncthreads();
+	const SmallChunk chunk = smallChunk(n_small);
+	for(int base = chunk.begin; base < chunk.end; base += BIN_THREADS) {
 		int q = base + threadIdx.x;
-		bool valid = q < n_small;
+		bool valid = q < chunk.end;
 		u32 enc = valid ? p.quad_aabbs[q] : 0u;
 		int bsx = enc & 0x7f, bsy = (enc >> 7) & 0x7f, bex = (enc >> 14) & 0x7f, bey = (enc >> 21) & 0x7f;
 		int w = bex - bsx + 1, n = valid ? w * (bey - bsy + 1) : 0;
@@ -102,8 +101,15 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
 		for(int k = 0; k < 4; k++) {
 			int by = bsy + k / max(w, 1), bx = bsx + k % max(w, 1);
 			bool ok = k < n && by >= p.row_begin && by < p.row_end;
-			warpAggregatedAdd<false>(quad_counts, by * bcx + bx, ok);
+			if(ok)
+				atomicAdd(&s_hist[by * bcx + bx], 1); // shared-memory atomics resolve same-bin lanes in hardware
 		}
+	}
+	__syncthreads();
+	for(int b = threadIdx.x; b < p.bin_count; b += BIN_THREADS) {
+		const int c = s_hist[b];
+		if(c != 0)
+			atomicAdd(quad_counts + b, c);
 	}
 	// large triangles: one thread per triangle, +1 at the first bin of each row span and -1 just
 	// after the last (bin_counter.glsl:123-133)
@@ -287,6 +293,7 @@ __device__ __forceinline__ void drainSegments(const Params &p, int *tri_cursor, 
 
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 	__shared__ uint2 s_ring[BIN_THREADS / 32][DISPATCH_RING];
+	extern __shared__ int s_hist[]; // one counter / cursor per bin
 	pdlEntry();
 	if(p.info->temp[1] != 0)
 		return; // lists would overflow their buffers
@@ -297,34 +304,41 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 	const int stride = gridDim.x * blockDim.x;
 	const int lane = laneId();
 
-	// small quads: the position claims of the (up to four) bins are all issued before the first
-	// result is needed
-	for(int base = blockIdx.x * blockDim.x; base < n_small; base += stride) {
-		int q = base + threadIdx.x;
-		bool valid = q < n_small;
-		u32 enc = valid ? p.quad_aabbs[q] : 0u;
-		u32 word = (u32)q | (enc & 0xf0000000u);
-		int bsx = enc & 0x7f, bsy = (enc >> 7) & 0x7f, bex = (enc >> 14) & 0x7f, bey = (enc >> 21) & 0x7f;
-		int w = bex - bsx + 1, n = valid ? w * (bey - bsy + 1) : 0;
-		u32 peers[4];
-		int claimed[4], bin[4];
-		bool ok[4];
+	// small quads: the CTA recounts its chunk into the shared-memory histogram, claims one range per
+	// non-zero bin with a single global atomic (all claims of a thread are in flight together), and
+	// hands out the positions inside its ranges with shared-memory atomics
+	for(int b = threadIdx.x; b < p.bin_count; b += BIN_THREADS)
+		s_hist[b] = 0;
+	__syncthreads();
+	const SmallChunk chunk = smallChunk(n_small);
+	for(int pass = 0; pass < 2; pass++) {
+		for(int base = chunk.begin; base < chunk.end; base += BIN_THREADS) {
+			int q = base + threadIdx.x;
+			bool valid = q < chunk.end;
+			u32 enc = valid ? p.quad_aabbs[q] : 0u;
+			u32 word = (u32)q | (enc & 0xf0000000u);
+			int bsx = enc & 0x7f, bsy = (enc >> 7) & 0x7f, bex = (enc >> 14) & 0x7f, bey = (enc >> 21) & 0x7f;
+			int w = bex - bsx + 1, n = valid ? w * (bey - bsy + 1) : 0;
 #pragma unroll
-		for(int k = 0; k < 4; k++) {
-			int by = bsy + k / max(w, 1), bx = bsx + k % max(w, 1);
-			ok[k] = k < n && by >= p.row_begin && by < p.row_end;
-			bin[k] = by * bcx + bx;
-			peers[k] = __match_any_sync(0xffffffffu, ok[k] ? bin[k] : -1);
-			claimed[k] = 0;
-			if(ok[k] && lane == __ffs(peers[k]) - 1)
-				claimed[k] = atomicAdd(quad_cursor + bin[k], __popc(peers[k]));
+			for(int k = 0; k < 4; k++) {
+				int by = bsy + k / max(w, 1), bx = bsx + k % max(w, 1);
+				bool ok = k < n && by >= p.row_begin && by < p.row_end;
+				if(ok) {
+					const int pos = atomicAdd(&s_hist[by * bcx + bx], 1);
+					if(pass == 1)
+						p.bin_quads[pos] = word;
+				}
+			}
 		}
-#pragma unroll
-		for(int k = 0; k < 4; k++) {
-			// lanes without a bin form the peer group of key -1: their shuffle result is unused
-			int first = __shfl_sync(0xffffffffu, claimed[k], __ffs(peers[k]) - 1);
-			if(ok[k])
-				p.bin_quads[first + __popc(peers[k] & laneMaskLt())] = word;
+		__syncthreads();
+		if(pass == 0) {
+#pragma unroll 4
+			for(int b = threadIdx.x; b < p.bin_count; b += BIN_THREADS) {
+				const int c = s_hist[b];
+				if(c != 0)
+					s_hist[b] = atomicAdd(quad_cursor + b, c);
+			}
+			__syncthreads();
 		}
 	}
 
@@ -384,13 +398,22 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *ev) {
 	int grid = 148 * 4;
-	launchPDL(k_bin_count, grid, BIN_THREADS, 0, stream, p);
+	const size_t hist_bytes = (size_t)p.bin_count * sizeof(int);
+	static bool configured[64] = {}; // function attributes are per device
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if(!configured[dev & 63]) { // up to 128 x 128 bins (7-bit bin coordinates)
+		cudaFuncSetAttribute(k_bin_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * (int)sizeof(int));
+		cudaFuncSetAttribute(k_bin_dispatch, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * (int)sizeof(int));
+		configured[dev & 63] = true;
+	}
+	launchPDL(k_bin_count, grid, BIN_THREADS, hist_bytes, stream, p);
 	if(ev)
 		cudaEventRecord(ev[0], stream);
 	launchPDL(k_bin_scan, 1, SCAN_THREADS, 0, stream, p);
 	if(ev)
 		cudaEventRecord(ev[1], stream);
-	launchPDL(k_bin_dispatch, grid, BIN_THREADS, 0, stream, p);
+	launchPDL(k_bin_dispatch, grid, BIN_THREADS, hist_bytes, stream, p);
 	if(ev)
 		cudaEventRecord(ev[2], stream);
 }

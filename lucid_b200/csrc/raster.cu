@@ -1530,11 +1530,13 @@ static int rasterBlocksGrid(int num_sms) { return num_sms * RB_MIN_CTAS; }
 size_t rasterLargeKeysCount(int num_sms) { return (size_t)rasterBlocksGrid(num_sms) * BLOCK_WARPS * MAX_HBLOCK_TRIS; }
 
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, cudaEvent_t *ev, int num_sms) {
-	static bool configured = false;
+	static bool configured[64] = {}; // function attributes are per device
 	const int blocks_smem = BLOCK_WARPS * WARP_SCRATCH_BYTES;
-	if(!configured) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if(!configured[dev & 63]) {
 		cudaFuncSetAttribute(k_raster_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, blocks_smem);
-		configured = true;
+		configured[dev & 63] = true;
 	}
 	const LucidVec4 &bg = cfg.background_color;
 	auto q = [](float v) { return (u32)(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f + 0.5f); };

@@ -36,7 +36,7 @@ python tools/ncu_traffic.py $traffic > $out/${tag}_dram_traffic.json 2>$out/${ta
 # per-function instruction / stall-sample shares of the dominant kernel, then drop the reports
 # (gpurun only copies 64 MiB back)
 for c in $full; do
-  ncu -i $out/${tag}_full_config$c.ncu-rep --page source --csv --kernel-name regex:k_raster_blocks > $out/src_$c.csv 2>/dev/null
+  ncu -i $out/${tag}_full_config$c.ncu-rep --page source --csv --print-source cuda,sass --kernel-name k_raster_blocks > $out/src_$c.csv 2>/dev/null
   python tools/ncu_funcs.py $out/src_$c.csv > $out/${tag}_raster_blocks_config${c}_functions.txt 2>&1
   rm -f $out/src_$c.csv $out/${tag}_full_config$c.ncu-rep
 done
