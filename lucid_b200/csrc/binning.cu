@@ -140,103 +140,113 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
 // offsets + categories (bin_categorizer.glsl:22-89), one CTA
 
 constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int MAX_SCAN_TILES = 128 * 128 / SCAN_THREADS; // 7-bit bin coordinates
 
-// exclusive prefix sum over the CTA of one int per thread
-__device__ __forceinline__ int blockExclusiveScan(int value, int *s_warp, int &total) {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int incl = value;
-#pragma unroll
-	for(int o = 1; o < 32; o <<= 1) {
-		int t = __shfl_up_sync(0xffffffffu, incl, o);
-		if(lane >= o)
-			incl += t;
-	}
-	if(lane == 31)
-		s_warp[warp] = incl;
-	__syncthreads();
-	if(warp == 0) {
-		int w = s_warp[lane];
-		int wi = w;
-#pragma unroll
-		for(int o = 1; o < 32; o <<= 1) {
-			int t = __shfl_up_sync(0xffffffffu, wi, o);
-			if(lane >= o)
-				wi += t;
-		}
-		s_warp[lane] = wi - w;
-		if(lane == 31)
-			s_warp[32] = wi;
-	}
-	__syncthreads();
-	int result = s_warp[warp] + incl - value;
-	total = s_warp[32];
-	__syncthreads();
-	return result;
-}
-
+// The CTA walks the bins in tiles of 1024 consecutive bins (thread = bin, so every load and store
+// is coalesced; the values of all tiles are requested up front): one fused block scan per tile over
+// (quad count, triangle count, LOW | HIGH << 16 membership) with the totals carried from tile to
+// tile, so offsets and level lists come out in bin order.
 __global__ void __launch_bounds__(SCAN_THREADS) k_bin_scan(const Params p) {
-	__shared__ int s_warp[33];
+	__shared__ int s_warp[3][SCAN_WARPS + 1];
 	pdlEntry();
 	const int bc = p.bin_count, bcx = p.bin_count_x, bcy = p.bin_count_y;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	int *qc = cnt(p, LUCID_CNT_QUAD_COUNTS), *qo = cnt(p, LUCID_CNT_QUAD_OFFSETS);
 	int *qt = cnt(p, LUCID_CNT_QUAD_OFFSETS_TEMP);
 	int *tc = cnt(p, LUCID_CNT_TRI_COUNTS), *to = cnt(p, LUCID_CNT_TRI_OFFSETS);
 	int *tt = cnt(p, LUCID_CNT_TRI_OFFSETS_TEMP);
 	int *low = cnt(p, LUCID_CNT_LOW_BINS), *high = cnt(p, LUCID_CNT_HIGH_BINS);
 
-	// integrate the large-triangle difference arrays row by row (one warp per bin row)
-	for(int by = threadIdx.x >> 5; by < bcy; by += SCAN_THREADS / 32) {
+	// integrate the large-triangle difference arrays row by row (one warp per bin row; the row's
+	// chunks of 32 bins are loaded together, then scanned in order)
+	for(int by = warp; by < bcy; by += SCAN_WARPS) {
+		int v[4];
+#pragma unroll
+		for(int c = 0; c < 4; c++) {
+			const int bx = c * 32 + lane;
+			v[c] = bx < bcx ? tc[by * bcx + bx] : 0;
+		}
 		int carry = 0;
-		for(int bx0 = 0; bx0 < bcx; bx0 += 32) {
-			int bx = bx0 + (threadIdx.x & 31);
-			int v = bx < bcx ? tc[by * bcx + bx] : 0;
+#pragma unroll
+		for(int c = 0; c < 4; c++) {
+			if(c * 32 >= bcx)
+				break;
+			int x = v[c];
 #pragma unroll
 			for(int o = 1; o < 32; o <<= 1) {
-				int t = __shfl_up_sync(0xffffffffu, v, o);
-				if((threadIdx.x & 31) >= o)
-					v += t;
+				int t = __shfl_up_sync(0xffffffffu, x, o);
+				if(lane >= o)
+					x += t;
 			}
-			v += carry;
+			x += carry;
+			const int bx = c * 32 + lane;
 			if(bx < bcx)
-				tc[by * bcx + bx] = v;
-			carry = __shfl_sync(0xffffffffu, v, 31);
+				tc[by * bcx + bx] = x;
+			carry = __shfl_sync(0xffffffffu, x, 31);
 		}
 	}
 	__syncthreads();
 
-	// each thread owns a contiguous run of bins so offsets and level lists come out in bin order
-	const int per = (bc + SCAN_THREADS - 1) / SCAN_THREADS;
-	const int b0 = min(threadIdx.x * per, bc), b1 = min(b0 + per, bc);
-	int sum_q = 0, sum_t = 0, n_low = 0, n_high = 0, n_empty = 0;
-	for(int b = b0; b < b1; b++) {
-		int q = qc[b], t = tc[b];
-		sum_q += q, sum_t += t;
-		int num_tris = t + q * 2;
-		if(num_tris == 0)
-			n_empty++;
-		else if(num_tris < 1024)
-			n_low++;
-		else
-			n_high++;
+	const int tiles = (bc + SCAN_THREADS - 1) / SCAN_THREADS;
+	int q_of[MAX_SCAN_TILES], t_of[MAX_SCAN_TILES];
+#pragma unroll
+	for(int i = 0; i < MAX_SCAN_TILES; i++) {
+		const int b = i * SCAN_THREADS + (int)threadIdx.x;
+		q_of[i] = 0, t_of[i] = 0;
+		if(i < tiles && b < bc)
+			q_of[i] = qc[b], t_of[i] = tc[b];
 	}
-	int tot_q, tot_t, tot_low, tot_high, tot_empty;
-	int off_q = blockExclusiveScan(sum_q, s_warp, tot_q);
-	int off_t = blockExclusiveScan(sum_t, s_warp, tot_t);
-	int off_low = blockExclusiveScan(n_low, s_warp, tot_low);
-	int off_high = blockExclusiveScan(n_high, s_warp, tot_high);
-	blockExclusiveScan(n_empty, s_warp, tot_empty);
-	for(int b = b0; b < b1; b++) {
-		int q = qc[b], t = tc[b];
-		qo[b] = off_q, qt[b] = off_q, to[b] = off_t, tt[b] = off_t;
-		off_q += q, off_t += t;
-		int num_tris = t + q * 2;
-		if(num_tris == 0) {
-		} else if(num_tris < 1024)
-			low[off_low++] = b;
-		else
-			high[off_high++] = b;
-		p.bin_flags[b] = 0;
+	int base_q = 0, base_t = 0, base_low = 0, base_high = 0;
+#pragma unroll
+	for(int i = 0; i < MAX_SCAN_TILES; i++) {
+		if(i >= tiles)
+			break;
+		const int b = i * SCAN_THREADS + (int)threadIdx.x;
+		const int q = q_of[i], t = t_of[i];
+		const int num_tris = t + q * 2;
+		const bool valid = b < bc;
+		const bool is_low = valid && num_tris != 0 && num_tris < 1024, is_high = valid && num_tris >= 1024;
+		int xq = q, xt = t, xl = (is_low ? 1 : 0) | (is_high ? 1 << 16 : 0);
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			int a0 = __shfl_up_sync(0xffffffffu, xq, o), a1 = __shfl_up_sync(0xffffffffu, xt, o);
+			int a2 = __shfl_up_sync(0xffffffffu, xl, o);
+			if(lane >= o)
+				xq += a0, xt += a1, xl += a2;
+		}
+		if(lane == 31)
+			s_warp[0][warp] = xq, s_warp[1][warp] = xt, s_warp[2][warp] = xl;
+		__syncthreads();
+		if(warp < 3) {
+			int w = s_warp[warp][lane], wi = w;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) {
+				int a = __shfl_up_sync(0xffffffffu, wi, o);
+				if(lane >= o)
+					wi += a;
+			}
+			s_warp[warp][lane] = wi - w;
+			if(lane == 31)
+				s_warp[warp][SCAN_WARPS] = wi;
+		}
+		__syncthreads();
+		const int off_q = base_q + s_warp[0][warp] + xq - q, off_t = base_t + s_warp[1][warp] + xt - t;
+		const int lh = s_warp[2][warp] + xl - ((is_low ? 1 : 0) | (is_high ? 1 << 16 : 0));
+		if(valid) {
+			qo[b] = off_q, qt[b] = off_q, to[b] = off_t, tt[b] = off_t;
+			if(is_low)
+				low[base_low + (lh & 0xffff)] = b;
+			if(is_high)
+				high[base_high + (lh >> 16)] = b;
+			p.bin_flags[b] = 0;
+		}
+		base_q += s_warp[0][SCAN_WARPS], base_t += s_warp[1][SCAN_WARPS];
+		base_low += s_warp[2][SCAN_WARPS] & 0xffff, base_high += s_warp[2][SCAN_WARPS] >> 16;
+		__syncthreads();
 	}
+	const int tot_q = base_q, tot_t = base_t, tot_low = base_low, tot_high = base_high;
+	const int tot_empty = bc - tot_low - tot_high;
 	if(threadIdx.x == 0) {
 		LucidInfo *info = p.info;
 		info->bin_level_counts[LUCID_BIN_LEVEL_EMPTY] = tot_empty;

@@ -281,7 +281,10 @@ __device__ __forceinline__ void lbStore(u64 *ptr, u64 v) {
 // quads tid, tid + 256, ... of the instance, so the loads of up to four quads are in flight
 // together and one look-back step covers 1024 quads.  The per-triangle records are left to
 // k_tri_setup, which runs over the compacted slots without any barrier.
-__global__ void __launch_bounds__(SETUP_THREADS, 3)
+#ifndef SETUP_CULL_MIN_CTAS
+#define SETUP_CULL_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 	k_quad_cull(const Params p, const __grid_constant__ LucidConfig cfg) {
 	__shared__ u32 s_vid;
 	__shared__ int s_counts[SETUP_PARTS * (SETUP_THREADS / 32)][2]; // per (part, warp): small, large
@@ -432,7 +435,10 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3)
 
 // k_tri_setup: one thread per triangle of a visible quad (storeTri / storeQuad,
 // quad_setup.glsl:256-340): plane, barycentric and scanline equations, attribute repack
-__global__ void __launch_bounds__(SETUP_THREADS) k_tri_setup(const Params p, const __grid_constant__ LucidConfig cfg) {
+#ifndef SETUP_TRI_MIN_CTAS
+#define SETUP_TRI_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(SETUP_THREADS, SETUP_TRI_MIN_CTAS) k_tri_setup(const Params p, const __grid_constant__ LucidConfig cfg) {
 	pdlEntry();
 	const int n_small = p.info->num_visible_quads[0], n_large = p.info->num_visible_quads[1];
 	const int n_tris = (n_small + n_large) * 2;
@@ -524,7 +530,7 @@ void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t strea
 	if(p.num_setup_ctas == 0)
 		return;
 	launchPDL(k_quad_cull, p.num_setup_ctas, SETUP_THREADS, 0, stream, p, cfg);
-	launchPDL(k_tri_setup, 148 * 8, SETUP_THREADS, 0, stream, p, cfg);
+	launchPDL(k_tri_setup, 148 * 2 * SETUP_TRI_MIN_CTAS, SETUP_THREADS, 0, stream, p, cfg);
 }
 
 } // namespace lucid
