@@ -354,6 +354,28 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 
 	uint2 *ring = s_ring[threadIdx.x >> 5];
 	int q_head = 0, q_tail = 0; // warp-uniform
+	// all lanes: queue the span [bmin, bmax] of bin row `row_cell / bcx` in segments, draining when 32 wait
+	auto pushSpan = [&](u32 tri_idx, int row_cell, int bmin, int bmax) {
+		while(true) {
+			const bool has = bmin <= bmax;
+			const u32 m = __ballot_sync(0xffffffffu, has);
+			if(m == 0)
+				break;
+			if(has) {
+				const int n = min(bmax - bmin + 1, SEGMENT_BINS);
+				ring[(q_tail + __popc(m & laneMaskLt())) & (DISPATCH_RING - 1)] =
+					make_uint2(tri_idx, (u32)(row_cell + bmin) | ((u32)n << 16));
+				bmin += n;
+			}
+			q_tail += __popc(m);
+			__syncwarp();
+			if(q_tail - q_head >= 32) {
+				drainSegments(p, tri_cursor, ring, q_head + lane, true);
+				q_head += 32;
+				__syncwarp();
+			}
+		}
+	};
 	for(int base = blockIdx.x * blockDim.x; base < n_large * 2; base += stride) {
 		int i = base + threadIdx.x;
 		bool valid = i < n_large * 2;
@@ -363,42 +385,68 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 		u32 tri_idx = (u32)quad_idx * 2 + second;
 		int bsx = enc & 0x7f, bex = (enc >> 14) & 0x7f, bsy = 0, bey = -1;
 		BinScan s;
+#pragma unroll
+		for(int e = 0; e < 3; e++)
+			s.mn[e] = s.mx[e] = s.step[e] = 0.0f;
 		if(valid) {
 			TriScan t;
 			const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_scan + tri_idx);
 			t.s0 = src[0], t.s1 = src[1];
 			s = loadBinScan(t, bsy, bey);
 		}
-		const int rows = valid ? bey - bsy + 1 : 0;
-		const int max_rows = __reduce_max_sync(0xffffffffu, rows);
+		int rows = valid ? bey - bsy + 1 : 0;
+		// A triangle with many segments (a wall across the screen) would keep the warp in the row
+		// loop with one busy lane: the warp takes it over afterwards, one lane per bin row.
+		const bool big = rows * ((bex - bsx) / SEGMENT_BINS + 1) > 48;
+		u32 big_mask = __ballot_sync(0xffffffffu, big);
+		const int own_rows = big ? 0 : rows;
+		const int max_rows = __reduce_max_sync(0xffffffffu, own_rows);
 		for(int r = 0; r < max_rows; r++) {
 			int bmin = 0, bmax = -1;
-			if(r < rows) {
+			if(r < own_rows) {
 				binScanStep(s, bmin, bmax);
 				bmin = max(bmin, bsx), bmax = min(bmax, bex);
 				const int by = bsy + r;
 				if(by < p.row_begin || by >= p.row_end)
 					bmax = bmin - 1;
 			}
-			const int row_cell = (bsy + r) * bcx;
-			while(true) {
-				const bool has = bmin <= bmax;
-				const u32 m = __ballot_sync(0xffffffffu, has);
-				if(m == 0)
-					break;
-				if(has) {
-					const int n = min(bmax - bmin + 1, SEGMENT_BINS);
-					ring[(q_tail + __popc(m & laneMaskLt())) & (DISPATCH_RING - 1)] =
-						make_uint2(tri_idx, (u32)(row_cell + bmin) | ((u32)n << 16));
-					bmin += n;
+			pushSpan(tri_idx, (bsy + r) * bcx, bmin, bmax);
+		}
+		while(big_mask) {
+			const int src_lane = __ffs(big_mask) - 1;
+			big_mask &= big_mask - 1;
+			BinScan bs;
+#pragma unroll
+			for(int e = 0; e < 3; e++) {
+				bs.mn[e] = __shfl_sync(0xffffffffu, s.mn[e], src_lane);
+				bs.mx[e] = __shfl_sync(0xffffffffu, s.mx[e], src_lane);
+				bs.step[e] = __shfl_sync(0xffffffffu, s.step[e], src_lane);
+			}
+			const int b_rows = __shfl_sync(0xffffffffu, rows, src_lane), b_bsy = __shfl_sync(0xffffffffu, bsy, src_lane);
+			const int b_bsx = __shfl_sync(0xffffffffu, bsx, src_lane), b_bex = __shfl_sync(0xffffffffu, bex, src_lane);
+			const u32 b_tri = __shfl_sync(0xffffffffu, tri_idx, src_lane);
+			for(int r0 = 0; r0 < b_rows; r0 += 32) {
+				// the row scan is a chain of additions: lane l repeats the first r0 + l of them, so its
+				// state is bit for bit the one the serial loop has at that row
+				BinScan mine = bs;
+				for(int k = 0; k < lane; k++)
+#pragma unroll
+					for(int e = 0; e < 3; e++)
+						mine.mn[e] += mine.step[e], mine.mx[e] += mine.step[e];
+				const int r = r0 + lane;
+				int bmin = 0, bmax = -1;
+				if(r < b_rows) {
+					binScanStep(mine, bmin, bmax);
+					bmin = max(bmin, b_bsx), bmax = min(bmax, b_bex);
+					const int by = b_bsy + r;
+					if(by < p.row_begin || by >= p.row_end)
+						bmax = bmin - 1;
 				}
-				q_tail += __popc(m);
-				__syncwarp();
-				if(q_tail - q_head >= 32) {
-					drainSegments(p, tri_cursor, ring, q_head + lane, true);
-					q_head += 32;
-					__syncwarp();
-				}
+				pushSpan(b_tri, (b_bsy + r) * bcx, bmin, bmax);
+				for(int k = 0; k < 32; k++)
+#pragma unroll
+					for(int e = 0; e < 3; e++)
+						bs.mn[e] += bs.step[e], bs.mx[e] += bs.step[e];
 			}
 		}
 	}

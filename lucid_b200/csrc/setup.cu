@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 // k_tri_setup: one thread per triangle of a visible quad (storeTri / storeQuad,
 // quad_setup.glsl:256-340): plane, barycentric and scanline equations, attribute repack
 #ifndef SETUP_TRI_MIN_CTAS
-#define SETUP_TRI_MIN_CTAS 4
+#define SETUP_TRI_MIN_CTAS 5
 #endif
 __global__ void __launch_bounds__(SETUP_THREADS, SETUP_TRI_MIN_CTAS) k_tri_setup(const Params p, const __grid_constant__ LucidConfig cfg) {
 	pdlEntry();
