@@ -47,9 +47,12 @@ struct lucid_renderer {
 	u32 *frag_counts = nullptr;
 	void *info_dev = nullptr;
 	size_t info_words = 0;
-	LucidInstanceData *d_instances = nullptr;
-	u32 *d_inst_colors = nullptr;
-	float4 *d_inst_uv_rects = nullptr;
+	// per-frame instance data: a ring of device blocks filled by a copy on upload_stream at submission
+	// time (instances, then uv rects, then colours, tightly packed), so the frame's kernels never read
+	// host memory -- zero-copy reads queue behind the posted writes of an image read-back on PCIe
+	unsigned char *d_inst_ring[NUM_STAGING] = {nullptr, nullptr, nullptr};
+	cudaStream_t upload_stream = nullptr;
+	cudaEvent_t upload_ready[NUM_STAGING] = {nullptr, nullptr, nullptr};
 
 	// pinned host staging
 	unsigned char *h_instances = nullptr; // instances + colors + uv rects
@@ -125,6 +128,11 @@ void freeAll(lucid_renderer *r) {
 			cudaEventDestroy(e);
 	if(r->copy_stream)
 		cudaStreamDestroy(r->copy_stream);
+	if(r->upload_stream)
+		cudaStreamDestroy(r->upload_stream);
+	for(cudaEvent_t e : r->upload_ready)
+		if(e)
+			cudaEventDestroy(e);
 	if(r->own_stream && r->stream)
 		cudaStreamDestroy(r->stream);
 }
@@ -187,6 +195,7 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 		for(auto &ev : set)
 			CUC(cudaEventCreate(&ev));
 	CUC(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+	CUC(cudaStreamCreateWithFlags(&r->upload_stream, cudaStreamNonBlocking));
 	for(int i = 0; i < 2; i++) {
 		CUC(cudaEventCreateWithFlags(&r->render_done[i], cudaEventDisableTiming));
 		CUC(cudaEventCreateWithFlags(&r->copy_done[i], cudaEventDisableTiming));
@@ -247,10 +256,10 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &r->images[1], (size_t)p.width * p.height));
 	r->image = r->images[0];
 	CUC(devAlloc(r, &r->frag_counts, (size_t)p.width * p.height));
-	CUC(devAlloc(r, &r->d_instances, (size_t)LUCID_MAX_INSTANCES));
-	CUC(devAlloc(r, &r->d_inst_colors, (size_t)LUCID_MAX_INSTANCES));
-	CUC(devAlloc(r, &r->d_inst_uv_rects, (size_t)LUCID_MAX_INSTANCES));
-	p.instances = r->d_instances, p.inst_colors = r->d_inst_colors, p.inst_uv_rects = r->d_inst_uv_rects;
+	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++) {
+		CUC(devAlloc(r, &r->d_inst_ring[i], STAGING_BYTES));
+		CUC(cudaEventCreateWithFlags(&r->upload_ready[i], cudaEventDisableTiming));
+	}
 	CUC(cudaMallocHost((void **)&r->h_instances, lucid_renderer::NUM_STAGING * STAGING_BYTES));
 	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++)
 		CUC(cudaEventCreateWithFlags(&r->upload_done[i], cudaEventDisableTiming));
@@ -373,6 +382,7 @@ int lucid_wait(lucid_renderer *r) {
 	CU(cudaSetDevice(r->ci.device));
 	CU(cudaStreamSynchronize(r->stream));
 	CU(cudaStreamSynchronize(r->copy_stream));
+	CU(cudaStreamSynchronize(r->upload_stream));
 	r->pending = false;
 	r->copy_pending[0] = r->copy_pending[1] = false;
 	for(bool &b : r->upload_pending)
@@ -418,18 +428,28 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 		r->upload_pending[sb] = false;
 	}
 
-	// per-frame uploads (uploadInstances / setupInputData): one pinned staging block
+	// per-frame uploads (uploadInstances / setupInputData): one pinned staging block, copied to the
+	// ring's device block on the upload stream right away -- in asynchronous use the host runs ahead of
+	// the GPU, so the data is resident long before the frame's first kernel
 	unsigned char *h = r->h_instances + (size_t)sb * STAGING_BYTES;
 	size_t n = (size_t)num_instances;
 	memcpy(h, instances, n * 16);
-	memcpy(h + (size_t)LUCID_MAX_INSTANCES * 16, instance_colors, n * 4);
-	float *h_uv = reinterpret_cast<float *>(h + (size_t)LUCID_MAX_INSTANCES * 20);
+	float *h_uv = reinterpret_cast<float *>(h + n * 16);
 	if(instance_uv_rects) {
 		memcpy(h_uv, instance_uv_rects, n * 16);
 	} else {
 		for(size_t i = 0; i < n; i++)
 			h_uv[i * 4] = 0.0f, h_uv[i * 4 + 1] = 0.0f, h_uv[i * 4 + 2] = 1.0f, h_uv[i * 4 + 3] = 1.0f;
 	}
+	memcpy(h + n * 32, instance_colors, n * 4);
+	unsigned char *d = r->d_inst_ring[sb];
+	p.instances = reinterpret_cast<const LucidInstanceData *>(d);
+	p.inst_uv_rects = reinterpret_cast<const float4 *>(d + n * 16);
+	p.inst_colors = reinterpret_cast<const u32 *>(d + n * 32);
+	if(n > 0)
+		CU(cudaMemcpyAsync(d, h, n * 36, cudaMemcpyHostToDevice, r->upload_stream));
+	CU(cudaEventRecord(r->upload_ready[sb], r->upload_stream));
+	CU(cudaStreamWaitEvent(st, r->upload_ready[sb], 0));
 	LucidConfig cfg = *config;
 	cfg.num_instances = num_instances; // taken from this call, not the previous frame
 	p.num_instances = num_instances;
@@ -459,9 +479,8 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	const bool stage_events = !(flags & LUCID_RENDER_NO_STAGE_TIMES);
 	r->ev_staged[ring] = stage_events;
 	CU(cudaEventRecord(ev[0], st));
-	// per-frame uploads and clears (uploadInstances / setupInputData): one kernel reading the
-	// pinned staging block; LucidInfo and the first 6 per-bin arrays are cleared (lucid_renderer.cpp:437)
-	launchFrameBegin(p, h, h + (size_t)LUCID_MAX_INSTANCES * 16, h_uv, st);
+	// per-frame clears (setupInputData): LucidInfo and the first 6 per-bin arrays (lucid_renderer.cpp:437)
+	launchFrameBegin(p, st);
 	launchQuadSetup(p, cfg, st);
 	if(stage_events)
 		CU(cudaEventRecord(ev[1], st));

@@ -255,8 +255,7 @@ inline void launchPDL(void (*kernel)(KArgs...), int grid, int block, size_t smem
 }
 
 // kernel launchers (each in its own translation unit)
-void launchFrameBegin(const Params &p, const void *staged_instances, const void *staged_colors,
-					  const void *staged_uv_rects, cudaStream_t stream);
+void launchFrameBegin(const Params &p, cudaStream_t stream);
 void launchInfoOut(const Params &p, u32 *host_info, int num_words, cudaStream_t stream);
 void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream);
 void launchPadPositions(const float *positions, float4 *positions4, int num_verts, cudaStream_t stream);

@@ -1030,9 +1030,11 @@ __device__ __forceinline__ void binPhaseA(const Params &p, const BinInfo &b, uin
 				ring[pos * 2] = make_uint4(__float_as_uint(scan0), __float_as_uint(scan1), __float_as_uint(scan2),
 										   tri_idx | ((u32)(min_g + k) << 24) | (xneg << 27));
 				ring[pos * 2 + 1] = make_uint4(__float_as_uint(step0), __float_as_uint(step1), __float_as_uint(step2), 0u);
+				if(k + 1 < n_g) { // the state at the triangle's next group: one addition per pixel row
 #pragma unroll
-				for(int r = 0; r < rows_per_group; r++)
-					scan0 += step0, scan1 += step1, scan2 += step2;
+					for(int r = 0; r < rows_per_group; r++)
+						scan0 += step0, scan1 += step1, scan2 += step2;
+				}
 			}
 			q_tail += __popc(m);
 			__syncwarp();

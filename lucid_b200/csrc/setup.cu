@@ -482,20 +482,13 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_TRI_MIN_CTAS) k_tri_setup
 	}
 }
 
-// Start of a frame (uploadInstances + the clears of setupInputData, lucid_renderer.cpp:352-451):
-// pulls the instance arrays out of the pinned staging block over PCIe and zeroes LucidInfo, the
-// first six per-bin counter arrays and the setup look-back state.  A kernel instead of
-// cudaMemcpyAsync / cudaMemsetAsync keeps the copy engines free for the image read-back of the
-// previous frame, which runs concurrently on another stream.
-__global__ void __launch_bounds__(256) k_frame_begin(const Params p, const uint4 *staged_instances,
-													  const u32 *staged_colors, const uint4 *staged_uv_rects) {
+// Start of a frame (the clears of setupInputData, lucid_renderer.cpp:437): zeroes LucidInfo, the
+// first six per-bin counter arrays, the setup look-back state and the row costs.  A kernel instead
+// of cudaMemsetAsync keeps the copy engines free for the image read-back of the previous frame and
+// the instance upload of the next one, which run concurrently on their own streams.
+__global__ void __launch_bounds__(256) k_frame_begin(const Params p) {
 	const int stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
 	pdlEntry();
-	for(int i = first; i < p.num_instances; i += stride) {
-		reinterpret_cast<uint4 *>(const_cast<LucidInstanceData *>(p.instances))[i] = staged_instances[i];
-		const_cast<u32 *>(p.inst_colors)[i] = staged_colors[i];
-		reinterpret_cast<uint4 *>(const_cast<float4 *>(p.inst_uv_rects))[i] = staged_uv_rects[i];
-	}
 	u32 *info = reinterpret_cast<u32 *>(p.info);
 	const int n_clear = (int)LUCID_INFO_U32_SIZE + p.bin_count * 6; // lucid_renderer.cpp:437
 	for(int i = first; i < n_clear; i += stride)
@@ -517,11 +510,7 @@ __global__ void __launch_bounds__(256) k_info_out(const Params p, u32 *host_info
 		host_info[i] = info[i];
 }
 
-void launchFrameBegin(const Params &p, const void *staged_instances, const void *staged_colors,
-					  const void *staged_uv_rects, cudaStream_t stream) {
-	launchPDL(k_frame_begin, 64, 256, 0, stream, p, (const uint4 *)staged_instances, (const u32 *)staged_colors,
-			  (const uint4 *)staged_uv_rects);
-}
+void launchFrameBegin(const Params &p, cudaStream_t stream) { launchPDL(k_frame_begin, 64, 256, 0, stream, p); }
 void launchInfoOut(const Params &p, u32 *host_info, int num_words, cudaStream_t stream) {
 	launchPDL(k_info_out, 32, 256, 0, stream, p, host_info, num_words);
 }

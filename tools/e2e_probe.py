@@ -32,10 +32,10 @@ def run(name, fn):
     print(f"{name:40s} submit {1e3 * (t1 - t0) / N:.3f} ms/frame  total {1e3 * (t2 - t0) / N:.3f} ms/frame")
 
 
-run("device only, async, skip info", lambda k: r.render(cfg, inst, cols, rects, flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO))
-run("device only, async, with info", lambda k: r.render(cfg, inst, cols, rects, flags=api.RENDER_ASYNC))
-run("host pinned, async", lambda k: r.render(cfg, inst, cols, rects, out=pinned[k & 1].data_ptr(), flags=api.RENDER_ASYNC))
-run("host pinned, async, skip info", lambda k: r.render(cfg, inst, cols, rects, out=pinned[k & 1].data_ptr(), flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO))
+run("device only, async, skip info", lambda k: r.render(cfg, inst, cols, rects, flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES))
+run("device only, async, with info", lambda k: r.render(cfg, inst, cols, rects, flags=api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES))
+run("host pinned, async", lambda k: r.render(cfg, inst, cols, rects, out=pinned[k & 1].data_ptr(), flags=api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES))
+run("host pinned, async, skip info", lambda k: r.render(cfg, inst, cols, rects, out=pinned[k & 1].data_ptr(), flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES))
 run("host pinned, sync", lambda k: r.render(cfg, inst, cols, rects, out=pinned[k & 1].data_ptr()))
 cam = api.make_camera(sc["camera"], w, h)
 t0 = time.perf_counter()
