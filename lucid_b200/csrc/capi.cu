@@ -249,7 +249,7 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.block_lists, (size_t)p.bin_count * (BIN_LIST_BYTES / sizeof(uint4))));
 	CUC(devAlloc(r, &p.block_counts, (size_t)p.bin_count * 32));
 	p.block_items_cap = (u32)p.bin_count * 32u;
-	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap));
+	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 5)); // one region per size class (raster.cu ITEM_CLASSES)
 	CUC(devAlloc(r, &p.large_keys, rasterLargeKeysCount(r->num_sms)));
 	CUC(devAlloc(r, &p.block_aux, rasterLargeKeysCount(r->num_sms)));
 	CUC(devAlloc(r, &r->images[0], (size_t)p.width * p.height));

@@ -82,11 +82,11 @@ struct Params {
 	int image_pitch;
 	u32 *frag_counts;	  // optional per-pixel fragment counts (debug / parity), may be null
 	u32 *bin_flags;		  // per bin: bit 0 promoted LOW->HIGH, bit 1 over the reference's HIGH limits (red)
-	u32 *work_counters;	  // [0] bins taken [1] block items taken [3] heavy items [4] light items
+	u32 *work_counters;	  // [0] bins taken [1] block items taken [3..7] block items per size class
 	u64 *row_cost;		  // per bin row: warp cycles the raster kernels spent on it this frame (split balancing)
 	uint4 *block_lists;	  // per bin BIN_LIST_BYTES: 32 half-block lists (HIGH) or 16 block lists (LOW)
 	int *block_counts;	  // 32 per bin: entries of each list
-	uint2 *block_items;	  // work items of k_raster_blocks (item, entries): heavy from the front, light from the back
+	uint2 *block_items;	  // work items of k_raster_blocks (item, entries): one region of block_items_cap per size class
 	u32 block_items_cap;
 	u32 *large_keys;	  // per k_raster_blocks warp: sort keys of lists too long for shared memory
 	uint4 *block_aux;	  // per k_raster_blocks warp: (depth plane, constant colour) per list entry

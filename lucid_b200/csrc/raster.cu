@@ -1055,7 +1055,11 @@ __device__ __forceinline__ void binPhaseA(const Params &p, const BinInfo &b, uin
 // computeRBlockGroups of the reference, raster_low.glsl:39-106, raster_high.glsl:54-144)
 
 constexpr int HB_LIST_CAP = MAX_HBLOCK_TRIS; // records per half-block list (HIGH)
-constexpr int HEAVY_BLOCK = 192;			 // blocks with more entries are shaded first
+// work items of stage 2 are queued by size class (entries of the list), heaviest class first
+constexpr int ITEM_CLASSES = 5;
+__device__ __forceinline__ int itemClass(int entries) {
+	return entries > 384 ? 0 : entries > 160 ? 1 : entries > 64 ? 2 : entries > 24 ? 3 : 4;
+}
 
 __device__ __forceinline__ unsigned char *binLists(const Params &p, int bin_id) {
 	return reinterpret_cast<unsigned char *>(p.block_lists) + (size_t)bin_id * BIN_LIST_BYTES;
@@ -1167,22 +1171,22 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 			const int c = tid < n_blocks ? sh.count[tid] : 0;
 			if(tid < n_blocks)
 				p.block_counts[bin_id * 32 + tid] = c;
-			// one queue, consumed from index 0: heavy items fill it from the front, light items from
-			// the back (so heavy blocks start first and the tail of the kernel is made of light ones)
+			// one queue per size class, consumed from the heaviest class down: the kernel ends with the
+			// shortest items, so its tail is a few microseconds instead of one long list
 			const u32 item = ((u32)bin_id << 6) | (high ? 32u : 0u) | (u32)tid;
-			const u32 heavy = __ballot_sync(0xffffffffu, c > HEAVY_BLOCK), light = __ballot_sync(0xffffffffu, c > 0) & ~heavy;
-			u32 base_h = 0, base_l = 0;
-			if(tid == 0) {
-				if(heavy)
-					base_h = atomicAdd(&p.work_counters[3], (u32)__popc(heavy));
-				if(light)
-					base_l = atomicAdd(&p.work_counters[4], (u32)__popc(light));
+			const int cls = itemClass(c);
+#pragma unroll
+			for(int k = 0; k < ITEM_CLASSES; k++) {
+				const u32 m = __ballot_sync(0xffffffffu, c > 0 && cls == k);
+				if(m == 0)
+					continue;
+				u32 base = 0;
+				if(tid == __ffs(m) - 1)
+					base = atomicAdd(&p.work_counters[3 + k], (u32)__popc(m));
+				base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+				if((m >> tid) & 1)
+					p.block_items[(size_t)k * p.block_items_cap + base + __popc(m & laneMaskLt())] = make_uint2(item, (u32)c);
 			}
-			base_h = __shfl_sync(0xffffffffu, base_h, 0), base_l = __shfl_sync(0xffffffffu, base_l, 0);
-			if((heavy >> tid) & 1)
-				p.block_items[base_h + __popc(heavy & laneMaskLt())] = make_uint2(item, (u32)c);
-			if((light >> tid) & 1)
-				p.block_items[p.block_items_cap - 1 - (base_l + __popc(light & laneMaskLt()))] = make_uint2(item, (u32)c);
 		}
 		if(tid == 0)
 			atomicAdd(reinterpret_cast<unsigned long long *>(p.row_cost) + b.pos_y / BIN_SIZE,
@@ -1346,7 +1350,14 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 	const WarpScratch ws = warpScratch(smem + (size_t)warp * WARP_SCRATCH_BYTES);
 	u32 *large_keys = p.large_keys + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
 	uint4 *aux = p.block_aux + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
-	const u32 n_heavy = p.work_counters[3], n_items = n_heavy + p.work_counters[4];
+	u32 class_end[ITEM_CLASSES]; // exclusive end of every class in ticket order
+	{
+		u32 acc = 0;
+#pragma unroll
+		for(int k = 0; k < ITEM_CLASSES; k++)
+			class_end[k] = acc += p.work_counters[3 + k];
+	}
+	const u32 n_items = class_end[ITEM_CLASSES - 1];
 	u32 frag_acc = 0, hbt_acc = 0;
 	// Work fetch: the queue index of the next item is requested when the current item's keys are
 	// built and its entry when they are sorted, so both round trips overlap the sort and the
@@ -1355,8 +1366,15 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 	auto fetchIndex = [&]() { return lane == 0 ? atomicAdd(&p.work_counters[1], 1u) : 0u; };
 	auto fetchEntry = [&](u32 i) {
 		uint2 e = make_uint2(0, 0);
-		if(lane == 0 && i < n_items)
-			e = __ldcg(p.block_items + (i < n_heavy ? i : p.block_items_cap - 1 - (i - n_heavy)));
+		if(lane == 0 && i < n_items) {
+			int k = 0;
+			u32 first = 0;
+#pragma unroll
+			for(int c = 0; c < ITEM_CLASSES - 1; c++)
+				if(i >= class_end[c])
+					k = c + 1, first = class_end[c];
+			e = __ldcg(p.block_items + (size_t)k * p.block_items_cap + (i - first));
+		}
 		return e;
 	};
 #ifdef RB_PHASE_CLOCKS
