@@ -1058,7 +1058,19 @@ constexpr int HB_LIST_CAP = MAX_HBLOCK_TRIS; // records per half-block list (HIG
 // work items of stage 2 are queued by size class (entries of the list), heaviest class first
 constexpr int ITEM_CLASSES = 5;
 __device__ __forceinline__ int itemClass(int entries) {
-	return entries > 384 ? 0 : entries > 160 ? 1 : entries > 64 ? 2 : entries > 24 ? 3 : 4;
+#ifndef RB_CL0
+#define RB_CL0 384
+#define RB_CL1 160
+#define RB_CL2 64
+#define RB_CL3 24
+#endif
+	const int limits[ITEM_CLASSES - 1] = {RB_CL0, RB_CL1, RB_CL2, RB_CL3};
+	int k = ITEM_CLASSES - 1;
+#pragma unroll
+	for(int c = ITEM_CLASSES - 2; c >= 0; c--)
+		if(entries > limits[c])
+			k = c;
+	return k;
 }
 
 __device__ __forceinline__ unsigned char *binLists(const Params &p, int bin_id) {
