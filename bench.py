@@ -307,11 +307,14 @@ def run_ours(args):
             max(("setup", stage[0]), ("bin_count", stage[1]), ("bin_dispatch", stage[3]), key=lambda t: t[1])[0]
         dom_ms = {"raster": raster_ms, "setup": stage[0], "bin_count": stage[1], "bin_dispatch": stage[3]}[dominant]
         achieved = ab[dominant] / (dom_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, issue_pct, traffic_src = None, None, None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(f"config{args.config}", {}).get(dominant)
+                captured = json.load(f).get(f"config{args.config}", {})
+            traffic = captured.get(dominant)
+            issue_pct = captured.get("issue_active_pct", {}).get(dominant)
+            traffic_src = captured.get("source")
         line = {
             "metric": "exact_oit_frames_per_sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
@@ -334,6 +337,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes": int(ab[dominant]),
+                         # from the committed ncu --set full capture of one frame of this workload (profiles/):
+                         # DRAM bytes of the stage's kernels, and their SM issue-slot utilisation -- the raster
+                         # kernels are bound by instruction issue, not by HBM
+                         "traffic_source": traffic_src, "sm_issue_active_pct": issue_pct,
                          "per_stage_frac": {k: (round(v, 4) if v is not None else None) for k, v in fracs.items()}},
             "e2e": {"value": round(e2e_value, 3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(len(inst) * 36 + 352),

@@ -17,7 +17,8 @@ for spec in sys.argv[1:]:
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    stages, kernels = {}, {}
+    stages, kernels, issue = {}, {}, {}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
     for r in rows[2:]:
         kname = r[idx["Kernel Name"]].split("(")[0].split("::")[-1]
         total = 0.0
@@ -26,6 +27,13 @@ for spec in sys.argv[1:]:
         kernels[kname] = kernels.get(kname, 0) + int(total)
         if kname in STAGE:
             stages[STAGE[kname]] = stages.get(STAGE[kname], 0) + int(total)
+            # SM issue-slot utilisation of the stage: time-weighted over its kernels
+            t = float(r[idx["gpu__time_duration.sum"]].replace(",", "")) * tscale[units[idx["gpu__time_duration.sum"]]]
+            ia = float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]].replace(",", ""))
+            acc = issue.setdefault(STAGE[kname], [0.0, 0.0])
+            acc[0] += t * ia
+            acc[1] += t
+    stages["issue_active_pct"] = {k: round(v[0] / v[1], 1) for k, v in issue.items() if v[1] > 0}
     stages["per_kernel"] = kernels
     stages["source"] = path.split("/")[-1] + " (ncu --set full, one frame, cold-cache serialised replays)"
     out[name] = stages
