@@ -167,17 +167,26 @@ def run_ours(args):
     inst, cols, rects = api.build_instances(scene["draw_calls"], scene["materials"])
     rows = None
     if split:
-        # row boundaries from the measured per-row raster cost of a full calibration frame (what an
-        # application takes from the previous frame); rank 0's measurement is used by every rank
+        # ownership from the measured raster cost of a full calibration frame (what an application takes
+        # from the previous frame); rank 0's measurement is used by every rank.  Default: contiguous
+        # row-major bin ranges of equal cost (a heavy bin row may be shared by two ranks); --split-rows
+        # keeps whole bin rows, --equal-rows equal row counts.
         from lucid_b200 import multigpu
         cam0 = api.make_camera(view_camera(scene, 0), width, height)
         for _ in range(2):
             r.render(api.make_config(cam0, len(inst), scene["background"]), inst, cols, rects)
-        cost = torch.from_numpy(r.read_row_costs().astype(np.float64)).cuda()
+        cost = torch.from_numpy(r.read_bin_costs().astype(np.float64)).cuda()
         dist.broadcast(cost, src=0)
-        weights = None if args.equal_rows else cost.cpu().numpy()
-        rows = multigpu.split_bin_rows(nby, world, weights)[rank]
-        r.set_bin_rows(*rows)
+        cost = cost.cpu().numpy()
+        if args.equal_rows or args.split_rows:
+            weights = None if args.equal_rows else cost.reshape(nby, -1).sum(axis=1)
+            rows = multigpu.split_bin_rows(nby, world, weights)[rank]
+            r.set_bin_rows(*rows)
+            split_kind = "equal rows" if args.equal_rows else "whole rows balanced on measured cost"
+        else:
+            rows = multigpu.split_bins(r.bin_count, world, cost)[rank]
+            r.set_bin_range(*rows)
+            split_kind = "row-major bin ranges balanced on measured cost"
 
     def config_for(step):
         view = 0 if split else (step * world + rank) % 64
@@ -322,9 +331,8 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.config], "resolution": [width, height],
                        "input_triangles": tris_per_frame, "scale": args.scale,
-                       "parallelism": ("bin-row split x%d (%s), P2P composite; rank 0 rows %s" %
-                                       (world, "equal rows" if args.equal_rows else "balanced on measured row cost",
-                                        list(rows))) if split else
+                       "parallelism": ("bin-row split x%d (%s), P2P composite; rank 0 owns %s" %
+                                       (world, split_kind, list(rows))) if split else
                        ("views sharded x%d" % world if world > 1 else "single GPU"),
                        "l2": "256 MiB device memset between timed frames (untimed)"},
             "mtris_per_sec": round(value * tris_per_frame / 1e6, 2),
@@ -431,6 +439,7 @@ def main():
     ap.add_argument("--mvq", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--equal-rows", action="store_true", help="--mode split: equal row counts instead of cost-balanced")
+    ap.add_argument("--split-rows", action="store_true", help="--mode split: whole bin rows, balanced on measured cost")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

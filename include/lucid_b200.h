@@ -74,6 +74,11 @@ int lucid_set_bin_rows(lucid_renderer *r, int32_t begin, int32_t end);
  * the caller picks the next frame's row boundaries ("choose boundaries from the previous
  * frame's per-row fragment counts"; measured cycles also cover list building and sorting) */
 int lucid_read_row_costs(lucid_renderer *r, uint64_t *dst, int32_t num_rows);
+/* finer than rows: own the bins [begin, end) in row-major order (a bin row may be shared between two
+ * devices when single rows are too heavy to balance), and the per-bin costs to choose the ranges from.
+ * Counts and lists of owned bins are identical to the full frame's; other bins stay empty. */
+int lucid_set_bin_range(lucid_renderer *r, int32_t begin, int32_t end);
+int lucid_read_bin_costs(lucid_renderer *r, uint64_t *dst, int32_t num_bins);
 
 /* LucidRenderer::render(const Context&), src/lucid_renderer.cpp:319-350: config as filled by
  * setupInputData, instances / colours / uv rects as filled by uploadInstances (host pointers).

@@ -80,7 +80,7 @@ _lib = None
 C_ABI_SYMBOLS = [
     "lucid_create", "lucid_destroy", "lucid_last_error", "lucid_set_geometry", "lucid_set_texture",
     "lucid_set_bin_rows", "lucid_render", "lucid_wait", "lucid_read_info", "lucid_bin_count",
-    "lucid_stage_times", "lucid_stage_times_at", "lucid_read_row_costs", "lucid_read_quad_aabbs", "lucid_read_tri_records", "lucid_read_quad_attrs",
+    "lucid_stage_times", "lucid_stage_times_at", "lucid_read_row_costs", "lucid_set_bin_range", "lucid_read_bin_costs", "lucid_read_quad_aabbs", "lucid_read_tri_records", "lucid_read_quad_attrs",
     "lucid_read_bin_lists", "lucid_read_frag_counts", "lucid_read_image", "lucid_image_pointer",
     "lucid_ipc_export_image", "lucid_ipc_open_image", "lucid_ipc_close_image",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
@@ -118,6 +118,8 @@ def load_library(build_if_needed: bool = True):
     lib.lucid_read_info.argtypes = [vp, vp, C.c_size_t]
     lib.lucid_bin_count.argtypes = [vp]
     lib.lucid_read_row_costs.argtypes = [vp, vp, C.c_int32]
+    lib.lucid_read_bin_costs.argtypes = [vp, vp, C.c_int32]
+    lib.lucid_set_bin_range.argtypes = [vp, C.c_int32, C.c_int32]
     lib.lucid_stage_times.argtypes = [vp, C.POINTER(C.c_float * 8)]
     lib.lucid_stage_times_at.argtypes = [vp, C.c_int32, C.POINTER(C.c_float * 8)]
     lib.lucid_read_quad_aabbs.argtypes = [vp, C.c_int32, vp, C.c_int32]
@@ -326,6 +328,16 @@ class LucidRenderer:
         ms = (C.c_float * 8)()
         self._check(self._lib.lucid_stage_times_at(self._h, frames_back, C.byref(ms)), "lucid_stage_times")
         return np.array(ms[:], np.float32)
+
+    def set_bin_range(self, begin, end):
+        """Own the bins [begin, end) in row-major order (finer than whole rows)."""
+        self._check(self._lib.lucid_set_bin_range(self._h, begin, end), "lucid_set_bin_range")
+
+    def read_bin_costs(self) -> np.ndarray:
+        """Warp cycles the raster kernels spent per bin in the last frame."""
+        out = np.zeros(self.bin_count, np.uint64)
+        self._check(self._lib.lucid_read_bin_costs(self._h, _ptr(out), out.size), "lucid_read_bin_costs")
+        return out
 
     def read_row_costs(self) -> np.ndarray:
         """Warp cycles the raster kernels spent per bin row in the last frame (bin-row split balancing)."""

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
 #pragma unroll
 		for(int k = 0; k < 4; k++) {
 			int by = bsy + k / max(w, 1), bx = bsx + k % max(w, 1);
-			bool ok = k < n && by >= p.row_begin && by < p.row_end;
+			bool ok = k < n && ownsBin(p, by * bcx + bx);
 			if(ok)
 				atomicAdd(&s_hist[by * bcx + bx], 1); // shared-memory atomics resolve same-bin lanes in hardware
 		}
@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
 			int bmin, bmax;
 			binScanStep(s, bmin, bmax);
 			bmin = max(bmin, bsx), bmax = min(bmax, bex);
-			if(bmax >= bmin && by >= p.row_begin && by < p.row_end) {
+			clipToOwnedBins(p, by, bmin, bmax);
+			if(bmax >= bmin) {
 				atomicAdd(tri_diff + by * bcx + bmin, 1);
 				if(bmax + 1 < bcx)
 					atomicAdd(tri_diff + by * bcx + bmax + 1, -1);
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 #pragma unroll
 			for(int k = 0; k < 4; k++) {
 				int by = bsy + k / max(w, 1), bx = bsx + k % max(w, 1);
-				bool ok = k < n && by >= p.row_begin && by < p.row_end;
+				bool ok = k < n && ownsBin(p, by * bcx + bx);
 				if(ok) {
 					const int pos = atomicAdd(&s_hist[by * bcx + bx], 1);
 					if(pass == 1)
@@ -406,9 +407,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 			if(r < own_rows) {
 				binScanStep(s, bmin, bmax);
 				bmin = max(bmin, bsx), bmax = min(bmax, bex);
-				const int by = bsy + r;
-				if(by < p.row_begin || by >= p.row_end)
-					bmax = bmin - 1;
+				clipToOwnedBins(p, bsy + r, bmin, bmax);
 			}
 			pushSpan(tri_idx, (bsy + r) * bcx, bmin, bmax);
 		}
@@ -438,9 +437,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 				if(r < b_rows) {
 					binScanStep(mine, bmin, bmax);
 					bmin = max(bmin, b_bsx), bmax = min(bmax, b_bex);
-					const int by = b_bsy + r;
-					if(by < p.row_begin || by >= p.row_end)
-						bmax = bmin - 1;
+					clipToOwnedBins(p, b_bsy + r, bmin, bmax);
 				}
 				pushSpan(b_tri, (b_bsy + r) * bcx, bmin, bmax);
 				for(int k = 0; k < 32; k++)

@@ -245,7 +245,8 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.setup_ticket, 4));
 	CUC(devAlloc(r, &p.bin_flags, (size_t)p.bin_count));
 	CUC(devAlloc(r, &p.work_counters, 8));
-	CUC(devAlloc(r, &p.row_cost, (size_t)p.bin_count_y));
+	CUC(devAlloc(r, &p.bin_cost, (size_t)p.bin_count));
+	p.bin_begin = p.row_begin * p.bin_count_x, p.bin_end = p.row_end * p.bin_count_x;
 	CUC(devAlloc(r, &p.block_lists, (size_t)p.bin_count * (BIN_LIST_BYTES / sizeof(uint4))));
 	CUC(devAlloc(r, &p.block_counts, (size_t)p.bin_count * 32));
 	p.block_items_cap = (u32)p.bin_count * 32u;
@@ -290,17 +291,44 @@ int lucid_set_bin_rows(lucid_renderer *r, int32_t begin, int32_t end) {
 	if(begin < 0 || end > r->p.bin_count_y || begin >= end)
 		return fail(r, LUCID_E_INVALID, "lucid_set_bin_rows: bad range");
 	r->p.row_begin = begin, r->p.row_end = end;
+	r->p.bin_begin = begin * r->p.bin_count_x, r->p.bin_end = end * r->p.bin_count_x;
+	return LUCID_OK;
+}
+
+int lucid_set_bin_range(lucid_renderer *r, int32_t begin, int32_t end) {
+	if(!r)
+		return LUCID_E_INVALID;
+	if(begin < 0 || end > r->p.bin_count || begin >= end)
+		return fail(r, LUCID_E_INVALID, "lucid_set_bin_range: bad range");
+	r->p.bin_begin = begin, r->p.bin_end = end;
+	r->p.row_begin = begin / r->p.bin_count_x, r->p.row_end = (end - 1) / r->p.bin_count_x + 1;
+	return LUCID_OK;
+}
+
+int lucid_read_bin_costs(lucid_renderer *r, uint64_t *dst, int32_t num_bins) {
+	if(!r || !dst || num_bins < 0)
+		return LUCID_E_INVALID;
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	const size_t n = (size_t)std::min(num_bins, r->p.bin_count);
+	CU(cudaMemcpy(dst, r->p.bin_cost, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
 	return LUCID_OK;
 }
 
 int lucid_read_row_costs(lucid_renderer *r, uint64_t *dst, int32_t num_rows) {
 	if(!r || !dst || num_rows < 0)
 		return LUCID_E_INVALID;
-	int rc = lucid_wait(r);
+	std::vector<uint64_t> bins((size_t)r->p.bin_count);
+	int rc = lucid_read_bin_costs(r, bins.data(), r->p.bin_count);
 	if(rc)
 		return rc;
-	const size_t n = (size_t)std::min(num_rows, r->p.bin_count_y);
-	CU(cudaMemcpy(dst, r->p.row_cost, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+	for(int by = 0; by < std::min(num_rows, r->p.bin_count_y); by++) {
+		uint64_t sum = 0;
+		for(int bx = 0; bx < r->p.bin_count_x; bx++)
+			sum += bins[(size_t)by * r->p.bin_count_x + bx];
+		dst[by] = sum;
+	}
 	return LUCID_OK;
 }
 

@@ -41,7 +41,10 @@ struct Params {
 	int width, height;
 	int bin_count_x, bin_count_y, bin_count;
 	int max_visible_quads;
-	int row_begin, row_end; // bin rows owned by this device (multi-GPU bin-row split)
+	// multi-GPU split: this device owns the bins [bin_begin, bin_end) in row-major order (whole bin rows
+	// in the plain bin-row split; a row may be shared when rows are too coarse to balance);
+	// [row_begin, row_end) are the bin rows that range touches
+	int row_begin, row_end, bin_begin, bin_end;
 	u32 opts;
 	int max_dispatches;
 	int num_instances;
@@ -83,7 +86,7 @@ struct Params {
 	u32 *frag_counts;	  // optional per-pixel fragment counts (debug / parity), may be null
 	u32 *bin_flags;		  // per bin: bit 0 promoted LOW->HIGH, bit 1 over the reference's HIGH limits (red)
 	u32 *work_counters;	  // [0] bins taken [1] block items taken [3..7] block items per size class
-	u64 *row_cost;		  // per bin row: warp cycles the raster kernels spent on it this frame (split balancing)
+	u64 *bin_cost;		  // per bin: warp cycles the raster kernels spent on it this frame (split balancing)
 	uint4 *block_lists;	  // per bin BIN_LIST_BYTES: 32 half-block lists (HIGH) or 16 block lists (LOW)
 	int *block_counts;	  // 32 per bin: entries of each list
 	uint2 *block_items;	  // work items of k_raster_blocks (item, entries): one region of block_items_cap per size class
@@ -241,6 +244,12 @@ __device__ __forceinline__ void pdlEntry() {
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// bins of row `by` owned by this device, as an inclusive column range clipped to [bmin, bmax]
+__device__ __forceinline__ void clipToOwnedBins(const Params &p, int by, int &bmin, int &bmax) {
+	bmin = max(bmin, p.bin_begin - by * p.bin_count_x);
+	bmax = min(bmax, p.bin_end - 1 - by * p.bin_count_x);
+}
+__device__ __forceinline__ bool ownsBin(const Params &p, int bin) { return bin >= p.bin_begin && bin < p.bin_end; }
 bool pdlEnabled(); // capi.cu: off with LUCID_NO_PDL=1 (A/B timing)
 template <typename... KArgs, typename... Args>
 inline void launchPDL(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args &&...args) {

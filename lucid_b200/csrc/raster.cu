@@ -1201,7 +1201,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 			}
 		}
 		if(tid == 0)
-			atomicAdd(reinterpret_cast<unsigned long long *>(p.row_cost) + b.pos_y / BIN_SIZE,
+			atomicAdd(reinterpret_cast<unsigned long long *>(p.bin_cost) + bin_id,
 					  (unsigned long long)(clock64() - t_bin) * RASTER_WARPS);
 		const int rows = high ? 4 : 8;
 		for(int blk = warp; blk < n_blocks; blk += RASTER_WARPS) {
@@ -1254,8 +1254,7 @@ __device__ __forceinline__ void finishBins(const Params &p, u32 background, u32 
 		const int b = first + lane;
 		u32 kind = 0; // 1 background, 2 red
 		if(b < p.bin_count) {
-			const int by = b / p.bin_count_x;
-			if(by >= p.row_begin && by < p.row_end) {
+			if(ownsBin(p, b)) {
 				const bool empty = cntc(p, LUCID_CNT_TRI_COUNTS)[b] + cntc(p, LUCID_CNT_QUAD_COUNTS)[b] * 2 == 0;
 				kind = (p.bin_flags[b] & 2u) ? 2u : empty ? 1u : 0u;
 			}
@@ -1519,7 +1518,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, RB_MIN_CTAS)
 		}
 		PHASE_MARK(3) // shading
 		if(lane == 0)
-			atomicAdd(reinterpret_cast<unsigned long long *>(p.row_cost) + bin_y, (unsigned long long)(clock64() - t_item));
+			atomicAdd(reinterpret_cast<unsigned long long *>(p.bin_cost) + bin_id, (unsigned long long)(clock64() - t_item));
 		if(!light_item) // a long item takes its successor only when it is done (dynamic balance)
 			next_entry = fetchEntry(fetchIndex());
 	}

@@ -495,8 +495,8 @@ __global__ void __launch_bounds__(256) k_frame_begin(const Params p) {
 		info[i] = 0;
 	for(int i = first; i < p.num_setup_ctas; i += stride)
 		p.setup_lookback[i] = 0;
-	for(int i = first; i < p.bin_count_y; i += stride)
-		p.row_cost[i] = 0;
+	for(int i = first; i < p.bin_count; i += stride)
+		p.bin_cost[i] = 0;
 	if(first == 0)
 		*p.setup_ticket = 0;
 }

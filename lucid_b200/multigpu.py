@@ -37,6 +37,22 @@ def split_bin_rows(bin_count_y: int, world_size: int, weights=None) -> list[tupl
     return [(bounds[i], bounds[i + 1]) for i in range(world_size)]
 
 
+def split_bins(bin_count: int, world_size: int, weights) -> list[tuple[int, int]]:
+    """Contiguous row-major bin ranges [begin, end) per rank with equal summed weight (per-bin raster
+    cost of the previous frame).  Finer than split_bin_rows: one heavy bin row can be shared."""
+    w = np.asarray(weights, np.float64)
+    if w.shape != (bin_count,):
+        raise ValueError("weights must have one entry per bin")
+    c = np.concatenate([[0.0], np.cumsum(w + 1e-9)])
+    targets = c[-1] * np.arange(1, world_size) / world_size
+    bounds = [0] + [int(b) for b in np.searchsorted(c, targets, side="left")] + [bin_count]
+    for i in range(1, world_size):
+        lo = bounds[i - 1] + (1 if bin_count >= world_size else 0)
+        hi = bin_count - ((world_size - i) if bin_count >= world_size else 0)
+        bounds[i] = min(max(bounds[i], lo), hi)
+    return [(bounds[i], bounds[i + 1]) for i in range(world_size)]
+
+
 def strip_pixel_rows(rows: tuple[int, int], height: int) -> tuple[int, int]:
     return min(rows[0] * BIN_SIZE, height), min(rows[1] * BIN_SIZE, height)
 

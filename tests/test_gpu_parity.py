@@ -332,3 +332,40 @@ def test_orbit_views_against_oracle(view):
         assert _clean(pu.compare(r, img, o)) == {}
     finally:
         r.close()
+
+
+def test_bin_range_split_matches_full_frame(small):
+    """Ownership finer than rows (lucid_set_bin_range): row-major bin ranges that cut through bin rows
+    compose to the single-GPU frame, and the counts of owned bins equal the full frame's."""
+    sc = small["arch"]
+    full_r, full_img = pu.run_cuda(sc)
+    _, full_counts = api.split_info(full_r.read_info(), full_r.bin_count)
+    full_frags = full_r.getStats()["fragments"]
+    cost = full_r.read_bin_costs().astype(np.float64)
+    bc = full_r.bin_count
+    full_r.close()
+    assert (cost > 0).sum() > 0
+    cfg, inst, cols, rects = api.prepare_frame(sc)
+    target = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20)
+    ptr, pitch = target.image_pointer()
+    frags = 0
+    try:
+        ranges = multigpu.split_bins(bc, 5, cost)
+        assert ranges[0][0] == 0 and ranges[-1][1] == bc and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        bcx = (sc["width"] + 31) // 32
+        assert any(a % bcx != 0 for a, _ in ranges[1:])  # at least one boundary inside a bin row
+        for lo, hi in ranges:
+            part = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20)
+            part.set_scene(sc)
+            part.set_bin_range(lo, hi)
+            part.render(cfg, inst, cols, rects, out_device_ptr=ptr, out_pitch=pitch)
+            frags += part.getStats()["fragments"]
+            _, pc = api.split_info(part.read_info(), bc)
+            for which in (0, 3):
+                assert np.array_equal(pc[which][lo:hi], full_counts[which][lo:hi])
+                assert pc[which][:lo].sum() == 0 and pc[which][hi:].sum() == 0
+            part.close()
+        assert np.array_equal(target.read_image(), full_img)
+        assert frags == full_frags
+    finally:
+        target.close()

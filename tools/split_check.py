@@ -21,9 +21,13 @@ for ci in [int(a) for a in sys.argv[1:]] or [0, 2]:
     sc = scenes.get_config(ci, 1.0)
     w, h = sc["width"], sc["height"]
     cfg, inst, cols, rects = api.prepare_frame(sc)
-    rows = multigpu.split_bin_rows((h + 31) // 32, world)[rank]
-    part = api.LucidRenderer(w, h, 0, 0, device=local, bin_rows=rows)
+    part = api.LucidRenderer(w, h, 0, 0, device=local)
     part.set_scene(sc)
+    # cost-balanced row-major bin ranges (rank 0's calibration frame), as bench.py --mode split uses
+    part.render(cfg, inst, cols, rects)
+    cost = torch.from_numpy(part.read_bin_costs().astype(np.float64)).cuda()
+    dist.broadcast(cost, src=0)
+    part.set_bin_range(*multigpu.split_bins(part.bin_count, world, cost.cpu().numpy())[rank])
     handle = [part.ipc_export_image() if rank == 0 else None]
     dist.broadcast_object_list(handle, src=0)
     peer = part.ipc_open_image(handle[0]) if rank != 0 else None
