@@ -184,9 +184,26 @@ def run_ours(args):
             r.set_bin_rows(*rows)
             split_kind = "equal rows" if args.equal_rows else "whole rows balanced on measured cost"
         else:
-            rows = multigpu.split_bins(r.bin_count, world, cost)[rank]
-            r.set_bin_range(*rows)
-            split_kind = "row-major bin ranges balanced on measured cost"
+            ranges = multigpu.split_bins(r.bin_count, world, cost)
+            r.set_bin_range(*ranges[rank])
+            # feedback, as an application would apply it from frame to frame: the cost of a rank's bins is
+            # rescaled by the time that rank actually needed for them (everything but the replicated
+            # setup), and the ranges are cut again
+            for _ in range(args.balance_iters):
+                for k in range(3):
+                    r.render(api.make_config(cam0, len(inst), scene["background"]), inst, cols, rects,
+                             flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
+                mine = float(np.median([r.stage_times(i)[1:7].sum() for i in range(2)]))
+                times = torch.zeros(world, device="cuda", dtype=torch.float64)
+                times[rank] = mine
+                dist.all_reduce(times)
+                times = times.cpu().numpy()
+                for q, (lo, hi) in enumerate(ranges):
+                    cost[lo:hi] *= times[q] / max(float(cost[lo:hi].sum()), 1e-9)
+                ranges = multigpu.split_bins(r.bin_count, world, cost)
+                r.set_bin_range(*ranges[rank])
+            rows = ranges[rank]
+            split_kind = "row-major bin ranges balanced on measured cost, %d feedback steps" % args.balance_iters
 
     def config_for(step):
         view = 0 if split else (step * world + rank) % 64
@@ -202,10 +219,13 @@ def run_ours(args):
             peer_ptr = r.ipc_open_image(handle[0])
 
     def render(step, **kw):
-        if peer_ptr is not None:
+        if peer_ptr is not None and args.composite == "stores":
+            # the raster kernels store their pixels straight into rank 0's image
             r.render(config_for(step), inst, cols, rects, out_device_ptr=peer_ptr, out_pitch=width * 4, **kw)
         else:
             r.render(config_for(step), inst, cols, rects, **kw)
+            if peer_ptr is not None:  # own image first, then the owned bins as whole 128-byte rows
+                r.composite_to(peer_ptr, width * 4)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     frame_token = torch.zeros(1, device="cuda")
@@ -238,6 +258,12 @@ def run_ours(args):
     wall = time.time() - t_wall
     kept = min(args.steps, 64)
     frame_ms = float(np.mean([r.stage_times(i)[7] for i in range(kept)]))  # library's own first->last event
+    rank_frame_ms = None
+    if dist is not None:  # every rank's own frame time (the split's balance; a step ends with the slowest)
+        t = torch.zeros(world, device="cuda", dtype=torch.float64)
+        t[rank] = frame_ms
+        dist.all_reduce(t)
+        rank_frame_ms = [round(float(x), 4) for x in t.cpu().numpy()]
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)], np.float64)
     total_ms = torch.tensor([float(step_ms.sum())], device="cuda", dtype=torch.float64)
     if dist is not None:
@@ -332,11 +358,13 @@ def run_ours(args):
             "config": {"workload": WORKLOADS[args.config], "resolution": [width, height],
                        "input_triangles": tris_per_frame, "scale": args.scale,
                        "parallelism": ("bin-row split x%d (%s), P2P composite; rank 0 owns %s" %
-                                       (world, split_kind, list(rows))) if split else
+                                       (world, split_kind + "; composite by " +
+                                        ("a bin-row copy kernel" if args.composite == "copy" else "direct raster stores"),
+                                        list(rows))) if split else
                        ("views sharded x%d" % world if world > 1 else "single GPU"),
                        "l2": "256 MiB device memset between timed frames (untimed)"},
             "mtris_per_sec": round(value * tris_per_frame / 1e6, 2),
-            "stage_ms": stage_ms,
+            "stage_ms": stage_ms, "rank_frame_ms": rank_frame_ms,
             "stage_ms_source": "a second pass over the same %d frames with a CUDA event after every stage; the timed "
                                "frames only carry the frame's first and last event (events between kernels disable "
                                "the launch overlap)" % kept,
@@ -440,6 +468,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--equal-rows", action="store_true", help="--mode split: equal row counts instead of cost-balanced")
     ap.add_argument("--split-rows", action="store_true", help="--mode split: whole bin rows, balanced on measured cost")
+    ap.add_argument("--composite", default="stores", choices=["copy", "stores"],
+                    help="--mode split: how the other ranks' strips reach rank 0's image")
+    ap.add_argument("--balance-iters", type=int, default=3, help="--mode split: feedback steps of the range balancing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

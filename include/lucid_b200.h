@@ -119,6 +119,10 @@ int lucid_read_image(lucid_renderer *r, void *dst_rgba8, size_t pitch_bytes);
 /* ---- multi-GPU composite over NVLink: share one GPU's image with the other ranks ---- */
 /* device pointer and pitch (bytes) of the renderer-owned image */
 int lucid_image_pointer(lucid_renderer *r, void **device_ptr, size_t *pitch_bytes);
+/* bin-row split, second way to composite: after a frame rendered into the renderer's own image, copy
+ * the pixels of the owned bins to dst (device or peer pointer) as whole 128-byte bin rows, asynchronously
+ * on the render stream.  Fewer, larger NVLink packets than the raster kernels' direct stores. */
+int lucid_composite_to(lucid_renderer *r, void *dst_rgba8_device, size_t pitch_bytes);
 /* 64-byte cudaIpcMemHandle_t of the renderer-owned image, to be sent to peer processes */
 int lucid_ipc_export_image(lucid_renderer *r, void *handle64);
 /* maps a peer's image into this process; pass the result as out_rgba8 with LUCID_MEM_DEVICE */

@@ -80,7 +80,7 @@ _lib = None
 C_ABI_SYMBOLS = [
     "lucid_create", "lucid_destroy", "lucid_last_error", "lucid_set_geometry", "lucid_set_texture",
     "lucid_set_bin_rows", "lucid_render", "lucid_wait", "lucid_read_info", "lucid_bin_count",
-    "lucid_stage_times", "lucid_stage_times_at", "lucid_read_row_costs", "lucid_set_bin_range", "lucid_read_bin_costs", "lucid_read_quad_aabbs", "lucid_read_tri_records", "lucid_read_quad_attrs",
+    "lucid_stage_times", "lucid_stage_times_at", "lucid_read_row_costs", "lucid_set_bin_range", "lucid_read_bin_costs", "lucid_composite_to", "lucid_read_quad_aabbs", "lucid_read_tri_records", "lucid_read_quad_attrs",
     "lucid_read_bin_lists", "lucid_read_frag_counts", "lucid_read_image", "lucid_image_pointer",
     "lucid_ipc_export_image", "lucid_ipc_open_image", "lucid_ipc_close_image",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
@@ -120,6 +120,7 @@ def load_library(build_if_needed: bool = True):
     lib.lucid_read_row_costs.argtypes = [vp, vp, C.c_int32]
     lib.lucid_read_bin_costs.argtypes = [vp, vp, C.c_int32]
     lib.lucid_set_bin_range.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.lucid_composite_to.argtypes = [vp, vp, C.c_size_t]
     lib.lucid_stage_times.argtypes = [vp, C.POINTER(C.c_float * 8)]
     lib.lucid_stage_times_at.argtypes = [vp, C.c_int32, C.POINTER(C.c_float * 8)]
     lib.lucid_read_quad_aabbs.argtypes = [vp, C.c_int32, vp, C.c_int32]
@@ -328,6 +329,12 @@ class LucidRenderer:
         ms = (C.c_float * 8)()
         self._check(self._lib.lucid_stage_times_at(self._h, frames_back, C.byref(ms)), "lucid_stage_times")
         return np.array(ms[:], np.float32)
+
+    def composite_to(self, device_ptr: int, pitch: int | None = None):
+        """Copies the owned bins of the last frame (rendered into the renderer's own image) to a device /
+        peer image as whole bin rows, asynchronously on the render stream."""
+        self._check(self._lib.lucid_composite_to(self._h, C.c_void_p(device_ptr), pitch or self.width * 4),
+                    "lucid_composite_to")
 
     def set_bin_range(self, begin, end):
         """Own the bins [begin, end) in row-major order (finer than whole rows)."""

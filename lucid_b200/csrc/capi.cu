@@ -703,6 +703,20 @@ int lucid_read_image(lucid_renderer *r, void *dst, size_t pitch_bytes) {
 	return LUCID_OK;
 }
 
+int lucid_composite_to(lucid_renderer *r, void *dst_rgba8_device, size_t pitch_bytes) {
+	if(!r || !dst_rgba8_device || pitch_bytes < (size_t)r->p.width * 4 || (pitch_bytes & 3))
+		return LUCID_E_INVALID;
+	if(r->frame_counter == 0)
+		return fail(r, LUCID_E_STATE, "lucid_composite_to: no frame has been rendered");
+	CU(cudaSetDevice(r->ci.device));
+	Params p = r->p;
+	p.image = r->image, p.image_pitch = p.width;
+	launchCompositeBins(p, (u32 *)dst_rgba8_device, (int)(pitch_bytes / 4), r->stream, r->num_sms);
+	CU(cudaGetLastError());
+	r->pending = true;
+	return LUCID_OK;
+}
+
 int lucid_image_pointer(lucid_renderer *r, void **device_ptr, size_t *pitch_bytes) {
 	if(!r || !device_ptr || !pitch_bytes)
 		return LUCID_E_INVALID;

@@ -271,6 +271,7 @@ void launchPadPositions(const float *positions, float4 *positions4, int num_vert
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *stage_events);
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream,
 				  cudaEvent_t *stage_events, int num_sms);
+void launchCompositeBins(const Params &p, u32 *dst, int dst_pitch, cudaStream_t stream, int num_sms);
 size_t rasterLargeKeysCount(int num_sms);
 
 // 32 half-block lists of up to 4096 8-byte records (raster_high.glsl:27); a LOW bin uses the first

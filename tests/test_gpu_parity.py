@@ -354,11 +354,15 @@ def test_bin_range_split_matches_full_frame(small):
         assert ranges[0][0] == 0 and ranges[-1][1] == bc and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
         bcx = (sc["width"] + 31) // 32
         assert any(a % bcx != 0 for a, _ in ranges[1:])  # at least one boundary inside a bin row
-        for lo, hi in ranges:
+        for n, (lo, hi) in enumerate(ranges):
             part = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20)
             part.set_scene(sc)
             part.set_bin_range(lo, hi)
-            part.render(cfg, inst, cols, rects, out_device_ptr=ptr, out_pitch=pitch)
+            if n % 2 == 0:  # the raster kernels store into the shared image ...
+                part.render(cfg, inst, cols, rects, out_device_ptr=ptr, out_pitch=pitch)
+            else:  # ... or the owned bins are copied there after the frame (lucid_composite_to)
+                part.render(cfg, inst, cols, rects)
+                part.composite_to(ptr, pitch)
             frags += part.getStats()["fragments"]
             _, pc = api.split_info(part.read_info(), bc)
             for which in (0, 3):

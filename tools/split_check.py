@@ -31,10 +31,9 @@ for ci in [int(a) for a in sys.argv[1:]] or [0, 2]:
     handle = [part.ipc_export_image() if rank == 0 else None]
     dist.broadcast_object_list(handle, src=0)
     peer = part.ipc_open_image(handle[0]) if rank != 0 else None
+    part.render(cfg, inst, cols, rects)
     if peer is not None:
-        part.render(cfg, inst, cols, rects, out_device_ptr=peer, out_pitch=w * 4)
-    else:
-        part.render(cfg, inst, cols, rects)
+        part.composite_to(peer, w * 4)
     st = part.getStats()
     frags = torch.tensor([st["fragments"]], device="cuda", dtype=torch.int64)
     dist.all_reduce(frags)
