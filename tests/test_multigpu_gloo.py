@@ -76,3 +76,20 @@ def test_split_bin_rows_properties():
     assert len({next(i for i, (b, e) in enumerate(parts) if b <= r < e) for r in range(30, 34)}) >= 3
     with pytest.raises(ValueError):
         multigpu.split_bin_rows(10, 2, np.ones(3))
+
+
+def test_split_bins_properties():
+    """Row-major bin ranges of equal cost: contiguous, complete, non-empty, balanced up to one bin."""
+    rng = np.random.default_rng(3)
+    for bins, world in ((2040, 2), (8160, 8), (920, 3), (7, 8)):
+        w = rng.random(bins) ** 4 * 1000.0
+        w[rng.random(bins) < 0.4] = 0.0  # empty bins cost nothing
+        parts = multigpu.split_bins(bins, world, w)
+        assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == bins
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        if bins >= world:
+            assert all(hi > lo for lo, hi in parts)
+            sums = np.array([w[lo:hi].sum() for lo, hi in parts])
+            assert sums.max() <= w.sum() / world + w.max() + 1e-6
+    with pytest.raises(ValueError):
+        multigpu.split_bins(10, 2, np.ones(9))
