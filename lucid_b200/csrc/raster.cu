@@ -1128,7 +1128,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 			__syncthreads();
 			if(sh.status != 0) {
 				// too many triangles for one block: the bin is redone by the HIGH path
-				// (raster_low.glsl:101-105,230-237); k_promote appends it to the HIGH list
+				// (raster_low.glsl:101-105,230-237); promoteBins (k_raster_blocks) appends it to the HIGH list
 				if(tid == 0)
 					p.bin_flags[bin_id] |= 1u;
 				high = true;
@@ -1174,7 +1174,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 			}
 			__syncthreads();
 			if(sh.status != 0)
-				continue; // k_raster_finish paints the bin
+				continue; // finishBins (k_raster_blocks) paints the bin
 		}
 
 		// publish the non-empty blocks as work items of stage 2; empty ones only get the background

@@ -329,11 +329,13 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 		const bool vis = res[k].status == -1;
 		const u32 bs = __ballot_sync(0xffffffffu, vis && res[k].size_type == 0);
 		const u32 bl = __ballot_sync(0xffffffffu, vis && res[k].size_type == 1);
-		// warp-aggregated rejection counters
-		int key = res[k].status >= 0 ? res[k].status : LUCID_REJECTION_TYPE_COUNT;
-		u32 peers = __match_any_sync(0xffffffffu, key);
-		if(res[k].status >= 0 && lane == __ffs(peers) - 1)
-			atomicAdd(&s_rejected[res[k].status], __popc(peers));
+		// rejection counters: one ballot per rejection type
+#pragma unroll
+		for(int t = 0; t < LUCID_REJECTION_TYPE_COUNT; t++) {
+			const u32 m = __ballot_sync(0xffffffffu, res[k].status == t);
+			if(m != 0 && lane == 0)
+				atomicAdd(&s_rejected[t], __popc(m));
+		}
 		if(lane == 0)
 			s_counts[k * (SETUP_THREADS / 32) + warp][0] = __popc(bs), s_counts[k * (SETUP_THREADS / 32) + warp][1] = __popc(bl);
 		before_small[k] = __popc(bs & laneMaskLt()), before_large[k] = __popc(bl & laneMaskLt());

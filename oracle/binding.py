@@ -38,6 +38,7 @@ def load():
     lib.oracle_destroy.argtypes = [vp]
     lib.oracle_set_threads.argtypes = [vp, C.c_int]
     lib.oracle_set_bin_rows.argtypes = [vp, C.c_int, C.c_int]
+    lib.oracle_set_bin_range.argtypes = [vp, C.c_int, C.c_int]
     lib.oracle_set_geometry.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, C.c_int]
     lib.oracle_set_texture.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int]
     lib.oracle_render.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int]
@@ -89,6 +90,9 @@ class Oracle:
 
     def set_bin_rows(self, begin, end):
         self.lib.oracle_set_bin_rows(self.h, begin, end)
+
+    def set_bin_range(self, begin, end):
+        self.lib.oracle_set_bin_range(self.h, begin, end)
 
     def set_scene(self, scene):
         pos = np.ascontiguousarray(scene["positions"], np.float32)

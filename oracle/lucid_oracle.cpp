@@ -221,6 +221,8 @@ struct Oracle {
 	int max_visible_quads = 0;
 	u32 opts = 0;
 	int row_begin = 0, row_end = 0; // owned bin rows [begin, end)
+	int bin_begin = 0, bin_end = 0; // owned bins in row-major order (whole rows unless set_bin_range was used)
+	bool ownsBin(int b) const { return b >= bin_begin && b < bin_end; }
 	int num_threads = 1;
 
 	// borrowed geometry
@@ -687,7 +689,8 @@ void Oracle::binning() {
 		u32 word = (u32)q | (enc & 0xf0000000u);
 		for(int by = std::max(bsy, row_begin); by <= std::min(bey, row_end - 1); by++)
 			for(int bx = bsx; bx <= bex; bx++)
-				bq[by * bin_count_x + bx].push_back(word);
+				if(ownsBin(by * bin_count_x + bx))
+					bq[by * bin_count_x + bx].push_back(word);
 	}
 	// large tris: per bin-row scanline at the trivial-reject corner (bin_counter.glsl:112-134,
 	// bin_dispatcher.glsl:89-114)
@@ -708,7 +711,8 @@ void Oracle::binning() {
 				if(by < row_begin || by >= row_end)
 					continue;
 				for(int bx = bmin; bx <= bmax; bx++)
-					bt[by * bin_count_x + bx].push_back(tri_idx);
+					if(ownsBin(by * bin_count_x + bx))
+						bt[by * bin_count_x + bx].push_back(tri_idx);
 			}
 		}
 	}
@@ -1390,6 +1394,7 @@ void *oracle_create(int width, int height, uint32_t opts, int max_visible_quads)
 	o->bin_count = o->bin_count_x * o->bin_count_y;
 	o->max_visible_quads = max_visible_quads;
 	o->row_begin = 0, o->row_end = o->bin_count_y;
+	o->bin_begin = 0, o->bin_end = o->bin_count;
 	return o;
 }
 void oracle_destroy(void *h) { delete(Oracle *)h; }
@@ -1397,6 +1402,13 @@ void oracle_set_threads(void *h, int n) { ((Oracle *)h)->num_threads = n < 1 ? 1
 void oracle_set_bin_rows(void *h, int begin, int end) {
 	Oracle *o = (Oracle *)h;
 	o->row_begin = std::max(0, begin), o->row_end = std::min(o->bin_count_y, end);
+	o->bin_begin = o->row_begin * o->bin_count_x, o->bin_end = o->row_end * o->bin_count_x;
+}
+// ownership finer than rows (include/lucid_b200.h lucid_set_bin_range): bins [begin, end) in row-major order
+void oracle_set_bin_range(void *h, int begin, int end) {
+	Oracle *o = (Oracle *)h;
+	o->bin_begin = std::max(0, begin), o->bin_end = std::min(o->bin_count, end);
+	o->row_begin = o->bin_begin / o->bin_count_x, o->row_end = (o->bin_end - 1) / o->bin_count_x + 1;
 }
 void oracle_set_geometry(void *h, const float *positions, int num_verts, const uint32_t *colors,
 						 const float *uvs, const uint32_t *normals, const uint32_t *quad_indices,

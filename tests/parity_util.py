@@ -24,11 +24,13 @@ def small_scenes():
     return out
 
 
-def run_oracle(scene, opts=0, camera=None, bin_rows=None, threads=8, mvq=1 << 20):
+def run_oracle(scene, opts=0, camera=None, bin_rows=None, threads=8, mvq=1 << 20, bin_range=None):
     cfg, inst, cols, rects = api.prepare_frame(scene, camera)
     o = Oracle(scene["width"], scene["height"], opts, mvq, threads=threads)
     if bin_rows:
         o.set_bin_rows(*bin_rows)
+    if bin_range:
+        o.set_bin_range(*bin_range)
     o.set_scene(scene)
     o.render(cfg, inst, cols, rects)
     return o

@@ -364,10 +364,17 @@ def test_bin_range_split_matches_full_frame(small):
                 part.render(cfg, inst, cols, rects)
                 part.composite_to(ptr, pitch)
             frags += part.getStats()["fragments"]
-            _, pc = api.split_info(part.read_info(), bc)
+            pi = part.read_info()
+            _, pc = api.split_info(pi, bc)
             for which in (0, 3):
                 assert np.array_equal(pc[which][lo:hi], full_counts[which][lo:hi])
                 assert pc[which][:lo].sum() == 0 and pc[which][hi:].sum() == 0
+            o = pu.run_oracle(sc, bin_range=(lo, hi))  # the oracle with the same ownership
+            for a, b in ((0, 10), (32, 36), (60, 63)):  # counts, rejections, statistics
+                assert np.array_equal(pi[a:b], o.info[a:b])
+            _, oc = api.split_info(o.info, bc)
+            for which in (0, 1, 3, 4):
+                assert np.array_equal(pc[which], oc[which])
             part.close()
         assert np.array_equal(target.read_image(), full_img)
         assert frags == full_frags

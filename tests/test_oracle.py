@@ -210,3 +210,28 @@ def test_bin_row_split_composes_to_the_full_frame(small):
         assert np.array_equal(cf[0][sl], cp[0][sl]) and np.array_equal(cf[3][sl], cp[3][sl])
     assert np.array_equal(img, full.read_image())
     assert frags == int(full.info[60])
+
+
+def test_bin_range_split_composes_to_the_full_frame(small):
+    """Ownership finer than rows: row-major bin ranges that cut through bin rows reproduce the full
+    frame's counts in their bins, nothing elsewhere, and their pixels compose to the full image."""
+    sc = small["arch"]
+    full = pu.run_oracle(sc)
+    bc, bcx = full.bin_count, (sc["width"] + 31) // 32
+    _, fc = api.split_info(full.info, bc)
+    cuts = [0, bcx + 3, 3 * bcx + bcx // 2, bc]
+    image = np.zeros_like(full.read_image())
+    frags = 0
+    for lo, hi in zip(cuts, cuts[1:]):
+        part = pu.run_oracle(sc, bin_range=(lo, hi))
+        _, pc = api.split_info(part.info, bc)
+        for which in (0, 3):
+            assert np.array_equal(pc[which][lo:hi], fc[which][lo:hi])
+            assert pc[which][:lo].sum() == 0 and pc[which][hi:].sum() == 0
+        frags += int(part.info[60])
+        img = part.read_image()
+        for b in range(lo, hi):
+            by, bx = divmod(b, bcx)
+            image[by * 32:(by + 1) * 32, bx * 32:(bx + 1) * 32] = img[by * 32:(by + 1) * 32, bx * 32:(bx + 1) * 32]
+    assert np.array_equal(image, full.read_image())
+    assert frags == int(full.info[60])
