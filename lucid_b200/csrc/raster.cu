@@ -1247,43 +1247,42 @@ constexpr int WARP_SCRATCH_BYTES = WARP_SCRATCH_FIXED + SMEM_KEYS * 4;
 // (raster_low.glsl:230-237,294-298).  Everything read here was written by k_raster_bins.
 __device__ __forceinline__ void finishBins(const Params &p, u32 background, u32 *s_mask) {
 	const int lane = laneId(), warp = threadIdx.x >> 5;
-	const int first = blockIdx.x * 32;
-	if(first >= p.bin_count)
-		return;
-	if(warp == 0) {
-		const int b = first + lane;
-		u32 kind = 0; // 1 background, 2 red
-		if(b < p.bin_count) {
-			if(ownsBin(p, b)) {
+	// 32 bins per CTA and round (one round on a B200: 740 CTAs cover 23 680 bins)
+	for(int first = blockIdx.x * 32; first < p.bin_count; first += gridDim.x * 32) {
+		if(warp == 0) {
+			const int b = first + lane;
+			u32 kind = 0; // 1 background, 2 red
+			if(b < p.bin_count && ownsBin(p, b)) {
 				const bool empty = cntc(p, LUCID_CNT_TRI_COUNTS)[b] + cntc(p, LUCID_CNT_QUAD_COUNTS)[b] * 2 == 0;
 				kind = (p.bin_flags[b] & 2u) ? 2u : empty ? 1u : 0u;
 			}
+			const u32 fill = __ballot_sync(0xffffffffu, kind != 0), red = __ballot_sync(0xffffffffu, kind == 2);
+			if(lane == 0)
+				s_mask[0] = fill, s_mask[1] = red;
 		}
-		const u32 fill = __ballot_sync(0xffffffffu, kind != 0), red = __ballot_sync(0xffffffffu, kind == 2);
-		if(lane == 0)
-			s_mask[0] = fill, s_mask[1] = red;
-	}
-	__syncthreads();
-	const u32 red = s_mask[1];
-	u32 fill = s_mask[0];
-	for(int n = 0; fill; n++) {
-		const int j = __ffs(fill) - 1;
-		fill &= fill - 1;
-		if((n & (BLOCK_WARPS - 1)) != warp)
-			continue;
-		const int b = first + j, by = b / p.bin_count_x, bx = b - by * p.bin_count_x;
-		const u32 value = ((red >> j) & 1u) ? 0x000000ffu : background;
-		const int gx = bx * BIN_SIZE + lane;
-		if(gx < p.width)
+		__syncthreads();
+		const u32 red = s_mask[1];
+		u32 fill = s_mask[0];
+		__syncthreads();
+		for(int n = 0; fill; n++) {
+			const int j = __ffs(fill) - 1;
+			fill &= fill - 1;
+			if((n & (BLOCK_WARPS - 1)) != warp)
+				continue;
+			const int b = first + j, by = b / p.bin_count_x, bx = b - by * p.bin_count_x;
+			const u32 value = ((red >> j) & 1u) ? 0x000000ffu : background;
+			const int gx = bx * BIN_SIZE + lane;
+			if(gx < p.width)
 #pragma unroll 4
-			for(int y = 0; y < BIN_SIZE; y++) {
-				const int gy = by * BIN_SIZE + y;
-				if(gy >= p.height)
-					break;
-				p.image[(size_t)gy * p.image_pitch + gx] = value;
-				if(p.frag_counts)
-					p.frag_counts[(size_t)gy * p.width + gx] = 0;
-			}
+				for(int y = 0; y < BIN_SIZE; y++) {
+					const int gy = by * BIN_SIZE + y;
+					if(gy >= p.height)
+						break;
+					p.image[(size_t)gy * p.image_pitch + gx] = value;
+					if(p.frag_counts)
+						p.frag_counts[(size_t)gy * p.width + gx] = 0;
+				}
+		}
 	}
 }
 
