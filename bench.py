@@ -242,8 +242,10 @@ def run_ours(args):
         render(w, flags=plain)
     barrier()
 
+    # NVML polling takes driver locks: only the rank that prints the line samples its GPU
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     t_wall = time.time()
