@@ -246,6 +246,8 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # --trace-split: an extra event between the frame and the completion all-reduce of every step
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if (split and args.trace_split) else None
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     t_wall = time.time()
@@ -254,6 +256,8 @@ def run_ours(args):
         starts[k].record(stream)
         render(args.warmup + k, flags=plain)
         if split:  # the frame is complete when every rank's strip has landed in rank 0's image
+            if mids is not None:
+                mids[k].record(stream)
             dist.all_reduce(frame_token)
         stops[k].record(stream)
     barrier()
@@ -267,6 +271,12 @@ def run_ours(args):
         dist.all_reduce(t)
         rank_frame_ms = [round(float(x), 4) for x in t.cpu().numpy()]
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)], np.float64)
+    if mids is not None:  # where a step's time goes on this rank: submission + frame, then waiting for the others
+        a = np.median([s.elapsed_time(m) for s, m in zip(starts, mids)])
+        b = np.median([m.elapsed_time(e) for m, e in zip(mids, stops)])
+        lib = np.median([r.stage_times(i)[7] for i in range(min(args.steps, 64))])
+        sys.stderr.write(f"[trace-split] rank {rank}: start->frame end {a:.4f} ms (library frame {lib:.4f} ms), "
+                         f"frame end->all-reduce done {b:.4f} ms, step {np.median(step_ms):.4f} ms\n")
     total_ms = torch.tensor([float(step_ms.sum())], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -472,6 +482,8 @@ def main():
     ap.add_argument("--split-rows", action="store_true", help="--mode split: whole bin rows, balanced on measured cost")
     ap.add_argument("--composite", default="stores", choices=["copy", "stores"],
                     help="--mode split: how the other ranks' strips reach rank 0's image")
+    ap.add_argument("--trace-split", action="store_true",
+                    help="--mode split: per-rank split of a step into frame and completion wait (stderr)")
     ap.add_argument("--balance-iters", type=int, default=3, help="--mode split: feedback steps of the range balancing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
