@@ -238,8 +238,10 @@ def run_ours(args):
     # timed frames carry only the frame's first and last event: per-stage events between the kernels would
     # keep each launch from overlapping its predecessor's tail (programmatic dependent launch)
     plain = api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES
-    for w in range(args.warmup):
+    for w in range(args.warmup):  # the same sequence as a timed step, completion all-reduce included
         render(w, flags=plain)
+        if split:
+            dist.all_reduce(frame_token)
     barrier()
 
     # NVML polling takes driver locks: only the rank that prints the line samples its GPU
@@ -276,7 +278,8 @@ def run_ours(args):
         b = np.median([m.elapsed_time(e) for m, e in zip(mids, stops)])
         lib = np.median([r.stage_times(i)[7] for i in range(min(args.steps, 64))])
         sys.stderr.write(f"[trace-split] rank {rank}: start->frame end {a:.4f} ms (library frame {lib:.4f} ms), "
-                         f"frame end->all-reduce done {b:.4f} ms, step {np.median(step_ms):.4f} ms\n")
+                         f"frame end->all-reduce done {b:.4f} ms, step median {np.median(step_ms):.4f} ms; steps "
+                         f"{[round(float(x), 3) for x in step_ms]}\n")
     total_ms = torch.tensor([float(step_ms.sum())], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
