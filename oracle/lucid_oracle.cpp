@@ -222,6 +222,13 @@ struct Oracle {
 	u32 opts = 0;
 	int row_begin = 0, row_end = 0; // owned bin rows [begin, end)
 	int bin_begin = 0, bin_end = 0; // owned bins in row-major order (whole rows unless set_bin_range was used)
+	// optional work statistics of the block stage (tools/item_stats.py): how the kernels' chunked shading
+	// loop would be filled -- [0] lists [1] entries [2] samples, then for chunks of 32 / 64 entries:
+	// chunks, shading rounds (32 samples each), reduce iterations (max samples of one pixel per chunk);
+	// [9..13] lists per size class, [14..18] entries per size class
+	bool collect_item_stats = false;
+	unsigned long long item_stats[24] = {};
+	void addItemStats(const std::vector<u32> &entry_bits);
 	bool ownsBin(int b) const { return b >= bin_begin && b < bin_end; }
 	int num_threads = 1;
 
@@ -1241,6 +1248,15 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 				u32 frag_total = 0, tri_count = (u32)list.size();
 				u32 processed = 0; // samples consumed so far (segment boundaries every 256)
 				bool stop = false;
+				if(collect_item_stats && !list.empty()) {
+					std::vector<u32> entry_bits;
+					for(const Entry &e : list) {
+						const RowTri &rt = rows[g][e.slot];
+						entry_bits.push_back(halfPixelMask(halfSpans(rt.mins[half], rt.maxs[half], startx)));
+					}
+#pragma omp critical(item_stats)
+					addItemStats(entry_bits);
+				}
 				for(const Entry &e : list) {
 					const RowTri &rt = rows[g][e.slot];
 					HalfSpans h = halfSpans(rt.mins[half], rt.maxs[half], startx);
@@ -1315,6 +1331,41 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 		}
 	}
 	bin_level[bin_id] = high ? LUCID_BIN_LEVEL_HIGH : LUCID_BIN_LEVEL_LOW;
+}
+
+void Oracle::addItemStats(const std::vector<u32> &entry_bits) {
+	const size_t n = entry_bits.size();
+	item_stats[0] += 1, item_stats[1] += n;
+	const int cls = n > 384 ? 0 : n > 160 ? 1 : n > 64 ? 2 : n > 24 ? 3 : 4; // raster.cu itemClass
+	item_stats[9 + cls] += 1, item_stats[14 + cls] += n;
+	for(int width_i = 0; width_i < 2; width_i++) {
+		const size_t chunk_entries = width_i == 0 ? 32 : 64;
+		size_t i = 0;
+		while(i < n) {
+			// a chunk takes entries while they fit into 256 samples (raster.cu shadeHalfBlock)
+			int per_pixel[32] = {};
+			u32 samples = 0;
+			size_t taken = 0;
+			while(i + taken < n && taken < chunk_entries) {
+				u32 c = (u32)__builtin_popcount(entry_bits[i + taken]);
+				if(taken > 0 && samples + c > 256)
+					break;
+				samples += c;
+				for(u32 b = entry_bits[i + taken]; b; b &= b - 1)
+					per_pixel[__builtin_ctz(b)]++;
+				taken++;
+			}
+			int max_px = 0;
+			for(int p = 0; p < 32; p++)
+				max_px = std::max(max_px, per_pixel[p]);
+			if(width_i == 0)
+				item_stats[2] += samples;
+			item_stats[3 + width_i * 3] += 1;
+			item_stats[4 + width_i * 3] += (samples + 31) / 32;
+			item_stats[5 + width_i * 3] += (u32)max_px;
+			i += taken;
+		}
+	}
 }
 
 void Oracle::raster() {
@@ -1399,6 +1450,17 @@ void *oracle_create(int width, int height, uint32_t opts, int max_visible_quads)
 }
 void oracle_destroy(void *h) { delete(Oracle *)h; }
 void oracle_set_threads(void *h, int n) { ((Oracle *)h)->num_threads = n < 1 ? 1 : n; }
+void oracle_set_item_stats(void *h, int on) {
+	Oracle *o = (Oracle *)h;
+	o->collect_item_stats = on != 0;
+	for(auto &v : o->item_stats)
+		v = 0;
+}
+void oracle_read_item_stats(void *h, unsigned long long *dst) {
+	Oracle *o = (Oracle *)h;
+	for(int i = 0; i < 24; i++)
+		dst[i] = o->item_stats[i];
+}
 void oracle_set_bin_rows(void *h, int begin, int end) {
 	Oracle *o = (Oracle *)h;
 	o->row_begin = std::max(0, begin), o->row_end = std::min(o->bin_count_y, end);
