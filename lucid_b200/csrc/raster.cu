@@ -617,22 +617,31 @@ __device__ __forceinline__ void recAt(const RecList &l, u32 pos, u32 &mins, u32 
 // shading of one 8x4 half-block from its depth-sorted list
 
 constexpr int CHUNK_SAMPLES = 256;
+// RB_CHUNK64 (experiment, off: not yet measured on a GPU): a chunk takes up to 64 list entries instead
+// of 32, as two sub-chunks that share one shading pass and one reduce pass.  Counted on the checker's
+// lists (profiles/r1k_item_statistics.txt) that raises the busy lanes of the shading rounds from 66 % to
+// 77 % and of the reduce loop from 46 % to 54 % on the 1M-triangle scene.
+#ifdef RB_CHUNK64
+constexpr int CHUNK_ENTRIES = 64;
+#else
+constexpr int CHUNK_ENTRIES = 32;
+#endif
 
 struct WarpScratch {
-	float4 *stage;	 // 32: depth plane + constant colour of the chunk's triangles
+	float4 *stage;	 // CHUNK_ENTRIES: depth plane + constant colour of the chunk's triangles
 	uint2 *results;	 // CHUNK_SAMPLES: (colour, depth) per sample
-	uint2 *chunk;	 // 32: (pixel mask, first sample) of the chunk's triangles
+	uint2 *chunk;	 // CHUNK_ENTRIES: (pixel mask, first sample) of the chunk's triangles
 	u32 *samples;	 // SAMPLE_BUF: pixel | tri << 8
 	u32 *mask;		 // 32 (segment path)
 	u32 *keys;		 // CAP
 };
-constexpr int WARP_SCRATCH_FIXED = 32 * 16 + CHUNK_SAMPLES * 8 + 32 * 8 + SAMPLE_BUF * 4 + 32 * 4;
+constexpr int WARP_SCRATCH_FIXED = CHUNK_ENTRIES * 16 + CHUNK_SAMPLES * 8 + CHUNK_ENTRIES * 8 + SAMPLE_BUF * 4 + 32 * 4;
 __device__ __forceinline__ WarpScratch warpScratch(unsigned char *base) {
 	WarpScratch ws;
 	ws.stage = reinterpret_cast<float4 *>(base);
-	ws.results = reinterpret_cast<uint2 *>(base + 32 * 16);
+	ws.results = reinterpret_cast<uint2 *>(base + CHUNK_ENTRIES * 16);
 	ws.chunk = ws.results + CHUNK_SAMPLES;
-	ws.samples = reinterpret_cast<u32 *>(ws.chunk + 32);
+	ws.samples = reinterpret_cast<u32 *>(ws.chunk + CHUNK_ENTRIES);
 	ws.mask = ws.samples + SAMPLE_BUF;
 	ws.keys = ws.mask + 32;
 	return ws;
@@ -816,6 +825,167 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 	writePixel(p, cfg, red, hb_x, hb_y, px_frags, additive, vis_errors);
 }
 
+#ifdef RB_CHUNK64
+// shadeHalfBlock with chunks of up to 64 entries.  Sub-chunk A is taken exactly as in shadeHalfBlock;
+// when all 32 of its entries fit, sub-chunk B continues the same sample budget (256 per chunk).  A
+// constant-colour chunk only takes a B that is constant-colour too, so a chunk stays on one path.
+// The per-pixel order of pushes is the list order in both variants: the pixels are identical.
+__device__ __forceinline__ void shadeHalfBlock64(const Params &p, const LucidConfig &cfg, const WarpScratch &ws,
+												 const u32 *keys, const uint4 *aux, int count, u32 pos_mask, int hb_x,
+												 int hb_y, const RecList &list) {
+	const int lane = laneId();
+	const bool additive = (p.opts & LUCID_OPT_ADDITIVE_BLENDING) != 0;
+	const bool vis_errors = (p.opts & LUCID_OPT_VISUALIZE_ERRORS) != 0;
+	const float fpx = float(hb_x + (lane & 7)), fpy = float(hb_y + (lane >> 3));
+	Reducer red;
+	reducerInit(red);
+	u32 px_frags = 0;
+	bool dead = false;
+
+	auto inclusiveScan = [&](int v) {
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) {
+			int t = __shfl_up_sync(0xffffffffu, v, o);
+			if(lane >= o)
+				v += t;
+		}
+		return v;
+	};
+
+	ChunkEntry ahead = loadEntry(list, aux, keys, lane, count, pos_mask);
+	for(int next = 0; next < count;) {
+		// ---- sub-chunk A
+		const ChunkEntry cur = ahead;
+		int nf;
+		u32 bits_a = rowsToBits(cur.mins, cur.maxs, list.startx, nf);
+		const int incl_a = inclusiveScan(nf);
+		const bool in_a = next + lane < count && incl_a <= CHUNK_SAMPLES;
+		const int taken_a = __popc(__ballot_sync(0xffffffffu, in_a)); // a prefix, never empty
+		int total = __shfl_sync(0xffffffffu, incl_a, taken_a - 1);
+		if(!in_a)
+			bits_a = 0;
+		const bool const_a = __all_sync(0xffffffffu, !in_a || cur.aux.w != AUX_VARYING);
+		next += taken_a;
+		ahead = loadEntry(list, aux, keys, next + lane, count, pos_mask);
+		u32 tm_a = transpose32(bits_a);
+		px_frags += __popc(tm_a);
+		const u32 dead_px = (vis_errors || dead) ? 0u : __ballot_sync(0xffffffffu, red.trans == 0.0f);
+
+		// what the paths need of A goes to shared memory now, so B can reuse the registers
+		int live_total = 0;
+		if(!dead) {
+			if(const_a) {
+				ws.stage[lane] = make_float4(__uint_as_float(cur.aux.x), __uint_as_float(cur.aux.y),
+											 __uint_as_float(cur.aux.z), __uint_as_float(cur.aux.w));
+			} else {
+				const u32 live = bits_a & ~dead_px;
+				const int nl = __popc(live), li = inclusiveScan(nl);
+				live_total = __shfl_sync(0xffffffffu, li, 31);
+				if(in_a) {
+					ws.chunk[lane] = make_uint2(live, (u32)(li - nl));
+					u32 dst = (u32)(li - nl), word = cur.tri << 8, b = live;
+					while(b) {
+						u32 pid = __ffs(b) - 1;
+						b &= b - 1;
+						ws.samples[dst++] = pid | word;
+					}
+				}
+			}
+		}
+
+		// ---- sub-chunk B: only after a full A, within the same 256 samples
+		u32 tm_b = 0;
+		if(taken_a == 32 && next < count) {
+			const ChunkEntry cb = ahead;
+			int nf_b;
+			u32 bits_b = rowsToBits(cb.mins, cb.maxs, list.startx, nf_b);
+			const int incl_b = total + inclusiveScan(nf_b);
+			bool in_b = next + lane < count && incl_b <= CHUNK_SAMPLES;
+			const bool const_b = __all_sync(0xffffffffu, !in_b || cb.aux.w != AUX_VARYING);
+			if(const_a && !const_b)
+				in_b = false; // a constant-colour chunk stays constant-colour; B starts the next chunk
+			const int taken_b = __popc(__ballot_sync(0xffffffffu, in_b)); // a prefix, possibly empty
+			if(taken_b > 0) {
+				total = __shfl_sync(0xffffffffu, incl_b, taken_b - 1);
+				if(!in_b)
+					bits_b = 0;
+				next += taken_b;
+				ahead = loadEntry(list, aux, keys, next + lane, count, pos_mask);
+				tm_b = transpose32(bits_b);
+				px_frags += __popc(tm_b);
+				if(!dead) {
+					if(const_a) {
+						ws.stage[32 + lane] = make_float4(__uint_as_float(cb.aux.x), __uint_as_float(cb.aux.y),
+														  __uint_as_float(cb.aux.z), __uint_as_float(cb.aux.w));
+					} else {
+						const u32 live = bits_b & ~dead_px;
+						const int nl = __popc(live), li = live_total + inclusiveScan(nl);
+						if(in_b) {
+							ws.chunk[32 + lane] = make_uint2(live, (u32)(li - nl));
+							u32 dst = (u32)(li - nl), word = cb.tri << 8, b = live;
+							while(b) {
+								u32 pid = __ffs(b) - 1;
+								b &= b - 1;
+								ws.samples[dst++] = pid | word;
+							}
+						}
+						live_total = __shfl_sync(0xffffffffu, li, 31);
+					}
+				}
+			}
+		}
+		if(dead)
+			continue;
+		if((dead_px >> lane) & 1u)
+			tm_a = 0, tm_b = 0;
+		__syncwarp();
+
+		if(const_a) {
+#pragma unroll
+			for(int half = 0; half < 2; half++) {
+				u32 tm = half == 0 ? tm_a : tm_b;
+				while(tm) {
+					int j = __ffs(tm) - 1;
+					tm &= tm - 1;
+					float4 s = ws.stage[half * 32 + j];
+					float depth = s.x * fpx + (s.y * fpy + s.z);
+					reducerPush(red, __float_as_uint(s.w), depth, additive, vis_errors);
+				}
+			}
+		} else {
+			for(int r0 = 0; r0 < live_total; r0 += 32) {
+				int idx = r0 + lane;
+				if(idx < live_total) {
+					u32 val = ws.samples[idx], pid = val & 31u;
+					float depth;
+					u32 color = shadeSample(p, cfg, hb_x + (int)(pid & 7), hb_y + (int)(pid >> 3), val >> 8, depth);
+					ws.results[idx] = make_uint2(color, __float_as_uint(depth));
+				}
+			}
+			__syncwarp();
+#pragma unroll
+			for(int half = 0; half < 2; half++) {
+				u32 tm = half == 0 ? tm_a : tm_b;
+				while(tm) {
+					int j = __ffs(tm) - 1;
+					tm &= tm - 1;
+					uint2 c = ws.chunk[half * 32 + j];
+					uint2 res = ws.results[c.y + __popc(c.x & laneMaskLt())];
+					reducerPush(red, res.x, __uint_as_float(res.y), additive, vis_errors);
+				}
+			}
+		}
+		__syncwarp();
+		if(!vis_errors && __all_sync(0xffffffffu, red.trans == 0.0f)) {
+			dead = true;
+			if(!p.frag_counts)
+				break;
+		}
+	}
+	writePixel(p, cfg, red, hb_x, hb_y, px_frags, additive, vis_errors);
+}
+#endif
+
 // Segment-accurate variant (raster.glsl:292-396) for ALPHA_THRESHOLD: samples are expanded and
 // consumed in the reference's 256-sample segments, so the early-out decisions fall on the same
 // sample boundaries.
@@ -923,7 +1093,11 @@ __device__ __forceinline__ void shadeHalfBlockAny(const Params &p, const LucidCo
 	if(alpha_thr)
 		shadeHalfBlockSegments(p, cfg, ws, keys, count, pos_mask, hb_x, hb_y, list);
 	else
+#ifdef RB_CHUNK64
+		shadeHalfBlock64(p, cfg, ws, keys, aux, count, pos_mask, hb_x, hb_y, list);
+#else
 		shadeHalfBlock(p, cfg, ws, keys, aux, count, pos_mask, hb_x, hb_y, list);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
