@@ -617,10 +617,11 @@ __device__ __forceinline__ void recAt(const RecList &l, u32 pos, u32 &mins, u32 
 // shading of one 8x4 half-block from its depth-sorted list
 
 constexpr int CHUNK_SAMPLES = 256;
-// RB_CHUNK64 (experiment, off: not yet measured on a GPU): a chunk takes up to 64 list entries instead
-// of 32, as two sub-chunks that share one shading pass and one reduce pass.  Counted on the checker's
-// lists (profiles/r1k_item_statistics.txt) that raises the busy lanes of the shading rounds from 66 % to
-// 77 % and of the reduce loop from 46 % to 54 % on the 1M-triangle scene.
+// RB_CHUNK64 (experiment build, off): a chunk takes up to 64 list entries instead of 32, as two
+// sub-chunks that share one shading pass and one reduce pass.  Counted on the checker's lists
+// (profiles/r1k_item_statistics.txt) that raises the busy lanes of the shading rounds from 66 % to 77 %
+// and of the reduce loop from 46 % to 54 % on the 1M-triangle scene; measured, it is bit-exact and 10 %
+// slower there (0.138 vs 0.126 ms): the second sub-chunk's scans and spills cost more than they return.
 #ifdef RB_CHUNK64
 constexpr int CHUNK_ENTRIES = 64;
 #else
