@@ -143,3 +143,17 @@ def test_bad_create_arguments():
     ci = api.CreateInfo(8192, 100, 0, 0, 0, 0, None, 0, 0)
     assert lib.lucid_create(C.byref(ci), C.byref(h)) == -3  # 7-bit bin coordinates
     assert b"4096" in lib.lucid_last_error(None)
+
+
+def test_committed_dram_traffic_file_serves_the_bench_line():
+    """bench.py takes roofline.traffic / sm_issue_active_pct from profiles/dram_traffic.json (written by
+    tools/ncu_traffic.py or tools/traffic_from_summary.py from an ncu --set full capture)."""
+    import json
+    path = os.path.join(HERE, "..", "profiles", "dram_traffic.json")
+    with open(path) as f:
+        d = json.load(f)
+    for cfg in ("config1", "config2", "config3"):
+        for stage in ("setup", "bin_count", "bin_dispatch", "raster"):
+            assert d[cfg][stage] > 0
+            assert 0 < d[cfg]["issue_active_pct"][stage] <= 100
+        assert d[cfg]["per_kernel"]["k_raster_blocks"] > 0 and "source" in d[cfg]
