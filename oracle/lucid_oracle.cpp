@@ -222,7 +222,7 @@ struct Oracle {
 	u32 opts = 0;
 	int row_begin = 0, row_end = 0; // owned bin rows [begin, end)
 	int bin_begin = 0, bin_end = 0; // owned bins in row-major order (whole rows unless set_bin_range was used)
-	// optional work statistics of the block stage (tools/item_stats.py): how the kernels' chunked shading
+	// optional work statistics of the block stage (tests/item_stats.py): how the kernels' chunked shading
 	// loop would be filled -- [0] lists [1] entries [2] samples, then for chunks of 32 / 64 entries:
 	// chunks, shading rounds (32 samples each), reduce iterations (max samples of one pixel per chunk);
 	// [9..13] lists per size class, [14..18] entries per size class

@@ -1,5 +1,6 @@
 """How full would the chunked shading loop of k_raster_blocks be?  Counted on the CPU checker's block
-lists (no GPU needed): python tools/item_stats.py [config ...] > profiles/<tag>_item_statistics.txt"""
+lists (no GPU needed; test infrastructure, like everything that loads oracle/):
+   python tests/item_stats.py [config ...] > profiles/<tag>_item_statistics.txt"""
 import ctypes as C
 import os
 import sys
