@@ -1,5 +1,5 @@
-"""Full-size probe: stage times + counters of the CUDA path on the BASELINE configs, optionally
-compared with the oracle.  usage: python tools/gpu_probe.py [config ...] [--oracle] [--scale S]"""
+"""Full-size probe: stage times + counters of the CUDA path on the BASELINE configs (parity against the
+checker is the GPU test suite's job).  usage: python tools/gpu_probe.py [config ...] [--scale=S]"""
 import json
 import os
 import sys
@@ -11,7 +11,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lucid_b200 import api, scenes  # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-with_oracle = "--oracle" in sys.argv
 scale = 1.0
 for a in sys.argv[1:]:
     if a.startswith("--scale="):
@@ -44,11 +43,4 @@ for ci in configs:
             f"gpurun_out/config{ci}.png")
     except Exception as e:
         print("   (no image saved)", e)
-    if with_oracle:
-        from tests import parity_util as pu
-        t1 = time.time()
-        o = pu.run_oracle(sc, threads=os.cpu_count(), mvq=4793490)
-        print(f"   oracle {time.time() - t1:.1f}s stage_ms {np.round(o.stage_ms(), 1).tolist()}")
-        bad = pu.compare(r, img, o)
-        print("   PARITY", "OK" if not [k for k in bad if not k.startswith('_')] else "MISMATCH", bad)
     r.close()
