@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""Compiles functions of the reference's compute shaders -- from the GLSL text where it lies under
+/root/reference/data/shaders -- into oracle/_ref/libref_shaders.so, so the CPU checker can be pinned
+against the reference's own source for the arithmetic that decides coverage (quad culling and bin
+AABBs, triangle plane / barycentric / scanline equations, scanline parameters, the 4-row span step,
+half-block centroids and block depth keys).
+
+    python oracle/build_ref_shaders.py [--reference /root/reference] [--keep-source]
+
+Nothing of the reference is copied into the repository: the extracted text only exists in the
+git-ignored oracle/_ref/ (generated C++ next to the .so).  The translation is purely textual and is
+listed in oracle/glsl_shim.h; the wrappers at the end of the generated file are ours.
+Test infrastructure (tests/golden/make_ref_shader_golden.py turns its outputs into committed vectors).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# (file under data/shaders, function names in the order they are emitted)
+FUNCTIONS = [
+    ("shared/funcs.glsl", ["encodeNormalUint", "encodeAABB28", "decodeAABB28"]),
+    ("quad_setup.glsl", ["vertexLoad", "vertexClipMask", "computeClippedAABB", "computeAABB", "processInputQuad", "storeTri"]),
+    ("shared/scanline.glsl", ["loadScanlineParamsRow", "loadScanlineParamsBin"]),
+    ("bin_counter.glsl", ["scanlineStep"]),
+    ("shared/raster.glsl", ["rasterBinStep", "rasterHalfBlockCentroid", "rasterHalfBlockBits", "rasterBlockDepth"]),
+]
+# #define lines taken over from the reference (name -> file)
+DEFINES = {
+    "shared/definitions.glsl": ["REJECTION_TYPE_COUNT", "REJECTION_TYPE_OTHER", "REJECTION_TYPE_BACKFACE",
+                                "REJECTION_TYPE_FRUSTUM", "REJECTION_TYPE_BETWEEN_SAMPLES", "INST_HAS_VERTEX_NORMALS",
+                                "STORAGE_TRI_BARY_OFFSET", "STORAGE_TRI_SCAN_OFFSET", "STORAGE_TRI_DEPTH_OFFSET"],
+    "shared/funcs.glsl": ["SATURATE"],
+    "quad_setup.glsl": ["MAX_INSTANCE_QUADS", "LSIZE"],
+    "shared/raster.glsl": ["BIN_MASK", "HBLOCK_WIDTH", "HBLOCK_WIDTH_SHIFT", "HBLOCK_COLS", "HBLOCK_COLS_SHIFT",
+                           "HBLOCK_COLS_MASK"],
+}
+
+
+def extract_function(text: str, name: str) -> str:
+    m = re.search(r"^[A-Za-z_]\w*(?:\s+\w+)*\s+" + re.escape(name) + r"\s*\(", text, re.M)
+    if not m:
+        raise SystemExit(f"function {name} not found")
+    i = text.index("{", m.end())
+    depth, j = 0, i
+    while True:
+        c = text[j]
+        if c == "{":
+            depth += 1
+        elif c == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        j += 1
+    return text[m.start():j + 1]
+
+
+def extract_struct(text: str, name: str) -> str:
+    m = re.search(r"^struct\s+" + re.escape(name) + r"\s*\{", text, re.M)
+    j = text.index("};", m.end())
+    return text[m.start():j + 2]
+
+
+def extract_define(text: str, name: str) -> str:
+    m = re.search(r"^#define\s+" + re.escape(name) + r"\b.*$", text, re.M)
+    if not m:
+        raise SystemExit(f"#define {name} not found")
+    return m.group(0)
+
+
+def translate(code: str) -> str:
+    """GLSL -> C++ on the text (see glsl_shim.h for the list)."""
+    # comments may contain anything: drop them first
+    code = re.sub(r"//[^\n]*", "", code)
+    # float literals are 32-bit
+    code = re.sub(r"(?<![\w.])(\d+\.\d*|\.\d+)(?![\w.])", r"\1f", code)
+    # out / inout parameters are references
+    code = re.sub(r"\b(?:in\s+out|inout|out)\s+(\w+)\s+(\w+)", r"\1 &\2", code)
+    # the one swizzle that is written to
+    code = re.sub(r"(\w+(?:\[\d+\])?)\.xyz\s*\*=\s*([^;]+);", r"\1.mul_xyz(\2);", code)
+    # swizzles that are read
+    code = re.sub(r"\.(xyz|xzw|xy|zw)\b(?!\s*\()", r".\1()", code)
+    # conversions of floats to integers saturate
+    code = re.sub(r"(?<![\w.])int\(", "glsl_int(", code)
+    code = re.sub(r"(?<![\w.])uint\(", "glsl_uint(", code)
+    # uvec4(uvec3, <int-typed>) needs the explicit component type
+    code = code.replace("uvec4(floatBitsToUint(depth_eq), instance_flags_id)", "make_uvec4(floatBitsToUint(depth_eq), instance_flags_id)")
+    code = code.replace("uvec4(floatBitsToUint(scan), y_aabb)", "make_uvec4(floatBitsToUint(scan), y_aabb)")
+    code = code.replace("uvec4(floatBitsToUint(scan_step), x_signs | y_signs)", "make_uvec4(floatBitsToUint(scan_step), x_signs | y_signs)")
+    # ivec4(<uint scalar>) broadcast
+    code = re.sub(r"ivec4\((tri_mins|tri_maxs)\)", r"ivec4(glsl_int(\1))", code)
+    # GLSL array initialisers with a trailing comma and `{...}` are fine in C++; bool vector ctor as well
+    return code
+
+
+WRAPPER = r'''
+// ---- C ABI (ours): one emulated invocation per call ----------------------------------------------
+extern "C" {
+
+// LucidConfig as laid out in include/lucid_abi.h (352 bytes): frustum 12 x vec4, view_proj 4 x vec4,
+// lighting 4 x vec4, background vec4, enable_backface_culling at word 84
+static void loadConfig(const float *cfg352) {
+	// structures.glsl Frustum: ws_origins[4], ws_dirs[4], ws_origin0, ws_dir0, ws_dirx, ws_diry (vec4 each)
+	const float *f = cfg352;
+	u_config.frustum.ws_origin0 = vec4(f[32], f[33], f[34], f[35]);
+	u_config.frustum.ws_dir0 = vec4(f[36], f[37], f[38], f[39]);
+	u_config.frustum.ws_dirx = vec4(f[40], f[41], f[42], f[43]);
+	u_config.frustum.ws_diry = vec4(f[44], f[45], f[46], f[47]);
+	for(int c = 0; c < 4; c++)
+		u_config.view_proj_matrix.col[c] = vec4(f[48 + c * 4], f[49 + c * 4], f[50 + c * 4], f[51 + c * 4]);
+	u_config.enable_backface_culling = ((const int *)cfg352)[84];
+}
+
+// quad_setup.glsl: processInputQuad for one quad given by four positions.
+// out[0] status (-1 visible, else the rejection type), out[1] size type, out[2] enc_aabb,
+// out[3], out[4] the two triangles' y ranges
+void ref_process_quad(const float *cfg352, int width, int height, const float *pos12, const uint32_t *idx4,
+					  uint32_t *out) {
+	loadConfig(cfg352);
+	VIEWPORT_SIZE_X = width, VIEWPORT_SIZE_Y = height;
+	for(int i = 0; i < 12; i++)
+		g_verts[i] = pos12[i];
+	for(uint &r : s_rejected_quads)
+		r = 0;
+	s_num_visible[0] = s_num_visible[1] = 0;
+	processInputQuad(0, idx4[0], idx4[1], idx4[2], idx4[3], 0);
+	out[0] = 0xffffffffu, out[1] = 0, out[2] = out[3] = out[4] = 0;
+	for(int t = 0; t < REJECTION_TYPE_COUNT; t++)
+		if(s_rejected_quads[t])
+			out[0] = (uint32_t)t;
+	if(out[0] != 0xffffffffu)
+		return;
+	const int large = s_num_visible[1] != 0;
+	const int slot = large ? LSIZE - 1 : 0;
+	out[1] = (uint32_t)large, out[2] = s_quad_aabbs[slot];
+	out[3] = s_tri_y_aabbs[slot].x, out[4] = s_tri_y_aabbs[slot].y;
+}
+
+// quad_setup.glsl: storeTri for one camera-relative triangle; s_ray_dir0 as main() computes it
+// (dir0 + (dirx + diry) * 0.5).  out: bary 2 x uvec4, scan 2 x uvec4, depth uvec4, normal (21 words)
+void ref_store_tri(const float *cfg352, const float *tri9, uint32_t flags_id, uint32_t y_aabb, uint32_t *out) {
+	loadConfig(cfg352);
+	s_ray_dir0 = u_config.frustum.ws_dir0.xyz() + (u_config.frustum.ws_dirx.xyz() + u_config.frustum.ws_diry.xyz()) * 0.5f;
+	vec3 t0(tri9[0], tri9[1], tri9[2]), t1(tri9[3], tri9[4], tri9[5]), t2(tri9[6], tri9[7], tri9[8]);
+	g_normals_storage[0] = 0;
+	storeTri(0, flags_id, t0, t1, t2, y_aabb);
+	const uvec4 *src[5] = {&g_uvec4_storage[STORAGE_TRI_BARY_OFFSET], &g_uvec4_storage[STORAGE_TRI_BARY_OFFSET + 1],
+						   &g_uvec4_storage[STORAGE_TRI_SCAN_OFFSET], &g_uvec4_storage[STORAGE_TRI_SCAN_OFFSET + 1],
+						   &g_uvec4_storage[STORAGE_TRI_DEPTH_OFFSET]};
+	for(int i = 0; i < 5; i++)
+		out[i * 4 + 0] = src[i]->x, out[i * 4 + 1] = src[i]->y, out[i * 4 + 2] = src[i]->z, out[i * 4 + 3] = src[i]->w;
+	out[20] = g_normals_storage[0];
+}
+
+// scanline.glsl + raster.glsl: loadScanlineParamsRow at `start`, then `steps` calls of rasterBinStep.
+// out: 3 words (min_bits, max_bits, bx_mask) per step
+void ref_raster_rows(const uint32_t *scan8, float start_x, float start_y, int steps, uint32_t *out) {
+	uvec4 v0(scan8[0], scan8[1], scan8[2], scan8[3]), v1(scan8[4], scan8[5], scan8[6], scan8[7]);
+	ScanlineParams p = loadScanlineParamsRow(v0, v1, vec2(start_x, start_y));
+	for(int s = 0; s < steps; s++) {
+		uvec3 r = rasterBinStep(p);
+		out[s * 3 + 0] = r.x, out[s * 3 + 1] = r.y, out[s * 3 + 2] = r.z;
+	}
+}
+
+// scanline.glsl + bin_counter.glsl: loadScanlineParamsBin, then one scanlineStep per bin row.
+// out[0] min_by, out[1] max_by, then (bmin, bmax) per row
+void ref_bin_rows(const uint32_t *scan8, int32_t *out) {
+	uvec4 v0(scan8[0], scan8[1], scan8[2], scan8[3]), v1(scan8[4], scan8[5], scan8[6], scan8[7]);
+	int min_by, max_by;
+	ScanlineParams p = loadScanlineParamsBin(v0, v1, min_by, max_by);
+	out[0] = min_by, out[1] = max_by;
+	for(int by = min_by, i = 0; by <= max_by && i < 128; by++, i++) {
+		int bmin, bmax;
+		scanlineStep(p, bmin, bmax);
+		out[2 + i * 2] = bmin, out[3 + i * 2] = bmax;
+	}
+}
+
+// raster.glsl: centroid sums, fragment count, packed (xmin, count) bits of one half-block column and the
+// block depth key of a depth plane at a centroid.  out: cx bits, cy bits, num_frags, bits, depth
+void ref_half_block(uint32_t mins, uint32_t maxs, int startx, const float *depth_eq3, float cpx, float cpy,
+					float depth_range, uint32_t *out) {
+	uint nf = 0, nf2 = 0;
+	vec2 c = rasterHalfBlockCentroid(mins, maxs, startx, nf);
+	out[0] = floatBitsToUint(c.x), out[1] = floatBitsToUint(c.y), out[2] = nf;
+	out[3] = rasterHalfBlockBits(mins, maxs, startx, nf2);
+	g_uvec4_storage[STORAGE_TRI_DEPTH_OFFSET] = uvec4(floatBitsToUint(depth_eq3[0]), floatBitsToUint(depth_eq3[1]),
+													  floatBitsToUint(depth_eq3[2]), 0u);
+	out[4] = rasterBlockDepth(vec2(cpx, cpy), 0, depth_range);
+}
+
+} // extern "C"
+'''
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("--keep-source", action="store_true", help="leave the generated C++ in oracle/_ref/ for inspection")
+    args = ap.parse_args()
+    shaders = os.path.join(args.reference, "data", "shaders")
+    if not os.path.isdir(shaders):
+        raise SystemExit(f"{shaders} not found: the reference tree is only mounted in the build container")
+    out_dir = os.path.join(HERE, "_ref")
+    os.makedirs(out_dir, exist_ok=True)
+
+    parts = ['#include "../glsl_shim.h"', "using namespace glsl;", ""]
+    parts += ["// ---- specialisation constants (definitions.glsl CONSTANT(...)) as variables",
+              "static int VIEWPORT_SIZE_X = 1280, VIEWPORT_SIZE_Y = 720;",
+              "static const int BIN_SIZE = 32, BIN_SHIFT = 5, MAX_VISIBLE_QUADS = 1024;", ""]
+    parts.append("// ---- #define lines of the reference")
+    for rel, names in DEFINES.items():
+        text = open(os.path.join(shaders, rel), encoding="latin-1").read()
+        for n in names:
+            parts.append(translate(extract_define(text, n)))
+    parts += ["", "// ---- buffers, shared variables and the uniform block the functions refer to (ours)",
+              "struct Frustum { vec4 ws_origin0, ws_dir0, ws_dirx, ws_diry; };",
+              "struct Config { Frustum frustum; mat4 view_proj_matrix; int enable_backface_culling; };",
+              "static Config u_config;",
+              "static float g_verts[64];",
+              "static uvec4 g_uvec4_storage[MAX_VISIBLE_QUADS * 14];",
+              "static uint g_normals_storage[8];",
+              "static vec3 s_ray_dir0;",
+              "static uint s_rejected_quads[REJECTION_TYPE_COUNT];",
+              "static uint s_num_visible[2];",
+              "static uint s_quad_aabbs[LSIZE];",
+              "static uvec2 s_tri_y_aabbs[LSIZE];",
+              "static uvec4 s_quad_indices[LSIZE];", ""]
+    parts.append("// ---- reference text (translated)")
+    scan = open(os.path.join(shaders, "shared/scanline.glsl"), encoding="latin-1").read()
+    for rel, names in FUNCTIONS:
+        text = open(os.path.join(shaders, rel), encoding="latin-1").read()
+        if rel == "shared/scanline.glsl":
+            # `min` / `max` members of ScanlineParams shadow the functions only inside GLSL's rules
+            parts.append(translate(extract_struct(scan, "ScanlineParams")))
+        for n in names:
+            parts.append(f"// {rel}: {n}")
+            parts.append(translate(extract_function(text, n)))
+            parts.append("")
+    parts.append(WRAPPER)
+    src = os.path.join(out_dir, "ref_shader_funcs.cpp")
+    with open(src, "w") as f:
+        f.write("\n".join(parts))
+    so = os.path.join(out_dir, "libref_shaders.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3",
+           "-Wno-div-by-zero", "-o", so, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stderr[:6000])
+        raise SystemExit("g++ failed on the translated reference functions")
+    if not args.keep_source:
+        os.remove(src)
+    print(so)
+
+
+if __name__ == "__main__":
+    main()

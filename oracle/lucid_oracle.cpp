@@ -1450,6 +1450,69 @@ void *oracle_create(int width, int height, uint32_t opts, int max_visible_quads)
 }
 void oracle_destroy(void *h) { delete(Oracle *)h; }
 void oracle_set_threads(void *h, int n) { ((Oracle *)h)->num_threads = n < 1 ? 1 : n; }
+// ---- function-level entry points: the same functions the pipeline above calls, one invocation per
+// call, so tests can compare them with the reference's own shader functions compiled from the
+// reference tree (oracle/build_ref_shaders.py -> tests/golden/ref_shader_funcs.json)
+// out[0] status (0xffffffff visible, else rejection type) [1] size type [2] enc_aabb [3],[4] y ranges
+void oracle_fn_process_quad(void *h, const LucidConfig *cfg, const uint32_t *idx4, uint32_t *out) {
+	Oracle *o = (Oracle *)h;
+	o->cfg = *cfg;
+	SetupQuad s = processInputQuad(*o, idx4[0], idx4[1], idx4[2], idx4[3]);
+	out[0] = s.status < 0 ? 0xffffffffu : (uint32_t)s.status;
+	out[1] = out[2] = out[3] = out[4] = 0;
+	if(s.status < 0)
+		out[1] = (uint32_t)s.size_type, out[2] = s.enc_aabb, out[3] = s.y_aabb[0], out[4] = s.y_aabb[1];
+}
+// camera-relative triangle -> the 21 words of a triangle record (bary 2x4, scan 2x4, depth 4, normal)
+void oracle_fn_store_tri(void *h, const LucidConfig *cfg, const float *tri9, uint32_t flags_id, uint32_t y_aabb,
+						 uint32_t *out) {
+	Oracle *o = (Oracle *)h;
+	o->cfg = *cfg;
+	V3 dir0 = xyz(cfg->frustum.ws_dir0), dirx = xyz(cfg->frustum.ws_dirx), diry = xyz(cfg->frustum.ws_diry);
+	V3 ray_dir0 = dir0 + (dirx + diry) * 0.5f;
+	TriRecord t = storeTri(*o, flags_id, v3(tri9[0], tri9[1], tri9[2]), v3(tri9[3], tri9[4], tri9[5]),
+						   v3(tri9[6], tri9[7], tri9[8]), y_aabb, ray_dir0);
+	if(flags_id & LUCID_INST_HAS_VERTEX_NORMALS)
+		t.normal = 0;
+	memcpy(out + 0, &t.bary0, 16), memcpy(out + 4, &t.bary1, 16), memcpy(out + 8, &t.scan0, 16);
+	memcpy(out + 12, &t.scan1, 16), memcpy(out + 16, &t.depth, 16);
+	out[20] = t.normal;
+}
+static TriRecord scanRecord(const uint32_t *scan8) {
+	TriRecord t;
+	memset(&t, 0, sizeof(t));
+	memcpy(&t.scan0, scan8, 16), memcpy(&t.scan1, scan8 + 4, 16);
+	return t;
+}
+void oracle_fn_raster_rows(const uint32_t *scan8, float start_x, float start_y, int steps, uint32_t *out) {
+	RowScan r = loadScanRow(scanRecord(scan8), start_x, start_y);
+	for(int s = 0; s < steps; s++)
+		rasterBinStep(r, out[s * 3 + 0], out[s * 3 + 1], out[s * 3 + 2]);
+}
+void oracle_fn_bin_rows(const uint32_t *scan8, int32_t *out) {
+	int min_by, max_by;
+	ScanParams p = loadScanBin(scanRecord(scan8), min_by, max_by);
+	out[0] = min_by, out[1] = max_by;
+	for(int by = min_by, i = 0; by <= max_by && i < 128; by++, i++)
+		scanlineStepBin(p, out[2 + i * 2], out[3 + i * 2]);
+}
+// out: centroid sum x bits, y bits, fragments, packed (xmin & 7, count) rows, block depth
+void oracle_fn_half_block(uint32_t mins, uint32_t maxs, int startx, const float *depth_eq3, float cpx, float cpy,
+						  float depth_range, uint32_t *out) {
+	HalfSpans hs = halfSpans(mins, maxs, startx);
+	float cx, cy;
+	halfCentroid(hs, cx, cy);
+	out[0] = floatBits(cx), out[1] = floatBits(cy), out[2] = hs.num_frags;
+	u32 packed = 0;
+	for(int r = 0; r < 4; r++)
+		packed |= ((u32)(hs.xmin[r] & 7) << (7 * r)) | ((u32)hs.count[r] << (7 * r + 3));
+	out[3] = packed;
+	TriRecord t;
+	memset(&t, 0, sizeof(t));
+	t.depth.x = floatBits(depth_eq3[0]), t.depth.y = floatBits(depth_eq3[1]), t.depth.z = floatBits(depth_eq3[2]);
+	out[4] = blockDepth(t, cpx, cpy, depth_range);
+}
+
 void oracle_set_item_stats(void *h, int on) {
 	Oracle *o = (Oracle *)h;
 	o->collect_item_stats = on != 0;

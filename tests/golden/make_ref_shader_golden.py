@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Golden vectors from the reference's own shader functions.
+
+oracle/build_ref_shaders.py compiles processInputQuad, storeTri (quad_setup.glsl), loadScanlineParamsRow /
+loadScanlineParamsBin (shared/scanline.glsl), scanlineStep (bin_counter.glsl), rasterBinStep,
+rasterHalfBlockCentroid / Bits and rasterBlockDepth (shared/raster.glsl) from the GLSL text under
+/root/reference into oracle/_ref/libref_shaders.so.  This script feeds them seeded inputs and writes inputs
+and outputs to tests/golden/ref_shader_funcs.json; tests/test_ref_shader_pins.py replays the inputs through
+the CPU checker's functions (oracle_fn_*) and demands identical words.  Only runs where the reference tree
+is mounted (the build container); the JSON travels.
+
+    python oracle/build_ref_shaders.py && python tests/golden/make_ref_shader_golden.py
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from lucid_b200 import api  # noqa: E402
+
+lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_shaders.so"))
+vp = C.c_void_p
+lib.ref_process_quad.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+lib.ref_store_tri.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+lib.ref_raster_rows.argtypes = [vp, C.c_float, C.c_float, C.c_int, vp]
+lib.ref_bin_rows.argtypes = [vp, vp]
+lib.ref_half_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, vp, C.c_float, C.c_float, C.c_float, vp]
+
+
+def ptr(a):
+    return a.ctypes.data_as(vp)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32).tolist()
+
+
+rng = np.random.default_rng(20261017)
+cameras = [
+    ({"kind": "orbit", "center": [0.0, 0.0, 0.0], "distance": 30.0, "rot_h": 0.5, "rot_v": 0.8}, 1280, 720, 0),
+    ({"kind": "orbit", "center": [1.0, -2.0, 0.5], "distance": 12.0, "rot_h": 2.1, "rot_v": -0.4}, 1920, 1080, 1),
+    ({"kind": "orbit", "center": [0.0, 0.0, 0.0], "distance": 3.0, "rot_h": -1.0, "rot_v": 0.2}, 3840, 2160, 0),
+    ({"kind": "orbit", "center": [0.0, 0.0, 0.0], "distance": 0.6, "rot_h": 4.0, "rot_v": 1.1}, 640, 360, 0),
+]
+out = {"about": "outputs of the reference's shader functions (nadult/lucid data/shaders, compiled by "
+                "oracle/build_ref_shaders.py) on seeded inputs; floats are stored as their binary32 bit patterns",
+       "cases": []}
+n_visible = 0
+for cam_spec, width, height, backface in cameras:
+    cam = api.make_camera(cam_spec, width, height)
+    cfg = api.make_config(cam, 1, (0.0, 30.0 / 255.0, 30.0 / 255.0, 1.0))
+    cfg.enable_backface_culling = backface
+    cfg_words = np.frombuffer(bytes(cfg), np.uint32).copy()
+    origin = np.frombuffer(bytes(cfg), np.float32)[32:35].copy()
+    case = {"camera": cam_spec, "width": width, "height": height, "config_words": cfg_words.tolist(), "quads": []}
+    for k in range(70):
+        # a planar-ish quad of log-uniform size somewhere around the scene; every 7th close to the eye
+        # (near-plane crossers), every 11th degenerate
+        centre = rng.uniform(-8, 8, 3) if k % 7 else origin + rng.uniform(-0.4, 0.4, 3)
+        size = float(np.exp(rng.uniform(np.log(0.02), np.log(6.0))))
+        u, v = rng.normal(size=3), rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        v -= u * np.dot(u, v)
+        v /= np.linalg.norm(v)
+        pos = np.array([centre, centre + u * size, centre + (u + v) * size + rng.normal(size=3) * 0.01 * size,
+                        centre + v * size], np.float32)
+        idx = np.array([0, 1, 2, 3], np.uint32)
+        if k % 11 == 5:
+            idx[3] = idx[2]  # a triangle
+        if k % 11 == 9:
+            pos[1] = pos[0]  # coincident positions
+        res = np.zeros(5, np.uint32)
+        lib.ref_process_quad(ptr(cfg_words), width, height, ptr(pos), ptr(idx), ptr(res))
+        q = {"pos": bits(pos), "idx": idx.tolist(), "process_quad": res.tolist()}
+        if res[0] == 0xFFFFFFFF:
+            n_visible += 1
+            q["tris"] = []
+            for second in range(2):
+                if (int(res[2]) >> (30 + second)) & 1:
+                    continue
+                tri = np.array([pos[idx[0]] - origin, pos[idx[1 + second]] - origin, pos[idx[2 + second]] - origin], np.float32)
+                flags_id = (0x004 if k % 3 == 0 else 0x200) | (k << 16)
+                rec = np.zeros(21, np.uint32)
+                lib.ref_store_tri(ptr(cfg_words), ptr(tri), flags_id, int(res[3 + second]), ptr(rec))
+                t = {"second": second, "tri": bits(tri), "flags_id": flags_id, "y_aabb": int(res[3 + second]),
+                     "record": rec.tolist()}
+                scan8 = rec[8:16].copy()
+                # bin rows (binning) and pixel rows (raster) of the bins the triangle's y range touches
+                rows = np.zeros(2 + 256, np.int32)
+                lib.ref_bin_rows(ptr(scan8), ptr(rows))
+                n_rows = max(0, min(int(rows[1]) - int(rows[0]) + 1, 128))
+                t["bin_rows"] = rows[:2 + 2 * n_rows].tolist()
+                ymin = int(res[3 + second]) & 0xFFFF
+                bx0 = ((int(res[2]) >> 0) & 0x7F) * 32
+                t["raster_rows"] = []
+                for n_probe, start_y in enumerate(float((ymin // 32) * 32 + 4 * g) for g in (0, 5)):
+                    for start_x in ((float(bx0),) if n_probe else (float(bx0), float(bx0 + 32))):
+                        spans = np.zeros(6, np.uint32)
+                        lib.ref_raster_rows(ptr(scan8), start_x, start_y, 2, ptr(spans))
+                        hb = []
+                        startxs = (0, 8) if (k + second) % 2 else (16, 24)
+                        for startx in startxs:
+                            depth_eq = rec[16:19].view(np.float32).copy()
+                            cpx, cpy = np.float32(start_x + startx + 3.25), np.float32(start_y + 1.75)
+                            o5 = np.zeros(5, np.uint32)
+                            lib.ref_half_block(int(spans[0]), int(spans[1]), startx, ptr(depth_eq), float(cpx), float(cpy),
+                                               float(0x7FFFE if startx % 16 else 0x3FFFFE), ptr(o5))
+                            hb.append(o5.tolist())
+                        t["raster_rows"].append({"start": [start_x, start_y], "spans": spans.tolist(),
+                                                 "half_block_startx": list(startxs), "half_blocks": hb})
+                q["tris"].append(t)
+        case["quads"].append(q)
+    out["cases"].append(case)
+path = os.path.join(HERE, "ref_shader_funcs.json")
+with open(path, "w") as f:
+    json.dump(out, f, separators=(",", ":"))
+statuses = [q["process_quad"][0] for c in out["cases"] for q in c["quads"]]
+print(path, os.path.getsize(path), "bytes;", len(statuses), "quads,", n_visible, "visible; rejection types seen:",
+      sorted(set(s for s in statuses if s != 0xFFFFFFFF)))

@@ -1,0 +1,114 @@
+"""Pins of the CPU checker against the reference's own shader source.
+
+tests/golden/ref_shader_funcs.json holds the outputs of functions compiled from the GLSL text of the
+reference tree (oracle/build_ref_shaders.py: processInputQuad, storeTri, loadScanlineParams*, scanlineStep,
+rasterBinStep, rasterHalfBlockCentroid / Bits, rasterBlockDepth) on seeded inputs.  The checker's own
+functions (oracle_fn_* in oracle/lucid_oracle.cpp -- the ones its pipeline calls) must give the same words.
+These are the functions that decide coverage: which quads survive, their bin AABBs, the plane, barycentric
+and scanline equations, the bin-row and pixel-row spans, fragment counts, centroids and block depth keys.
+The CUDA kernels are compared with the checker by the GPU suite, so the pin carries over to them.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.binding import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+vp = C.c_void_p
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(os.path.join(HERE, "golden", "ref_shader_funcs.json")) as f:
+        return json.load(f)
+
+
+def ptr(a):
+    return a.ctypes.data_as(vp)
+
+
+def _lib(o):
+    lib = o.lib
+    lib.oracle_fn_process_quad.argtypes = [vp, vp, vp, vp]
+    lib.oracle_fn_store_tri.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp]
+    lib.oracle_fn_raster_rows.argtypes = [vp, C.c_float, C.c_float, C.c_int, vp]
+    lib.oracle_fn_bin_rows.argtypes = [vp, vp]
+    lib.oracle_fn_half_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, vp, C.c_float, C.c_float, C.c_float, vp]
+    return lib
+
+
+def test_checker_functions_match_the_reference_shader_functions(golden):
+    counts = {"quads": 0, "visible": 0, "tris": 0, "bin_rows": 0, "raster_rows": 0, "half_blocks": 0}
+    for case in golden["cases"]:
+        o = Oracle(case["width"], case["height"], 0, 1 << 16, threads=1)
+        lib = _lib(o)
+        cfg = np.array(case["config_words"], np.uint32)
+        try:
+            for q in case["quads"]:
+                pos = np.array(q["pos"], np.uint32).view(np.float32).reshape(4, 3)
+                idx = np.array(q["idx"], np.uint32)
+                o.set_scene({"positions": pos, "quads": idx.reshape(1, 4)})
+                res = np.zeros(5, np.uint32)
+                lib.oracle_fn_process_quad(o.h, ptr(cfg), ptr(idx), ptr(res))
+                assert res.tolist() == q["process_quad"], ("processInputQuad", q["pos"], res.tolist(), q["process_quad"])
+                counts["quads"] += 1
+                for t in q.get("tris", []):
+                    counts["visible"] += t["second"] == 0
+                    tri = np.array(t["tri"], np.uint32).view(np.float32)
+                    rec = np.zeros(21, np.uint32)
+                    lib.oracle_fn_store_tri(o.h, ptr(cfg), ptr(tri), t["flags_id"], t["y_aabb"], ptr(rec))
+                    assert rec.tolist() == t["record"], ("storeTri", t["tri"], rec.tolist(), t["record"])
+                    counts["tris"] += 1
+                    scan8 = rec[8:16].copy()
+                    rows = np.zeros(2 + 256, np.int32)
+                    lib.oracle_fn_bin_rows(ptr(scan8), ptr(rows))
+                    assert rows[:len(t["bin_rows"])].tolist() == t["bin_rows"], ("bin rows", t["record"][8:16])
+                    counts["bin_rows"] += (len(t["bin_rows"]) - 2) // 2
+                    for rr in t["raster_rows"]:
+                        spans = np.zeros(6, np.uint32)
+                        lib.oracle_fn_raster_rows(ptr(scan8), rr["start"][0], rr["start"][1], 2, ptr(spans))
+                        assert spans.tolist() == rr["spans"], ("rasterBinStep", rr["start"], t["record"][8:16])
+                        counts["raster_rows"] += 8
+                        for startx, want in zip(rr["half_block_startx"], rr["half_blocks"]):
+                            depth_eq = rec[16:19].view(np.float32).copy()
+                            cpx, cpy = np.float32(rr["start"][0] + startx + 3.25), np.float32(rr["start"][1] + 1.75)
+                            o5 = np.zeros(5, np.uint32)
+                            lib.oracle_fn_half_block(int(spans[0]), int(spans[1]), startx, ptr(depth_eq), float(cpx), float(cpy),
+                                                     float(0x7FFFE if startx % 16 else 0x3FFFFE), ptr(o5))
+                            assert o5.tolist() == want, ("half block", startx, spans.tolist(), o5.tolist(), want)
+                            counts["half_blocks"] += 1
+        finally:
+            o.close()
+    # the vectors exercise every path: rejections of all kinds but "other", large and small quads
+    assert counts["quads"] >= 200 and counts["tris"] >= 150 and counts["half_blocks"] >= 1000, counts
+    statuses = {q["process_quad"][0] for c in golden["cases"] for q in c["quads"]}
+    assert {1, 2, 3, 0xFFFFFFFF} <= statuses
+    sizes = {q["process_quad"][1] for c in golden["cases"] for q in c["quads"] if q["process_quad"][0] == 0xFFFFFFFF}
+    assert sizes == {0, 1}
+
+
+def test_reference_library_matches_golden_when_available(golden):
+    """Where the reference tree is mounted and oracle/_ref/libref_shaders.so is built, the library itself
+    reproduces the committed vectors (guards against a stale JSON)."""
+    path = os.path.join(HERE, "..", "oracle", "_ref", "libref_shaders.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_shaders.so not built (needs /root/reference)")
+    lib = C.CDLL(path)
+    lib.ref_process_quad.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.ref_store_tri.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
+    for case in golden["cases"]:
+        cfg = np.array(case["config_words"], np.uint32)
+        for q in case["quads"]:
+            pos = np.array(q["pos"], np.uint32)
+            idx = np.array(q["idx"], np.uint32)
+            res = np.zeros(5, np.uint32)
+            lib.ref_process_quad(ptr(cfg), case["width"], case["height"], ptr(pos), ptr(idx), ptr(res))
+            assert res.tolist() == q["process_quad"]
+            for t in q.get("tris", []):
+                rec = np.zeros(21, np.uint32)
+                lib.ref_store_tri(ptr(cfg), ptr(np.array(t["tri"], np.uint32)), t["flags_id"], t["y_aabb"], ptr(rec))
+                assert rec.tolist() == t["record"]
