@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 # (file under data/shaders, function names in the order they are emitted)
 FUNCTIONS = [
-    ("shared/funcs.glsl", ["encodeNormalUint", "encodeAABB28", "decodeAABB28"]),
+    ("shared/funcs.glsl", ["encodeNormalUint", "encodeAABB28", "decodeAABB28", "decodeRGBA8", "encodeRGBA8"]),
     ("quad_setup.glsl", ["vertexLoad", "vertexClipMask", "computeClippedAABB", "computeAABB", "processInputQuad", "storeTri"]),
     ("shared/scanline.glsl", ["loadScanlineParamsRow", "loadScanlineParamsBin"]),
     ("bin_counter.glsl", ["scanlineStep"]),
@@ -85,6 +85,9 @@ def translate(code: str) -> str:
     code = re.sub(r"(\w+(?:\[\d+\])?)\.xyz\s*\*=\s*([^;]+);", r"\1.mul_xyz(\2);", code)
     # swizzles that are read
     code = re.sub(r"\.(xyz|xzw|xy|zw)\b(?!\s*\()", r".\1()", code)
+    # colour names of components
+    code = re.sub(r"\.rgb\b", ".xyz()", code)
+    code = re.sub(r"\.([rgba])\b", lambda m: "." + "xyzw"["rgba".index(m.group(1))], code)
     # conversions of floats to integers saturate
     code = re.sub(r"(?<![\w.])int\(", "glsl_int(", code)
     code = re.sub(r"(?<![\w.])uint\(", "glsl_uint(", code)
@@ -113,6 +116,7 @@ static void loadConfig(const float *cfg352) {
 	u_config.frustum.ws_diry = vec4(f[44], f[45], f[46], f[47]);
 	for(int c = 0; c < 4; c++)
 		u_config.view_proj_matrix.col[c] = vec4(f[48 + c * 4], f[49 + c * 4], f[50 + c * 4], f[51 + c * 4]);
+	u_config.background_color = vec4(f[80], f[81], f[82], f[83]);
 	u_config.enable_backface_culling = ((const int *)cfg352)[84];
 }
 
@@ -195,6 +199,23 @@ void ref_half_block(uint32_t mins, uint32_t maxs, int startx, const float *depth
 	out[4] = rasterBlockDepth(vec2(cpx, cpy), 0, depth_range);
 }
 
+// shading.glsl: one pixel's reduction over n (colour, depth bits) samples in stream order, fed in rounds
+// of 32 like shadeAndReduceSamples does (raster.glsl:358-396); out: r, g, b, a as binary32 bits
+void ref_reduce_pixel(const float *cfg352, const uint32_t *samples, int n, uint32_t *out) {
+	loadConfig(cfg352);
+	ReductionContext ctx;
+	initReduceSamples(ctx);
+	for(int i = 0; i < n; i += 32) {
+		const int m = n - i < 32 ? n - i : 32;
+		for(int j = 0; j < m; j++)
+			g_lane_samples[j] = uvec2(samples[2 * (i + j)], samples[2 * (i + j) + 1]);
+		reduceSample(ctx, ctx.out_color, g_lane_samples[0], m == 32 ? 0xffffffffu : (1u << m) - 1u);
+	}
+	vec4 r = finishReduceSamples(ctx);
+	out[0] = floatBitsToUint(r.x), out[1] = floatBitsToUint(r.y), out[2] = floatBitsToUint(r.z), out[3] = floatBitsToUint(r.w);
+}
+uint32_t ref_encode_rgba8(const float *rgba) { return encodeRGBA8(vec4(rgba[0], rgba[1], rgba[2], rgba[3])); }
+
 } // extern "C"
 '''
 
@@ -221,7 +242,7 @@ def main():
             parts.append(translate(extract_define(text, n)))
     parts += ["", "// ---- buffers, shared variables and the uniform block the functions refer to (ours)",
               "struct Frustum { vec4 ws_origin0, ws_dir0, ws_dirx, ws_diry; };",
-              "struct Config { Frustum frustum; mat4 view_proj_matrix; int enable_backface_culling; };",
+              "struct Config { Frustum frustum; mat4 view_proj_matrix; vec4 background_color; int enable_backface_culling; };",
               "static Config u_config;",
               "static float g_verts[64];",
               "static uvec4 g_uvec4_storage[MAX_VISIBLE_QUADS * 14];",
@@ -243,6 +264,18 @@ def main():
             parts.append(f"// {rel}: {n}")
             parts.append(translate(extract_function(text, n)))
             parts.append("")
+    # shared/shading.glsl: the per-pixel reduction (3-entry insertion window, blending, final colour), from
+    # its RC_* defines to the end of finishReduceSamples, for one emulated lane: the subgroup operations
+    # become "this lane" / a lookup in the 32 samples of the round
+    shading = open(os.path.join(shaders, "shared/shading.glsl"), encoding="latin-1").read()
+    a = shading.index("#define RC_COLOR_SIZE 3")
+    fin = extract_function(shading, "finishReduceSamples")
+    b = shading.index(fin) + len(fin)
+    parts += ["// shared/shading.glsl: ReductionContext, swap, initReduceSamples, reduceSample, finishReduceSamples",
+              "#define SUBGROUP_SIZE 32", "#define HALFGROUP_SIZE 32",
+              "static uvec2 g_lane_samples[32];",
+              "#define subgroupAny(x) (x)", "#define subgroupShuffle(v, lane) g_lane_samples[lane]",
+              translate(shading[a:b]), ""]
     parts.append(WRAPPER)
     src = os.path.join(out_dir, "ref_shader_funcs.cpp")
     with open(src, "w") as f:

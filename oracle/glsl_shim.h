@@ -195,6 +195,18 @@ inline vec4 operator*(const mat4 &m, const vec4 &v) {
 	return r;
 }
 
+inline vec3 clamp(const vec3 &v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
+inline int bitCount(uint v) { return __builtin_popcount(v); }
+inline int findLSB(uint v) { return v == 0 ? -1 : __builtin_ctz(v); }
+inline void swap(float &a, float &b) {
+	float t = a;
+	a = b, b = t;
+}
+inline void swap(uint &a, uint &b) {
+	uint t = a;
+	a = b, b = t;
+}
+
 // shared-memory atomics of a single emulated invocation
 inline uint atomicAdd(uint &mem, uint v) {
 	uint old = mem;

@@ -4,12 +4,23 @@
 // this file; it exists so tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can
 // check the CUDA path and time a CPU baseline.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or fixtures for the
-// renderer and its own implementation (GLSL compute on Vulkan) cannot run in
-// this image (no Vulkan ICD, no shaderc).  The pins we do have are the reference's runtime
-// invariants (verifyInfo, sortedness, stats[2]), closed-form scenes, an independent brute-force
-// rasteriser in tests/, and -- for the host-side camera/frustum math only -- the reference's own
-// libfwk sources compiled into oracle/_ref (see oracle/Makefile).
+// PARITY: the reference ships no golden vectors, known-answer tests or fixtures for the renderer
+//  and its own implementation (GLSL compute on Vulkan) cannot run in this image
+// (no Vulkan ICD, no shaderc).  What pins this file:
+//   * PINNED against outputs of the reference's own source: the functions that decide coverage and
+//     blending -- processInputQuad, storeTri (quad_setup.glsl), loadScanlineParamsRow / Bin
+//     (scanline.glsl), scanlineStep (bin_counter.glsl), rasterBinStep, rasterHalfBlockCentroid / Bits,
+//     rasterBlockDepth (raster.glsl), initReduceSamples / reduceSample / finishReduceSamples
+//     (shading.glsl), encodeRGBA8 (funcs.glsl) -- are compiled from the GLSL text where it lies
+//     (oracle/build_ref_shaders.py, oracle/glsl_shim.h -> oracle/_ref/libref_shaders.so), run on seeded
+//     inputs (tests/golden/make_ref_shader_golden.py -> tests/golden/ref_shader_funcs.json) and the
+//     oracle_fn_* entry points below must reproduce every word (tests/test_ref_shader_pins.py);
+//     the host-side camera / frustum math is pinned the same way against libfwk (oracle/Makefile ref);
+//   * UNPINNED (no reference output obtainable): the colour arithmetic of shadeSample (driver pow,
+//     the Vulkan sampler's filtering: DESIGN.md sections 4 and 9), and the control structure around the
+//     pinned functions (work distribution, list orders from racing atomics, the block sort), which
+//     rest on the reference's runtime invariants (verifyInfo, sortedness, stats[2]), closed-form
+//     scenes and an independent brute-force rasteriser in tests/.
 //
 // What is restated (file:line under /root/reference):
 //   quad setup      data/shaders/quad_setup.glsl:64-489
@@ -1511,6 +1522,22 @@ void oracle_fn_half_block(uint32_t mins, uint32_t maxs, int startx, const float 
 	memset(&t, 0, sizeof(t));
 	t.depth.x = floatBits(depth_eq3[0]), t.depth.y = floatBits(depth_eq3[1]), t.depth.z = floatBits(depth_eq3[2]);
 	out[4] = blockDepth(t, cpx, cpy, depth_range);
+}
+
+// one pixel's reduction over n (colour, depth bits) samples in stream order; out: r, g, b, a bits
+void oracle_fn_reduce_pixel(const LucidConfig *cfg, const uint32_t *samples, int n, uint32_t *out) {
+	Reducer red;
+	red.init(false);
+	for(int i = 0; i < n; i++)
+		red.push(samples[2 * i], bitsToFloat(samples[2 * i + 1]), false);
+	float rgb[3];
+	red.finish(cfg->background_color, rgb);
+	out[0] = floatBits(rgb[0]), out[1] = floatBits(rgb[1]), out[2] = floatBits(rgb[2]), out[3] = floatBits(1.0f);
+}
+uint32_t oracle_fn_encode_rgba8(const float *rgba) {
+	V4 c;
+	c.x = rgba[0], c.y = rgba[1], c.z = rgba[2], c.w = rgba[3];
+	return encodeRGBA8(c);
 }
 
 void oracle_set_item_stats(void *h, int on) {

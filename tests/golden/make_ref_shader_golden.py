@@ -30,6 +30,9 @@ lib.ref_store_tri.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
 lib.ref_raster_rows.argtypes = [vp, C.c_float, C.c_float, C.c_int, vp]
 lib.ref_bin_rows.argtypes = [vp, vp]
 lib.ref_half_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, vp, C.c_float, C.c_float, C.c_float, vp]
+lib.ref_reduce_pixel.argtypes = [vp, vp, C.c_int, vp]
+lib.ref_encode_rgba8.argtypes = [vp]
+lib.ref_encode_rgba8.restype = C.c_uint32
 
 
 def ptr(a):
@@ -116,6 +119,39 @@ for cam_spec, width, height, backface in cameras:
                 q["tris"].append(t)
         case["quads"].append(q)
     out["cases"].append(case)
+# shading.glsl: per-pixel reduction (3-entry insertion window + front-to-back blending) on sample streams
+# that are sorted near to far (larger inverse depth first) up to local inversions, as the block sort leaves them
+out["reduce"] = []
+cfg_words = np.array(out["cases"][0]["config_words"], np.uint32)
+for k in range(60):
+    n = int(rng.integers(0, 90))
+    depth = np.sort(rng.uniform(0.01, 4.0, n).astype(np.float32))[::-1].copy()
+    for _ in range(n // 4):  # local inversions, mostly within the window's reach, sometimes beyond it
+        i = int(rng.integers(0, max(n - 1, 1)))
+        j = min(n - 1, i + int(rng.choice([1, 1, 2, 2, 3, 5])))
+        depth[i], depth[j] = depth[j], depth[i]
+    if n > 4 and k % 5 == 0:
+        depth[2] = depth[1]  # equal depths
+    colour = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    alpha_kind = rng.integers(0, 6, n)
+    colour[alpha_kind == 0] |= 0xFF000000  # opaque
+    colour[alpha_kind == 1] &= 0x00FFFFFF  # alpha 0 but colour bits set
+    if n > 2 and k % 7 == 0:
+        colour[1] = 0  # "no sample" (shadeSample returned 0)
+    samples = np.empty(2 * n, np.uint32)
+    samples[0::2], samples[1::2] = colour, depth.view(np.uint32)
+    o4 = np.zeros(4, np.uint32)
+    lib.ref_reduce_pixel(ptr(cfg_words), ptr(samples), n, ptr(o4))
+    out["reduce"].append({"samples": samples.tolist(), "rgba": o4.tolist()})
+out["encode_rgba8"] = []
+for k in range(64):
+    c = rng.uniform(0.0, 1.0, 4).astype(np.float32)
+    if k % 8 == 0:
+        c[k % 4] = np.float32(1.0)
+    if k % 8 == 4:
+        c[k % 4] = np.float32((k + 1) / 255.0)  # exactly on a step
+    out["encode_rgba8"].append({"rgba": bits(c), "packed": int(lib.ref_encode_rgba8(ptr(c)))})
+
 path = os.path.join(HERE, "ref_shader_funcs.json")
 with open(path, "w") as f:
     json.dump(out, f, separators=(",", ":"))

@@ -91,6 +91,31 @@ def test_checker_functions_match_the_reference_shader_functions(golden):
     assert sizes == {0, 1}
 
 
+def test_checker_reduction_and_codec_match_the_reference(golden):
+    """shading.glsl initReduceSamples / reduceSample / finishReduceSamples (3-entry insertion window, blending,
+    background) and funcs.glsl encodeRGBA8 against the checker's Reducer and codec, bit for bit."""
+    o = Oracle(64, 64, 0, 1 << 10, threads=1)
+    lib = o.lib
+    lib.oracle_fn_reduce_pixel.argtypes = [vp, vp, C.c_int, vp]
+    lib.oracle_fn_encode_rgba8.argtypes = [vp]
+    lib.oracle_fn_encode_rgba8.restype = C.c_uint32
+    cfg = np.array(golden["cases"][0]["config_words"], np.uint32)
+    try:
+        longest = 0
+        for r in golden["reduce"]:
+            samples = np.array(r["samples"], np.uint32)
+            o4 = np.zeros(4, np.uint32)
+            lib.oracle_fn_reduce_pixel(ptr(cfg), ptr(samples), samples.size // 2, ptr(o4))
+            assert o4.tolist() == r["rgba"], (samples.size // 2, o4.tolist(), r["rgba"])
+            longest = max(longest, samples.size // 2)
+        assert len(golden["reduce"]) >= 50 and longest > 64  # more than two rounds of 32
+        for e in golden["encode_rgba8"]:
+            c = np.array(e["rgba"], np.uint32)
+            assert int(lib.oracle_fn_encode_rgba8(ptr(c))) == e["packed"]
+    finally:
+        o.close()
+
+
 def test_reference_library_matches_golden_when_available(golden):
     """Where the reference tree is mounted and oracle/_ref/libref_shaders.so is built, the library itself
     reproduces the committed vectors (guards against a stale JSON)."""
