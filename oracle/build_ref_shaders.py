@@ -24,17 +24,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 # (file under data/shaders, function names in the order they are emitted)
 FUNCTIONS = [
-    ("shared/funcs.glsl", ["encodeNormalUint", "encodeAABB28", "decodeAABB28", "decodeRGBA8", "encodeRGBA8"]),
+    ("shared/funcs.glsl", ["encodeNormalUint", "encodeAABB28", "decodeAABB28", "decodeNormalUint", "decodeRGBA8", "encodeRGBA8",
+                           "linearToSRGB", "SRGBToLinear", "finalShading"]),
     ("quad_setup.glsl", ["vertexLoad", "vertexClipMask", "computeClippedAABB", "computeAABB", "processInputQuad", "storeTri"]),
     ("shared/scanline.glsl", ["loadScanlineParamsRow", "loadScanlineParamsBin"]),
     ("bin_counter.glsl", ["scanlineStep"]),
     ("shared/raster.glsl", ["rasterBinStep", "rasterHalfBlockCentroid", "rasterHalfBlockBits", "rasterBlockDepth"]),
+    ("shared/shading.glsl", ["getTriangleParams", "getTriangleVertexColors", "getTriangleVertexNormals",
+                             "getTriangleVertexTexCoords", "shadeSample"]),
 ]
 # #define lines taken over from the reference (name -> file)
 DEFINES = {
     "shared/definitions.glsl": ["REJECTION_TYPE_COUNT", "REJECTION_TYPE_OTHER", "REJECTION_TYPE_BACKFACE",
                                 "REJECTION_TYPE_FRUSTUM", "REJECTION_TYPE_BETWEEN_SAMPLES", "INST_HAS_VERTEX_NORMALS",
-                                "STORAGE_TRI_BARY_OFFSET", "STORAGE_TRI_SCAN_OFFSET", "STORAGE_TRI_DEPTH_OFFSET"],
+                                "INST_HAS_VERTEX_COLORS", "INST_TEX_OPAQUE", "INST_HAS_UV_RECT", "INST_HAS_ALBEDO_TEXTURE",
+                                "INST_HAS_COLOR",
+                                "STORAGE_TRI_BARY_OFFSET", "STORAGE_TRI_SCAN_OFFSET", "STORAGE_TRI_DEPTH_OFFSET",
+                                "STORAGE_QUAD_COLOR_OFFSET", "STORAGE_QUAD_NORMAL_OFFSET", "STORAGE_QUAD_TEXTURE_OFFSET"],
     "shared/funcs.glsl": ["SATURATE"],
     "quad_setup.glsl": ["MAX_INSTANCE_QUADS", "LSIZE"],
     "shared/raster.glsl": ["BIN_MASK", "HBLOCK_WIDTH", "HBLOCK_WIDTH_SHIFT", "HBLOCK_COLS", "HBLOCK_COLS_SHIFT",
@@ -85,7 +91,8 @@ def translate(code: str) -> str:
     code = re.sub(r"(\w+(?:\[\d+\])?)\.xyz\s*\*=\s*([^;]+);", r"\1.mul_xyz(\2);", code)
     # swizzles that are read
     code = re.sub(r"\.(xyz|xzw|xy|zw)\b(?!\s*\()", r".\1()", code)
-    # colour names of components
+    # colour names of components; the one colour swizzle that is assigned to
+    code = re.sub(r"(\w+)\.rgb\s*=(?!=)\s*([^;]+);", r"\1.set_xyz(\2);", code)
     code = re.sub(r"\.rgb\b", ".xyz()", code)
     code = re.sub(r"\.([rgba])\b", lambda m: "." + "xyzw"["rgba".index(m.group(1))], code)
     # conversions of floats to integers saturate
@@ -116,6 +123,11 @@ static void loadConfig(const float *cfg352) {
 	u_config.frustum.ws_diry = vec4(f[44], f[45], f[46], f[47]);
 	for(int c = 0; c < 4; c++)
 		u_config.view_proj_matrix.col[c] = vec4(f[48 + c * 4], f[49 + c * 4], f[50 + c * 4], f[51 + c * 4]);
+	// structures.glsl Lighting: ambient_color, sun_color, sun_dir, sun_power, ambient_power (64 bytes)
+	u_config.lighting.ambient_color = vec4(f[64], f[65], f[66], f[67]);
+	u_config.lighting.sun_color = vec4(f[68], f[69], f[70], f[71]);
+	u_config.lighting.sun_dir = vec4(f[72], f[73], f[74], f[75]);
+	u_config.lighting.sun_power = f[76], u_config.lighting.ambient_power = f[77];
 	u_config.background_color = vec4(f[80], f[81], f[82], f[83]);
 	u_config.enable_backface_culling = ((const int *)cfg352)[84];
 }
@@ -214,6 +226,33 @@ void ref_reduce_pixel(const float *cfg352, const uint32_t *samples, int n, uint3
 	vec4 r = finishReduceSamples(ctx);
 	out[0] = floatBitsToUint(r.x), out[1] = floatBitsToUint(r.y), out[2] = floatBitsToUint(r.z), out[3] = floatBitsToUint(r.w);
 }
+// shading.glsl: shadeSample of triangle `second` of one quad.  rec21: the triangle's record (bary 2x4, scan 2x4,
+// depth 4, normal); attrs16: the quad's colours, normals, uv0, uv1; the texture fetch returns tex_preset.
+// out: colour, depth bits, 6 textureGrad argument bits (coord, dx, dy), texture slot, fetch-happened flag
+void ref_shade_sample(const float *cfg352, const uint32_t *rec21, const uint32_t *attrs16, uint32_t inst_color,
+					  const float *uv_rect4, const float *tex_preset4, int px, int py, int second, uint32_t *out) {
+	loadConfig(cfg352);
+	const uint tri = (uint)second;
+	for(int i = 0; i < 2; i++)
+		g_uvec4_storage[STORAGE_TRI_BARY_OFFSET + tri * 2 + i] = uvec4(rec21[i * 4], rec21[i * 4 + 1], rec21[i * 4 + 2], rec21[i * 4 + 3]);
+	g_uvec4_storage[STORAGE_TRI_DEPTH_OFFSET + tri] = uvec4(rec21[16], rec21[17], rec21[18], rec21[19]);
+	g_normals_storage[tri] = rec21[20];
+	g_uvec4_storage[STORAGE_QUAD_COLOR_OFFSET] = uvec4(attrs16[0], attrs16[1], attrs16[2], attrs16[3]);
+	g_uvec4_storage[STORAGE_QUAD_NORMAL_OFFSET] = uvec4(attrs16[4], attrs16[5], attrs16[6], attrs16[7]);
+	g_uvec4_storage[STORAGE_QUAD_TEXTURE_OFFSET] = uvec4(attrs16[8], attrs16[9], attrs16[10], attrs16[11]);
+	g_uvec4_storage[STORAGE_QUAD_TEXTURE_OFFSET + 1] = uvec4(attrs16[12], attrs16[13], attrs16[14], attrs16[15]);
+	const uint instance_id = rec21[19] >> 16;
+	g_instance_colors[instance_id & 255] = inst_color;
+	g_instance_uv_rects[instance_id & 255] = vec4(uv_rect4[0], uv_rect4[1], uv_rect4[2], uv_rect4[3]);
+	g_tex_preset = vec4(tex_preset4[0], tex_preset4[1], tex_preset4[2], tex_preset4[3]);
+	for(float &a : g_tex_args)
+		a = 0.0f;
+	float depth = 0.0f;
+	out[0] = shadeSample(ivec2(px, py), tri, depth);
+	out[1] = floatBitsToUint(depth);
+	for(int i = 0; i < 8; i++)
+		out[2 + i] = floatBitsToUint(g_tex_args[i]);
+}
 uint32_t ref_encode_rgba8(const float *rgba) { return encodeRGBA8(vec4(rgba[0], rgba[1], rgba[2], rgba[3])); }
 
 } // extern "C"
@@ -242,7 +281,18 @@ def main():
             parts.append(translate(extract_define(text, n)))
     parts += ["", "// ---- buffers, shared variables and the uniform block the functions refer to (ours)",
               "struct Frustum { vec4 ws_origin0, ws_dir0, ws_dirx, ws_diry; };",
-              "struct Config { Frustum frustum; mat4 view_proj_matrix; vec4 background_color; int enable_backface_culling; };",
+              "struct Lighting { vec4 ambient_color, sun_color, sun_dir; float sun_power, ambient_power; };",
+              "struct Config { Frustum frustum; mat4 view_proj_matrix; Lighting lighting; vec4 background_color; int enable_backface_culling; };",
+              "static uint g_instance_colors[256];",
+              "static vec4 g_instance_uv_rects[256];",
+              "// the Vulkan sampler is not part of the source: textureGrad records its arguments and returns a preset colour",
+              "static int opaque_texture = 0, transparent_texture = 1;",
+              "static vec4 g_tex_preset; static float g_tex_args[8];",
+              "static vec4 textureGrad(int which, vec2 c, vec2 dx, vec2 dy) {",
+              "	g_tex_args[0] = c.x, g_tex_args[1] = c.y, g_tex_args[2] = dx.x, g_tex_args[3] = dx.y, g_tex_args[4] = dy.x, g_tex_args[5] = dy.y;",
+              "	g_tex_args[6] = float(which), g_tex_args[7] = 1.0f;",
+              "	return g_tex_preset;",
+              "}",
               "static Config u_config;",
               "static float g_verts[64];",
               "static uvec4 g_uvec4_storage[MAX_VISIBLE_QUADS * 14];",

@@ -80,6 +80,7 @@ template <class T> struct tvec4 {
 	tvec2<T> xy() const { return tvec2<T>(x, y); }
 	tvec2<T> zw() const { return tvec2<T>(z, w); }
 	void mul_xyz(T s) { x *= s, y *= s, z *= s; }
+	void set_xyz(const tvec3<T> &v) { x = v.x, y = v.y, z = v.z; }
 };
 // conversions between component types: float -> uint / int saturate, everything else is a plain cast
 template <class T, class U> inline T convertComponent(U v) { return (T)v; }
@@ -126,7 +127,9 @@ GLSL_VEC_OPS(tvec2, 2, E2_2, ES_2)
 GLSL_VEC_OPS(tvec3, 3, E2_3, ES_3)
 GLSL_VEC_OPS(tvec4, 4, E2_4, ES_4)
 
+template <class T> inline tvec2<T> operator*(T s, const tvec2<T> &a) { return a * s; }
 template <class T> inline tvec3<T> operator*(T s, const tvec3<T> &a) { return a * s; }
+template <class T> inline tvec4<T> operator*(T s, const tvec4<T> &a) { return a * s; }
 template <class T> inline tvec3<T> operator-(const tvec3<T> &a) { return tvec3<T>(-a.x, -a.y, -a.z); }
 // GLSL's == on vectors is "all components equal"
 template <class T> inline bool operator==(const tvec3<T> &a, const tvec3<T> &b) {
@@ -176,6 +179,8 @@ inline float uintBitsToFloat(uint u) {
 	memcpy(&f, &u, 4);
 	return f;
 }
+inline vec2 uintBitsToFloat(const uvec2 &v) { return vec2(uintBitsToFloat(v.x), uintBitsToFloat(v.y)); }
+inline vec2 fract(const vec2 &v) { return vec2(v.x - std::floor(v.x), v.y - std::floor(v.y)); }
 inline uvec3 floatBitsToUint(const vec3 &v) { return uvec3(floatBitsToUint(v.x), floatBitsToUint(v.y), floatBitsToUint(v.z)); }
 inline uvec4 floatBitsToUint(const vec4 &v) {
 	return uvec4(floatBitsToUint(v.x), floatBitsToUint(v.y), floatBitsToUint(v.z), floatBitsToUint(v.w));
@@ -205,6 +210,46 @@ inline void swap(float &a, float &b) {
 inline void swap(uint &a, uint &b) {
 	uint t = a;
 	a = b, b = t;
+}
+
+// pow: driver-defined in GLSL.  This is the polynomial contract of DESIGN.md section 4 (the same
+// definition as orc_pow in lucid_oracle.cpp and pow_poly in lucid_b200/csrc/common.cuh): what the pin of
+// shadeSample covers is the reference's arithmetic *around* pow, not pow itself.
+inline float contract_log2(float x) {
+	uint ix = floatBitsToUint(x);
+	int e = (int)(ix - 0x3f3504f3u) >> 23;
+	float m = uintBitsToFloat(ix - ((uint)e << 23));
+	float f = m - 1.0f;
+	float p = -0.146203533f;
+	p = fmaf(p, f, 0.23420985f);
+	p = fmaf(p, f, -0.24882181f);
+	p = fmaf(p, f, 0.287075609f);
+	p = fmaf(p, f, -0.360241979f);
+	p = fmaf(p, f, 0.48092404f);
+	p = fmaf(p, f, -0.721352756f);
+	p = fmaf(p, f, 1.4426949f);
+	return fmaf(p, f, (float)e);
+}
+inline float contract_exp2(float t) {
+	float n = std::floor(t + 0.5f);
+	float r = t - n;
+	float p = 0.00134004327f;
+	p = fmaf(p, r, 0.00967603736f);
+	p = fmaf(p, r, 0.0555032715f);
+	p = fmaf(p, r, 0.240221068f);
+	p = fmaf(p, r, 0.693147182f);
+	p = fmaf(p, r, 1.0f);
+	int ni = glsl_int(n);
+	if(ni < -126)
+		return 0.0f;
+	if(ni > 127)
+		ni = 127;
+	return uintBitsToFloat(floatBitsToUint(p) + ((uint)ni << 23));
+}
+inline float pow(float x, float y) {
+	if(!(x > 0.0f))
+		return 0.0f;
+	return contract_exp2(y * contract_log2(x));
 }
 
 // shared-memory atomics of a single emulated invocation

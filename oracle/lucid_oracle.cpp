@@ -10,14 +10,16 @@
 //   * PINNED against outputs of the reference's own source: the functions that decide coverage and
 //     blending -- processInputQuad, storeTri (quad_setup.glsl), loadScanlineParamsRow / Bin
 //     (scanline.glsl), scanlineStep (bin_counter.glsl), rasterBinStep, rasterHalfBlockCentroid / Bits,
-//     rasterBlockDepth (raster.glsl), initReduceSamples / reduceSample / finishReduceSamples
-//     (shading.glsl), encodeRGBA8 (funcs.glsl) -- are compiled from the GLSL text where it lies
+//     rasterBlockDepth (raster.glsl), initReduceSamples / reduceSample / finishReduceSamples,
+//     shadeSample + getTriangle* (shading.glsl), finalShading, sRGB conversions, normal and RGBA8
+//     codecs (funcs.glsl) -- are compiled from the GLSL text where it lies
 //     (oracle/build_ref_shaders.py, oracle/glsl_shim.h -> oracle/_ref/libref_shaders.so), run on seeded
-//     inputs (tests/golden/make_ref_shader_golden.py -> tests/golden/ref_shader_funcs.json) and the
+//     inputs (tests/golden/make_ref_shader_golden.py -> tests/golden/ref_shader_funcs.json.gz) and the
 //     oracle_fn_* entry points below must reproduce every word (tests/test_ref_shader_pins.py);
 //     the host-side camera / frustum math is pinned the same way against libfwk (oracle/Makefile ref);
-//   * UNPINNED (no reference output obtainable): the colour arithmetic of shadeSample (driver pow,
-//     the Vulkan sampler's filtering: DESIGN.md sections 4 and 9), and the control structure around the
+//   * UNPINNED (no reference output obtainable): the driver's pow and the Vulkan sampler's filtering
+//     (both defined here: DESIGN.md sections 4 and 9; stand-ins on both sides of the shadeSample
+//     comparison), and the control structure around the
 //     pinned functions (work distribution, list orders from racing atomics, the block sort), which
 //     rest on the reference's runtime invariants (verifyInfo, sortedness, stats[2]), closed-form
 //     scenes and an independent brute-force rasteriser in tests/.
@@ -251,6 +253,10 @@ struct Oracle {
 	const u32 *indices = nullptr;
 	int num_verts = 0, num_quads = 0;
 	Texture tex[2]; // 0 opaque, 1 transparent
+	// test hook (oracle_fn_shade_sample): the texture fetch records its arguments and returns a preset
+	// colour, so shadeSample can be compared with the reference's, whose sampler is not part of its source
+	const float *tex_probe = nullptr;
+	mutable float tex_probe_args[8] = {};
 
 	// per-frame inputs
 	LucidConfig cfg;
@@ -818,6 +824,12 @@ V4 bilinear(const Texture &t, int level, float uf, float vf) {
 }
 V4 Oracle::sampleTexture(const Texture &t, float u, float v, float dudx, float dvdx, float dudy,
 						 float dvdy) const {
+	if(tex_probe) {
+		tex_probe_args[0] = u, tex_probe_args[1] = v, tex_probe_args[2] = dudx, tex_probe_args[3] = dvdx;
+		tex_probe_args[4] = dudy, tex_probe_args[5] = dvdy;
+		tex_probe_args[6] = float(&t - tex), tex_probe_args[7] = 1.0f;
+		return V4{tex_probe[0], tex_probe[1], tex_probe[2], tex_probe[3]};
+	}
 	if(!t.valid())
 		return V4{1.0f, 1.0f, 1.0f, 1.0f};
 	float w0 = float(t.w[0]), h0 = float(t.h[0]);
@@ -1463,7 +1475,7 @@ void oracle_destroy(void *h) { delete(Oracle *)h; }
 void oracle_set_threads(void *h, int n) { ((Oracle *)h)->num_threads = n < 1 ? 1 : n; }
 // ---- function-level entry points: the same functions the pipeline above calls, one invocation per
 // call, so tests can compare them with the reference's own shader functions compiled from the
-// reference tree (oracle/build_ref_shaders.py -> tests/golden/ref_shader_funcs.json)
+// reference tree (oracle/build_ref_shaders.py -> tests/golden/ref_shader_funcs.json.gz)
 // out[0] status (0xffffffff visible, else rejection type) [1] size type [2] enc_aabb [3],[4] y ranges
 void oracle_fn_process_quad(void *h, const LucidConfig *cfg, const uint32_t *idx4, uint32_t *out) {
 	Oracle *o = (Oracle *)h;
@@ -1538,6 +1550,37 @@ uint32_t oracle_fn_encode_rgba8(const float *rgba) {
 	V4 c;
 	c.x = rgba[0], c.y = rgba[1], c.z = rgba[2], c.w = rgba[3];
 	return encodeRGBA8(c);
+}
+
+// shadeSample of triangle `second` of one quad given by its records; the texture fetch is the probe.
+// out: colour, depth bits, u, v, du/dx, dv/dx, du/dy, dv/dy bits, texture slot, fetch-happened flag
+void oracle_fn_shade_sample(void *h, const LucidConfig *cfg, const uint32_t *rec21, const uint32_t *attrs16,
+							uint32_t inst_color, const float *uv_rect4, const float *tex_preset4, int px, int py,
+							int second, uint32_t *out) {
+	Oracle *o = (Oracle *)h;
+	o->cfg = *cfg;
+	o->quad_aabbs[0].assign(1, 0u);
+	o->tris[0].assign(2, TriRecord());
+	TriRecord &t = o->tris[0][second];
+	memcpy(&t.bary0, rec21, 16), memcpy(&t.bary1, rec21 + 4, 16), memcpy(&t.scan0, rec21 + 8, 16);
+	memcpy(&t.scan1, rec21 + 12, 16), memcpy(&t.depth, rec21 + 16, 16);
+	t.normal = rec21[20];
+	o->qattrs[0].assign(1, QuadAttrs());
+	memcpy(&o->qattrs[0][0], attrs16, 64);
+	const u32 instance_id = rec21[19] >> 16;
+	o->inst_colors.assign(instance_id + 1, 0u);
+	o->inst_colors[instance_id] = inst_color;
+	o->inst_uv_rects.assign(instance_id + 1, V4{0.0f, 0.0f, 1.0f, 1.0f});
+	o->inst_uv_rects[instance_id] = V4{uv_rect4[0], uv_rect4[1], uv_rect4[2], uv_rect4[3]};
+	o->tex_probe = tex_preset4;
+	for(float &a : o->tex_probe_args)
+		a = 0.0f;
+	float depth = 0.0f;
+	out[0] = o->shadeSample(px, py, (u32)second, depth);
+	out[1] = floatBits(depth);
+	for(int i = 0; i < 8; i++)
+		out[2 + i] = floatBits(o->tex_probe_args[i]);
+	o->tex_probe = nullptr;
 }
 
 void oracle_set_item_stats(void *h, int on) {

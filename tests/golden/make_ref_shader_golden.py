@@ -5,13 +5,14 @@ oracle/build_ref_shaders.py compiles processInputQuad, storeTri (quad_setup.glsl
 loadScanlineParamsBin (shared/scanline.glsl), scanlineStep (bin_counter.glsl), rasterBinStep,
 rasterHalfBlockCentroid / Bits and rasterBlockDepth (shared/raster.glsl) from the GLSL text under
 /root/reference into oracle/_ref/libref_shaders.so.  This script feeds them seeded inputs and writes inputs
-and outputs to tests/golden/ref_shader_funcs.json; tests/test_ref_shader_pins.py replays the inputs through
+and outputs to tests/golden/ref_shader_funcs.json.gz; tests/test_ref_shader_pins.py replays the inputs through
 the CPU checker's functions (oracle_fn_*) and demands identical words.  Only runs where the reference tree
 is mounted (the build container); the JSON travels.
 
     python oracle/build_ref_shaders.py && python tests/golden/make_ref_shader_golden.py
 """
 import ctypes as C
+import gzip
 import json
 import os
 import sys
@@ -31,6 +32,7 @@ lib.ref_raster_rows.argtypes = [vp, C.c_float, C.c_float, C.c_int, vp]
 lib.ref_bin_rows.argtypes = [vp, vp]
 lib.ref_half_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, vp, C.c_float, C.c_float, C.c_float, vp]
 lib.ref_reduce_pixel.argtypes = [vp, vp, C.c_int, vp]
+lib.ref_shade_sample.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, vp]
 lib.ref_encode_rgba8.argtypes = [vp]
 lib.ref_encode_rgba8.restype = C.c_uint32
 
@@ -143,6 +145,45 @@ for k in range(60):
     o4 = np.zeros(4, np.uint32)
     lib.ref_reduce_pixel(ptr(cfg_words), ptr(samples), n, ptr(o4))
     out["reduce"].append({"samples": samples.tolist(), "rgba": o4.tolist()})
+# shading.glsl: shadeSample on the visible triangles above with every combination of instance flags, random
+# vertex attributes and a preset colour standing in for the texture fetch (whose arguments are recorded)
+out["shade"] = []
+INST = {"vcolors": 0x001, "vnormals": 0x004, "tex_opaque": 0x010, "uv_rect": 0x020, "albedo": 0x040, "color": 0x200}
+n_shade = 0
+for case in out["cases"]:
+    cw = np.array(case["config_words"], np.uint32)
+    for q in case["quads"]:
+        for t in q.get("tris", []):
+            if n_shade >= 160:
+                break
+            k = n_shade
+            n_shade += 1
+            flags = 0
+            for bit, name in enumerate(INST):
+                if (k * 2654435761 >> (8 + bit)) & 1:
+                    flags |= INST[name]
+            rec = np.array(t["record"], np.uint32)
+            instance_id = k % 200
+            rec[19] = flags | (instance_id << 16)
+            if flags & INST["vnormals"]:
+                rec[20] = 0
+            attrs = rng.integers(0, 1 << 32, 16, dtype=np.uint64).astype(np.uint32)
+            attrs[8:16] = rng.uniform(-2.0, 3.0, 8).astype(np.float32).view(np.uint32)  # uv0, uv1-uv0, uv2-uv0, uv3-uv0
+            inst_color = int(rng.integers(0, 1 << 32)) | (0xFF000000 if k % 3 == 0 else 0)
+            if k % 17 == 0:
+                inst_color &= 0x00FFFFFF  # alpha 0: the sample is dropped
+            uv_rect = rng.uniform(0.0, 1.0, 4).astype(np.float32)
+            preset = rng.uniform(0.0, 1.0, 4).astype(np.float32)
+            # a pixel inside the triangle's y range and bin column
+            ymin, ymax = t["y_aabb"] & 0xFFFF, t["y_aabb"] >> 16
+            py = int(rng.integers(ymin, max(ymax, ymin) + 1))
+            px = (q["process_quad"][2] & 0x7F) * 32 + int(rng.integers(0, 64))
+            o10 = np.zeros(10, np.uint32)
+            lib.ref_shade_sample(ptr(cw), ptr(rec), ptr(attrs), inst_color, ptr(uv_rect), ptr(preset), px, py,
+                                 t["second"], ptr(o10))
+            out["shade"].append({"case": out["cases"].index(case), "record": rec.tolist(), "attrs": attrs.tolist(),
+                                 "inst_color": inst_color, "uv_rect": bits(uv_rect), "tex_preset": bits(preset),
+                                 "pixel": [px, py], "second": t["second"], "out": o10.tolist()})
 out["encode_rgba8"] = []
 for k in range(64):
     c = rng.uniform(0.0, 1.0, 4).astype(np.float32)
@@ -152,9 +193,9 @@ for k in range(64):
         c[k % 4] = np.float32((k + 1) / 255.0)  # exactly on a step
     out["encode_rgba8"].append({"rgba": bits(c), "packed": int(lib.ref_encode_rgba8(ptr(c)))})
 
-path = os.path.join(HERE, "ref_shader_funcs.json")
-with open(path, "w") as f:
-    json.dump(out, f, separators=(",", ":"))
+path = os.path.join(HERE, "ref_shader_funcs.json.gz")
+with gzip.GzipFile(path, "wb", mtime=0) as f:
+    f.write(json.dumps(out, separators=(",", ":")).encode())
 statuses = [q["process_quad"][0] for c in out["cases"] for q in c["quads"]]
 print(path, os.path.getsize(path), "bytes;", len(statuses), "quads,", n_visible, "visible; rejection types seen:",
       sorted(set(s for s in statuses if s != 0xFFFFFFFF)))

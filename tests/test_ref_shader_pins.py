@@ -1,14 +1,16 @@
 """Pins of the CPU checker against the reference's own shader source.
 
-tests/golden/ref_shader_funcs.json holds the outputs of functions compiled from the GLSL text of the
+tests/golden/ref_shader_funcs.json.gz holds the outputs of functions compiled from the GLSL text of the
 reference tree (oracle/build_ref_shaders.py: processInputQuad, storeTri, loadScanlineParams*, scanlineStep,
-rasterBinStep, rasterHalfBlockCentroid / Bits, rasterBlockDepth) on seeded inputs.  The checker's own
+rasterBinStep, rasterHalfBlockCentroid / Bits, rasterBlockDepth, the sample reduction, shadeSample) on seeded
+inputs.  The checker's own
 functions (oracle_fn_* in oracle/lucid_oracle.cpp -- the ones its pipeline calls) must give the same words.
 These are the functions that decide coverage: which quads survive, their bin AABBs, the plane, barycentric
 and scanline equations, the bin-row and pixel-row spans, fragment counts, centroids and block depth keys.
 The CUDA kernels are compared with the checker by the GPU suite, so the pin carries over to them.
 """
 import ctypes as C
+import gzip
 import json
 import os
 
@@ -23,7 +25,7 @@ vp = C.c_void_p
 
 @pytest.fixture(scope="module")
 def golden():
-    with open(os.path.join(HERE, "golden", "ref_shader_funcs.json")) as f:
+    with gzip.open(os.path.join(HERE, "golden", "ref_shader_funcs.json.gz"), "rt") as f:
         return json.load(f)
 
 
@@ -114,6 +116,37 @@ def test_checker_reduction_and_codec_match_the_reference(golden):
             assert int(lib.oracle_fn_encode_rgba8(ptr(c))) == e["packed"]
     finally:
         o.close()
+
+
+def test_checker_shade_sample_matches_the_reference(golden):
+    """shading.glsl shadeSample (+ getTriangle*, funcs.glsl finalShading / sRGB conversions / codecs): sample
+    depth, perspective-correct barycentrics, uv and its analytic derivatives as handed to the sampler, instance
+    and vertex colours, interpolated or flat normals, lighting, truncating RGBA8 encode.  The texture fetch is a
+    probe on both sides (the Vulkan sampler is not part of the reference's source) and pow is the polynomial
+    contract on both sides: what is pinned is the reference's arithmetic around them."""
+    seen_flags, fetched, dropped = set(), 0, 0
+    oracles = {}
+    try:
+        for e in golden["shade"]:
+            case = golden["cases"][e["case"]]
+            if e["case"] not in oracles:
+                oracles[e["case"]] = Oracle(case["width"], case["height"], 0, 1 << 10, threads=1)
+            o = oracles[e["case"]]
+            o.lib.oracle_fn_shade_sample.argtypes = [vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+            cfg = np.array(case["config_words"], np.uint32)
+            rec, attrs = np.array(e["record"], np.uint32), np.array(e["attrs"], np.uint32)
+            uv_rect, preset = np.array(e["uv_rect"], np.uint32), np.array(e["tex_preset"], np.uint32)
+            o10 = np.zeros(10, np.uint32)
+            o.lib.oracle_fn_shade_sample(o.h, ptr(cfg), ptr(rec), ptr(attrs), e["inst_color"], ptr(uv_rect), ptr(preset),
+                                         e["pixel"][0], e["pixel"][1], e["second"], ptr(o10))
+            assert o10.tolist() == e["out"], (hex(int(rec[19]) & 0xFFFF), o10.tolist(), e["out"])
+            seen_flags.add(int(rec[19]) & 0xFFFF)
+            fetched += e["out"][9] != 0
+            dropped += e["out"][0] == 0
+    finally:
+        for o in oracles.values():
+            o.close()
+    assert len(golden["shade"]) >= 150 and len(seen_flags) >= 30 and fetched >= 40 and dropped >= 3
 
 
 def test_reference_library_matches_golden_when_available(golden):
