@@ -26,7 +26,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FUNCTIONS = [
     ("shared/funcs.glsl", ["encodeNormalUint", "encodeAABB28", "decodeAABB28", "decodeNormalUint", "decodeRGBA8", "encodeRGBA8",
                            "linearToSRGB", "SRGBToLinear", "finalShading"]),
-    ("quad_setup.glsl", ["vertexLoad", "vertexClipMask", "computeClippedAABB", "computeAABB", "processInputQuad", "storeTri"]),
+    ("quad_setup.glsl", ["vertexLoad", "vertexClipMask", "computeClippedAABB", "computeAABB", "processInputQuad", "storeQuad", "storeTri"]),
     ("shared/scanline.glsl", ["loadScanlineParamsRow", "loadScanlineParamsBin"]),
     ("bin_counter.glsl", ["scanlineStep"]),
     ("shared/raster.glsl", ["rasterBinStep", "rasterHalfBlockCentroid", "rasterHalfBlockBits", "rasterBlockDepth"]),
@@ -253,6 +253,19 @@ void ref_shade_sample(const float *cfg352, const uint32_t *rec21, const uint32_t
 	for(int i = 0; i < 8; i++)
 		out[2 + i] = floatBitsToUint(g_tex_args[i]);
 }
+// quad_setup.glsl: storeQuad for a quad with vertices 0..3; out: colours 4, normals 4, uv0 4, uv1 4
+void ref_store_quad(uint32_t flags, const uint32_t *colors4, const uint32_t *normals4, const float *uvs8, uint32_t *out) {
+	for(int i = 0; i < 4; i++)
+		g_colors[i] = colors4[i], g_normals[i] = normals4[i], g_tex_coords[i] = vec2(uvs8[i * 2], uvs8[i * 2 + 1]);
+	const uvec4 zero(0u, 0u, 0u, 0u);
+	g_uvec4_storage[STORAGE_QUAD_COLOR_OFFSET] = g_uvec4_storage[STORAGE_QUAD_NORMAL_OFFSET] = zero;
+	g_uvec4_storage[STORAGE_QUAD_TEXTURE_OFFSET] = g_uvec4_storage[STORAGE_QUAD_TEXTURE_OFFSET + 1] = zero;
+	storeQuad(0, flags, 0, 1, 2, 3);
+	const uvec4 *src[4] = {&g_uvec4_storage[STORAGE_QUAD_COLOR_OFFSET], &g_uvec4_storage[STORAGE_QUAD_NORMAL_OFFSET],
+						   &g_uvec4_storage[STORAGE_QUAD_TEXTURE_OFFSET], &g_uvec4_storage[STORAGE_QUAD_TEXTURE_OFFSET + 1]};
+	for(int i = 0; i < 4; i++)
+		out[i * 4 + 0] = src[i]->x, out[i * 4 + 1] = src[i]->y, out[i * 4 + 2] = src[i]->z, out[i * 4 + 3] = src[i]->w;
+}
 uint32_t ref_encode_rgba8(const float *rgba) { return encodeRGBA8(vec4(rgba[0], rgba[1], rgba[2], rgba[3])); }
 
 } // extern "C"
@@ -283,6 +296,8 @@ def main():
               "struct Frustum { vec4 ws_origin0, ws_dir0, ws_dirx, ws_diry; };",
               "struct Lighting { vec4 ambient_color, sun_color, sun_dir; float sun_power, ambient_power; };",
               "struct Config { Frustum frustum; mat4 view_proj_matrix; Lighting lighting; vec4 background_color; int enable_backface_culling; };",
+              "static uint g_colors[8], g_normals[8];",
+              "static vec2 g_tex_coords[8];",
               "static uint g_instance_colors[256];",
               "static vec4 g_instance_uv_rects[256];",
               "// the Vulkan sampler is not part of the source: textureGrad records its arguments and returns a preset colour",

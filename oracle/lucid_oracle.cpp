@@ -8,7 +8,7 @@
 //  and its own implementation (GLSL compute on Vulkan) cannot run in this image
 // (no Vulkan ICD, no shaderc).  What pins this file:
 //   * PINNED against outputs of the reference's own source: the functions that decide coverage and
-//     blending -- processInputQuad, storeTri (quad_setup.glsl), loadScanlineParamsRow / Bin
+//     blending -- processInputQuad, storeTri, storeQuad (quad_setup.glsl), loadScanlineParamsRow / Bin
 //     (scanline.glsl), scanlineStep (bin_counter.glsl), rasterBinStep, rasterHalfBlockCentroid / Bits,
 //     rasterBlockDepth (raster.glsl), initReduceSamples / reduceSample / finishReduceSamples,
 //     shadeSample + getTriangle* (shading.glsl), finalShading, sRGB conversions, normal and RGBA8
@@ -1581,6 +1581,16 @@ void oracle_fn_shade_sample(void *h, const LucidConfig *cfg, const uint32_t *rec
 	for(int i = 0; i < 8; i++)
 		out[2 + i] = floatBits(o->tex_probe_args[i]);
 	o->tex_probe = nullptr;
+}
+
+// storeQuad for a quad with vertices 0..3; out: colours 4, normals 4, uv0 4, uv1 4
+void oracle_fn_store_quad(uint32_t flags, const uint32_t *colors4, const uint32_t *normals4, const float *uvs8,
+						  uint32_t *out) {
+	Oracle o;
+	o.colors = colors4, o.normals = normals4, o.uvs = uvs8;
+	const u32 v[4] = {0, 1, 2, 3};
+	QuadAttrs a = storeQuad(o, flags, v);
+	memcpy(out, &a, 64);
 }
 
 void oracle_set_item_stats(void *h, int on) {

@@ -33,6 +33,7 @@ lib.ref_bin_rows.argtypes = [vp, vp]
 lib.ref_half_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, vp, C.c_float, C.c_float, C.c_float, vp]
 lib.ref_reduce_pixel.argtypes = [vp, vp, C.c_int, vp]
 lib.ref_shade_sample.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+lib.ref_store_quad.argtypes = [C.c_uint32, vp, vp, vp, vp]
 lib.ref_encode_rgba8.argtypes = [vp]
 lib.ref_encode_rgba8.restype = C.c_uint32
 
@@ -184,6 +185,17 @@ for case in out["cases"]:
             out["shade"].append({"case": out["cases"].index(case), "record": rec.tolist(), "attrs": attrs.tolist(),
                                  "inst_color": inst_color, "uv_rect": bits(uv_rect), "tex_preset": bits(preset),
                                  "pixel": [px, py], "second": t["second"], "out": o10.tolist()})
+# quad_setup.glsl: storeQuad (vertex attribute repack) for every combination of the three attribute flags
+out["store_quad"] = []
+for k in range(24):
+    flags = (0x001 if k & 1 else 0) | (0x004 if k & 2 else 0) | (0x040 if k & 4 else 0) | (0x200 if k & 8 else 0)
+    cols = rng.integers(0, 1 << 32, 4, dtype=np.uint64).astype(np.uint32)
+    nrms = rng.integers(0, 1 << 30, 4, dtype=np.uint64).astype(np.uint32)
+    uvs = rng.uniform(-4.0, 4.0, 8).astype(np.float32)
+    o16 = np.zeros(16, np.uint32)
+    lib.ref_store_quad(flags, ptr(cols), ptr(nrms), ptr(uvs), ptr(o16))
+    out["store_quad"].append({"flags": flags, "colors": cols.tolist(), "normals": nrms.tolist(), "uvs": bits(uvs),
+                              "out": o16.tolist()})
 out["encode_rgba8"] = []
 for k in range(64):
     c = rng.uniform(0.0, 1.0, 4).astype(np.float32)

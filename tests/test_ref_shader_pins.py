@@ -114,6 +114,14 @@ def test_checker_reduction_and_codec_match_the_reference(golden):
         for e in golden["encode_rgba8"]:
             c = np.array(e["rgba"], np.uint32)
             assert int(lib.oracle_fn_encode_rgba8(ptr(c))) == e["packed"]
+        # quad_setup.glsl storeQuad: vertex colours / normals / uv0 + deltas per quad
+        lib.oracle_fn_store_quad.argtypes = [C.c_uint32, vp, vp, vp, vp]
+        assert len(golden["store_quad"]) >= 16
+        for e in golden["store_quad"]:
+            o16 = np.zeros(16, np.uint32)
+            lib.oracle_fn_store_quad(e["flags"], ptr(np.array(e["colors"], np.uint32)), ptr(np.array(e["normals"], np.uint32)),
+                                     ptr(np.array(e["uvs"], np.uint32)), ptr(o16))
+            assert o16.tolist() == e["out"], (hex(e["flags"]), o16.tolist(), e["out"])
     finally:
         o.close()
 
