@@ -26,9 +26,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FUNCTIONS = [
     ("shared/funcs.glsl", ["encodeNormalUint", "encodeAABB28", "decodeAABB28", "decodeNormalUint", "decodeRGBA8", "encodeRGBA8",
                            "linearToSRGB", "SRGBToLinear", "finalShading"]),
-    ("quad_setup.glsl", ["vertexLoad", "vertexClipMask", "computeClippedAABB", "computeAABB", "processInputQuad", "storeQuad", "storeTri"]),
+    ("quad_setup.glsl", ["vertexLoad", "vertexClipMask", "computeClippedAABB", "computeAABB", "processInputQuad", "storeQuad", "storeTri", "addVisibleTri"]),
     ("shared/scanline.glsl", ["loadScanlineParamsRow", "loadScanlineParamsBin"]),
-    ("bin_counter.glsl", ["scanlineStep"]),
+    ("bin_counter.glsl", ["scanlineStep", "countSmallQuadBins", "loadScanlineParamsBin", "countLargeTriBins"]),
+    ("bin_dispatcher.glsl", ["dispatchQuad", "dispatchLargeTriSimple"]),
     ("shared/raster.glsl", ["rasterBinStep", "rasterHalfBlockCentroid", "rasterHalfBlockBits", "rasterBlockDepth"]),
     ("shared/shading.glsl", ["getTriangleParams", "getTriangleVertexColors", "getTriangleVertexNormals",
                              "getTriangleVertexTexCoords", "shadeSample"]),
@@ -266,6 +267,79 @@ void ref_store_quad(uint32_t flags, const uint32_t *colors4, const uint32_t *nor
 	for(int i = 0; i < 4; i++)
 		out[i * 4 + 0] = src[i]->x, out[i * 4 + 1] = src[i]->y, out[i * 4 + 2] = src[i]->z, out[i * 4 + 3] = src[i]->w;
 }
+// Scene level: quad setup -> bin counting -> bin dispatch of one frame through the reference's per-invocation
+// functions, invocations run one after the other (processInputQuad, addVisibleTri/storeTri, countSmallQuadBins,
+// countLargeTriBins, dispatchQuad, dispatchLargeTriSimple).  What the shaders' main() functions add around them --
+// slot assignment and the prefix sums of the categoriser -- is done here in the canonical order of the checker:
+// visible small quads take slots 0.. in input order, large quads MAX_VISIBLE_QUADS-1.. downwards.
+// out_counts: quad counts then triangle counts per bin; out_lists: per-bin quad lists then per-bin triangle lists,
+// each bin's segment sorted; out_n: visible small, visible large, list lengths; returns 0, or 1 on overflow.
+int ref_bin_scene(const float *cfg352, int width, int height, const float *positions, int num_verts,
+				  const uint32_t *indices, int num_quads, int32_t *out_counts, uint32_t *out_lists, uint32_t *out_n) {
+	loadConfig(cfg352);
+	VIEWPORT_SIZE_X = width, VIEWPORT_SIZE_Y = height;
+	BIN_COUNT_X = (width + BIN_SIZE - 1) / BIN_SIZE;
+	const int bcy = (height + BIN_SIZE - 1) / BIN_SIZE, bc = BIN_COUNT_X * bcy;
+	if(num_verts > 524288 || bc > 128 * 128)
+		return 1;
+	for(int i = 0; i < num_verts * 3; i++)
+		g_verts[i] = positions[i];
+	s_ray_dir0 = u_config.frustum.ws_dir0.xyz() + (u_config.frustum.ws_dirx.xyz() + u_config.frustum.ws_diry.xyz()) * 0.5f;
+	int n_small = 0, n_large = 0;
+	for(int q = 0; q < num_quads; q++) {
+		for(uint &r : s_rejected_quads)
+			r = 0;
+		s_num_visible[0] = s_num_visible[1] = 0;
+		processInputQuad((uint)q, indices[q * 4], indices[q * 4 + 1], indices[q * 4 + 2], indices[q * 4 + 3], 0);
+		if(s_num_visible[0] + s_num_visible[1] == 0)
+			continue;
+		const bool large = s_num_visible[1] != 0;
+		const int src = large ? LSIZE - 1 : 0;
+		if(n_small + n_large + 1 >= MAX_VISIBLE_QUADS)
+			return 1;
+		const int slot = large ? (MAX_VISIBLE_QUADS - 1) - n_large++ : n_small++;
+		g_quad_aabbs[slot] = s_quad_aabbs[src];
+		addVisibleTri(slot, src, 0u, 0);
+		addVisibleTri(slot, src, 0u, 1);
+	}
+	out_n[0] = (uint32_t)n_small, out_n[1] = (uint32_t)n_large;
+	// counting
+	for(int b = 0; b < bc; b++)
+		s_bins[b] = 0;
+	for(int q = 0; q < n_small; q++)
+		countSmallQuadBins((uint)q);
+	for(int b = 0; b < bc; b++)
+		out_counts[b] = s_bins[b], s_bins[b] = 0;
+	for(int k = 0; k < n_large; k++)
+		for(int second = 0; second < 2; second++)
+			countLargeTriBins((MAX_VISIBLE_QUADS - 1) - k, second);
+	for(int by = 0; by < bcy; by++) // accumulateLargeTriCountsAcrossRows, its sequential form
+		for(int bx = 0, accum = 0; bx < BIN_COUNT_X; bx++) {
+			accum += s_bins[bx + by * BIN_COUNT_X];
+			out_counts[bc + bx + by * BIN_COUNT_X] = accum;
+		}
+	// dispatch: exclusive prefix sums as the categoriser leaves them in the *_OFFSETS_TEMP arrays
+	int total_q = 0, total_t = 0;
+	for(int b = 0; b < bc; b++)
+		total_q += out_counts[b], total_t += out_counts[bc + b];
+	if(total_q > MAX_VISIBLE_QUADS * 8 || total_t > MAX_VISIBLE_QUADS * 64)
+		return 1;
+	for(int b = 0, off = 0; b < bc; b++)
+		s_bins[b] = off, off += out_counts[b];
+	for(int q = 0; q < n_small; q++)
+		dispatchQuad(q);
+	for(int b = 0, off = 0; b < bc; b++)
+		s_bins[b] = off, off += out_counts[bc + b];
+	for(int k = 0; k < n_large; k++)
+		for(int second = 0; second < 2; second++)
+			dispatchLargeTriSimple(k, second, n_large);
+	out_n[2] = (uint32_t)total_q, out_n[3] = (uint32_t)total_t;
+	for(int i = 0; i < total_q; i++)
+		out_lists[i] = g_bin_quads[i];
+	for(int i = 0; i < total_t; i++)
+		out_lists[total_q + i] = g_bin_tris[i];
+	return 0;
+}
 uint32_t ref_encode_rgba8(const float *rgba) { return encodeRGBA8(vec4(rgba[0], rgba[1], rgba[2], rgba[3])); }
 
 } // extern "C"
@@ -286,7 +360,8 @@ def main():
     parts = ['#include "../glsl_shim.h"', "using namespace glsl;", ""]
     parts += ["// ---- specialisation constants (definitions.glsl CONSTANT(...)) as variables",
               "static int VIEWPORT_SIZE_X = 1280, VIEWPORT_SIZE_Y = 720;",
-              "static const int BIN_SIZE = 32, BIN_SHIFT = 5, MAX_VISIBLE_QUADS = 1024;", ""]
+              "static const int BIN_SIZE = 32, BIN_SHIFT = 5, MAX_VISIBLE_QUADS = 32768;",
+              "static int BIN_COUNT_X = 40;", ""]
     parts.append("// ---- #define lines of the reference")
     for rel, names in DEFINES.items():
         text = open(os.path.join(shaders, rel), encoding="latin-1").read()
@@ -309,7 +384,10 @@ def main():
               "	return g_tex_preset;",
               "}",
               "static Config u_config;",
-              "static float g_verts[64];",
+              "static float g_verts[3 * 524288];",
+              "static uint g_quad_aabbs[MAX_VISIBLE_QUADS];",
+              "static uint g_bin_quads[MAX_VISIBLE_QUADS * 8], g_bin_tris[MAX_VISIBLE_QUADS * 64];",
+              "static int s_bins[128 * 128];",
               "static uvec4 g_uvec4_storage[MAX_VISIBLE_QUADS * 14];",
               "static uint g_normals_storage[8];",
               "static vec3 s_ray_dir0;",

@@ -13,6 +13,7 @@ is mounted (the build container); the JSON travels.
 """
 import ctypes as C
 import gzip
+import hashlib
 import json
 import os
 import sys
@@ -34,6 +35,7 @@ lib.ref_half_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, vp, C.c_float, C
 lib.ref_reduce_pixel.argtypes = [vp, vp, C.c_int, vp]
 lib.ref_shade_sample.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, vp]
 lib.ref_store_quad.argtypes = [C.c_uint32, vp, vp, vp, vp]
+lib.ref_bin_scene.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp]
 lib.ref_encode_rgba8.argtypes = [vp]
 lib.ref_encode_rgba8.restype = C.c_uint32
 
@@ -196,6 +198,35 @@ for k in range(24):
     lib.ref_store_quad(flags, ptr(cols), ptr(nrms), ptr(uvs), ptr(o16))
     out["store_quad"].append({"flags": flags, "colors": cols.tolist(), "normals": nrms.tolist(), "uvs": bits(uvs),
                               "out": o16.tolist()})
+# Scene level: setup -> bin counts -> bin lists of whole (small) scenes through the reference's per-invocation
+# functions run one after the other (oracle/build_ref_shaders.py ref_bin_scene).  The scenes are the seeded
+# procedural ones of tests/parity_util.py, so only their names and the reference's results are stored.
+from tests import parity_util as pu  # noqa: E402
+out["bin_scenes"] = []
+small = pu.small_scenes()
+for name in ("soup_close", "arch", "soup"):
+    sc = small[name]
+    cfg, inst, _, _ = api.prepare_frame(sc)
+    cw = np.frombuffer(bytes(cfg), np.uint32).copy()
+    pos = np.ascontiguousarray(sc["positions"], np.float32)
+    quads = np.ascontiguousarray(sc["quads"], np.uint32)
+    assert int(inst[:, 2].sum()) == quads.shape[0] and (inst[:, 1] == 0).all()  # instances cover the index buffer in order
+    bc = ((sc["width"] + 31) // 32) * ((sc["height"] + 31) // 32)
+    counts = np.zeros(2 * bc, np.int32)
+    lists = np.zeros(32768 * 72, np.uint32)
+    n = np.zeros(4, np.uint32)
+    rc = lib.ref_bin_scene(ptr(cw), sc["width"], sc["height"], ptr(pos), pos.shape[0], ptr(quads), quads.shape[0],
+                           ptr(counts), ptr(lists), ptr(n))
+    assert rc == 0, (name, rc)
+    nq, nt = int(n[2]), int(n[3])
+    bq = pu.canonical_lists(lists[:nq], counts[:bc])
+    bt = pu.canonical_lists(lists[nq:nq + nt], counts[bc:])
+    out["bin_scenes"].append({"scene": name, "max_visible_quads": 32768, "visible": [int(n[0]), int(n[1])],
+                              "quad_counts": counts[:bc].tolist(), "tri_counts": counts[bc:].tolist(),
+                              "list_entries": [nq, nt],
+                              "bin_quads_sha256": hashlib.sha256(np.ascontiguousarray(bq, np.uint32).tobytes()).hexdigest(),
+                              "bin_tris_sha256": hashlib.sha256(np.ascontiguousarray(bt, np.uint32).tobytes()).hexdigest()})
+    print("   bin scene", name, "visible small/large", int(n[0]), int(n[1]), "list entries", nq, nt)
 out["encode_rgba8"] = []
 for k in range(64):
     c = rng.uniform(0.0, 1.0, 4).astype(np.float32)
