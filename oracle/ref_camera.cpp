@@ -9,7 +9,10 @@
 //
 // usage: ref_camera orbit cx cy cz dist rot_h rot_v fov_deg znear zfar width height
 //        ref_camera lookat px py pz tx ty tz ux uy uz fov_deg znear zfar width height
+//        ref_camera color r g b opacity   -> u32(IColor(FColor(diffuse, opacity))), the material colour of
+//                                            LucidRenderer::uploadInstances (src/lucid_renderer.cpp:364-365)
 #include <fwk/gfx/camera.h>
+#include <fwk/gfx/color.h>
 #include <fwk/gfx/orbiting_camera.h>
 #include <fwk/math/frustum.h>
 #include <fwk/math/matrix4.h>
@@ -30,6 +33,11 @@ int main(int argc, char **argv) {
 	Camera cam;
 	int a = 2;
 	auto f = [&]() { return (float)atof(argv[a++]); };
+	if(!strcmp(argv[1], "color") && argc == 6) {
+		float r = f(), g = f(), b = f(), opacity = f();
+		printf("color %u\n", u32(IColor(FColor(float3(r, g, b), opacity))));
+		return 0;
+	}
 	if(!strcmp(argv[1], "orbit") && argc == 13) {
 		float cx = f(), cy = f(), cz = f(); // sequenced reads (argument evaluation order is unspecified)
 		float3 center(cx, cy, cz);

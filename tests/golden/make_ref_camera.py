@@ -19,6 +19,12 @@ CASES = [
 ]
 
 
+# material colours (diffuse rgb, opacity) for the IColor(FColor(...)) conversion of uploadInstances
+COLORS = [(1.0, 1.0, 1.0, 1.0), (1.0, 0.5, 0.25, 0.5), (0.0, 0.0, 0.0, 0.0), (0.999, 0.001, 0.5019608, 0.7490196),
+          (0.2, 0.4, 0.6, 0.8), (1.5, -0.25, 0.0039215, 1.0), (0.3333333, 0.6666667, 0.9960785, 0.25),
+          (0.0627451, 0.1254902, 0.2509804, 0.5019608)]
+
+
 def main():
     out = []
     for kind, args in CASES:
@@ -30,6 +36,9 @@ def main():
             parts = line.split()
             rec[parts[0]] = [float(v) for v in parts[1:]]
         out.append(rec)
+    for c in COLORS:
+        txt = subprocess.run([BIN, "color"] + [repr(float(v)) for v in c], check=True, capture_output=True, text=True).stdout
+        out.append({"kind": "color", "args": list(c), "color": int(txt.split()[1])})
     with open(os.path.join(HERE, "ref_camera.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", len(out), "cases")

@@ -18,9 +18,13 @@ def _v(v):
     return np.array([v.x, v.y, v.z], np.float64)
 
 
-def _cases():
+def _all_cases():
     with open(os.path.join(HERE, "golden", "ref_camera.json")) as f:
         return json.load(f)
+
+
+def _cases():
+    return [c for c in _all_cases() if c["kind"] != "color"]
 
 
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: f"{c['kind']}-{c['args'][-2]}x{c['args'][-1]}")
@@ -104,6 +108,18 @@ def test_build_instances_slices_and_colours():
     f = inst[:, 3].astype(np.uint32)
     assert (f[:3] == (scenes.INST_HAS_VERTEX_COLORS | scenes.INST_HAS_COLOR)).all() and f[3] == 0
     assert rects[3].tolist() == [0.25, 0.5, 0.125, 0.125]
+
+
+def test_material_colours_match_libfwk():
+    """The instance colour of uploadInstances is u32(IColor(FColor(diffuse, opacity))) (src/lucid_renderer.cpp:364-365):
+    libfwk's conversion, compiled from the reference tree (oracle/_ref/ref_camera color ...), against
+    lucid_host_build_instances."""
+    cases = [c for c in _all_cases() if c["kind"] == "color"]
+    assert len(cases) >= 8
+    for c in cases:
+        r, g, b, opacity = c["args"]
+        _, cols, _ = api.build_instances([(0, 1, 0, 0)], [((r, g, b), opacity, (0.0, 0.0, 1.0, 1.0))])
+        assert int(cols[0]) == c["color"], (c["args"], hex(int(cols[0])), hex(c["color"]))
 
 
 def test_struct_layouts():
