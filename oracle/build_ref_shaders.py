@@ -340,6 +340,86 @@ int ref_bin_scene(const float *cfg352, int width, int height, const float *posit
 		out_lists[total_q + i] = g_bin_tris[i];
 	return 0;
 }
+// Scene level, raster coverage: after ref_bin_scene has run on the same inputs (its buffers are kept), every
+// triangle of every bin's lists is walked the way generateRowTris does -- raster_low.glsl:39-64 for LOW bins
+// (y range clamped to the bin, loadScanlineParamsRow at the first 8-row block row, two rasterBinStep per block
+// row), raster_high.glsl:54-90 for HIGH bins (first 4-row half-block row, one step per row) -- and the pixels
+// of rasterHalfBlockBits are counted.  The two walks accumulate the scanline state from different rows, so a
+// span can differ in its last pixel between them: which walk a bin gets is part of the result.  A bin is LOW
+// with fewer than 1024 triangles (bin_categorizer.glsl:69-79) unless one of its 8x8 blocks collects more than
+// 256 (raster_low.glsl:101-105: promoted to HIGH).  out: fragments per pixel; returns total fragments.
+static int walkBin(int b, bool high, int q_off, int t_off, int n_q, int n_t, int width, int height, uint32_t *out,
+				   uint64_t *total) {
+	const ivec2 bin_pos((b % BIN_COUNT_X) * BIN_SIZE, (b / BIN_COUNT_X) * BIN_SIZE);
+	const int shift = high ? 2 : 3, steps = high ? 1 : 2;
+	int block_tris[16] = {0};
+	for(int i = 0; i < n_q * 2 + n_t; i++) {
+		uint tri_idx;
+		if(i < n_q * 2) {
+			const uint w = g_bin_quads[q_off + (i >> 1)];
+			if((w >> (30 + (i & 1))) & 1)
+				continue;
+			tri_idx = (w & 0x0fffffffu) * 2 + (i & 1);
+		} else {
+			tri_idx = g_bin_tris[t_off + (i - n_q * 2)];
+		}
+		const uint scan_offset = STORAGE_TRI_SCAN_OFFSET + tri_idx * 2;
+		const uvec4 val0 = g_uvec4_storage[scan_offset + 0], val1 = g_uvec4_storage[scan_offset + 1];
+		const int min_by = clamp(glsl_int(val0.w & 0xffff) - bin_pos.y, 0, BIN_MASK) >> shift;
+		const int max_by = clamp(glsl_int(val0.w >> 16) - bin_pos.y, 0, BIN_MASK) >> shift;
+		ScanlineParams scan = loadScanlineParamsRow(val0, val1, vec2(float(bin_pos.x), float(bin_pos.y + (min_by << shift))));
+		for(int by = min_by; by <= max_by; by++) {
+			uint block_mask = 0;
+			for(int s = 0; s < steps; s++) {
+				const uvec3 bits = rasterBinStep(scan);
+				block_mask |= bits.z;
+				if(!out)
+					continue;
+				for(int hbx = 0; hbx < HBLOCK_COLS; hbx++) {
+					if(!((bits.z >> hbx) & 1))
+						continue;
+					uint nf = 0;
+					const uint packed = rasterHalfBlockBits(bits.x, bits.y, hbx * 8, nf);
+					*total += nf;
+					for(int r = 0; r < 4; r++) {
+						const int xmin = (packed >> (7 * r)) & 7, cnt = (packed >> (7 * r + 3)) & 15;
+						const int gy = bin_pos.y + ((by * steps + s) << 2) + r;
+						for(int x = xmin; x < xmin + cnt; x++) {
+							const int gx = bin_pos.x + hbx * 8 + x;
+							if(gx < width && gy < height)
+								out[gy * width + gx]++;
+						}
+					}
+				}
+			}
+			if(!high)
+				for(int bx = 0; bx < 4; bx++)
+					if((block_mask >> bx) & 1)
+						block_tris[by * 4 + bx]++;
+		}
+	}
+	int most = 0;
+	for(int c : block_tris)
+		most = c > most ? c : most;
+	return most;
+}
+uint64_t ref_frag_counts(int width, int height, const int32_t *counts, uint32_t *out, uint8_t *out_high) {
+	const int bcy = (height + BIN_SIZE - 1) / BIN_SIZE, bc = BIN_COUNT_X * bcy;
+	for(int i = 0; i < width * height; i++)
+		out[i] = 0;
+	uint64_t total = 0;
+	int q_off = 0, t_off = 0;
+	for(int b = 0; b < bc; b++) {
+		const int n_q = counts[b], n_t = counts[bc + b];
+		bool high = n_q * 2 + n_t >= 1024;
+		if(!high && walkBin(b, false, q_off, t_off, n_q, n_t, width, height, nullptr, nullptr) > 256)
+			high = true; // promoted
+		out_high[b] = high;
+		walkBin(b, high, q_off, t_off, n_q, n_t, width, height, out, &total);
+		q_off += n_q, t_off += n_t;
+	}
+	return total;
+}
 uint32_t ref_encode_rgba8(const float *rgba) { return encodeRGBA8(vec4(rgba[0], rgba[1], rgba[2], rgba[3])); }
 
 } // extern "C"

@@ -156,6 +156,7 @@ inline vec2 max(const vec2 &a, const vec2 &b) { return vec2(max(a.x, b.x), max(a
 inline ivec4 min(const ivec4 &a, int b) { return ivec4(min(a.x, b), min(a.y, b), min(a.z, b), min(a.w, b)); }
 inline ivec4 max(const ivec4 &a, int b) { return ivec4(max(a.x, b), max(a.y, b), max(a.z, b), max(a.w, b)); }
 inline float clamp(float v, float lo, float hi) { return min(max(v, lo), hi); }
+inline int clamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
 inline vec4 clamp(const vec4 &v, const vec4 &lo, const vec4 &hi) {
 	return vec4(clamp(v.x, lo.x, hi.x), clamp(v.y, lo.y, hi.y), clamp(v.z, lo.z, hi.z), clamp(v.w, lo.w, hi.w));
 }

@@ -36,6 +36,8 @@ lib.ref_reduce_pixel.argtypes = [vp, vp, C.c_int, vp]
 lib.ref_shade_sample.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, vp]
 lib.ref_store_quad.argtypes = [C.c_uint32, vp, vp, vp, vp]
 lib.ref_bin_scene.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+lib.ref_frag_counts.argtypes = [C.c_int, C.c_int, vp, vp, vp]
+lib.ref_frag_counts.restype = C.c_uint64
 lib.ref_encode_rgba8.argtypes = [vp]
 lib.ref_encode_rgba8.restype = C.c_uint32
 
@@ -221,7 +223,17 @@ for name in ("soup_close", "arch", "soup"):
     nq, nt = int(n[2]), int(n[3])
     bq = pu.canonical_lists(lists[:nq], counts[:bc])
     bt = pu.canonical_lists(lists[nq:nq + nt], counts[bc:])
+    # raster coverage of the same frame: every listed triangle walked like generateRowTris, pixels of
+    # rasterHalfBlockBits counted
+    frag = np.zeros(sc["width"] * sc["height"], np.uint32)
+    is_high = np.zeros(bc, np.uint8)
+    frag_total = int(lib.ref_frag_counts(sc["width"], sc["height"], ptr(counts), ptr(frag), ptr(is_high)))
+    print("   fragments", frag_total, "inside the image", int(frag.sum()), "max per pixel", int(frag.max()),
+          "HIGH bins", int(is_high.sum()))
     out["bin_scenes"].append({"scene": name, "max_visible_quads": 32768, "visible": [int(n[0]), int(n[1])],
+                              "fragments": frag_total, "fragments_in_image": int(frag.sum()),
+                              "high_bins": np.flatnonzero(is_high).tolist(),
+                              "frag_counts_sha256": hashlib.sha256(frag.tobytes()).hexdigest(),
                               "quad_counts": counts[:bc].tolist(), "tri_counts": counts[bc:].tolist(),
                               "list_entries": [nq, nt],
                               "bin_quads_sha256": hashlib.sha256(np.ascontiguousarray(bq, np.uint32).tobytes()).hexdigest(),

@@ -162,7 +162,8 @@ def test_checker_bin_counts_and_lists_match_the_reference_on_whole_scenes(golden
     """Scene level: the reference's per-invocation functions of quad setup, bin counting and bin dispatch
     (processInputQuad, addVisibleTri / storeTri, countSmallQuadBins, countLargeTriBins, dispatchQuad,
     dispatchLargeTriSimple) run over every quad of a scene give the checker's visible-quad counts, per-bin quad and
-    triangle counts and per-bin lists (as sorted sets) exactly."""
+    triangle counts and per-bin lists (as sorted sets) exactly; walking every listed triangle the way generateRowTris
+    does (loadScanlineParamsRow, rasterBinStep, rasterHalfBlockBits) gives its per-pixel fragment counts."""
     from lucid_b200 import api
     from tests import parity_util as pu
     small = pu.small_scenes()
@@ -182,6 +183,11 @@ def test_checker_bin_counts_and_lists_match_the_reference_on_whole_scenes(golden
                 canon = np.ascontiguousarray(pu.canonical_lists(values, cnt), np.uint32)
                 assert hashlib.sha256(canon.tobytes()).hexdigest() == want  # every entry of every bin's list
             large_seen += e["visible"][1]
+            # raster coverage: fragments per pixel from the reference's scanline / span / half-block functions
+            fc = np.ascontiguousarray(o.read_frag_counts(), np.uint32)
+            assert np.flatnonzero(o.read_bin_levels() == 4).tolist() == e["high_bins"]  # incl. promoted LOW bins
+            assert int(o.info[60]) == e["fragments"] and int(fc.sum()) == e["fragments_in_image"]
+            assert hashlib.sha256(fc.tobytes()).hexdigest() == e["frag_counts_sha256"]
         finally:
             o.close()
     assert large_seen > 0  # the large-triangle path (per bin row scan) is exercised
