@@ -243,8 +243,8 @@ void ref_shade_sample(const float *cfg352, const uint32_t *rec21, const uint32_t
 	g_uvec4_storage[STORAGE_QUAD_TEXTURE_OFFSET] = uvec4(attrs16[8], attrs16[9], attrs16[10], attrs16[11]);
 	g_uvec4_storage[STORAGE_QUAD_TEXTURE_OFFSET + 1] = uvec4(attrs16[12], attrs16[13], attrs16[14], attrs16[15]);
 	const uint instance_id = rec21[19] >> 16;
-	g_instance_colors[instance_id & 255] = inst_color;
-	g_instance_uv_rects[instance_id & 255] = vec4(uv_rect4[0], uv_rect4[1], uv_rect4[2], uv_rect4[3]);
+	g_instance_colors[instance_id] = inst_color;
+	g_instance_uv_rects[instance_id] = vec4(uv_rect4[0], uv_rect4[1], uv_rect4[2], uv_rect4[3]);
 	g_tex_preset = vec4(tex_preset4[0], tex_preset4[1], tex_preset4[2], tex_preset4[3]);
 	for(float &a : g_tex_args)
 		a = 0.0f;
@@ -274,8 +274,11 @@ void ref_store_quad(uint32_t flags, const uint32_t *colors4, const uint32_t *nor
 // visible small quads take slots 0.. in input order, large quads MAX_VISIBLE_QUADS-1.. downwards.
 // out_counts: quad counts then triangle counts per bin; out_lists: per-bin quad lists then per-bin triangle lists,
 // each bin's segment sorted; out_n: visible small, visible large, list lengths; returns 0, or 1 on overflow.
+// quad_flags_id (may be null): per input quad, instance flags | instance id << 16; colors / normals / uvs (may be
+// null): the vertex attribute buffers storeQuad repacks.
 int ref_bin_scene(const float *cfg352, int width, int height, const float *positions, int num_verts,
-				  const uint32_t *indices, int num_quads, int32_t *out_counts, uint32_t *out_lists, uint32_t *out_n) {
+				  const uint32_t *indices, int num_quads, const uint32_t *quad_flags_id, const uint32_t *colors,
+				  const uint32_t *normals, const float *uvs, int32_t *out_counts, uint32_t *out_lists, uint32_t *out_n) {
 	loadConfig(cfg352);
 	VIEWPORT_SIZE_X = width, VIEWPORT_SIZE_Y = height;
 	BIN_COUNT_X = (width + BIN_SIZE - 1) / BIN_SIZE;
@@ -284,6 +287,10 @@ int ref_bin_scene(const float *cfg352, int width, int height, const float *posit
 		return 1;
 	for(int i = 0; i < num_verts * 3; i++)
 		g_verts[i] = positions[i];
+	for(int i = 0; i < num_verts; i++) {
+		g_colors[i] = colors ? colors[i] : 0u, g_normals[i] = normals ? normals[i] : 0u;
+		g_tex_coords[i] = uvs ? vec2(uvs[i * 2], uvs[i * 2 + 1]) : vec2(0.0f, 0.0f);
+	}
 	s_ray_dir0 = u_config.frustum.ws_dir0.xyz() + (u_config.frustum.ws_dirx.xyz() + u_config.frustum.ws_diry.xyz()) * 0.5f;
 	int n_small = 0, n_large = 0;
 	for(int q = 0; q < num_quads; q++) {
@@ -299,8 +306,11 @@ int ref_bin_scene(const float *cfg352, int width, int height, const float *posit
 			return 1;
 		const int slot = large ? (MAX_VISIBLE_QUADS - 1) - n_large++ : n_small++;
 		g_quad_aabbs[slot] = s_quad_aabbs[src];
-		addVisibleTri(slot, src, 0u, 0);
-		addVisibleTri(slot, src, 0u, 1);
+		const uint flags_id = quad_flags_id ? quad_flags_id[q] : 0u;
+		storeQuad((uint)slot, flags_id & 0xffffu, s_quad_indices[src].x, s_quad_indices[src].y, s_quad_indices[src].z,
+				  s_quad_indices[src].w); // addVisibleQuad, quad_setup.glsl:342-353
+		addVisibleTri(slot, src, flags_id, 0);
+		addVisibleTri(slot, src, flags_id, 1);
 	}
 	out_n[0] = (uint32_t)n_small, out_n[1] = (uint32_t)n_large;
 	// counting
@@ -420,6 +430,129 @@ uint64_t ref_frag_counts(int width, int height, const int32_t *counts, uint32_t 
 	}
 	return total;
 }
+// Scene level, image: after ref_bin_scene (buffers kept).  The flow of raster_low / raster_high restated around
+// the reference's functions: per bin (level as in ref_frag_counts), per 8x8 block (LOW) or 8x4 half-block (HIGH),
+// the triangles whose 4-row spans touch the column, in list order; depth key from rasterHalfBlockCentroid (LOW: the
+// sum over both halves, raster_low.glsl:119-131) and rasterBlockDepth, 22 / 18 bits; stable sort by key (ties keep
+// list order -- the reference's tie order is the arrival order of atomics), not at all for LOW blocks of <= 3
+// (raster_low.glsl:144); then per half-block, per entry, per pixel of rasterHalfBlockBits: shadeSample, reduceSample;
+// finishReduceSamples; rgba8 store rounds to nearest.  Bins without triangles keep `background8`.
+struct BlockEntry {
+	uint tri, key;
+	uint mins[2], maxs[2];
+};
+static void shadeList(BlockEntry *list, int n, int halves, int startx, ivec2 block_pos, int width, int height, uint32_t *image) {
+	for(int half = 0; half < halves; half++) {
+		ReductionContext ctx[32];
+		for(auto &c : ctx)
+			initReduceSamples(c);
+		for(int i = 0; i < n; i++) {
+			uint nf = 0;
+			const uint packed = rasterHalfBlockBits(list[i].mins[half], list[i].maxs[half], startx, nf);
+			for(int r = 0; r < 4; r++) {
+				const int xmin = (packed >> (7 * r)) & 7, cnt = (packed >> (7 * r + 3)) & 15;
+				for(int x = xmin; x < xmin + cnt; x++) {
+					float depth = 0.0f;
+					const uint color = shadeSample(ivec2(block_pos.x + x, block_pos.y + half * 4 + r), list[i].tri, depth);
+					g_lane_samples[0] = uvec2(color, floatBitsToUint(depth));
+					reduceSample(ctx[r * 8 + x], ctx[r * 8 + x].out_color, g_lane_samples[0], 1u);
+				}
+			}
+		}
+		for(int p = 0; p < 32; p++) {
+			const int gx = block_pos.x + (p & 7), gy = block_pos.y + half * 4 + (p >> 3);
+			if(gx >= width || gy >= height)
+				continue;
+			const vec4 c = finishReduceSamples(ctx[p]);
+			image[gy * width + gx] = glsl_uint(c.x * 255.0f + 0.5f) | (glsl_uint(c.y * 255.0f + 0.5f) << 8) |
+									 (glsl_uint(c.z * 255.0f + 0.5f) << 16) | 0xff000000u;
+		}
+	}
+}
+int ref_shade_image(const float *cfg352, int width, int height, const int32_t *counts, const uint8_t *is_high,
+					const uint32_t *inst_colors, const float *inst_uv_rects, int num_instances, uint32_t background8,
+					uint32_t *image) {
+	loadConfig(cfg352);
+	const int bcy = (height + BIN_SIZE - 1) / BIN_SIZE, bc = BIN_COUNT_X * bcy;
+	for(int i = 0; i < num_instances && i < 65536; i++) {
+		g_instance_colors[i] = inst_colors[i];
+		g_instance_uv_rects[i] = vec4(inst_uv_rects[i * 4], inst_uv_rects[i * 4 + 1], inst_uv_rects[i * 4 + 2], inst_uv_rects[i * 4 + 3]);
+	}
+	for(int i = 0; i < width * height; i++)
+		image[i] = background8;
+	static BlockEntry lists[16][4096];
+	int q_off = 0, t_off = 0;
+	for(int b = 0; b < bc; b++) {
+		const int n_q = counts[b], n_t = counts[bc + b];
+		const bool high = is_high[b] != 0;
+		const ivec2 bin_pos((b % BIN_COUNT_X) * BIN_SIZE, (b / BIN_COUNT_X) * BIN_SIZE);
+		const int shift = high ? 2 : 3, steps = high ? 1 : 2, n_rows = BIN_SIZE >> shift;
+		if(n_q * 2 + n_t == 0)
+			continue;
+		// triangle list of the bin in the canonical order: quads by slot, then large triangles ascending
+		static uint tris[65536];
+		int n_tris = 0;
+		for(int i = 0; i < n_q * 2; i++) {
+			const uint w = g_bin_quads[q_off + (i >> 1)];
+			if(!((w >> (30 + (i & 1))) & 1))
+				tris[n_tris++] = (w & 0x0fffffffu) * 2 + (i & 1);
+		}
+		const int first_large = n_tris;
+		for(int i = 0; i < n_t; i++)
+			tris[n_tris++] = g_bin_tris[t_off + i];
+		for(int i = first_large + 1; i < n_tris; i++) // insertion sort of the (short) large part
+			for(int j = i; j > first_large && tris[j - 1] > tris[j]; j--) {
+				uint t = tris[j];
+				tris[j] = tris[j - 1], tris[j - 1] = t;
+			}
+		for(int row = 0; row < n_rows; row++) {
+			int n[4] = {0, 0, 0, 0};
+			for(int i = 0; i < n_tris; i++) {
+				const uint scan_offset = STORAGE_TRI_SCAN_OFFSET + tris[i] * 2;
+				const uvec4 val0 = g_uvec4_storage[scan_offset + 0], val1 = g_uvec4_storage[scan_offset + 1];
+				const int min_by = clamp(glsl_int(val0.w & 0xffff) - bin_pos.y, 0, BIN_MASK) >> shift;
+				const int max_by = clamp(glsl_int(val0.w >> 16) - bin_pos.y, 0, BIN_MASK) >> shift;
+				if(row < min_by || row > max_by)
+					continue;
+				ScanlineParams scan = loadScanlineParamsRow(val0, val1, vec2(float(bin_pos.x), float(bin_pos.y + (min_by << shift))));
+				uvec3 bits[2] = {uvec3(0u, 0u, 0u), uvec3(0u, 0u, 0u)};
+				for(int by = min_by; by <= row; by++) // the incremental state, advanced from the triangle's first row
+					for(int s = 0; s < steps; s++)
+						bits[s] = rasterBinStep(scan);
+				const uint bx_mask = bits[0].z | (steps == 2 ? bits[1].z : 0u);
+				for(int bx = 0; bx < 4; bx++) {
+					if(!((bx_mask >> bx) & 1) || n[bx] >= 4096)
+						continue;
+					BlockEntry &e = lists[bx][n[bx]++];
+					e.tri = tris[i];
+					e.mins[0] = bits[0].x, e.maxs[0] = bits[0].y, e.mins[1] = bits[1].x, e.maxs[1] = bits[1].y;
+				}
+			}
+			for(int bx = 0; bx < 4; bx++) {
+				const int cnt = n[bx], startx = bx * 8;
+				const ivec2 block_pos(bin_pos.x + startx, bin_pos.y + (row << shift));
+				for(int i = 0; i < cnt; i++) {
+					BlockEntry &e = lists[bx][i];
+					uint nf0 = 0, nf1 = 0;
+					vec2 cpos = rasterHalfBlockCentroid(e.mins[0], e.maxs[0], startx, nf0);
+					if(!high)
+						cpos = cpos + rasterHalfBlockCentroid(e.mins[1], e.maxs[1], startx, nf1);
+					const vec2 at = cpos * (0.5f / float(nf0 + nf1)) + vec2(float(block_pos.x), float(block_pos.y));
+					e.key = rasterBlockDepth(at, e.tri, high ? float(0x7fffe) : float(0x3ffffe));
+				}
+				if(high || cnt > 3) // stable insertion sort by depth key
+					for(int i = 1; i < cnt; i++)
+						for(int j = i; j > 0 && lists[bx][j - 1].key > lists[bx][j].key; j--) {
+							BlockEntry t = lists[bx][j];
+							lists[bx][j] = lists[bx][j - 1], lists[bx][j - 1] = t;
+						}
+				shadeList(lists[bx], cnt, high ? 1 : 2, startx, block_pos, width, height, image);
+			}
+		}
+		q_off += n_q, t_off += n_t;
+	}
+	return 0;
+}
 uint32_t ref_encode_rgba8(const float *rgba) { return encodeRGBA8(vec4(rgba[0], rgba[1], rgba[2], rgba[3])); }
 
 } // extern "C"
@@ -451,10 +584,10 @@ def main():
               "struct Frustum { vec4 ws_origin0, ws_dir0, ws_dirx, ws_diry; };",
               "struct Lighting { vec4 ambient_color, sun_color, sun_dir; float sun_power, ambient_power; };",
               "struct Config { Frustum frustum; mat4 view_proj_matrix; Lighting lighting; vec4 background_color; int enable_backface_culling; };",
-              "static uint g_colors[8], g_normals[8];",
-              "static vec2 g_tex_coords[8];",
-              "static uint g_instance_colors[256];",
-              "static vec4 g_instance_uv_rects[256];",
+              "static uint g_colors[524288], g_normals[524288];",
+              "static vec2 g_tex_coords[524288];",
+              "static uint g_instance_colors[65536];",
+              "static vec4 g_instance_uv_rects[65536];",
               "// the Vulkan sampler is not part of the source: textureGrad records its arguments and returns a preset colour",
               "static int opaque_texture = 0, transparent_texture = 1;",
               "static vec4 g_tex_preset; static float g_tex_args[8];",
@@ -469,7 +602,7 @@ def main():
               "static uint g_bin_quads[MAX_VISIBLE_QUADS * 8], g_bin_tris[MAX_VISIBLE_QUADS * 64];",
               "static int s_bins[128 * 128];",
               "static uvec4 g_uvec4_storage[MAX_VISIBLE_QUADS * 14];",
-              "static uint g_normals_storage[8];",
+              "static uint g_normals_storage[MAX_VISIBLE_QUADS * 2];",
               "static vec3 s_ray_dir0;",
               "static uint s_rejected_quads[REJECTION_TYPE_COUNT];",
               "static uint s_num_visible[2];",

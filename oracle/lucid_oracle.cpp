@@ -18,7 +18,8 @@
 //     oracle_fn_* entry points below must reproduce every word (tests/test_ref_shader_pins.py); at scene
 //     level the reference's setup / bin-count / bin-dispatch functions, run quad by quad, give this
 //     file's visible counts, per-bin counts, per-bin lists, HIGH-bin set and per-pixel fragment counts
-//     on three seeded scenes;
+//     on four seeded scenes, and -- with the raster flow restated a second time around the reference's
+//     key, shading and reduction functions -- its RGBA8 images on the three scenes without textures;
 //     the host-side camera / frustum math is pinned the same way against libfwk (oracle/Makefile ref);
 //   * UNPINNED (no reference output obtainable): the driver's pow and the Vulkan sampler's filtering
 //     (both defined here: DESIGN.md sections 4 and 9; stand-ins on both sides of the shadeSample

@@ -35,7 +35,8 @@ lib.ref_half_block.argtypes = [C.c_uint32, C.c_uint32, C.c_int, vp, C.c_float, C
 lib.ref_reduce_pixel.argtypes = [vp, vp, C.c_int, vp]
 lib.ref_shade_sample.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, C.c_int, C.c_int, vp]
 lib.ref_store_quad.argtypes = [C.c_uint32, vp, vp, vp, vp]
-lib.ref_bin_scene.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+lib.ref_bin_scene.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+lib.ref_shade_image.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_uint32, vp]
 lib.ref_frag_counts.argtypes = [C.c_int, C.c_int, vp, vp, vp]
 lib.ref_frag_counts.restype = C.c_uint64
 lib.ref_encode_rgba8.argtypes = [vp]
@@ -206,9 +207,9 @@ for k in range(24):
 from tests import parity_util as pu  # noqa: E402
 out["bin_scenes"] = []
 small = pu.small_scenes()
-for name in ("soup_close", "arch", "soup"):
+for name in ("soup_close", "arch", "soup", "meshlets"):
     sc = small[name]
-    cfg, inst, _, _ = api.prepare_frame(sc)
+    cfg, inst, inst_cols, inst_rects = api.prepare_frame(sc)
     cw = np.frombuffer(bytes(cfg), np.uint32).copy()
     pos = np.ascontiguousarray(sc["positions"], np.float32)
     quads = np.ascontiguousarray(sc["quads"], np.uint32)
@@ -217,8 +218,13 @@ for name in ("soup_close", "arch", "soup"):
     counts = np.zeros(2 * bc, np.int32)
     lists = np.zeros(32768 * 72, np.uint32)
     n = np.zeros(4, np.uint32)
+    # per input quad: instance flags | instance id << 16 (instances are consecutive slices of the index buffer)
+    flags_id = np.repeat(inst[:, 3].astype(np.uint32) | (np.arange(inst.shape[0], dtype=np.uint32) << 16), inst[:, 2])
+    opt = lambda key, dt: None if sc.get(key) is None else np.ascontiguousarray(sc[key], dt)  # noqa: E731
+    vcol, vnrm, vuv = opt("colors", np.uint32), opt("normals", np.uint32), opt("uvs", np.float32)
     rc = lib.ref_bin_scene(ptr(cw), sc["width"], sc["height"], ptr(pos), pos.shape[0], ptr(quads), quads.shape[0],
-                           ptr(counts), ptr(lists), ptr(n))
+                           ptr(flags_id), None if vcol is None else ptr(vcol), None if vnrm is None else ptr(vnrm),
+                           None if vuv is None else ptr(vuv), ptr(counts), ptr(lists), ptr(n))
     assert rc == 0, (name, rc)
     nq, nt = int(n[2]), int(n[3])
     bq = pu.canonical_lists(lists[:nq], counts[:bc])
@@ -230,7 +236,20 @@ for name in ("soup_close", "arch", "soup"):
     frag_total = int(lib.ref_frag_counts(sc["width"], sc["height"], ptr(counts), ptr(frag), ptr(is_high)))
     print("   fragments", frag_total, "inside the image", int(frag.sum()), "max per pixel", int(frag.max()),
           "HIGH bins", int(is_high.sum()))
+    # the image, for scenes without textures (the sampler is not part of the reference's source)
+    image_sha = None
+    if not any(int(f) & 0x040 for f in inst[:, 3]):
+        bg = sc["background"]
+        bg8 = sum(int(min(max(float(bg[i]), 0.0), 1.0) * 255.0 + 0.5) << (8 * i) for i in range(3)) | 0xFF000000
+        image = np.zeros(sc["width"] * sc["height"], np.uint32)
+        ic = np.ascontiguousarray(inst_cols, np.uint32)
+        ir = np.ascontiguousarray(inst_rects, np.float32)
+        assert lib.ref_shade_image(ptr(cw), sc["width"], sc["height"], ptr(counts), ptr(is_high), ptr(ic), ptr(ir),
+                                   inst.shape[0], bg8, ptr(image)) == 0
+        image_sha = hashlib.sha256(image.tobytes()).hexdigest()
+        print("   image digest", image_sha[:16], "non-background pixels", int((image != bg8).sum()))
     out["bin_scenes"].append({"scene": name, "max_visible_quads": 32768, "visible": [int(n[0]), int(n[1])],
+                              "image_sha256": image_sha,
                               "fragments": frag_total, "fragments_in_image": int(frag.sum()),
                               "high_bins": np.flatnonzero(is_high).tolist(),
                               "frag_counts_sha256": hashlib.sha256(frag.tobytes()).hexdigest(),
