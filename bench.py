@@ -1,28 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- exact-OIT frames/s of the B200 rasteriser on BASELINE.json's synthetic configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config I] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config I] [--impl ours|reference] [--mode split|views]
 
-A "step" is one frame: quad setup -> binning -> raster low/high -> image, for one view of the
-workload scene.  At N=1 the workload is BASELINE.json configs[1] (1M-triangle meshlet scene,
-1920x1080).  With N>1 every rank renders its own view of an orbit around the same scene per step
-(views sharded per GPU, no data-path collective: "scaling": "weak"); `--mode split` instead splits
-the bin rows of ONE frame over the ranks and stores every strip straight into rank 0's image over
-NVLink (strong scaling, reported for config 3 in DESIGN.md).
+A "step" is one frame: quad setup -> binning -> raster low/high -> image.  The workload is the configuration
+BASELINE.json's target is quoted on: configs[3], the 10M-triangle textured architecture scene at 3840x2160.
+  N = 1   one GPU renders the whole frame;
+  N > 1   `--mode split` (the default): the bin rows of that SAME frame are split over the ranks as
+          cost-balanced row-major bin ranges, every rank stores its strip straight into rank 0's image over
+          NVLink ("scaling": "strong").  The line also carries "views": the 64-view orbit of the 1M-triangle
+          scene (configs[4]) with the views sharded over the ranks, no data-path collective.
 
-`value` is frames/s with geometry resident in HBM (per-frame config + instance upload included);
-`e2e` is the same frame through lucid_render() with host buffers in and the RGBA8 image plus
-LucidInfo copied back to the host inside the timed region.  `--impl reference` times the CPU
-restatement of the reference shaders (oracle/) with all host threads: the reference's own Vulkan
-path cannot run on this image (no ICD, no shaderc).
+`value` is frames/s with geometry resident in HBM, timed with CUDA events on the stream the kernels are launched
+on.  The frame's own per-frame inputs (352-byte LucidConfig as kernel arguments, 36 bytes per instance) are
+submitted inside the bracket, but the instance copy runs on the library's upload stream at submission time and
+the host runs up to three frames ahead, so in steady state that copy overlaps the previous frame.  `e2e` is the
+same frame through lucid_render() with HOST buffers in and the RGBA8 image + LucidInfo copied back into pinned
+host memory inside the timed region (wall clock).  `sustained` is at least a second of back-to-back frames by
+wall clock.  `--impl reference` times the CPU restatement of the reference shaders (oracle/) with all host
+threads: the reference's own Vulkan path cannot run on this image (no ICD, no shaderc).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
+import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -33,10 +38,22 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     0: "config0: 100k-triangle quad soup, 50% alpha=0.5, 1280x720",
     1: "config1: 1M-triangle meshlet scene (489 patches of 32x32 quads), mixed opaque/transparent, 1920x1080",
-    2: "config2: hairball-like dense overlap, 5M triangles, 3840x2160",
+    2: "config2: hairball-like dense overlap (median depth complexity 72), 5M triangles, 3840x2160",
     3: "config3: 10M-triangle architecture scene, textured atlas shading, 3840x2160",
     4: "config4: 64-view orbit of the 1M-triangle scene, 1920x1080",
 }
+DEFAULT_CONFIG = 3  # BASELINE.json: "4K exact-OIT frames/sec on a 10M-triangle synthetic scene"
+KERNEL_SOURCES = ["lucid_b200/csrc/common.cuh", "lucid_b200/csrc/setup.cu", "lucid_b200/csrc/binning.cu",
+                  "lucid_b200/csrc/raster.cu"]
+
+
+def kernel_source_hash() -> str:
+    """Digest of the kernel sources: profiles/dram_traffic.json records the one its ncu capture was taken at."""
+    h = hashlib.sha256()
+    for rel in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, rel), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 def load_peaks():
@@ -47,54 +64,60 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_SAMPLER = r"""
+import json, sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+sm, bits = [], 0
+print("ready", flush=True)
+import select
+while True:
+    if select.select([sys.stdin], [], [], 0.005)[0]:
+        break
+    try:
+        sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+    except Exception:
+        pass
+print(json.dumps({"sm": sm, "bits": bits, "max": mx}), flush=True)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML every ~2 ms while the timed region runs
-    (the region lasts tens of milliseconds, too short for `nvidia-smi -lms`)."""
+    """SM clock and throttle reasons sampled through NVML every ~5 ms while the timed region runs.  The poller
+    is a separate PROCESS: as a thread of this one it took the GIL (and NVML's locks) in the middle of a frame's
+    launches, which showed up as millisecond outliers in the multi-GPU step times."""
 
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int):
-        self.index = index
-        self.sm, self.reason_bits = [], 0
-        self.stop_flag = False
-        self.thread = None
-        self.handle = None
-        self.max_mhz = None
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+        self.proc = None
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() \
-                else self.index
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER, str(self.phys)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            if self.proc.stdout.readline().strip() != "ready":
+                self.proc = None
         except Exception:
-            self.handle = None
-            return
-        self.thread = threading.Thread(target=self._poll, daemon=True)
-        self.thread.start()
-
-    def _poll(self):
-        nv = self.nv
-        while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
-                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-            except Exception:
-                pass
-            time.sleep(0.002)
+            self.proc = None
 
     def stop(self):
-        if self.handle is None:
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        self.stop_flag = True
-        self.thread.join(timeout=1.0)
-        reasons = sorted(n for n, bit in self.REASONS.items() if self.reason_bits & bit)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
-                "reasons": reasons, "samples": len(self.sm)}
+        try:
+            out, _ = self.proc.communicate("stop\n", timeout=5.0)
+            d = json.loads(out.strip().splitlines()[-1])
+        except Exception:
+            self.proc.kill()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = sorted(n for n, bit in self.REASONS.items() if d["bits"] & bit)
+        return {"sm_mhz": float(np.median(d["sm"])) if d["sm"] else None, "sm_max_mhz": d["max"], "reasons": reasons,
+                "samples": len(d["sm"])}
 
 
 def make_scene(config: int, scale: float):
@@ -110,7 +133,7 @@ def view_camera(scene, view: int, num_views: int = 64):
 
 
 def algorithmic_bytes(stats: dict, scene, width, height):
-    """SURVEY.md 8(d) byte formulas with this implementation's record sizes (DESIGN.md)."""
+    """SURVEY.md 8(d) byte formulas with this implementation's record sizes (DESIGN.md section 6)."""
     n_in = stats["input_quads"]
     n_vis = stats["visible_small"] + stats["visible_large"]
     n_bq, n_bt = stats["bin_quads"], stats["bin_tris"]
@@ -123,6 +146,145 @@ def algorithmic_bytes(stats: dict, scene, width, height):
     dispatch = count + 4 * (n_bq + n_bt)
     raster = 4 * (n_bq + n_bt) + (96 + attr / 2) * t_bin + 4 * n_px
     return {"setup": setup, "bin_count": count, "bin_dispatch": dispatch, "raster": raster}
+
+
+def depth_complexity(frag_counts: np.ndarray) -> dict:
+    cov = frag_counts[frag_counts > 0]
+    if cov.size == 0:
+        return {"covered_frac": 0.0, "median": 0, "p99": 0, "max": 0}
+    return {"covered_frac": round(float(cov.size) / frag_counts.size, 4), "median": float(np.median(cov)),
+            "p99": float(np.percentile(cov, 99)), "max": int(cov.max())}
+
+
+class Rig:
+    """One renderer on this rank's GPU with a scene resident, plus what the timed loops share."""
+
+    def __init__(self, args, config, torch, dist, rank, world, local_rank, stream):
+        from lucid_b200 import api
+        self.api, self.torch, self.dist = api, torch, dist
+        self.rank, self.world = rank, world
+        self.scene = make_scene(config, args.scale)
+        self.width, self.height = self.scene["width"], self.scene["height"]
+        self.stream = stream
+        self.r = api.LucidRenderer(self.width, self.height, 0, args.mvq, device=local_rank, stream=stream.cuda_stream)
+        self.r.set_scene(self.scene)
+        self.inst, self.cols, self.rects = api.build_instances(self.scene["draw_calls"], self.scene["materials"])
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        self.host_imgs = [torch.empty((self.height, self.width), dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def config_for(self, view):
+        api = self.api
+        cam = api.make_camera(view_camera(self.scene, view), self.width, self.height)
+        return api.make_config(cam, len(self.inst), self.scene["background"])
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def close(self):
+        self.r.close()
+
+
+def timed_steps(rig, args, render, after_frame, steps):
+    """W warm-up steps, then exactly `steps` steps between a barrier + synchronize on both sides; every step is
+    bracketed by CUDA events on the launching stream, L2 flushed (untimed) between steps.  Returns the per-step
+    times of this rank (ms) and the wall time of the loop."""
+    torch = rig.torch
+    plain = rig.api.RENDER_ASYNC | rig.api.RENDER_SKIP_INFO | rig.api.RENDER_NO_STAGE_TIMES
+    for w in range(args.warmup):  # the same sequence as a timed step
+        render(w, plain)
+        after_frame()
+    rig.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    t_wall = time.time()
+    for k in range(steps):
+        rig.flush.fill_(k & 0xFF)  # L2 flush between timed iterations (untimed)
+        starts[k].record(rig.stream)
+        render(args.warmup + k, plain)
+        after_frame()
+        stops[k].record(rig.stream)
+    rig.barrier()
+    wall = time.time() - t_wall
+    return np.array([s.elapsed_time(e) for s, e in zip(starts, stops)], np.float64), wall
+
+
+def max_over_ranks(rig, value: float) -> float:
+    if rig.dist is None:
+        return value
+    t = rig.torch.tensor([value], device="cuda", dtype=rig.torch.float64)
+    rig.dist.all_reduce(t, op=rig.dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sustained_run(rig, render, after_frame, seconds: float, frames_per_step: int):
+    """Back-to-back frames for at least `seconds` of wall clock, no flush in between (the scene's records are
+    several times the L2), device-timed by one event pair around the whole run."""
+    torch = rig.torch
+    plain = rig.api.RENDER_ASYNC | rig.api.RENDER_SKIP_INFO | rig.api.RENDER_NO_STAGE_TIMES
+    rig.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(rig.stream)
+    n = 0
+    while True:
+        for _ in range(16):
+            render(n, plain)
+            after_frame()
+            n += 1
+        done = time.perf_counter() - t0 >= seconds  # the host is never more than three frames ahead of the GPU
+        if rig.dist is not None:  # every rank runs the same number of frames: rank 0's clock decides
+            stop = rig.torch.tensor([1.0 if done else 0.0], device="cuda")
+            rig.dist.broadcast(stop, src=0)
+            done = float(stop.item()) > 0
+        if done:
+            break
+    e1.record(rig.stream)
+    rig.barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = max_over_ranks(rig, e0.elapsed_time(e1))
+    return {"frames": n * frames_per_step, "wall_s": round(wall, 3), "device_s": round(dev_ms / 1e3, 3),
+            "value": round(n * frames_per_step / (dev_ms / 1e3), 3), "unit": "frames/s",
+            "note": "back-to-back frames, no L2 flush (per-frame records exceed the L2), one CUDA event pair"}
+
+
+def e2e_run(rig, frame, steps, frames_per_step):
+    for w in range(3):
+        frame(w)
+    rig.r.wait()
+    rig.barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        frame(k)
+    rig.r.wait()
+    rig.barrier()
+    return frames_per_step * steps / max_over_ranks(rig, time.perf_counter() - t0)
+
+
+def run_views(args, torch, dist, rank, world, local_rank, stream, config):
+    """Multi-view batch: view v of the orbit goes to rank v % world; no data-path communication."""
+    rig = Rig(args, config, torch, dist, rank, world, local_rank, stream)
+    api, r = rig.api, rig.r
+
+    def render(step, flags):
+        r.render(rig.config_for((step * world + rank) % 64), rig.inst, rig.cols, rig.rects, flags=flags)
+
+    step_ms, _ = timed_steps(rig, args, render, lambda: None, args.steps)
+    total_ms = max_over_ranks(rig, float(step_ms.sum()))
+    e2e_steps = max(args.steps, 3)
+
+    def e2e_frame(k):
+        r.render(rig.config_for((k * world + rank) % 64), rig.inst, rig.cols, rig.rects,
+                 out=rig.host_imgs[k & 1].data_ptr(), flags=api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES)
+
+    e2e = e2e_run(rig, e2e_frame, e2e_steps, world)
+    out = {"workload": WORKLOADS[4], "value": round(world * 1000.0 * args.steps / total_ms, 3), "unit": "frames/s",
+           "ms_per_step": round(total_ms / args.steps, 4), "scaling": "weak",
+           "e2e": {"value": round(e2e, 3), "unit": "frames/s", "h2d_bytes_per_step": int(len(rig.inst) * 36 + 352),
+                   "d2h_bytes_per_step": int(rig.width * rig.height * 4 + (1152 + 10 * r.bin_count) * 4)}}
+    rig.close()
+    return out
 
 
 def run_ours(args):
@@ -152,29 +314,43 @@ def run_ours(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    scene = make_scene(args.config, args.scale)
-    width, height = scene["width"], scene["height"]
     # a stream of our own, made torch's current stream: the library launches every kernel on the stream it
     # is handed (handle 0 would make it create a private one, invisible to torch.cuda.Event), so the
     # flush, the timing events and the kernels are all ordered on this one stream
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    split = args.mode == "split" and world > 1
+    mode = args.mode or ("split" if world > 1 else "single")
+    if world == 1:
+        mode = "single"
+    if mode == "views":  # the secondary workload on its own (configs[4]); the line is that run's
+        v = run_views(args, torch, dist, rank, world, local_rank, stream, 1 if args.config == DEFAULT_CONFIG else args.config)
+        if rank == 0:
+            line = {"metric": "exact_oit_frames_per_sec", "value": v["value"], "unit": "frames/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": v["ms_per_step"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": v["workload"], "parallelism": "views sharded x%d" % world,
+                               "l2": "256 MiB device memset between timed frames (untimed)"},
+                    "e2e": v["e2e"], "gpu_launches": int(8 * args.steps)}
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    split = mode == "split"
+    rig = Rig(args, args.config, torch, dist, rank, world, local_rank, stream)
+    r, scene, width, height = rig.r, rig.scene, rig.width, rig.height
+    inst, cols, rects = rig.inst, rig.cols, rig.rects
     nby = (height + 31) // 32
-    r = api.LucidRenderer(width, height, 0, args.mvq, device=local_rank, stream=stream.cuda_stream)
-    r.set_scene(scene)
-    inst, cols, rects = api.build_instances(scene["draw_calls"], scene["materials"])
-    rows = None
+    rows, split_kind = None, None
     if split:
         # ownership from the measured raster cost of a full calibration frame (what an application takes
         # from the previous frame); rank 0's measurement is used by every rank.  Default: contiguous
         # row-major bin ranges of equal cost (a heavy bin row may be shared by two ranks); --split-rows
         # keeps whole bin rows, --equal-rows equal row counts.
         from lucid_b200 import multigpu
-        cam0 = api.make_camera(view_camera(scene, 0), width, height)
         for _ in range(2):
-            r.render(api.make_config(cam0, len(inst), scene["background"]), inst, cols, rects)
+            r.render(rig.config_for(0), inst, cols, rects)
         cost = torch.from_numpy(r.read_bin_costs().astype(np.float64)).cuda()
         dist.broadcast(cost, src=0)
         cost = cost.cpu().numpy()
@@ -191,8 +367,7 @@ def run_ours(args):
             # setup), and the ranges are cut again
             for _ in range(args.balance_iters):
                 for k in range(3):
-                    r.render(api.make_config(cam0, len(inst), scene["background"]), inst, cols, rects,
-                             flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
+                    r.render(rig.config_for(0), inst, cols, rects, flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
                 mine = float(np.median([r.stage_times(i)[1:7].sum() for i in range(2)]))
                 times = torch.zeros(world, device="cuda", dtype=torch.float64)
                 times[rank] = mine
@@ -205,11 +380,6 @@ def run_ours(args):
             rows = ranges[rank]
             split_kind = "row-major bin ranges balanced on measured cost, %d feedback steps" % args.balance_iters
 
-    def config_for(step):
-        view = 0 if split else (step * world + rank) % 64
-        cam = api.make_camera(view_camera(scene, view), width, height)
-        return api.make_config(cam, len(inst), scene["background"])
-
     # composite target for the bin-row split: every rank stores into rank 0's image over NVLink
     peer_ptr = None
     if split:
@@ -217,53 +387,30 @@ def run_ours(args):
         dist.broadcast_object_list(handle, src=0)
         if rank != 0:
             peer_ptr = r.ipc_open_image(handle[0])
+    frame_token = torch.zeros(1, device="cuda")
 
-    def render(step, **kw):
+    def view_of(step):
+        return 0 if split else step % 64
+
+    def render(step, flags):
         if peer_ptr is not None and args.composite == "stores":
             # the raster kernels store their pixels straight into rank 0's image
-            r.render(config_for(step), inst, cols, rects, out_device_ptr=peer_ptr, out_pitch=width * 4, **kw)
+            r.render(rig.config_for(view_of(step)), inst, cols, rects, out_device_ptr=peer_ptr, out_pitch=width * 4,
+                     flags=flags)
         else:
-            r.render(config_for(step), inst, cols, rects, **kw)
+            r.render(rig.config_for(view_of(step)), inst, cols, rects, flags=flags)
             if peer_ptr is not None:  # own image first, then the owned bins as whole 128-byte rows
                 r.composite_to(peer_ptr, width * 4)
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    frame_token = torch.zeros(1, device="cuda")
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # timed frames carry only the frame's first and last event: per-stage events between the kernels would
-    # keep each launch from overlapping its predecessor's tail (programmatic dependent launch)
-    plain = api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES
-    for w in range(args.warmup):  # the same sequence as a timed step, completion all-reduce included
-        render(w, flags=plain)
-        if split:
+    def after_frame():
+        if split:  # the frame is complete when every rank's strip has landed in rank 0's image
             dist.all_reduce(frame_token)
-    barrier()
 
-    # NVML polling takes driver locks: only the rank that prints the line samples its GPU
+    # NVML is polled by a separate process, for the GPU of the rank that prints the line
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # --trace-split: an extra event between the frame and the completion all-reduce of every step
-    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if (split and args.trace_split) else None
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    t_wall = time.time()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (untimed)
-        starts[k].record(stream)
-        render(args.warmup + k, flags=plain)
-        if split:  # the frame is complete when every rank's strip has landed in rank 0's image
-            if mids is not None:
-                mids[k].record(stream)
-            dist.all_reduce(frame_token)
-        stops[k].record(stream)
-    barrier()
-    wall = time.time() - t_wall
+    step_ms, wall = timed_steps(rig, args, render, after_frame, args.steps)
     kept = min(args.steps, 64)
     frame_ms = float(np.mean([r.stage_times(i)[7] for i in range(kept)]))  # library's own first->last event
     rank_frame_ms = None
@@ -272,74 +419,65 @@ def run_ours(args):
         t[rank] = frame_ms
         dist.all_reduce(t)
         rank_frame_ms = [round(float(x), 4) for x in t.cpu().numpy()]
-    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)], np.float64)
-    if mids is not None:  # where a step's time goes on this rank: submission + frame, then waiting for the others
-        a = np.median([s.elapsed_time(m) for s, m in zip(starts, mids)])
-        b = np.median([m.elapsed_time(e) for m, e in zip(mids, stops)])
-        lib = np.median([r.stage_times(i)[7] for i in range(min(args.steps, 64))])
-        sys.stderr.write(f"[trace-split] rank {rank}: start->frame end {a:.4f} ms (library frame {lib:.4f} ms), "
-                         f"frame end->all-reduce done {b:.4f} ms, step median {np.median(step_ms):.4f} ms; steps "
-                         f"{[round(float(x), 3) for x in step_ms]}\n")
-    total_ms = torch.tensor([float(step_ms.sum())], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    if split and args.trace_split:
+        sys.stderr.write(f"[trace-split] rank {rank}: library frame {frame_ms:.4f} ms, step median "
+                         f"{np.median(step_ms):.4f} ms; steps {[round(float(x), 3) for x in step_ms]}\n")
+    total_ms = max_over_ranks(rig, float(step_ms.sum()))
+    step_median = max_over_ranks(rig, float(np.median(step_ms)))
+
+    sustained = sustained_run(rig, render, after_frame, args.sustained_seconds, 1)
+    clocks = sampler.stop()
+
     # per-stage CUDA-event times: the same frames again, same L2 flush, this time with an event after every
     # stage (recorded on the stream the kernels are launched on; the library keeps its last 64 frames)
     for k in range(kept):
-        flush.fill_(k & 0xFF)
-        render(args.warmup + k, flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
-    barrier()
+        rig.flush.fill_(k & 0xFF)
+        render(args.warmup + k, api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
+        after_frame()
+    rig.barrier()
     stage = np.mean([r.stage_times(i).astype(np.float64) for i in range(kept)], axis=0)
 
     # end to end through the C ABI: host instance arrays in (the library stages them through pinned
     # memory), RGBA8 image + LucidInfo read back into pinned host memory every frame.  Frames are
     # submitted asynchronously: the copy-out of frame n overlaps the rendering of frame n+1.
-    host_imgs = [torch.empty((height, width), dtype=torch.int32).pin_memory() for _ in range(2)]
     e2e_steps = max(args.steps, 3)
 
     def e2e_frame(k):
         if split:
-            # every rank rasterises its bin rows into rank 0's image, then rank 0 reads it back
-            render(k, flags=api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES)
+            # every rank rasterises its bin ranges into rank 0's image, then rank 0 reads it back
+            render(k, api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES)
             dist.all_reduce(frame_token)
             if rank == 0:
                 torch.cuda.current_stream().synchronize()
-                r.read_image_into(host_imgs[k & 1].data_ptr())
+                r.read_image_into(rig.host_imgs[k & 1].data_ptr())
         else:
-            r.render(config_for(k), inst, cols, rects, out=host_imgs[k & 1].data_ptr(),
+            r.render(rig.config_for(view_of(k)), inst, cols, rects, out=rig.host_imgs[k & 1].data_ptr(),
                      flags=api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES)
 
-    for w in range(3):
-        e2e_frame(w)
-    r.wait()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_frame(k)
-    r.wait()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    clocks = sampler.stop()
+    e2e_value = e2e_run(rig, e2e_frame, e2e_steps, 1)
 
-    # counters of one frame for the roofline arithmetic
-    r.render(config_for(0), inst, cols, rects)
+    # counters of one frame for the roofline arithmetic, and the frame's depth complexity
+    r.render(rig.config_for(0), inst, cols, rects, flags=api.RENDER_FRAG_COUNTS)
     info = r.read_info()
     stats = api.decode_stats(info, r.bin_count, width, height)
+    depth = depth_complexity(r.read_frag_counts()) if not split else None
 
-    frames_per_step = 1 if split else world
     tris_per_frame = 2 * stats["input_quads"]
     ms_per_step = total_ms / args.steps
-    value = frames_per_step * 1000.0 / ms_per_step
-    e2e_value = frames_per_step * e2e_steps / e2e_s
+    value = 1000.0 / ms_per_step
+
+    views = None
+    if split and not args.no_views:
+        if peer_ptr is not None:
+            r.ipc_close_image(peer_ptr)
+            peer_ptr = None
+        rig.close()
+        views = run_views(args, torch, dist, rank, world, local_rank, stream, 1)
 
     if rank == 0:
         peak, peak_src = load_peaks()
         ab = algorithmic_bytes(stats, scene, width, height)
-        # LOW and HIGH bins share the two raster kernels (block lists, then block sort + shading)
+        # LOW and HIGH bins share the raster kernels (block lists, then block sort + shading)
         stage_names = ["setup", "bin_count", "bin_scan", "bin_dispatch", "raster_lists", "raster_shade", "finish"]
         stage_ms = {n: round(float(stage[i]), 4) for i, n in enumerate(stage_names)}
         stage_ms["frame_with_stage_events"] = round(float(stage[7]), 4)
@@ -359,12 +497,23 @@ def run_ours(args):
         achieved = ab[dominant] / (dom_ms * 1e-3) / 1e9
         traffic, issue_pct, traffic_src = None, None, None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and not split:
             with open(tpath) as f:
-                captured = json.load(f).get(f"config{args.config}", {})
-            traffic = captured.get(dominant)
-            issue_pct = captured.get("issue_active_pct", {}).get(dominant)
-            traffic_src = captured.get("source")
+                tfile = json.load(f)
+            captured = tfile.get(f"config{args.config}", {})
+            # only a capture taken with the kernels as they are now describes this run
+            if tfile.get("kernel_source_hash") == kernel_source_hash():
+                traffic = captured.get(dominant)
+                issue_pct = captured.get("issue_active_pct", {}).get(dominant)
+                traffic_src = captured.get("source")
+            else:
+                traffic_src = "none: profiles/dram_traffic.json was captured with different kernel sources"
+        counters = {k: stats[k] for k in ("visible_small", "visible_large", "bin_quads", "bin_tris", "low_bins",
+                                          "high_bins", "promoted_bins", "fragments", "half_block_tris")}
+        if depth is not None:
+            counters["depth_complexity"] = depth  # fragments per covered pixel of this frame
+        if split:
+            counters["scope"] = "rank 0's bin range only (every rank counts its own bins)"
         line = {
             "metric": "exact_oit_frames_per_sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
@@ -375,19 +524,20 @@ def run_ours(args):
                        "parallelism": ("bin-row split x%d (%s), P2P composite; rank 0 owns %s" %
                                        (world, split_kind + "; composite by " +
                                         ("a bin-row copy kernel" if args.composite == "copy" else "direct raster stores"),
-                                        list(rows))) if split else
-                       ("views sharded x%d" % world if world > 1 else "single GPU"),
-                       "l2": "256 MiB device memset between timed frames (untimed)"},
+                                        list(rows))) if split else "single GPU",
+                       "l2": "256 MiB device memset between timed frames (untimed); the frame's own records "
+                             "(~1 GB) exceed the 126 MB L2"},
             "mtris_per_sec": round(value * tris_per_frame / 1e6, 2),
+            "ms_per_step_median": round(step_median, 4),
             "stage_ms": stage_ms, "rank_frame_ms": rank_frame_ms,
             "stage_ms_source": "a second pass over the same %d frames with a CUDA event after every stage; the timed "
                                "frames only carry the frame's first and last event (events between kernels disable "
                                "the launch overlap)" % kept,
-            "counters": {k: stats[k] for k in ("visible_small", "visible_large", "bin_quads", "bin_tris", "low_bins",
-                                               "high_bins", "promoted_bins", "fragments", "half_block_tris")},
+            "counters": counters,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": round(achieved, 2), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes": int(ab[dominant]),
+                         "kernel_ms": round(float(dom_ms), 4),
                          # from the committed ncu --set full capture of one frame of this workload (profiles/):
                          # DRAM bytes of the stage's kernels, and their SM issue-slot utilisation -- the raster
                          # kernels are bound by instruction issue, not by HBM
@@ -396,30 +546,36 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 3), "unit": "frames/s",
                     "h2d_bytes_per_step": int(len(inst) * 36 + 352),
                     "d2h_bytes_per_step": int(width * height * 4 + info.size * 4)},
+            "sustained": sustained,
             # k_frame_begin, k_quad_cull, k_tri_setup, k_bin_count, k_bin_scan, k_bin_dispatch, k_raster_bins,
             # k_raster_blocks (+ k_info_out when LucidInfo is read back)
             "gpu_launches": int(8 * args.steps),
             "clocks": clocks,
             "wall_s": round(wall, 3),
         }
+        if views is not None:
+            line["views"] = views
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(scene, args)
         print(json.dumps(line), flush=True)
     if peer_ptr is not None:
         r.ipc_close_image(peer_ptr)
-    r.close()
+    if views is None:
+        rig.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
-def cpu_baseline(scene, args, frames: int = 1):
-    """The oracle (CPU restatement of the reference shaders) timed on the host cores."""
+def cpu_baseline(scene, args, frames: int = 3):
+    """The oracle (CPU restatement of the reference shaders) timed on the host cores: one warm-up frame, then
+    `frames` frames of the same workload and camera (a bounded sample: the 4K scenes take seconds per frame)."""
     from lucid_b200 import api
     from oracle.binding import Oracle
     threads = os.cpu_count() or 1
     o = Oracle(scene["width"], scene["height"], 0, args.mvq or 4793490, threads=threads)
     o.set_scene(scene)
     cfg, inst, cols, rects = api.prepare_frame(scene)
+    o.render(cfg, inst, cols, rects)
     times = []
     for _ in range(frames):
         t0 = time.perf_counter()
@@ -427,11 +583,13 @@ def cpu_baseline(scene, args, frames: int = 1):
         times.append(time.perf_counter() - t0)
     o.close()
     return {"value": round(1.0 / float(np.mean(times)), 4), "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"{frames} full frame(s) of the same workload and camera",
+            "sample": f"{frames} full frames of the same workload and camera after one warm-up frame",
             "note": "CPU restatement of the reference shaders (OpenMP); Vulkan/lavapipe unavailable on this image"}
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement on all host threads, on rank 0 only.  Loads oracle/ and the
+    host-only input preparation library -- never the kernels' library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -448,23 +606,33 @@ def run_reference(args):
         cfg = api.make_config(cam, len(inst), scene["background"])
         o.render(cfg, inst, cols, rects)
 
-    for w in range(args.warmup):
-        frame(w)
+    # a frame of the 4K scenes takes the CPU seconds: the run is bounded to about two minutes of CPU work
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        frame(args.warmup + k)
+    frame(0)
+    first = time.perf_counter() - t0
+    budget = 120.0
+    warmup = max(0, min(args.warmup, int(0.2 * budget / max(first, 1e-3))) - 1)
+    steps = max(1, min(args.steps, int(0.8 * budget / max(first, 1e-3))))
+    for w in range(warmup):
+        frame(1 + w)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        frame(1 + warmup + k)
     dt = time.perf_counter() - t0
-    value = args.steps / dt
+    value = steps / dt
     stats = api.decode_stats(o.info, o.bin_count, o.width, o.height)
+    sample = "every step is one full frame of the workload on all host threads"
+    if steps != args.steps:
+        sample += f"; bounded to {steps} timed steps after {warmup + 1} warm-up frames ({first:.1f} s per frame)"
     line = {
         "impl": "reference", "metric": "exact_oit_frames_per_sec", "value": round(value, 4), "unit": "frames/s",
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(1000.0 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warmup + 1,
+        "ms_per_step": round(1000.0 * dt / steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config], "resolution": [scene["width"], scene["height"]],
                    "input_triangles": 2 * stats["input_quads"], "scale": args.scale},
         "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "every step is one full frame of the workload (one orbit view per step)"},
+                         "sample": sample},
         "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -476,17 +644,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=1)
+    ap.add_argument("--config", type=int, default=DEFAULT_CONFIG)
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--mode", default="views", choices=["views", "split"])
+    ap.add_argument("--mode", default=None, choices=["views", "split"],
+                    help="N>1: split (default) = bin ranges of one frame per rank; views = one orbit view per rank")
     ap.add_argument("--mvq", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-views", action="store_true", help="--mode split: skip the secondary views-sharded run")
+    ap.add_argument("--sustained-seconds", type=float, default=1.0)
     ap.add_argument("--equal-rows", action="store_true", help="--mode split: equal row counts instead of cost-balanced")
     ap.add_argument("--split-rows", action="store_true", help="--mode split: whole bin rows, balanced on measured cost")
     ap.add_argument("--composite", default="stores", choices=["copy", "stores"],
                     help="--mode split: how the other ranks' strips reach rank 0's image")
-    ap.add_argument("--trace-split", action="store_true",
-                    help="--mode split: per-rank split of a step into frame and completion wait (stderr)")
+    ap.add_argument("--trace-split", action="store_true", help="--mode split: per-rank step times (stderr)")
     ap.add_argument("--balance-iters", type=int, default=3, help="--mode split: feedback steps of the range balancing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -97,9 +97,10 @@ def load_library(build_if_needed: bool = True):
     if build_if_needed and path == _build.SO_PATH and _build.needs_build():
         try:
             _build.build()
-        except Exception:
-            if not os.path.exists(path):
-                raise
+        except Exception as e:
+            # never run a stale binary silently after a source edit that does not compile
+            if not os.path.exists(path) or os.environ.get("LUCID_B200_ALLOW_STALE") != "1":
+                raise RuntimeError(f"lucid_b200: sources are newer than {path} and the build failed: {e}") from e
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: run `python -m lucid_b200.build` (needs nvcc); there is no CPU fallback")
     lib = C.CDLL(path)
@@ -133,6 +134,13 @@ def load_library(build_if_needed: bool = True):
     lib.lucid_ipc_export_image.argtypes = [vp, vp]
     lib.lucid_ipc_open_image.argtypes = [vp, vp, C.POINTER(vp)]
     lib.lucid_ipc_close_image.argtypes = [vp, vp]
+    _host_prototypes(lib)
+    _lib = lib
+    return lib
+
+
+def _host_prototypes(lib):
+    vp = C.c_void_p
     lib.lucid_host_orbit_camera.argtypes = [C.POINTER(C.c_float * 3), C.c_float, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(Camera)]
     lib.lucid_host_orbit_camera.restype = None
@@ -146,7 +154,25 @@ def load_library(build_if_needed: bool = True):
     lib.lucid_host_build_instances.argtypes = [C.POINTER(DrawCall), C.c_int, C.POINTER(Material), C.c_int, vp, vp,
                                                vp, C.c_int]
     lib.lucid_host_packet_size.argtypes = [C.c_int, C.c_int]
-    _lib = lib
+
+
+_host_lib = None
+
+
+def load_host_library():
+    """The host-side input preparation (include/lucid_host.h) from lucid_b200/_lucid_host.so: plain C++,
+    no CUDA code in the file, so a process that only prepares inputs (the CPU reference arm of bench.py, the
+    CPU tests) never maps the kernels' library.  The same functions are also linked into _lucid_b200.so for
+    C and C++ callers."""
+    global _host_lib
+    if _host_lib is not None:
+        return _host_lib
+    path = _build.HOST_SO_PATH
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "host", "lucid_host.cpp")):
+        _build.build_host()
+    lib = C.CDLL(path)
+    _host_prototypes(lib)
+    _host_lib = lib
     return lib
 
 
@@ -162,7 +188,7 @@ DEFAULT_DEPTH = (1.0 / 16.0, 1024.0)
 
 
 def make_camera(spec: dict, width: int, height: int) -> Camera:
-    lib = load_library()
+    lib = load_host_library()
     cam = Camera()
     fov = float(spec.get("fov", DEFAULT_FOV))
     zn, zf = spec.get("depth", DEFAULT_DEPTH)
@@ -181,7 +207,7 @@ def make_camera(spec: dict, width: int, height: int) -> Camera:
 
 def make_config(camera: Camera, num_instances: int, background=(0.0, 30.0 / 255.0, 30.0 / 255.0, 1.0),
                 backface_culling: bool = False, max_dispatches: int = 256, lighting: Lighting | None = None):
-    lib = load_library()
+    lib = load_host_library()
     if lighting is None:
         lighting = Lighting()
         lib.lucid_host_default_lighting(C.byref(lighting))
@@ -194,7 +220,7 @@ def make_config(camera: Camera, num_instances: int, background=(0.0, 30.0 / 255.
 
 def build_instances(draw_calls, materials):
     """uploadInstances: returns (instances[n] structured, colors u32[n], uv_rects f32[n,4])."""
-    lib = load_library()
+    lib = load_host_library()
     dcs = (DrawCall * len(draw_calls))()
     for i, (mat, nq, off, opts) in enumerate(draw_calls):
         dcs[i] = DrawCall(mat, nq, off, opts)

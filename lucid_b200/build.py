@@ -15,6 +15,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO_PATH = os.path.join(HERE, "_lucid_b200.so")
+# the host-side input preparation (include/lucid_host.h) on its own, without any CUDA code: what a
+# process that only prepares inputs loads (bench.py's CPU reference arm, the CPU tests)
+HOST_SO_PATH = os.path.join(HERE, "_lucid_host.so")
 
 CUDA_SOURCES = ["csrc/setup.cu", "csrc/binning.cu", "csrc/raster.cu", "csrc/capi.cu"]
 HOST_SOURCES = ["host/lucid_host.cpp", "host/lucid_renderer.cpp"]
@@ -30,9 +33,9 @@ def _nvcc() -> str:
 
 
 def needs_build() -> bool:
-    if not os.path.exists(SO_PATH):
+    if not os.path.exists(SO_PATH) or not os.path.exists(HOST_SO_PATH):
         return True
-    t = os.path.getmtime(SO_PATH)
+    t = min(os.path.getmtime(SO_PATH), os.path.getmtime(HOST_SO_PATH))
     for rel in CUDA_SOURCES + HOST_SOURCES + HEADERS + ["build.py"]:
         path = os.path.join(HERE, rel)
         if os.path.exists(path) and os.path.getmtime(path) > t:
@@ -62,7 +65,20 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
+    if out is None:
+        build_host()
     return out or SO_PATH
+
+
+def build_host() -> str:
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-shared", "-I", os.path.join(ROOT, "include"),
+           "-o", HOST_SO_PATH, os.path.join(HERE, "host/lucid_host.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed (lucid_host)")
+    return HOST_SO_PATH
 
 
 if __name__ == "__main__":

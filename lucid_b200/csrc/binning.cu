@@ -454,14 +454,11 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *ev) {
 	int grid = 148 * 4;
 	const size_t hist_bytes = (size_t)p.bin_count * sizeof(int);
-	static bool configured[64] = {}; // function attributes are per device
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if(!configured[dev & 63]) { // up to 128 x 128 bins (7-bit bin coordinates)
+	static std::once_flag configured[64]; // function attributes are per device
+	oncePerDevice(configured, [] { // up to 128 x 128 bins (7-bit bin coordinates)
 		cudaFuncSetAttribute(k_bin_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * (int)sizeof(int));
 		cudaFuncSetAttribute(k_bin_dispatch, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * (int)sizeof(int));
-		configured[dev & 63] = true;
-	}
+	});
 	launchPDL(k_bin_count, grid, BIN_THREADS, hist_bytes, stream, p);
 	if(ev)
 		cudaEventRecord(ev[0], stream);

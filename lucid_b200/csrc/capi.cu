@@ -20,6 +20,13 @@ bool lucid::pdlEnabled() {
 	return on;
 }
 
+static thread_local const char *g_failed_kernel = nullptr;
+static thread_local cudaError_t g_failed_err = cudaSuccess;
+void lucid::noteLaunchFailure(const char *kernel_name, cudaError_t err) {
+	if(!g_failed_kernel)
+		g_failed_kernel = kernel_name, g_failed_err = err;
+}
+
 struct lucid_renderer {
 	LucidCreateInfo ci;
 	Params p;
@@ -36,7 +43,8 @@ struct lucid_renderer {
 	// renders into the other one (the reference double-buffers its per-frame data the same way,
 	// lucid_renderer.h:78-81)
 	u32 *images[2] = {nullptr, nullptr};
-	u32 *image = nullptr; // the one the last frame rendered into
+	u32 *image = nullptr; // the renderer-owned image the last frame rendered into; null after a frame that
+						  // rendered into a caller's LUCID_MEM_DEVICE image
 	int image_index = 0;
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t render_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
@@ -57,6 +65,8 @@ struct lucid_renderer {
 	// pinned host staging
 	unsigned char *h_instances = nullptr; // instances + colors + uv rects
 	u32 *h_info = nullptr;
+	// one status word per staging slot, written by the frame's kernels only when the bin lists overflowed
+	u32 *h_status = nullptr;
 	bool info_valid = false;
 	bool has_geometry = false;
 	int num_quads = 0, num_verts = 0;
@@ -113,6 +123,8 @@ void freeAll(lucid_renderer *r) {
 		cudaFreeHost(r->h_instances);
 	if(r->h_info)
 		cudaFreeHost(r->h_info);
+	if(r->h_status)
+		cudaFreeHost(r->h_status);
 	for(auto &set : r->ev)
 		for(auto &e : set)
 			if(e)
@@ -265,6 +277,8 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++)
 		CUC(cudaEventCreateWithFlags(&r->upload_done[i], cudaEventDisableTiming));
 	CUC(cudaMallocHost((void **)&r->h_info, r->info_words * 4));
+	CUC(cudaMallocHost((void **)&r->h_status, lucid_renderer::NUM_STAGING * 4));
+	memset(r->h_status, 0, lucid_renderer::NUM_STAGING * 4);
 	CUC(cudaMemsetAsync(r->info_dev, 0, r->info_words * 4, r->stream));
 	CUC(cudaMemsetAsync(r->images[0], 0, (size_t)p.width * p.height * 4, r->stream));
 	CUC(cudaMemsetAsync(r->images[1], 0, (size_t)p.width * p.height * 4, r->stream));
@@ -376,6 +390,7 @@ int lucid_set_geometry(lucid_renderer *r, const float *positions, int32_t num_ve
 	launchPadPositions(p.positions, (float4 *)r->geom_owned[5], num_verts, r->stream);
 	CU(cudaStreamSynchronize(r->stream));
 	r->num_quads = num_quads, r->num_verts = num_verts;
+	p.num_verts = num_verts;
 	r->has_geometry = true;
 	return LUCID_OK;
 }
@@ -416,6 +431,15 @@ int lucid_wait(lucid_renderer *r) {
 	for(bool &b : r->upload_pending)
 		b = false;
 	CU(cudaGetLastError());
+	bool overflow = false;
+	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++) {
+		overflow = overflow || r->h_status[i] != 0;
+		r->h_status[i] = 0;
+	}
+	if(overflow)
+		return fail(r, LUCID_E_LIMIT,
+					"a frame's per-bin lists exceeded 2 * max_visible_quads entries: nothing was rasterised and the "
+					"owned bins were painted red; create the renderer with a larger max_visible_quads");
 	return LUCID_OK;
 }
 
@@ -435,7 +459,8 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	for(int i = 0; i < num_instances; i++) {
 		const LucidInstanceData &in = instances[i];
 		if(in.num_quads < 0 || in.num_quads > LUCID_MAX_INSTANCE_QUADS || (in.index_offset & 3) != 0 ||
-		   in.index_offset < 0 || (int64_t)in.index_offset / 4 + in.num_quads > r->num_quads)
+		   in.index_offset < 0 || (int64_t)in.index_offset / 4 + in.num_quads > r->num_quads ||
+		   in.vertex_offset < 0 || in.vertex_offset >= r->num_verts)
 			return fail(r, LUCID_E_INVALID, "lucid_render: instance " + std::to_string(i) + " out of range");
 	}
 	if(out_memory != LUCID_MEM_NONE && (!out_rgba8 || pitch_bytes < (size_t)p.width * 4 || (pitch_bytes & 3)))
@@ -482,9 +507,12 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	cfg.num_instances = num_instances; // taken from this call, not the previous frame
 	p.num_instances = num_instances;
 	p.num_setup_ctas = num_instances; // one k_quad_cull CTA per instance
+	p.host_status = r->h_status + sb;
+	g_failed_kernel = nullptr;
 	if(out_memory == LUCID_MEM_DEVICE) {
 		p.image = (u32 *)out_rgba8;
 		p.image_pitch = (int)(pitch_bytes / 4);
+		r->image = nullptr; // no renderer-owned image holds this frame
 	} else {
 		// frames that stay on the device always use image 0 (the one lucid_image_pointer and the
 		// IPC export name); frames copied to the host alternate
@@ -521,6 +549,12 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 		CU(cudaEventRecord(ev[7], st));
 	CU(cudaEventRecord(r->upload_done[sb], st));
 	r->upload_pending[sb] = true;
+	if(g_failed_kernel) {
+		const std::string what = std::string("launch of ") + g_failed_kernel;
+		g_failed_kernel = nullptr;
+		cudaGetLastError();
+		return failCuda(r, g_failed_err, what.c_str());
+	}
 	CU(cudaGetLastError());
 	r->frame_counter++;
 	double t4 = host_profile ? now() : 0.0;
@@ -698,6 +732,8 @@ int lucid_read_image(lucid_renderer *r, void *dst, size_t pitch_bytes) {
 	int rc = lucid_wait(r);
 	if(rc)
 		return rc;
+	if(!r->image)
+		return fail(r, LUCID_E_STATE, "lucid_read_image: the last frame was rendered into the caller's device image");
 	CU(cudaMemcpy2D(dst, pitch_bytes, r->image, (size_t)r->p.width * 4, (size_t)r->p.width * 4,
 					r->p.height, cudaMemcpyDeviceToHost));
 	return LUCID_OK;
@@ -706,8 +742,8 @@ int lucid_read_image(lucid_renderer *r, void *dst, size_t pitch_bytes) {
 int lucid_composite_to(lucid_renderer *r, void *dst_rgba8_device, size_t pitch_bytes) {
 	if(!r || !dst_rgba8_device || pitch_bytes < (size_t)r->p.width * 4 || (pitch_bytes & 3))
 		return LUCID_E_INVALID;
-	if(r->frame_counter == 0)
-		return fail(r, LUCID_E_STATE, "lucid_composite_to: no frame has been rendered");
+	if(r->frame_counter == 0 || !r->image)
+		return fail(r, LUCID_E_STATE, "lucid_composite_to: no frame has been rendered into the renderer's own image");
 	CU(cudaSetDevice(r->ci.device));
 	Params p = r->p;
 	p.image = r->image, p.image_pitch = p.width;
@@ -720,7 +756,9 @@ int lucid_composite_to(lucid_renderer *r, void *dst_rgba8_device, size_t pitch_b
 int lucid_image_pointer(lucid_renderer *r, void **device_ptr, size_t *pitch_bytes) {
 	if(!r || !device_ptr || !pitch_bytes)
 		return LUCID_E_INVALID;
-	*device_ptr = r->image;
+	// always image 0: the one frames that stay on the device (LUCID_MEM_NONE) render into, whatever the
+	// previous frame's output was
+	*device_ptr = r->images[0];
 	*pitch_bytes = (size_t)r->p.width * 4;
 	return LUCID_OK;
 }
@@ -730,7 +768,7 @@ int lucid_ipc_export_image(lucid_renderer *r, void *handle64) {
 		return LUCID_E_INVALID;
 	CU(cudaSetDevice(r->ci.device));
 	cudaIpcMemHandle_t h;
-	CU(cudaIpcGetMemHandle(&h, r->image));
+	CU(cudaIpcGetMemHandle(&h, r->images[0])); // the image LUCID_MEM_NONE frames render into
 	static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t");
 	memcpy(handle64, &h, 64);
 	return LUCID_OK;

@@ -7,6 +7,7 @@
 #include "../../include/lucid_abi.h"
 
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 
 namespace lucid {
@@ -49,6 +50,7 @@ struct Params {
 	int max_dispatches;
 	int num_instances;
 	int num_setup_ctas;
+	int num_verts; // vertices of the caller's geometry: indices at or above it reject the quad
 
 	// caller geometry (device pointers)
 	const float *positions;
@@ -86,6 +88,7 @@ struct Params {
 	u32 *frag_counts;	  // optional per-pixel fragment counts (debug / parity), may be null
 	u32 *bin_flags;		  // per bin: bit 0 promoted LOW->HIGH, bit 1 over the reference's HIGH limits (red)
 	u32 *work_counters;	  // [0] bins taken [1] block items taken [3..7] block items per size class
+	u32 *host_status;	  // pinned host word of this frame: set non-zero when the bin lists overflowed (the frame is red)
 	u64 *bin_cost;		  // per bin: warp cycles the raster kernels spent on it this frame (split balancing)
 	uint4 *block_lists;	  // per bin BIN_LIST_BYTES: 32 half-block lists (HIGH) or 16 block lists (LOW)
 	int *block_counts;	  // 32 per bin: entries of each list
@@ -251,8 +254,13 @@ __device__ __forceinline__ void clipToOwnedBins(const Params &p, int by, int &bm
 }
 __device__ __forceinline__ bool ownsBin(const Params &p, int bin) { return bin >= p.bin_begin && bin < p.bin_end; }
 bool pdlEnabled(); // capi.cu: off with LUCID_NO_PDL=1 (A/B timing)
+// first failed launch of the calling thread's current frame (capi.cu reads and clears it): a bad launch
+// configuration is reported with the kernel's name instead of surfacing at some later call
+void noteLaunchFailure(const char *kernel_name, cudaError_t err);
+#define launchPDL(kernel, ...) launchPDLNamed(#kernel, kernel, __VA_ARGS__)
 template <typename... KArgs, typename... Args>
-inline void launchPDL(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args &&...args) {
+inline void launchPDLNamed(const char *name, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream,
+						   Args &&...args) {
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((unsigned)block);
 	cfg.dynamicSmemBytes = smem, cfg.stream = stream;
@@ -260,7 +268,15 @@ inline void launchPDL(void (*kernel)(KArgs...), int grid, int block, size_t smem
 	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr, cfg.numAttrs = pdlEnabled() ? 1 : 0;
-	cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+	const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+	if(err != cudaSuccess)
+		noteLaunchFailure(name, err);
+}
+// per-device one-time function attributes (handles on different devices / threads may launch concurrently)
+template <typename F> inline void oncePerDevice(std::once_flag (&flags)[64], F &&f) {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	std::call_once(flags[dev & 63], f);
 }
 
 // kernel launchers (each in its own translation unit)

@@ -1264,6 +1264,8 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 	__shared__ __align__(16) uint4 s_ring[RASTER_WARPS][PHASE_A_RING * 2];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	pdlEntry();
+	if(p.info->temp[1] != 0)
+		return; // the bin lists did not fit their buffers (k_bin_scan): no list is valid, the frame is painted red
 	const int n_high = p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH];
 	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
 	while(true) {
@@ -1422,6 +1424,11 @@ constexpr int WARP_SCRATCH_BYTES = WARP_SCRATCH_FIXED + SMEM_KEYS * 4;
 // (raster_low.glsl:230-237,294-298).  Everything read here was written by k_raster_bins.
 __device__ __forceinline__ void finishBins(const Params &p, u32 background, u32 *s_mask) {
 	const int lane = laneId(), warp = threadIdx.x >> 5;
+	// bin lists over their capacity (k_bin_scan set temp[1], dispatch and k_raster_bins did nothing): every
+	// owned bin is painted red, like a bin over the reference's own limits, and the host is told
+	const bool list_overflow = p.info->temp[1] != 0;
+	if(list_overflow && blockIdx.x == 0 && threadIdx.x == 0 && p.host_status)
+		*p.host_status = 1u;
 	// 32 bins per CTA and round (one round on a B200: 740 CTAs cover 23 680 bins)
 	for(int first = blockIdx.x * 32; first < p.bin_count; first += gridDim.x * 32) {
 		if(warp == 0) {
@@ -1429,7 +1436,7 @@ __device__ __forceinline__ void finishBins(const Params &p, u32 background, u32 
 			u32 kind = 0; // 1 background, 2 red
 			if(b < p.bin_count && ownsBin(p, b)) {
 				const bool empty = cntc(p, LUCID_CNT_TRI_COUNTS)[b] + cntc(p, LUCID_CNT_QUAD_COUNTS)[b] * 2 == 0;
-				kind = (p.bin_flags[b] & 2u) ? 2u : empty ? 1u : 0u;
+				kind = (list_overflow || (p.bin_flags[b] & 2u)) ? 2u : empty ? 1u : 0u;
 			}
 			const u32 fill = __ballot_sync(0xffffffffu, kind != 0), red = __ballot_sync(0xffffffffu, kind == 2);
 			if(lane == 0)
@@ -1759,14 +1766,9 @@ static int rasterBlocksGrid(int num_sms) { return num_sms * RB_MIN_CTAS; }
 size_t rasterLargeKeysCount(int num_sms) { return (size_t)rasterBlocksGrid(num_sms) * BLOCK_WARPS * MAX_HBLOCK_TRIS; }
 
 void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, cudaEvent_t *ev, int num_sms) {
-	static bool configured[64] = {}; // function attributes are per device
+	static std::once_flag configured[64]; // function attributes are per device
 	const int blocks_smem = BLOCK_WARPS * WARP_SCRATCH_BYTES;
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if(!configured[dev & 63]) {
-		cudaFuncSetAttribute(k_raster_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, blocks_smem);
-		configured[dev & 63] = true;
-	}
+	oncePerDevice(configured, [=] { cudaFuncSetAttribute(k_raster_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, blocks_smem); });
 	const LucidVec4 &bg = cfg.background_color;
 	auto q = [](float v) { return (u32)(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f + 0.5f); };
 	const u32 bg8 = q(bg.x) | (q(bg.y) << 8) | (q(bg.z) << 16) | 0xff000000u;

@@ -106,7 +106,10 @@ __device__ QuadResult processInputQuad(const Params &p, const LucidConfig &cfg, 
 	u32 v0 = vi.x, v1 = vi.y, v2 = vi.z, v3 = vi.w;
 	bool cull0 = v0 == v1 || v1 == v2 || v2 == v0;
 	bool cull1 = v0 == v2 || v2 == v3 || v3 == v0;
-	if(cull0 && cull1) {
+	// an index outside the vertex buffer rejects the quad instead of reading out of bounds (the reference
+	// trusts its indices; valid inputs never take this branch)
+	const u32 nv = (u32)p.num_verts;
+	if((cull0 && cull1) || v0 >= nv || v1 >= nv || v2 >= nv || v3 >= nv) {
 		out.status = LUCID_REJECTION_OTHER;
 		return out;
 	}

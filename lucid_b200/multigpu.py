@@ -84,11 +84,47 @@ def composite_gather(dist, strip, rows, all_rows, height, width, dst: int = 0):
     return None
 
 
-def reduce_info(dist, info):
-    """LucidInfo counters of the bin-row split: statistics sum over ranks, per-bin arrays are
-    disjoint (owned rows only) so they also sum."""
+def reduce_info(dist, info, bin_count: int):
+    """LucidInfo + per-bin arrays of the whole frame from the ranks of a bin split (every rank passes its own
+    lucid_read_info words).  Only what is additive is summed -- the statistics and the per-bin counts, which are
+    disjoint because a rank only counts the bins it owns; the rest is rebuilt or taken as is:
+      * num_input_quads and the rejection counters are identical on every rank (setup is replicated): maximum;
+      * num_visible_quads / num_counted_quads are per rank (a quad is visible on every rank whose rows it
+        touches) and are returned as the per-rank maximum, NOT a frame total;
+      * bin offsets are the exclusive prefix sums of the summed counts (what bin_categorizer computes,
+        bin_categorizer.glsl:22-89), the *_OFFSETS_TEMP arrays offsets + counts (their value after dispatch);
+      * LOW / HIGH bin lists are the sorted unions of the ranks' lists, EMPTY the remainder.
+    Returns the words as a uint32 array of the same length."""
     import torch
 
-    t = torch.as_tensor(np.asarray(info).astype(np.int64))
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return t.numpy()
+    words = np.asarray(info).astype(np.int64)
+    head_n = 1152
+    assert words.size >= head_n + 10 * bin_count
+    head, counts = words[:head_n].copy(), words[head_n:head_n + 10 * bin_count].reshape(10, bin_count).copy()
+
+    def allred(a, op):
+        t = torch.from_numpy(np.array(a, dtype=np.int64, copy=True))  # a copy: all_reduce works in place
+        dist.all_reduce(t, op=op)
+        return t.numpy()
+
+    SUM, MAX = dist.ReduceOp.SUM, dist.ReduceOp.MAX
+    out_head = allred(head, MAX)  # identical or per-rank words: maximum
+    out_head[60:64] = allred(head[60:64], SUM)  # stats: fragments, half-block triangles, invalid pixels
+    out_head[1088:1090] = allred(head[1088:1090], MAX)  # temp[0] dropped quads (replicated), temp[1] list overflow
+    quad_counts, tri_counts = allred(counts[0], SUM), allred(counts[3], SUM)
+    # level membership: a rank lists only bins it owns; one-hot per bin, summed
+    n_low, n_high = int(head[7]), int(head[9])
+    member = np.zeros((2, bin_count), np.int64)
+    member[0, counts[7][:n_low]] = 1
+    member[1, counts[9][:n_high]] = 1  # includes bins promoted from LOW (they stay in the LOW list too)
+    member = allred(member, SUM)
+    low, high = np.nonzero(member[0])[0], np.nonzero(member[1])[0]
+    out = np.zeros((10, bin_count), np.int64)
+    out[0], out[3] = quad_counts, tri_counts
+    out[1] = np.concatenate([[0], np.cumsum(quad_counts)[:-1]])
+    out[4] = np.concatenate([[0], np.cumsum(tri_counts)[:-1]])
+    out[2], out[5] = out[1] + out[0], out[4] + out[3]
+    out[7][:low.size], out[9][:high.size] = low, high
+    promoted = int(np.count_nonzero(member[0] * member[1]))
+    out_head[5:10] = [bin_count - low.size - (high.size - promoted), 0, low.size, 0, high.size]
+    return np.concatenate([out_head, out.reshape(-1)]).astype(np.uint32)

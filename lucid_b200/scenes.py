@@ -204,13 +204,13 @@ def meshlet_patches(num_patches=489, seed=2, width=1920, height=1080, grid=32, e
 
 
 def hairball(num_strands=39_063, segments=64, seed=3, width=3840, height=2160, radius=10.0,
-             ribbon_width=None, distance=22.0, alpha=127, name="config3_hairball"):
+             ribbon_width=None, distance=22.0, alpha=127, start_frac=0.35, name="config3_hairball"):
     """Config 3: curly ribbons inside a sphere; dense overlap drives bins into raster_high."""
     rng = Rng(seed)
     ns, sg = num_strands, segments
     if ribbon_width is None:
         ribbon_width = 0.002 * radius
-    start = rng.normal_dirs(ns) * (rng.f32(ns) ** np.float32(1.0 / 3.0))[:, None] * np.float32(0.35 * radius)
+    start = rng.normal_dirs(ns) * (rng.f32(ns) ** np.float32(1.0 / 3.0))[:, None] * np.float32(start_frac * radius)
     d = rng.normal_dirs(ns)
     step = np.float32(1.6 * radius / sg)
     pts = np.empty((ns, sg + 1, 3), np.float32)
@@ -368,7 +368,11 @@ def get_config(index: int, scale: float = 1.0):
     if index == 1:
         return meshlet_patches(num_patches=max(2, int(489 * scale)))
     if index == 2:
-        return hairball(num_strands=max(16, int(39_063 * scale)))
+        # BASELINE configs[2]: "depth complexity > 64 per pixel, raster_high path".  The ball fills the 4K frame
+        # (94 % of the pixels covered) and the ribbons are wide enough for a median of 72 fragments per covered pixel
+        # (p99 182, max 228; tests/depth_histogram.py) with no bin over the reference's HIGH limits
+        # (raster_high.glsl:80-83,140-141).
+        return hairball(num_strands=max(16, int(39_063 * scale)), ribbon_width=0.08, distance=14.0, start_frac=0.7)
     if index == 3:
         return architecture(num_small=max(2048, int(4_900_000 * scale)), num_large=max(8, int(2_000 * scale)))
     if index == 4:

@@ -32,8 +32,16 @@ def record(o):
                 tri_records=digest(np.concatenate([o.read_tri_records(0), o.read_tri_records(1)])))
 
 
+FULL_MVQ = 4793490  # the reference's MAX_VISIBLE_QUADS formula at the default memory budget
+
+
 def main():
+    """Small parity scenes, then BASELINE.json configs[0..3] at full size ("config0" .. "config3": about a
+    minute of CPU for the two 4K scenes)."""
+    from lucid_b200 import scenes
     out = {name: record(pu.run_oracle(sc)) for name, sc in pu.small_scenes().items()}
+    for ci in range(4):
+        out[f"config{ci}"] = record(pu.run_oracle(scenes.get_config(ci), mvq=FULL_MVQ, threads=os.cpu_count() or 8))
     with open(os.path.join(HERE, "oracle_golden.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print("wrote", list(out))

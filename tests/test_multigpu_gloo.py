@@ -37,14 +37,20 @@ def _worker(rank, world, port, out_path):
         y0, y1 = multigpu.strip_pixel_rows(rows, h)
         strip = torch.from_numpy(part.read_image()[y0:y1].view(np.int32).copy())
         full = multigpu.composite_gather(dist, strip, rows, all_rows, h, w, dst=0)
-        summed = multigpu.reduce_info(dist, part.info[:64])
+        summed = multigpu.reduce_info(dist, part.info, part.bin_count)
         views = multigpu.views_for_rank(7, rank, world)
         gathered = [None] * world
         dist.all_gather_object(gathered, views)
         if rank == 0:
             ref = pu.run_oracle(sc, threads=2)
             ok_img = np.array_equal(full.numpy().view(np.uint32), ref.read_image())
-            ok_frag = int(summed[60]) == int(ref.info[60])
+            # statistics, rejections, per-bin counts, offsets and level counts of the composed frame equal the
+            # single-device frame's; the LOW / HIGH lists as sets
+            hs, cs = api.split_info(summed, ref.bin_count)
+            hr, cr = api.split_info(ref.info, ref.bin_count)
+            ok_frag = (np.array_equal(hs[60:63], hr[60:63]) and hs[0] == hr[0] and np.array_equal(hs[32:36], hr[32:36])
+                       and np.array_equal(cs[:6], cr[:6]) and np.array_equal(hs[5:10], hr[5:10])
+                       and set(cs[7][:hs[7]]) == set(cr[7][:hr[7]]) and set(cs[9][:hs[9]]) == set(cr[9][:hr[9]]))
             ok_views = sorted(v for g in gathered for v in g) == list(range(7))
             with open(out_path, "w") as f:
                 f.write(f"{int(ok_img)} {int(ok_frag)} {int(ok_views)}")

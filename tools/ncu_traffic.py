@@ -37,4 +37,9 @@ for spec in sys.argv[1:]:
     stages["per_kernel"] = kernels
     stages["source"] = path.split("/")[-1] + " (ncu --set full, one frame, cold-cache serialised replays)"
     out[name] = stages
+# the digest of the kernel sources the capture was taken with: bench.py only quotes a capture that matches
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+out["kernel_source_hash"] = bench.kernel_source_hash()
 print(json.dumps(out, indent=1))
