@@ -5,6 +5,7 @@
 #pragma once
 
 #include "../../include/lucid_abi.h"
+#include "../../include/lucid_colour_tables.h"
 
 #include <cuda_runtime.h>
 #include <mutex>
@@ -118,47 +119,6 @@ __device__ __forceinline__ float smallUintToFloat(u32 v, float bias = 0.0f) {
 	return __uint_as_float(v | 0x4b000000u) - (8388608.0f + bias);
 }
 
-// log2 / exp2 / pow: the polynomial contract shared with the CPU checker (oracle/lucid_oracle.cpp
-// orc_log2 / orc_exp2): log2 of the mantissa on [sqrt(1/2), sqrt(2)) as f * P7(f), 2^r on
-// [-1/2, 1/2] as P5(r), no division.  The Horner steps are explicit fused multiply-adds (fmaf on
-// the host, FFMA here): single rounding on both sides, so the result is bit-identical.
-__device__ __forceinline__ float log2_poly(float x) {
-	u32 ix = __float_as_uint(x);
-	int e = (int)(ix - 0x3f3504f3u) >> 23;
-	float m = __uint_as_float(ix - ((u32)e << 23));
-	float f = m - 1.0f;
-	float p = -0.146203533f;
-	p = __fmaf_rn(p, f, 0.23420985f);
-	p = __fmaf_rn(p, f, -0.24882181f);
-	p = __fmaf_rn(p, f, 0.287075609f);
-	p = __fmaf_rn(p, f, -0.360241979f);
-	p = __fmaf_rn(p, f, 0.48092404f);
-	p = __fmaf_rn(p, f, -0.721352756f);
-	p = __fmaf_rn(p, f, 1.4426949f);
-	return __fmaf_rn(p, f, (float)e);
-}
-__device__ __forceinline__ float exp2_poly(float t) {
-	float n = floorf(t + 0.5f);
-	float r = t - n;
-	float p = 0.00134004327f;
-	p = __fmaf_rn(p, r, 0.00967603736f);
-	p = __fmaf_rn(p, r, 0.0555032715f);
-	p = __fmaf_rn(p, r, 0.240221068f);
-	p = __fmaf_rn(p, r, 0.693147182f);
-	p = __fmaf_rn(p, r, 1.0f);
-	int ni = f2i(n);
-	if(ni < -126)
-		return 0.0f;
-	if(ni > 127)
-		ni = 127;
-	return __uint_as_float(__float_as_uint(p) + ((u32)ni << 23));
-}
-__device__ __forceinline__ float pow_poly(float x, float y) {
-	if(!(x > 0.0f))
-		return 0.0f;
-	return exp2_poly(y * log2_poly(x));
-}
-
 struct F3 {
 	float x, y, z;
 };
@@ -196,24 +156,61 @@ __device__ __forceinline__ u32 encodeRGBA8(float4 c) {
 	return f2u(c.x * 255.0f) | (f2u(c.y * 255.0f) << 8) | (f2u(c.z * 255.0f) << 16) |
 		   (f2u(c.w * 255.0f) << 24);
 }
-__device__ __forceinline__ float linearToSRGB1(float c) {
-	return c < 0.0031308f ? 12.92f * c : 1.055f * pow_poly(c, 1.0f / 2.4f) - 0.055f;
+// ---- colour contract ------------------------------------------------------
+// Coverage, depth keys and sample depths are evaluated one rounding per operation (the translation
+// units are compiled with -fmad=false).  Colour has a 1/255 budget: its multiply-adds are fused
+// (explicit __fmaf_rn, mirrored by fmaf in oracle/lucid_oracle.cpp shadeSampleFast) and the two pow()
+// of finalShading (funcs.glsl:261-271) are interpolations in two tables of (value, slope) pairs,
+// include/lucid_colour_tables.h -- the same words the CPU checker reads.
+static __device__ const u32 d_s2l_words[LUCID_S2L_SIZE * 2] = {LUCID_S2L_WORDS};
+static __device__ const u32 d_l2s_words[LUCID_L2S_SIZE * 2] = {LUCID_L2S_WORDS};
+struct ColourTables {
+	const float2 *s2l, *l2s; // global (L1-cached) or a shared-memory copy
+};
+__device__ __forceinline__ ColourTables globalColourTables() {
+	ColourTables t;
+	t.s2l = reinterpret_cast<const float2 *>(d_s2l_words), t.l2s = reinterpret_cast<const float2 *>(d_l2s_words);
+	return t;
 }
-__device__ __forceinline__ float SRGBToLinear1(float c) {
-	return c < 0.04045f ? (1.0f / 12.92f) * c : pow_poly((c + 0.055f) * (1.0f / 1.055f), 2.4f);
+// sRGB decoding of c (256 intervals over c * 255: decoded bytes hit the nodes)
+__device__ __forceinline__ float tabSRGBToLinear(const ColourTables &tab, float c) {
+	const float t = fminf(fmaxf(c * 255.0f, 0.0f), 255.0f);
+	const float fi = truncf(t);
+	const float2 e = tab.s2l[f2i(fi)];
+	return __fmaf_rn(t - fi, e.y, e.x);
 }
-
-// finalShading (funcs.glsl:261-271) + Lambert term of shadeSample (shading.glsl:181-183)
-__device__ __forceinline__ u32 shadeFinal(const LucidLighting &L, float4 color, F3 normal) {
-	F3 msun = mk3(-L.sun_dir.x, -L.sun_dir.y, -L.sun_dir.z);
-	float light_value = fmaxf(0.0f, dot3(msun, normal) * 0.7f + 0.3f);
-	float ambx = L.ambient_color.x * L.ambient_power, amby = L.ambient_color.y * L.ambient_power;
-	float ambz = L.ambient_color.z * L.ambient_power;
-	float difx = L.sun_color.x * L.sun_power * light_value, dify = L.sun_color.y * L.sun_power * light_value;
-	float difz = L.sun_color.z * L.sun_power * light_value;
-	color.x = saturatef(linearToSRGB1(SRGBToLinear1(color.x) * (ambx + difx)));
-	color.y = saturatef(linearToSRGB1(SRGBToLinear1(color.y) * (amby + dify)));
-	color.z = saturatef(linearToSRGB1(SRGBToLinear1(color.z) * (ambz + difz)));
+// sRGB encoding of x <= 1: linear branch below 0.0031308, else 32 intervals per octave
+__device__ __forceinline__ float tabLinearToSRGB(const ColourTables &tab, float x) {
+	const u32 bits = __float_as_uint(x);
+	const u32 i = min((bits - LUCID_L2S_FIRST_BITS) >> LUCID_L2S_SHIFT, (u32)(LUCID_L2S_SIZE - 1)); // clamp: unused below 2^-9
+	const float x0 = __uint_as_float(bits & ~((1u << LUCID_L2S_SHIFT) - 1u));
+	const float2 e = tab.l2s[i];
+	const float hi = __fmaf_rn(x - x0, e.y, e.x);
+	return x < 0.0031308f ? 12.92f * x : hi;
+}
+__device__ __forceinline__ float finalShadeFast(const ColourTables &tab, float c, float light) {
+	const float x = fminf(tabSRGBToLinear(tab, c) * light, 1.0f);
+	return saturatef(tabLinearToSRGB(tab, x));
+}
+// per-frame light terms of finalShading: ambient and sun colour times their powers
+struct LightTerms {
+	float amb[3], sun[3], msun[3];
+};
+__device__ __forceinline__ LightTerms lightTerms(const LucidLighting &L) {
+	LightTerms t;
+	t.amb[0] = L.ambient_color.x * L.ambient_power, t.amb[1] = L.ambient_color.y * L.ambient_power;
+	t.amb[2] = L.ambient_color.z * L.ambient_power;
+	t.sun[0] = L.sun_color.x * L.sun_power, t.sun[1] = L.sun_color.y * L.sun_power, t.sun[2] = L.sun_color.z * L.sun_power;
+	t.msun[0] = -L.sun_dir.x, t.msun[1] = -L.sun_dir.y, t.msun[2] = -L.sun_dir.z;
+	return t;
+}
+// Lambert term of shadeSample (shading.glsl:181-183) + finalShading, then the RGBA8 sample
+__device__ __forceinline__ u32 shadeFinal(const ColourTables &tab, const LightTerms &lt, float4 color, F3 normal) {
+	const float ndl = __fmaf_rn(lt.msun[0], normal.x, __fmaf_rn(lt.msun[1], normal.y, lt.msun[2] * normal.z));
+	const float light_value = fmaxf(0.0f, __fmaf_rn(ndl, 0.7f, 0.3f));
+	color.x = finalShadeFast(tab, color.x, __fmaf_rn(lt.sun[0], light_value, lt.amb[0]));
+	color.y = finalShadeFast(tab, color.y, __fmaf_rn(lt.sun[1], light_value, lt.amb[1]));
+	color.z = finalShadeFast(tab, color.z, __fmaf_rn(lt.sun[2], light_value, lt.amb[2]));
 	return encodeRGBA8(color);
 }
 // A triangle without vertex colours, vertex normals or a texture shades to the same RGBA8 value
@@ -227,7 +224,7 @@ __device__ __forceinline__ u32 shadeConstant(const LucidLighting &L, u32 flags, 
 		color = decodeRGBA8(inst_color);
 	if(color.w == 0.0f)
 		return 0;
-	return shadeFinal(L, color, decodeNormalUint(enc_normal));
+	return shadeFinal(globalColourTables(), lightTerms(L), color, decodeNormalUint(enc_normal));
 }
 
 __device__ __forceinline__ u32 laneId() { return threadIdx.x & 31; }

@@ -85,7 +85,7 @@ __device__ __forceinline__ float4 texelBytes(u32 t) {
 }
 // uf, vf in [0, 1]; result on the 0..255 scale
 __device__ __forceinline__ float4 bilinear(const u32 *level_base, int w, int h, float uf, float vf) {
-	float fx = uf * float(w) - 0.5f, fy = vf * float(h) - 0.5f;
+	float fx = __fmaf_rn(uf, float(w), -0.5f), fy = __fmaf_rn(vf, float(h), -0.5f);
 	float x0f = floorf(fx), y0f = floorf(fy);
 	float ax = fx - x0f, ay = fy - y0f;
 	int x0 = f2i(x0f), y0 = f2i(y0f); // in [-1, size - 1]
@@ -104,9 +104,9 @@ __device__ __forceinline__ float4 bilinear(const u32 *level_base, int w, int h, 
 	float4 o;
 #define LERP2(c)                                                                                   \
 	{                                                                                              \
-		float top = c00.c + (c10.c - c00.c) * ax;                                                  \
-		float bot = c01.c + (c11.c - c01.c) * ax;                                                  \
-		o.c = top + (bot - top) * ay;                                                              \
+		float top = __fmaf_rn(c10.c - c00.c, ax, c00.c);                                           \
+		float bot = __fmaf_rn(c11.c - c01.c, ax, c01.c);                                           \
+		o.c = __fmaf_rn(bot - top, ay, top);                                                       \
 	}
 	LERP2(x) LERP2(y) LERP2(z) LERP2(w)
 #undef LERP2
@@ -120,7 +120,7 @@ __device__ __forceinline__ float4 sampleTexture(const Params &p, int slot, float
 	const int wi = p.tex_width[slot], hi = p.tex_height[slot];
 	float w0 = float(wi), h0 = float(hi);
 	float ax = dudx * w0, ay = dvdx * h0, bx = dudy * w0, by = dvdy * h0;
-	float rho2 = fmaxf(ax * ax + ay * ay, bx * bx + by * by);
+	float rho2 = fmaxf(__fmaf_rn(ax, ax, ay * ay), __fmaf_rn(bx, bx, by * by));
 	int levels = p.tex_levels[slot];
 	float lod = 0.0f;
 	if(rho2 > 1.0f)
@@ -135,8 +135,8 @@ __device__ __forceinline__ float4 sampleTexture(const Params &p, int slot, float
 	if(a == 0.0f || l1 == l0)
 		return make_float4(c0.x * s, c0.y * s, c0.z * s, c0.w * s);
 	float4 c1 = bilinear(data + p.tex_level_offset[slot][l1], max(1, wi >> l1), max(1, hi >> l1), uf, vf);
-	return make_float4((c0.x + (c1.x - c0.x) * a) * s, (c0.y + (c1.y - c0.y) * a) * s,
-					   (c0.z + (c1.z - c0.z) * a) * s, (c0.w + (c1.w - c0.w) * a) * s);
+	return make_float4(__fmaf_rn(c1.x - c0.x, a, c0.x) * s, __fmaf_rn(c1.y - c0.y, a, c0.y) * s,
+					   __fmaf_rn(c1.z - c0.z, a, c0.z) * s, __fmaf_rn(c1.w - c0.w, a, c0.w) * s);
 }
 
 __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg, int ipx, int ipy, u32 tri_idx,
@@ -157,13 +157,15 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 	float e0x = __uint_as_float(b0q.x), e0y = __uint_as_float(b0q.y), e0z = __uint_as_float(b0q.z);
 	float e1x = __uint_as_float(b1q.x), e1y = __uint_as_float(b1q.y), e1z = __uint_as_float(b1q.z);
 
+	// the sample depth orders the blending: one rounding per operation, as in the reference; everything
+	// below it is colour (fused multiply-adds, see the colour contract in common.cuh)
 	float inv_ray_pos = dx * px + (dy * py + dz);
 	out_depth = inv_ray_pos;
 	if(misc.w != 0)
 		return misc.z; // attribute-free triangle: colour was evaluated once in quad setup
 	float ray_pos = rcp(inv_ray_pos);
-	float e0 = e0x * px + (e0y * py + e0z);
-	float e1 = e1x * px + (e1y * py + e1z);
+	float e0 = __fmaf_rn(e0x, px, __fmaf_rn(e0y, py, e0z));
+	float e1 = __fmaf_rn(e1x, px, __fmaf_rn(e1y, py, e1z));
 	float b0 = e0 * ray_pos, b1 = e1 * ray_pos;
 
 	float bdx0 = 0, bdx1 = 0, bdy0 = 0, bdy1 = 0;
@@ -171,8 +173,8 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 	if(textured) {
 		float ray_posx = rcp(inv_ray_pos + dx);
 		float ray_posy = rcp(inv_ray_pos + dy);
-		bdx0 = (e0 + e0x) * ray_posx - b0, bdx1 = (e1 + e1x) * ray_posx - b1;
-		bdy0 = (e0 + e0y) * ray_posy - b0, bdy1 = (e1 + e1y) * ray_posy - b1;
+		bdx0 = __fmaf_rn(e0 + e0x, ray_posx, -b0), bdx1 = __fmaf_rn(e1 + e1x, ray_posx, -b1);
+		bdy0 = __fmaf_rn(e0 + e0y, ray_posy, -b0), bdy1 = __fmaf_rn(e1 + e1y, ray_posy, -b1);
 	}
 	b0 -= __uint_as_float(b0q.w), b1 -= __uint_as_float(b1q.w);
 
@@ -185,12 +187,12 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 		float t0x = __uint_as_float(q0.x), t0y = __uint_as_float(q0.y);
 		float t1x = __uint_as_float(second == 0 ? q0.z : q1.x), t1y = __uint_as_float(second == 0 ? q0.w : q1.y);
 		float t2x = __uint_as_float(second == 0 ? q1.x : q1.z), t2y = __uint_as_float(second == 0 ? q1.y : q1.w);
-		float u = b0 * t1x + (b1 * t2x + t0x), v = b0 * t1y + (b1 * t2y + t0y);
-		float dudx = bdx0 * t1x + bdx1 * t2x, dvdx = bdx0 * t1y + bdx1 * t2y;
-		float dudy = bdy0 * t1x + bdy1 * t2x, dvdy = bdy0 * t1y + bdy1 * t2y;
+		float u = __fmaf_rn(b0, t1x, __fmaf_rn(b1, t2x, t0x)), v = __fmaf_rn(b0, t1y, __fmaf_rn(b1, t2y, t0y));
+		float dudx = __fmaf_rn(bdx0, t1x, bdx1 * t2x), dvdx = __fmaf_rn(bdx0, t1y, bdx1 * t2y);
+		float dudy = __fmaf_rn(bdy0, t1x, bdy1 * t2x), dvdy = __fmaf_rn(bdy0, t1y, bdy1 * t2y);
 		if(flags & LUCID_INST_HAS_UV_RECT) {
 			float4 r = __ldg(p.inst_uv_rects + instance_id);
-			u = r.z * fractf(u) + r.x, v = r.w * fractf(v) + r.y;
+			u = __fmaf_rn(r.z, fractf(u), r.x), v = __fmaf_rn(r.w, fractf(v), r.y);
 			dudx *= r.z, dvdx *= r.w, dudy *= r.z, dvdy *= r.w;
 		}
 		const bool tex_opaque = (flags & LUCID_INST_TEX_OPAQUE) != 0;
@@ -203,10 +205,10 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 		uint4 c = attr_c;
 		float4 c0 = decodeRGBA8(c.x), c1 = decodeRGBA8(second ? c.z : c.y), c2 = decodeRGBA8(second ? c.w : c.z);
 		float w0 = 1.0f - b0 - b1;
-		color.x *= w0 * c0.x + (b0 * c1.x + b1 * c2.x);
-		color.y *= w0 * c0.y + (b0 * c1.y + b1 * c2.y);
-		color.z *= w0 * c0.z + (b0 * c1.z + b1 * c2.z);
-		color.w *= w0 * c0.w + (b0 * c1.w + b1 * c2.w);
+		color.x *= __fmaf_rn(w0, c0.x, __fmaf_rn(b0, c1.x, b1 * c2.x));
+		color.y *= __fmaf_rn(w0, c0.y, __fmaf_rn(b0, c1.y, b1 * c2.y));
+		color.z *= __fmaf_rn(w0, c0.z, __fmaf_rn(b0, c1.z, b1 * c2.z));
+		color.w *= __fmaf_rn(w0, c0.w, __fmaf_rn(b0, c1.w, b1 * c2.w));
 	}
 	if(color.w == 0.0f)
 		return 0;
@@ -216,12 +218,12 @@ __device__ __noinline__ u32 shadeSample(const Params &p, const LucidConfig &cfg,
 		uint4 n = attr_n;
 		F3 n0 = decodeNormalUint(n.x);
 		F3 n1 = decodeNormalUint(second ? n.z : n.y) - n0, n2 = decodeNormalUint(second ? n.w : n.z) - n0;
-		normal = mk3(b0 * n1.x + (b1 * n2.x + n0.x), b0 * n1.y + (b1 * n2.y + n0.y),
-					 b0 * n1.z + (b1 * n2.z + n0.z));
+		normal = mk3(__fmaf_rn(b0, n1.x, __fmaf_rn(b1, n2.x, n0.x)), __fmaf_rn(b0, n1.y, __fmaf_rn(b1, n2.y, n0.y)),
+					 __fmaf_rn(b0, n1.z, __fmaf_rn(b1, n2.z, n0.z)));
 	} else {
 		normal = decodeNormalUint(misc.x);
 	}
-	return shadeFinal(cfg.lighting, color, normal);
+	return shadeFinal(globalColourTables(), lightTerms(cfg.lighting), color, normal);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,10 +246,11 @@ __device__ __forceinline__ void reducerInit(Reducer &s) {
 __device__ __forceinline__ void reducerBlend(Reducer &s, u32 c, bool additive) {
 	float4 cc = decodeRGBA8(c);
 	if(additive) {
-		s.r += cc.x * cc.w, s.g += cc.y * cc.w, s.b += cc.z * cc.w;
+		s.r = __fmaf_rn(cc.x, cc.w, s.r), s.g = __fmaf_rn(cc.y, cc.w, s.g), s.b = __fmaf_rn(cc.z, cc.w, s.b);
 	} else {
-		s.r += cc.x * cc.w * s.trans, s.g += cc.y * cc.w * s.trans, s.b += cc.z * cc.w * s.trans;
-		s.trans *= 1.0f - cc.w;
+		const float wt = cc.w * s.trans;
+		s.r = __fmaf_rn(cc.x, wt, s.r), s.g = __fmaf_rn(cc.y, wt, s.g), s.b = __fmaf_rn(cc.z, wt, s.b);
+		s.trans = __fmaf_rn(-cc.w, s.trans, s.trans);
 	}
 }
 __device__ __forceinline__ void reducerPush(Reducer &s, u32 color, float depth, bool additive,
@@ -658,9 +661,9 @@ __device__ __forceinline__ void writePixel(const Params &p, const LucidConfig &c
 		reducerBlend(red, red.c1, additive);
 	if(red.c0 != 0)
 		reducerBlend(red, red.c0, additive);
-	float fr = saturatef(red.r + red.trans * cfg.background_color.x);
-	float fg = saturatef(red.g + red.trans * cfg.background_color.y);
-	float fb = saturatef(red.b + red.trans * cfg.background_color.z);
+	float fr = saturatef(__fmaf_rn(red.trans, cfg.background_color.x, red.r));
+	float fg = saturatef(__fmaf_rn(red.trans, cfg.background_color.y, red.g));
+	float fb = saturatef(__fmaf_rn(red.trans, cfg.background_color.z, red.b));
 	int gx = hb_x + (lane & 7), gy = hb_y + (lane >> 3);
 	if(gx < p.width && gy < p.height) {
 		// rgba8 unorm store: round to nearest

@@ -57,6 +57,10 @@ def load():
     lib.oracle_log2.restype = C.c_float
     lib.oracle_shade_probe.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_float)]
     lib.oracle_shade_probe.restype = C.c_uint32
+    lib.oracle_set_reference_colour.argtypes = [vp, C.c_int]
+    for name in ("oracle_final_shade_fast", "oracle_final_shade_reference"):
+        getattr(lib, name).argtypes = [C.c_float, C.c_float]
+        getattr(lib, name).restype = C.c_float
     _lib = lib
     return lib
 
@@ -90,6 +94,11 @@ class Oracle:
 
     def set_bin_rows(self, begin, end):
         self.lib.oracle_set_bin_rows(self.h, begin, end)
+
+    def set_reference_colour(self, on: bool):
+        """True: colour arithmetic in the reference's operation order (what the GLSL pins compare); False
+        (default): the product's colour contract, which the CUDA kernels reproduce bit for bit."""
+        self.lib.oracle_set_reference_colour(self.h, int(on))
 
     def set_bin_range(self, begin, end):
         self.lib.oracle_set_bin_range(self.h, begin, end)

@@ -53,6 +53,7 @@
 // multiply-adds of the contract (explicit fmaf, single rounding on both sides).
 
 #include "../include/lucid_abi.h"
+#include "../include/lucid_colour_tables.h"
 
 #include <algorithm>
 #include <chrono>
@@ -210,6 +211,36 @@ inline float SRGBToLinear1(float c) {
 	return c < 0.04045f ? (1.0f / 12.92f) * c : orc_pow((c + 0.055f) * (1.0f / 1.055f), 2.4f);
 }
 
+// ---- the product's colour contract ("fast" arithmetic) -------------------------------------
+// Coverage, depth keys and sample depths keep the reference's one-rounding-per-operation arithmetic.  Colour has a
+// 1/255 budget, so its arithmetic is stated once more in the form the sm_100a kernels execute: multiply-adds are
+// fused (explicit fmaf here, FFMA there) and the two pow() of finalShading become table interpolations
+// (include/lucid_colour_tables.h, the same words on both sides).  The reference-order functions above stay: they
+// are what the pins against the reference's GLSL compare, and tests/test_colour_contract.py bounds the distance
+// between the two forms.
+inline float tabSRGBToLinear(float c) {
+	float t = fmin2(fmax2(c * 255.0f, 0.0f), 255.0f);
+	int i = f2i(t);
+	if(i > LUCID_S2L_SIZE - 1)
+		i = LUCID_S2L_SIZE - 1;
+	float f = t - float(i);
+	return fmaf(f, bitsToFloat(LUCID_S2L_TABLE[i * 2 + 1]), bitsToFloat(LUCID_S2L_TABLE[i * 2]));
+}
+// x <= 1; below 0.0031308 the linear branch
+inline float tabLinearToSRGB(float x) {
+	if(x < 0.0031308f)
+		return 12.92f * x;
+	u32 bits = floatBits(x);
+	u32 i = (bits - LUCID_L2S_FIRST_BITS) >> LUCID_L2S_SHIFT;
+	float x0 = bitsToFloat(bits & ~((1u << LUCID_L2S_SHIFT) - 1u));
+	return fmaf(x - x0, bitsToFloat(LUCID_L2S_TABLE[i * 2 + 1]), bitsToFloat(LUCID_L2S_TABLE[i * 2]));
+}
+// finalShading for one channel: colour c under light L
+inline float finalShadeFast(float c, float L) {
+	float x = fmin2(tabSRGBToLinear(c) * L, 1.0f);
+	return saturate(tabLinearToSRGB(x));
+}
+
 inline u32 encodeAABB28(u32 x0, u32 y0, u32 x1, u32 y1) {
 	return (x0 & 0x7fu) | ((y0 & 0x7fu) << 7) | ((x1 & 0x7fu) << 14) | ((y1 & 0x7fu) << 21);
 }
@@ -261,6 +292,9 @@ struct Oracle {
 	// colour, so shadeSample can be compared with the reference's, whose sampler is not part of its source
 	const float *tex_probe = nullptr;
 	mutable float tex_probe_args[8] = {};
+	// false (default): colour in the product's contract (fused multiply-adds, table sRGB) -- what the kernels
+	// reproduce bit for bit; true: colour in the reference's operation order (what the GLSL pins compare)
+	bool reference_colour = false;
 
 	// per-frame inputs
 	LucidConfig cfg;
@@ -308,8 +342,10 @@ struct Oracle {
 	void raster();
 	void rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]);
 	u32 shadeSample(int px, int py, u32 tri_idx, float &out_depth) const;
+	u32 shadeSampleFast(int px, int py, u32 tri_idx, float &out_depth) const;
 	V4 sampleTexture(const Texture &, float u, float v, float dudx, float dvdx, float dudy,
 					 float dvdy) const;
+	V4 sampleTextureFast(const Texture &, float u, float v, float dudx, float dvdx, float dudy, float dvdy) const;
 	void run();
 };
 
@@ -956,6 +992,154 @@ u32 Oracle::shadeSample(int ipx, int ipy, u32 tri_idx, float &out_depth) const {
 	return encodeRGBA8(color);
 }
 
+// ---- the same functions in the product's colour contract (fused multiply-adds, table sRGB) ----------------------
+V4 bilinearFast(const Texture &t, int level, float uf, float vf) {
+	const int w = t.w[level], h = t.h[level];
+	Footprint f;
+	float fx = fmaf(uf, float(w), -0.5f), fy = fmaf(vf, float(h), -0.5f);
+	float x0f = floorf(fx), y0f = floorf(fy);
+	f.ax = fx - x0f, f.ay = fy - y0f;
+	f.x0 = f2i(x0f), f.y0 = f2i(y0f);
+	f.x1 = f.x0 + 1, f.y1 = f.y0 + 1;
+	if(f.x0 < 0)
+		f.x0 += w;
+	if(f.x1 >= w)
+		f.x1 -= w;
+	if(f.y0 < 0)
+		f.y0 += h;
+	if(f.y1 >= h)
+		f.y1 -= h;
+	const uint8_t *base = t.mips[level].data();
+	const uint8_t *p00 = base + ((size_t)f.y0 * w + f.x0) * 4, *p10 = base + ((size_t)f.y0 * w + f.x1) * 4;
+	const uint8_t *p01 = base + ((size_t)f.y1 * w + f.x0) * 4, *p11 = base + ((size_t)f.y1 * w + f.x1) * 4;
+	V4 out;
+	for(int i = 0; i < 4; i++) {
+		float c00 = float(p00[i]), c10 = float(p10[i]), c01 = float(p01[i]), c11 = float(p11[i]);
+		float top = fmaf(c10 - c00, f.ax, c00);
+		float bot = fmaf(c11 - c01, f.ax, c01);
+		out[i] = fmaf(bot - top, f.ay, top);
+	}
+	return out;
+}
+V4 Oracle::sampleTextureFast(const Texture &t, float u, float v, float dudx, float dvdx, float dudy, float dvdy) const {
+	if(!t.valid())
+		return V4{1.0f, 1.0f, 1.0f, 1.0f};
+	float w0 = float(t.w[0]), h0 = float(t.h[0]);
+	float ax = dudx * w0, ay = dvdx * h0, bx = dudy * w0, by = dvdy * h0;
+	float rho2 = fmax2(fmaf(ax, ax, ay * ay), fmaf(bx, bx, by * by));
+	int levels = (int)t.mips.size();
+	float lod = 0.0f;
+	if(rho2 > 1.0f)
+		lod = float((int)(floatBits(rho2) - 0x3f800000u)) * (0.5f / 8388608.0f);
+	lod = clampf(lod, 0.0f, float(levels - 1));
+	float l0f = floorf(lod);
+	int l0 = f2i(l0f), l1 = std::min(l0 + 1, levels - 1);
+	float a = lod - l0f;
+	const float uf = u - floorf(u), vf = v - floorf(v);
+	const float s = 1.0f / 255.0f;
+	V4 c0 = bilinearFast(t, l0, uf, vf);
+	V4 out;
+	if(a == 0.0f || l1 == l0) {
+		for(int i = 0; i < 4; i++)
+			out[i] = c0[i] * s;
+		return out;
+	}
+	V4 c1 = bilinearFast(t, l1, uf, vf);
+	for(int i = 0; i < 4; i++)
+		out[i] = fmaf(c1[i] - c0[i], a, c0[i]) * s;
+	return out;
+}
+
+u32 Oracle::shadeSampleFast(int ipx, int ipy, u32 tri_idx, float &out_depth) const {
+	float px = float(ipx), py = float(ipy);
+	const TriRecord &t = tri(tri_idx);
+	float dx = bitsToFloat(t.depth.x), dy = bitsToFloat(t.depth.y), dz = bitsToFloat(t.depth.z);
+	u32 flags = t.depth.w & 0xffff, instance_id = t.depth.w >> 16;
+	float e0x = bitsToFloat(t.bary0.x), e0y = bitsToFloat(t.bary0.y), e0z = bitsToFloat(t.bary0.z);
+	float e1x = bitsToFloat(t.bary1.x), e1y = bitsToFloat(t.bary1.y), e1z = bitsToFloat(t.bary1.z);
+	float param0 = bitsToFloat(t.bary0.w), param1 = bitsToFloat(t.bary1.w);
+
+	// the sample depth orders the blending: one rounding per operation, as in the reference
+	float inv_ray_pos = dx * px + (dy * py + dz);
+	out_depth = inv_ray_pos;
+	float ray_pos = rcp(inv_ray_pos);
+	float e0 = fmaf(e0x, px, fmaf(e0y, py, e0z));
+	float e1 = fmaf(e1x, px, fmaf(e1y, py, e1z));
+	float b0 = e0 * ray_pos, b1 = e1 * ray_pos;
+
+	float bdx0 = 0, bdx1 = 0, bdy0 = 0, bdy1 = 0;
+	bool textured = (flags & LUCID_INST_HAS_ALBEDO_TEXTURE) != 0;
+	if(textured) {
+		float ray_posx = rcp(inv_ray_pos + dx);
+		float ray_posy = rcp(inv_ray_pos + dy);
+		bdx0 = fmaf(e0 + e0x, ray_posx, -b0), bdx1 = fmaf(e1 + e1x, ray_posx, -b1);
+		bdy0 = fmaf(e0 + e0y, ray_posy, -b0), bdy1 = fmaf(e1 + e1y, ray_posy, -b1);
+	}
+	b0 -= param0, b1 -= param1;
+
+	V4 color{1.0f, 1.0f, 1.0f, 1.0f};
+	if(flags & LUCID_INST_HAS_COLOR)
+		color = decodeRGBA8(inst_colors[instance_id]);
+
+	u32 second = tri_idx & 1;
+	if(textured) {
+		const QuadAttrs &qa = quadAttrs(tri_idx >> 1);
+		float t0x = bitsToFloat(qa.uv0.x), t0y = bitsToFloat(qa.uv0.y);
+		float t1x = bitsToFloat(second == 0 ? qa.uv0.z : qa.uv1.x);
+		float t1y = bitsToFloat(second == 0 ? qa.uv0.w : qa.uv1.y);
+		float t2x = bitsToFloat(second == 0 ? qa.uv1.x : qa.uv1.z);
+		float t2y = bitsToFloat(second == 0 ? qa.uv1.y : qa.uv1.w);
+		float u = fmaf(b0, t1x, fmaf(b1, t2x, t0x)), v = fmaf(b0, t1y, fmaf(b1, t2y, t0y));
+		float dudx = fmaf(bdx0, t1x, bdx1 * t2x), dvdx = fmaf(bdx0, t1y, bdx1 * t2y);
+		float dudy = fmaf(bdy0, t1x, bdy1 * t2x), dvdy = fmaf(bdy0, t1y, bdy1 * t2y);
+		if(flags & LUCID_INST_HAS_UV_RECT) {
+			V4 r = inst_uv_rects[instance_id];
+			u = fmaf(r.z, fractf(u), r.x), v = fmaf(r.w, fractf(v), r.y);
+			dudx *= r.z, dvdx *= r.w, dudy *= r.z, dvdy *= r.w;
+		}
+		V4 tc;
+		if(flags & LUCID_INST_TEX_OPAQUE) {
+			tc = sampleTextureFast(tex[0], u, v, dudx, dvdx, dudy, dvdy);
+			tc.w = 1.0f;
+		} else {
+			tc = sampleTextureFast(tex[1], u, v, dudx, dvdx, dudy, dvdy);
+		}
+		for(int i = 0; i < 4; i++)
+			color[i] *= tc[i];
+	}
+	if(flags & LUCID_INST_HAS_VERTEX_COLORS) {
+		const QuadAttrs &qa = quadAttrs(tri_idx >> 1);
+		const u32 *c = &qa.colors.x;
+		V4 c0 = decodeRGBA8(c[0]), c1 = decodeRGBA8(c[1 + second]), c2 = decodeRGBA8(c[2 + second]);
+		float w0 = 1.0f - b0 - b1;
+		for(int i = 0; i < 4; i++)
+			color[i] *= fmaf(w0, c0[i], fmaf(b0, c1[i], b1 * c2[i]));
+	}
+	if(color.w == 0.0f)
+		return 0;
+
+	V3 normal;
+	if(flags & LUCID_INST_HAS_VERTEX_NORMALS) {
+		const QuadAttrs &qa = quadAttrs(tri_idx >> 1);
+		const u32 *n = &qa.normals.x;
+		V3 n0 = decodeNormalUint(n[0]);
+		V3 n1 = decodeNormalUint(n[1 + second]) - n0, n2 = decodeNormalUint(n[2 + second]) - n0;
+		normal = v3(fmaf(b0, n1.x, fmaf(b1, n2.x, n0.x)), fmaf(b0, n1.y, fmaf(b1, n2.y, n0.y)),
+					fmaf(b0, n1.z, fmaf(b1, n2.z, n0.z)));
+	} else {
+		normal = decodeNormalUint(t.normal);
+	}
+	const LucidLighting &L = cfg.lighting;
+	float ndl = fmaf(-L.sun_dir.x, normal.x, fmaf(-L.sun_dir.y, normal.y, -L.sun_dir.z * normal.z));
+	float light_value = fmax2(0.0f, fmaf(ndl, 0.7f, 0.3f));
+	float amb[3] = {L.ambient_color.x * L.ambient_power, L.ambient_color.y * L.ambient_power,
+					L.ambient_color.z * L.ambient_power};
+	float sun[3] = {L.sun_color.x * L.sun_power, L.sun_color.y * L.sun_power, L.sun_color.z * L.sun_power};
+	for(int i = 0; i < 3; i++)
+		color[i] = finalShadeFast(color[i], fmaf(sun[i], light_value, amb[i]));
+	return encodeRGBA8(color);
+}
+
 // shared/shading.glsl:186-314; window of 3 (+1 depth when counting invalid pixels)
 struct Reducer {
 	float prev_depths[4];
@@ -963,8 +1147,10 @@ struct Reducer {
 	float out_trans;
 	float out_color[3];
 	bool additive;
+	bool fast = false; // the product's colour contract: fused multiply-adds in the blend
 	u32 invalid;
-	void init(bool additive_) {
+	void init(bool additive_, bool fast_ = false) {
+		fast = fast_;
 		for(int i = 0; i < 4; i++)
 			prev_depths[i] = 999999999.0f;
 		for(int i = 0; i < 3; i++)
@@ -975,6 +1161,18 @@ struct Reducer {
 	}
 	void blend(u32 c) {
 		V4 cc = decodeRGBA8(c);
+		if(fast) {
+			if(additive) {
+				for(int i = 0; i < 3; i++)
+					out_color[i] = fmaf(cc[i], cc.w, out_color[i]);
+			} else {
+				const float wt = cc.w * out_trans;
+				for(int i = 0; i < 3; i++)
+					out_color[i] = fmaf(cc[i], wt, out_color[i]);
+				out_trans = fmaf(-cc.w, out_trans, out_trans);
+			}
+			return;
+		}
 		if(additive) {
 			for(int i = 0; i < 3; i++)
 				out_color[i] += cc[i] * cc.w;
@@ -1022,6 +1220,12 @@ struct Reducer {
 		for(int i = 2; i >= 0; i--)
 			if(prev_colors[i] != 0)
 				blend(prev_colors[i]);
+		if(fast) {
+			rgb[0] = saturate(fmaf(out_trans, bg.x, out_color[0]));
+			rgb[1] = saturate(fmaf(out_trans, bg.y, out_color[1]));
+			rgb[2] = saturate(fmaf(out_trans, bg.z, out_color[2]));
+			return;
+		}
 		rgb[0] = saturate(out_color[0] + out_trans * bg.x);
 		rgb[1] = saturate(out_color[1] + out_trans * bg.y);
 		rgb[2] = saturate(out_color[2] + out_trans * bg.z);
@@ -1270,7 +1474,7 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 				std::vector<std::pair<float, u32>> exact[32];
 				u32 px_frags[32];
 				for(int p = 0; p < 32; p++)
-					red[p].init(additive), px_frags[p] = 0;
+					red[p].init(additive, !reference_colour), px_frags[p] = 0;
 
 				u32 frag_total = 0, tri_count = (u32)list.size();
 				u32 processed = 0; // samples consumed so far (segment boundaries every 256)
@@ -1296,7 +1500,8 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 						px_frags[pid]++;
 						if(!stop) {
 							float depth;
-							u32 color = shadeSample(ipx, ipy, rt.tri_idx, depth);
+							u32 color = reference_colour ? shadeSample(ipx, ipy, rt.tri_idx, depth) :
+														  shadeSampleFast(ipx, ipy, rt.tri_idx, depth);
 							red[pid].push(color, depth, vis_errors);
 							exact[pid].push_back(std::make_pair(depth, color));
 						}
@@ -1344,7 +1549,7 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 									 [](const std::pair<float, u32> &a,
 										const std::pair<float, u32> &b) { return a.first > b.first; });
 					Reducer ex;
-					ex.init(additive);
+					ex.init(additive, !reference_colour);
 					for(auto &s : exact[p])
 						if(s.second != 0)
 							ex.blend(s.second);
@@ -1729,6 +1934,13 @@ void oracle_read_bin_levels(void *h, uint8_t *dst) {
 float oracle_pow(float x, float y) { return orc_pow(x, y); }
 float oracle_log2(float x) { return orc_log2(x); }
 uint32_t oracle_shade_probe(void *h, int px, int py, uint32_t tri_idx, float *depth) {
-	return ((Oracle *)h)->shadeSample(px, py, tri_idx, *depth);
+	Oracle *o = (Oracle *)h;
+	return o->reference_colour ? o->shadeSample(px, py, tri_idx, *depth) : o->shadeSampleFast(px, py, tri_idx, *depth);
 }
+// 1: colour arithmetic in the reference's operation order (pow by polynomial, one rounding per operation);
+// 0 (default): the product's colour contract (fused multiply-adds, table sRGB) that the kernels reproduce bit for bit
+void oracle_set_reference_colour(void *h, int on) { ((Oracle *)h)->reference_colour = on != 0; }
+// finalShading of one channel in both forms (tests/test_colour_contract.py)
+float oracle_final_shade_fast(float c, float light) { return finalShadeFast(c, light); }
+float oracle_final_shade_reference(float c, float light) { return saturate(linearToSRGB1(SRGBToLinear1(c) * light)); }
 }

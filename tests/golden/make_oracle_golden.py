@@ -29,7 +29,7 @@ def record(o):
                 image=digest(o.read_image()), frag_counts=digest(o.read_frag_counts()),
                 bin_counts=digest(counts[:6]), bin_quads=digest(bq), bin_tris=digest(bt),
                 quad_aabbs=digest(np.concatenate([o.read_quad_aabbs(0), o.read_quad_aabbs(1)])),
-                tri_records=digest(np.concatenate([o.read_tri_records(0), o.read_tri_records(1)])))
+                tri_records=digest(pu.canonical_tri_records(np.concatenate([o.read_tri_records(0), o.read_tri_records(1)]))))
 
 
 FULL_MVQ = 4793490  # the reference's MAX_VISIBLE_QUADS formula at the default memory budget

@@ -215,7 +215,8 @@ def _golden_mismatches(r, img, g):
     for name, value in (("bin_counts", counts[:6]), ("bin_quads", pu.canonical_lists(bq, counts[0])),
                         ("bin_tris", pu.canonical_lists(bt, counts[3])), ("frag_counts", r.read_frag_counts()),
                         ("quad_aabbs", np.concatenate([r.read_quad_aabbs(0, ns), r.read_quad_aabbs(1, nl)])),
-                        ("tri_records", np.concatenate([r.read_tri_records(0, ns), r.read_tri_records(1, nl)])),
+                        ("tri_records", pu.canonical_tri_records(np.concatenate([r.read_tri_records(0, ns),
+                                                                                  r.read_tri_records(1, nl)]))),
                         ("image", img)):  # the fp contract makes even the colours bit-identical
         if digest(value) != g[name]:
             bad.append(name)

@@ -171,7 +171,8 @@ def test_checker_bin_counts_and_lists_match_the_reference_on_whole_scenes(golden
     large_seen = images = 0
     for e in golden["bin_scenes"]:
         sc = small[e["scene"]]
-        o = pu.run_oracle(sc, mvq=e["max_visible_quads"], threads=4)
+        # the reference's operation order for colour: that is the form the image digest was taken in
+        o = pu.run_oracle(sc, mvq=e["max_visible_quads"], threads=4, reference_colour=True)
         try:
             assert [int(o.info[1]), int(o.info[2])] == e["visible"]
             _, counts = api.split_info(o.info, o.bin_count)
