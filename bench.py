@@ -44,7 +44,8 @@ WORKLOADS = {
 }
 DEFAULT_CONFIG = 3  # BASELINE.json: "4K exact-OIT frames/sec on a 10M-triangle synthetic scene"
 KERNEL_SOURCES = ["lucid_b200/csrc/common.cuh", "lucid_b200/csrc/setup.cu", "lucid_b200/csrc/binning.cu",
-                  "lucid_b200/csrc/raster.cu"]
+                  "lucid_b200/csrc/raster_common.cuh", "lucid_b200/csrc/raster_bins.cu", "lucid_b200/csrc/raster_sort.cu",
+                  "lucid_b200/csrc/raster_shade.cu"]
 
 
 def kernel_source_hash() -> str:
@@ -331,7 +332,7 @@ def run_ours(args):
                     "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                     "config": {"workload": v["workload"], "parallelism": "views sharded x%d" % world,
                                "l2": "256 MiB device memset between timed frames (untimed)"},
-                    "e2e": v["e2e"], "gpu_launches": int(8 * args.steps)}
+                    "e2e": v["e2e"], "gpu_launches": int(9 * args.steps)}
             print(json.dumps(line), flush=True)
         if dist is not None:
             dist.destroy_process_group()
@@ -477,14 +478,14 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         ab = algorithmic_bytes(stats, scene, width, height)
-        # LOW and HIGH bins share the raster kernels (block lists, then block sort + shading)
-        stage_names = ["setup", "bin_count", "bin_scan", "bin_dispatch", "raster_lists", "raster_shade", "finish"]
+        # LOW and HIGH bins share the three raster kernels: block lists, block sort, shading
+        stage_names = ["setup", "bin_count", "bin_scan", "bin_dispatch", "raster_lists", "raster_sort", "raster_shade"]
         stage_ms = {n: round(float(stage[i]), 4) for i, n in enumerate(stage_names)}
         stage_ms["frame_with_stage_events"] = round(float(stage[7]), 4)
         stage_ms["frame"] = round(frame_ms, 4)  # timed frames: first launch -> last kernel done, the library's own events
         # the library's events and ours are on one stream: our bracket can only be the wider one
         assert ms_per_step >= 0.98 * frame_ms, (ms_per_step, frame_ms)
-        raster_ms = float(stage[4] + stage[5])
+        raster_ms = float(stage[4] + stage[5] + stage[6])
         fracs = {
             "setup": ab["setup"] / (stage[0] * 1e-3) / 1e9 / peak if stage[0] > 0 else None,
             "bin_count": ab["bin_count"] / (stage[1] * 1e-3) / 1e9 / peak if stage[1] > 0 else None,
@@ -548,8 +549,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(width * height * 4 + info.size * 4)},
             "sustained": sustained,
             # k_frame_begin, k_quad_cull, k_tri_setup, k_bin_count, k_bin_scan, k_bin_dispatch, k_raster_bins,
-            # k_raster_blocks (+ k_info_out when LucidInfo is read back)
-            "gpu_launches": int(8 * args.steps),
+            # k_block_sort, k_block_shade (+ k_info_out when LucidInfo is read back)
+            "gpu_launches": int(9 * args.steps),
             "clocks": clocks,
             "wall_s": round(wall, 3),
         }

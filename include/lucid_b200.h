@@ -48,6 +48,11 @@ typedef struct LucidCreateInfo {
 	int32_t device;				  /* CUDA device ordinal */
 	void *stream;				  /* cudaStream_t to run on; NULL -> the renderer creates one */
 	int32_t bin_row_begin, bin_row_end; /* owned bin rows [begin,end) for the multi-GPU split; 0,0 -> all */
+	uint32_t max_block_entries;	  /* capacity of the sorted-entry stream between the block sort and the shading
+									 kernel: one 32-byte entry per (triangle, 8x4 half-block or 8x8 block) pair of a
+									 frame; 0 -> max(16 * max_visible_quads, 2^22).  A frame that needs more paints the
+									 bins that did not fit red and reports LUCID_E_LIMIT (the reference bounds the same
+									 lists per work group: raster_low.glsl:22-32, raster_high.glsl:35-44) */
 } LucidCreateInfo;
 
 int lucid_create(const LucidCreateInfo *info, lucid_renderer **out);

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_bin_scan(const Params p) {
 		// list capacity check: the reference sizes both lists at 2 * MAX_VISIBLE_QUADS and never checks
 		if((u32)tot_q > p.bin_list_capacity || (u32)tot_t > p.bin_list_capacity)
 			info->temp[1] = 1;
-		for(int i = 0; i < 8; i++)
+		for(int i = 0; i < WORK_COUNTERS; i++)
 			p.work_counters[i] = 0;
 	}
 }

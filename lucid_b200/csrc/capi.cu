@@ -256,15 +256,22 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.setup_lookback, (size_t)LUCID_MAX_INSTANCES * 4));
 	CUC(devAlloc(r, &p.setup_ticket, 4));
 	CUC(devAlloc(r, &p.bin_flags, (size_t)p.bin_count));
-	CUC(devAlloc(r, &p.work_counters, 8));
+	CUC(devAlloc(r, &p.work_counters, (size_t)WORK_COUNTERS));
 	CUC(devAlloc(r, &p.bin_cost, (size_t)p.bin_count));
 	p.bin_begin = p.row_begin * p.bin_count_x, p.bin_end = p.row_end * p.bin_count_x;
 	CUC(devAlloc(r, &p.block_lists, (size_t)p.bin_count * (BIN_LIST_BYTES / sizeof(uint4))));
 	CUC(devAlloc(r, &p.block_counts, (size_t)p.bin_count * 32));
 	p.block_items_cap = (u32)p.bin_count * 32u;
-	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 5)); // one region per size class (raster.cu ITEM_CLASSES)
+	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 5)); // one region per size class (ITEM_CLASSES)
 	CUC(devAlloc(r, &p.large_keys, rasterLargeKeysCount(r->num_sms)));
-	CUC(devAlloc(r, &p.block_aux, rasterLargeKeysCount(r->num_sms)));
+	// sorted-entry stream: one entry per (triangle, half-block or block) pair of the frame
+	{
+		const unsigned long long def = std::max<unsigned long long>(16ull * mvq, 1ull << 22);
+		const unsigned long long want = info->max_block_entries > 0 ? (unsigned long long)info->max_block_entries : def;
+		p.stream_capacity = (u32)std::min<unsigned long long>(want, 0x7fffffffull);
+	}
+	CUC(devAlloc(r, &p.sorted_rec, (size_t)p.stream_capacity));
+	CUC(devAlloc(r, &p.sorted_aux, (size_t)p.stream_capacity));
 	CUC(devAlloc(r, &r->images[0], (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->images[1], (size_t)p.width * p.height));
 	r->image = r->images[0];
@@ -438,8 +445,9 @@ int lucid_wait(lucid_renderer *r) {
 	}
 	if(overflow)
 		return fail(r, LUCID_E_LIMIT,
-					"a frame's per-bin lists exceeded 2 * max_visible_quads entries: nothing was rasterised and the "
-					"owned bins were painted red; create the renderer with a larger max_visible_quads");
+					"a frame exceeded the renderer's list storage (per-bin lists of 2 * max_visible_quads entries, or the "
+					"sorted-entry stream of max_block_entries): the affected bins were painted red; create the renderer "
+					"with a larger max_visible_quads / max_block_entries");
 	return LUCID_OK;
 }
 

@@ -88,15 +88,18 @@ struct Params {
 	int image_pitch;
 	u32 *frag_counts;	  // optional per-pixel fragment counts (debug / parity), may be null
 	u32 *bin_flags;		  // per bin: bit 0 promoted LOW->HIGH, bit 1 over the reference's HIGH limits (red)
-	u32 *work_counters;	  // [0] bins taken [1] block items taken [3..7] block items per size class
+	u32 *work_counters;	  // WC_*: bins / sort items / shade items taken, items per size class, stream entries handed out
 	u32 *host_status;	  // pinned host word of this frame: set non-zero when the bin lists overflowed (the frame is red)
 	u64 *bin_cost;		  // per bin: warp cycles the raster kernels spent on it this frame (split balancing)
 	uint4 *block_lists;	  // per bin BIN_LIST_BYTES: 32 half-block lists (HIGH) or 16 block lists (LOW)
 	int *block_counts;	  // 32 per bin: entries of each list
-	uint2 *block_items;	  // work items of k_raster_blocks (item, entries): one region of block_items_cap per size class
+	uint4 *block_items;	  // work items of the block stages (item, entries, stream offset, -): one region of block_items_cap per size class
 	u32 block_items_cap;
-	u32 *large_keys;	  // per k_raster_blocks warp: sort keys of lists too long for shared memory
-	uint4 *block_aux;	  // per k_raster_blocks warp: (depth plane, constant colour) per list entry
+	u32 *large_keys;	  // per k_block_sort warp: sort keys of lists too long for shared memory
+	// the sorted-entry stream k_block_sort writes and k_block_shade reads: per work item a slice of both planes
+	uint4 *sorted_rec;	  // (triangle, pixel mask of the upper / only half, pixel mask of the lower half, -)
+	uint4 *sorted_aux;	  // (depth plane xyz, constant colour or AUX_VARYING)
+	u32 stream_capacity;  // entries
 	// textures: level offsets into one RGBA8 array per slot
 	const uchar4 *tex_data[2];
 	int tex_width[2], tex_height[2], tex_levels[2];
@@ -286,6 +289,7 @@ void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream,
 				  cudaEvent_t *stage_events, int num_sms);
 void launchCompositeBins(const Params &p, u32 *dst, int dst_pitch, cudaStream_t stream, int num_sms);
 size_t rasterLargeKeysCount(int num_sms);
+constexpr int WORK_COUNTERS = 12; // raster_common.cuh WC_*
 
 // 32 half-block lists of up to 4096 8-byte records (raster_high.glsl:27); a LOW bin uses the first
 // 16 x 256 16-byte records

@@ -497,7 +497,7 @@ template <bool FULL_SORT> __device__ __forceinline__ void tileSteps(u32 *keys, i
 }
 
 // keys[0..n) ascending in shared memory; the array has room for n rounded up to a power of two
-__device__ __noinline__ void warpSortShared(u32 *keys, int n) {
+static __device__ __noinline__ void warpSortShared(u32 *keys, int n) {
 	const u32 lane = laneId();
 	if(n <= 1)
 		return;
@@ -531,7 +531,7 @@ __device__ __noinline__ void warpSortShared(u32 *keys, int n) {
 // sorted in an L2-resident global array: 1024-key blocks are staged through shared memory, only
 // the steps with a partner distance of 1024 or more touch global memory directly.
 constexpr int SMEM_KEYS = 1024;
-__device__ __noinline__ void warpSortLarge(u32 *gkeys, int n, u32 *skeys) {
+static __device__ __noinline__ void warpSortLarge(u32 *gkeys, int n, u32 *skeys) {
 	const u32 lane = laneId();
 	int padded = 2 * SMEM_KEYS;
 	while(padded < n)

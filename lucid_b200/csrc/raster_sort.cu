@@ -1,0 +1,278 @@
+// raster_sort.cu -- stage 2 of the raster pipeline: depth sort of every block list (generateBlocks /
+// generateRBlocks sort, raster_low.glsl:107-160, raster_high.glsl:146-260) and the frame's bookkeeping.
+// A work item is one 8x8 block of a LOW bin or one 8x4 half-block of a HIGH bin and belongs to one warp.  The
+// kernel leaves the item's entries in depth order in the sorted-entry stream: two contiguous planes of 16-byte
+// words, (triangle, pixel mask of the upper / only half, pixel mask of the lower half, -) and (depth plane xyz,
+// constant colour or AUX_VARYING), which is all k_block_shade reads of a list.
+#include "raster_common.cuh"
+
+namespace lucid {
+
+#ifndef SORT_MIN_CTAS
+#define SORT_MIN_CTAS 8
+#endif
+#ifndef RB_KEY_UNROLL
+#define RB_KEY_UNROLL 2
+#endif
+constexpr int KEY_UNROLL = RB_KEY_UNROLL;
+
+// ------------------------------------------------------------------------------------------------
+// frame bookkeeping done by the first CTAs of k_block_sort before they take work items (two
+// more launches on a frame of a few hundred microseconds would cost more than the work itself):
+// background for empty bins (the reference leaves them to the application's clear,
+// lucid_app.cpp:606-619), red for bins over the reference's limits (raster_high.glsl:313-317), and
+// the level bookkeeping of promoted bins: appended to the HIGH list in bin order
+// (raster_low.glsl:230-237,294-298).  Everything read here was written by k_raster_bins.
+__device__ __forceinline__ void finishBins(const Params &p, u32 background, u32 *s_mask) {
+	const int lane = laneId(), warp = threadIdx.x >> 5;
+	// bin lists over their capacity (k_bin_scan set temp[1], dispatch and k_raster_bins did nothing): every
+	// owned bin is painted red, like a bin over the reference's own limits, and the host is told
+	const u32 overflow = p.info->temp[1]; // bit 0: bin lists, bit 1: sorted-entry stream (those bins carry flag 2)
+	const bool list_overflow = (overflow & 1u) != 0;
+	if(overflow != 0 && blockIdx.x == 0 && threadIdx.x == 0 && p.host_status)
+		*p.host_status = overflow;
+	// 32 bins per CTA and round (one round on a B200: 740 CTAs cover 23 680 bins)
+	for(int first = blockIdx.x * 32; first < p.bin_count; first += gridDim.x * 32) {
+		if(warp == 0) {
+			const int b = first + lane;
+			u32 kind = 0; // 1 background, 2 red
+			if(b < p.bin_count && ownsBin(p, b)) {
+				const bool empty = cntc(p, LUCID_CNT_TRI_COUNTS)[b] + cntc(p, LUCID_CNT_QUAD_COUNTS)[b] * 2 == 0;
+				kind = (list_overflow || (p.bin_flags[b] & 2u)) ? 2u : empty ? 1u : 0u;
+			}
+			const u32 fill = __ballot_sync(0xffffffffu, kind != 0), red = __ballot_sync(0xffffffffu, kind == 2);
+			if(lane == 0)
+				s_mask[0] = fill, s_mask[1] = red;
+		}
+		__syncthreads();
+		const u32 red = s_mask[1];
+		u32 fill = s_mask[0];
+		__syncthreads();
+		for(int n = 0; fill; n++) {
+			const int j = __ffs(fill) - 1;
+			fill &= fill - 1;
+			if((n & (BLOCK_WARPS - 1)) != warp)
+				continue;
+			const int b = first + j, by = b / p.bin_count_x, bx = b - by * p.bin_count_x;
+			const u32 value = ((red >> j) & 1u) ? 0x000000ffu : background;
+			const int gx = bx * BIN_SIZE + lane;
+			if(gx < p.width)
+#pragma unroll 4
+				for(int y = 0; y < BIN_SIZE; y++) {
+					const int gy = by * BIN_SIZE + y;
+					if(gy >= p.height)
+						break;
+					p.image[(size_t)gy * p.image_pitch + gx] = value;
+					if(p.frag_counts)
+						p.frag_counts[(size_t)gy * p.width + gx] = 0;
+				}
+		}
+	}
+}
+
+__device__ __forceinline__ void promoteBins(const Params &p, int *s_warp) {
+	const int threads = BLOCK_WARPS * 32;
+	const int n_low = p.info->bin_level_counts[LUCID_BIN_LEVEL_LOW];
+	const int *low = cntc(p, LUCID_CNT_LOW_BINS);
+	int *high = p.counts + (size_t)LUCID_CNT_HIGH_BINS * p.bin_count;
+	const int n_high = p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH];
+	const int per = (n_low + threads - 1) / threads;
+	const int i0 = min((int)threadIdx.x * per, n_low), i1 = min(i0 + per, n_low);
+	int mine = 0;
+	for(int i = i0; i < i1; i++)
+		mine += (p.bin_flags[low[i]] & 1u) ? 1 : 0;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int incl = mine;
+	for(int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if(lane >= o)
+			incl += t;
+	}
+	if(lane == 31)
+		s_warp[warp] = incl;
+	__syncthreads();
+	int before = 0, total = 0;
+	for(int w = 0; w < BLOCK_WARPS; w++) {
+		before += w < warp ? s_warp[w] : 0;
+		total += s_warp[w];
+	}
+	if(total == 0)
+		return;
+	int pos = n_high + before + incl - mine;
+	for(int i = i0; i < i1; i++)
+		if(p.bin_flags[low[i]] & 1u)
+			high[pos++] = low[i];
+	if(threadIdx.x == 0) {
+		const int all = n_high + total;
+		p.info->bin_level_counts[LUCID_BIN_LEVEL_HIGH] = all;
+		u32 nd = (u32)min(all, p.max_dispatches / 2);
+		if(nd > p.info->bin_level_dispatches[LUCID_BIN_LEVEL_HIGH][0])
+			p.info->bin_level_dispatches[LUCID_BIN_LEVEL_HIGH][0] = nd;
+	}
+}
+
+
+__global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(const __grid_constant__ Params p, u32 background) {
+	__shared__ __align__(16) u32 s_keys[BLOCK_WARPS][SMEM_KEYS];
+	__shared__ int s_misc[BLOCK_WARPS];
+	const int lane = laneId(), warp = threadIdx.x >> 5;
+	pdlEntry();
+	finishBins(p, background, reinterpret_cast<u32 *>(s_misc));
+	if(blockIdx.x == gridDim.x - 1) {
+		__syncthreads();
+		promoteBins(p, s_misc);
+	}
+	u32 *large_keys = p.large_keys + (size_t)(blockIdx.x * BLOCK_WARPS + warp) * MAX_HBLOCK_TRIS;
+	u32 class_end[ITEM_CLASSES]; // exclusive end of every class in ticket order
+	{
+		u32 acc = 0;
+#pragma unroll
+		for(int k = 0; k < ITEM_CLASSES; k++)
+			class_end[k] = acc += p.work_counters[WC_CLASS + k];
+	}
+	const u32 n_items = class_end[ITEM_CLASSES - 1];
+	u32 frag_acc = 0, hbt_acc = 0;
+	while(true) {
+		u32 index = lane == 0 ? atomicAdd(&p.work_counters[WC_SORT], 1u) : 0u;
+		index = __shfl_sync(0xffffffffu, index, 0);
+		if(index >= n_items)
+			break;
+		const uint4 entry = fetchWorkItem(p, index, class_end);
+		const long long t_item = clock64();
+		const u32 item = entry.x;
+		const int count = (int)entry.y;
+		const int bin_id = (int)(item >> 6), sub = (int)(item & 31u);
+		const bool high = (item & 32u) != 0;
+		const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
+		const int pos_x = bin_x * BIN_SIZE, pos_y = bin_y * BIN_SIZE;
+		const int cx8 = (sub & 3) * 8, ry = sub >> 2;
+		const unsigned char *list = binLists(p, bin_id) + (high ? (size_t)sub * HB_LIST_CAP * 8 : (size_t)sub * MAX_BLOCK_TRIS * 16);
+		const bool large = count > SMEM_KEYS;
+		u32 *keys = large ? large_keys : s_keys[warp];
+
+		// depth keys from the centroid of the covered pixels (raster.glsl:142-176); the records are one round
+		// trip, the triangles' depth planes a second, dependent one: the records of the next iteration are
+		// requested together with this iteration's planes
+		auto loadRec = [&](int i) {
+			uint4 r4 = make_uint4(0, 0, 0, 0);
+			if(i < count) {
+				if(high) {
+					uint2 r = __ldg(reinterpret_cast<const uint2 *>(list) + i);
+					r4.x = r.x, r4.y = r.y;
+				} else {
+					r4 = __ldg(reinterpret_cast<const uint4 *>(list) + i);
+				}
+			}
+			return r4;
+		};
+		uint4 rec_next[KEY_UNROLL];
+#pragma unroll
+		for(int u = 0; u < KEY_UNROLL; u++)
+			rec_next[u] = loadRec(u * 32 + lane);
+		for(int i0 = 0; i0 < count; i0 += 32 * KEY_UNROLL) {
+			uint4 rec[KEY_UNROLL], dq[KEY_UNROLL];
+#pragma unroll
+			for(int u = 0; u < KEY_UNROLL; u++) {
+				rec[u] = rec_next[u];
+				dq[u] = __ldg(reinterpret_cast<const uint4 *>(p.tri_shade + (rec[u].x & 0xffffffu)));
+			}
+			if(i0 + 32 * KEY_UNROLL < count) {
+#pragma unroll
+				for(int u = 0; u < KEY_UNROLL; u++)
+					rec_next[u] = loadRec(i0 + 32 * KEY_UNROLL + u * 32 + lane);
+			}
+#pragma unroll
+			for(int u = 0; u < KEY_UNROLL; u++) {
+				const int i = i0 + u * 32 + lane;
+				if(i >= count)
+					continue;
+				u32 tri_idx, mins, maxs, depth;
+				if(high) {
+					unpackHighRecord(make_uint2(rec[u].x, rec[u].y), tri_idx, mins, maxs);
+					int nf, cx, cy;
+					rowsCentroid(mins, maxs, cx8, nf, cx, cy);
+					float scale = __fdiv_rn(0.5f, float(nf));
+					float cpx = float(cx) * scale + (float(cx8) + float(pos_x));
+					float cpy = float(cy) * scale + (float(ry * 4) + float(pos_y));
+					depth = blockDepth(dq[u], cpx, cpy, float(0x7fffe)) << 14;
+					frag_acc += (u32)nf;
+				} else {
+					int nf0, cx0, cy0, nf1, cx1, cy1;
+					unpackLowRecord(rec[u], false, tri_idx, mins, maxs);
+					rowsCentroid(mins, maxs, cx8, nf0, cx0, cy0);
+					unpackLowRecord(rec[u], true, tri_idx, mins, maxs);
+					rowsCentroid(mins, maxs, cx8, nf1, cx1, cy1);
+					// both halves use row offsets 1,3,5,7 for the centroid, exactly as the reference does
+					float cx = float(cx0) + float(cx1), cy = float(cy0) + float(cy1);
+					float scale = __fdiv_rn(0.5f, float(nf0 + nf1));
+					float cpx = cx * scale + float(pos_x + cx8), cpy = cy * scale + float(pos_y + ry * 8);
+					depth = blockDepth(dq[u], cpx, cpy, float(0x3ffffe)) << 10;
+					frag_acc += (u32)(nf0 + nf1);
+				}
+				keys[i] = (u32)i | depth;
+			}
+		}
+		__syncwarp();
+		// stats: LOW counts the block's triangles once per half-block (raster_low.glsl:272-275),
+		// HIGH the exact half-block list (raster_high.glsl:309-310)
+		hbt_acc += lane == 0 ? (u32)count * (high ? 1u : 2u) : 0u;
+		const int slot_bits = high ? 14 : 10;
+		if(high || count > 3) { // LOW blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
+			if(large)
+				warpSortLarge(keys, count, s_keys[warp]);
+			else
+				warpSortShared(keys, count);
+			// depth ties by triangle index: the triangle of a list position is looked up in the list itself
+			if(high)
+				warpFixDepthTies(keys, count, slot_bits,
+								 [&](u32 pos) { return __ldg(reinterpret_cast<const uint2 *>(list) + pos).x & 0xffffffu; });
+			else
+				warpFixDepthTies(keys, count, slot_bits, [&](u32 pos) { return __ldg(reinterpret_cast<const uint4 *>(list) + pos).x; });
+		}
+		// the entries in sorted order: (triangle, pixel masks) and (depth plane, constant colour)
+		const u32 pos_mask = (1u << slot_bits) - 1u;
+		uint4 *out_rec = p.sorted_rec + entry.z, *out_aux = p.sorted_aux + entry.z;
+		for(int i = lane; i < count; i += 32) {
+			const u32 pos = (large ? __ldcg(keys + i) : keys[i]) & pos_mask;
+			u32 tri_idx, mins, maxs, mask0, mask1 = 0;
+			int nf;
+			if(high) {
+				unpackHighRecord(__ldg(reinterpret_cast<const uint2 *>(list) + pos), tri_idx, mins, maxs);
+				mask0 = rowsToBits(mins, maxs, cx8, nf);
+			} else {
+				const uint4 r = __ldg(reinterpret_cast<const uint4 *>(list) + pos);
+				unpackLowRecord(r, false, tri_idx, mins, maxs);
+				mask0 = rowsToBits(mins, maxs, cx8, nf);
+				unpackLowRecord(r, true, tri_idx, mins, maxs);
+				mask1 = rowsToBits(mins, maxs, cx8, nf);
+			}
+			const uint4 *src = reinterpret_cast<const uint4 *>(p.tri_shade + tri_idx);
+			const uint4 dq = __ldg(src), misc = __ldg(src + 1);
+			__stcg(out_rec + i, make_uint4(tri_idx, mask0, mask1, 0u));
+			__stcg(out_aux + i, make_uint4(dq.x, dq.y, dq.z, misc.w != 0 ? misc.z : AUX_VARYING));
+		}
+		__syncwarp();
+		if(lane == 0)
+			atomicAdd(reinterpret_cast<unsigned long long *>(p.bin_cost) + bin_id, (unsigned long long)(clock64() - t_item));
+	}
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1) {
+		frag_acc += __shfl_xor_sync(0xffffffffu, frag_acc, o);
+		hbt_acc += __shfl_xor_sync(0xffffffffu, hbt_acc, o);
+	}
+	if(lane == 0) {
+		if(frag_acc)
+			atomicAdd(&p.info->stats[0], frag_acc);
+		if(hbt_acc)
+			atomicAdd(&p.info->stats[1], hbt_acc);
+	}
+}
+
+static int blockSortGrid(int num_sms) { return num_sms * SORT_MIN_CTAS; }
+size_t rasterLargeKeysCount(int num_sms) { return (size_t)blockSortGrid(num_sms) * BLOCK_WARPS * MAX_HBLOCK_TRIS; }
+
+void launchBlockSort(const Params &p, u32 background, cudaStream_t stream, int num_sms) {
+	launchPDL(k_block_sort, blockSortGrid(num_sms), BLOCK_WARPS * 32, 0, stream, p, background);
+}
+
+} // namespace lucid

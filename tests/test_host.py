@@ -159,9 +159,9 @@ def test_create_without_gpu_fails_loudly():
 def test_bad_create_arguments():
     lib = api.load_library()
     h = C.c_void_p()
-    ci = api.CreateInfo(0, 0, 0, 0, 0, 0, None, 0, 0)
+    ci = api.CreateInfo(0, 0, 0, 0, 0, 0, None, 0, 0, 0)
     assert lib.lucid_create(C.byref(ci), C.byref(h)) == -1
-    ci = api.CreateInfo(8192, 100, 0, 0, 0, 0, None, 0, 0)
+    ci = api.CreateInfo(8192, 100, 0, 0, 0, 0, None, 0, 0, 0)
     assert lib.lucid_create(C.byref(ci), C.byref(h)) == -3  # 7-bit bin coordinates
     assert b"4096" in lib.lucid_last_error(None)
 

@@ -32,7 +32,7 @@ for ci in configs:
     ms = np.median(np.array(times), axis=0)
     st = r.getStats()
     print(f"== config {ci} ({sc['name']}) gen+setup {time.time() - t0:.1f}s")
-    print("   stage_ms", dict(zip(["setup", "count", "scan", "dispatch", "low", "high", "finish", "frame"],
+    print("   stage_ms", dict(zip(["setup", "count", "scan", "dispatch", "lists", "sort", "shade", "frame"],
                                   np.round(ms, 3).tolist())))
     print("   stats", json.dumps(st))
     print("   verifyInfo", r.verifyInfo()[:3], "frag image sum", int(r.read_frag_counts().sum()))

@@ -6,7 +6,7 @@
 tag=${1:-r2}
 what=${2:-"tests bench others ncu"}
 full=${3:-"3 1"}
-lpf=${LAUNCHES_PER_FRAME:-9}   # kernels per frame incl. k_info_out
+lpf=${LAUNCHES_PER_FRAME:-10}   # kernels per frame incl. k_info_out
 out=gpurun_out
 mkdir -p $out
 nproc > $out/${tag}_nproc.txt
@@ -43,7 +43,7 @@ if [[ $what == *ncu* ]]; then
   # per-function instruction / stall-sample shares of the shading kernel, then drop the reports
   # (gpurun only copies 64 MiB back)
   for c in $full; do
-    for k in ${NCU_KERNELS:-k_raster_blocks}; do
+    for k in ${NCU_KERNELS:-k_block_shade k_block_sort}; do
       ncu -i $out/${tag}_full_config$c.ncu-rep --page source --csv --print-source cuda,sass --kernel-name $k > $out/src_$c.csv 2>/dev/null
       python tools/ncu_funcs.py $out/src_$c.csv > $out/${tag}_${k}_config${c}_functions.txt 2>&1
     done
