@@ -192,7 +192,8 @@ def timed_steps(rig, args, render, after_frame, steps):
     bracketed by CUDA events on the launching stream, L2 flushed (untimed) between steps.  Returns the per-step
     times of this rank (ms) and the wall time of the loop."""
     torch = rig.torch
-    plain = rig.api.RENDER_ASYNC | rig.api.RENDER_SKIP_INFO | rig.api.RENDER_NO_STAGE_TIMES
+    plain = rig.api.RENDER_ASYNC | rig.api.RENDER_SKIP_INFO | rig.api.RENDER_NO_STAGE_TIMES | rig.api.RENDER_CULL_INSTANCES
+    rig.barrier()  # every rank enters the loop together (the device-side frame flags give up after a few seconds)
     for w in range(args.warmup):  # the same sequence as a timed step
         render(w, plain)
         after_frame()
@@ -223,7 +224,7 @@ def sustained_run(rig, render, after_frame, seconds: float, frames_per_step: int
     """Back-to-back frames for at least `seconds` of wall clock, no flush in between (the scene's records are
     several times the L2), device-timed by one event pair around the whole run."""
     torch = rig.torch
-    plain = rig.api.RENDER_ASYNC | rig.api.RENDER_SKIP_INFO | rig.api.RENDER_NO_STAGE_TIMES
+    plain = rig.api.RENDER_ASYNC | rig.api.RENDER_SKIP_INFO | rig.api.RENDER_NO_STAGE_TIMES | rig.api.RENDER_CULL_INSTANCES
     rig.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -251,6 +252,7 @@ def sustained_run(rig, render, after_frame, seconds: float, frames_per_step: int
 
 
 def e2e_run(rig, frame, steps, frames_per_step):
+    rig.barrier()
     for w in range(3):
         frame(w)
     rig.r.wait()
@@ -381,19 +383,31 @@ def run_ours(args):
             rows = ranges[rank]
             split_kind = "row-major bin ranges balanced on measured cost, %d feedback steps" % args.balance_iters
 
-    # composite target for the bin-row split: every rank stores into rank 0's image over NVLink
-    peer_ptr = None
+    # composite target for the bin-row split: every rank stores into rank 0's image over NVLink, and signals the
+    # frame's completion through a flag in rank 0's memory (lucid_signal / lucid_wait_flags); --completion allreduce
+    # is the NCCL alternative
+    peer_ptr, flags_ptr = None, None
+    use_flags = split and args.completion == "flags"
     if split:
-        handle = [r.ipc_export_image() if rank == 0 else None]
+        handle = [(r.ipc_export_image(), r.ipc_export_sync()) if rank == 0 else None]
         dist.broadcast_object_list(handle, src=0)
         if rank != 0:
-            peer_ptr = r.ipc_open_image(handle[0])
+            peer_ptr = r.ipc_open_image(handle[0][0])
+            flags_ptr = r.ipc_open_image(handle[0][1])
+        else:
+            flags_ptr = r.sync_pointer()
     frame_token = torch.zeros(1, device="cuda")
+    frame_no = [0]
+    RELEASED = api.LucidRenderer.SYNC_RELEASED
 
     def view_of(step):
         return 0 if split else step % 64
 
     def render(step, flags):
+        if use_flags:
+            frame_no[0] += 1
+            if rank != 0:  # the shared image may be stored into once the previous frame was released
+                r.set_frame_gate(flags_ptr, RELEASED, frame_no[0] - 1)
         if peer_ptr is not None and args.composite == "stores":
             # the raster kernels store their pixels straight into rank 0's image
             r.render(rig.config_for(view_of(step)), inst, cols, rects, out_device_ptr=peer_ptr, out_pitch=width * 4,
@@ -403,9 +417,20 @@ def run_ours(args):
             if peer_ptr is not None:  # own image first, then the owned bins as whole 128-byte rows
                 r.composite_to(peer_ptr, width * 4)
 
-    def after_frame():
-        if split:  # the frame is complete when every rank's strip has landed in rank 0's image
+    def after_frame(consume=None):
+        """The frame is complete when every rank's strip has landed in rank 0's image."""
+        if use_flags:
+            if rank != 0:
+                r.signal(flags_ptr, rank, frame_no[0])
+            else:
+                r.wait_flags(flags_ptr, 1, world - 1, frame_no[0])
+                if consume is not None:
+                    consume()
+                r.signal(flags_ptr, RELEASED, frame_no[0])
+        elif split:
             dist.all_reduce(frame_token)
+            if consume is not None and rank == 0:
+                consume()
 
     # NVML is polled by a separate process, for the GPU of the rank that prints the line
     sampler = ClockSampler(local_rank)
@@ -431,9 +456,10 @@ def run_ours(args):
 
     # per-stage CUDA-event times: the same frames again, same L2 flush, this time with an event after every
     # stage (recorded on the stream the kernels are launched on; the library keeps its last 64 frames)
+    rig.barrier()
     for k in range(kept):
         rig.flush.fill_(k & 0xFF)
-        render(args.warmup + k, api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
+        render(args.warmup + k, api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_CULL_INSTANCES)
         after_frame()
     rig.barrier()
     stage = np.mean([r.stage_times(i).astype(np.float64) for i in range(kept)], axis=0)
@@ -446,11 +472,13 @@ def run_ours(args):
     def e2e_frame(k):
         if split:
             # every rank rasterises its bin ranges into rank 0's image, then rank 0 reads it back
-            render(k, api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES)
-            dist.all_reduce(frame_token)
-            if rank == 0:
+            render(k, api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES)
+
+            def read_back():
                 torch.cuda.current_stream().synchronize()
                 r.read_image_into(rig.host_imgs[k & 1].data_ptr())
+
+            after_frame(read_back)
         else:
             r.render(rig.config_for(view_of(k)), inst, cols, rects, out=rig.host_imgs[k & 1].data_ptr(),
                      flags=api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES)
@@ -472,6 +500,9 @@ def run_ours(args):
         if peer_ptr is not None:
             r.ipc_close_image(peer_ptr)
             peer_ptr = None
+        if rank != 0 and flags_ptr is not None:
+            r.ipc_close_image(flags_ptr)
+            flags_ptr = None
         rig.close()
         views = run_views(args, torch, dist, rank, world, local_rank, stream, 1)
 
@@ -524,7 +555,8 @@ def run_ours(args):
                        "input_triangles": tris_per_frame, "scale": args.scale,
                        "parallelism": ("bin-row split x%d (%s), P2P composite; rank 0 owns %s" %
                                        (world, split_kind + "; composite by " +
-                                        ("a bin-row copy kernel" if args.composite == "copy" else "direct raster stores"),
+                                        ("a bin-row copy kernel" if args.composite == "copy" else "direct raster stores") +
+                                        "; frame completion by " + ("P2P flags (no collective)" if use_flags else "NCCL all-reduce"),
                                         list(rows))) if split else "single GPU",
                        "l2": "256 MiB device memset between timed frames (untimed); the frame's own records "
                              "(~1 GB) exceed the 126 MB L2"},
@@ -562,6 +594,8 @@ def run_ours(args):
     if peer_ptr is not None:
         r.ipc_close_image(peer_ptr)
     if views is None:
+        if split and rank != 0 and flags_ptr is not None:
+            r.ipc_close_image(flags_ptr)
         rig.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -658,6 +692,8 @@ def main():
     ap.add_argument("--composite", default="stores", choices=["copy", "stores"],
                     help="--mode split: how the other ranks' strips reach rank 0's image")
     ap.add_argument("--trace-split", action="store_true", help="--mode split: per-rank step times (stderr)")
+    ap.add_argument("--completion", default="flags", choices=["flags", "allreduce"],
+                    help="--mode split: how rank 0 learns that every strip of a frame has landed")
     ap.add_argument("--balance-iters", type=int, default=3, help="--mode split: feedback steps of the range balancing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

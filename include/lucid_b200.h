@@ -33,9 +33,14 @@ enum {
 									 buffer should be pinned and must not be reused before lucid_wait() */
 	LUCID_RENDER_SKIP_INFO = 2,	  /* do not copy LucidInfo back this frame */
 	LUCID_RENDER_FRAG_COUNTS = 4, /* also write the per-pixel fragment-count image (parity tests) */
-	LUCID_RENDER_NO_STAGE_TIMES = 8 /* record only the frame's first and last timing event: without events
+	LUCID_RENDER_NO_STAGE_TIMES = 8, /* record only the frame's first and last timing event: without events
 									 between them the kernels of a frame overlap their launches
 									 (lucid_stage_times then reports the frame time only) */
+	LUCID_RENDER_CULL_INSTANCES = 16 /* bin-row split only: an instance whose bounding box projects outside the
+									 owned bin rows is dropped before its quads are loaded (the box is computed
+									 once per instance list and cached).  Conservative, so the visible quads, the
+									 per-bin lists and the pixels of the owned bins are unchanged;
+									 num_rejected_quads then only covers the instances that were processed */
 };
 
 /* LucidRenderer::exConstruct(device, compiler, opts, view_size), src/lucid_renderer.cpp:186-317.
@@ -130,6 +135,28 @@ int lucid_image_pointer(lucid_renderer *r, void **device_ptr, size_t *pitch_byte
 int lucid_composite_to(lucid_renderer *r, void *dst_rgba8_device, size_t pitch_bytes);
 /* 64-byte cudaIpcMemHandle_t of the renderer-owned image, to be sent to peer processes */
 int lucid_ipc_export_image(lucid_renderer *r, void *handle64);
+/* ---- frame hand-over of the bin-row split over NVLink, without a collective -------------------------------
+ * Every renderer owns a block of LUCID_SYNC_FLAGS 32-bit flags in device memory (zero at creation).  The
+ * gathering rank exports its block, the other ranks map it (lucid_ipc_open_image opens any handle exported by
+ * this library) and, after rendering their strip of frame k into the shared image, store k into "their" flag:
+ *     lucid_signal(r, peer_flags + rank, k);            // stream-ordered, system-scope release
+ * The gathering rank waits for all of them on the device and then releases the image:
+ *     lucid_wait_flags(r, flags + 1, world - 1, k);     // one warp, system-scope acquire, gives up after 5 s
+ *     ... consume the image (read-back, present) ...
+ *     lucid_signal(r, flags + LUCID_SYNC_RELEASED, k);
+ * and a rank may only store into the shared image again when frame k - 1 has been released:
+ *     lucid_set_frame_gate(r, peer_flags + LUCID_SYNC_RELEASED, k - 1);  // applies to the next lucid_render only:
+ *                                                        // its raster kernels start after the flag reached the value
+ * Setup and binning of the next frame overlap the wait.  A wait that times out makes the next lucid_wait()
+ * return LUCID_E_STATE. */
+#define LUCID_SYNC_FLAGS 64
+#define LUCID_SYNC_RELEASED 32
+int lucid_sync_pointer(lucid_renderer *r, uint32_t **device_flags);
+int lucid_ipc_export_sync(lucid_renderer *r, void *handle64);
+int lucid_signal(lucid_renderer *r, uint32_t *flag, uint32_t value);
+int lucid_wait_flags(lucid_renderer *r, const uint32_t *flags, int32_t count, uint32_t value);
+int lucid_set_frame_gate(lucid_renderer *r, const uint32_t *flag, uint32_t value);
+
 /* maps a peer's image into this process; pass the result as out_rgba8 with LUCID_MEM_DEVICE */
 int lucid_ipc_open_image(lucid_renderer *r, const void *handle64, void **device_ptr);
 int lucid_ipc_close_image(lucid_renderer *r, void *device_ptr);

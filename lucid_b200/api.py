@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LUCID_INFO_U32_SIZE = 1152
 COUNTS_PER_BIN = 10
 MEM_HOST, MEM_DEVICE, MEM_NONE = 0, 1, 2
-RENDER_ASYNC, RENDER_SKIP_INFO, RENDER_FRAG_COUNTS, RENDER_NO_STAGE_TIMES = 1, 2, 4, 8
+RENDER_ASYNC, RENDER_SKIP_INFO, RENDER_FRAG_COUNTS, RENDER_NO_STAGE_TIMES, RENDER_CULL_INSTANCES = 1, 2, 4, 8, 16
 
 OPT_TIMERS = 1 << 4
 OPT_ADDITIVE_BLENDING = 1 << 5
@@ -84,6 +84,7 @@ C_ABI_SYMBOLS = [
     "lucid_stage_times", "lucid_stage_times_at", "lucid_read_row_costs", "lucid_set_bin_range", "lucid_read_bin_costs", "lucid_composite_to", "lucid_read_quad_aabbs", "lucid_read_tri_records", "lucid_read_quad_attrs",
     "lucid_read_bin_lists", "lucid_read_frag_counts", "lucid_read_image", "lucid_image_pointer",
     "lucid_ipc_export_image", "lucid_ipc_open_image", "lucid_ipc_close_image",
+    "lucid_sync_pointer", "lucid_ipc_export_sync", "lucid_signal", "lucid_wait_flags", "lucid_set_frame_gate",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
     "lucid_host_camera_matrices", "lucid_host_build_instances", "lucid_host_packet_size",
 ]
@@ -135,6 +136,11 @@ def load_library(build_if_needed: bool = True):
     lib.lucid_ipc_export_image.argtypes = [vp, vp]
     lib.lucid_ipc_open_image.argtypes = [vp, vp, C.POINTER(vp)]
     lib.lucid_ipc_close_image.argtypes = [vp, vp]
+    lib.lucid_sync_pointer.argtypes = [vp, C.POINTER(vp)]
+    lib.lucid_ipc_export_sync.argtypes = [vp, vp]
+    lib.lucid_signal.argtypes = [vp, vp, C.c_uint32]
+    lib.lucid_wait_flags.argtypes = [vp, vp, C.c_int32, C.c_uint32]
+    lib.lucid_set_frame_gate.argtypes = [vp, vp, C.c_uint32]
     _host_prototypes(lib)
     _lib = lib
     return lib
@@ -434,6 +440,28 @@ class LucidRenderer:
 
     def ipc_close_image(self, ptr: int):
         self._check(self._lib.lucid_ipc_close_image(self._h, C.c_void_p(ptr)), "lucid_ipc_close_image")
+
+    # ---- frame hand-over of the bin-row split (include/lucid_b200.h) ---------------------------------
+    SYNC_RELEASED = 32
+
+    def sync_pointer(self) -> int:
+        ptr = C.c_void_p()
+        self._check(self._lib.lucid_sync_pointer(self._h, C.byref(ptr)), "lucid_sync_pointer")
+        return ptr.value
+
+    def ipc_export_sync(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.lucid_ipc_export_sync(self._h, buf), "lucid_ipc_export_sync")
+        return buf.raw
+
+    def signal(self, flags_ptr: int, index: int, value: int):
+        self._check(self._lib.lucid_signal(self._h, C.c_void_p(flags_ptr + 4 * index), value), "lucid_signal")
+
+    def wait_flags(self, flags_ptr: int, first: int, count: int, value: int):
+        self._check(self._lib.lucid_wait_flags(self._h, C.c_void_p(flags_ptr + 4 * first), count, value), "lucid_wait_flags")
+
+    def set_frame_gate(self, flags_ptr: int, index: int, value: int):
+        self._check(self._lib.lucid_set_frame_gate(self._h, C.c_void_p(flags_ptr + 4 * index), value), "lucid_set_frame_gate")
 
     # ---- the reference's host-side decoders --------------------------------------------------
     def getStats(self, info: np.ndarray | None = None) -> dict:

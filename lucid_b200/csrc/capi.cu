@@ -59,6 +59,15 @@ struct lucid_renderer {
 	// time (instances, then uv rects, then colours, tightly packed), so the frame's kernels never read
 	// host memory -- zero-copy reads queue behind the posted writes of an image read-back on PCIe
 	unsigned char *d_inst_ring[NUM_STAGING] = {nullptr, nullptr, nullptr};
+	// frame hand-over flags of the bin-row split (lucid_signal / lucid_wait_flags) and the one-shot gate of the
+	// next frame's raster kernels
+	u32 *d_sync = nullptr;
+	const u32 *gate_flag = nullptr;
+	u32 gate_value = 0;
+	// LUCID_RENDER_CULL_INSTANCES: boxes of the instance list they were computed for
+	float4 *d_inst_boxes = nullptr;
+	std::vector<LucidInstanceData> boxed_instances;
+	bool boxes_valid = false;
 	cudaStream_t upload_stream = nullptr;
 	cudaEvent_t upload_ready[NUM_STAGING] = {nullptr, nullptr, nullptr};
 
@@ -263,6 +272,8 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.block_counts, (size_t)p.bin_count * 32));
 	p.block_items_cap = (u32)p.bin_count * 32u;
 	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 5)); // one region per size class (ITEM_CLASSES)
+	p.shade_items_cap = (u32)p.bin_count * 128u; // a LOW bin: 16 blocks x 2 halves x 4 pixel rows
+	CUC(devAlloc(r, &p.shade_items, (size_t)p.shade_items_cap * 5));
 	CUC(devAlloc(r, &p.large_keys, rasterLargeKeysCount(r->num_sms)));
 	// sorted-entry stream: one entry per (triangle, half-block or block) pair of the frame
 	{
@@ -276,6 +287,9 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &r->images[1], (size_t)p.width * p.height));
 	r->image = r->images[0];
 	CUC(devAlloc(r, &r->frag_counts, (size_t)p.width * p.height));
+	CUC(devAlloc(r, &r->d_inst_boxes, (size_t)LUCID_MAX_INSTANCES * 2));
+	CUC(devAlloc(r, &r->d_sync, (size_t)LUCID_SYNC_FLAGS));
+	CUC(cudaMemsetAsync(r->d_sync, 0, LUCID_SYNC_FLAGS * 4, r->stream));
 	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++) {
 		CUC(devAlloc(r, &r->d_inst_ring[i], STAGING_BYTES));
 		CUC(cudaEventCreateWithFlags(&r->upload_ready[i], cudaEventDisableTiming));
@@ -398,6 +412,7 @@ int lucid_set_geometry(lucid_renderer *r, const float *positions, int32_t num_ve
 	CU(cudaStreamSynchronize(r->stream));
 	r->num_quads = num_quads, r->num_verts = num_verts;
 	p.num_verts = num_verts;
+	r->boxes_valid = false;
 	r->has_geometry = true;
 	return LUCID_OK;
 }
@@ -438,11 +453,14 @@ int lucid_wait(lucid_renderer *r) {
 	for(bool &b : r->upload_pending)
 		b = false;
 	CU(cudaGetLastError());
-	bool overflow = false;
+	bool overflow = false, timed_out = false;
 	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++) {
-		overflow = overflow || r->h_status[i] != 0;
+		overflow = overflow || (r->h_status[i] & 3u) != 0;
+		timed_out = timed_out || (r->h_status[i] & 4u) != 0;
 		r->h_status[i] = 0;
 	}
+	if(timed_out)
+		return fail(r, LUCID_E_STATE, "a device-side wait for a peer's frame flag gave up after 5 s (lucid_wait_flags / frame gate)");
 	if(overflow)
 		return fail(r, LUCID_E_LIMIT,
 					"a frame exceeded the renderer's list storage (per-bin lists of 2 * max_visible_quads entries, or the "
@@ -533,6 +551,18 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 		p.image_pitch = p.width;
 	}
 	p.frag_counts = (flags & LUCID_RENDER_FRAG_COUNTS) ? r->frag_counts : nullptr;
+	// instance boxes for the split's early instance cull: recomputed only when the instance list changes
+	p.inst_boxes = nullptr;
+	const bool restricted = p.bin_begin > 0 || p.bin_end < p.bin_count;
+	if((flags & LUCID_RENDER_CULL_INSTANCES) && restricted && num_instances > 0) {
+		if(!r->boxes_valid || r->boxed_instances.size() != n ||
+		   memcmp(r->boxed_instances.data(), instances, n * sizeof(LucidInstanceData)) != 0) {
+			r->boxed_instances.assign(instances, instances + n);
+			launchInstanceBoxes(p, r->d_inst_boxes, st); // after the upload wait above; before the frame's first kernel
+			r->boxes_valid = true;
+		}
+		p.inst_boxes = r->d_inst_boxes;
+	}
 
 	double t1 = host_profile ? now() : 0.0;
 	const int ring = (int)(r->frame_counter % lucid_renderer::TIMING_RING);
@@ -551,7 +581,12 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	double t2 = host_profile ? now() : 0.0;
 	launchBinning(p, st, stage_events ? &ev[2] : nullptr); // ev[2] count, ev[3] scan, ev[4] dispatch
 	double t3 = host_profile ? now() : 0.0;
-	// ev[5] block lists, ev[6] sort + shade (+ frame bookkeeping), ev[7] end of frame
+	// a shared image may only be stored into once the gathering device has released it (lucid_set_frame_gate)
+	if(r->gate_flag) {
+		launchWaitFlags(r->gate_flag, 1, r->gate_value, p.host_status, 5000000000ull, st);
+		r->gate_flag = nullptr;
+	}
+	// ev[5] block lists, ev[6] block sort (+ frame bookkeeping), ev[7] shading = end of frame
 	launchRaster(p, cfg, st, stage_events ? &ev[5] : nullptr, r->num_sms);
 	if(!stage_events)
 		CU(cudaEventRecord(ev[7], st));
@@ -779,6 +814,50 @@ int lucid_ipc_export_image(lucid_renderer *r, void *handle64) {
 	CU(cudaIpcGetMemHandle(&h, r->images[0])); // the image LUCID_MEM_NONE frames render into
 	static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t");
 	memcpy(handle64, &h, 64);
+	return LUCID_OK;
+}
+
+int lucid_sync_pointer(lucid_renderer *r, uint32_t **device_flags) {
+	if(!r || !device_flags)
+		return LUCID_E_INVALID;
+	*device_flags = r->d_sync;
+	return LUCID_OK;
+}
+
+int lucid_ipc_export_sync(lucid_renderer *r, void *handle64) {
+	if(!r || !handle64)
+		return LUCID_E_INVALID;
+	CU(cudaSetDevice(r->ci.device));
+	cudaIpcMemHandle_t h;
+	CU(cudaIpcGetMemHandle(&h, r->d_sync));
+	memcpy(handle64, &h, 64);
+	return LUCID_OK;
+}
+
+int lucid_signal(lucid_renderer *r, uint32_t *flag, uint32_t value) {
+	if(!r || !flag)
+		return LUCID_E_INVALID;
+	CU(cudaSetDevice(r->ci.device));
+	launchSignal(flag, value, r->stream);
+	CU(cudaGetLastError());
+	r->pending = true;
+	return LUCID_OK;
+}
+
+int lucid_wait_flags(lucid_renderer *r, const uint32_t *flags, int32_t count, uint32_t value) {
+	if(!r || !flags || count < 0 || count > LUCID_SYNC_FLAGS)
+		return LUCID_E_INVALID;
+	CU(cudaSetDevice(r->ci.device));
+	launchWaitFlags(flags, count, value, r->h_status, 5000000000ull, r->stream);
+	CU(cudaGetLastError());
+	r->pending = true;
+	return LUCID_OK;
+}
+
+int lucid_set_frame_gate(lucid_renderer *r, const uint32_t *flag, uint32_t value) {
+	if(!r)
+		return LUCID_E_INVALID;
+	r->gate_flag = flag, r->gate_value = value;
 	return LUCID_OK;
 }
 

@@ -35,6 +35,71 @@ __device__ __forceinline__ u32 vertexClipMask(float4 v) {
 
 __device__ __forceinline__ float &comp(float4 &v, int i) { return (&v.x)[i]; }
 
+// Bounding boxes of the instances' vertices (bin-row split, LUCID_RENDER_CULL_INSTANCES): one CTA per instance,
+// once per instance list.  k_quad_cull projects the box and drops the instance when it cannot reach an owned row.
+__global__ void __launch_bounds__(256) k_instance_boxes(const Params p, float4 *boxes) {
+	__shared__ float s_red[8][6];
+	const LucidInstanceData inst = p.instances[blockIdx.x];
+	const uint4 *ib = reinterpret_cast<const uint4 *>(reinterpret_cast<const u32 *>(p.quad_indices) + inst.index_offset);
+	const float inf = __int_as_float(0x7f800000);
+	float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+	for(int q = threadIdx.x; q < inst.num_quads; q += blockDim.x) {
+		const uint4 vi = __ldg(ib + q);
+		const u32 idx[4] = {vi.x, vi.y, vi.z, vi.w};
+#pragma unroll
+		for(int k = 0; k < 4; k++) {
+			const u32 v = idx[k] + (u32)inst.vertex_offset;
+			if(v >= (u32)p.num_verts)
+				continue;
+			const float4 pos = __ldg(p.positions4 + v);
+			lo[0] = fminf(lo[0], pos.x), lo[1] = fminf(lo[1], pos.y), lo[2] = fminf(lo[2], pos.z);
+			hi[0] = fmaxf(hi[0], pos.x), hi[1] = fmaxf(hi[1], pos.y), hi[2] = fmaxf(hi[2], pos.z);
+		}
+	}
+#pragma unroll
+	for(int k = 0; k < 3; k++)
+#pragma unroll
+		for(int o = 16; o > 0; o >>= 1) {
+			lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+			hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+		}
+	if((threadIdx.x & 31) == 0)
+		for(int k = 0; k < 3; k++)
+			s_red[threadIdx.x >> 5][k] = lo[k], s_red[threadIdx.x >> 5][3 + k] = hi[k];
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		for(int w = 1; w < 8; w++)
+			for(int k = 0; k < 3; k++)
+				lo[k] = fminf(lo[k], s_red[w][k]), hi[k] = fmaxf(hi[k], s_red[w][3 + k]);
+		boxes[blockIdx.x * 2] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+		boxes[blockIdx.x * 2 + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+	}
+}
+void launchInstanceBoxes(const Params &p, float4 *boxes, cudaStream_t stream) {
+	if(p.num_instances > 0)
+		k_instance_boxes<<<p.num_instances, 256, 0, stream>>>(p, boxes);
+}
+
+// true when the box certainly projects outside the owned bin rows: all eight corners are in front of the camera
+// (w above a small positive bound) and their screen y range, widened by two pixels, misses [row_begin, row_end)
+__device__ __forceinline__ bool boxOutsideOwnedRows(const Params &p, const LucidConfig &cfg, float4 lo, float4 hi) {
+	if(!(lo.x <= hi.x))
+		return false; // empty or invalid box: let the quads decide
+	const LucidVec4 *m = cfg.view_proj_matrix;
+	float ymin = __int_as_float(0x7f800000), ymax = -ymin;
+#pragma unroll
+	for(int c = 0; c < 8; c++) {
+		const float x = (c & 1) ? hi.x : lo.x, y = (c & 2) ? hi.y : lo.y, z = (c & 4) ? hi.z : lo.z;
+		const float cy = m[0].y * x + m[1].y * y + m[2].y * z + m[3].y;
+		const float cw = m[0].w * x + m[1].w * y + m[2].w * z + m[3].w;
+		if(!(cw > 1e-3f))
+			return false;
+		const float sy = (cy / cw + 1.0f) * (float(p.height) * 0.5f);
+		ymin = fminf(ymin, sy), ymax = fmaxf(ymax, sy);
+	}
+	return ymax + 2.0f < float(p.row_begin * BIN_SIZE) || ymin - 2.0f >= float(p.row_end * BIN_SIZE);
+}
+
 // quad_setup.glsl:77-128 -- screen AABB of a triangle that crosses the near plane (Blinn 1996)
 __device__ float4 clippedAABB(float4 v0, float4 v1, float4 v2, float w0, float w1, float w2,
 							  u32 clipmask) {
@@ -307,6 +372,9 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 	const LucidInstanceData inst = p.instances[inst_id];
 	if(tid == 0)
 		atomicAdd(&p.info->num_input_quads, inst.num_quads);
+	// bin-row split: an instance that cannot reach the owned rows keeps its place in the look-back chain but
+	// loads nothing (every quad counts as "visible elsewhere")
+	const bool skip = p.inst_boxes != nullptr && boxOutsideOwnedRows(p, cfg, __ldg(p.inst_boxes + inst_id * 2), __ldg(p.inst_boxes + inst_id * 2 + 1));
 
 	uint4 vi[SETUP_PARTS];
 	QuadResult res[SETUP_PARTS];
@@ -316,7 +384,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 	for(int k = 0; k < SETUP_PARTS; k++) {
 		const int local_quad = k * SETUP_THREADS + tid;
 		vi[k] = make_uint4(0, 0, 0, 0);
-		if(local_quad < inst.num_quads) {
+		if(local_quad < inst.num_quads && !skip) {
 			vi[k] = __ldg(ib + local_quad);
 			vi[k].x += inst.vertex_offset, vi[k].y += inst.vertex_offset;
 			vi[k].z += inst.vertex_offset, vi[k].w += inst.vertex_offset;
@@ -328,6 +396,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 		const int local_quad = k * SETUP_THREADS + tid;
 		res[k].status = -3, res[k].size_type = 0, res[k].enc_aabb = 0, res[k].y_aabb0 = res[k].y_aabb1 = 0;
 		if(local_quad < inst.num_quads)
+			res[k].status = -2;
+		if(local_quad < inst.num_quads && !skip)
 			res[k] = processInputQuad(p, cfg, vi[k]);
 		const bool vis = res[k].status == -1;
 		const u32 bs = __ballot_sync(0xffffffffu, vis && res[k].size_type == 0);

@@ -378,6 +378,84 @@ def test_image_pointer_names_the_device_resident_image(small):
         other.close()
 
 
+def test_instance_culling_of_the_split_changes_nothing_but_the_rejection_counters(small):
+    """LUCID_RENDER_CULL_INSTANCES: instances whose bounding box projects outside the owned bin rows are skipped
+    before their quads are loaded.  Visible quads, per-bin counts, lists and pixels of the owned bins are the ones
+    of the plain split; only num_rejected_quads shrinks to the processed instances."""
+    for name in ("arch", "meshlets"):
+        sc = small[name]
+        cfg, inst, cols, rects = api.prepare_frame(sc)
+        nby = (sc["height"] + 31) // 32
+        r = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20)
+        try:
+            r.set_scene(sc)
+            skipped_any = False
+            for rows in multigpu.split_bin_rows(nby, 4):
+                r.set_bin_rows(*rows)
+                a = np.zeros((sc["height"], sc["width"]), np.uint32)
+                b = np.zeros_like(a)
+                r.render(cfg, inst, cols, rects, out=a)
+                ia = r.read_info().copy()
+                bqa, bta = r.read_bin_lists(int(api.split_info(ia, r.bin_count)[1][0].sum()),
+                                            int(api.split_info(ia, r.bin_count)[1][3].sum()))
+                for _ in range(2):  # second frame: boxes come from the cache
+                    r.render(cfg, inst, cols, rects, out=b, flags=api.RENDER_CULL_INSTANCES)
+                ib = r.read_info()
+                _, ca = api.split_info(ia, r.bin_count)
+                _, cb = api.split_info(ib, r.bin_count)
+                y0, y1 = rows[0] * 32, min(rows[1] * 32, sc["height"])
+                assert np.array_equal(a[y0:y1], b[y0:y1])
+                assert np.array_equal(ia[0:10], ib[0:10]) and np.array_equal(ia[60:63], ib[60:63])
+                assert np.array_equal(ca[:6], cb[:6])
+                bqb, btb = r.read_bin_lists(bqa.size, bta.size)
+                assert np.array_equal(pu.canonical_lists(bqa, ca[0]), pu.canonical_lists(bqb, ca[0]))
+                assert np.array_equal(pu.canonical_lists(bta, ca[3]), pu.canonical_lists(btb, ca[3]))
+                assert (ib[32:36] <= ia[32:36]).all()
+                skipped_any = skipped_any or (ib[32:36] < ia[32:36]).any()
+            assert skipped_any  # some instance was dropped by its box
+        finally:
+            r.close()
+
+
+def test_frame_hand_over_flags(small):
+    """lucid_signal / lucid_wait_flags / lucid_set_frame_gate: the device-side hand-over of the bin-row split, here
+    between two renderers on one GPU (each on its own stream).  The gathering renderer sees the complete composite
+    after its flag wait, a gated frame does not store before the image was released, and a wait nobody answers
+    gives up with LUCID_E_STATE instead of hanging the device."""
+    sc = small["soup_close"]
+    full_r, full_img = pu.run_cuda(sc)
+    full_r.close()
+    cfg, inst, cols, rects = api.prepare_frame(sc)
+    nby = (sc["height"] + 31) // 32
+    rows = multigpu.split_bin_rows(nby, 2)
+    gather = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20, bin_rows=rows[0])
+    peer = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20, bin_rows=rows[1])
+    try:
+        gather.set_scene(sc), peer.set_scene(sc)
+        ptr, pitch = gather.image_pointer()
+        flags = gather.sync_pointer()
+        for frame in (1, 2, 3):
+            # the peer may store into the shared image once frame - 1 was released; it signals its flag when done
+            peer.set_frame_gate(flags, api.LucidRenderer.SYNC_RELEASED, frame - 1)
+            peer.render(cfg, inst, cols, rects, out_device_ptr=ptr, out_pitch=pitch, flags=api.RENDER_ASYNC)
+            peer.signal(flags, 1, frame)
+            gather.render(cfg, inst, cols, rects, flags=api.RENDER_ASYNC)
+            gather.wait_flags(flags, 1, 1, frame)
+            img = gather.read_image()  # after the wait on the gathering stream: both strips are there
+            assert np.array_equal(img, full_img)
+            gather.signal(flags, api.LucidRenderer.SYNC_RELEASED, frame)
+        peer.wait()
+        # nobody ever signals flag 5: the wait gives up after five seconds and the next lucid_wait reports it
+        gather.wait_flags(flags, 5, 1, 1)
+        with pytest.raises(api.LucidError) as e:
+            gather.wait()
+        assert "(-4)" in str(e.value)
+        gather.wait()  # reported once
+    finally:
+        gather.close()
+        peer.close()
+
+
 def test_frames_without_stage_events_and_row_costs(small):
     """LUCID_RENDER_NO_STAGE_TIMES changes timing bookkeeping only; lucid_read_row_costs reports raster
     cost exactly for the bin rows that hold work."""
