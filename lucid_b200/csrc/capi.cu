@@ -272,8 +272,6 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.block_counts, (size_t)p.bin_count * 32));
 	p.block_items_cap = (u32)p.bin_count * 32u;
 	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 5)); // one region per size class (ITEM_CLASSES)
-	p.shade_items_cap = (u32)p.bin_count * 128u; // a LOW bin: 16 blocks x 2 halves x 4 pixel rows
-	CUC(devAlloc(r, &p.shade_items, (size_t)p.shade_items_cap * 5));
 	CUC(devAlloc(r, &p.large_keys, rasterLargeKeysCount(r->num_sms)));
 	// sorted-entry stream: one entry per (triangle, half-block or block) pair of the frame
 	{

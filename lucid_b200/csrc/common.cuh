@@ -96,8 +96,6 @@ struct Params {
 	int *block_counts;	  // 32 per bin: entries of each list
 	uint4 *block_items;	  // work items of the block stages (item, entries, stream offset, -): one region of block_items_cap per size class
 	u32 block_items_cap;
-	uint4 *shade_items;	  // work items of k_block_shade, queued by k_block_sort (lists with many samples are cut into sub-items)
-	u32 shade_items_cap;
 	u32 *large_keys;	  // per k_block_sort warp: sort keys of lists too long for shared memory
 	// the sorted-entry stream k_block_sort writes and k_block_shade reads: per work item a slice of both planes
 	uint4 *sorted_rec;	  // (triangle, pixel mask of the upper / only half, pixel mask of the lower half, -)
@@ -295,7 +293,7 @@ void launchSignal(u32 *flag, u32 value, cudaStream_t stream);
 void launchWaitFlags(const u32 *flags, int count, u32 value, u32 *status, unsigned long long timeout_ns, cudaStream_t stream);
 void launchCompositeBins(const Params &p, u32 *dst, int dst_pitch, cudaStream_t stream, int num_sms);
 size_t rasterLargeKeysCount(int num_sms);
-constexpr int WORK_COUNTERS = 16; // raster_common.cuh WC_*
+constexpr int WORK_COUNTERS = 12; // raster_common.cuh WC_*
 
 // 32 half-block lists of up to 4096 8-byte records (raster_high.glsl:27); a LOW bin uses the first
 // 16 x 256 16-byte records

@@ -56,33 +56,22 @@ __device__ __forceinline__ int itemClass(int entries) {
 	return k;
 }
 // work_counters: [0] bins taken (k_raster_bins) [1] items taken by k_block_sort [2] items taken by k_block_shade
-// [3..7] sort items per size class [8] sorted-stream entries handed out [9..13] shade items per size class
-constexpr int WC_BINS = 0, WC_SORT = 1, WC_SHADE = 2, WC_CLASS = 3, WC_STREAM = 8, WC_SHADE_CLASS = 9, WC_COUNT = 16;
-static_assert(WC_COUNT == WORK_COUNTERS, "common.cuh WORK_COUNTERS");
-
-// Shade items: k_block_sort queues every sorted list for k_block_shade, and cuts a list with many samples into
-// sub-items by pixel rows (and a LOW block into its halves): each sub-item walks the same sorted entries but only
-// owns some of the half-block's pixels.  Per-pixel results do not depend on the cut; what it buys is a short
-// critical path -- one warp used to own the frame's deepest half-block from its first sample to its last, which
-// bounds the kernel from below once a device only holds an eighth of the frame (bin-row split).
-//   item word: bin << 6 | high << 5 | block, | half mask << 26 (LOW: which halves), | row mask << 28 (pixel rows)
-#ifndef SHADE_SPLIT_SAMPLES
-#define SHADE_SPLIT_SAMPLES 1536
-#endif
+// [3..7] items per size class [8] sorted-stream entries handed out
+constexpr int WC_BINS = 0, WC_SORT = 1, WC_SHADE = 2, WC_CLASS = 3, WC_STREAM = 8, WC_COUNT = 12;
 
 // A work item: item = bin << 6 | high << 5 | block, its list length and the start of its slice of the sorted stream
 struct WorkItem {
 	u32 item, count, offset, pad;
 };
 // queue order: class by class, heaviest first; i-th item overall
-__device__ __forceinline__ uint4 fetchWorkItem(const uint4 *items, u32 cap, u32 i, const u32 (&class_end)[ITEM_CLASSES]) {
+__device__ __forceinline__ uint4 fetchWorkItem(const Params &p, u32 i, const u32 (&class_end)[ITEM_CLASSES]) {
 	int k = 0;
 	u32 first = 0;
 #pragma unroll
 	for(int c = 0; c < ITEM_CLASSES - 1; c++)
 		if(i >= class_end[c])
 			k = c + 1, first = class_end[c];
-	return __ldcg(items + (size_t)k * cap + (i - first));
+	return __ldcg(p.block_items + (size_t)k * p.block_items_cap + (i - first));
 }
 
 // ------------------------------------------------------------------------------------------------

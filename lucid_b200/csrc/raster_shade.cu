@@ -125,7 +125,7 @@ __device__ __forceinline__ int ringIndex(const RingStream &rs, int e) {
 // ------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void writePixel(const Params &p, const LucidConfig &cfg, Reducer &red, int hb_x, int hb_y,
-										   u32 px_frags, bool additive, bool vis_errors, bool owned) {
+										   u32 px_frags, bool additive, bool vis_errors) {
 	const int lane = laneId();
 	// finishReduceSamples (shading.glsl:297-314)
 	if(red.c2 != 0)
@@ -138,7 +138,7 @@ __device__ __forceinline__ void writePixel(const Params &p, const LucidConfig &c
 	float fg = saturatef(__fmaf_rn(red.trans, cfg.background_color.y, red.g));
 	float fb = saturatef(__fmaf_rn(red.trans, cfg.background_color.z, red.b));
 	int gx = hb_x + (lane & 7), gy = hb_y + (lane >> 3);
-	if(owned && gx < p.width && gy < p.height) {
+	if(gx < p.width && gy < p.height) {
 		// rgba8 unorm store: round to nearest
 		u32 out = f2u(fr * 255.0f + 0.5f) | (f2u(fg * 255.0f + 0.5f) << 8) | (f2u(fb * 255.0f + 0.5f) << 16) |
 				  0xff000000u;
@@ -172,7 +172,6 @@ struct ItemCtx {
 	int count;
 	int hb_x, hb_y; // top-left pixel of the half-block
 	bool lower;		// LOW items: the block's lower half (second pixel mask)
-	u32 px_mask;	// the pixels of the half-block this (sub-)item owns
 };
 
 // one 8x4 half-block from its sorted entries
@@ -184,11 +183,8 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 	const bool vis_errors = (p.opts & LUCID_OPT_VISUALIZE_ERRORS) != 0;
 	const float fpx = float(it.hb_x + (lane & 7)), fpy = float(it.hb_y + (lane >> 3));
 	const int count = it.count;
-	const bool owned = (it.px_mask >> lane) & 1u;
 	Reducer red;
 	reducerInit(red);
-	if(!owned)
-		red.trans = 0.0f; // pixels of other sub-items never hold the half-block back
 	u32 px_frags = 0;
 	bool dead = false;
 
@@ -221,7 +217,7 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 		} else {
 			rec = ahead_rec, aux = ahead_aux;
 		}
-		u32 bits = e < count ? (it.lower ? rec.z : rec.y) & it.px_mask : 0u;
+		u32 bits = e < count ? (it.lower ? rec.z : rec.y) : 0u;
 		const int nf = __popc(bits);
 		const int incl = warpInclusiveScan(nf);
 		const bool in_chunk = e < count && incl <= CHUNK_SAMPLES;
@@ -322,7 +318,7 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 		seq_base = rs.seq_base + (u32)rs.issued;
 		__syncwarp();
 	}
-	writePixel(p, cfg, red, it.hb_x, it.hb_y, px_frags, additive, vis_errors, owned);
+	writePixel(p, cfg, red, it.hb_x, it.hb_y, px_frags, additive, vis_errors);
 }
 
 // shadeSample straight from global memory (segment-accurate build only)
@@ -376,7 +372,7 @@ __device__ __forceinline__ void shadeHalfBlockSegments(const Params &p, const Lu
 			if(i < count)
 				rec = __ldcg(it.src_rec + i);
 			const u32 tri_idx = rec.x;
-			u32 bits = (it.lower ? rec.z : rec.y) & it.px_mask;
+			u32 bits = it.lower ? rec.z : rec.y;
 			const int nf = __popc(bits);
 			const int incl = warpInclusiveScan(nf);
 			u32 my_off = off + (u32)(incl - nf);
@@ -437,7 +433,7 @@ __device__ __forceinline__ void shadeHalfBlockSegments(const Params &p, const Lu
 			stop = true;
 		seg_start += SEGMENT_SIZE;
 	}
-	writePixel(p, cfg, red, it.hb_x, it.hb_y, px_frags, false, false, (it.px_mask >> lane) & 1u);
+	writePixel(p, cfg, red, it.hb_x, it.hb_y, px_frags, false, false);
 }
 
 // TMA: entry stream through the bulk-copy ring; SEGMENTS: the ALPHA_THRESHOLD build
@@ -471,7 +467,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SHADE_MIN_CTAS)
 		u32 acc = 0;
 #pragma unroll
 		for(int k = 0; k < ITEM_CLASSES; k++)
-			class_end[k] = acc += p.work_counters[WC_SHADE_CLASS + k];
+			class_end[k] = acc += p.work_counters[WC_CLASS + k];
 	}
 	const u32 n_items = class_end[ITEM_CLASSES - 1];
 	u32 seq_base = 0;
@@ -481,7 +477,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SHADE_MIN_CTAS)
 		if(lane == 0) {
 			const u32 i = atomicAdd(&p.work_counters[WC_SHADE], 1u);
 			if(i < n_items)
-				e = fetchWorkItem(p.shade_items, p.shade_items_cap, i, class_end);
+				e = fetchWorkItem(p, i, class_end);
 		}
 		return e;
 	};
@@ -494,20 +490,15 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SHADE_MIN_CTAS)
 			break;
 		next_entry = fetch();
 		const long long t_item = clock64();
-		const int bin_id = (int)((item & 0xfffffu) >> 6), sub = (int)(item & 31u);
+		const int bin_id = (int)(item >> 6), sub = (int)(item & 31u);
 		const bool high = (item & 32u) != 0;
-		const u32 half_mask = (item >> 26) & 3u, row_mask = item >> 28;
 		const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
 		ItemCtx it;
-		it.px_mask = ((row_mask & 1u) ? 0xffu : 0u) | ((row_mask & 2u) ? 0xff00u : 0u) | ((row_mask & 4u) ? 0xff0000u : 0u) |
-					 ((row_mask & 8u) ? 0xff000000u : 0u);
 		it.src_rec = p.sorted_rec + offset, it.src_aux = p.sorted_aux + offset, it.count = count;
 		it.hb_x = bin_x * BIN_SIZE + (sub & 3) * 8;
 		const int y0 = bin_y * BIN_SIZE + (sub >> 2) * (high ? 4 : 8);
 		const int halves = high ? 1 : 2;
 		for(int half = 0; half < halves; half++) {
-			if(!((half_mask >> half) & 1u))
-				continue;
 			it.lower = half != 0, it.hb_y = y0 + half * 4;
 			if(SEGMENTS)
 				shadeHalfBlockSegments(p, cfg, tab, lt, wm, it);

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 		index = __shfl_sync(0xffffffffu, index, 0);
 		if(index >= n_items)
 			break;
-		const uint4 entry = fetchWorkItem(p.block_items, p.block_items_cap, index, class_end);
+		const uint4 entry = fetchWorkItem(p, index, class_end);
 		const long long t_item = clock64();
 		const u32 item = entry.x;
 		const int count = (int)entry.y;
@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 			}
 			return r4;
 		};
-		u32 item_frags0 = 0, item_frags1 = 0; // samples of the upper / only half and of the lower half
 		uint4 rec_next[KEY_UNROLL];
 #pragma unroll
 		for(int u = 0; u < KEY_UNROLL; u++)
@@ -196,7 +195,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 					float cpx = float(cx) * scale + (float(cx8) + float(pos_x));
 					float cpy = float(cy) * scale + (float(ry * 4) + float(pos_y));
 					depth = blockDepth(dq[u], cpx, cpy, float(0x7fffe)) << 14;
-					item_frags0 += (u32)nf;
+					frag_acc += (u32)nf;
 				} else {
 					int nf0, cx0, cy0, nf1, cx1, cy1;
 					unpackLowRecord(rec[u], false, tri_idx, mins, maxs);
@@ -208,7 +207,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 					float scale = __fdiv_rn(0.5f, float(nf0 + nf1));
 					float cpx = cx * scale + float(pos_x + cx8), cpy = cy * scale + float(pos_y + ry * 8);
 					depth = blockDepth(dq[u], cpx, cpy, float(0x3ffffe)) << 10;
-					item_frags0 += (u32)nf0, item_frags1 += (u32)nf1;
+					frag_acc += (u32)(nf0 + nf1);
 				}
 				keys[i] = (u32)i | depth;
 			}
@@ -233,7 +232,6 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 		// the entries in sorted order: (triangle, pixel masks) and (depth plane, constant colour)
 		const u32 pos_mask = (1u << slot_bits) - 1u;
 		uint4 *out_rec = p.sorted_rec + entry.z, *out_aux = p.sorted_aux + entry.z;
-		bool has_varying = false;
 		for(int i = lane; i < count; i += 32) {
 			const u32 pos = (large ? __ldcg(keys + i) : keys[i]) & pos_mask;
 			u32 tri_idx, mins, maxs, mask0, mask1 = 0;
@@ -252,43 +250,10 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 			const uint4 dq = __ldg(src), misc = __ldg(src + 1);
 			__stcg(out_rec + i, make_uint4(tri_idx, mask0, mask1, 0u));
 			__stcg(out_aux + i, make_uint4(dq.x, dq.y, dq.z, misc.w != 0 ? misc.z : AUX_VARYING));
-			has_varying = has_varying || misc.w == 0;
 		}
-		has_varying = __any_sync(0xffffffffu, has_varying);
 		__syncwarp();
-		// queue the list for k_block_shade; a list with many samples becomes several sub-items
-#pragma unroll
-		for(int o = 16; o > 0; o >>= 1) {
-			item_frags0 += __shfl_xor_sync(0xffffffffu, item_frags0, o);
-			item_frags1 += __shfl_xor_sync(0xffffffffu, item_frags1, o);
-		}
-		if(lane == 0) {
-			frag_acc += item_frags0 + item_frags1;
-			auto rowCuts = [](u32 samples) { return samples > 2u * SHADE_SPLIT_SAMPLES ? 4 : samples > SHADE_SPLIT_SAMPLES ? 2 : 1; };
-			// the ALPHA_THRESHOLD build decides its early out on 256-sample segments of the whole half-block
-			// (raster.glsl:394-395): its lists are never cut
-			const bool segments = (p.opts & (LUCID_OPT_ALPHA_THRESHOLD | LUCID_OPT_ADDITIVE_BLENDING | LUCID_OPT_VISUALIZE_ERRORS)) ==
-								  LUCID_OPT_ALPHA_THRESHOLD;
-			// A cut only shortens the sample-parallel shading (the per-pixel loop is sequential per pixel either way)
-			// and costs lanes in the pixel loop, so lists of constant-colour triangles are never cut, and nothing is
-			// cut while the frame has plenty of items per resident warp (a whole frame on one device).
-			const bool cut = !segments && has_varying && n_items < 16u * gridDim.x * BLOCK_WARPS;
-			const bool cut_halves = cut && !high && item_frags0 + item_frags1 > SHADE_SPLIT_SAMPLES;
-			const int cuts0 = !cut ? 1 : (high || cut_halves) ? rowCuts(item_frags0) : 1, cuts1 = cut_halves ? rowCuts(item_frags1) : 0;
-			const int cls = itemClass(count);
-			const u32 base = atomicAdd(&p.work_counters[WC_SHADE_CLASS + cls], (u32)(cuts0 + cuts1));
-			uint4 *dst = p.shade_items + (size_t)cls * p.shade_items_cap + base;
-			int n = 0;
-			for(int half = 0; half < 2; half++) {
-				const int cuts = half == 0 ? cuts0 : cuts1;
-				const u32 half_mask = high ? 1u : cut_halves ? (1u << half) : 3u;
-				for(int c = 0; c < cuts; c++) {
-					const u32 row_mask = cuts == 4 ? (1u << c) : cuts == 2 ? (3u << (2 * c)) : 0xfu;
-					dst[n++] = make_uint4(item | (half_mask << 26) | (row_mask << 28), (u32)count, entry.z, 0u);
-				}
-			}
+		if(lane == 0)
 			atomicAdd(reinterpret_cast<unsigned long long *>(p.bin_cost) + bin_id, (unsigned long long)(clock64() - t_item));
-		}
 	}
 #pragma unroll
 	for(int o = 16; o > 0; o >>= 1) {
