@@ -366,12 +366,13 @@ def run_ours(args):
             ranges = multigpu.split_bins(r.bin_count, world, cost)
             r.set_bin_range(*ranges[rank])
             # feedback, as an application would apply it from frame to frame: the cost of a rank's bins is
-            # rescaled by the time that rank actually needed for them (everything but the replicated
-            # setup), and the ranges are cut again
+            # rescaled by the time that rank's whole frame actually took, and the ranges are cut again (seven
+            # rounds bring the slowest rank within 2 % of the mean on the 10M-triangle scene, tools/split_probe.py)
             for _ in range(args.balance_iters):
                 for k in range(3):
-                    r.render(rig.config_for(0), inst, cols, rects, flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO)
-                mine = float(np.median([r.stage_times(i)[1:7].sum() for i in range(2)]))
+                    r.render(rig.config_for(0), inst, cols, rects,
+                             flags=api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_CULL_INSTANCES)
+                mine = float(np.median([r.stage_times(i)[7] for i in range(2)]))  # the rank's whole frame
                 times = torch.zeros(world, device="cuda", dtype=torch.float64)
                 times[rank] = mine
                 dist.all_reduce(times)
@@ -694,7 +695,7 @@ def main():
     ap.add_argument("--trace-split", action="store_true", help="--mode split: per-rank step times (stderr)")
     ap.add_argument("--completion", default="flags", choices=["flags", "allreduce"],
                     help="--mode split: how rank 0 learns that every strip of a frame has landed")
-    ap.add_argument("--balance-iters", type=int, default=3, help="--mode split: feedback steps of the range balancing")
+    ap.add_argument("--balance-iters", type=int, default=7, help="--mode split: feedback steps of the range balancing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

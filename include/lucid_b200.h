@@ -135,6 +135,11 @@ int lucid_image_pointer(lucid_renderer *r, void **device_ptr, size_t *pitch_byte
 int lucid_composite_to(lucid_renderer *r, void *dst_rgba8_device, size_t pitch_bytes);
 /* 64-byte cudaIpcMemHandle_t of the renderer-owned image, to be sent to peer processes */
 int lucid_ipc_export_image(lucid_renderer *r, void *handle64);
+/* Test hook: n samples (u, v, lod triples, host memory) of the texture in `slot`, fetched by the texture unit
+ * exactly as the shading kernel fetches them (tex2DLod); out_rgba receives 4 floats per sample.  Pins the CPU
+ * checker's restatement of the unit's filter arithmetic against the hardware (tests/test_gpu_parity.py). */
+int lucid_debug_sample_texture(lucid_renderer *r, int32_t slot, const float *uvl, int32_t n, float *out_rgba);
+
 /* ---- frame hand-over of the bin-row split over NVLink, without a collective -------------------------------
  * Every renderer owns a block of LUCID_SYNC_FLAGS 32-bit flags in device memory (zero at creation).  The
  * gathering rank exports its block, the other ranks map it (lucid_ipc_open_image opens any handle exported by

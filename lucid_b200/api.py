@@ -84,7 +84,7 @@ C_ABI_SYMBOLS = [
     "lucid_stage_times", "lucid_stage_times_at", "lucid_read_row_costs", "lucid_set_bin_range", "lucid_read_bin_costs", "lucid_composite_to", "lucid_read_quad_aabbs", "lucid_read_tri_records", "lucid_read_quad_attrs",
     "lucid_read_bin_lists", "lucid_read_frag_counts", "lucid_read_image", "lucid_image_pointer",
     "lucid_ipc_export_image", "lucid_ipc_open_image", "lucid_ipc_close_image",
-    "lucid_sync_pointer", "lucid_ipc_export_sync", "lucid_signal", "lucid_wait_flags", "lucid_set_frame_gate",
+    "lucid_debug_sample_texture", "lucid_sync_pointer", "lucid_ipc_export_sync", "lucid_signal", "lucid_wait_flags", "lucid_set_frame_gate",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
     "lucid_host_camera_matrices", "lucid_host_build_instances", "lucid_host_packet_size",
 ]
@@ -136,6 +136,7 @@ def load_library(build_if_needed: bool = True):
     lib.lucid_ipc_export_image.argtypes = [vp, vp]
     lib.lucid_ipc_open_image.argtypes = [vp, vp, C.POINTER(vp)]
     lib.lucid_ipc_close_image.argtypes = [vp, vp]
+    lib.lucid_debug_sample_texture.argtypes = [vp, C.c_int32, vp, C.c_int32, vp]
     lib.lucid_sync_pointer.argtypes = [vp, C.POINTER(vp)]
     lib.lucid_ipc_export_sync.argtypes = [vp, vp]
     lib.lucid_signal.argtypes = [vp, vp, C.c_uint32]
@@ -326,6 +327,14 @@ class LucidRenderer:
     def set_texture(self, slot, data, width, height, levels):
         data = np.ascontiguousarray(data, np.uint8)
         self._check(self._lib.lucid_set_texture(self._h, slot, _ptr(data), width, height, levels), "lucid_set_texture")
+
+    def debug_sample_texture(self, slot, uvl) -> np.ndarray:
+        """(u, v, lod) triples -> RGBA floats, fetched by the texture unit as the shading kernel does."""
+        uvl = np.ascontiguousarray(uvl, np.float32).reshape(-1, 3)
+        out = np.zeros((uvl.shape[0], 4), np.float32)
+        self._check(self._lib.lucid_debug_sample_texture(self._h, slot, _ptr(uvl), uvl.shape[0], _ptr(out)),
+                    "lucid_debug_sample_texture")
+        return out
 
     def set_bin_rows(self, begin, end):
         self._check(self._lib.lucid_set_bin_rows(self._h, begin, end), "lucid_set_bin_rows")

@@ -38,7 +38,8 @@ struct lucid_renderer {
 	// owned device allocations
 	std::vector<void *> owned;
 	void *geom_owned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [5] padded positions
-	void *tex_owned[2] = {nullptr, nullptr};
+	cudaMipmappedArray_t tex_array[2] = {nullptr, nullptr};
+	cudaTextureObject_t tex_object[2] = {0, 0};
 	// two renderer-owned images: while frame n is copied to the host on copy_stream, frame n+1
 	// renders into the other one (the reference double-buffers its per-frame data the same way,
 	// lucid_renderer.h:78-81)
@@ -125,9 +126,12 @@ void freeAll(lucid_renderer *r) {
 	for(void *v : r->geom_owned)
 		if(v)
 			cudaFree(v);
-	for(void *v : r->tex_owned)
-		if(v)
-			cudaFree(v);
+	for(int i = 0; i < 2; i++) {
+		if(r->tex_object[i])
+			cudaDestroyTextureObject(r->tex_object[i]);
+		if(r->tex_array[i])
+			cudaFreeMipmappedArray(r->tex_array[i]);
+	}
 	if(r->h_instances)
 		cudaFreeHost(r->h_instances);
 	if(r->h_info)
@@ -423,19 +427,67 @@ int lucid_set_texture(lucid_renderer *r, int32_t slot, const uint8_t *data, int3
 		return fail(r, LUCID_E_INVALID, "lucid_set_texture: bad argument");
 	CU(cudaSetDevice(r->ci.device));
 	CU(cudaStreamSynchronize(r->stream));
-	if(r->tex_owned[slot]) {
-		cudaFree(r->tex_owned[slot]);
-		r->tex_owned[slot] = nullptr;
+	// the chain goes into a mipmapped array sampled by the texture unit (raster_common.cuh sampleTexture)
+	if(r->tex_object[slot]) {
+		cudaDestroyTextureObject(r->tex_object[slot]);
+		r->tex_object[slot] = 0;
 	}
-	size_t texels = 0;
+	if(r->tex_array[slot]) {
+		cudaFreeMipmappedArray(r->tex_array[slot]);
+		r->tex_array[slot] = nullptr;
+	}
+	r->p.tex_object[slot] = 0;
+	if((width & (width - 1)) != 0 || (height & (height - 1)) != 0)
+		return fail(r, LUCID_E_INVALID, "lucid_set_texture: width and height must be powers of two (the filter arithmetic of the "
+										"texture unit is only pinned for those)");
+	cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+	CU(cudaMallocMipmappedArray(&r->tex_array[slot], &desc, make_cudaExtent((size_t)width, (size_t)height, 0), (unsigned)levels));
+	size_t off = 0;
 	for(int l = 0; l < levels; l++) {
-		r->p.tex_level_offset[slot][l] = (u32)texels;
-		texels += (size_t)std::max(1, width >> l) * std::max(1, height >> l);
+		const int lw = std::max(1, width >> l), lh = std::max(1, height >> l);
+		cudaArray_t level;
+		CU(cudaGetMipmappedArrayLevel(&level, r->tex_array[slot], (unsigned)l));
+		CU(cudaMemcpy2DToArray(level, 0, 0, data + off, (size_t)lw * 4, (size_t)lw * 4, (size_t)lh, cudaMemcpyHostToDevice));
+		off += (size_t)lw * lh * 4;
 	}
-	CU(cudaMalloc(&r->tex_owned[slot], texels * 4));
-	CU(cudaMemcpy(r->tex_owned[slot], data, texels * 4, cudaMemcpyHostToDevice));
-	r->p.tex_data[slot] = (const uchar4 *)r->tex_owned[slot];
+	cudaResourceDesc res{};
+	res.resType = cudaResourceTypeMipmappedArray;
+	res.res.mipmap.mipmap = r->tex_array[slot];
+	cudaTextureDesc td{};
+	td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+	td.filterMode = cudaFilterModeLinear, td.mipmapFilterMode = cudaFilterModeLinear;
+	td.readMode = cudaReadModeNormalizedFloat, td.normalizedCoords = 1;
+	td.maxAnisotropy = 1, td.minMipmapLevelClamp = 0.0f, td.maxMipmapLevelClamp = float(levels - 1);
+	CU(cudaCreateTextureObject(&r->tex_object[slot], &res, &td, nullptr));
+	r->p.tex_object[slot] = (unsigned long long)r->tex_object[slot];
 	r->p.tex_width[slot] = width, r->p.tex_height[slot] = height, r->p.tex_levels[slot] = levels;
+	return LUCID_OK;
+}
+
+// test hook: n samples (u, v, lod) of the texture in `slot` straight through the texture unit
+__global__ void k_debug_sample_texture(cudaTextureObject_t tex, const float *uvl, float4 *out, int n) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n)
+		out[i] = tex2DLod<float4>(tex, uvl[i * 3], uvl[i * 3 + 1], uvl[i * 3 + 2]);
+}
+int lucid_debug_sample_texture(lucid_renderer *r, int32_t slot, const float *uvl, int32_t n, float *out_rgba) {
+	if(!r || slot < 0 || slot > 1 || !uvl || !out_rgba || n < 0)
+		return LUCID_E_INVALID;
+	if(!r->tex_object[slot])
+		return fail(r, LUCID_E_STATE, "lucid_debug_sample_texture: no texture in the slot");
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	float *d_in = nullptr;
+	float4 *d_out = nullptr;
+	CU(cudaMalloc(&d_in, (size_t)n * 12 + 16));
+	CU(cudaMalloc(&d_out, (size_t)n * 16 + 16));
+	CU(cudaMemcpy(d_in, uvl, (size_t)n * 12, cudaMemcpyHostToDevice));
+	if(n > 0)
+		k_debug_sample_texture<<<(n + 255) / 256, 256, 0, r->stream>>>(r->tex_object[slot], d_in, d_out, n);
+	CU(cudaStreamSynchronize(r->stream));
+	CU(cudaMemcpy(out_rgba, d_out, (size_t)n * 16, cudaMemcpyDeviceToHost));
+	cudaFree(d_in), cudaFree(d_out);
 	return LUCID_OK;
 }
 

@@ -101,10 +101,10 @@ struct Params {
 	uint4 *sorted_rec;	  // (triangle, pixel mask of the upper / only half, pixel mask of the lower half, -)
 	uint4 *sorted_aux;	  // (depth plane xyz, constant colour or AUX_VARYING)
 	u32 stream_capacity;  // entries
-	// textures: level offsets into one RGBA8 array per slot
-	const uchar4 *tex_data[2];
+	// textures: the two atlases as CUDA mipmapped arrays behind texture objects (RGBA8 unorm, normalised coordinates,
+	// wrap, linear + mip-linear); 0 = no texture in the slot
 	int tex_width[2], tex_height[2], tex_levels[2];
-	u32 tex_level_offset[2][16];
+	unsigned long long tex_object[2];
 };
 
 // ---- floating-point contract ------------------------------------------------------------------

@@ -115,73 +115,26 @@ __device__ __forceinline__ u32 blockDepth(uint4 d, float cx, float cy, float ran
 
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
 
-// Filter definition (the reference leaves this to the Vulkan sampler; same arithmetic as
-// oracle/lucid_oracle.cpp sampleTexture): repeat addressing, bilinear within a level, linear between
-// the two nearest levels, isotropic lod.  Coordinates are wrapped once in floating point, so the
-// 2x2 footprint leaves the level by at most one texel (compares, no integer remainder); lod takes
-// log2 piecewise linearly from the exponent / mantissa bits; texels are filtered on the 0..255
-// scale (byte -> float by a permute into the mantissa of 2^23) and scaled by 1/255 once.
-__device__ __forceinline__ float4 texelBytes(u32 t) {
-	const float magic = 8388608.0f; // 0x4b000000: float(2^23 + b) - 2^23 == float(b), exactly
-	return make_float4(__uint_as_float(__byte_perm(t, 0x4b000000u, 0x7650)) - magic,
-					   __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7651)) - magic,
-					   __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7652)) - magic,
-					   __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7653)) - magic);
-}
-// uf, vf in [0, 1]; result on the 0..255 scale
-__device__ __forceinline__ float4 bilinear(const u32 *level_base, int w, int h, float uf, float vf) {
-	float fx = __fmaf_rn(uf, float(w), -0.5f), fy = __fmaf_rn(vf, float(h), -0.5f);
-	float x0f = floorf(fx), y0f = floorf(fy);
-	float ax = fx - x0f, ay = fy - y0f;
-	int x0 = f2i(x0f), y0 = f2i(y0f); // in [-1, size - 1]
-	int x1 = x0 + 1, y1 = y0 + 1;
-	if(x0 < 0)
-		x0 += w;
-	if(x1 >= w)
-		x1 -= w;
-	if(y0 < 0)
-		y0 += h;
-	if(y1 >= h)
-		y1 -= h;
-	const u32 *row0 = level_base + y0 * w, *row1 = level_base + y1 * w;
-	u32 t00 = __ldg(row0 + x0), t10 = __ldg(row0 + x1), t01 = __ldg(row1 + x0), t11 = __ldg(row1 + x1);
-	float4 c00 = texelBytes(t00), c10 = texelBytes(t10), c01 = texelBytes(t01), c11 = texelBytes(t11);
-	float4 o;
-#define LERP2(c)                                                                                   \
-	{                                                                                              \
-		float top = __fmaf_rn(c10.c - c00.c, ax, c00.c);                                           \
-		float bot = __fmaf_rn(c11.c - c01.c, ax, c01.c);                                           \
-		o.c = __fmaf_rn(bot - top, ay, top);                                                       \
-	}
-	LERP2(x) LERP2(y) LERP2(z) LERP2(w)
-#undef LERP2
-	return o;
-}
+// Filter definition.  The reference leaves filtering to the Vulkan sampler (textureGrad on a trilinear sampler,
+// lucid_base.h:30-31, shading.glsl:153-158).  Here the texture unit does it: the atlases are CUDA mipmapped arrays
+// behind texture objects (RGBA8 unorm, normalised coordinates, wrap, linear + mip-linear, no anisotropy) and a
+// sample is one tex2DLod.  Its arithmetic -- 8-bit weights split level -> x -> y, 16-bit unorm texels -- is
+// restated in integers in the CPU checker (oracle/lucid_oracle.cpp textureUnitSample; fitted and verified bit for
+// bit with tools/hwtex/), so the images still compare exactly.  lod: log2 of the larger screen-space derivative in
+// texels, taken piecewise linearly from the exponent / mantissa bits of its square; one rounding per operation
+// (it addresses the texture, like a coordinate).
 __device__ __forceinline__ float4 sampleTexture(const Params &p, int slot, float u, float v, float dudx, float dvdx,
 												float dudy, float dvdy) {
-	const u32 *data = reinterpret_cast<const u32 *>(p.tex_data[slot]);
-	if(data == nullptr)
+	if(p.tex_object[slot] == 0)
 		return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-	const int wi = p.tex_width[slot], hi = p.tex_height[slot];
-	float w0 = float(wi), h0 = float(hi);
-	float ax = dudx * w0, ay = dvdx * h0, bx = dudy * w0, by = dvdy * h0;
-	float rho2 = fmaxf(__fmaf_rn(ax, ax, ay * ay), __fmaf_rn(bx, bx, by * by));
-	int levels = p.tex_levels[slot];
+	const float w0 = float(p.tex_width[slot]), h0 = float(p.tex_height[slot]);
+	const float ax = dudx * w0, ay = dvdx * h0, bx = dudy * w0, by = dvdy * h0;
+	const float rho2 = fmaxf(ax * ax + ay * ay, bx * bx + by * by);
 	float lod = 0.0f;
 	if(rho2 > 1.0f)
 		lod = float((int)(__float_as_uint(rho2) - 0x3f800000u)) * (0.5f / 8388608.0f);
-	lod = clampf(lod, 0.0f, float(levels - 1));
-	float l0f = floorf(lod);
-	int l0 = f2i(l0f), l1 = min(l0 + 1, levels - 1);
-	float a = lod - l0f;
-	const float uf = u - floorf(u), vf = v - floorf(v);
-	const float s = 1.0f / 255.0f;
-	float4 c0 = bilinear(data + p.tex_level_offset[slot][l0], max(1, wi >> l0), max(1, hi >> l0), uf, vf);
-	if(a == 0.0f || l1 == l0)
-		return make_float4(c0.x * s, c0.y * s, c0.z * s, c0.w * s);
-	float4 c1 = bilinear(data + p.tex_level_offset[slot][l1], max(1, wi >> l1), max(1, hi >> l1), uf, vf);
-	return make_float4(__fmaf_rn(c1.x - c0.x, a, c0.x) * s, __fmaf_rn(c1.y - c0.y, a, c0.y) * s,
-					   __fmaf_rn(c1.z - c0.z, a, c0.z) * s, __fmaf_rn(c1.w - c0.w, a, c0.w) * s);
+	lod = clampf(lod, 0.0f, float(p.tex_levels[slot] - 1));
+	return tex2DLod<float4>((cudaTextureObject_t)p.tex_object[slot], u, v, lod);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -58,6 +58,7 @@ def load():
     lib.oracle_shade_probe.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_float)]
     lib.oracle_shade_probe.restype = C.c_uint32
     lib.oracle_set_reference_colour.argtypes = [vp, C.c_int]
+    lib.oracle_texture_samples.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     for name in ("oracle_final_shade_fast", "oracle_final_shade_reference"):
         getattr(lib, name).argtypes = [C.c_float, C.c_float]
         getattr(lib, name).restype = C.c_float
@@ -94,6 +95,13 @@ class Oracle:
 
     def set_bin_rows(self, begin, end):
         self.lib.oracle_set_bin_rows(self.h, begin, end)
+
+    def texture_samples(self, slot, uvl) -> np.ndarray:
+        """(u, v, lod) triples through the restated texture-unit filter (lod clamped to the chain)."""
+        uvl = np.ascontiguousarray(uvl, np.float32).reshape(-1, 3)
+        out = np.zeros((uvl.shape[0], 4), np.float32)
+        self.lib.oracle_texture_samples(self.h, slot, _ptr(uvl), uvl.shape[0], _ptr(out))
+        return out
 
     def set_reference_colour(self, on: bool):
         """True: colour arithmetic in the reference's operation order (what the GLSL pins compare); False

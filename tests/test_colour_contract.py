@@ -72,10 +72,14 @@ def test_images_of_both_forms_agree_within_one_level(name):
 
 
 def test_render_options_in_both_forms():
+    """ALPHA_THRESHOLD keeps the 1 / 255 bound.  ADDITIVE_BLENDING sums the samples of a pixel without the
+    transmittance weights, so the per-sample differences of at most one level (a texture coordinate that differs in
+    its last bit can move an 8-bit filter weight by one step) add up over the layers: 2 / 255 at a handful of pixels
+    of the textured scene."""
     from lucid_b200 import api
     sc = pu.small_scenes()["arch"]
-    for opts in (api.OPT_ADDITIVE_BLENDING, api.OPT_ALPHA_THRESHOLD):
+    for opts, bound in ((api.OPT_ADDITIVE_BLENDING, 2), (api.OPT_ALPHA_THRESHOLD, 1)):
         a = pu.run_oracle(sc, opts=opts, threads=4)
         b = pu.run_oracle(sc, opts=opts, threads=4, reference_colour=True)
         d = np.abs(a.read_image().view(np.uint8).astype(np.int32) - b.read_image().view(np.uint8).astype(np.int32))
-        assert d.max() <= 1
+        assert d.max() <= bound and (d > 1).sum() < 100

@@ -41,4 +41,27 @@ for q, (lo, hi) in enumerate(ranges):
     print(f"rank {q} bins [{lo},{hi}) cost share {cost[lo:hi].sum() / cost.sum():.3f}", dict(zip(names, np.round(ms, 3).tolist())),
           "fragments", st["fragments"], "hbt", st["half_block_tris"])
 print("sum    ", dict(zip(names, np.round(tot, 3).tolist())))
+
+# the feedback of bench.py --mode split, played on one GPU: every rank's bins are rescaled to the time the rank needed
+iters = 0
+for a in sys.argv:
+    if a.startswith("--feedback="):
+        iters = int(a.split("=")[1])
+for mode in ("after-setup", "frame"):
+    c = cost.copy()
+    rg = multigpu.split_bins(r.bin_count, world, c)
+    for it in range(iters):
+        times = []
+        for lo, hi in rg:
+            r.set_bin_range(lo, hi)
+            ms = measure(cull)
+            times.append(float(ms[1:7].sum()) if mode == "after-setup" else float(ms[:7].sum()))
+        frames = []
+        for lo, hi in rg:
+            r.set_bin_range(lo, hi)
+            frames.append(float(measure(cull)[7]))
+        print(f"[{mode}] iteration {it}: frame max {max(frames):.3f} mean {np.mean(frames):.3f} min {min(frames):.3f}  bounds {[lo for lo, _ in rg]}")
+        for q, (lo, hi) in enumerate(rg):
+            c[lo:hi] *= times[q] / max(float(c[lo:hi].sum()), 1e-9)
+        rg = multigpu.split_bins(r.bin_count, world, c)
 r.close()
