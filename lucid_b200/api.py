@@ -512,6 +512,13 @@ def decode_stats(info: np.ndarray, bin_count: int, width: int, height: int) -> d
         fragments=int(stats[0]), half_block_tris=int(stats[1]), invalid_pixels=int(stats[2]),
         avg_fragments_per_pixel=float(stats[0]) / (width * height),
         dropped_quads=int(h[_OFF["temp"]]), list_overflow=int(h[_OFF["temp"] + 1]),
+        # LUCID_OPT_TIMERS: clock ticks >> 4 per phase, in the reference's slot meaning (lucid_renderer.cpp:754-762)
+        setup_timers=dict(zip(("init & finish", "process input quads", "store tri data", "store quad data"),
+                              (int(v) for v in head[_OFF["setup_timers"]:_OFF["setup_timers"] + 4]))),
+        bin_dispatcher_timers=dict(zip(("count small quads", "count large tris", "dispatch small quads", "dispatch large tris"),
+                                       (int(v) for v in head[_OFF["bin_dispatcher_timers"]:_OFF["bin_dispatcher_timers"] + 4]))),
+        raster_timers=dict(zip(("generate rows", "generate blocks", "unpack samples", "shade and reduce", "finish reduce"),
+                               (int(v) for v in head[_OFF["raster_timers"]:_OFF["raster_timers"] + 5]))),
     )
 
 

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
 	const int bcx = p.bin_count_x;
 	const int stride = gridDim.x * blockDim.x;
 	const int first = blockIdx.x * blockDim.x + threadIdx.x;
+	PhaseTimer timer = timerStart(p); // bin_dispatcher_timers: 0 count small quads, 1 count large tris, 2 / 3 dispatch
 
 	// small quads: every bin of the (<= 4 bins) AABB, conservative.  A CTA counts a contiguous chunk
 	// of the visible quads into a private shared-memory histogram and adds its non-zero bins to the
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
 		if(c != 0)
 			atomicAdd(quad_counts + b, c);
 	}
+	timerMark(timer, p.info->bin_dispatcher_timers, 0);
 	// large triangles: one thread per triangle, +1 at the first bin of each row span and -1 just
 	// after the last (bin_counter.glsl:123-133)
 	for(int i = first; i < n_large * 2; i += stride) {
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_count(const Params p) {
 			}
 		}
 	}
+	timerMark(timer, p.info->bin_dispatcher_timers, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 	const int bcx = p.bin_count_x;
 	const int stride = gridDim.x * blockDim.x;
 	const int lane = laneId();
+	PhaseTimer timer = timerStart(p);
 
 	// small quads: the CTA recounts its chunk into the shared-memory histogram, claims one range per
 	// non-zero bin with a single global atomic (all claims of a thread are in flight together), and
@@ -353,6 +357,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 		}
 	}
 
+	timerMark(timer, p.info->bin_dispatcher_timers, 2);
 	uint2 *ring = s_ring[threadIdx.x >> 5];
 	int q_head = 0, q_tail = 0; // warp-uniform
 	// all lanes: queue the span [bmin, bmax] of bin row `row_cell / bcx` in segments, draining when 32 wait
@@ -449,6 +454,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_dispatch(const Params p) {
 	}
 	if(q_tail > q_head)
 		drainSegments(p, tri_cursor, ring, q_head + lane, lane < q_tail - q_head);
+	timerMark(timer, p.info->bin_dispatcher_timers, 3);
 }
 
 void launchBinning(const Params &p, cudaStream_t stream, cudaEvent_t *ev) {

@@ -238,6 +238,29 @@ __device__ __forceinline__ u32 laneMaskLt() {
 	return m;
 }
 
+// ---- LUCID_OPT_TIMERS: the reference's `_timers` shader variants (shared/timers.glsl:9-39) -------------------------
+// A warp's leader adds the clock ticks (>> 4, like UPDATE_TIMER) it spent since the previous mark to one of the eight
+// slots of LucidInfo.setup_timers / bin_dispatcher_timers / raster_timers; getStats() turns them into the same
+// percentage rows (src/lucid_renderer.cpp:582-596,754-762).  Off: one predicate test per mark.
+struct PhaseTimer {
+	long long t0;
+	bool on;
+};
+__device__ __forceinline__ PhaseTimer timerStart(const Params &p) {
+	PhaseTimer t;
+	t.on = (p.opts & LUCID_OPT_TIMERS) != 0;
+	t.t0 = t.on ? clock64() : 0;
+	return t;
+}
+__device__ __forceinline__ void timerMark(PhaseTimer &t, u32 *slots, int idx) {
+	if(t.on) {
+		const long long now = clock64();
+		if((threadIdx.x & 31) == 0)
+			atomicAdd(slots + idx, (u32)((unsigned long long)(now - t.t0) >> 4));
+		t.t0 = now;
+	}
+}
+
 // ---- programmatic dependent launch -----------------------------------------------------------
 // The frame is a chain of short kernels (tens of microseconds at 1080p), so the gap between two
 // launches matters.  Every kernel is launched with programmatic stream serialisation and starts

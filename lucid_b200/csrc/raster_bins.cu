@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 		if(idx >= n_high + n_low)
 			break;
 		const long long t_bin = clock64();
+		PhaseTimer timer = timerStart(p); // raster_timers 0: generate rows (the span walk and the per-block lists)
 		bool high = idx < n_high;
 		const int bin_id = high ? cntc(p, LUCID_CNT_HIGH_BINS)[idx] : cntc(p, LUCID_CNT_LOW_BINS)[idx - n_high];
 		const BinInfo b = loadBin(p, bin_id);
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 		__syncthreads();
 		if(sh.status != 0)
 			continue; // finishBins (k_block_sort) paints the bin
+		timerMark(timer, p.info->raster_timers, 0);
 		if(tid == 0)
 			atomicAdd(reinterpret_cast<unsigned long long *>(p.bin_cost) + bin_id,
 					  (unsigned long long)(clock64() - t_bin) * RASTER_WARPS);

@@ -187,6 +187,7 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 	reducerInit(red);
 	u32 px_frags = 0;
 	bool dead = false;
+	PhaseTimer timer = timerStart(p); // raster_timers: 2 unpack samples, 3 shade and reduce, 4 finish reduce
 
 	RingStream rs;
 	uint4 ahead_rec = make_uint4(0, 0, 0, 0), ahead_aux = make_uint4(0, 0, 0, 0);
@@ -232,6 +233,7 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 
 		u32 tm = transpose32(bits);
 		px_frags += __popc(tm);
+		timerMark(timer, p.info->raster_timers, 2);
 		if(dead)
 			continue;
 		// a pixel whose transmittance has reached zero takes exactly +0 from every later sample:
@@ -306,6 +308,7 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 			}
 		}
 		__syncwarp();
+		timerMark(timer, p.info->raster_timers, 3);
 		if(!vis_errors && __all_sync(0xffffffffu, red.trans == 0.0f)) {
 			dead = true;
 			if(!p.frag_counts)
@@ -319,6 +322,7 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 		__syncwarp();
 	}
 	writePixel(p, cfg, red, it.hb_x, it.hb_y, px_frags, additive, vis_errors);
+	timerMark(timer, p.info->raster_timers, 4);
 }
 
 // shadeSample straight from global memory (segment-accurate build only)

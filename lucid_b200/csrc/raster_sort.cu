@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 			break;
 		const uint4 entry = fetchWorkItem(p, index, class_end);
 		const long long t_item = clock64();
+		PhaseTimer timer = timerStart(p); // raster_timers 1: generate blocks (keys, sort, sorted entries)
 		const u32 item = entry.x;
 		const int count = (int)entry.y;
 		const int bin_id = (int)(item >> 6), sub = (int)(item & 31u);
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 			__stcg(out_aux + i, make_uint4(dq.x, dq.y, dq.z, misc.w != 0 ? misc.z : AUX_VARYING));
 		}
 		__syncwarp();
+		timerMark(timer, p.info->raster_timers, 1);
 		if(lane == 0)
 			atomicAdd(reinterpret_cast<unsigned long long *>(p.bin_cost) + bin_id, (unsigned long long)(clock64() - t_item));
 	}

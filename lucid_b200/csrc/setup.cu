@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	pdlEntry();
+	PhaseTimer timer = timerStart(p); // setup_timers: 0 init & finish, 1 process input quads, 2 store tri data, 3 store quad data
 	// CTAs are ordered by ticket, not by blockIdx, so every predecessor in the look-back chain is
 	// guaranteed to be running or finished.
 	if(tid == 0)
@@ -376,6 +377,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 	// loads nothing (every quad counts as "visible elsewhere")
 	const bool skip = p.inst_boxes != nullptr && boxOutsideOwnedRows(p, cfg, __ldg(p.inst_boxes + inst_id * 2), __ldg(p.inst_boxes + inst_id * 2 + 1));
 
+	timerMark(timer, p.info->setup_timers, 0);
 	uint4 vi[SETUP_PARTS];
 	QuadResult res[SETUP_PARTS];
 	// one 128-bit load per quad: the index buffer is 4 x u32 per quad (quad_setup.glsl:405-409)
@@ -413,6 +415,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 			s_counts[k * (SETUP_THREADS / 32) + warp][0] = __popc(bs), s_counts[k * (SETUP_THREADS / 32) + warp][1] = __popc(bl);
 		before_small[k] = __popc(bs & laneMaskLt()), before_large[k] = __popc(bl & laneMaskLt());
 	}
+	timerMark(timer, p.info->setup_timers, 1);
 	__syncthreads();
 
 	// warp 0: exclusive scan of the 32 (part, warp) counts in input order, then the decoupled
@@ -506,6 +509,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 	}
 	if(tid < LUCID_REJECTION_TYPE_COUNT && s_rejected[tid] != 0)
 		atomicAdd(&p.info->num_rejected_quads[tid], s_rejected[tid]);
+	timerMark(timer, p.info->setup_timers, 0);
 }
 
 // k_tri_setup: one thread per triangle of a visible quad (storeTri / storeQuad,
@@ -520,6 +524,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_TRI_MIN_CTAS) k_tri_setup
 	const F3 dir0 = xyz(cfg.frustum.ws_dir0), dirx = xyz(cfg.frustum.ws_dirx);
 	const F3 diry = xyz(cfg.frustum.ws_diry), origin = xyz(cfg.frustum.ws_origin0);
 	const F3 ray_dir0 = dir0 + (dirx + diry) * 0.5f;
+	PhaseTimer timer = timerStart(p);
 	for(int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tris; t += gridDim.x * blockDim.x) {
 		const int q = t >> 1, second = t & 1;
 		const int slot = q < n_small ? q : (p.max_visible_quads - 1) - (q - n_small);
@@ -536,6 +541,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_TRI_MIN_CTAS) k_tri_setup
 			storeTri(p, cfg, (u32)slot * 2 + second, flags | (inst_id << 16), __ldg(p.inst_colors + inst_id), t0, t1,
 					 t2, second ? qi.y : qi.x, ray_dir0);
 		}
+		timerMark(timer, p.info->setup_timers, 2);
 		if(second)
 			continue;
 		// quad records (quad_setup.glsl:256-272, 342-354)
@@ -554,6 +560,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_TRI_MIN_CTAS) k_tri_setup
 				make_uint4(__float_as_uint(t2.x - t0.x), __float_as_uint(t2.y - t0.y), __float_as_uint(t3.x - t0.x),
 						   __float_as_uint(t3.y - t0.y));
 		}
+		timerMark(timer, p.info->setup_timers, 3);
 	}
 }
 

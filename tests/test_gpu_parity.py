@@ -62,6 +62,29 @@ def test_render_options(name, opts, small):
         r.close()
 
 
+def test_timers_option(small):
+    """LUCID_OPT_TIMERS (the reference's `_timers` shader variants, shared/timers.glsl, lucid_renderer.cpp:754-762):
+    the phases' clock ticks land in LucidInfo.setup_timers / bin_dispatcher_timers / raster_timers in the reference's
+    slot meaning; without the option they stay zero; results are the same either way."""
+    sc = small["arch"]
+    plain_r, plain_img = pu.run_cuda(sc)
+    r, img = pu.run_cuda(sc, opts=api.OPT_TIMERS)
+    try:
+        assert np.array_equal(img, plain_img)
+        st, st0 = r.getStats(), plain_r.getStats()
+        for group in ("setup_timers", "bin_dispatcher_timers", "raster_timers"):
+            assert all(v > 0 for v in st[group].values()), (group, st[group])
+            assert all(v == 0 for v in st0[group].values())
+        info, info0 = r.read_info(), plain_r.read_info()
+        assert np.array_equal(info[0:36], info0[0:36]) and np.array_equal(info[60:63], info0[60:63])
+        # shading is the bulk of the raster work on this scene
+        rt = st["raster_timers"]
+        assert rt["shade and reduce"] > rt["finish reduce"]
+    finally:
+        r.close()
+        plain_r.close()
+
+
 def test_backface_culling(small):
     sc = small["soup"]
     cfg, inst, cols, rects = api.prepare_frame(sc)
