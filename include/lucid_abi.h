@@ -69,7 +69,14 @@ enum {
 	LUCID_OPT_TIMERS = 1 << 4,
 	LUCID_OPT_ADDITIVE_BLENDING = 1 << 5,
 	LUCID_OPT_VISUALIZE_ERRORS = 1 << 6,
-	LUCID_OPT_ALPHA_THRESHOLD = 1 << 7
+	LUCID_OPT_ALPHA_THRESHOLD = 1 << 7,
+	/* Extensions (not LucidRenderOpt bits of the reference).
+	 * OPAQUE_PREPASS -- the TODO of shared/shading.glsl:31-32 as an option: at every pixel the nearest sample of an
+	 * INST_IS_OPAQUE instance (the caller's promise that every sample of the instance has alpha 1, the reference's
+	 * DrawCallOpt::is_opaque, src/scene.cpp:496) hides all samples behind it: they are dropped before sorting and
+	 * shading.  The image does not change; per-pixel fragment counts and stats[0] count the surviving samples only, so
+	 * it is outside the parity mode.  Ignored together with ADDITIVE_BLENDING or ALPHA_THRESHOLD. */
+	LUCID_OPT_OPAQUE_PREPASS = 1 << 8
 };
 
 typedef struct LucidVec4 {

@@ -24,6 +24,7 @@ OPT_TIMERS = 1 << 4
 OPT_ADDITIVE_BLENDING = 1 << 5
 OPT_VISUALIZE_ERRORS = 1 << 6
 OPT_ALPHA_THRESHOLD = 1 << 7
+OPT_OPAQUE_PREPASS = 1 << 8  # extension, include/lucid_abi.h
 
 
 class Vec4(C.Structure):
@@ -87,6 +88,7 @@ C_ABI_SYMBOLS = [
     "lucid_debug_sample_texture", "lucid_sync_pointer", "lucid_ipc_export_sync", "lucid_signal", "lucid_wait_flags", "lucid_set_frame_gate",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
     "lucid_host_camera_matrices", "lucid_host_build_instances", "lucid_host_packet_size",
+    "lucid_quadgen", "lucid_quadgen_last_error",
 ]
 
 

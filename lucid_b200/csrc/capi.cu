@@ -285,6 +285,8 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	}
 	CUC(devAlloc(r, &p.sorted_rec, (size_t)p.stream_capacity));
 	CUC(devAlloc(r, &p.sorted_aux, (size_t)p.stream_capacity));
+	if(info->opts & LUCID_OPT_OPAQUE_PREPASS)
+		CUC(devAlloc(r, &p.opaque_depth, (size_t)p.bin_count * BIN_SIZE * BIN_SIZE));
 	CUC(devAlloc(r, &r->images[0], (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->images[1], (size_t)p.width * p.height));
 	r->image = r->images[0];

@@ -101,6 +101,10 @@ struct Params {
 	uint4 *sorted_rec;	  // (triangle, pixel mask of the upper / only half, pixel mask of the lower half, -)
 	uint4 *sorted_aux;	  // (depth plane xyz, constant colour or AUX_VARYING)
 	u32 stream_capacity;  // entries
+	// LUCID_OPT_OPAQUE_PREPASS: per pixel the depth of the nearest INST_IS_OPAQUE sample (-inf: none), tiled like the
+	// work items -- [bin][half-block 0..31 = (4-row group, 8-pixel column)][pixel 0..31]; k_block_sort writes,
+	// k_block_shade reads; null without the option
+	float *opaque_depth;
 	// textures: the two atlases as CUDA mipmapped arrays behind texture objects (RGBA8 unorm, normalised coordinates,
 	// wrap, linear + mip-linear); 0 = no texture in the slot
 	int tex_width[2], tex_height[2], tex_levels[2];

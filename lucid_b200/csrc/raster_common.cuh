@@ -74,6 +74,21 @@ __device__ __forceinline__ uint4 fetchWorkItem(const Params &p, u32 i, const u32
 	return __ldcg(p.block_items + (size_t)k * p.block_items_cap + (i - first));
 }
 
+__device__ __forceinline__ uint4 *workItemSlot(const Params &p, u32 i, const u32 (&class_end)[ITEM_CLASSES]) {
+	int k = 0;
+	u32 first = 0;
+#pragma unroll
+	for(int c = 0; c < ITEM_CLASSES - 1; c++)
+		if(i >= class_end[c])
+			k = c + 1, first = class_end[c];
+	return p.block_items + (size_t)k * p.block_items_cap + (i - first);
+}
+// LUCID_OPT_OPAQUE_PREPASS is honoured by the front-to-back blend only (lucid_abi.h)
+__host__ __device__ __forceinline__ bool opaquePrepass(const Params &p) {
+	return (p.opts & LUCID_OPT_OPAQUE_PREPASS) != 0 && (p.opts & (LUCID_OPT_ADDITIVE_BLENDING | LUCID_OPT_ALPHA_THRESHOLD)) == 0 &&
+		   p.opaque_depth != nullptr;
+}
+
 // ------------------------------------------------------------------------------------------------
 // scanline evaluation (scanline.glsl:13-26, raster.glsl:116-140)
 

@@ -172,10 +172,13 @@ struct ItemCtx {
 	int count;
 	int hb_x, hb_y; // top-left pixel of the half-block
 	bool lower;		// LOW items: the block's lower half (second pixel mask)
+	const float *opaque_depth; // PREPASS: the half-block's 32 nearest-opaque depths
 };
 
-// one 8x4 half-block from its sorted entries
-template <bool TMA>
+// one 8x4 half-block from its sorted entries.  PREPASS (LUCID_OPT_OPAQUE_PREPASS): a sample behind the nearest opaque
+// sample of its pixel does not exist -- it is not counted, shaded or reduced; the pixel lane decides that from the
+// entry's depth plane before the chunk's samples are laid out.
+template <bool TMA, bool PREPASS>
 __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfig &cfg, const ColourTables &tab, const LightTerms &lt,
 											   const WarpMem &wm, const ItemCtx &it, u32 &seq_base) {
 	const int lane = laneId();
@@ -187,6 +190,7 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 	reducerInit(red);
 	u32 px_frags = 0;
 	bool dead = false;
+	const float zo = PREPASS ? __ldcg(it.opaque_depth + lane) : 0.0f;
 	PhaseTimer timer = timerStart(p); // raster_timers: 2 unpack samples, 3 shade and reduce, 4 finish reduce
 
 	RingStream rs;
@@ -232,6 +236,26 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 			loadAhead(next + lane);
 
 		u32 tm = transpose32(bits);
+		// the chunk's planes by chunk-local entry index
+		const u32 plane_base = TMA ? rs.seq_base * RING_BLOCK + (u32)base : 0u;
+		auto planeAt = [&](int j) { return wm.plane[TMA ? ((plane_base + (u32)j) & (RING_ENTRIES - 1)) : (u32)j]; };
+		if(PREPASS) {
+			// the pixel's surviving samples of this chunk; every one of them counts, also at a pixel that is
+			// already opaque
+			if(!TMA) {
+				wm.plane[lane] = aux;
+				__syncwarp();
+			}
+			u32 keep = 0;
+			for(u32 b = tm; b; b &= b - 1) {
+				const int j = __ffs(b) - 1;
+				const uint4 s = planeAt(j);
+				const float depth = __uint_as_float(s.x) * fpx + (__uint_as_float(s.y) * fpy + __uint_as_float(s.z));
+				if(!(depth < zo))
+					keep |= 1u << j;
+			}
+			tm = keep;
+		}
 		px_frags += __popc(tm);
 		timerMark(timer, p.info->raster_timers, 2);
 		if(dead)
@@ -241,13 +265,18 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 		const u32 dead_px = vis_errors ? 0u : __ballot_sync(0xffffffffu, red.trans == 0.0f);
 		if((dead_px >> lane) & 1u)
 			tm = 0;
-		// the chunk's planes by chunk-local entry index
-		const u32 plane_base = TMA ? rs.seq_base * RING_BLOCK + (u32)base : 0u;
-		auto planeAt = [&](int j) { return wm.plane[TMA ? ((plane_base + (u32)j) & (RING_ENTRIES - 1)) : (u32)j]; };
+		if(PREPASS) {
+			// back to the entries' view: the pixels of entry `lane` that are still to be shaded
+			bits = transpose32(tm);
+			if(__all_sync(0xffffffffu, bits == 0)) {
+				__syncwarp();
+				continue;
+			}
+		}
 
 		if(__all_sync(0xffffffffu, !in_chunk || aux.w != AUX_VARYING)) {
 			// constant-colour triangles only: the pixel lane evaluates its own depths
-			if(!TMA) {
+			if(!TMA && !PREPASS) {
 				wm.plane[lane] = aux;
 				__syncwarp();
 			}
@@ -260,9 +289,9 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 			}
 		} else {
 			// samples of live pixels only: offsets are recomputed over the masked pixel sets
-			const u32 live = bits & ~dead_px;
+			const u32 live = PREPASS ? bits : bits & ~dead_px;
 			int live_off = off, live_total = total;
-			if(dead_px != 0) {
+			if(PREPASS || dead_px != 0) {
 				const int nl = __popc(live);
 				const int li = warpInclusiveScan(nl);
 				live_off = li - nl;
@@ -281,7 +310,7 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 				if(aux.w == AUX_VARYING && live != 0)
 					stageEntry(p, lt, rec.x, wm.stage + lane * STAGE_WORDS);
 			}
-			if(!TMA)
+			if(!TMA && !PREPASS)
 				wm.plane[lane] = aux;
 			__syncwarp();
 			for(int r0 = 0; r0 < live_total; r0 += 32) {
@@ -311,9 +340,17 @@ __device__ __forceinline__ void shadeHalfBlock(const Params &p, const LucidConfi
 		timerMark(timer, p.info->raster_timers, 3);
 		if(!vis_errors && __all_sync(0xffffffffu, red.trans == 0.0f)) {
 			dead = true;
-			if(!p.frag_counts)
+			if(!p.frag_counts && !PREPASS) // the pre-pass counts the surviving samples of the rest of the list too
 				break;
 		}
+	}
+	if(PREPASS) {
+		u32 n = px_frags;
+#pragma unroll
+		for(int o = 16; o > 0; o >>= 1)
+			n += __shfl_xor_sync(0xffffffffu, n, o);
+		if(lane == 0 && n)
+			atomicAdd(&p.info->stats[0], n);
 	}
 	if(TMA) {
 		// copies still in flight land before the ring is used again
@@ -440,8 +477,8 @@ __device__ __forceinline__ void shadeHalfBlockSegments(const Params &p, const Lu
 	writePixel(p, cfg, red, it.hb_x, it.hb_y, px_frags, false, false);
 }
 
-// TMA: entry stream through the bulk-copy ring; SEGMENTS: the ALPHA_THRESHOLD build
-template <bool TMA, bool SEGMENTS>
+// TMA: entry stream through the bulk-copy ring; SEGMENTS: the ALPHA_THRESHOLD build; PREPASS: LUCID_OPT_OPAQUE_PREPASS
+template <bool TMA, bool SEGMENTS, bool PREPASS = false>
 __global__ void __launch_bounds__(BLOCK_WARPS * 32, SHADE_MIN_CTAS)
 	k_block_shade(const __grid_constant__ Params p, const __grid_constant__ LucidConfig cfg) {
 	extern __shared__ __align__(128) unsigned char smem[];
@@ -504,10 +541,14 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SHADE_MIN_CTAS)
 		const int halves = high ? 1 : 2;
 		for(int half = 0; half < halves; half++) {
 			it.lower = half != 0, it.hb_y = y0 + half * 4;
+			if(PREPASS) {
+				const int hbi = high ? sub : (((sub >> 2) * 2 + half) * 4 + (sub & 3));
+				it.opaque_depth = p.opaque_depth + ((size_t)bin_id * 32 + hbi) * 32;
+			}
 			if(SEGMENTS)
 				shadeHalfBlockSegments(p, cfg, tab, lt, wm, it);
 			else
-				shadeHalfBlock<TMA>(p, cfg, tab, lt, wm, it, seq_base);
+				shadeHalfBlock<TMA, PREPASS>(p, cfg, tab, lt, wm, it, seq_base);
 			__syncwarp();
 		}
 		if(lane == 0)
@@ -561,6 +602,7 @@ void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, 
 		cudaFuncSetAttribute(k_block_shade<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tma);
 		cudaFuncSetAttribute(k_block_shade<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ldg);
 		cudaFuncSetAttribute(k_block_shade<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ldg);
+		cudaFuncSetAttribute(k_block_shade<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ldg);
 	});
 	const LucidVec4 &bg = cfg.background_color;
 	auto q = [](float v) { return (u32)(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f + 0.5f); };
@@ -576,6 +618,8 @@ void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, 
 	const int grid = num_sms * SHADE_MIN_CTAS;
 	if(segments)
 		launchPDL((k_block_shade<false, true>), grid, BLOCK_WARPS * 32, (size_t)smem_ldg, stream, p, cfg);
+	else if(opaquePrepass(p))
+		launchPDL((k_block_shade<false, false, true>), grid, BLOCK_WARPS * 32, (size_t)smem_ldg, stream, p, cfg);
 	else if(shadeStreamTma())
 		launchPDL((k_block_shade<true, false>), grid, BLOCK_WARPS * 32, (size_t)smem_tma, stream, p, cfg);
 	else

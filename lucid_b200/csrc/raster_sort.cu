@@ -112,6 +112,12 @@ __device__ __forceinline__ void promoteBins(const Params &p, int *s_warp) {
 }
 
 
+// PREPASS: LUCID_OPT_OPAQUE_PREPASS -- before the keys, the warp works out the depth of the nearest INST_IS_OPAQUE
+// sample of every pixel of the item (lane = pixel, one pass over the opaque entries) and leaves it in
+// p.opaque_depth for k_block_shade; an entry that lies behind that depth at every pixel of its half-block(s) --
+// decided conservatively from the depth plane at the tile corners -- gets the padding key, sorts to the end and is
+// cut off the item, so it is neither sorted nor streamed nor shaded.
+template <bool PREPASS>
 __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(const __grid_constant__ Params p, u32 background) {
 	__shared__ __align__(16) u32 s_keys[BLOCK_WARPS][SMEM_KEYS];
 	__shared__ int s_misc[BLOCK_WARPS];
@@ -166,6 +172,66 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 			}
 			return r4;
 		};
+		// ---- opaque pre-pass: nearest opaque sample depth per pixel (sample depths are inverse ray positions:
+		// larger = nearer); zfar[h] = the farthest of them over the pixels of half h (-inf: some pixel has no opaque cover)
+		float zfar[2] = {-INFINITY, -INFINITY};
+		const float tile_x = float(pos_x + cx8), tile_y = float(pos_y + ry * (high ? 4 : 8));
+		if(PREPASS) {
+			float zo[2] = {-INFINITY, -INFINITY};
+			const float fpx = float(pos_x + cx8 + (lane & 7)), fpy = float(pos_y + ry * (high ? 4 : 8) + (lane >> 3));
+			for(int i0 = 0; i0 < count; i0 += 32) {
+				const uint4 rec = loadRec(i0 + lane);
+				uint4 dq = make_uint4(0, 0, 0, 0);
+				if(i0 + lane < count)
+					dq = __ldg(reinterpret_cast<const uint4 *>(p.tri_shade + (rec.x & 0xffffffu)));
+				const bool opaque = (dq.w & LUCID_INST_IS_OPAQUE) != 0;
+				u32 m0 = 0, m1 = 0;
+				if(opaque) {
+					u32 tri_idx, mins, maxs;
+					int nf;
+					if(high) {
+						unpackHighRecord(make_uint2(rec.x, rec.y), tri_idx, mins, maxs);
+						m0 = rowsToBits(mins, maxs, cx8, nf);
+					} else {
+						unpackLowRecord(rec, false, tri_idx, mins, maxs);
+						m0 = rowsToBits(mins, maxs, cx8, nf);
+						unpackLowRecord(rec, true, tri_idx, mins, maxs);
+						m1 = rowsToBits(mins, maxs, cx8, nf);
+					}
+				}
+				for(u32 todo = __ballot_sync(0xffffffffu, opaque); todo; todo &= todo - 1) {
+					const int j = __ffs(todo) - 1;
+					const float dx = __uint_as_float(__shfl_sync(0xffffffffu, dq.x, j));
+					const float dy = __uint_as_float(__shfl_sync(0xffffffffu, dq.y, j));
+					const float dz = __uint_as_float(__shfl_sync(0xffffffffu, dq.z, j));
+					const u32 c0 = __shfl_sync(0xffffffffu, m0, j), c1 = __shfl_sync(0xffffffffu, m1, j);
+					if((c0 >> lane) & 1u)
+						zo[0] = fmaxf(zo[0], dx * fpx + (dy * fpy + dz));
+					if((c1 >> lane) & 1u)
+						zo[1] = fmaxf(zo[1], dx * fpx + (dy * (fpy + 4.0f) + dz));
+				}
+			}
+			const int halves = high ? 1 : 2;
+			for(int h = 0; h < halves; h++) {
+				const int hbi = high ? sub : ((ry * 2 + h) * 4 + (sub & 3));
+				p.opaque_depth[((size_t)bin_id * 32 + hbi) * 32 + lane] = zo[h];
+				float z = zo[h];
+#pragma unroll
+				for(int o = 16; o > 0; o >>= 1)
+					z = fminf(z, __shfl_xor_sync(0xffffffffu, z, o));
+				zfar[h] = z;
+			}
+		}
+		const bool cull_any = PREPASS && (zfar[0] > -INFINITY || zfar[1] > -INFINITY);
+		// the nearest depth a triangle's plane takes on a half-block: every rounding of the evaluation is monotone in
+		// x and in y, so the largest value over the 8x4 pixels is taken at a corner
+		auto nearestOnTile = [&](uint4 d, float y0) {
+			const float dx = __uint_as_float(d.x), dy = __uint_as_float(d.y), dz = __uint_as_float(d.z);
+			const float a = dx * tile_x, b = dx * (tile_x + 7.0f), c = dy * y0 + dz, e = dy * (y0 + 3.0f) + dz;
+			return fmaxf(fmaxf(a + c, a + e), fmaxf(b + c, b + e));
+		};
+		int n_culled = 0;
+
 		uint4 rec_next[KEY_UNROLL];
 #pragma unroll
 		for(int u = 0; u < KEY_UNROLL; u++)
@@ -197,6 +263,8 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 					float cpy = float(cy) * scale + (float(ry * 4) + float(pos_y));
 					depth = blockDepth(dq[u], cpx, cpy, float(0x7fffe)) << 14;
 					frag_acc += (u32)nf;
+					if(cull_any && nearestOnTile(dq[u], tile_y) < zfar[0])
+						depth = 0xffffffffu;
 				} else {
 					int nf0, cx0, cy0, nf1, cx1, cy1;
 					unpackLowRecord(rec[u], false, tri_idx, mins, maxs);
@@ -209,7 +277,14 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 					float cpx = cx * scale + float(pos_x + cx8), cpy = cy * scale + float(pos_y + ry * 8);
 					depth = blockDepth(dq[u], cpx, cpy, float(0x3ffffe)) << 10;
 					frag_acc += (u32)(nf0 + nf1);
+					if(PREPASS && count <= 3)
+						depth = 0; // unsorted lists keep their order when hidden entries are cut out of them
+					if(cull_any && (nf0 == 0 || nearestOnTile(dq[u], tile_y) < zfar[0]) &&
+					   (nf1 == 0 || nearestOnTile(dq[u], tile_y + 4.0f) < zfar[1]))
+						depth = 0xffffffffu;
 				}
+				if(PREPASS && depth == 0xffffffffu)
+					n_culled++;
 				keys[i] = (u32)i | depth;
 			}
 		}
@@ -218,6 +293,13 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 		// HIGH the exact half-block list (raster_high.glsl:309-310)
 		hbt_acc += lane == 0 ? (u32)count * (high ? 1u : 2u) : 0u;
 		const int slot_bits = high ? 14 : 10;
+		int kept = count; // entries that go into the stream
+		if(PREPASS && cull_any) {
+#pragma unroll
+			for(int o = 16; o > 0; o >>= 1)
+				n_culled += __shfl_xor_sync(0xffffffffu, n_culled, o);
+			kept = count - n_culled;
+		}
 		if(high || count > 3) { // LOW blocks with <= 3 triangles rely on the window alone (raster_low.glsl:144)
 			if(large)
 				warpSortLarge(keys, count, s_keys[warp]);
@@ -225,15 +307,19 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 				warpSortShared(keys, count);
 			// depth ties by triangle index: the triangle of a list position is looked up in the list itself
 			if(high)
-				warpFixDepthTies(keys, count, slot_bits,
+				warpFixDepthTies(keys, kept, slot_bits,
 								 [&](u32 pos) { return __ldg(reinterpret_cast<const uint2 *>(list) + pos).x & 0xffffffu; });
 			else
-				warpFixDepthTies(keys, count, slot_bits, [&](u32 pos) { return __ldg(reinterpret_cast<const uint4 *>(list) + pos).x; });
+				warpFixDepthTies(keys, kept, slot_bits, [&](u32 pos) { return __ldg(reinterpret_cast<const uint4 *>(list) + pos).x; });
+		} else if(PREPASS && kept < count) {
+			warpSortShared(keys, count); // keys are list positions: the kept entries move to the front in list order
 		}
+		if(PREPASS && kept < count && lane == 0)
+			workItemSlot(p, index, class_end)->y = (u32)kept; // k_block_shade takes the item's length from here
 		// the entries in sorted order: (triangle, pixel masks) and (depth plane, constant colour)
 		const u32 pos_mask = (1u << slot_bits) - 1u;
 		uint4 *out_rec = p.sorted_rec + entry.z, *out_aux = p.sorted_aux + entry.z;
-		for(int i = lane; i < count; i += 32) {
+		for(int i = lane; i < kept; i += 32) {
 			const u32 pos = (large ? __ldcg(keys + i) : keys[i]) & pos_mask;
 			u32 tri_idx, mins, maxs, mask0, mask1 = 0;
 			int nf;
@@ -263,7 +349,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 		hbt_acc += __shfl_xor_sync(0xffffffffu, hbt_acc, o);
 	}
 	if(lane == 0) {
-		if(frag_acc)
+		if(frag_acc && !PREPASS) // with the pre-pass stats[0] counts the surviving samples: k_block_shade adds them
 			atomicAdd(&p.info->stats[0], frag_acc);
 		if(hbt_acc)
 			atomicAdd(&p.info->stats[1], hbt_acc);
@@ -274,7 +360,10 @@ static int blockSortGrid(int num_sms) { return num_sms * SORT_MIN_CTAS; }
 size_t rasterLargeKeysCount(int num_sms) { return (size_t)blockSortGrid(num_sms) * BLOCK_WARPS * MAX_HBLOCK_TRIS; }
 
 void launchBlockSort(const Params &p, u32 background, cudaStream_t stream, int num_sms) {
-	launchPDL(k_block_sort, blockSortGrid(num_sms), BLOCK_WARPS * 32, 0, stream, p, background);
+	if(opaquePrepass(p))
+		launchPDL(k_block_sort<true>, blockSortGrid(num_sms), BLOCK_WARPS * 32, 0, stream, p, background);
+	else
+		launchPDL(k_block_sort<false>, blockSortGrid(num_sms), BLOCK_WARPS * 32, 0, stream, p, background);
 }
 
 } // namespace lucid

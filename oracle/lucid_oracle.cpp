@@ -986,6 +986,11 @@ V4 Oracle::sampleTextureFast(const Texture &t, float u, float v, float dudx, flo
 	return textureUnitSample(t, u, v, textureLod(t, dudx, dvdx, dudy, dvdy, false));
 }
 
+// the sample depth alone (the first lines of shadeSample, shading.glsl:107-116): one rounding per operation
+inline float sampleDepth(const TriRecord &t, int ipx, int ipy) {
+	return bitsToFloat(t.depth.x) * float(ipx) + (bitsToFloat(t.depth.y) * float(ipy) + bitsToFloat(t.depth.z));
+}
+
 u32 Oracle::shadeSampleFast(int ipx, int ipy, u32 tri_idx, float &out_depth) const {
 	float px = float(ipx), py = float(ipy);
 	const TriRecord &t = tri(tri_idx);
@@ -1343,6 +1348,9 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 	bool vis_errors = (opts & LUCID_OPT_VISUALIZE_ERRORS) != 0;
 	bool alpha_thr = (opts & LUCID_OPT_ALPHA_THRESHOLD) != 0 && !additive && !vis_errors;
 	const float alpha_threshold = 1.0f / 128.0f;
+	// the opaque pre-pass relies on the front-to-back blend (a hidden sample contributes exactly +0): it is ignored
+	// under ADDITIVE_BLENDING and in the segment-accurate ALPHA_THRESHOLD mode
+	const bool prepass = (opts & LUCID_OPT_OPAQUE_PREPASS) != 0 && !additive && !(opts & LUCID_OPT_ALPHA_THRESHOLD);
 
 	if(error) {
 		// raster_high.glsl:313-317: the bin is painted red with alpha 0.  (The reference adds
@@ -1415,6 +1423,25 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 				u32 frag_total = 0, tri_count = (u32)list.size();
 				u32 processed = 0; // samples consumed so far (segment boundaries every 256)
 				bool stop = false;
+				// LUCID_OPT_OPAQUE_PREPASS (the TODO of shading.glsl:31-32 as an option): the nearest sample of an
+				// INST_IS_OPAQUE triangle at a pixel hides every sample behind it.  Sample depths are inverse ray
+				// positions (larger = nearer), so zo = the largest opaque sample depth of the pixel and a sample
+				// survives iff depth >= zo.  Hidden samples are neither counted nor shaded nor reduced.
+				float zo[32];
+				for(int p = 0; p < 32; p++)
+					zo[p] = -INF;
+				if(prepass)
+					for(const Entry &e : list) {
+						const RowTri &rt = rows[g][e.slot];
+						const TriRecord &t = tri(rt.tri_idx);
+						if(!(t.depth.w & LUCID_INST_IS_OPAQUE))
+							continue;
+						u32 bits = halfPixelMask(halfSpans(rt.mins[half], rt.maxs[half], startx));
+						for(; bits != 0; bits &= bits - 1) {
+							int pid = findLSB(bits);
+							zo[pid] = fmax2(zo[pid], sampleDepth(t, hb_x + (pid & 7), hb_y + (pid >> 3)));
+						}
+					}
 				if(collect_item_stats && !list.empty()) {
 					std::vector<u32> entry_bits;
 					for(const Entry &e : list) {
@@ -1427,12 +1454,14 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 				for(const Entry &e : list) {
 					const RowTri &rt = rows[g][e.slot];
 					HalfSpans h = halfSpans(rt.mins[half], rt.maxs[half], startx);
-					frag_total += h.num_frags;
 					u32 bits = halfPixelMask(h);
 					while(bits != 0) {
 						int pid = findLSB(bits);
 						bits &= bits - 1;
 						int ipx = hb_x + (pid & 7), ipy = hb_y + (pid >> 3);
+						if(prepass && sampleDepth(tri(rt.tri_idx), ipx, ipy) < zo[pid])
+							continue;
+						frag_total++;
 						px_frags[pid]++;
 						if(!stop) {
 							float depth;

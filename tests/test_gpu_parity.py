@@ -62,6 +62,84 @@ def test_render_options(name, opts, small):
         r.close()
 
 
+@pytest.mark.parametrize("name", ["soup", "soup_close", "meshlets", "arch", "planes"])
+@pytest.mark.parametrize("extra", [0, api.OPT_VISUALIZE_ERRORS])
+def test_opaque_prepass_option(name, extra, small):
+    """LUCID_OPT_OPAQUE_PREPASS (the TODO of shared/shading.glsl:31-32 as an option): samples behind the
+    nearest INST_IS_OPAQUE sample of their pixel are dropped before sorting and shading.  Against the oracle's own
+    pre-pass mode: per-pixel counts of the surviving samples, stats and image are identical; against the plain
+    frame: setup and binning products are untouched, fewer fragments, and the image can only differ by more than
+    1/255 where the reference's 3-entry window was too small (pixels VISUALIZE_ERRORS flags); 1/255 is what a
+    flagged-opaque sample leaks when its interpolated vertex alpha truncates to 254."""
+    sc = small[name]
+    opts = api.OPT_OPAQUE_PREPASS | extra
+    o = pu.run_oracle(sc, opts=opts)
+    r, img = pu.run_cuda(sc, opts=opts)
+    plain_r, plain_img = pu.run_cuda(sc, opts=extra)
+    try:
+        assert _clean(pu.compare(r, img, o)) == {}
+        st, st0 = api.decode_stats(r.read_info(), r.bin_count, r.width, r.height), plain_r.getStats()
+        assert st["fragments"] <= st0["fragments"] and st["half_block_tris"] == st0["half_block_tris"]
+        if name in ("soup", "meshlets", "arch"):
+            assert st["fragments"] < st0["fragments"]
+        assert (r.read_frag_counts() <= plain_r.read_frag_counts()).all()
+        if extra == 0:
+            ev_r, _ = pu.run_cuda(sc, opts=api.OPT_VISUALIZE_ERRORS)
+            invalid = ev_r.getStats()["invalid_pixels"]
+            ev_r.close()
+            d = np.abs(img.view(np.uint8).astype(np.int32) - plain_img.view(np.uint8).astype(np.int32))
+            differing = int((d.reshape(img.shape + (4,)).max(axis=-1) > 1).sum())
+            assert differing <= invalid, (differing, invalid)
+    finally:
+        r.close()
+        plain_r.close()
+
+
+def test_opaque_prepass_closed_form():
+    """Stacked planes with layer k opaque: k + 1 surviving samples wherever all layers overlap."""
+    from tests.test_oracle import planes_with_opaque_layer
+    k, n = 5, 12
+    sc = planes_with_opaque_layer(k, n)
+    r, img = pu.run_cuda(sc, opts=api.OPT_OPAQUE_PREPASS)
+    r0, img0 = pu.run_cuda(sc)
+    try:
+        f1, f0 = r.read_frag_counts(), r0.read_frag_counts()
+        assert (f1[f0 == n] == k + 1).all() and int(r.read_info()[60]) == int(f1.sum())
+        assert np.abs(img.view(np.uint8).astype(np.int32) - img0.view(np.uint8).astype(np.int32)).max() <= 1
+    finally:
+        r.close()
+        r0.close()
+
+
+def test_opaque_prepass_is_ignored_where_it_would_change_the_image(small):
+    """Additive blending has no transmittance and the alpha-threshold build stops on segment boundaries: the option
+    is ignored there (include/lucid_abi.h), frames equal the ones without it."""
+    sc = small["soup_close"]
+    for other in (api.OPT_ADDITIVE_BLENDING, api.OPT_ALPHA_THRESHOLD):
+        r, img = pu.run_cuda(sc, opts=other | api.OPT_OPAQUE_PREPASS)
+        r0, img0 = pu.run_cuda(sc, opts=other)
+        try:
+            assert np.array_equal(img, img0) and np.array_equal(r.read_info()[60:63], r0.read_info()[60:63])
+            assert np.array_equal(r.read_frag_counts(), r0.read_frag_counts())
+        finally:
+            r.close()
+            r0.close()
+
+
+def test_opaque_prepass_full_size_architecture():
+    """configs[3] at full size with the pre-pass against the oracle's pre-pass mode: 357.6 M fragments become the
+    ~10 % that lie in front of the nearest opaque sample."""
+    sc = scenes.get_config(3)
+    o = pu.run_oracle(sc, opts=api.OPT_OPAQUE_PREPASS, mvq=FULL_MVQ, threads=os.cpu_count())
+    r, img = pu.run_cuda(sc, opts=api.OPT_OPAQUE_PREPASS, mvq=FULL_MVQ)
+    try:
+        assert _clean(pu.compare(r, img, o)) == {}
+        st = api.decode_stats(r.read_info(), r.bin_count, r.width, r.height)
+        assert st["fragments"] < 357_598_648 // 4
+    finally:
+        r.close()
+
+
 def test_timers_option(small):
     """LUCID_OPT_TIMERS (the reference's `_timers` shader variants, shared/timers.glsl, lucid_renderer.cpp:754-762):
     the phases' clock ticks land in LucidInfo.setup_timers / bin_dispatcher_timers / raster_timers in the reference's

@@ -132,7 +132,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = api.load_library()
     declared = set()
     import re
-    for hdr in ("lucid_b200.h", "lucid_host.h"):
+    for hdr in ("lucid_b200.h", "lucid_host.h", "lucid_quadgen.h"):
         with open(os.path.join(HERE, "..", "include", hdr)) as f:
             txt = f.read()
         declared |= set(re.findall(r"\b(lucid_[a-z0-9_]+)\s*\(", txt))

@@ -97,6 +97,55 @@ def test_planes_closed_form(small):
     assert img == exact
 
 
+def planes_with_opaque_layer(k=5, n=12, width=320, height=200):
+    """#planes with plane k made opaque (its own INST_IS_OPAQUE draw call): k + 1 samples are in front of or on the
+    opaque layer at every pixel it covers."""
+    sc = scenes.planes(num_planes=n, width=width, height=height)
+    sc["materials"] = [((1.0, 1.0, 1.0), 0.25, (0.0, 0.0, 1.0, 1.0)), ((1.0, 1.0, 1.0), 1.0, (0.0, 0.0, 1.0, 1.0))]
+    vc = scenes.INST_HAS_VERTEX_COLORS
+    sc["draw_calls"] = [(0, k, 0, vc), (1, 1, k, vc | scenes.INST_IS_OPAQUE), (0, n - k - 1, k + 1, vc)]
+    return sc
+
+
+def _max_channel_diff(a, b):
+    return np.abs(a.view(np.uint8).astype(np.int32) - b.view(np.uint8).astype(np.int32)).reshape(a.shape + (4,)).max(axis=-1)
+
+
+def test_opaque_prepass_mode(small):
+    """LUCID_OPT_OPAQUE_PREPASS in the checker (shared/shading.glsl:31-32 TODO as an option): closed form on stacked
+    planes; on the parity scenes the exact per-pixel-sort image stays within 1/255 (a flagged-opaque sample whose
+    interpolated vertex alpha truncates to 254 leaks 1/255 of what lies behind it without the option), the window
+    image differs by more only where the window was too small, everything before the raster stage is untouched, and
+    the option is ignored under additive blending."""
+    k, n = 5, 12
+    sc = planes_with_opaque_layer(k, n)
+    plain, pre = pu.run_oracle(sc, threads=4), pu.run_oracle(sc, opts=api.OPT_OPAQUE_PREPASS, threads=4)
+    f0, f1 = plain.read_frag_counts(), pre.read_frag_counts()
+    cy, cx = sc["height"] // 2, sc["width"] // 2
+    assert f0[cy, cx] == n and f1[cy, cx] == k + 1
+    inside = f0 == n  # pixels inside the smallest plane: all layers present
+    assert (f1[inside] == k + 1).all()
+    assert _max_channel_diff(plain.read_image(), pre.read_image()).max() <= 1
+    assert int(pre.info[60]) == int(f1.sum()) < int(plain.info[60])
+    for name in ("soup", "meshlets", "arch", "hairball"):
+        plain = pu.run_oracle(small[name], threads=8)
+        pre = pu.run_oracle(small[name], opts=api.OPT_OPAQUE_PREPASS, threads=8)
+        assert np.array_equal(plain.info[:60], pre.info[:60]) and plain.info[61] == pre.info[61]
+        assert _max_channel_diff(plain.read_exact_image(), pre.read_exact_image()).max() <= 1
+        f0, f1 = plain.read_frag_counts(), pre.read_frag_counts()
+        assert (f1 <= f0).all() and int(pre.info[60]) == int(f1.sum())
+        if name == "hairball":  # no opaque instance: nothing changes
+            assert np.array_equal(f0, f1)
+        else:
+            assert f1.sum() < f0.sum()
+        vis = pu.run_oracle(small[name], opts=api.OPT_VISUALIZE_ERRORS, threads=8)
+        invalid = api.decode_stats(vis.info, vis.bin_count, vis.width, vis.height)["invalid_pixels"]
+        assert int((_max_channel_diff(plain.read_image(), pre.read_image()) > 1).sum()) <= invalid
+    add = pu.run_oracle(small["soup"], opts=api.OPT_ADDITIVE_BLENDING, threads=8)
+    add_pre = pu.run_oracle(small["soup"], opts=api.OPT_ADDITIVE_BLENDING | api.OPT_OPAQUE_PREPASS, threads=8)
+    assert np.array_equal(add.read_image(), add_pre.read_image()) and np.array_equal(add.info, add_pre.info)
+
+
 def test_pow_contract_accuracy():
     """orc_pow is the shared polynomial pow; it must stay within 3e-6 relative of libm on the
     sRGB ranges so colours stay well inside the 1/255 tolerance."""

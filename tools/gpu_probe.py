@@ -1,5 +1,5 @@
 """Full-size probe: stage times + counters of the CUDA path on the BASELINE configs (parity against the
-checker is the GPU test suite's job).  usage: python tools/gpu_probe.py [config ...] [--scale=S]"""
+checker is the GPU test suite's job).  usage: python tools/gpu_probe.py [config ...] [--scale=S] [--opts=BITS]"""
 import json
 import os
 import sys
@@ -11,16 +11,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lucid_b200 import api, scenes  # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-scale = 1.0
+scale, opts = 1.0, 0
 for a in sys.argv[1:]:
     if a.startswith("--scale="):
         scale = float(a.split("=")[1])
+    if a.startswith("--opts="):
+        opts = int(a.split("=")[1], 0)
 configs = [int(a) for a in args] or [0, 1]
 for ci in configs:
     t0 = time.time()
     sc = scenes.get_config(ci, scale)
     cfg, inst, cols, rects = api.prepare_frame(sc)
-    r = api.LucidRenderer(sc["width"], sc["height"], 0, 0)
+    r = api.LucidRenderer(sc["width"], sc["height"], opts, 0)
     r.set_scene(sc)
     img = np.zeros((sc["height"], sc["width"]), np.uint32)
     for _ in range(3):
@@ -31,7 +33,7 @@ for ci in configs:
         times.append(r.stage_times())
     ms = np.median(np.array(times), axis=0)
     st = r.getStats()
-    print(f"== config {ci} ({sc['name']}) gen+setup {time.time() - t0:.1f}s")
+    print(f"== config {ci} ({sc['name']}) opts {opts:#x} gen+setup {time.time() - t0:.1f}s")
     print("   stage_ms", dict(zip(["setup", "count", "scan", "dispatch", "lists", "sort", "shade", "frame"],
                                   np.round(ms, 3).tolist())))
     print("   stats", json.dumps(st))
