@@ -36,11 +36,12 @@ enum {
 	LUCID_RENDER_NO_STAGE_TIMES = 8, /* record only the frame's first and last timing event: without events
 									 between them the kernels of a frame overlap their launches
 									 (lucid_stage_times then reports the frame time only) */
-	LUCID_RENDER_CULL_INSTANCES = 16 /* bin-row split only: an instance whose bounding box projects outside the
-									 owned bin rows is dropped before its quads are loaded (the box is computed
-									 once per instance list and cached).  Conservative, so the visible quads, the
-									 per-bin lists and the pixels of the owned bins are unchanged;
-									 num_rejected_quads then only covers the instances that were processed */
+	LUCID_RENDER_CULL_INSTANCES = 16 /* an instance whose bounding box lies outside one frustum plane or projects
+									 outside the owned bin rows is dropped before its quads are loaded (the box
+									 is computed once per instance list and cached; the kept instances are
+									 compacted in input order by k_instance_select).  Conservative, so the
+									 visible quads with their slots, the per-bin lists and the pixels are
+									 unchanged; num_rejected_quads then only covers the processed instances */
 };
 
 /* LucidRenderer::exConstruct(device, compiler, opts, view_size), src/lucid_renderer.cpp:186-317.

@@ -67,6 +67,7 @@ struct lucid_renderer {
 	u32 gate_value = 0;
 	// LUCID_RENDER_CULL_INSTANCES: boxes of the instance list they were computed for
 	float4 *d_inst_boxes = nullptr;
+	u32 *d_active_instances = nullptr;
 	std::vector<LucidInstanceData> boxed_instances;
 	bool boxes_valid = false;
 	cudaStream_t upload_stream = nullptr;
@@ -292,6 +293,7 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	r->image = r->images[0];
 	CUC(devAlloc(r, &r->frag_counts, (size_t)p.width * p.height));
 	CUC(devAlloc(r, &r->d_inst_boxes, (size_t)LUCID_MAX_INSTANCES * 2));
+	CUC(devAlloc(r, &r->d_active_instances, (size_t)LUCID_MAX_INSTANCES + 1));
 	CUC(devAlloc(r, &r->d_sync, (size_t)LUCID_SYNC_FLAGS));
 	CUC(cudaMemsetAsync(r->d_sync, 0, LUCID_SYNC_FLAGS * 4, r->stream));
 	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++) {
@@ -603,10 +605,10 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 		p.image_pitch = p.width;
 	}
 	p.frag_counts = (flags & LUCID_RENDER_FRAG_COUNTS) ? r->frag_counts : nullptr;
-	// instance boxes for the split's early instance cull: recomputed only when the instance list changes
+	// instance boxes for the early instance cull: recomputed only when the instance list changes
 	p.inst_boxes = nullptr;
-	const bool restricted = p.bin_begin > 0 || p.bin_end < p.bin_count;
-	if((flags & LUCID_RENDER_CULL_INSTANCES) && restricted && num_instances > 0) {
+	p.active_instances = nullptr;
+	if((flags & LUCID_RENDER_CULL_INSTANCES) && num_instances > 0) {
 		if(!r->boxes_valid || r->boxed_instances.size() != n ||
 		   memcmp(r->boxed_instances.data(), instances, n * sizeof(LucidInstanceData)) != 0) {
 			r->boxed_instances.assign(instances, instances + n);
@@ -614,6 +616,7 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 			r->boxes_valid = true;
 		}
 		p.inst_boxes = r->d_inst_boxes;
+		p.active_instances = r->d_active_instances;
 	}
 
 	double t1 = host_profile ? now() : 0.0;

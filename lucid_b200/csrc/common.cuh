@@ -64,7 +64,8 @@ struct Params {
 	const LucidInstanceData *instances;
 	const u32 *inst_colors;
 	const float4 *inst_uv_rects;
-	const float4 *inst_boxes; // per instance (min, max) of its vertices, or null: instance culling of the bin-row split
+	const float4 *inst_boxes; // per instance (min, max) of its vertices, or null: instance culling (LUCID_RENDER_CULL_INSTANCES)
+	u32 *active_instances;	  // with inst_boxes: [0] number of instances k_quad_cull works on, [1..] their ids in input order
 
 	// renderer-owned storage
 	u32 *quad_aabbs;

@@ -42,7 +42,7 @@ __device__ __forceinline__ BinInfo loadBin(const Params &p, int bin_id) {
 // lane busy.  emit(active, tri, group, mins0, maxs0, mins1, maxs1, bx) is called by all lanes.
 constexpr int PHASE_A_RING = 64; // items; 32 bytes each, in the warp's (idle) phase-B scratch
 
-template <bool HIGH, typename Emit>
+template <bool HIGH, int THREADS, typename Emit>
 __device__ __forceinline__ void binPhaseA(const Params &p, const BinInfo &b, uint4 *ring, Emit emit) {
 	constexpr int shift = HIGH ? 2 : 3, rows_per_group = HIGH ? 4 : 8;
 	const int lane = laneId(), warp = threadIdx.x >> 5;
@@ -79,10 +79,10 @@ __device__ __forceinline__ void binPhaseA(const Params &p, const BinInfo &b, uin
 		return f;
 	};
 	Fetched ahead = fetch(warp * 32);
-	for(int base = warp * 32; base < b.n_T; base += RASTER_THREADS) {
+	for(int base = warp * 32; base < b.n_T; base += THREADS) {
 		const Fetched cur = ahead;
-		if(base + RASTER_THREADS < b.n_T)
-			ahead = fetch(base + RASTER_THREADS);
+		if(base + THREADS < b.n_T)
+			ahead = fetch(base + THREADS);
 		const u32 tri_idx = cur.tri_idx;
 		const bool ok = cur.ok;
 		int n_g = 0, min_g = 0;
@@ -139,10 +139,14 @@ struct BinShared {
 	int bin_index, status;
 };
 
-// a persistent 256-thread CTA takes one bin at a time: HIGH bins first (they take longest)
-__global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_constant__ Params p, u32 background) {
+// a persistent CTA takes one bin at a time: HIGH bins first (they take longest).  256 threads when there are bins for
+// every CTA slot of the device; a device that owns few bins (its share of a bin-range split) takes them with 512- or
+// 1024-thread CTAs, so that the heaviest bin -- the kernel's critical path -- is walked by 16 or 32 warps instead of 8
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_raster_bins(const __grid_constant__ Params p, u32 background) {
+	constexpr int WARPS = THREADS / 32;
 	__shared__ BinShared sh;
-	__shared__ __align__(16) uint4 s_ring[RASTER_WARPS][PHASE_A_RING * 2];
+	extern __shared__ __align__(16) uint4 s_ring_all[]; // WARPS rings of PHASE_A_RING items (32 bytes each)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	pdlEntry();
 	if(p.info->temp[1] != 0)
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 				sh.status = 0;
 			__syncthreads();
 			uint4 *recs = reinterpret_cast<uint4 *>(lists);
-			binPhaseA<false>(p, b, s_ring[warp], [&](bool, u32 tri_idx, int g, u32 mn0, u32 mx0, u32 mn1, u32 mx1, u32 bx) {
+			binPhaseA<false, THREADS>(p, b, s_ring_all + warp * (PHASE_A_RING * 2), [&](bool, u32 tri_idx, int g, u32 mn0, u32 mx0, u32 mn1, u32 mx1, u32 bx) {
 				while(bx) {
 					int c = __ffs(bx) - 1;
 					bx &= bx - 1;
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 				sh.status = 0;
 			__syncthreads();
 			uint2 *recs = reinterpret_cast<uint2 *>(lists);
-			binPhaseA<true>(p, b, s_ring[warp], [&](bool, u32 tri_idx, int g, u32 mn, u32 mx, u32, u32, u32 bx) {
+			binPhaseA<true, THREADS>(p, b, s_ring_all + warp * (PHASE_A_RING * 2), [&](bool, u32 tri_idx, int g, u32 mn, u32 mx, u32, u32, u32 bx) {
 				if(bx == 0)
 					return;
 				const int lo = __ffs(bx) - 1, hi = 31 - __clz(bx);
@@ -290,9 +294,9 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 		timerMark(timer, p.info->raster_timers, 0);
 		if(tid == 0)
 			atomicAdd(reinterpret_cast<unsigned long long *>(p.bin_cost) + bin_id,
-					  (unsigned long long)(clock64() - t_bin) * RASTER_WARPS);
+					  (unsigned long long)(clock64() - t_bin) * WARPS);
 		const int rows = high ? 4 : 8;
-		for(int blk = warp; blk < n_blocks; blk += RASTER_WARPS) {
+		for(int blk = warp; blk < n_blocks; blk += WARPS) {
 			if(sh.count[blk] != 0)
 				continue;
 			const int bx0 = b.pos_x + (blk & 3) * 8, by0 = b.pos_y + (blk >> 2) * rows;
@@ -310,7 +314,26 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster_bins(const __grid_con
 
 
 void launchRasterBins(const Params &p, u32 background, cudaStream_t stream, int num_sms) {
-	launchPDL(k_raster_bins, num_sms * 4, RASTER_THREADS, 0, stream, p, background);
+	// LUCID_RASTER_BINS_THREADS=256|512|1024 overrides the choice (measurements)
+	static const int forced = [] {
+		const char *v = getenv("LUCID_RASTER_BINS_THREADS");
+		return v ? atoi(v) : 0;
+	}();
+	const int owned = p.bin_end - p.bin_begin;
+	int threads = owned >= num_sms * 6 ? 256 : owned >= num_sms * 3 ? 512 : 1024;
+	if(forced == 256 || forced == 512 || forced == 1024)
+		threads = forced;
+	constexpr size_t ring_bytes_per_warp = PHASE_A_RING * 2 * sizeof(uint4);
+	static std::once_flag configured[64];
+	oncePerDevice(configured, [] {
+		cudaFuncSetAttribute(k_raster_bins<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * ring_bytes_per_warp));
+	});
+	if(threads == 256)
+		launchPDL(k_raster_bins<256>, num_sms * 4, 256, 8 * ring_bytes_per_warp, stream, p, background);
+	else if(threads == 512)
+		launchPDL(k_raster_bins<512>, num_sms * 2, 512, 16 * ring_bytes_per_warp, stream, p, background);
+	else
+		launchPDL(k_raster_bins<1024>, num_sms, 1024, 32 * ring_bytes_per_warp, stream, p, background);
 }
 
 } // namespace lucid

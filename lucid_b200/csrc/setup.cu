@@ -100,6 +100,82 @@ __device__ __forceinline__ bool boxOutsideOwnedRows(const Params &p, const Lucid
 	return ymax + 2.0f < float(p.row_begin * BIN_SIZE) || ymin - 2.0f >= float(p.row_end * BIN_SIZE);
 }
 
+// true when all eight corners lie outside one clip plane by more than the rounding of the transform: every vertex in
+// the box then has that plane's bit in its clip mask, so processInputQuad would reject each of its quads
+// (and_mask != 0, quad_setup.glsl:176-180)
+__device__ __forceinline__ bool boxOutsideFrustum(const LucidConfig &cfg, float4 lo, float4 hi) {
+	if(!(lo.x <= hi.x))
+		return false;
+	const LucidVec4 *m = cfg.view_proj_matrix;
+	u32 all = 0x3fu;
+#pragma unroll
+	for(int c = 0; c < 8; c++) {
+		const float x = (c & 1) ? hi.x : lo.x, y = (c & 2) ? hi.y : lo.y, z = (c & 4) ? hi.z : lo.z;
+		float v[4], mag[4];
+#pragma unroll
+		for(int k = 0; k < 4; k++) {
+			const float a = (&m[0].x)[k] * x, b = (&m[1].x)[k] * y, d = (&m[2].x)[k] * z, e = (&m[3].x)[k];
+			v[k] = a + b + d + e;
+			mag[k] = fabsf(a) + fabsf(b) + fabsf(d) + fabsf(e);
+		}
+		u32 mask = 0;
+#pragma unroll
+		for(int k = 0; k < 3; k++) {
+			const float tol = 1e-5f * (mag[k] + mag[3]);
+			mask |= (v[k] + v[3] < -tol ? 1u : 0u) << (2 * k);
+			mask |= (v[k] - v[3] > tol ? 2u : 0u) << (2 * k);
+		}
+		all &= mask;
+	}
+	return all != 0;
+}
+
+// Instance culling (LUCID_RENDER_CULL_INSTANCES): the instances whose box can reach the frustum and the owned bin rows,
+// in input order, for k_quad_cull to work on -- one CTA, an ordered compaction over tiles of 1024 instances.  The
+// quads of the others only count as input.
+__global__ void __launch_bounds__(1024) k_instance_select(const Params p, const __grid_constant__ LucidConfig cfg) {
+	__shared__ int s_warp[32];
+	__shared__ int s_base;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	pdlEntry();
+	if(tid == 0)
+		s_base = 0;
+	__syncthreads();
+	u32 skipped_quads = 0;
+	for(int first = 0; first < p.num_instances; first += 1024) {
+		const int i = first + tid;
+		bool keep = false;
+		if(i < p.num_instances) {
+			const float4 lo = __ldg(p.inst_boxes + i * 2), hi = __ldg(p.inst_boxes + i * 2 + 1);
+			keep = !(boxOutsideOwnedRows(p, cfg, lo, hi) || boxOutsideFrustum(cfg, lo, hi));
+			if(!keep)
+				skipped_quads += (u32)p.instances[i].num_quads;
+		}
+		const u32 bal = __ballot_sync(0xffffffffu, keep);
+		if(lane == 0)
+			s_warp[warp] = __popc(bal);
+		__syncthreads();
+		int before = s_base, total = 0;
+		for(int w = 0; w < 32; w++) {
+			before += w < warp ? s_warp[w] : 0;
+			total += s_warp[w];
+		}
+		if(keep)
+			p.active_instances[1 + before + __popc(bal & laneMaskLt())] = (u32)i;
+		__syncthreads();
+		if(tid == 0)
+			s_base += total;
+		__syncthreads();
+	}
+#pragma unroll
+	for(int o = 16; o > 0; o >>= 1)
+		skipped_quads += __shfl_xor_sync(0xffffffffu, skipped_quads, o);
+	if(lane == 0 && skipped_quads)
+		atomicAdd(&p.info->num_input_quads, skipped_quads);
+	if(tid == 0)
+		p.active_instances[0] = (u32)s_base;
+}
+
 // quad_setup.glsl:77-128 -- screen AABB of a triangle that crosses the near plane (Blinn 1996)
 __device__ float4 clippedAABB(float4 v0, float4 v1, float4 v2, float w0, float w1, float w2,
 							  u32 clipmask) {
@@ -369,13 +445,15 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 	if(tid < LUCID_REJECTION_TYPE_COUNT)
 		s_rejected[tid] = 0;
 	__syncthreads();
-	const u32 inst_id = s_vid;
+	// instance culling: the chain only runs over the instances k_instance_select kept
+	const u32 vid = s_vid;
+	if(p.active_instances != nullptr && vid >= __ldcg(p.active_instances))
+		return;
+	const u32 inst_id = p.active_instances != nullptr ? __ldcg(p.active_instances + 1 + vid) : vid;
 	const LucidInstanceData inst = p.instances[inst_id];
 	if(tid == 0)
 		atomicAdd(&p.info->num_input_quads, inst.num_quads);
-	// bin-row split: an instance that cannot reach the owned rows keeps its place in the look-back chain but
-	// loads nothing (every quad counts as "visible elsewhere")
-	const bool skip = p.inst_boxes != nullptr && boxOutsideOwnedRows(p, cfg, __ldg(p.inst_boxes + inst_id * 2), __ldg(p.inst_boxes + inst_id * 2 + 1));
+	constexpr bool skip = false;
 
 	timerMark(timer, p.info->setup_timers, 0);
 	uint4 vi[SETUP_PARTS];
@@ -435,7 +513,6 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CULL_MIN_CTAS)
 
 		u64 *lb = p.setup_lookback;
 		u32 ex_small = 0, ex_large = 0;
-		const u32 vid = inst_id;
 		if(vid == 0) {
 			if(lane == 0)
 				lbStore(lb, lbPack(LB_PREFIX, total_small, total_large));
@@ -600,6 +677,8 @@ void launchInfoOut(const Params &p, u32 *host_info, int num_words, cudaStream_t 
 void launchQuadSetup(const Params &p, const LucidConfig &cfg, cudaStream_t stream) {
 	if(p.num_setup_ctas == 0)
 		return;
+	if(p.active_instances != nullptr)
+		launchPDL(k_instance_select, 1, 1024, 0, stream, p, cfg);
 	launchPDL(k_quad_cull, p.num_setup_ctas, SETUP_THREADS, 0, stream, p, cfg);
 	launchPDL(k_tri_setup, 148 * 2 * SETUP_TRI_MIN_CTAS, SETUP_THREADS, 0, stream, p, cfg);
 }

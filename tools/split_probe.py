@@ -10,7 +10,7 @@ from lucid_b200 import api, multigpu, scenes  # noqa: E402
 
 ci = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 world = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-cull = api.RENDER_CULL_INSTANCES if "--cull" in sys.argv else 0
+cull = api.RENDER_CULL_INSTANCES if "--cull" in sys.argv else 0  # full frame below: always without
 sc = scenes.get_config(ci)
 cfg, inst, cols, rects = api.prepare_frame(sc)
 r = api.LucidRenderer(sc["width"], sc["height"], 0, 0)
