@@ -160,11 +160,11 @@ def depth_complexity(frag_counts: np.ndarray) -> dict:
 class Rig:
     """One renderer on this rank's GPU with a scene resident, plus what the timed loops share."""
 
-    def __init__(self, args, config, torch, dist, rank, world, local_rank, stream):
+    def __init__(self, args, config, torch, dist, rank, world, local_rank, stream, scene=None):
         from lucid_b200 import api
         self.api, self.torch, self.dist = api, torch, dist
         self.rank, self.world = rank, world
-        self.scene = make_scene(config, args.scale)
+        self.scene = scene if scene is not None else make_scene(config, args.scale)
         self.width, self.height = self.scene["width"], self.scene["height"]
         self.stream = stream
         self.r = api.LucidRenderer(self.width, self.height, 0, args.mvq, device=local_rank, stream=stream.cuda_stream)
@@ -386,52 +386,69 @@ def run_ours(args):
 
     # composite target for the bin-row split: every rank stores into rank 0's image over NVLink, and signals the
     # frame's completion through a flag in rank 0's memory (lucid_signal / lucid_wait_flags); --completion allreduce
-    # is the NCCL alternative
-    peer_ptr, flags_ptr = None, None
+    # is the NCCL alternative.  A lane = one renderer handle on its own stream with its own gathered image and
+    # flags on rank 0; lane 0 is the rig's handle, further lanes carry the frames in flight (below).
     use_flags = split and args.completion == "flags"
-    if split:
-        handle = [(r.ipc_export_image(), r.ipc_export_sync()) if rank == 0 else None]
-        dist.broadcast_object_list(handle, src=0)
-        if rank != 0:
-            peer_ptr = r.ipc_open_image(handle[0][0])
-            flags_ptr = r.ipc_open_image(handle[0][1])
-        else:
-            flags_ptr = r.sync_pointer()
     frame_token = torch.zeros(1, device="cuda")
-    frame_no = [0]
     RELEASED = api.LucidRenderer.SYNC_RELEASED
+
+    class Lane:
+        def __init__(self, lane_rig):
+            self.rig, self.r, self.stream = lane_rig, lane_rig.r, lane_rig.stream
+            self.peer_ptr, self.flags_ptr, self.frame_no = None, None, 0
+            if split:
+                handle = [(self.r.ipc_export_image(), self.r.ipc_export_sync()) if rank == 0 else None]
+                dist.broadcast_object_list(handle, src=0)
+                if rank != 0:
+                    self.peer_ptr = self.r.ipc_open_image(handle[0][0])
+                    self.flags_ptr = self.r.ipc_open_image(handle[0][1])
+                else:
+                    self.flags_ptr = self.r.sync_pointer()
+
+        def render(self, step, flags):
+            r = self.r
+            if use_flags:
+                self.frame_no += 1
+                if rank != 0:  # the shared image may be stored into once the previous frame was released
+                    r.set_frame_gate(self.flags_ptr, RELEASED, self.frame_no - 1)
+            if self.peer_ptr is not None and args.composite == "stores":
+                # the raster kernels store their pixels straight into rank 0's image
+                r.render(rig.config_for(view_of(step)), inst, cols, rects, out_device_ptr=self.peer_ptr,
+                         out_pitch=width * 4, flags=flags)
+            else:
+                r.render(rig.config_for(view_of(step)), inst, cols, rects, flags=flags)
+                if self.peer_ptr is not None:  # own image first, then the owned bins as whole 128-byte rows
+                    r.composite_to(self.peer_ptr, width * 4)
+
+        def after_frame(self, consume=None):
+            """The frame is complete when every rank's strip has landed in rank 0's image."""
+            r = self.r
+            if use_flags:
+                if rank != 0:
+                    r.signal(self.flags_ptr, rank, self.frame_no)
+                else:
+                    r.wait_flags(self.flags_ptr, 1, world - 1, self.frame_no)
+                    if consume is not None:
+                        consume()
+                    r.signal(self.flags_ptr, RELEASED, self.frame_no)
+            elif split:
+                dist.all_reduce(frame_token)
+                if consume is not None and rank == 0:
+                    consume()
+
+        def close(self):
+            if self.peer_ptr is not None:
+                self.r.ipc_close_image(self.peer_ptr)
+                self.peer_ptr = None
+            if rank != 0 and self.flags_ptr is not None:
+                self.r.ipc_close_image(self.flags_ptr)
+            self.flags_ptr = None
 
     def view_of(step):
         return 0 if split else step % 64
 
-    def render(step, flags):
-        if use_flags:
-            frame_no[0] += 1
-            if rank != 0:  # the shared image may be stored into once the previous frame was released
-                r.set_frame_gate(flags_ptr, RELEASED, frame_no[0] - 1)
-        if peer_ptr is not None and args.composite == "stores":
-            # the raster kernels store their pixels straight into rank 0's image
-            r.render(rig.config_for(view_of(step)), inst, cols, rects, out_device_ptr=peer_ptr, out_pitch=width * 4,
-                     flags=flags)
-        else:
-            r.render(rig.config_for(view_of(step)), inst, cols, rects, flags=flags)
-            if peer_ptr is not None:  # own image first, then the owned bins as whole 128-byte rows
-                r.composite_to(peer_ptr, width * 4)
-
-    def after_frame(consume=None):
-        """The frame is complete when every rank's strip has landed in rank 0's image."""
-        if use_flags:
-            if rank != 0:
-                r.signal(flags_ptr, rank, frame_no[0])
-            else:
-                r.wait_flags(flags_ptr, 1, world - 1, frame_no[0])
-                if consume is not None:
-                    consume()
-                r.signal(flags_ptr, RELEASED, frame_no[0])
-        elif split:
-            dist.all_reduce(frame_token)
-            if consume is not None and rank == 0:
-                consume()
+    lane0 = Lane(rig)
+    render, after_frame = lane0.render, lane0.after_frame
 
     # NVML is polled by a separate process, for the GPU of the rank that prints the line
     sampler = ClockSampler(local_rank)
@@ -453,6 +470,62 @@ def run_ours(args):
     step_median = max_over_ranks(rig, float(np.median(step_ms)))
 
     sustained = sustained_run(rig, render, after_frame, args.sustained_seconds, 1)
+
+    # Frames in flight (bin-range split): with an eighth of the bins on a device every kernel of a frame runs out of
+    # parallel work before it runs out of work (one bin per CTA, one list per warp), so F handles on F streams render
+    # alternate frames and the kernels of neighbouring frames fill each other's tails.  The same K steps, timed as one
+    # bracket; no L2 flush in between (a rank's frame reads > 400 MB of geometry and records, the L2 holds 126 MB).
+    inflight = None
+    n_lanes = args.frames_in_flight if (split and use_flags) else 1
+    if n_lanes > 1:
+        lanes = [lane0]
+        for _ in range(n_lanes - 1):
+            lane_stream = torch.cuda.Stream(device=local_rank)
+            lr = Rig(args, args.config, torch, dist, rank, world, local_rank, lane_stream, scene=scene)
+            if args.equal_rows or args.split_rows:
+                lr.r.set_bin_rows(*rows)
+            else:
+                lr.r.set_bin_range(*rows)
+            lanes.append(Lane(lr))
+        plain = api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES
+
+        def pipelined(steps):
+            rig.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(rig.stream)
+            for ln in lanes[1:]:
+                ln.stream.wait_event(e0)
+            for k in range(steps):
+                ln = lanes[k % n_lanes]
+                ln.render(k, plain)
+                ln.after_frame()
+            for ln in lanes[1:]:
+                done = torch.cuda.Event()
+                done.record(ln.stream)
+                rig.stream.wait_event(done)
+            e1.record(rig.stream)
+            rig.barrier()
+            return e0.elapsed_time(e1)
+
+        pipelined(max(args.warmup, n_lanes) * n_lanes)
+        pipe_ms = max_over_ranks(rig, pipelined(args.steps))
+        t0 = time.perf_counter()
+        n_sus, sus_ms = 0, 0.0
+        while time.perf_counter() - t0 < args.sustained_seconds:  # rank 0's clock decides for everybody
+            sus_ms += pipelined(16 * n_lanes)
+            n_sus += 16 * n_lanes
+            stop = torch.tensor([1.0 if time.perf_counter() - t0 >= args.sustained_seconds else 0.0], device="cuda")
+            dist.broadcast(stop, src=0)
+            if float(stop.item()) > 0:
+                break
+        sus_ms = max_over_ranks(rig, sus_ms)
+        inflight = {"frames_in_flight": n_lanes, "ms_per_step": pipe_ms / args.steps,
+                    "value": 1000.0 * args.steps / pipe_ms,
+                    "sustained": {"frames": n_sus, "device_s": round(sus_ms / 1e3, 3),
+                                  "value": round(n_sus / (sus_ms / 1e3), 3), "unit": "frames/s"}}
+        for ln in lanes[1:]:
+            ln.close()
+            ln.rig.close()
     clocks = sampler.stop()
 
     # per-stage CUDA-event times: the same frames again, same L2 flush, this time with an event after every
@@ -485,6 +558,39 @@ def run_ours(args):
                      flags=api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES)
 
     e2e_value = e2e_run(rig, e2e_frame, e2e_steps, 1)
+    e2e_extra = {}
+    if split:
+        # The frame gathered in HOST memory instead: one image shared by the processes (POSIX shared memory, pinned
+        # in every process), every rank copies its own bins into it over its own PCIe link
+        # (LUCID_RENDER_OWNED_BINS_ONLY) -- no device gathers the frame first, the 33 MB read-back of a 4K frame is
+        # spread over the ranks' links.  Checked against the frame gathered on rank 0.
+        from lucid_b200 import multigpu
+        e2e_extra["gathered_on_rank0"] = {"value": round(e2e_value, 3), "unit": "frames/s",
+                                          "d2h_bytes_per_step": int(width * height * 4)}
+        render(0, api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES)
+        after_frame()
+        rig.barrier()
+        ref_img = r.read_image() if rank == 0 else None
+        name = "lucid_b200_e2e_%s" % os.environ.get("MASTER_PORT", "0")
+        shared = None
+        if rank == 0:
+            shared = multigpu.SharedHostImages(name, width, height, 2, create=True)
+        rig.barrier()
+        if rank != 0:
+            shared = multigpu.SharedHostImages(name, width, height, 2, create=False)
+        shared.pin()
+        host_flags = api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES | api.RENDER_OWNED_BINS_ONLY
+
+        def e2e_frame_host(k):
+            r.render(rig.config_for(view_of(k)), inst, cols, rects, out=shared.pointer(k & 1), flags=host_flags)
+
+        e2e_value = e2e_run(rig, e2e_frame_host, e2e_steps, 1)
+        if rank == 0:
+            e2e_extra["delivery"] = ("every rank copies its own bins into one host image shared by the processes "
+                                     "(/dev/shm, page-locked), over its own PCIe link")
+            e2e_extra["verified_against_gathered_frame"] = bool(np.array_equal(shared.array[(e2e_steps - 1) & 1], ref_img))
+        rig.barrier()
+        shared.close()
 
     # counters of one frame for the roofline arithmetic, and the frame's depth complexity
     r.render(rig.config_for(0), inst, cols, rects, flags=api.RENDER_FRAG_COUNTS)
@@ -493,17 +599,13 @@ def run_ours(args):
     depth = depth_complexity(r.read_frag_counts()) if not split else None
 
     tris_per_frame = 2 * stats["input_quads"]
-    ms_per_step = total_ms / args.steps
+    serial_ms_per_step = total_ms / args.steps
+    ms_per_step = serial_ms_per_step if inflight is None else inflight["ms_per_step"]
     value = 1000.0 / ms_per_step
 
     views = None
     if split and not args.no_views:
-        if peer_ptr is not None:
-            r.ipc_close_image(peer_ptr)
-            peer_ptr = None
-        if rank != 0 and flags_ptr is not None:
-            r.ipc_close_image(flags_ptr)
-            flags_ptr = None
+        lane0.close()
         rig.close()
         views = run_views(args, torch, dist, rank, world, local_rank, stream, 1)
 
@@ -516,7 +618,7 @@ def run_ours(args):
         stage_ms["frame_with_stage_events"] = round(float(stage[7]), 4)
         stage_ms["frame"] = round(frame_ms, 4)  # timed frames: first launch -> last kernel done, the library's own events
         # the library's events and ours are on one stream: our bracket can only be the wider one
-        assert ms_per_step >= 0.98 * frame_ms, (ms_per_step, frame_ms)
+        assert serial_ms_per_step >= 0.98 * frame_ms, (serial_ms_per_step, frame_ms)
         raster_ms = float(stage[4] + stage[5] + stage[6])
         fracs = {
             "setup": ab["setup"] / (stage[0] * 1e-3) / 1e9 / peak if stage[0] > 0 else None,
@@ -577,9 +679,10 @@ def run_ours(args):
                          # kernels are bound by instruction issue, not by HBM
                          "traffic_source": traffic_src, "sm_issue_active_pct": issue_pct,
                          "per_stage_frac": {k: (round(v, 4) if v is not None else None) for k, v in fracs.items()}},
-            "e2e": {"value": round(e2e_value, 3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(len(inst) * 36 + 352),
-                    "d2h_bytes_per_step": int(width * height * 4 + info.size * 4)},
+            "e2e": dict({"value": round(e2e_value, 3), "unit": "frames/s",
+                         "h2d_bytes_per_step": int((len(inst) * 36 + 352) * (world if split else 1)),
+                         "d2h_bytes_per_step": int(width * height * 4 + info.size * 4 * (world if split else 1))},
+                        **e2e_extra),
             "sustained": sustained,
             # k_frame_begin, k_quad_cull, k_tri_setup, k_bin_count, k_bin_scan, k_bin_dispatch, k_raster_bins,
             # k_block_sort, k_block_shade (+ k_info_out when LucidInfo is read back)
@@ -587,16 +690,25 @@ def run_ours(args):
             "clocks": clocks,
             "wall_s": round(wall, 3),
         }
+        if inflight is not None:
+            # value / ms_per_step are the pipelined run's; the classic loop (one handle, one frame after the other,
+            # L2 flushed in between) stays beside it, and `sustained`, `stage_ms`, `rank_frame_ms` describe that loop
+            line["frames_in_flight"] = inflight["frames_in_flight"]
+            line["one_frame_at_a_time"] = {"value": round(1000.0 / serial_ms_per_step, 3), "unit": "frames/s",
+                                           "ms_per_step": round(serial_ms_per_step, 4),
+                                           "ms_per_step_median": round(step_median, 4), "sustained": sustained}
+            line["sustained"] = inflight["sustained"]
+            line["config"]["l2"] = ("no flush between the pipelined frames: a rank's frame reads several hundred MB of "
+                                    "geometry and records, the L2 holds 126 MB; the one-frame-at-a-time loop flushes "
+                                    "with a 256 MiB memset between timed frames (untimed)")
+            line["config"]["parallelism"] += "; %d frames in flight (handles on separate streams)" % inflight["frames_in_flight"]
         if views is not None:
             line["views"] = views
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(scene, args)
         print(json.dumps(line), flush=True)
-    if peer_ptr is not None:
-        r.ipc_close_image(peer_ptr)
     if views is None:
-        if split and rank != 0 and flags_ptr is not None:
-            r.ipc_close_image(flags_ptr)
+        lane0.close()
         rig.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -696,6 +808,8 @@ def main():
     ap.add_argument("--completion", default="flags", choices=["flags", "allreduce"],
                     help="--mode split: how rank 0 learns that every strip of a frame has landed")
     ap.add_argument("--balance-iters", type=int, default=7, help="--mode split: feedback steps of the range balancing")
+    ap.add_argument("--frames-in-flight", type=int, default=3,
+                    help="--mode split: renderer handles per rank rendering alternate frames on their own streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -42,6 +42,11 @@ enum {
 									 compacted in input order by k_instance_select).  Conservative, so the
 									 visible quads with their slots, the per-bin lists and the pixels are
 									 unchanged; num_rejected_quads then only covers the processed instances */
+	,
+	LUCID_RENDER_OWNED_BINS_ONLY = 32 /* LUCID_MEM_HOST with a bin-row split: only the pixels of the owned bins are
+									 copied to out_rgba8 (which has the layout of the whole image) -- every device
+									 of a split delivers its own strip over its own PCIe link, e.g. into host
+									 memory shared by the processes, instead of one device gathering the frame */
 };
 
 /* LucidRenderer::exConstruct(device, compiler, opts, view_size), src/lucid_renderer.cpp:186-317.

@@ -19,6 +19,7 @@ LUCID_INFO_U32_SIZE = 1152
 COUNTS_PER_BIN = 10
 MEM_HOST, MEM_DEVICE, MEM_NONE = 0, 1, 2
 RENDER_ASYNC, RENDER_SKIP_INFO, RENDER_FRAG_COUNTS, RENDER_NO_STAGE_TIMES, RENDER_CULL_INSTANCES = 1, 2, 4, 8, 16
+RENDER_OWNED_BINS_ONLY = 32  # MEM_HOST read-back of the owned bins only (bin-row split)
 
 OPT_TIMERS = 1 << 4
 OPT_ADDITIVE_BLENDING = 1 << 5

@@ -665,7 +665,29 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 		const int b = r->image_index;
 		CU(cudaEventRecord(r->render_done[b], st));
 		CU(cudaStreamWaitEvent(r->copy_stream, r->render_done[b], 0));
-		if(pitch_bytes == (size_t)p.width * 4)
+		if((flags & LUCID_RENDER_OWNED_BINS_ONLY) && (p.bin_begin > 0 || p.bin_end < p.bin_count)) {
+			// the owned bins [bin_begin, bin_end) in row-major order: part of a first bin row, whole rows, part of a last one
+			auto copyBins = [&](int by0, int by1, int bx0, int bx1) -> cudaError_t { // bin rows [by0, by1), bin columns [bx0, bx1)
+				const int x0 = bx0 * BIN_SIZE, x1 = std::min(p.width, bx1 * BIN_SIZE);
+				const int y0 = by0 * BIN_SIZE, y1 = std::min(p.height, by1 * BIN_SIZE);
+				if(x1 <= x0 || y1 <= y0)
+					return cudaSuccess;
+				return cudaMemcpy2DAsync((char *)out_rgba8 + (size_t)y0 * pitch_bytes + (size_t)x0 * 4, pitch_bytes,
+										 r->image + (size_t)y0 * p.width + x0, (size_t)p.width * 4, (size_t)(x1 - x0) * 4,
+										 (size_t)(y1 - y0), cudaMemcpyDeviceToHost, r->copy_stream);
+			};
+			const int nbx = p.bin_count_x, last = p.bin_end - 1;
+			const int by0 = p.bin_begin / nbx, bx0 = p.bin_begin % nbx, by1 = last / nbx, bx1 = last % nbx + 1;
+			if(p.bin_end > p.bin_begin) {
+				if(by0 == by1) {
+					CU(copyBins(by0, by0 + 1, bx0, bx1));
+				} else {
+					CU(copyBins(by0, by0 + 1, bx0, nbx));
+					CU(copyBins(by0 + 1, by1, 0, nbx));
+					CU(copyBins(by1, by1 + 1, 0, bx1));
+				}
+			}
+		} else if(pitch_bytes == (size_t)p.width * 4)
 			CU(cudaMemcpyAsync(out_rgba8, r->image, pitch_bytes * p.height, cudaMemcpyDeviceToHost, r->copy_stream));
 		else
 			CU(cudaMemcpy2DAsync(out_rgba8, pitch_bytes, r->image, (size_t)p.width * 4, (size_t)p.width * 4,

@@ -128,3 +128,52 @@ def reduce_info(dist, info, bin_count: int):
     promoted = int(np.count_nonzero(member[0] * member[1]))
     out_head[5:10] = [bin_count - low.size - (high.size - promoted), 0, low.size, 0, high.size]
     return np.concatenate([out_head, out.reshape(-1)]).astype(np.uint32)
+
+
+class SharedHostImages:
+    """Host images shared by the processes of a split (POSIX shared memory under /dev/shm), page-locked in every
+    process so that each device copies its own strip of a frame straight into them over its own PCIe link
+    (LucidRenderer.render(out=..., flags=RENDER_OWNED_BINS_ONLY)): the frame is gathered in host memory, no device
+    gathers it first.  `count` images of height x width RGBA8; rank 0 creates (and unlinks on close), the others attach."""
+
+    def __init__(self, name: str, width: int, height: int, count: int, create: bool):
+        import mmap
+        import os
+        self.path = "/dev/shm/" + name
+        self.width, self.height, self.count = width, height, count
+        self.nbytes = width * height * 4 * count
+        self._owner = create
+        fd = os.open(self.path, os.O_RDWR | (os.O_CREAT if create else 0), 0o600)
+        try:
+            if create:
+                os.ftruncate(fd, self.nbytes)
+            self._mm = mmap.mmap(fd, self.nbytes)
+        finally:
+            os.close(fd)
+        self.array = np.frombuffer(self._mm, np.uint32).reshape(count, height, width)
+        self._registered = False
+
+    def pin(self):
+        """cudaHostRegister in this process (needs torch with CUDA); copies into unpinned memory still work, slowly."""
+        import torch
+        rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed: {rc}")
+        self._registered = True
+
+    def pointer(self, index: int) -> int:
+        return self.array.ctypes.data + index * self.width * self.height * 4
+
+    def close(self):
+        import os
+        if self._registered:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            self._registered = False
+        self.array = None
+        try:
+            self._mm.close()
+        except BufferError:
+            pass
+        if self._owner and os.path.exists(self.path):
+            os.unlink(self.path)

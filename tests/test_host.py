@@ -186,3 +186,18 @@ def test_committed_dram_traffic_file_serves_the_bench_line():
         import warnings
         warnings.warn("profiles/dram_traffic.json is older than the kernel sources: bench.py reports traffic = null "
                       "until tools/gpu_round.sh has taken a new capture")
+
+
+def test_shared_host_images_are_one_memory():
+    """multigpu.SharedHostImages: what one process of a split writes into the shared frame, the others see."""
+    from lucid_b200 import multigpu
+    name = "lucid_b200_test_%d" % os.getpid()
+    a = multigpu.SharedHostImages(name, 64, 32, 2, create=True)
+    try:
+        b = multigpu.SharedHostImages(name, 64, 32, 2, create=False)
+        a.array[1, 3, 5] = 0xCAFE
+        assert b.array[1, 3, 5] == 0xCAFE and b.pointer(1) - b.pointer(0) == 64 * 32 * 4
+        b.close()
+    finally:
+        a.close()
+    assert not os.path.exists("/dev/shm/" + name)
