@@ -808,7 +808,7 @@ def main():
     ap.add_argument("--completion", default="flags", choices=["flags", "allreduce"],
                     help="--mode split: how rank 0 learns that every strip of a frame has landed")
     ap.add_argument("--balance-iters", type=int, default=7, help="--mode split: feedback steps of the range balancing")
-    ap.add_argument("--frames-in-flight", type=int, default=3,
+    ap.add_argument("--frames-in-flight", type=int, default=5,
                     help="--mode split: renderer handles per rank rendering alternate frames on their own streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

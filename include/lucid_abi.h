@@ -79,6 +79,19 @@ enum {
 	LUCID_OPT_OPAQUE_PREPASS = 1 << 8
 };
 
+/* LUCID_OPT_DEBUG_RASTER (the reference's raster_low_debug / raster_high_debug pipelines, src/lucid_renderer.cpp:
+ * 147-158,263-296): the block stage checks what the `DEBUG_ENABLED` code of the shaders checks and writes a record per
+ * violation (lucid_read_debug_records):
+ *   LUCID_DEBUG_EMPTY_COVERAGE    a block-list entry without a covered pixel (raster_low.glsl:125-126,
+ *                                 raster_high.glsl:184-185): values 0, 0, 0, 0 -- "bx_mask is invalid"
+ *   LUCID_DEBUG_UNSORTED          sort keys not strictly increasing after the sort (raster_low.glsl:154-163,
+ *                                 raster_high.glsl:196-203): values i, tri_count, prev_value, value
+ * A record is {check id, thread of the CTA, work item (bin << 6 | HIGH << 5 | block), four values}; the reference's
+ * records carry line id, local index and work-group index in those places. */
+enum { LUCID_DEBUG_EMPTY_COVERAGE = 1, LUCID_DEBUG_UNSORTED = 2 };
+#define LUCID_DEBUG_RECORD_WORDS 7
+#define LUCID_DEBUG_MAX_RECORDS 65536
+
 typedef struct LucidVec4 {
 	float x, y, z, w;
 } LucidVec4;

@@ -141,6 +141,11 @@ int lucid_image_pointer(lucid_renderer *r, void **device_ptr, size_t *pitch_byte
 int lucid_composite_to(lucid_renderer *r, void *dst_rgba8_device, size_t pitch_bytes);
 /* 64-byte cudaIpcMemHandle_t of the renderer-owned image, to be sent to peer processes */
 int lucid_ipc_export_image(lucid_renderer *r, void *handle64);
+/* LUCID_OPT_DEBUG_RASTER: the records of the last frame (include/lucid_abi.h), up to max_records of them into dst
+ * (LUCID_DEBUG_RECORD_WORDS words each); *num_records = how many the frame produced (may exceed what was stored).
+ * Replaces printDebugData / shaderDebugDownloadResults, src/lucid_renderer.cpp:112-117. */
+int lucid_read_debug_records(lucid_renderer *r, uint32_t *dst, int32_t max_records, int32_t *num_records);
+
 /* Test hook: n samples (u, v, lod triples, host memory) of the texture in `slot`, fetched by the texture unit
  * exactly as the shading kernel fetches them (tex2DLod); out_rgba receives 4 floats per sample.  Pins the CPU
  * checker's restatement of the unit's filter arithmetic against the hardware (tests/test_gpu_parity.py). */

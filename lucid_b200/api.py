@@ -21,6 +21,7 @@ MEM_HOST, MEM_DEVICE, MEM_NONE = 0, 1, 2
 RENDER_ASYNC, RENDER_SKIP_INFO, RENDER_FRAG_COUNTS, RENDER_NO_STAGE_TIMES, RENDER_CULL_INSTANCES = 1, 2, 4, 8, 16
 RENDER_OWNED_BINS_ONLY = 32  # MEM_HOST read-back of the owned bins only (bin-row split)
 
+OPT_DEBUG_RASTER = 1 << 3  # the reference's raster_*_debug pipelines: lucid_read_debug_records
 OPT_TIMERS = 1 << 4
 OPT_ADDITIVE_BLENDING = 1 << 5
 OPT_VISUALIZE_ERRORS = 1 << 6
@@ -89,7 +90,7 @@ C_ABI_SYMBOLS = [
     "lucid_debug_sample_texture", "lucid_sync_pointer", "lucid_ipc_export_sync", "lucid_signal", "lucid_wait_flags", "lucid_set_frame_gate",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
     "lucid_host_camera_matrices", "lucid_host_build_instances", "lucid_host_packet_size",
-    "lucid_quadgen", "lucid_quadgen_last_error",
+    "lucid_quadgen", "lucid_quadgen_last_error", "lucid_read_debug_records",
 ]
 
 
@@ -406,6 +407,13 @@ class LucidRenderer:
     def read_image_into(self, host_ptr: int, pitch: int | None = None):
         self._check(self._lib.lucid_read_image(self._h, C.c_void_p(host_ptr), pitch or self.width * 4),
                     "lucid_read_image")
+
+    def read_debug_records(self, max_records: int = 4096):
+        """OPT_DEBUG_RASTER: (records [n, 7] uint32 = check id, thread, work item, four values; number produced)."""
+        out = np.zeros((max_records, 7), np.uint32)
+        n = C.c_int32(0)
+        self._check(self._lib.lucid_read_debug_records(self._h, _ptr(out), max_records, C.byref(n)), "lucid_read_debug_records")
+        return out[:min(n.value, max_records)], n.value
 
     def read_frag_counts(self) -> np.ndarray:
         out = np.zeros((self.height, self.width), np.uint32)

@@ -296,6 +296,17 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &r->d_active_instances, (size_t)LUCID_MAX_INSTANCES + 1));
 	CUC(devAlloc(r, &r->d_sync, (size_t)LUCID_SYNC_FLAGS));
 	CUC(cudaMemsetAsync(r->d_sync, 0, LUCID_SYNC_FLAGS * 4, r->stream));
+	p.debug_records = nullptr;
+	if(p.opts & LUCID_OPT_DEBUG_RASTER) {
+		const size_t words = 2 + (size_t)LUCID_DEBUG_MAX_RECORDS * LUCID_DEBUG_RECORD_WORDS;
+		CUC(devAlloc(r, &p.debug_records, words));
+		CUC(cudaMemsetAsync(p.debug_records, 0, words * 4, r->stream));
+		const u32 cap = LUCID_DEBUG_MAX_RECORDS;
+		CUC(cudaMemcpyAsync(p.debug_records, &cap, 4, cudaMemcpyHostToDevice, r->stream));
+		// test hook: the sort of the first work item's list is undone by one swap, so the UNSORTED check has something to find
+		const char *inject = getenv("LUCID_DEBUG_RASTER_INJECT");
+		p.debug_inject = inject && inject[0] == '1';
+	}
 	for(int i = 0; i < lucid_renderer::NUM_STAGING; i++) {
 		CUC(devAlloc(r, &r->d_inst_ring[i], STAGING_BYTES));
 		CUC(cudaEventCreateWithFlags(&r->upload_ready[i], cudaEventDisableTiming));
@@ -630,6 +641,8 @@ int lucid_render(lucid_renderer *r, const LucidConfig *config, const LucidInstan
 	CU(cudaEventRecord(ev[0], st));
 	// per-frame clears (setupInputData): LucidInfo and the first 6 per-bin arrays (lucid_renderer.cpp:437)
 	launchFrameBegin(p, st);
+	if(p.debug_records)
+		CU(cudaMemsetAsync(p.debug_records + 1, 0, 4, st));
 	launchQuadSetup(p, cfg, st);
 	if(stage_events)
 		CU(cudaEventRecord(ev[1], st));
@@ -856,6 +869,23 @@ int lucid_read_image(lucid_renderer *r, void *dst, size_t pitch_bytes) {
 		return fail(r, LUCID_E_STATE, "lucid_read_image: the last frame was rendered into the caller's device image");
 	CU(cudaMemcpy2D(dst, pitch_bytes, r->image, (size_t)r->p.width * 4, (size_t)r->p.width * 4,
 					r->p.height, cudaMemcpyDeviceToHost));
+	return LUCID_OK;
+}
+
+int lucid_read_debug_records(lucid_renderer *r, uint32_t *dst, int32_t max_records, int32_t *num_records) {
+	if(!r || !num_records || max_records < 0 || (max_records > 0 && !dst))
+		return LUCID_E_INVALID;
+	if(!r->p.debug_records)
+		return fail(r, LUCID_E_STATE, "lucid_read_debug_records: the renderer was created without LUCID_OPT_DEBUG_RASTER");
+	int rc = lucid_wait(r);
+	if(rc)
+		return rc;
+	u32 n = 0;
+	CU(cudaMemcpy(&n, r->p.debug_records + 1, 4, cudaMemcpyDeviceToHost));
+	*num_records = (int32_t)std::min<u32>(n, 0x7fffffffu);
+	const size_t stored = std::min(std::min((size_t)n, (size_t)max_records), (size_t)LUCID_DEBUG_MAX_RECORDS);
+	if(stored)
+		CU(cudaMemcpy(dst, r->p.debug_records + 2, stored * LUCID_DEBUG_RECORD_WORDS * 4, cudaMemcpyDeviceToHost));
 	return LUCID_OK;
 }
 

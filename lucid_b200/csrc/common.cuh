@@ -106,6 +106,10 @@ struct Params {
 	// work items -- [bin][half-block 0..31 = (4-row group, 8-pixel column)][pixel 0..31]; k_block_sort writes,
 	// k_block_shade reads; null without the option
 	float *opaque_depth;
+	// LUCID_OPT_DEBUG_RASTER: [0] capacity in records, [1] records written (may run past the capacity), then records of
+	// LUCID_DEBUG_RECORD_WORDS words (the reference's `_debug` shader variants write fwk's ShaderDebugRecord)
+	u32 *debug_records;
+	bool debug_inject; // test hook of the debug variant (LUCID_DEBUG_RASTER_INJECT=1 at lucid_create)
 	// textures: the two atlases as CUDA mipmapped arrays behind texture objects (RGBA8 unorm, normalised coordinates,
 	// wrap, linear + mip-linear); 0 = no texture in the slot
 	int tex_width[2], tex_height[2], tex_levels[2];
@@ -264,6 +268,18 @@ __device__ __forceinline__ void timerMark(PhaseTimer &t, u32 *slots, int idx) {
 			atomicAdd(slots + idx, (u32)((unsigned long long)(now - t.t0) >> 4));
 		t.t0 = now;
 	}
+}
+
+// DEBUG_RECORD of the reference's `_debug` shader variants (libfwk shader_debug: line, thread, work group, four
+// values), here: check id, lane, work item, four values.  Only called under LUCID_OPT_DEBUG_RASTER.
+__device__ __forceinline__ void debugRecord(const Params &p, u32 check_id, u32 item, u32 v0, u32 v1, u32 v2, u32 v3) {
+	if(!p.debug_records)
+		return;
+	const u32 n = atomicAdd(p.debug_records + 1, 1u);
+	if(n >= p.debug_records[0])
+		return;
+	u32 *dst = p.debug_records + 2 + (size_t)n * LUCID_DEBUG_RECORD_WORDS;
+	dst[0] = check_id, dst[1] = threadIdx.x, dst[2] = item, dst[3] = v0, dst[4] = v1, dst[5] = v2, dst[6] = v3;
 }
 
 // ---- programmatic dependent launch -----------------------------------------------------------

@@ -615,6 +615,8 @@ void launchRaster(const Params &p, const LucidConfig &cfg, cudaStream_t stream, 
 		cudaEventRecord(ev[1], stream);
 	const bool segments = (p.opts & (LUCID_OPT_ALPHA_THRESHOLD | LUCID_OPT_ADDITIVE_BLENDING | LUCID_OPT_VISUALIZE_ERRORS)) ==
 						  LUCID_OPT_ALPHA_THRESHOLD;
+	// (fewer persistent CTAs per SM, to leave room for the kernels of a neighbouring frame in flight, was measured:
+	// 4 or 5 instead of 7 CTAs change nothing with three frames in flight and cost 10-20 % with one, profiles/r2u_*)
 	const int grid = num_sms * SHADE_MIN_CTAS;
 	if(segments)
 		launchPDL((k_block_shade<false, true>), grid, BLOCK_WARPS * 32, (size_t)smem_ldg, stream, p, cfg);

@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 					float cpy = float(cy) * scale + (float(ry * 4) + float(pos_y));
 					depth = blockDepth(dq[u], cpx, cpy, float(0x7fffe)) << 14;
 					frag_acc += (u32)nf;
+					if(nf == 0 && p.debug_records)
+						debugRecord(p, LUCID_DEBUG_EMPTY_COVERAGE, item, 0, 0, 0, 0);
 					if(cull_any && nearestOnTile(dq[u], tile_y) < zfar[0])
 						depth = 0xffffffffu;
 				} else {
@@ -277,6 +279,8 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 					float cpx = cx * scale + float(pos_x + cx8), cpy = cy * scale + float(pos_y + ry * 8);
 					depth = blockDepth(dq[u], cpx, cpy, float(0x3ffffe)) << 10;
 					frag_acc += (u32)(nf0 + nf1);
+					if(nf0 + nf1 == 0 && p.debug_records)
+						debugRecord(p, LUCID_DEBUG_EMPTY_COVERAGE, item, 0, 0, 0, 0);
 					if(PREPASS && count <= 3)
 						depth = 0; // unsorted lists keep their order when hidden entries are cut out of them
 					if(cull_any && (nf0 == 0 || nearestOnTile(dq[u], tile_y) < zfar[0]) &&
@@ -305,6 +309,28 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 				warpSortLarge(keys, count, s_keys[warp]);
 			else
 				warpSortShared(keys, count);
+			if(p.debug_records) {
+				// "making sure that tris are properly ordered" (raster_low.glsl:154-163, raster_high.glsl:196-203)
+				if(p.debug_inject && index == 0 && count > 1 && lane == 0) {
+					volatile u32 *vk = keys;
+					const u32 t = vk[0];
+					vk[0] = vk[1], vk[1] = t;
+				}
+				__syncwarp();
+				for(int i = lane; i < count; i += 32) {
+					const u32 value = large ? __ldcg(keys + i) : keys[i];
+					const u32 prev_value = i == 0 ? 0u : large ? __ldcg(keys + i - 1) : keys[i - 1];
+					if(value <= prev_value && i > 0)
+						debugRecord(p, LUCID_DEBUG_UNSORTED, item, (u32)i, (u32)count, prev_value, value);
+				}
+				__syncwarp();
+				if(p.debug_inject && index == 0 && count > 1 && lane == 0) {
+					volatile u32 *vk = keys;
+					const u32 t = vk[0];
+					vk[0] = vk[1], vk[1] = t;
+				}
+				__syncwarp();
+			}
 			// depth ties by triangle index: the triangle of a list position is looked up in the list itself
 			if(high)
 				warpFixDepthTies(keys, kept, slot_bits,

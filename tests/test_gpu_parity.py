@@ -140,6 +140,44 @@ def test_opaque_prepass_full_size_architecture():
         r.close()
 
 
+@pytest.mark.parametrize("name", ["soup", "soup_close", "meshlets", "arch", "hairball", "planes"])
+def test_debug_raster_variant_finds_nothing_on_a_correct_frame(name, small):
+    """LUCID_OPT_DEBUG_RASTER (the reference's raster_*_debug pipelines): the checks of the shaders' DEBUG_ENABLED code
+    -- no block-list entry without coverage (raster_low.glsl:125-126), keys strictly increasing after the sort
+    (raster_low.glsl:154-163) -- run over every list of the frame and record nothing; the frame is the plain one."""
+    sc = small[name]
+    r, img = pu.run_cuda(sc, opts=api.OPT_DEBUG_RASTER)
+    r0, img0 = pu.run_cuda(sc)
+    try:
+        recs, n = r.read_debug_records()
+        assert n == 0, recs[:4]
+        assert np.array_equal(img, img0) and np.array_equal(r.read_info()[60:63], r0.read_info()[60:63])
+    finally:
+        r.close()
+        r0.close()
+
+
+def test_debug_raster_variant_records_a_violation(small, monkeypatch):
+    """The recording path itself: with the test hook the sorted keys of the frame's first work item are swapped once
+    before the check, which then writes DEBUG_RECORD(i, tri_count, prev_value, value) for position 1."""
+    monkeypatch.setenv("LUCID_DEBUG_RASTER_INJECT", "1")
+    sc = small["soup_close"]
+    r, img = pu.run_cuda(sc, opts=api.OPT_DEBUG_RASTER)
+    monkeypatch.delenv("LUCID_DEBUG_RASTER_INJECT")
+    r0, img0 = pu.run_cuda(sc)
+    try:
+        recs, n = r.read_debug_records()
+        assert n >= 1 and (recs[:, 0] == 2).all()  # LUCID_DEBUG_UNSORTED
+        first = recs[recs[:, 3] == 1][0]
+        assert first[4] > 3 and first[6] <= first[5]  # a list the sort applies to; value <= prev_value
+        assert np.array_equal(img, img0)  # the swap is undone after the check
+        with pytest.raises(RuntimeError):
+            r0.read_debug_records()
+    finally:
+        r.close()
+        r0.close()
+
+
 def test_timers_option(small):
     """LUCID_OPT_TIMERS (the reference's `_timers` shader variants, shared/timers.glsl, lucid_renderer.cpp:754-762):
     the phases' clock ticks land in LucidInfo.setup_timers / bin_dispatcher_timers / raster_timers in the reference's

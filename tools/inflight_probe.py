@@ -16,7 +16,8 @@ ci = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 sc = scenes.get_config(ci)
 cfg, inst, cols, rects = api.prepare_frame(sc)
-streams = [torch.cuda.Stream() for _ in range(3)]
+NH = int(os.environ.get('PROBE_HANDLES', '3'))
+streams = [torch.cuda.Stream() for _ in range(NH)]
 rs = [api.LucidRenderer(sc["width"], sc["height"], 0, 0, stream=s.cuda_stream) for s in streams]
 for r in rs:
     r.set_scene(sc)
@@ -36,12 +37,12 @@ def run(handles, n):
 
 rs[0].render(cfg, inst, cols, rects)
 cost = rs[0].read_bin_costs().astype(np.float64)
-print(f"config {ci} full frame: 1 handle {run([0], frames):.1f} frames/s, 2 handles {run([0, 1], frames):.1f}, 3 handles {run([0, 1, 2], frames):.1f}")
+print(f"config {ci} full frame:", ", ".join(f"{h} handles {run(list(range(h)), frames):.1f} frames/s" for h in range(1, NH + 1)))
 ranges = multigpu.split_bins(rs[0].bin_count, 8, cost)
 for q in (0, 3, 7):
     for r in rs:
         r.set_bin_range(*ranges[q])
-    a, b, c = run([0], frames * 4), run([0, 1], frames * 4), run([0, 1, 2], frames * 4)
-    print(f"rank {q} of 8, bins {ranges[q]}: 1 handle {a:.1f} frames/s ({1e3 / a:.3f} ms), 2 handles {b:.1f} ({1e3 / b:.3f} ms), 3 handles {c:.1f} ({1e3 / c:.3f} ms)")
+    res = [run(list(range(h)), frames * 4) for h in range(1, NH + 1)]
+    print(f"rank {q} of 8, bins {ranges[q]}:", ", ".join(f"{h + 1} handles {v:.1f} frames/s ({1e3 / v:.3f} ms)" for h, v in enumerate(res)))
 for r in rs:
     r.close()
