@@ -684,9 +684,10 @@ def run_ours(args):
                          "d2h_bytes_per_step": int(width * height * 4 + info.size * 4 * (world if split else 1))},
                         **e2e_extra),
             "sustained": sustained,
-            # k_frame_begin, k_quad_cull, k_tri_setup, k_bin_count, k_bin_scan, k_bin_dispatch, k_raster_bins,
-            # k_block_sort, k_block_shade (+ k_info_out when LucidInfo is read back)
-            "gpu_launches": int(9 * args.steps),
+            # k_frame_begin, k_instance_select, k_quad_cull, k_tri_setup, k_bin_count, k_bin_scan, k_bin_dispatch,
+            # k_raster_bins, k_block_sort, k_block_shade (+ k_info_out when LucidInfo is read back; the split adds
+            # the frame gate / flag kernels of sync.cu)
+            "gpu_launches": int(10 * args.steps),
             "clocks": clocks,
             "wall_s": round(wall, 3),
         }

@@ -64,7 +64,16 @@ typedef struct LucidCreateInfo {
 									 frame; 0 -> max(16 * max_visible_quads, 2^22).  A frame that needs more paints the
 									 bins that did not fit red and reports LUCID_E_LIMIT (the reference bounds the same
 									 lists per work group: raster_low.glsl:22-32, raster_high.glsl:35-44) */
+	uint32_t flags;				  /* LUCID_CREATE_* */
 } LucidCreateInfo;
+
+enum {
+	/* Block lists (the per-bin lists between k_raster_bins and k_block_sort) in a pool sized by max_block_entries
+	 * (16 bytes per entry) instead of a fixed 1 MiB slot per bin (8 GiB at 3840x2160): every bin is walked twice --
+	 * a counting pass, one allocation of exactly its entries, a filling pass -- so the list stage takes about twice
+	 * as long.  For handles that have to be small: several per device, devices with less memory. */
+	LUCID_CREATE_COMPACT_LISTS = 1
+};
 
 int lucid_create(const LucidCreateInfo *info, lucid_renderer **out);
 void lucid_destroy(lucid_renderer *r);

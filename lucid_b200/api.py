@@ -73,7 +73,10 @@ class CreateInfo(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("opts", C.c_uint32),
                 ("max_visible_quads", C.c_int32), ("max_dispatches", C.c_int32), ("device", C.c_int32),
                 ("stream", C.c_void_p), ("bin_row_begin", C.c_int32), ("bin_row_end", C.c_int32),
-                ("max_block_entries", C.c_uint32)]
+                ("max_block_entries", C.c_uint32), ("flags", C.c_uint32)]
+
+
+CREATE_COMPACT_LISTS = 1
 
 
 assert C.sizeof(LucidConfig) == 352 and C.sizeof(InstanceData) == 16
@@ -276,11 +279,11 @@ class LucidRenderer:
 
     def __init__(self, width: int, height: int, opts: int = 0, max_visible_quads: int = 0, device: int = 0,
                  stream: int | None = None, bin_rows: tuple[int, int] | None = None, max_dispatches: int = 0,
-                 max_block_entries: int = 0):
+                 max_block_entries: int = 0, create_flags: int = 0):
         self._lib = load_library()
         self._h = C.c_void_p()
         ci = CreateInfo(width, height, opts, max_visible_quads, max_dispatches, device, stream,
-                        bin_rows[0] if bin_rows else 0, bin_rows[1] if bin_rows else 0, max_block_entries)
+                        bin_rows[0] if bin_rows else 0, bin_rows[1] if bin_rows else 0, max_block_entries, create_flags)
         rc = self._lib.lucid_create(C.byref(ci), C.byref(self._h))
         if rc != 0:
             raise LucidError(f"lucid_create failed ({rc}): {self._lib.lucid_last_error(None).decode()}")

@@ -273,7 +273,6 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	CUC(devAlloc(r, &p.work_counters, (size_t)WORK_COUNTERS));
 	CUC(devAlloc(r, &p.bin_cost, (size_t)p.bin_count));
 	p.bin_begin = p.row_begin * p.bin_count_x, p.bin_end = p.row_end * p.bin_count_x;
-	CUC(devAlloc(r, &p.block_lists, (size_t)p.bin_count * (BIN_LIST_BYTES / sizeof(uint4))));
 	CUC(devAlloc(r, &p.block_counts, (size_t)p.bin_count * 32));
 	p.block_items_cap = (u32)p.bin_count * 32u;
 	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 5)); // one region per size class (ITEM_CLASSES)
@@ -283,6 +282,16 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 		const unsigned long long def = std::max<unsigned long long>(16ull * mvq, 1ull << 22);
 		const unsigned long long want = info->max_block_entries > 0 ? (unsigned long long)info->max_block_entries : def;
 		p.stream_capacity = (u32)std::min<unsigned long long>(want, 0x7fffffffull);
+	}
+	p.compact_lists = (info->flags & LUCID_CREATE_COMPACT_LISTS) != 0;
+	p.list_offsets = nullptr, p.list_pool_units = 0;
+	if(p.compact_lists) {
+		// a stream entry is one list record: 16 bytes in a LOW list, 8 in a HIGH list
+		p.list_pool_units = (u32)std::min<unsigned long long>(2ull * p.stream_capacity, 0xfffffff0ull);
+		CUC(devAlloc(r, &p.block_lists, (size_t)p.list_pool_units / 2 + 1));
+		CUC(devAlloc(r, &p.list_offsets, (size_t)p.bin_count * 32));
+	} else {
+		CUC(devAlloc(r, &p.block_lists, (size_t)p.bin_count * (BIN_LIST_BYTES / sizeof(uint4))));
 	}
 	CUC(devAlloc(r, &p.sorted_rec, (size_t)p.stream_capacity));
 	CUC(devAlloc(r, &p.sorted_aux, (size_t)p.stream_capacity));

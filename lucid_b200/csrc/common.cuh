@@ -93,7 +93,10 @@ struct Params {
 	u32 *work_counters;	  // WC_*: bins / sort items / shade items taken, items per size class, stream entries handed out
 	u32 *host_status;	  // pinned host word of this frame: set non-zero when the bin lists overflowed (the frame is red)
 	u64 *bin_cost;		  // per bin: warp cycles the raster kernels spent on it this frame (split balancing)
-	uint4 *block_lists;	  // per bin BIN_LIST_BYTES: 32 half-block lists (HIGH) or 16 block lists (LOW)
+	uint4 *block_lists;	  // per bin BIN_LIST_BYTES: 32 half-block lists (HIGH) or 16 block lists (LOW); compact_lists: a pool
+	u32 *list_offsets;	  // compact_lists: per bin 32 list starts in the pool, in 8-byte units
+	u32 list_pool_units;  // compact_lists: capacity of the pool in 8-byte units
+	bool compact_lists;	  // LUCID_CREATE_COMPACT_LISTS
 	int *block_counts;	  // 32 per bin: entries of each list
 	uint4 *block_items;	  // work items of the block stages (item, entries, stream offset, -): one region of block_items_cap per size class
 	u32 block_items_cap;

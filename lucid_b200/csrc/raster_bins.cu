@@ -136,13 +136,18 @@ __device__ __forceinline__ void binPhaseA(const Params &p, const BinInfo &b, uin
 struct BinShared {
 	int count[32]; // entries per half-block (HIGH) / block (LOW)
 	int holes[32]; // HIGH: columns inside a record's [first, last] range without coverage
+	int fill[32];  // COMPACT: entries written so far by the filling pass
+	u32 start[32]; // COMPACT: the list's first 8-byte unit in the pool
 	int bin_index, status;
 };
 
 // a persistent CTA takes one bin at a time: HIGH bins first (they take longest).  256 threads when there are bins for
 // every CTA slot of the device; a device that owns few bins (its share of a bin-range split) takes them with 512- or
 // 1024-thread CTAs, so that the heaviest bin -- the kernel's critical path -- is walked by 16 or 32 warps instead of 8
-template <int THREADS>
+// COMPACT (LUCID_CREATE_COMPACT_LISTS): the walk below only counts; the bin then takes exactly its entries from the list
+// pool with one atomic and a second walk fills the lists (slots by the same shared-memory atomics, so a list may come
+// out in another order than the counting pass met it: the block sort orders it anyway).
+template <int THREADS, bool COMPACT>
 __global__ void __launch_bounds__(THREADS) k_raster_bins(const __grid_constant__ Params p, u32 background) {
 	constexpr int WARPS = THREADS / 32;
 	__shared__ BinShared sh;
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(THREADS) k_raster_bins(const __grid_constant__
 					int c = __ffs(bx) - 1;
 					bx &= bx - 1;
 					int slot = atomicAdd(&sh.count[g * 4 + c], 1);
-					if(slot < MAX_BLOCK_TRIS)
+					if(!COMPACT && slot < MAX_BLOCK_TRIS)
 						recs[(g * 4 + c) * MAX_BLOCK_TRIS + slot] =
 							packLowRecord(tri_idx, mn0, mx0, mn1, mx1);
 				}
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(THREADS) k_raster_bins(const __grid_constant__
 					int c = __ffs(bx) - 1;
 					bx &= bx - 1;
 					int slot = atomicAdd(&sh.count[g * 4 + c], 1);
-					if(slot < HB_LIST_CAP)
+					if(!COMPACT && slot < HB_LIST_CAP)
 						recs[(g * 4 + c) * HB_LIST_CAP + slot] = packHighRecord(tri_idx, mn, mx);
 				}
 				while(holes) {
@@ -238,6 +243,64 @@ __global__ void __launch_bounds__(THREADS) k_raster_bins(const __grid_constant__
 			__syncthreads();
 			if(sh.status != 0)
 				continue; // finishBins (k_block_sort) paints the bin
+		}
+
+		if(COMPACT) {
+			// exactly the bin's entries from the pool (8-byte units: one per HIGH record, two per LOW record), the
+			// lists one after the other; then the walk again, this time writing
+			const int n_lists = high ? 32 : 16, units = high ? 1 : 2;
+			if(tid < 32) {
+				const int c = tid < n_lists ? sh.count[tid] * units : 0;
+				int incl = c;
+#pragma unroll
+				for(int o = 1; o < 32; o <<= 1) {
+					int t = __shfl_up_sync(0xffffffffu, incl, o);
+					if(tid >= o)
+						incl += t;
+				}
+				// an even number of units per bin: every bin starts on 16 bytes (the LOW records are 16-byte stores)
+				const int total = (__shfl_sync(0xffffffffu, incl, 31) + 1) & ~1;
+				u32 base = 0;
+				if(tid == 0 && total > 0)
+					base = atomicAdd(&p.work_counters[WC_LIST_POOL], (u32)total);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if((unsigned long long)base + (u32)total > p.list_pool_units) {
+					if(tid == 0) { // the pool is full: a red bin and LUCID_E_LIMIT, like a full sorted-entry stream
+						p.bin_flags[bin_id] |= 2u;
+						p.info->temp[1] |= 2u;
+						sh.status = 2;
+					}
+				} else {
+					sh.start[tid] = base + (u32)(incl - c);
+					sh.fill[tid] = 0;
+					p.list_offsets[bin_id * 32 + tid] = base + (u32)(incl - c);
+				}
+			}
+			__syncthreads();
+			if(sh.status != 0)
+				continue; // finishBins (k_block_sort) paints the bin
+			unsigned char *pool = reinterpret_cast<unsigned char *>(p.block_lists);
+			if(high)
+				binPhaseA<true, THREADS>(p, b, s_ring_all + warp * (PHASE_A_RING * 2), [&](bool, u32 tri_idx, int g, u32 mn, u32 mx, u32, u32, u32 bx) {
+					while(bx) {
+						int c = __ffs(bx) - 1;
+						bx &= bx - 1;
+						const int l = g * 4 + c, slot = atomicAdd(&sh.fill[l], 1);
+						if(slot < sh.count[l])
+							reinterpret_cast<uint2 *>(pool + (size_t)sh.start[l] * 8)[slot] = packHighRecord(tri_idx, mn, mx);
+					}
+				});
+			else
+				binPhaseA<false, THREADS>(p, b, s_ring_all + warp * (PHASE_A_RING * 2), [&](bool, u32 tri_idx, int g, u32 mn0, u32 mx0, u32 mn1, u32 mx1, u32 bx) {
+					while(bx) {
+						int c = __ffs(bx) - 1;
+						bx &= bx - 1;
+						const int l = g * 4 + c, slot = atomicAdd(&sh.fill[l], 1);
+						if(slot < sh.count[l])
+							reinterpret_cast<uint4 *>(pool + (size_t)sh.start[l] * 8)[slot] = packLowRecord(tri_idx, mn0, mx0, mn1, mx1);
+					}
+				});
+			__syncthreads();
 		}
 
 		// publish the non-empty blocks as work items of the block stages; empty ones only get the background.
@@ -326,14 +389,27 @@ void launchRasterBins(const Params &p, u32 background, cudaStream_t stream, int 
 	constexpr size_t ring_bytes_per_warp = PHASE_A_RING * 2 * sizeof(uint4);
 	static std::once_flag configured[64];
 	oncePerDevice(configured, [] {
-		cudaFuncSetAttribute(k_raster_bins<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * ring_bytes_per_warp));
+		cudaFuncSetAttribute((k_raster_bins<1024, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * ring_bytes_per_warp));
+		cudaFuncSetAttribute((k_raster_bins<1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * ring_bytes_per_warp));
 	});
-	if(threads == 256)
-		launchPDL(k_raster_bins<256>, num_sms * 4, 256, 8 * ring_bytes_per_warp, stream, p, background);
-	else if(threads == 512)
-		launchPDL(k_raster_bins<512>, num_sms * 2, 512, 16 * ring_bytes_per_warp, stream, p, background);
-	else
-		launchPDL(k_raster_bins<1024>, num_sms, 1024, 32 * ring_bytes_per_warp, stream, p, background);
+	auto launch = [&](auto kernel, int ctas_per_sm, int nthreads) {
+		launchPDL(kernel, num_sms * ctas_per_sm, nthreads, (size_t)(nthreads / 32) * ring_bytes_per_warp, stream, p, background);
+	};
+	if(p.compact_lists) {
+		if(threads == 256)
+			launch(k_raster_bins<256, true>, 4, 256);
+		else if(threads == 512)
+			launch(k_raster_bins<512, true>, 2, 512);
+		else
+			launch(k_raster_bins<1024, true>, 1, 1024);
+	} else {
+		if(threads == 256)
+			launch(k_raster_bins<256, false>, 4, 256);
+		else if(threads == 512)
+			launch(k_raster_bins<512, false>, 2, 512);
+		else
+			launch(k_raster_bins<1024, false>, 1, 1024);
+	}
 }
 
 } // namespace lucid

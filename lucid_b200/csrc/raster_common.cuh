@@ -34,6 +34,14 @@ constexpr u32 AUX_VARYING = 0x00ffffffu; // alpha 0 with colour bits set: never 
 __device__ __forceinline__ const int *cntc(const Params &p, int which) {
 	return p.counts + (size_t)which * p.bin_count;
 }
+// list `sub` of a bin: a fixed slot (32 x 4096 x 8 bytes per bin: HIGH lists of 4096 8-byte records, LOW lists of 256
+// 16-byte records), or -- LUCID_CREATE_COMPACT_LISTS -- where k_raster_bins put it in the pool
+__device__ __forceinline__ unsigned char *blockList(const Params &p, int bin_id, int sub, bool high) {
+	if(p.compact_lists)
+		return reinterpret_cast<unsigned char *>(p.block_lists) + (size_t)p.list_offsets[bin_id * 32 + sub] * 8;
+	return reinterpret_cast<unsigned char *>(p.block_lists) + (size_t)bin_id * BIN_LIST_BYTES +
+		   (high ? (size_t)sub * HB_LIST_CAP * 8 : (size_t)sub * MAX_BLOCK_TRIS * 16);
+}
 __device__ __forceinline__ unsigned char *binLists(const Params &p, int bin_id) {
 	return reinterpret_cast<unsigned char *>(p.block_lists) + (size_t)bin_id * BIN_LIST_BYTES;
 }
@@ -57,7 +65,7 @@ __device__ __forceinline__ int itemClass(int entries) {
 }
 // work_counters: [0] bins taken (k_raster_bins) [1] items taken by k_block_sort [2] items taken by k_block_shade
 // [3..7] items per size class [8] sorted-stream entries handed out
-constexpr int WC_BINS = 0, WC_SORT = 1, WC_SHADE = 2, WC_CLASS = 3, WC_STREAM = 8, WC_COUNT = 12;
+constexpr int WC_BINS = 0, WC_SORT = 1, WC_SHADE = 2, WC_CLASS = 3, WC_STREAM = 8, WC_LIST_POOL = 9, WC_COUNT = 12;
 
 // A work item: item = bin << 6 | high << 5 | block, its list length and the start of its slice of the sorted stream
 struct WorkItem {

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 		const int bin_y = bin_id / p.bin_count_x, bin_x = bin_id - bin_y * p.bin_count_x;
 		const int pos_x = bin_x * BIN_SIZE, pos_y = bin_y * BIN_SIZE;
 		const int cx8 = (sub & 3) * 8, ry = sub >> 2;
-		const unsigned char *list = binLists(p, bin_id) + (high ? (size_t)sub * HB_LIST_CAP * 8 : (size_t)sub * MAX_BLOCK_TRIS * 16);
+		const unsigned char *list = blockList(p, bin_id, sub, high);
 		const bool large = count > SMEM_KEYS;
 		u32 *keys = large ? large_keys : s_keys[warp];
 

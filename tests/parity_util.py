@@ -40,9 +40,10 @@ def run_oracle(scene, opts=0, camera=None, bin_rows=None, threads=8, mvq=1 << 20
     return o
 
 
-def run_cuda(scene, opts=0, camera=None, bin_rows=None, mvq=1 << 20, renderer=None):
+def run_cuda(scene, opts=0, camera=None, bin_rows=None, mvq=1 << 20, renderer=None, create_flags=0, max_block_entries=0):
     cfg, inst, cols, rects = api.prepare_frame(scene, camera)
-    r = renderer or api.LucidRenderer(scene["width"], scene["height"], opts, mvq, bin_rows=bin_rows)
+    r = renderer or api.LucidRenderer(scene["width"], scene["height"], opts, mvq, bin_rows=bin_rows,
+                                      create_flags=create_flags, max_block_entries=max_block_entries)
     if renderer is None:
         r.set_scene(scene)
     img = np.zeros((scene["height"], scene["width"]), np.uint32)

@@ -178,6 +178,50 @@ def test_debug_raster_variant_records_a_violation(small, monkeypatch):
         r0.close()
 
 
+@pytest.mark.parametrize("name", ["soup", "soup_close", "meshlets", "arch", "hairball", "planes"])
+def test_compact_block_lists_render_the_same_frame(name, small):
+    """LUCID_CREATE_COMPACT_LISTS: block lists in a pool sized by max_block_entries (count pass, one allocation per
+    bin, fill pass) instead of a fixed 1 MiB per bin.  Everything the frame produces equals the oracle's, as with the
+    fixed slots (LOW and HIGH bins, promoted bins, the pre-pass)."""
+    sc = small[name]
+    o = pu.run_oracle(sc)
+    r, img = pu.run_cuda(sc, create_flags=api.CREATE_COMPACT_LISTS)
+    try:
+        assert _clean(pu.compare(r, img, o)) == {}
+    finally:
+        r.close()
+    if name in ("arch", "soup"):
+        op = pu.run_oracle(sc, opts=api.OPT_OPAQUE_PREPASS)
+        r, img = pu.run_cuda(sc, opts=api.OPT_OPAQUE_PREPASS, create_flags=api.CREATE_COMPACT_LISTS)
+        try:
+            assert _clean(pu.compare(r, img, op)) == {}
+        finally:
+            r.close()
+
+
+def test_compact_block_lists_full_size_and_pool_limit():
+    """configs[3] at full size with a pool of 2^25 entries (512 MB of lists where the fixed slots take 8 GiB): the
+    oracle's frame; with a pool that is too small the bins that did not fit are red and the frame says so."""
+    sc = scenes.get_config(3)
+    o = pu.run_oracle(sc, mvq=FULL_MVQ, threads=os.cpu_count())
+    r, img = pu.run_cuda(sc, mvq=FULL_MVQ, create_flags=api.CREATE_COMPACT_LISTS, max_block_entries=1 << 25)
+    try:
+        assert _clean(pu.compare(r, img, o)) == {}
+    finally:
+        r.close()
+    small_sc = scenes.quad_soup(num_quads=20_000, width=640, height=360, distance=12.0, seed=3)
+    cfg, inst, cols, rects = api.prepare_frame(small_sc)
+    r = api.LucidRenderer(640, 360, 0, 1 << 20, create_flags=api.CREATE_COMPACT_LISTS, max_block_entries=4096)
+    try:
+        r.set_scene(small_sc)
+        out = np.zeros((360, 640), np.uint32)
+        with pytest.raises(api.LucidError):
+            r.render(cfg, inst, cols, rects, out=out)
+        assert (r.read_image() == 0x000000FF).any()  # red bins
+    finally:
+        r.close()
+
+
 def test_timers_option(small):
     """LUCID_OPT_TIMERS (the reference's `_timers` shader variants, shared/timers.glsl, lucid_renderer.cpp:754-762):
     the phases' clock ticks land in LucidInfo.setup_timers / bin_dispatcher_timers / raster_timers in the reference's

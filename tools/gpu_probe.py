@@ -1,5 +1,5 @@
 """Full-size probe: stage times + counters of the CUDA path on the BASELINE configs (parity against the
-checker is the GPU test suite's job).  usage: python tools/gpu_probe.py [config ...] [--scale=S] [--opts=BITS]"""
+checker is the GPU test suite's job).  usage: python tools/gpu_probe.py [config ...] [--scale=S] [--opts=BITS] [--compact]"""
 import json
 import os
 import sys
@@ -11,8 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lucid_b200 import api, scenes  # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-scale, opts = 1.0, 0
+scale, opts, create_flags, mbe = 1.0, 0, 0, 0
 for a in sys.argv[1:]:
+    if a == "--compact":
+        create_flags, mbe = api.CREATE_COMPACT_LISTS, 0
     if a.startswith("--scale="):
         scale = float(a.split("=")[1])
     if a.startswith("--opts="):
@@ -22,7 +24,7 @@ for ci in configs:
     t0 = time.time()
     sc = scenes.get_config(ci, scale)
     cfg, inst, cols, rects = api.prepare_frame(sc)
-    r = api.LucidRenderer(sc["width"], sc["height"], opts, 0)
+    r = api.LucidRenderer(sc["width"], sc["height"], opts, 0, create_flags=create_flags, max_block_entries=mbe)
     r.set_scene(sc)
     img = np.zeros((sc["height"], sc["width"]), np.uint32)
     for _ in range(3):
