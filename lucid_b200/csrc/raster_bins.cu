@@ -142,8 +142,8 @@ struct BinShared {
 };
 
 // a persistent CTA takes one bin at a time: HIGH bins first (they take longest).  256 threads when there are bins for
-// every CTA slot of the device; a device that owns few bins (its share of a bin-range split) takes them with 512- or
-// 1024-thread CTAs, so that the heaviest bin -- the kernel's critical path -- is walked by 16 or 32 warps instead of 8
+// every CTA slot of the device; a device that owns few bins (its share of a bin-range split) takes them with 512-thread
+// CTAs, so that the heaviest bin -- the kernel's critical path -- is walked by 16 warps instead of 8
 // COMPACT (LUCID_CREATE_COMPACT_LISTS): the walk below only counts; the bin then takes exactly its entries from the list
 // pool with one atomic and a second walk fills the lists (slots by the same shared-memory atomics, so a list may come
 // out in another order than the counting pass met it: the block sort orders it anyway).
@@ -377,38 +377,31 @@ __global__ void __launch_bounds__(THREADS) k_raster_bins(const __grid_constant__
 
 
 void launchRasterBins(const Params &p, u32 background, cudaStream_t stream, int num_sms) {
-	// LUCID_RASTER_BINS_THREADS=256|512|1024 overrides the choice (measurements)
+	// LUCID_RASTER_BINS_THREADS=256|512 overrides the choice (measurements).  Measured on the ranks of an 8-way split of
+	// the 10M-triangle frame (profiles/r2w_*): with under a thousand heavy bins 512 threads take the list stage from
+	// 0.145-0.158 to 0.106-0.109 ms, with many light bins 256 are faster (0.031 against 0.043 ms); 1024 never win
 	static const int forced = [] {
 		const char *v = getenv("LUCID_RASTER_BINS_THREADS");
 		return v ? atoi(v) : 0;
 	}();
 	const int owned = p.bin_end - p.bin_begin;
-	int threads = owned >= num_sms * 6 ? 256 : owned >= num_sms * 3 ? 512 : 1024;
-	if(forced == 256 || forced == 512 || forced == 1024)
+	int threads = owned >= num_sms * 6 ? 256 : 512;
+	if(forced == 256 || forced == 512)
 		threads = forced;
 	constexpr size_t ring_bytes_per_warp = PHASE_A_RING * 2 * sizeof(uint4);
-	static std::once_flag configured[64];
-	oncePerDevice(configured, [] {
-		cudaFuncSetAttribute((k_raster_bins<1024, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * ring_bytes_per_warp));
-		cudaFuncSetAttribute((k_raster_bins<1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * ring_bytes_per_warp));
-	});
 	auto launch = [&](auto kernel, int ctas_per_sm, int nthreads) {
 		launchPDL(kernel, num_sms * ctas_per_sm, nthreads, (size_t)(nthreads / 32) * ring_bytes_per_warp, stream, p, background);
 	};
 	if(p.compact_lists) {
 		if(threads == 256)
 			launch(k_raster_bins<256, true>, 4, 256);
-		else if(threads == 512)
-			launch(k_raster_bins<512, true>, 2, 512);
 		else
-			launch(k_raster_bins<1024, true>, 1, 1024);
+			launch(k_raster_bins<512, true>, 2, 512);
 	} else {
 		if(threads == 256)
 			launch(k_raster_bins<256, false>, 4, 256);
-		else if(threads == 512)
-			launch(k_raster_bins<512, false>, 2, 512);
 		else
-			launch(k_raster_bins<1024, false>, 1, 1024);
+			launch(k_raster_bins<512, false>, 2, 512);
 	}
 }
 
