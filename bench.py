@@ -167,6 +167,7 @@ class Rig:
         self.scene = scene if scene is not None else make_scene(config, args.scale)
         self.width, self.height = self.scene["width"], self.scene["height"]
         self.stream = stream
+        self._configs = {}
         self.r = api.LucidRenderer(self.width, self.height, 0, args.mvq, device=local_rank, stream=stream.cuda_stream)
         self.r.set_scene(self.scene)
         self.inst, self.cols, self.rects = api.build_instances(self.scene["draw_calls"], self.scene["materials"])
@@ -175,8 +176,10 @@ class Rig:
 
     def config_for(self, view):
         api = self.api
-        cam = api.make_camera(view_camera(self.scene, view), self.width, self.height)
-        return api.make_config(cam, len(self.inst), self.scene["background"])
+        if view not in self._configs:  # a handful of cameras, asked for every frame
+            cam = api.make_camera(view_camera(self.scene, view), self.width, self.height)
+            self._configs[view] = api.make_config(cam, len(self.inst), self.scene["background"])
+        return self._configs[view]
 
     def barrier(self):
         if self.dist is not None:
@@ -508,6 +511,43 @@ def run_ours(args):
             return e0.elapsed_time(e1)
 
         pipelined(max(args.warmup, n_lanes) * n_lanes)
+        # The ranges were balanced on frames rendered one at a time; with frames in flight the ranks gain differently
+        # (a rank of many light bins overlaps better than one of few heavy bins), so the same feedback runs again on
+        # each rank's own pipelined frame time: frames into the rank's own image, no hand-over, ranks uncoupled.
+        if not (args.equal_rows or args.split_rows):
+            local = api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES
+            cfg0 = rig.config_for(0)
+
+            def standalone(frames):
+                rig.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(rig.stream)
+                for ln in lanes[1:]:
+                    ln.stream.wait_event(e0)
+                for k in range(frames):
+                    lanes[k % n_lanes].r.render(cfg0, inst, cols, rects, flags=local)
+                for ln in lanes[1:]:
+                    done = torch.cuda.Event()
+                    done.record(ln.stream)
+                    rig.stream.wait_event(done)
+                e1.record(rig.stream)
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / frames
+
+            for _ in range(args.balance_iters_in_flight):
+                standalone(2 * n_lanes)
+                mine = standalone(6 * n_lanes)
+                times = torch.zeros(world, device="cuda", dtype=torch.float64)
+                times[rank] = mine
+                dist.all_reduce(times)
+                times = times.cpu().numpy()
+                for q, (lo, hi) in enumerate(ranges):
+                    cost[lo:hi] *= times[q] / max(float(cost[lo:hi].sum()), 1e-9)
+                ranges = multigpu.split_bins(r.bin_count, world, cost)
+                rows = ranges[rank]
+                for ln in lanes:
+                    ln.r.set_bin_range(*rows)
+            pipelined(max(args.warmup, n_lanes) * n_lanes)
         pipe_ms = max_over_ranks(rig, pipelined(args.steps))
         t0 = time.perf_counter()
         n_sus, sus_ms = 0, 0.0
@@ -809,6 +849,8 @@ def main():
     ap.add_argument("--completion", default="flags", choices=["flags", "allreduce"],
                     help="--mode split: how rank 0 learns that every strip of a frame has landed")
     ap.add_argument("--balance-iters", type=int, default=7, help="--mode split: feedback steps of the range balancing")
+    ap.add_argument("--balance-iters-in-flight", type=int, default=5,
+                    help="--mode split: further feedback steps on the ranks' pipelined frame times")
     ap.add_argument("--frames-in-flight", type=int, default=5,
                     help="--mode split: renderer handles per rank rendering alternate frames on their own streams")
     args = ap.parse_args()
