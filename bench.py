@@ -254,16 +254,19 @@ def sustained_run(rig, render, after_frame, seconds: float, frames_per_step: int
             "note": "back-to-back frames, no L2 flush (per-frame records exceed the L2), one CUDA event pair"}
 
 
-def e2e_run(rig, frame, steps, frames_per_step):
+def e2e_run(rig, frame, steps, frames_per_step, renderers=None):
+    renderers = renderers or [rig.r]
     rig.barrier()
-    for w in range(3):
+    for w in range(max(3, len(renderers))):
         frame(w)
-    rig.r.wait()
+    for r in renderers:
+        r.wait()
     rig.barrier()
     t0 = time.perf_counter()
     for k in range(steps):
         frame(k)
-    rig.r.wait()
+    for r in renderers:
+        r.wait()
     rig.barrier()
     return frames_per_step * steps / max_over_ranks(rig, time.perf_counter() - t0)
 
@@ -474,23 +477,30 @@ def run_ours(args):
 
     sustained = sustained_run(rig, render, after_frame, args.sustained_seconds, 1)
 
-    # Frames in flight (bin-range split): with an eighth of the bins on a device every kernel of a frame runs out of
-    # parallel work before it runs out of work (one bin per CTA, one list per warp), so F handles on F streams render
-    # alternate frames and the kernels of neighbouring frames fill each other's tails.  The same K steps, timed as one
-    # bracket; no L2 flush in between (a rank's frame reads > 400 MB of geometry and records, the L2 holds 126 MB).
+    # Frames in flight: the kernels of a frame differ in what bounds them (setup: HBM; shading: instruction issue) and
+    # each ends with a tail of few busy SMs -- long tails on a device that owns an eighth of the bins (one bin per
+    # CTA, one list per warp).  F handles on F streams render alternate frames and the kernels of neighbouring frames
+    # fill each other's gaps.  The same K steps, timed as one bracket; no L2 flush in between (a frame reads several
+    # hundred MB of geometry and records, the L2 holds 126 MB).  Programmatic dependent launch is off here
+    # (LUCID_RENDER_NO_DEPENDENT_LAUNCH): CTAs launched early wait on the SMs in the other handles' way.
     inflight = None
-    n_lanes = args.frames_in_flight if (split and use_flags) else 1
+    if split:
+        n_lanes = args.frames_in_flight if use_flags else 1
+    else:
+        n_lanes = args.frames_in_flight_single
+    lanes = [lane0]
     if n_lanes > 1:
-        lanes = [lane0]
         for _ in range(n_lanes - 1):
             lane_stream = torch.cuda.Stream(device=local_rank)
             lr = Rig(args, args.config, torch, dist, rank, world, local_rank, lane_stream, scene=scene)
-            if args.equal_rows or args.split_rows:
+            if split and (args.equal_rows or args.split_rows):
                 lr.r.set_bin_rows(*rows)
-            else:
+            elif split:
                 lr.r.set_bin_range(*rows)
             lanes.append(Lane(lr))
-        plain = api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES
+        # several handles busy on one device: no programmatic dependent launch (include/lucid_b200.h)
+        plain = (api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES |
+                 api.RENDER_NO_DEPENDENT_LAUNCH)
 
         def pipelined(steps):
             rig.barrier()
@@ -514,8 +524,8 @@ def run_ours(args):
         # The ranges were balanced on frames rendered one at a time; with frames in flight the ranks gain differently
         # (a rank of many light bins overlaps better than one of few heavy bins), so the same feedback runs again on
         # each rank's own pipelined frame time: frames into the rank's own image, no hand-over, ranks uncoupled.
-        if not (args.equal_rows or args.split_rows):
-            local = api.RENDER_ASYNC | api.RENDER_SKIP_INFO | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES
+        if split and not (args.equal_rows or args.split_rows):
+            local = plain
             cfg0 = rig.config_for(0)
 
             def standalone(frames):
@@ -555,7 +565,8 @@ def run_ours(args):
             sus_ms += pipelined(16 * n_lanes)
             n_sus += 16 * n_lanes
             stop = torch.tensor([1.0 if time.perf_counter() - t0 >= args.sustained_seconds else 0.0], device="cuda")
-            dist.broadcast(stop, src=0)
+            if dist is not None:
+                dist.broadcast(stop, src=0)
             if float(stop.item()) > 0:
                 break
         sus_ms = max_over_ranks(rig, sus_ms)
@@ -563,9 +574,6 @@ def run_ours(args):
                     "value": 1000.0 * args.steps / pipe_ms,
                     "sustained": {"frames": n_sus, "device_s": round(sus_ms / 1e3, 3),
                                   "value": round(n_sus / (sus_ms / 1e3), 3), "unit": "frames/s"}}
-        for ln in lanes[1:]:
-            ln.close()
-            ln.rig.close()
     clocks = sampler.stop()
 
     # per-stage CUDA-event times: the same frames again, same L2 flush, this time with an event after every
@@ -599,6 +607,19 @@ def run_ours(args):
 
     e2e_value = e2e_run(rig, e2e_frame, e2e_steps, 1)
     e2e_extra = {}
+    lane_renderers = [ln.r for ln in lanes]
+    if not split and n_lanes > 1:
+        # the same with the frames in flight: alternate frames on the handles, each with its own pair of host images
+        e2e_extra["one_handle"] = {"value": round(e2e_value, 3), "unit": "frames/s"}
+        e2e_flags = api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES | api.RENDER_NO_DEPENDENT_LAUNCH
+
+        def e2e_frame_lanes(k):
+            ln = lanes[k % n_lanes]
+            ln.r.render(rig.config_for(view_of(k)), inst, cols, rects,
+                        out=ln.rig.host_imgs[(k // n_lanes) & 1].data_ptr(), flags=e2e_flags)
+
+        e2e_value = e2e_run(rig, e2e_frame_lanes, e2e_steps, 1, lane_renderers)
+        e2e_extra["frames_in_flight"] = n_lanes
     if split:
         # The frame gathered in HOST memory instead: one image shared by the processes (POSIX shared memory, pinned
         # in every process), every rank copies its own bins into it over its own PCIe link
@@ -613,22 +634,27 @@ def run_ours(args):
         ref_img = r.read_image() if rank == 0 else None
         name = "lucid_b200_e2e_%s" % os.environ.get("MASTER_PORT", "0")
         shared = None
+        n_shared = 2 * n_lanes
         if rank == 0:
-            shared = multigpu.SharedHostImages(name, width, height, 2, create=True)
+            shared = multigpu.SharedHostImages(name, width, height, n_shared, create=True)
         rig.barrier()
         if rank != 0:
-            shared = multigpu.SharedHostImages(name, width, height, 2, create=False)
+            shared = multigpu.SharedHostImages(name, width, height, n_shared, create=False)
         shared.pin()
-        host_flags = api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES | api.RENDER_OWNED_BINS_ONLY
+        host_flags = (api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES | api.RENDER_CULL_INSTANCES | api.RENDER_OWNED_BINS_ONLY |
+                      (api.RENDER_NO_DEPENDENT_LAUNCH if n_lanes > 1 else 0))
 
         def e2e_frame_host(k):
-            r.render(rig.config_for(view_of(k)), inst, cols, rects, out=shared.pointer(k & 1), flags=host_flags)
+            lanes[k % n_lanes].r.render(rig.config_for(view_of(k)), inst, cols, rects, out=shared.pointer(k % n_shared),
+                                        flags=host_flags)
 
-        e2e_value = e2e_run(rig, e2e_frame_host, e2e_steps, 1)
+        e2e_value = e2e_run(rig, e2e_frame_host, e2e_steps, 1, lane_renderers)
+        e2e_extra["frames_in_flight"] = n_lanes
         if rank == 0:
             e2e_extra["delivery"] = ("every rank copies its own bins into one host image shared by the processes "
                                      "(/dev/shm, page-locked), over its own PCIe link")
-            e2e_extra["verified_against_gathered_frame"] = bool(np.array_equal(shared.array[(e2e_steps - 1) & 1], ref_img))
+            e2e_extra["verified_against_gathered_frame"] = bool(
+                np.array_equal(shared.array[(e2e_steps - 1) % n_shared], ref_img))
         rig.barrier()
         shared.close()
 
@@ -643,6 +669,9 @@ def run_ours(args):
     ms_per_step = serial_ms_per_step if inflight is None else inflight["ms_per_step"]
     value = 1000.0 / ms_per_step
 
+    for ln in lanes[1:]:  # the extra handles of the frames in flight
+        ln.close()
+        ln.rig.close()
     views = None
     if split and not args.no_views:
         lane0.close()
@@ -739,9 +768,9 @@ def run_ours(args):
                                            "ms_per_step": round(serial_ms_per_step, 4),
                                            "ms_per_step_median": round(step_median, 4), "sustained": sustained}
             line["sustained"] = inflight["sustained"]
-            line["config"]["l2"] = ("no flush between the pipelined frames: a rank's frame reads several hundred MB of "
-                                    "geometry and records, the L2 holds 126 MB; the one-frame-at-a-time loop flushes "
-                                    "with a 256 MiB memset between timed frames (untimed)")
+            line["config"]["l2"] = ("no flush between the pipelined frames: a frame (a rank's share of it) reads several "
+                                    "hundred MB of geometry and records, the L2 holds 126 MB; the one-frame-at-a-time "
+                                    "loop flushes with a 256 MiB memset between timed frames (untimed)")
             line["config"]["parallelism"] += "; %d frames in flight (handles on separate streams)" % inflight["frames_in_flight"]
         if views is not None:
             line["views"] = views
@@ -851,7 +880,9 @@ def main():
     ap.add_argument("--balance-iters", type=int, default=7, help="--mode split: feedback steps of the range balancing")
     ap.add_argument("--balance-iters-in-flight", type=int, default=5,
                     help="--mode split: further feedback steps on the ranks' pipelined frame times")
-    ap.add_argument("--frames-in-flight", type=int, default=5,
+    ap.add_argument("--frames-in-flight-single", type=int, default=2,
+                    help="N = 1: renderer handles rendering alternate frames on their own streams (1 = off)")
+    ap.add_argument("--frames-in-flight", type=int, default=3,
                     help="--mode split: renderer handles per rank rendering alternate frames on their own streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

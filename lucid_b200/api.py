@@ -20,6 +20,7 @@ COUNTS_PER_BIN = 10
 MEM_HOST, MEM_DEVICE, MEM_NONE = 0, 1, 2
 RENDER_ASYNC, RENDER_SKIP_INFO, RENDER_FRAG_COUNTS, RENDER_NO_STAGE_TIMES, RENDER_CULL_INSTANCES = 1, 2, 4, 8, 16
 RENDER_OWNED_BINS_ONLY = 32  # MEM_HOST read-back of the owned bins only (bin-row split)
+RENDER_NO_DEPENDENT_LAUNCH = 64  # several handles busy on one device: no programmatic dependent launch
 
 OPT_DEBUG_RASTER = 1 << 3  # the reference's raster_*_debug pipelines: lucid_read_debug_records
 OPT_TIMERS = 1 << 4
