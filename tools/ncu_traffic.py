@@ -7,8 +7,8 @@ import json
 import subprocess
 import sys
 
-STAGE = {"k_quad_cull": "setup", "k_tri_setup": "setup", "k_bin_count": "bin_count", "k_bin_dispatch": "bin_dispatch",
-         "k_raster_bins": "raster", "k_raster_blocks": "raster"}
+STAGE = {"k_instance_select": "setup", "k_quad_cull": "setup", "k_tri_setup": "setup", "k_bin_count": "bin_count",
+         "k_bin_dispatch": "bin_dispatch", "k_raster_bins": "raster", "k_block_sort": "raster", "k_block_shade": "raster"}
 out = {}
 for spec in sys.argv[1:]:
     name, _, path = spec.partition("=")
@@ -20,7 +20,8 @@ for spec in sys.argv[1:]:
     stages, kernels, issue = {}, {}, {}
     tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
     for r in rows[2:]:
-        kname = r[idx["Kernel Name"]].split("(")[0].split("::")[-1]
+        # "void k_block_sort<0>(Params, unsigned int)" -> k_block_sort
+        kname = r[idx["Kernel Name"]].split("(")[0].split("<")[0].split("::")[-1].replace("void ", "").strip()
         total = 0.0
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             total += float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]]
