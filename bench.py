@@ -618,8 +618,13 @@ def run_ours(args):
             ln.r.render(rig.config_for(view_of(k)), inst, cols, rects,
                         out=ln.rig.host_imgs[(k // n_lanes) & 1].data_ptr(), flags=e2e_flags)
 
-        e2e_value = e2e_run(rig, e2e_frame_lanes, e2e_steps, 1, lane_renderers)
-        e2e_extra["frames_in_flight"] = n_lanes
+        lanes_value = e2e_run(rig, e2e_frame_lanes, e2e_steps, 1, lane_renderers)
+        if lanes_value > e2e_value:
+            e2e_value = lanes_value
+            e2e_extra["frames_in_flight"] = n_lanes
+        else:  # the faster mode's figure is the line's, the other stays beside it
+            e2e_extra["frames_in_flight"] = 1
+            e2e_extra["with_%d_frames_in_flight" % n_lanes] = {"value": round(lanes_value, 3), "unit": "frames/s"}
     if split:
         # The frame gathered in HOST memory instead: one image shared by the processes (POSIX shared memory, pinned
         # in every process), every rank copies its own bins into it over its own PCIe link
@@ -666,6 +671,14 @@ def run_ours(args):
 
     tris_per_frame = 2 * stats["input_quads"]
     serial_ms_per_step = total_ms / args.steps
+    frames_in_flight_tried = None
+    if inflight is not None and not split and inflight["ms_per_step"] >= serial_ms_per_step:
+        # one GPU, whole frames: frames in flight pay where a frame's kernels leave gaps to fill (the 10M-triangle
+        # scene +5 %, the 1M-triangle scene +27 %) and not where one kernel after the other already fills the GPU
+        # (hairball -4 %); an application would measure both once, and so does this run: the line is the faster mode's
+        frames_in_flight_tried = {"frames_in_flight": inflight["frames_in_flight"],
+                                  "value": round(inflight["value"], 3), "ms_per_step": round(inflight["ms_per_step"], 4)}
+        inflight = None
     ms_per_step = serial_ms_per_step if inflight is None else inflight["ms_per_step"]
     value = 1000.0 / ms_per_step
 
@@ -772,6 +785,9 @@ def run_ours(args):
                                     "hundred MB of geometry and records, the L2 holds 126 MB; the one-frame-at-a-time "
                                     "loop flushes with a 256 MiB memset between timed frames (untimed)")
             line["config"]["parallelism"] += "; %d frames in flight (handles on separate streams)" % inflight["frames_in_flight"]
+        if frames_in_flight_tried is not None:
+            line["frames_in_flight"] = 1
+            line["frames_in_flight_tried"] = frames_in_flight_tried
         if views is not None:
             line["views"] = views
         if not args.no_cpu_baseline and world == 1:

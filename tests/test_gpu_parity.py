@@ -656,6 +656,38 @@ def test_owned_bins_read_back_composes_the_frame_in_host_memory(small):
         r.close()
 
 
+def test_frames_in_flight_on_two_handles_render_the_same_frames(small):
+    """Two handles on their own streams render alternate frames of an orbit (what bench.py does on every GPU), without
+    programmatic dependent launch (LUCID_RENDER_NO_DEPENDENT_LAUNCH); every frame equals the one a single handle
+    renders with the default launch mode, whichever handle rendered it."""
+    sc = small["arch"]
+    base = sc["camera"]  # kind "lookat": a camera that walks sideways
+    cams = [dict(base, pos=(base["pos"][0] + 0.7 * k, base["pos"][1], base["pos"][2] - 0.4 * k)) for k in range(6)]
+    frames = [api.prepare_frame(sc, c) for c in cams]
+    ref = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20)
+    a = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20)
+    b = api.LucidRenderer(sc["width"], sc["height"], 0, 1 << 20)
+    try:
+        for r in (ref, a, b):
+            r.set_scene(sc)
+        want = []
+        for cfg, inst, cols, rects in frames:
+            img = np.zeros((sc["height"], sc["width"]), np.uint32)
+            ref.render(cfg, inst, cols, rects, out=img)
+            want.append(img)
+        got = [np.zeros((sc["height"], sc["width"]), np.uint32) for _ in frames]
+        flags = api.RENDER_ASYNC | api.RENDER_NO_STAGE_TIMES | api.RENDER_NO_DEPENDENT_LAUNCH | api.RENDER_CULL_INSTANCES
+        for k, (cfg, inst, cols, rects) in enumerate(frames):
+            (a, b)[k & 1].render(cfg, inst, cols, rects, out=got[k], flags=flags)
+        a.wait()
+        b.wait()
+        for k in range(len(frames)):
+            assert np.array_equal(got[k], want[k]), k
+    finally:
+        for r in (ref, a, b):
+            r.close()
+
+
 def test_texture_unit_filter_equals_its_restatement():
     """The filter is the B200 texture unit's (tex2DLod on RGBA8 mipmapped arrays).  The CPU checker restates its
     arithmetic in integers (8-bit weights split level -> x -> y, 16-bit unorm texels; fitted with tools/hwtex/):
