@@ -94,8 +94,16 @@ def _read_string(f) -> str:
 # ---- Scene::load ------------------------------------------------------------------------------------------------
 
 
-def load_scene(path_or_file, width: int = 1920, height: int = 1080, name: str | None = None) -> dict:
-    """Reads a `.scene` file (Scene::load, src/scene.cpp:119-151) into a scene dict."""
+def load_scene(path_or_file, width: int = 1920, height: int = 1080, name: str | None = None, quads: str = "file",
+               square_weight: float = 4.0, device: int = 0) -> dict:
+    """Reads a `.scene` file (Scene::load, src/scene.cpp:119-151) into a scene dict.
+
+    quads="file" takes every mesh's quads as stored; quads="gpu" pairs the mesh's triangles again on the GPU
+    (Scene::generateQuads, src/scene.cpp:237-247, through lucid_quadgen: needs the CUDA library) -- for files that carry
+    triangles only, or to re-pair with another squareness weight (the reference's converter uses the input scene's
+    quad_squareness, its procedural scenes 4.0: src/scene_convert.cpp:430, scene_setup.cpp:186)."""
+    if quads not in ("file", "gpu"):
+        raise ValueError('quads must be "file" or "gpu"')
     f = open(path_or_file, "rb") if isinstance(path_or_file, str) else path_or_file
     try:
         if _read(f, 5) != b"SCENE":
@@ -115,13 +123,13 @@ def load_scene(path_or_file, width: int = 1920, height: int = 1080, name: str | 
         meshes = []
         for _ in range(num_meshes):
             material_id, colors_opaque = struct.unpack("<i?", _read(f, 5))
-            _read_vector(f, np.int32, 3)  # triangles: the quad path does not use them
-            quads = _read_vector(f, np.int32, 4)
+            tris = _read_vector(f, np.int32, 3)  # the renderer itself only reads the quads
+            mesh_quads = _read_vector(f, np.int32, 4)
             (num_degenerate,) = struct.unpack("<i", _read(f, 4))
             _read(f, 24)  # mesh bounding box
             if not 0 <= material_id < num_materials:
                 raise SceneFormatError("mesh refers to a material that does not exist")
-            meshes.append(dict(material_id=material_id, colors_opaque=colors_opaque, quads=quads,
+            meshes.append(dict(material_id=material_id, colors_opaque=colors_opaque, quads=mesh_quads, tris=tris,
                                num_degenerate_quads=num_degenerate))
 
         materials = []
@@ -152,6 +160,9 @@ def load_scene(path_or_file, width: int = 1920, height: int = 1080, name: str | 
     finally:
         if isinstance(path_or_file, str):
             f.close()
+    if quads == "gpu":
+        from . import quadgen
+        quadgen.generate_quads(meshes, positions, square_weight, device)
     return scene_from_parts(positions, colors, tex_coords, qnormals, bbox, meshes, materials, textures, width, height,
                             name or (path_or_file if isinstance(path_or_file, str) else "scene"))
 
@@ -207,8 +218,10 @@ def scene_from_parts(positions, colors, tex_coords, qnormals, bbox, meshes, mate
 # ---- Scene::save ---------------------------------------------------------------------------------------------------
 
 
-def save_scene(path_or_file, scene: dict):
-    """Writes a scene dict in the reference's format (Scene::save, src/scene.cpp:153-179): one mesh per draw call."""
+def save_scene(path_or_file, scene: dict, with_tris: bool = False, with_quads: bool = True):
+    """Writes a scene dict in the reference's format (Scene::save, src/scene.cpp:153-179): one mesh per draw call.
+    with_tris also writes every mesh's triangles (the two of each quad, degenerate ones left out) as the reference's
+    files carry them; with_quads=False leaves the quads out: a triangle-only file for load_scene(quads="gpu")."""
     f = open(path_or_file, "wb") if isinstance(path_or_file, str) else path_or_file
     try:
         pos = np.ascontiguousarray(scene["positions"], np.float32)
@@ -228,9 +241,13 @@ def save_scene(path_or_file, scene: dict):
         for mat_id, nq, off, opts in scene["draw_calls"]:
             q = quads[off:off + nq]
             f.write(struct.pack("<i?", mat_id, True))
-            _write_vector(f, None, np.int32, 3)
-            _write_vector(f, q, np.int32, 4)
-            f.write(struct.pack("<i", 0))
+            tris = None
+            if with_tris and q.size:
+                second = q[q[:, 2] != q[:, 3]]  # (a, b, c, c) stands for one triangle
+                tris = np.concatenate([q[:, [0, 1, 2]], second[:, [0, 2, 3]]])
+            _write_vector(f, tris, np.int32, 3)
+            _write_vector(f, q if with_quads else None, np.int32, 4)
+            f.write(struct.pack("<i", int((q[:, 2] == q[:, 3]).sum()) if (with_quads and q.size) else 0))
             v = pos[q.reshape(-1)] if q.size else np.zeros((1, 3), np.float32)
             f.write(np.stack([v.min(axis=0), v.max(axis=0)]).astype(np.float32).tobytes())
         # which texture a material uses follows from the draw calls that use the material

@@ -80,3 +80,45 @@ def test_truncated_and_foreign_files_are_rejected():
         scene_io.load_scene(io.BytesIO(b"MODEL" + raw[5:]))
     with pytest.raises(scene_io.SceneFormatError):
         scene_io.load_scene(io.BytesIO(raw[:len(raw) // 2]))
+
+
+def test_triangles_are_written_and_read_back():
+    """with_tris: the two triangles of every quad, in the reference's mesh record; the loader keeps them."""
+    sc = pu.small_scenes()["meshlets"]
+    f = io.BytesIO()
+    scene_io.save_scene(f, sc, with_tris=True)
+    f.seek(0)
+    out = scene_io.load_scene(f, sc["width"], sc["height"])
+    assert np.array_equal(out["quads"], sc["quads"])  # quads="file": as stored
+    f.seek(0)
+    # triangle-only file: no quads to take
+    g = io.BytesIO()
+    scene_io.save_scene(g, sc, with_tris=True, with_quads=False)
+    g.seek(0)
+    only = scene_io.load_scene(g, sc["width"], sc["height"])
+    assert only["quads"].shape[0] == 0
+    with pytest.raises(ValueError):
+        scene_io.load_scene(io.BytesIO(g.getvalue()), quads="cpu")
+
+
+@pytest.mark.gpu
+def test_triangle_only_scene_is_paired_on_the_gpu_and_renders_the_same():
+    """f2 + f3 together: a scene file that carries triangles only is paired by lucid_quadgen when it is loaded
+    (Scene::generateQuads) and renders the fragments of the scene it was written from."""
+    sc = pu.small_scenes()["meshlets"]
+    g = io.BytesIO()
+    scene_io.save_scene(g, sc, with_tris=True, with_quads=False)
+    g.seek(0)
+    paired = scene_io.load_scene(g, sc["width"], sc["height"], quads="gpu")
+    paired["camera"], paired["background"] = sc["camera"], sc["background"]
+    nq0, nq1 = sc["quads"].shape[0], paired["quads"].shape[0]
+    assert nq0 <= nq1 <= 1.05 * nq0  # a height-field patch pairs back into (almost) as many quads as it was made of
+    r0, img0 = pu.run_cuda(sc)
+    r1, img1 = pu.run_cuda(paired)
+    try:
+        a, b = r0.read_frag_counts(), r1.read_frag_counts()
+        assert abs(int(a.sum()) - int(b.sum())) <= 2e-3 * a.sum()
+        assert np.count_nonzero(a != b) <= 5e-3 * np.count_nonzero(a)
+    finally:
+        r0.close()
+        r1.close()
