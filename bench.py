@@ -767,9 +767,9 @@ def run_ours(args):
                         **e2e_extra),
             "sustained": sustained,
             # k_frame_begin, k_instance_select, k_quad_cull, k_tri_setup, k_bin_count, k_bin_scan, k_bin_dispatch,
-            # k_raster_bins, k_block_sort, k_block_shade (+ k_info_out when LucidInfo is read back; the split adds
-            # the frame gate / flag kernels of sync.cu)
-            "gpu_launches": int(10 * args.steps),
+            # k_raster_bins, k_block_sort, k_tie_runs, k_block_shade (+ k_info_out when LucidInfo is read back; the
+            # split adds the frame gate / flag kernels of sync.cu)
+            "gpu_launches": int(11 * args.steps),
             "clocks": clocks,
             "wall_s": round(wall, 3),
         }

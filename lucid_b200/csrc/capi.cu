@@ -290,6 +290,8 @@ int lucid_create(const LucidCreateInfo *info, lucid_renderer **out) {
 	p.block_items_cap = (u32)p.bin_count * 32u;
 	CUC(devAlloc(r, &p.block_items, (size_t)p.block_items_cap * 5)); // one region per size class (ITEM_CLASSES)
 	CUC(devAlloc(r, &p.large_keys, rasterLargeKeysCount(r->num_sms)));
+	CUC(devAlloc(r, &p.tie_runs, (size_t)2 + 2 * TIE_RUN_QUEUE));
+	CUC(devAlloc(r, &p.tie_scratch, rasterTieScratchCount(r->num_sms)));
 	// sorted-entry stream: one entry per (triangle, half-block or block) pair of the frame
 	{
 		const unsigned long long def = std::max<unsigned long long>(16ull * mvq, 1ull << 22);

@@ -101,6 +101,10 @@ struct Params {
 	uint4 *block_items;	  // work items of the block stages (item, entries, stream offset, -): one region of block_items_cap per size class
 	u32 block_items_cap;
 	u32 *large_keys;	  // per k_block_sort warp: sort keys of lists too long for shared memory
+	// long runs of equal depth keys that k_block_sort left in arrival order for k_tie_runs: [0] count, then
+	// (first stream entry, length) pairs; tie_scratch: per k_tie_runs warp room for one run's entries (2 x 4096 uint4)
+	u32 *tie_runs;
+	uint4 *tie_scratch;
 	// the sorted-entry stream k_block_sort writes and k_block_shade reads: per work item a slice of both planes
 	uint4 *sorted_rec;	  // (triangle, pixel mask of the upper / only half, pixel mask of the lower half, -)
 	uint4 *sorted_aux;	  // (depth plane xyz, constant colour or AUX_VARYING)
@@ -340,6 +344,8 @@ void launchSignal(u32 *flag, u32 value, cudaStream_t stream);
 void launchWaitFlags(const u32 *flags, int count, u32 value, u32 *status, unsigned long long timeout_ns, cudaStream_t stream);
 void launchCompositeBins(const Params &p, u32 *dst, int dst_pitch, cudaStream_t stream, int num_sms);
 size_t rasterLargeKeysCount(int num_sms);
+size_t rasterTieScratchCount(int num_sms); // uint4 words of k_tie_runs' scratch
+constexpr int TIE_RUN_QUEUE = 65536;	  // long runs of depth ties one frame can hand to k_tie_runs
 constexpr int WORK_COUNTERS = 12; // raster_common.cuh WC_*
 
 // 32 half-block lists of up to 4096 8-byte records (raster_high.glsl:27); a LOW bin uses the first

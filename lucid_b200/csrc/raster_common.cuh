@@ -560,9 +560,17 @@ static __device__ __noinline__ void warpSortLarge(u32 *gkeys, int n, u32 *skeys)
 
 // Entries with equal quantised depth are ordered by triangle index.  The low key bits only make
 // keys unique (they are list positions that depend on atomic arrival order); this pass makes the
-// final order -- and therefore the image -- independent of them.  Runs of equal depth are rare and
-// short: the lane that finds the start of a run sorts it by insertion.
-template <typename TriOf> __device__ void warpFixDepthTies(u32 *keys, int n, int slot_bits, TriOf triOf) {
+// final order -- and therefore the image -- independent of them.  Runs of equal depth are mostly
+// short: the lane that finds the start of a run sorts it by insertion, 32 runs at a time.  A long run
+// (coplanar stacks, geometry so far away that the 18 / 22 key bits no longer separate it) would make
+// that one lane's work quadratic: a run of long_run entries or more (TIE_RUN_LONG_SMEM when triOf reads shared
+// memory, TIE_RUN_LONG when every comparison is a global load) is handed to onLongRun(first, length) instead and
+// stays in arrival order here -- k_tie_runs (raster_sort.cu) ranks it in the sorted-entry stream.
+// (Ranking long runs inside this kernel was built first: correct, but the extra code took the block sort of the
+// 10M-triangle scene from 0.52 to 0.65 ms -- the kernel sits at the edge of the instruction cache.)
+constexpr int TIE_RUN_LONG = 24, TIE_RUN_LONG_SMEM = 96;
+template <typename TriOf, typename OnLongRun>
+__device__ void warpFixDepthTies(u32 *keys, int n, int slot_bits, int long_run, TriOf triOf, OnLongRun onLongRun) {
 	const int lane = laneId();
 	const u32 slot_mask = (1u << slot_bits) - 1u;
 	for(int i0 = 0; i0 + 1 < n; i0 += 32) {
@@ -575,6 +583,13 @@ template <typename TriOf> __device__ void warpFixDepthTies(u32 *keys, int n, int
 		if(start) {
 			const u32 d = keys[i] >> slot_bits;
 			for(int e = i + 1; e < n && (keys[e] >> slot_bits) == d; e++) {
+				if(e - i >= long_run) {
+					int end = e;
+					while(end < n && (keys[end] >> slot_bits) == d)
+						end++;
+					onLongRun(i, end - i);
+					break;
+				}
 				u32 ke = keys[e], te = triOf(ke & slot_mask);
 				int q = e;
 				while(q > i) {

@@ -339,13 +339,20 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 				__syncwarp();
 			}
 			// depth ties by triangle index: the triangle of a list position is looked up in the list itself
+			// a long run of ties is left to k_tie_runs: where it starts in the sorted-entry stream, and its length
+			auto onLongRun = [&](int first, int len) {
+				const u32 q = atomicAdd(p.tie_runs, 1u);
+				if(q < TIE_RUN_QUEUE)
+					reinterpret_cast<uint2 *>(p.tie_runs + 2)[q] = make_uint2(entry.z + (u32)first, (u32)len);
+			};
 			if(tris_in_smem)
-				warpFixDepthTies(keys, kept, slot_bits, [&](u32 pos) { return keys[SMEM_KEYS / 2 + pos]; });
+				warpFixDepthTies(keys, kept, slot_bits, TIE_RUN_LONG_SMEM, [&](u32 pos) { return keys[SMEM_KEYS / 2 + pos]; }, onLongRun);
 			else if(high)
-				warpFixDepthTies(keys, kept, slot_bits,
-								 [&](u32 pos) { return __ldg(reinterpret_cast<const uint2 *>(list) + pos).x & 0xffffffu; });
+				warpFixDepthTies(keys, kept, slot_bits, TIE_RUN_LONG,
+								 [&](u32 pos) { return __ldg(reinterpret_cast<const uint2 *>(list) + pos).x & 0xffffffu; }, onLongRun);
 			else
-				warpFixDepthTies(keys, kept, slot_bits, [&](u32 pos) { return __ldg(reinterpret_cast<const uint4 *>(list) + pos).x; });
+				warpFixDepthTies(keys, kept, slot_bits, TIE_RUN_LONG, [&](u32 pos) { return __ldg(reinterpret_cast<const uint4 *>(list) + pos).x; },
+								 onLongRun);
 		} else if(PREPASS && kept < count) {
 			warpSortShared(keys, count); // keys are list positions: the kept entries move to the front in list order
 		}
@@ -392,14 +399,56 @@ __global__ void __launch_bounds__(BLOCK_WARPS * 32, SORT_MIN_CTAS) k_block_sort(
 	}
 }
 
+// Long runs of depth ties (k_block_sort's queue): a warp takes a run, copies its stream entries aside, keeps their
+// triangle indices in shared memory, and moves every entry to the place its triangle index has among the run's --
+// the order the short runs get by insertion.  Runs are rare (coplanar stacks, very distant geometry), so the kernel
+// usually finds an empty queue; it exists so that such a frame costs milliseconds, not seconds.
+constexpr int TIE_WARPS = 4;
+__global__ void __launch_bounds__(TIE_WARPS * 32) k_tie_runs(const __grid_constant__ Params p) {
+	extern __shared__ u32 s_tris[]; // TIE_WARPS x MAX_HBLOCK_TRIS
+	const int lane = laneId(), warp = threadIdx.x >> 5;
+	pdlEntry();
+	const u32 n_runs = min(p.tie_runs[0], (u32)TIE_RUN_QUEUE);
+	u32 *tris = s_tris + warp * MAX_HBLOCK_TRIS;
+	uint4 *scratch = p.tie_scratch + (size_t)(blockIdx.x * TIE_WARPS + warp) * (2 * MAX_HBLOCK_TRIS);
+	for(u32 run = blockIdx.x * TIE_WARPS + warp; run < n_runs; run += gridDim.x * TIE_WARPS) {
+		const uint2 r = reinterpret_cast<const uint2 *>(p.tie_runs + 2)[run];
+		const int len = min((int)r.y, MAX_HBLOCK_TRIS);
+		uint4 *rec = p.sorted_rec + r.x, *aux = p.sorted_aux + r.x;
+		for(int e = lane; e < len; e += 32) {
+			const uint4 a = __ldcg(rec + e), b = __ldcg(aux + e);
+			scratch[e] = a, scratch[MAX_HBLOCK_TRIS + e] = b;
+			tris[e] = a.x;
+		}
+		__syncwarp();
+		for(int e = lane; e < len; e += 32) {
+			const u32 te = tris[e];
+			int rank = 0;
+			for(int m = 0; m < len; m++) {
+				const u32 tm = tris[m];
+				rank += (tm < te || (tm == te && m < e)) ? 1 : 0;
+			}
+			__stcg(rec + rank, scratch[e]);
+			__stcg(aux + rank, scratch[MAX_HBLOCK_TRIS + e]);
+		}
+		__syncwarp();
+	}
+}
+
 static int blockSortGrid(int num_sms) { return num_sms * SORT_MIN_CTAS; }
 size_t rasterLargeKeysCount(int num_sms) { return (size_t)blockSortGrid(num_sms) * BLOCK_WARPS * MAX_HBLOCK_TRIS; }
+static int tieRunsGrid(int num_sms) { return num_sms; }
+size_t rasterTieScratchCount(int num_sms) { return (size_t)tieRunsGrid(num_sms) * TIE_WARPS * 2 * MAX_HBLOCK_TRIS; }
 
 void launchBlockSort(const Params &p, u32 background, cudaStream_t stream, int num_sms) {
 	if(opaquePrepass(p))
 		launchPDL(k_block_sort<true>, blockSortGrid(num_sms), BLOCK_WARPS * 32, 0, stream, p, background);
 	else
 		launchPDL(k_block_sort<false>, blockSortGrid(num_sms), BLOCK_WARPS * 32, 0, stream, p, background);
+	static std::once_flag configured[64];
+	constexpr int tie_smem = TIE_WARPS * MAX_HBLOCK_TRIS * (int)sizeof(u32);
+	oncePerDevice(configured, [] { cudaFuncSetAttribute(k_tie_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, tie_smem); });
+	launchPDL(k_tie_runs, tieRunsGrid(num_sms), TIE_WARPS * 32, (size_t)tie_smem, stream, p);
 }
 
 } // namespace lucid

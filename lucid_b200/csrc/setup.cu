@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(256) k_frame_begin(const Params p) {
 	for(int i = first; i < p.bin_count; i += stride)
 		p.bin_cost[i] = 0;
 	if(first == 0)
-		*p.setup_ticket = 0;
+		*p.setup_ticket = 0, p.tie_runs[0] = 0;
 }
 
 // End of a frame: LucidInfo and the per-bin arrays go to the pinned read-back buffer

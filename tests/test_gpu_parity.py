@@ -222,6 +222,37 @@ def test_compact_block_lists_full_size_and_pool_limit():
         r.close()
 
 
+def coplanar_stack(n=700, width=320, height=200):
+    """n coplanar, nearly coincident half-transparent quads with a colour each: every interior block's list is one long
+    run of equal depth keys, and the blend order -- by triangle index -- decides the image."""
+    rng = np.random.default_rng(12)
+    base = np.array([[-1.0, -0.6, 0.0], [1.0, -0.6, 0.0], [1.0, 0.6, 0.0], [-1.0, 0.6, 0.0]], np.float32)
+    pos = np.concatenate([base + np.array([0.0007 * k, 0.0004 * k, 0.0], np.float32) for k in range(n)])
+    quads = np.arange(4 * n, dtype=np.uint32).reshape(n, 4)
+    cols = np.repeat(rng.integers(0, 1 << 24, n, dtype=np.uint32) | np.uint32(0x60000000), 4)  # alpha 96 / 255
+    return scenes._scene(pos, quads, [(0, n, 0, scenes.INST_HAS_VERTEX_COLORS)], [((1.0, 1.0, 1.0), 1.0, (0.0, 0.0, 1.0, 1.0))],
+                         dict(kind="orbit", center=(0.0, 0.0, 0.0), distance=3.0, rot_h=0.0, rot_v=0.0), width, height,
+                         colors=cols, name="coplanar_stack")
+
+
+@pytest.mark.parametrize("n", [40, 150, 300, 700])
+def test_long_runs_of_depth_ties_follow_the_triangle_index(n):
+    """Depth-key ties are ordered by triangle index (the canonical form of SURVEY 8c).  Coplanar stacks make runs as
+    long as the list: short ones are fixed by one lane inside k_block_sort, runs of 96 entries or more (24 where the
+    triangle indices are not in shared memory) are queued and
+    ranked by a warp each in the sorted-entry stream (k_tie_runs) -- lists in shared memory (<= 512 entries), in the
+    shared-memory key array with the list in global memory (<= 1024), and in the L2 key array (700 entries of a HIGH
+    bin stay below that; the promoted bins of n = 700 cover the rest of the paths)."""
+    sc = coplanar_stack(n)
+    o = pu.run_oracle(sc)
+    r, img = pu.run_cuda(sc)
+    try:
+        assert _clean(pu.compare(r, img, o)) == {}
+        assert r.getStats()["fragments"] > 10_000 * n // 40
+    finally:
+        r.close()
+
+
 def test_timers_option(small):
     """LUCID_OPT_TIMERS (the reference's `_timers` shader variants, shared/timers.glsl, lucid_renderer.cpp:754-762):
     the phases' clock ticks land in LucidInfo.setup_timers / bin_dispatcher_timers / raster_timers in the reference's

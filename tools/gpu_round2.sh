@@ -6,7 +6,7 @@
 tag=${1:-r2}
 what=${2:-"tests bench others ncu"}
 full=${3:-"3 1"}
-lpf=${LAUNCHES_PER_FRAME:-10}   # kernels per frame incl. k_info_out
+lpf=${LAUNCHES_PER_FRAME:-11}   # kernels per frame incl. k_tie_runs and k_info_out
 out=gpurun_out
 mkdir -p $out
 nproc > $out/${tag}_nproc.txt

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 STAGE = {"k_instance_select": "setup", "k_quad_cull": "setup", "k_tri_setup": "setup", "k_bin_count": "bin_count",
-         "k_bin_dispatch": "bin_dispatch", "k_raster_bins": "raster", "k_block_sort": "raster", "k_block_shade": "raster"}
+         "k_bin_dispatch": "bin_dispatch", "k_raster_bins": "raster", "k_block_sort": "raster", "k_tie_runs": "raster", "k_block_shade": "raster"}
 out = {}
 for spec in sys.argv[1:]:
     name, _, path = spec.partition("=")
