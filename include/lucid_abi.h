@@ -79,6 +79,16 @@ enum {
 	LUCID_OPT_OPAQUE_PREPASS = 1 << 8
 };
 
+/* lucid_compare_render (lucid_b200.h): the per-pixel rule the last frame's samples are reduced with instead of the
+ * exact front-to-back blend -- the renderers the reference is compared with (docs/readme.md:7-8) */
+enum {
+	LUCID_COMPARE_HW_BLEND = 0, /* SimpleRenderer (src/simple_renderer.cpp:69-132): opaque phase with depth write, then
+								   alpha blending in submission order on an 8-bit target */
+	LUCID_COMPARE_WBOIT = 1,	/* weighted blended OIT (McGuire & Bavoil 2013, weight of eq. 7) */
+	LUCID_COMPARE_MLAB4 = 2,	/* multi-layer alpha blending with four layers (Salvi & Vaidyanathan 2014) */
+	LUCID_COMPARE_MODE_COUNT = 3
+};
+
 /* LUCID_OPT_DEBUG_RASTER (the reference's raster_low_debug / raster_high_debug pipelines, src/lucid_renderer.cpp:
  * 147-158,263-296): the block stage checks what the `DEBUG_ENABLED` code of the shaders checks and writes a record per
  * violation (lucid_read_debug_records):

@@ -168,6 +168,18 @@ int lucid_read_debug_records(lucid_renderer *r, uint32_t *dst, int32_t max_recor
  * checker's restatement of the unit's filter arithmetic against the hardware (tests/test_gpu_parity.py). */
 int lucid_debug_sample_texture(lucid_renderer *r, int32_t slot, const float *uvl, int32_t n, float *out_rgba);
 
+/* ---- comparators (SimpleRenderer::render, src/simple_renderer.cpp:134-196, and the techniques of
+ * docs/readme.md:7-8) ------------------------------------------------------------------------------------------
+ * Re-reduces the SAMPLES of the frame this handle rendered last -- same coverage, same sample colours and depths --
+ * with the per-pixel rule of a cheaper technique (LUCID_COMPARE_*, lucid_abi.h) and copies the RGBA8 image to host
+ * memory: what hardware alpha blending in submission order, weighted blended OIT or 4-layer MLAB would have shown
+ * where lucid_render shows the exact blend.  `config` is the frame's config (lighting, background).  Synchronous;
+ * no lucid_render may be issued on the handle in between.  kernel_ms (may be NULL): device time of the comparator's
+ * kernels -- the time of a CUDA restatement, not of raster-operation hardware.  LUCID_E_STATE without a frame or on
+ * a LUCID_OPT_OPAQUE_PREPASS renderer; the approximate-OIT modes reject LUCID_OPT_ADDITIVE_BLENDING renderers. */
+int lucid_compare_render(lucid_renderer *r, int32_t mode, const LucidConfig *config, void *out_rgba8, size_t pitch_bytes,
+						 float *kernel_ms);
+
 /* ---- frame hand-over of the bin-row split over NVLink, without a collective -------------------------------
  * Every renderer owns a block of LUCID_SYNC_FLAGS 32-bit flags in device memory (zero at creation).  The
  * gathering rank exports its block, the other ranks map it (lucid_ipc_open_image opens any handle exported by

@@ -28,6 +28,7 @@ OPT_ADDITIVE_BLENDING = 1 << 5
 OPT_VISUALIZE_ERRORS = 1 << 6
 OPT_ALPHA_THRESHOLD = 1 << 7
 OPT_OPAQUE_PREPASS = 1 << 8  # extension, include/lucid_abi.h
+COMPARE_HW_BLEND, COMPARE_WBOIT, COMPARE_MLAB4 = 0, 1, 2  # lucid_compare_render modes (include/lucid_abi.h)
 
 
 class Vec4(C.Structure):
@@ -150,6 +151,7 @@ def load_library(build_if_needed: bool = True):
     lib.lucid_signal.argtypes = [vp, vp, C.c_uint32]
     lib.lucid_wait_flags.argtypes = [vp, vp, C.c_int32, C.c_uint32]
     lib.lucid_set_frame_gate.argtypes = [vp, vp, C.c_uint32]
+    lib.lucid_compare_render.argtypes = [vp, C.c_int32, C.POINTER(LucidConfig), vp, C.c_size_t, C.POINTER(C.c_float)]
     _host_prototypes(lib)
     _lib = lib
     return lib
@@ -369,6 +371,16 @@ class LucidRenderer:
 
     def wait(self):
         self._check(self._lib.lucid_wait(self._h), "lucid_wait")
+
+    def compare_render(self, mode: int, config: LucidConfig):
+        """The last frame's samples under a comparator's per-pixel rule (COMPARE_*): SimpleRenderer's hardware alpha
+        blending in submission order (src/simple_renderer.cpp:69-132), weighted blended OIT, 4-layer MLAB.
+        Returns (uint32[h, w] RGBA8 image, device milliseconds of the comparator's kernels)."""
+        img = np.zeros((self.height, self.width), np.uint32)
+        ms = C.c_float(0.0)
+        self._check(self._lib.lucid_compare_render(self._h, mode, C.byref(config), _ptr(img), self.width * 4, C.byref(ms)),
+                    "lucid_compare_render")
+        return img, float(ms.value)
 
     # ---- results -------------------------------------------------------------------------
     def read_info(self) -> np.ndarray:

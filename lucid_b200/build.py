@@ -20,7 +20,7 @@ SO_PATH = os.path.join(HERE, "_lucid_b200.so")
 HOST_SO_PATH = os.path.join(HERE, "_lucid_host.so")
 
 CUDA_SOURCES = ["csrc/setup.cu", "csrc/binning.cu", "csrc/raster_bins.cu", "csrc/raster_sort.cu", "csrc/raster_shade.cu",
-                "csrc/sync.cu", "csrc/capi.cu", "csrc/quadgen.cu"]
+                "csrc/sync.cu", "csrc/capi.cu", "csrc/quadgen.cu", "csrc/comparators.cu"]
 HOST_SOURCES = ["host/lucid_host.cpp", "host/lucid_renderer.cpp"]
 HEADERS = ["csrc/common.cuh", "csrc/raster_common.cuh", "csrc/quadgen_rules.h", "../include/lucid_quadgen.h", "../include/lucid_colour_tables.h", "../include/lucid_abi.h", "../include/lucid_b200.h", "../include/lucid_host.h",
            "../include/lucid_renderer.hpp"]

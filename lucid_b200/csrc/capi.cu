@@ -13,6 +13,12 @@
 
 using namespace lucid;
 
+namespace lucid {
+size_t compareScratchKeys(int num_sms);
+void launchCompare(const Params &p, const LucidConfig &cfg, int mode, u32 *order, u64 *scratch, u32 *ticket, u32 *out_image,
+				   cudaStream_t stream, int num_sms);
+} // namespace lucid
+
 static thread_local std::string g_create_error;
 
 // Programmatic dependent launch per frame.  Overlapping the launch of kernel n+1 with the tail of kernel n pays on
@@ -99,6 +105,12 @@ struct lucid_renderer {
 	cudaEvent_t ev[TIMING_RING][8];
 	bool ev_staged[TIMING_RING] = {};
 	float last_frame_ms = 0.0f; // the latest frame known to be finished (programmatic dependent launch: on or off)
+	// lucid_compare_render (comparators.cu), allocated on first use: submission order per visible-quad slot, sort
+	// scratch for lists over 1024 entries, the work-item ticket, the comparator's image
+	u32 *cmp_order = nullptr;
+	u64 *cmp_scratch = nullptr;
+	u32 *cmp_ticket = nullptr;
+	u32 *cmp_image = nullptr;
 	long long frame_counter = 0;
 	bool pending = false;
 };
@@ -923,6 +935,51 @@ int lucid_read_debug_records(lucid_renderer *r, uint32_t *dst, int32_t max_recor
 	const size_t stored = std::min(std::min((size_t)n, (size_t)max_records), (size_t)LUCID_DEBUG_MAX_RECORDS);
 	if(stored)
 		CU(cudaMemcpy(dst, r->p.debug_records + 2, stored * LUCID_DEBUG_RECORD_WORDS * 4, cudaMemcpyDeviceToHost));
+	return LUCID_OK;
+}
+
+int lucid_compare_render(lucid_renderer *r, int32_t mode, const LucidConfig *config, void *out_rgba8, size_t pitch_bytes,
+						 float *kernel_ms) {
+	if(!r)
+		return LUCID_E_INVALID;
+	if(!config || !out_rgba8 || mode < 0 || mode >= LUCID_COMPARE_MODE_COUNT || pitch_bytes < (size_t)r->p.width * 4)
+		return fail(r, LUCID_E_INVALID, "lucid_compare_render: bad argument");
+	if(r->frame_counter == 0)
+		return fail(r, LUCID_E_STATE, "lucid_compare_render: no frame has been rendered (the comparators re-reduce the last frame's samples)");
+	if(r->p.opts & LUCID_OPT_OPAQUE_PREPASS)
+		return fail(r, LUCID_E_STATE, "lucid_compare_render: LUCID_OPT_OPAQUE_PREPASS drops samples before they reach the entry stream");
+	if(mode != LUCID_COMPARE_HW_BLEND && (r->p.opts & LUCID_OPT_ADDITIVE_BLENDING))
+		return fail(r, LUCID_E_INVALID, "lucid_compare_render: the approximate-OIT comparators are defined for the normal blend only");
+	int rc = lucid_wait(r); // a frame that overflowed its storage has no complete entry stream either
+	if(rc)
+		return rc;
+	CU(cudaSetDevice(r->ci.device));
+	if(!r->cmp_order) {
+		CU(devAlloc(r, &r->cmp_order, (size_t)r->p.max_visible_quads));
+		CU(devAlloc(r, &r->cmp_scratch, compareScratchKeys(r->num_sms)));
+		CU(devAlloc(r, &r->cmp_ticket, 4));
+		CU(devAlloc(r, &r->cmp_image, (size_t)r->p.width * r->p.height));
+	}
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
+	CU(cudaEventCreate(&t0));
+	CU(cudaEventCreate(&t1));
+	cudaEventRecord(t0, r->stream);
+	launchCompare(r->p, *config, mode, r->cmp_order, r->cmp_scratch, r->cmp_ticket, r->cmp_image, r->stream, r->num_sms);
+	cudaEventRecord(t1, r->stream);
+	cudaError_t e = cudaStreamSynchronize(r->stream);
+	if(e == cudaSuccess)
+		e = cudaGetLastError();
+	float ms = 0.0f;
+	if(e == cudaSuccess)
+		e = cudaEventElapsedTime(&ms, t0, t1);
+	cudaEventDestroy(t0);
+	cudaEventDestroy(t1);
+	if(e != cudaSuccess)
+		return failCuda(r, e, "lucid_compare_render");
+	if(kernel_ms)
+		*kernel_ms = ms;
+	CU(cudaMemcpy2D(out_rgba8, pitch_bytes, r->cmp_image, (size_t)r->p.width * 4, (size_t)r->p.width * 4, r->p.height,
+					cudaMemcpyDeviceToHost));
 	return LUCID_OK;
 }
 

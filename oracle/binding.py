@@ -58,6 +58,10 @@ def load():
     lib.oracle_shade_probe.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_float)]
     lib.oracle_shade_probe.restype = C.c_uint32
     lib.oracle_set_reference_colour.argtypes = [vp, C.c_int]
+    lib.oracle_set_comparators.argtypes = [vp, C.c_int]
+    lib.oracle_read_compare_image.argtypes = [vp, C.c_int, vp]
+    lib.oracle_fn_compare_pixel.argtypes = [C.c_int, vp, C.c_int, C.c_uint32, C.c_int]
+    lib.oracle_fn_compare_pixel.restype = C.c_uint32
     lib.oracle_texture_samples.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     for name in ("oracle_final_shade_fast", "oracle_final_shade_reference"):
         getattr(lib, name).argtypes = [C.c_float, C.c_float]
@@ -68,6 +72,12 @@ def load():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def compare_pixel(mode: int, samples, bg8: int, additive: bool = False) -> int:
+    """One pixel through a comparator: samples = rows of (submission order, depth as float bits, RGBA8, opaque)."""
+    s = np.ascontiguousarray(samples, np.uint32).reshape(-1, 4)
+    return int(load().oracle_fn_compare_pixel(mode, _ptr(s), s.shape[0], bg8, int(additive)))
 
 
 class Oracle:
@@ -110,6 +120,16 @@ class Oracle:
 
     def set_bin_range(self, begin, end):
         self.lib.oracle_set_bin_range(self.h, begin, end)
+
+    def set_comparators(self, on: bool):
+        """Also reduce the frame's samples the way the comparators of SURVEY 8 f4 would (read_compare_image)."""
+        self.lib.oracle_set_comparators(self.h, int(on))
+
+    def read_compare_image(self, mode: int):
+        """mode 0: hardware alpha blending in submission order, 1: weighted blended OIT, 2: 4-layer MLAB."""
+        out = np.zeros((self.height, self.width), np.uint32)
+        self.lib.oracle_read_compare_image(self.h, mode, _ptr(out))
+        return out
 
     def set_scene(self, scene):
         pos = np.ascontiguousarray(scene["positions"], np.float32)

@@ -335,6 +335,16 @@ struct Oracle {
 			return quad_aabbs[0][q];
 		return quad_aabbs[1][(u32)(max_visible_quads - 1) - q];
 	}
+	u32 quadInputId(u32 q) const {
+		if((int)q < (int)quad_aabbs[0].size())
+			return quad_input_id[0][q];
+		return quad_input_id[1][(u32)(max_visible_quads - 1) - q];
+	}
+	// Comparators (oracle_set_comparators): what the frame's samples blend to under [0] hardware alpha
+	// blending in submission order (SimpleRenderer, src/simple_renderer.cpp:69-132,134-196), [1] weighted blended
+	// OIT, [2] multi-layer alpha blending with four layers -- see comparePixel
+	bool comparators = false;
+	std::vector<u32> compare_image[3];
 	int *cnt(int which) { return counts.data() + (size_t)which * bin_count; }
 
 	void setup();
@@ -1174,6 +1184,101 @@ struct Reducer {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Comparators: the same samples -- RGBA8 colour and depth of every covered (pixel, triangle) pair, as
+// the exact renderer shades them -- reduced the way the renderers LucidRaster is compared with would reduce them.
+// All three start with the reference's opaque phase (SimpleRenderer::renderPhase(opaque = true),
+// src/simple_renderer.cpp:69-89,176-177: depth test `less` + depth write, no blending, draw calls in submission
+// order): the nearest sample of an INST_IS_OPAQUE instance gives the pixel's base colour (alpha ignored) and the
+// depth zo every other sample is tested against; among equal depths the first submitted wins.  Transparent samples
+// (instances without INST_IS_OPAQUE) pass when strictly nearer than zo (sample depths are inverse ray positions:
+// larger = nearer) and are visited in SUBMISSION order: instance, quad of the instance, triangle of the quad.
+//   0  hardware alpha blending (renderPhase(opaque = false): VBlendFactor src_alpha / one_minus_src_alpha, or
+//      src_alpha / one with additive blending) on an 8-bit unorm render target: every blend reads the target's
+//      bytes and rounds its result back to bytes
+//   1  weighted blended OIT (McGuire & Bavoil, JCGT 2013, weight of eq. 7 on the ray position)
+//   2  multi-layer alpha blending (Salvi & Vaidyanathan, I3D 2014) with four layers
+struct CmpSample {
+	u32 order; // input quad * 2 + second triangle
+	float depth;
+	u32 color;
+	bool opaque;
+};
+inline u32 quant8(float v) { return f2u(saturate(v) * 255.0f + 0.5f); }
+
+u32 comparePixel(int mode, const std::vector<CmpSample> &s, u32 bg8, bool additive) {
+	u32 base8 = bg8;
+	float zo = -INF;
+	for(const CmpSample &x : s)
+		if(x.opaque && x.depth > zo)
+			zo = x.depth, base8 = x.color;
+	if(mode == 0) {
+		u32 dst8 = base8;
+		for(const CmpSample &x : s) {
+			if(x.opaque || x.color == 0 || !(x.depth > zo))
+				continue;
+			V4 c = decodeRGBA8(x.color), d = decodeRGBA8(dst8);
+			float out[3];
+			for(int i = 0; i < 3; i++)
+				out[i] = additive ? fmaf(c[i], c.w, d[i]) : fmaf(c[i], c.w, d[i] * (1.0f - c.w));
+			dst8 = quant8(out[0]) | (quant8(out[1]) << 8) | (quant8(out[2]) << 16);
+		}
+		return dst8 | 0xff000000u;
+	}
+	V4 base = decodeRGBA8(base8);
+	float out[3];
+	if(mode == 1) {
+		float acc[3] = {0.0f, 0.0f, 0.0f}, acc_a = 0.0f, trans = 1.0f;
+		for(const CmpSample &x : s) {
+			if(x.opaque || x.color == 0 || !(x.depth > zo))
+				continue;
+			V4 c = decodeRGBA8(x.color);
+			float z = rcp(x.depth);
+			float z5 = z * 0.2f, t2 = z5 * z5;
+			float z200 = z * 0.005f, s2 = z200 * z200, s6 = (s2 * s2) * s2;
+			float den = (1e-5f + t2) + s6;
+			float wz = fmin2(fmax2(10.0f / den, 1e-2f), 3e3f);
+			float w = c.w * wz, aw = c.w * w;
+			for(int i = 0; i < 3; i++)
+				acc[i] = fmaf(c[i], aw, acc[i]);
+			acc_a = acc_a + aw;
+			trans = fmaf(-c.w, trans, trans);
+		}
+		float den = fmax2(acc_a, 1e-5f);
+		for(int i = 0; i < 3; i++)
+			out[i] = fmaf(acc[i] / den, 1.0f - trans, base[i] * trans);
+	} else {
+		// layers near to far; an empty layer is (0, 0, 0), transmittance 1, at depth -inf
+		float lr[4], lg[4], lb[4], lt[4], ld[4];
+		for(int i = 0; i < 4; i++)
+			lr[i] = lg[i] = lb[i] = 0.0f, lt[i] = 1.0f, ld[i] = -INF;
+		for(const CmpSample &x : s) {
+			if(x.opaque || x.color == 0 || !(x.depth > zo))
+				continue;
+			V4 c = decodeRGBA8(x.color);
+			float fr = c.x * c.w, fg = c.y * c.w, fb = c.z * c.w, ft = 1.0f - c.w, fd = x.depth;
+			// insertion: the fragment goes in front of the first layer that is farther; what falls out at the far
+			// end is merged under the last layer
+			for(int i = 0; i < 4; i++)
+				if(fd > ld[i]) {
+					std::swap(fr, lr[i]), std::swap(fg, lg[i]), std::swap(fb, lb[i]);
+					std::swap(ft, lt[i]), std::swap(fd, ld[i]);
+				}
+			lr[3] = fmaf(fr, lt[3], lr[3]), lg[3] = fmaf(fg, lt[3], lg[3]), lb[3] = fmaf(fb, lt[3], lb[3]);
+			lt[3] = lt[3] * ft;
+		}
+		float trans = 1.0f;
+		out[0] = out[1] = out[2] = 0.0f;
+		for(int i = 0; i < 4; i++) {
+			out[0] = fmaf(lr[i], trans, out[0]), out[1] = fmaf(lg[i], trans, out[1]), out[2] = fmaf(lb[i], trans, out[2]);
+			trans = trans * lt[i];
+		}
+		for(int i = 0; i < 3; i++)
+			out[i] = fmaf(base[i], trans, out[i]);
+	}
+	return quant8(out[0]) | (quant8(out[1]) << 8) | (quant8(out[2]) << 16) | 0xff000000u;
+}
+
+// ------------------------------------------------------------------------------------------------
 // rasterisation of one bin
 
 // scanline.glsl:13-26 + raster.glsl:116-140: four rows of [xmin,xmax] spans, 5 bits each
@@ -1490,6 +1595,33 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 						for(int i = 0; i < 3; i++)
 							red[p].out_color[i] = saturate(red[p].out_color[i]);
 
+				if(comparators) {
+					std::vector<CmpSample> cmp[32];
+					for(const Entry &e : list) {
+						const RowTri &rt = rows[g][e.slot];
+						const bool opaque = (tri(rt.tri_idx).depth.w & LUCID_INST_IS_OPAQUE) != 0;
+						const u32 order = quadInputId(rt.tri_idx >> 1) * 2 + (rt.tri_idx & 1);
+						for(u32 bits = halfPixelMask(halfSpans(rt.mins[half], rt.maxs[half], startx)); bits != 0; bits &= bits - 1) {
+							int pid = findLSB(bits);
+							CmpSample cs;
+							cs.order = order, cs.opaque = opaque;
+							cs.color = shadeSampleFast(hb_x + (pid & 7), hb_y + (pid >> 3), rt.tri_idx, cs.depth);
+							cmp[pid].push_back(cs);
+						}
+					}
+					const LucidVec4 &bg = cfg.background_color;
+					const u32 bg8 = quant8(bg.x) | (quant8(bg.y) << 8) | (quant8(bg.z) << 16) | 0xff000000u;
+					for(int p = 0; p < 32; p++) {
+						int gx = hb_x + (p & 7), gy = hb_y + (p >> 3);
+						if(gx >= width || gy >= height)
+							continue;
+						std::stable_sort(cmp[p].begin(), cmp[p].end(),
+										 [](const CmpSample &a, const CmpSample &b) { return a.order < b.order; });
+						for(int mode = 0; mode < 3; mode++)
+							compare_image[mode][(size_t)gy * width + gx] = comparePixel(mode, cmp[p], bg8, additive);
+					}
+				}
+
 				stats[0] += frag_total;
 				stats[1] += tri_count;
 				for(int p = 0; p < 32; p++) {
@@ -1580,6 +1712,8 @@ void Oracle::raster() {
 					   image_f[i * 3 + 2] = saturate(bg.z);
 	frag_counts.assign(npix, 0);
 	bin_level.assign(bin_count, 0);
+	for(int mode = 0; mode < 3; mode++)
+		compare_image[mode].assign(comparators ? npix : 0, bg8);
 
 	int *low = cnt(LUCID_CNT_LOW_BINS), *high = cnt(LUCID_CNT_HIGH_BINS);
 	int n_low = info.bin_level_counts[LUCID_BIN_LEVEL_LOW];
@@ -1914,6 +2048,21 @@ void oracle_texture_samples(void *h, int slot, const float *uvl, int n, float *o
 }
 // 1: colour arithmetic in the reference's operation order (pow by polynomial, one rounding per operation);
 // 0 (default): the product's colour contract (fused multiply-adds, table sRGB) that the kernels reproduce bit for bit
+void oracle_set_comparators(void *h, int on) { ((Oracle *)h)->comparators = on != 0; }
+void oracle_read_compare_image(void *h, int mode, uint32_t *rgba8) {
+	Oracle *o = (Oracle *)h;
+	if(mode >= 0 && mode < 3 && !o->compare_image[mode].empty())
+		memcpy(rgba8, o->compare_image[mode].data(), o->compare_image[mode].size() * 4);
+}
+// one pixel through a comparator: samples as (order, depth bits, RGBA8, opaque) words, sorted by order here
+uint32_t oracle_fn_compare_pixel(int mode, const uint32_t *samples, int n, uint32_t bg8, int additive) {
+	std::vector<CmpSample> s(n);
+	for(int i = 0; i < n; i++)
+		s[i].order = samples[i * 4], s[i].depth = bitsToFloat(samples[i * 4 + 1]), s[i].color = samples[i * 4 + 2],
+		s[i].opaque = samples[i * 4 + 3] != 0;
+	std::stable_sort(s.begin(), s.end(), [](const CmpSample &a, const CmpSample &b) { return a.order < b.order; });
+	return comparePixel(mode, s, bg8, additive != 0);
+}
 void oracle_set_reference_colour(void *h, int on) { ((Oracle *)h)->reference_colour = on != 0; }
 // finalShading of one channel in both forms (tests/test_colour_contract.py)
 float oracle_final_shade_fast(float c, float light) { return finalShadeFast(c, light); }
