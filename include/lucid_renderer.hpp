@@ -164,6 +164,7 @@ class LucidRenderer {
 	int verifyInfo();
 	std::vector<StatsGroup> getStats() const;
 	const LucidInfo &lastInfo() const { return m_info; }
+	const LucidConfig &lastConfig() const { return m_config; } // what setupInputData made of the last context
 	Ex stageTimes(float ms[8]);
 
 	Opts opts() const { return m_opts; }
@@ -192,7 +193,30 @@ class LucidRenderer {
 	std::vector<float> m_instance_uv_rects;
 	std::vector<uint32_t> m_last_info;
 	LucidInfo m_info;
+	LucidConfig m_config;
 	bool m_last_info_updated = false;
+};
+
+// The comparison renderer of the reference's application (src/simple_renderer.h:19-60, SimpleRenderer::render,
+// src/simple_renderer.cpp:134-196): the same RenderContext through the fixed-function pipeline -- an opaque phase with
+// depth write, then alpha blending in submission order -- instead of the exact blend.  Here it is a second reduction
+// of the samples the LucidRenderer it is bound to produces for the context (lucid_compare_render):
+// render() draws the context with that renderer and writes the comparator's image to ctx.out_image (host memory).
+// Besides the reference's hardware blending, the two approximate order-independent techniques the reference is
+// measured against (docs/readme.md:7-8) can be selected.
+class SimpleRenderer {
+  public:
+	enum class Technique { hw_blend = LUCID_COMPARE_HW_BLEND, wboit = LUCID_COMPARE_WBOIT, mlab4 = LUCID_COMPARE_MLAB4 };
+
+	Ex exConstruct(LucidRenderer &sample_source, Technique = Technique::hw_blend);
+	// wireframe (VPolygonMode::line in the reference) is not available: there is no line rasteriser on this path
+	Ex render(const RenderContext &ctx, bool wireframe = false);
+	float lastKernelMs() const { return m_kernel_ms; } // device time of the comparator's kernels
+
+  private:
+	LucidRenderer *m_source = nullptr;
+	Technique m_technique = Technique::hw_blend;
+	float m_kernel_ms = 0.0f;
 };
 
 } // namespace lucid_b200

@@ -95,7 +95,7 @@ C_ABI_SYMBOLS = [
     "lucid_debug_sample_texture", "lucid_sync_pointer", "lucid_ipc_export_sync", "lucid_signal", "lucid_wait_flags", "lucid_set_frame_gate",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
     "lucid_host_camera_matrices", "lucid_host_build_instances", "lucid_host_packet_size",
-    "lucid_quadgen", "lucid_quadgen_last_error", "lucid_read_debug_records",
+    "lucid_quadgen", "lucid_quadgen_last_error", "lucid_read_debug_records", "lucid_compare_render",
 ]
 
 

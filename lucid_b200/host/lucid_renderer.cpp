@@ -167,6 +167,7 @@ Ex LucidRenderer::render(const Context &ctx) {
 	lucid_host_make_config(&ctx.camera, &ctx.lighting, background, ctx.config.backface_culling ? 1 : 0, n,
 						   m_max_dispatches, &config);
 
+	m_config = config;
 	int rc = lucid_render(m_handle, &config, m_instances.data(), m_instance_colors.data(),
 						  m_instance_uv_rects.data(), n, ctx.out_image, ctx.out_pitch_bytes, ctx.out_memory, 0);
 	if(rc != LUCID_OK)
@@ -177,6 +178,43 @@ Ex LucidRenderer::render(const Context &ctx) {
 	memcpy(&m_info, m_last_info.data(), sizeof(m_info));
 	m_last_info_updated = true;
 	return {};
+}
+
+Ex SimpleRenderer::exConstruct(LucidRenderer &sample_source, Technique technique) {
+	Ex e;
+	if(!sample_source.handle()) {
+		e.code = LUCID_E_STATE, e.message = "SimpleRenderer::exConstruct: the LucidRenderer has not been constructed";
+		return e;
+	}
+	m_source = &sample_source, m_technique = technique;
+	return e;
+}
+
+Ex SimpleRenderer::render(const RenderContext &ctx, bool wireframe) {
+	Ex e;
+	if(!m_source) {
+		e.code = LUCID_E_STATE, e.message = "SimpleRenderer::render: exConstruct has not succeeded";
+		return e;
+	}
+	if(wireframe || !ctx.out_image || ctx.out_memory != LUCID_MEM_HOST) {
+		e.code = LUCID_E_INVALID;
+		e.message = wireframe ? "SimpleRenderer::render: no wireframe mode on this path" :
+								"SimpleRenderer::render: the comparator's image goes to host memory (out_image, LUCID_MEM_HOST)";
+		return e;
+	}
+	// the exact frame of the context stays in the LucidRenderer's own image; its samples are reduced a second time
+	RenderContext frame = ctx;
+	frame.out_image = nullptr, frame.out_pitch_bytes = 0, frame.out_memory = LUCID_MEM_NONE;
+	e = m_source->render(frame);
+	if(!e)
+		return e;
+	int rc = lucid_compare_render(m_source->handle(), int(m_technique), &m_source->lastConfig(), ctx.out_image,
+								  ctx.out_pitch_bytes, &m_kernel_ms);
+	if(rc != LUCID_OK) {
+		e.code = rc;
+		e.message = std::string("SimpleRenderer::render: ") + lucid_last_error(m_source->handle());
+	}
+	return e;
 }
 
 Ex LucidRenderer::stageTimes(float ms[8]) {

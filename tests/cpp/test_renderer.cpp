@@ -140,6 +140,46 @@ int main(int argc, char **argv) {
 	if(!renderer.stageTimes(ms))
 		return fail("stageTimes");
 	printf("frame %.3f ms\n", ms[7]);
+
+	// The reference's comparison renderer on the same context (SimpleRenderer, src/simple_renderer.cpp:134-196) and the
+	// two approximate techniques.  Every sample of this scene has the same colour, so the blend order cannot matter:
+	// hardware blending gives the exact image up to its rounding to bytes after every layer (a = 0.25: at most
+	// 0.5 / (1 - 0.75) = 2 steps of 1/255), weighted blended OIT averages equal colours and keeps the exact
+	// coverage, and MLAB merges equal colours.
+	const SimpleRenderer::Technique techniques[3] = {SimpleRenderer::Technique::hw_blend, SimpleRenderer::Technique::wboit,
+													 SimpleRenderer::Technique::mlab4};
+	const char *names[3] = {"hardware blending", "weighted blended OIT", "4-layer MLAB"};
+	for(int t = 0; t < 3; t++) {
+		SimpleRenderer simple;
+		if(simple.render(ctx))
+			return fail("SimpleRenderer::render succeeded without exConstruct");
+		ex = simple.exConstruct(renderer, techniques[t]);
+		if(!ex)
+			return fail(ex.message.c_str());
+		std::vector<uint32_t> cmp((size_t)width * height, 0u);
+		RenderContext cctx = ctx;
+		cctx.out_image = cmp.data();
+		if(simple.render(cctx, true))
+			return fail("wireframe accepted");
+		ex = simple.render(cctx);
+		if(!ex)
+			return fail(ex.message.c_str());
+		int worst = 0;
+		long long differing = 0;
+		for(size_t i = 0; i < image.size(); i++) {
+			if((image[i] == bg) != (cmp[i] == bg))
+				return fail("comparator coverage differs from the exact frame");
+			for(int ch = 0; ch < 3; ch++) {
+				int d = std::abs((int)((image[i] >> (8 * ch)) & 0xff) - (int)((cmp[i] >> (8 * ch)) & 0xff));
+				worst = std::max(worst, d);
+				differing += d != 0;
+			}
+		}
+		printf("%s: worst difference to the exact frame %d/255 (%lld channel values differ), kernels %.3f ms\n", names[t], worst,
+			   differing, simple.lastKernelMs());
+		if(worst > 3)
+			return fail("comparator image off on a scene of equal colours");
+	}
 	printf("OK\n");
 	return 0;
 }
