@@ -59,6 +59,8 @@ def load():
     lib.oracle_shade_probe.restype = C.c_uint32
     lib.oracle_set_reference_colour.argtypes = [vp, C.c_int]
     lib.oracle_set_comparators.argtypes = [vp, C.c_int]
+    lib.oracle_set_reverse_ties.argtypes = [vp, C.c_int]
+    lib.oracle_read_tie_pixels.argtypes = [vp, vp, vp]
     lib.oracle_read_compare_image.argtypes = [vp, C.c_int, vp]
     lib.oracle_fn_compare_pixel.argtypes = [C.c_int, vp, C.c_int, C.c_uint32, C.c_int]
     lib.oracle_fn_compare_pixel.restype = C.c_uint32
@@ -120,6 +122,18 @@ class Oracle:
 
     def set_bin_range(self, begin, end):
         self.lib.oracle_set_bin_range(self.h, begin, end)
+
+    def set_reverse_ties(self, on: bool):
+        """Test hook: every run of equal depth keys in reverse order (the canonical order is the triangle index)."""
+        self.lib.oracle_set_reverse_ties(self.h, int(on))
+
+    def read_tie_pixels(self):
+        """(uint8[h, w] mask of the pixels covered by two or more entries of one run of equal depth keys -- the only
+        pixels whose colour can depend on the tie order --, dict(lists, entries, pixels))."""
+        mask = np.zeros((self.height, self.width), np.uint8)
+        st = np.zeros(3, np.uint64)
+        self.lib.oracle_read_tie_pixels(self.h, _ptr(mask), _ptr(st))
+        return mask, dict(lists=int(st[0]), entries=int(st[1]), pixels=int(st[2]))
 
     def set_comparators(self, on: bool):
         """Also reduce the frame's samples the way the comparators of SURVEY 8 f4 would (read_compare_image)."""

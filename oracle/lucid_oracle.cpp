@@ -345,6 +345,14 @@ struct Oracle {
 	// OIT, [2] multi-layer alpha blending with four layers -- see comparePixel
 	bool comparators = false;
 	std::vector<u32> compare_image[3];
+	// Depth-key ties ("report pixels whose block had depth-key ties separately").  The reference leaves
+	// entries of equal quantised depth in the arrival order of racing atomics; here they follow the triangle index.
+	// tie_pixels marks the pixels covered by two or more entries of one run of equal keys -- the only pixels whose
+	// colour can depend on that convention; tie_stats: [0] lists with a run [1] entries in runs [2] marked pixels.
+	// reverse_ties renders the frame with every run reversed (test hook: the images may differ at marked pixels only).
+	std::vector<uint8_t> tie_pixels;
+	unsigned long long tie_stats[3] = {};
+	bool reverse_ties = false;
 	int *cnt(int which) { return counts.data() + (size_t)which * bin_count; }
 
 	void setup();
@@ -1515,9 +1523,57 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 				std::sort(list.begin(), list.end(),
 						  [](const Entry &a, const Entry &b) { return a.key < b.key; });
 
+			// runs of equal quantised depth: their order is a convention (triangle index), not the reference's
+			std::vector<std::pair<int, int>> tie_runs;
+			{
+				const int slot_bits = high ? 14 : 10;
+				for(size_t a = 0; a < list.size();) {
+					size_t b = a + 1;
+					while(b < list.size() && (list[b].key >> slot_bits) == (list[a].key >> slot_bits))
+						b++;
+					if(b - a > 1) {
+						tie_runs.push_back(std::make_pair((int)a, (int)b));
+						if(reverse_ties)
+							std::reverse(list.begin() + a, list.begin() + b);
+					}
+					a = b;
+				}
+				if(!tie_runs.empty()) {
+					unsigned long long in_runs = 0;
+					for(auto &r : tie_runs)
+						in_runs += (unsigned long long)(r.second - r.first);
+#pragma omp atomic
+					tie_stats[0] += 1;
+#pragma omp atomic
+					tie_stats[1] += in_runs;
+				}
+			}
+
 			int halves = high ? 1 : 2;
 			for(int half = 0; half < halves; half++) {
 				int hb_y = pos_y + g * rows_per_group + half * 4; // top row of the half-block
+				{
+					u32 tied = 0;
+					for(auto &r : tie_runs) {
+						u32 once = 0;
+						for(int i = r.first; i < r.second; i++) {
+							const RowTri &rt = rows[g][list[i].slot];
+							const u32 bits = halfPixelMask(halfSpans(rt.mins[half], rt.maxs[half], startx));
+							tied |= once & bits, once |= bits;
+						}
+					}
+					unsigned long long marked = 0;
+					for(u32 b = tied; b != 0; b &= b - 1) {
+						const int pid = findLSB(b);
+						const int gx = pos_x + bx * 8 + (pid & 7), gy = hb_y + (pid >> 3);
+						if(gx < width && gy < height)
+							tie_pixels[(size_t)gy * width + gx] = 1, marked++;
+					}
+					if(marked) {
+#pragma omp atomic
+						tie_stats[2] += marked;
+					}
+				}
 				int hb_x = pos_x + bx * 8;
 				Reducer red[32];
 				std::vector<std::pair<float, u32>> exact[32];
@@ -1714,6 +1770,8 @@ void Oracle::raster() {
 	bin_level.assign(bin_count, 0);
 	for(int mode = 0; mode < 3; mode++)
 		compare_image[mode].assign(comparators ? npix : 0, bg8);
+	tie_pixels.assign(npix, 0);
+	tie_stats[0] = tie_stats[1] = tie_stats[2] = 0;
 
 	int *low = cnt(LUCID_CNT_LOW_BINS), *high = cnt(LUCID_CNT_HIGH_BINS);
 	int n_low = info.bin_level_counts[LUCID_BIN_LEVEL_LOW];
@@ -2048,6 +2106,14 @@ void oracle_texture_samples(void *h, int slot, const float *uvl, int n, float *o
 }
 // 1: colour arithmetic in the reference's operation order (pow by polynomial, one rounding per operation);
 // 0 (default): the product's colour contract (fused multiply-adds, table sRGB) that the kernels reproduce bit for bit
+void oracle_set_reverse_ties(void *h, int on) { ((Oracle *)h)->reverse_ties = on != 0; }
+void oracle_read_tie_pixels(void *h, uint8_t *dst, unsigned long long *stats3) {
+	Oracle *o = (Oracle *)h;
+	if(dst)
+		memcpy(dst, o->tie_pixels.data(), o->tie_pixels.size());
+	if(stats3)
+		memcpy(stats3, o->tie_stats, sizeof(o->tie_stats));
+}
 void oracle_set_comparators(void *h, int on) { ((Oracle *)h)->comparators = on != 0; }
 void oracle_read_compare_image(void *h, int mode, uint32_t *rgba8) {
 	Oracle *o = (Oracle *)h;

@@ -284,3 +284,36 @@ def test_bin_range_split_composes_to_the_full_frame(small):
             image[by * 32:(by + 1) * 32, bx * 32:(bx + 1) * 32] = img[by * 32:(by + 1) * 32, bx * 32:(bx + 1) * 32]
     assert np.array_equal(image, full.read_image())
     assert frags == int(full.info[60])
+
+
+def test_depth_key_ties_are_reported_and_bound_the_order_dependence(small):
+    """"report pixels whose block had depth-key ties separately".  The reference leaves entries of equal
+    quantised depth in the arrival order of racing atomics; checker and kernels order them by triangle index.  The
+    checker marks the pixels covered by two or more entries of one run of equal keys: rendering every run in REVERSE
+    order may change marked pixels only.  On the parity scenes it changes none at all (the per-pixel window orders
+    samples by their own depth); on a coplanar stack -- equal sample depths too -- it changes every covered pixel."""
+    from tests.test_gpu_parity import coplanar_stack
+
+    def both_orders(sc):
+        cfg, inst, cols, rects = api.prepare_frame(sc)
+        out = []
+        for reverse in (False, True):
+            o = binding.Oracle(sc["width"], sc["height"], 0, 1 << 20, threads=8)
+            o.set_reverse_ties(reverse)
+            o.set_scene(sc)
+            o.render(cfg, inst, cols, rects)
+            mask, st = o.read_tie_pixels()
+            out.append((o.read_image(), mask, st, o.read_frag_counts()))
+        return out
+
+    for name in ("meshlets", "hairball", "arch"):
+        (img, mask, st, _), (img_r, mask_r, st_r, _) = both_orders(small[name])
+        assert st == st_r and np.array_equal(mask, mask_r)
+        assert st["lists"] > 0 and st["entries"] >= 2 * st["lists"] and st["pixels"] == int(mask.sum())
+        differ = img != img_r
+        assert not (differ & (mask == 0)).any()
+        assert int(differ.sum()) == 0
+    (img, mask, st, frags), (img_r, _, _, _) = both_orders(coplanar_stack(40))
+    covered = frags > 0
+    assert np.array_equal(mask != 0, covered)
+    assert np.array_equal(img != img_r, covered)
