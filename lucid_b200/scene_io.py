@@ -95,13 +95,16 @@ def _read_string(f) -> str:
 
 
 def load_scene(path_or_file, width: int = 1920, height: int = 1080, name: str | None = None, quads: str = "file",
-               square_weight: float = 4.0, device: int = 0) -> dict:
+               square_weight: float = 4.0, device: int = 0, cluster: bool = False) -> dict:
     """Reads a `.scene` file (Scene::load, src/scene.cpp:119-151) into a scene dict.
 
     quads="file" takes every mesh's quads as stored; quads="gpu" pairs the mesh's triangles again on the GPU
     (Scene::generateQuads, src/scene.cpp:237-247, through lucid_quadgen: needs the CUDA library) -- for files that carry
     triangles only, or to re-pair with another squareness weight (the reference's converter uses the input scene's
-    quad_squareness, its procedural scenes 4.0: src/scene_convert.cpp:430, scene_setup.cpp:186)."""
+    quad_squareness, its procedural scenes 4.0: src/scene_convert.cpp:430, scene_setup.cpp:186).
+
+    cluster=True lists every mesh's quads in Morton order, so that the 1024-quad instances uploadInstances cuts are
+    spatially compact (lucid_b200.clustering; the goal of the reference's meshPartition, src/meshlet.cpp:68-222)."""
     if quads not in ("file", "gpu"):
         raise ValueError('quads must be "file" or "gpu"')
     f = open(path_or_file, "rb") if isinstance(path_or_file, str) else path_or_file
@@ -163,8 +166,12 @@ def load_scene(path_or_file, width: int = 1920, height: int = 1080, name: str | 
     if quads == "gpu":
         from . import quadgen
         quadgen.generate_quads(meshes, positions, square_weight, device)
-    return scene_from_parts(positions, colors, tex_coords, qnormals, bbox, meshes, materials, textures, width, height,
-                            name or (path_or_file if isinstance(path_or_file, str) else "scene"))
+    scene = scene_from_parts(positions, colors, tex_coords, qnormals, bbox, meshes, materials, textures, width, height,
+                             name or (path_or_file if isinstance(path_or_file, str) else "scene"))
+    if cluster:
+        from . import clustering
+        scene = clustering.cluster_scene(scene)
+    return scene
 
 
 def scene_from_parts(positions, colors, tex_coords, qnormals, bbox, meshes, materials, textures, width, height, name):
