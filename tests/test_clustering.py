@@ -95,7 +95,8 @@ def test_load_scene_can_cluster_while_loading():
 
     from lucid_b200 import scene_io
 
-    sc = pu.small_scenes()["soup"]
+    sc = scenes.quad_soup(num_quads=5_000, width=320, height=200)
+    sc["draw_calls"], sc["materials"] = [(0, 5_000, 0, 0)], [sc["materials"][0]]  # one mesh: five instances
     f = io.BytesIO()
     scene_io.save_scene(f, sc)
     f.seek(0)
