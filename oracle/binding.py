@@ -59,6 +59,7 @@ def load():
     lib.oracle_shade_probe.restype = C.c_uint32
     lib.oracle_set_reference_colour.argtypes = [vp, C.c_int]
     lib.oracle_set_comparators.argtypes = [vp, C.c_int]
+    lib.oracle_set_tie_report.argtypes = [vp, C.c_int]
     lib.oracle_set_reverse_ties.argtypes = [vp, C.c_int]
     lib.oracle_read_tie_pixels.argtypes = [vp, vp, vp]
     lib.oracle_read_compare_image.argtypes = [vp, C.c_int, vp]
@@ -122,6 +123,10 @@ class Oracle:
 
     def set_bin_range(self, begin, end):
         self.lib.oracle_set_bin_range(self.h, begin, end)
+
+    def set_tie_report(self, on: bool):
+        """Mark the pixels whose colour can depend on the order of depth-key ties while rendering (read_tie_pixels)."""
+        self.lib.oracle_set_tie_report(self.h, int(on))
 
     def set_reverse_ties(self, on: bool):
         """Test hook: every run of equal depth keys in reverse order (the canonical order is the triangle index)."""

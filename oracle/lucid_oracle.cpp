@@ -350,9 +350,10 @@ struct Oracle {
 	// tie_pixels marks the pixels covered by two or more entries of one run of equal keys -- the only pixels whose
 	// colour can depend on that convention; tie_stats: [0] lists with a run [1] entries in runs [2] marked pixels.
 	// reverse_ties renders the frame with every run reversed (test hook: the images may differ at marked pixels only).
+	// Off by default (oracle_set_tie_report): the frames timed as the CPU baseline do not carry the bookkeeping.
 	std::vector<uint8_t> tie_pixels;
 	unsigned long long tie_stats[3] = {};
-	bool reverse_ties = false;
+	bool report_ties = false, reverse_ties = false;
 	int *cnt(int which) { return counts.data() + (size_t)which * bin_count; }
 
 	void setup();
@@ -1525,7 +1526,7 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 
 			// runs of equal quantised depth: their order is a convention (triangle index), not the reference's
 			std::vector<std::pair<int, int>> tie_runs;
-			{
+			if(report_ties || reverse_ties) {
 				const int slot_bits = high ? 14 : 10;
 				for(size_t a = 0; a < list.size();) {
 					size_t b = a + 1;
@@ -1552,7 +1553,7 @@ void Oracle::rasterBin(int bin_id, bool high, bool &promote, u32 stats[4]) {
 			int halves = high ? 1 : 2;
 			for(int half = 0; half < halves; half++) {
 				int hb_y = pos_y + g * rows_per_group + half * 4; // top row of the half-block
-				{
+				if(!tie_runs.empty()) {
 					u32 tied = 0;
 					for(auto &r : tie_runs) {
 						u32 once = 0;
@@ -1770,7 +1771,7 @@ void Oracle::raster() {
 	bin_level.assign(bin_count, 0);
 	for(int mode = 0; mode < 3; mode++)
 		compare_image[mode].assign(comparators ? npix : 0, bg8);
-	tie_pixels.assign(npix, 0);
+	tie_pixels.assign(report_ties || reverse_ties ? npix : 0, 0);
 	tie_stats[0] = tie_stats[1] = tie_stats[2] = 0;
 
 	int *low = cnt(LUCID_CNT_LOW_BINS), *high = cnt(LUCID_CNT_HIGH_BINS);
@@ -2106,10 +2107,11 @@ void oracle_texture_samples(void *h, int slot, const float *uvl, int n, float *o
 }
 // 1: colour arithmetic in the reference's operation order (pow by polynomial, one rounding per operation);
 // 0 (default): the product's colour contract (fused multiply-adds, table sRGB) that the kernels reproduce bit for bit
+void oracle_set_tie_report(void *h, int on) { ((Oracle *)h)->report_ties = on != 0; }
 void oracle_set_reverse_ties(void *h, int on) { ((Oracle *)h)->reverse_ties = on != 0; }
 void oracle_read_tie_pixels(void *h, uint8_t *dst, unsigned long long *stats3) {
 	Oracle *o = (Oracle *)h;
-	if(dst)
+	if(dst && !o->tie_pixels.empty())
 		memcpy(dst, o->tie_pixels.data(), o->tie_pixels.size());
 	if(stats3)
 		memcpy(stats3, o->tie_stats, sizeof(o->tie_stats));

@@ -12,6 +12,7 @@ from tests import parity_util as pu
 def _oracle(sc, bin_rows=None):
     cfg, inst, cols, rects = api.prepare_frame(sc)
     o = Oracle(sc["width"], sc["height"], 0, 1 << 20, threads=8)
+    o.set_tie_report(True)
     if bin_rows:
         o.set_bin_rows(*bin_rows)
     o.set_scene(sc)

@@ -299,6 +299,7 @@ def test_depth_key_ties_are_reported_and_bound_the_order_dependence(small):
         out = []
         for reverse in (False, True):
             o = binding.Oracle(sc["width"], sc["height"], 0, 1 << 20, threads=8)
+            o.set_tie_report(True)
             o.set_reverse_ties(reverse)
             o.set_scene(sc)
             o.render(cfg, inst, cols, rects)

@@ -21,6 +21,7 @@ for ci in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3]:
     imgs, st, mask, covered = [], None, None, 0
     for reverse in (False, True):
         o = Oracle(sc["width"], sc["height"], 0, 4793490, threads=os.cpu_count() or 1)
+        o.set_tie_report(True)
         o.set_reverse_ties(reverse)
         o.set_scene(sc)
         o.render(cfg, inst, cols, rects)
