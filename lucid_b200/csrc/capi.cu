@@ -954,7 +954,7 @@ int lucid_compare_render(lucid_renderer *r, int32_t mode, const LucidConfig *con
 	if(rc)
 		return rc;
 	CU(cudaSetDevice(r->ci.device));
-	if(!r->cmp_order) {
+	if(!r->cmp_image) { // the image is allocated last: a partly failed attempt is repeated as a whole (the rest is freed with the handle)
 		CU(devAlloc(r, &r->cmp_order, (size_t)r->p.max_visible_quads));
 		CU(devAlloc(r, &r->cmp_scratch, compareScratchKeys(r->num_sms)));
 		CU(devAlloc(r, &r->cmp_ticket, 4));
@@ -962,7 +962,10 @@ int lucid_compare_render(lucid_renderer *r, int32_t mode, const LucidConfig *con
 	}
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	CU(cudaEventCreate(&t0));
-	CU(cudaEventCreate(&t1));
+	if(cudaError_t ee = cudaEventCreate(&t1); ee != cudaSuccess) {
+		cudaEventDestroy(t0);
+		return failCuda(r, ee, "lucid_compare_render: cudaEventCreate");
+	}
 	cudaEventRecord(t0, r->stream);
 	launchCompare(r->p, *config, mode, r->cmp_order, r->cmp_scratch, r->cmp_ticket, r->cmp_image, r->stream, r->num_sms);
 	cudaEventRecord(t1, r->stream);
