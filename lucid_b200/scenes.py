@@ -361,6 +361,45 @@ def planes(num_planes=32, width=1280, height=720, opacity=0.25, plane_size=2.0, 
                   width, height, colors=np.array(cols, np.uint32), name=name)
 
 
+def boxes(dims=(10, 10, 10), box_size=0.5, box_dist=0.1, opacity=0.5, width=1280, height=720, seed=123,
+          name="boxes"):
+    """The reference's '#boxes' scene (BoxesSetup::updateScene, src/scene_setup.cpp:159-196: dims jittered colour
+    cubes, scene opacity 0.5, OrbitingCamera({}, 10, 0.5, 0.8)).  Corners in fwk's Box::corners order (bit i of the
+    corner number picks max on axis i, libfwk/include/fwk/math/box.h:163-172), the twelve triangles of addBox
+    (scene_setup.cpp:134-145) paired into the six face quads Scene::generateQuads(4.0) makes of them, in its order and vertex
+    rotation (checked against the restated quad generator in tests/test_oracle.py).  The jitter of +-0.1 comes from this module's counter-based
+    generator instead of fwk's Random (std::mt19937_64 + libstdc++ distributions, SURVEY 8c)."""
+    dims = tuple(int(d) for d in dims)
+    rng = Rng(seed)
+    n = dims[0] * dims[1] * dims[2]
+    step = np.float32(box_size + box_dist)
+    grid = np.stack(np.meshgrid(np.arange(dims[0]), np.arange(dims[1]), np.arange(dims[2]), indexing="ij"), axis=3)
+    grid = grid.reshape(-1, 3).astype(np.float32)  # x outermost, z innermost, as the reference's loops
+    offset = -np.array(dims, np.float32) * step * np.float32(0.5)
+    jitter = np.stack([rng.uniform(-0.1, 0.1, n) for _ in range(3)], axis=1)
+    pos = offset[None, :] + grid * step + jitter
+    bits = np.array([[(c >> a) & 1 for a in range(3)] for c in range(8)], np.float32)
+    positions = (pos[:, None, :] + bits[None, :, :] * np.float32(box_size)).reshape(-1, 3).astype(np.float32)
+    faces = np.array([[3, 1, 0, 2], [7, 5, 1, 3], [7, 3, 2, 6], [0, 4, 6, 2], [0, 1, 5, 4], [4, 5, 7, 6]], np.uint32)
+    quads = (faces[None, :, :] + (np.arange(n, dtype=np.uint32) * np.uint32(8))[:, None, None]).reshape(-1, 4)
+    col_scale = 1.0 / np.maximum(np.array(dims, np.float32) - 1.0, 1.0)
+    rgb = (grid * col_scale[None, :] * np.float32(255.0)).astype(np.uint32)  # IColor(FColor): truncation
+    col = rgb[:, 0] | (rgb[:, 1] << np.uint32(8)) | (rgb[:, 2] << np.uint32(16)) | np.uint32(0xFF000000)
+    colors = np.repeat(col, 8)
+    # scene_opacity < 1 clears DrawCallOpt::is_opaque (src/lucid_app.cpp:646-650)
+    draw_calls = [(0, int(quads.shape[0]), 0, INST_HAS_VERTEX_COLORS)]
+    materials = [((1.0, 1.0, 1.0), opacity, (0.0, 0.0, 1.0, 1.0))]
+    camera = dict(kind="orbit", center=(0.0, 0.0, 0.0), distance=10.0, rot_h=0.5, rot_v=0.8)
+    return _scene(positions, quads, draw_calls, materials, camera, width, height, colors=colors, name=name)
+
+
+def box_triangles(num_boxes: int) -> np.ndarray:
+    """The triangle list addBox writes for `num_boxes` boxes (src/scene_setup.cpp:136-143), int32[12 n, 3]."""
+    tris = np.array([[0, 2, 3], [0, 3, 1], [1, 3, 7], [1, 7, 5], [2, 6, 7], [2, 7, 3],
+                     [0, 6, 2], [0, 4, 6], [0, 5, 4], [0, 1, 5], [4, 7, 6], [4, 5, 7]], np.int32)
+    return (tris[None, :, :] + (np.arange(num_boxes, dtype=np.int32) * 8)[:, None, None]).reshape(-1, 3)
+
+
 def get_config(index: int, scale: float = 1.0):
     """BASELINE.json configs[index]; scale < 1 shrinks primitive counts for tests."""
     if index == 0:

@@ -14,7 +14,7 @@ from tests.golden.make_oracle_golden import digest
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-SCENES = ["soup", "soup_close", "planes", "meshlets", "hairball", "arch"]
+SCENES = ["soup", "soup_close", "planes", "meshlets", "hairball", "arch", "boxes"]
 FULL_MVQ = 4793490
 
 

@@ -26,7 +26,7 @@ def golden():
         return json.load(f)
 
 
-@pytest.mark.parametrize("name", ["soup", "soup_close", "planes", "meshlets", "hairball", "arch"])
+@pytest.mark.parametrize("name", ["soup", "soup_close", "planes", "meshlets", "hairball", "arch", "boxes"])
 def test_oracle_matches_golden_and_invariants(name, small, golden):
     o = pu.run_oracle(small[name], threads=4)
     assert record(o) == golden[name]
@@ -318,3 +318,24 @@ def test_depth_key_ties_are_reported_and_bound_the_order_dependence(small):
     covered = frags > 0
     assert np.array_equal(mask != 0, covered)
     assert np.array_equal(img != img_r, covered)
+
+
+def test_boxes_scene_is_the_reference_s(small):
+    """'#boxes' (BoxesSetup::updateScene, src/scene_setup.cpp:159-196): the quads are exactly what the reference's
+    quad generator (restated in oracle/quadgen_oracle.cpp and pinned against the reference's own source) makes of
+    addBox's triangles -- order and vertex rotation included; every ray through closed boxes enters and leaves, so
+    (away from silhouette pixels) every pixel holds an even number of fragments; no bin overflows."""
+    from oracle import quadgen_binding as qb
+
+    sc = small["boxes"]
+    assert sc["quads"].shape == (6000, 4) and sc["positions"].shape == (8000, 3)
+    want = qb.run(qb.load_oracle(), sc["positions"], scenes.box_triangles(1000), 4.0, mode=0)
+    assert np.array_equal(np.asarray(want["quads"], np.uint32), sc["quads"]) and want["num_degenerate"] == 0
+    # colour ramp: FColor(float3(x, y, z) / 9, 1) truncated to bytes; the last box is white
+    assert int(sc["colors"][0]) == 0xFF000000 and int(sc["colors"][-1]) == 0xFFFFFFFF
+    o = pu.run_oracle(sc, threads=4)
+    st = api.decode_stats(o.info, o.bin_count, o.width, o.height)
+    assert st["input_quads"] == 6000 and st["promoted_bins"] == 0 and not (o.read_bin_levels() == 5).any()
+    covered = o.read_frag_counts()
+    covered = covered[covered > 0]
+    assert covered.size > 200_000 and (covered % 2 == 0).mean() > 0.999
