@@ -221,7 +221,7 @@ def test_checker_images_on_scenes():
 
 # ---- GPU ------------------------------------------------------------------------------------------------------------
 
-GPU_SCENES = ["soup", "soup_close", "planes", "meshlets", "hairball", "arch", "mixed_order"]
+GPU_SCENES = ["soup", "soup_close", "planes", "meshlets", "hairball", "arch", "boxes", "mixed_order"]
 
 
 @pytest.fixture(scope="module")
@@ -319,3 +319,19 @@ def test_cuda_comparators_on_long_lists():
             assert np.array_equal(got, o.read_compare_image(mode))
     finally:
         r.close()
+
+
+def test_checker_comparator_images_match_committed_digests():
+    """tests/golden/comparators_golden.json (written by make_comparators_golden.py): the checker's comparator modes
+    do not drift silently."""
+    import json
+    import os
+
+    from tests.golden import make_comparators_golden as mk
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "comparators_golden.json")) as f:
+        golden = json.load(f)
+    scenes_ = mk.scenes_to_pin()
+    assert set(golden) == set(scenes_)
+    for name, sc in scenes_.items():
+        assert mk.record(_run_oracle(sc)) == golden[name], name
