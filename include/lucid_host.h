@@ -68,6 +68,14 @@ int lucid_host_build_instances(const LucidDrawCall *dcs, int num_dcs, const Luci
 /* instance_packet_size = clamp(num_instances / (max_dispatches / 2), 1, 2) */
 int lucid_host_packet_size(int num_instances, int max_dispatches);
 
+/* Spatially coherent instances (the goal of meshPartition, src/meshlet.cpp:68-222): the order in which
+ * the num_quads quads (4 vertex indices each) of one draw call should be listed so that the 1024-quad instances
+ * uploadInstances cuts (src/lucid_renderer.cpp:352-429) have small bounding boxes -- ascending 30-bit Morton code of
+ * the quad centroids inside their bounding box, equal codes in input order.  out_order[i] = index of the quad that
+ * goes to place i.  Returns 0, or -1 on bad arguments (null pointers, an index at or above num_verts). */
+int lucid_host_cluster_order(const float *positions, int32_t num_verts, const uint32_t *quads, int32_t num_quads,
+							 int32_t *out_order);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,7 +94,7 @@ C_ABI_SYMBOLS = [
     "lucid_ipc_export_image", "lucid_ipc_open_image", "lucid_ipc_close_image",
     "lucid_debug_sample_texture", "lucid_sync_pointer", "lucid_ipc_export_sync", "lucid_signal", "lucid_wait_flags", "lucid_set_frame_gate",
     "lucid_host_orbit_camera", "lucid_host_default_lighting", "lucid_host_make_config",
-    "lucid_host_camera_matrices", "lucid_host_build_instances", "lucid_host_packet_size",
+    "lucid_host_camera_matrices", "lucid_host_build_instances", "lucid_host_packet_size", "lucid_host_cluster_order",
     "lucid_quadgen", "lucid_quadgen_last_error", "lucid_read_debug_records", "lucid_compare_render",
 ]
 
@@ -172,6 +172,7 @@ def _host_prototypes(lib):
     lib.lucid_host_build_instances.argtypes = [C.POINTER(DrawCall), C.c_int, C.POINTER(Material), C.c_int, vp, vp,
                                                vp, C.c_int]
     lib.lucid_host_packet_size.argtypes = [C.c_int, C.c_int]
+    lib.lucid_host_cluster_order.argtypes = [vp, C.c_int32, vp, C.c_int32, vp]
 
 
 _host_lib = None

@@ -41,7 +41,22 @@ def morton_keys(points: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> np.ndarra
 
 
 def cluster_order(positions: np.ndarray, quads: np.ndarray) -> np.ndarray:
-    """Permutation that puts the quads in Morton order of their centroids (stable: equal keys keep their order)."""
+    """Permutation that puts the quads in Morton order of their centroids (stable: equal keys keep their order):
+    lucid_host_cluster_order of the C++ host library (include/lucid_host.h)."""
+    from . import api
+
+    positions = np.ascontiguousarray(positions, np.float32)
+    quads = np.ascontiguousarray(quads, np.uint32)
+    order = np.zeros(quads.shape[0], np.int32)
+    rc = api.load_host_library().lucid_host_cluster_order(api._ptr(positions), positions.shape[0], api._ptr(quads),
+                                                          quads.shape[0], api._ptr(order))
+    if rc != 0:
+        raise ValueError("cluster_order: a quad refers to a vertex that does not exist")
+    return order.astype(np.int64)
+
+
+def cluster_order_numpy(positions: np.ndarray, quads: np.ndarray) -> np.ndarray:
+    """The same order stated in numpy (what tests hold the C++ function to)."""
     if quads.shape[0] == 0:
         return np.zeros(0, np.int64)
     centroids = positions[quads.reshape(-1)].reshape(-1, 4, 3).mean(axis=1, dtype=np.float64).astype(np.float32)

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -115,6 +116,56 @@ void lucid_host_camera_matrices(const LucidCamera *camera, float view[16], float
 	M4 v = viewMatrix(cameraBasis(*camera)), p = projMatrix(*camera);
 	memcpy(view, &v, sizeof(v));
 	memcpy(proj, &p, sizeof(p));
+}
+
+static uint32_t spreadBits3(uint32_t v) { // 10 bits -> every bit followed by two zero bits
+	v &= 0x3ffu;
+	v = (v | (v << 16)) & 0x030000ffu;
+	v = (v | (v << 8)) & 0x0300f00fu;
+	v = (v | (v << 4)) & 0x030c30c3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+
+int lucid_host_cluster_order(const float *positions, int32_t num_verts, const uint32_t *quads, int32_t num_quads,
+							 int32_t *out_order) {
+	if(num_quads < 0 || num_verts < 0 || (num_quads > 0 && (!positions || !quads || !out_order)))
+		return -1;
+	if(num_quads == 0)
+		return 0;
+	std::vector<float> cen((size_t)num_quads * 3);
+	float lo[3], hi[3];
+	for(int32_t q = 0; q < num_quads; q++) {
+		double sum[3] = {0.0, 0.0, 0.0};
+		for(int k = 0; k < 4; k++) {
+			const uint32_t vi = quads[(size_t)q * 4 + k];
+			if(vi >= (uint32_t)num_verts)
+				return -1;
+			for(int a = 0; a < 3; a++)
+				sum[a] += (double)positions[(size_t)vi * 3 + a];
+		}
+		for(int a = 0; a < 3; a++) {
+			const float c = (float)(sum[a] / 4.0);
+			cen[(size_t)q * 3 + a] = c;
+			lo[a] = q == 0 ? c : std::min(lo[a], c);
+			hi[a] = q == 0 ? c : std::max(hi[a], c);
+		}
+	}
+	std::vector<uint32_t> keys((size_t)num_quads);
+	for(int32_t q = 0; q < num_quads; q++) {
+		uint32_t key = 0;
+		for(int a = 0; a < 3; a++) {
+			const float extent = std::max(hi[a] - lo[a], 1e-30f);
+			float t = (cen[(size_t)q * 3 + a] - lo[a]) / extent * 1024.0f;
+			t = std::min(std::max(t, 0.0f), 1023.0f);
+			key |= spreadBits3((uint32_t)t) << a;
+		}
+		keys[q] = key;
+	}
+	for(int32_t q = 0; q < num_quads; q++)
+		out_order[q] = q;
+	std::stable_sort(out_order, out_order + num_quads, [&](int32_t a, int32_t b) { return keys[a] < keys[b]; });
+	return 0;
 }
 
 int lucid_host_packet_size(int num_instances, int max_dispatches) {

@@ -107,3 +107,19 @@ def test_load_scene_can_cluster_while_loading():
     assert np.array_equal(clustered["quads"], clustering.cluster_scene(plain)["quads"])
     assert clustering.box_surface_area(clustering.instance_boxes(clustered)).sum() < \
         clustering.box_surface_area(clustering.instance_boxes(plain)).sum()
+
+
+def test_native_order_equals_the_numpy_statement():
+    """lucid_host_cluster_order (C++, include/lucid_host.h) against clustering.cluster_order_numpy, element for element."""
+    small = pu.small_scenes()
+    for name in ("soup", "meshlets", "hairball", "arch", "boxes"):
+        sc = small[name]
+        assert np.array_equal(clustering.cluster_order(sc["positions"], sc["quads"]),
+                              clustering.cluster_order_numpy(sc["positions"], sc["quads"])), name
+    # degenerate inputs: no quads; all centroids equal (input order is kept); an index outside the vertex array
+    pos = np.zeros((4, 3), np.float32)
+    assert clustering.cluster_order(pos, np.zeros((0, 4), np.uint32)).size == 0
+    same = np.tile(np.arange(4, dtype=np.uint32), (5, 1))
+    assert clustering.cluster_order(pos, same).tolist() == [0, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        clustering.cluster_order(pos, np.array([[0, 1, 2, 4]], np.uint32))
