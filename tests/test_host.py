@@ -201,3 +201,16 @@ def test_shared_host_images_are_one_memory():
     finally:
         a.close()
     assert not os.path.exists("/dev/shm/" + name)
+
+
+def test_public_headers_are_plain_c():
+    """The drop-in boundary is a C ABI: every header under include/ except the C++ facade compiles as C99 on its own
+    (plain pointers and sizes, no C++ or CUDA types in a signature)."""
+    import subprocess
+
+    inc = os.path.join(HERE, "..", "include")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    for hdr in ("lucid_abi.h", "lucid_b200.h", "lucid_host.h", "lucid_quadgen.h"):
+        res = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c", "-"],
+                             input=f'#include "{hdr}"\n', capture_output=True, text=True)
+        assert res.returncode == 0, hdr + ": " + res.stderr
