@@ -331,6 +331,9 @@ def test_boxes_scene_is_the_reference_s(small):
     assert sc["quads"].shape == (6000, 4) and sc["positions"].shape == (8000, 3)
     want = qb.run(qb.load_oracle(), sc["positions"], scenes.box_triangles(1000), 4.0, mode=0)
     assert np.array_equal(np.asarray(want["quads"], np.uint32), sc["quads"]) and want["num_degenerate"] == 0
+    if qb.reference_available():  # the reference's own src/quad_generator.cpp, where /root/reference is mounted
+        ref = qb.run(qb.load_reference(), sc["positions"], scenes.box_triangles(1000), 4.0)
+        assert np.array_equal(np.asarray(ref["quads"], np.uint32), sc["quads"])
     # colour ramp: FColor(float3(x, y, z) / 9, 1) truncated to bytes; the last box is white
     assert int(sc["colors"][0]) == 0xFF000000 and int(sc["colors"][-1]) == 0xFFFFFFFF
     o = pu.run_oracle(sc, threads=4)

@@ -46,7 +46,7 @@ def test_layout_of_a_tiny_scene():
     assert struct.unpack("<i??ffff", tail[26:48]) == (-1, False, True, 0.0, 0.0, 1.0, 1.0)
 
 
-@pytest.mark.parametrize("name", ["soup", "meshlets", "arch", "hairball"])
+@pytest.mark.parametrize("name", ["soup", "meshlets", "arch", "hairball", "boxes"])
 def test_round_trip_gives_the_same_frame(name):
     """save -> load reproduces geometry, draw calls, materials and atlases, and the checker renders the reloaded
     scene to the committed digests of the original."""
