@@ -207,7 +207,7 @@ for k in range(24):
 from tests import parity_util as pu  # noqa: E402
 out["bin_scenes"] = []
 small = pu.small_scenes()
-for name in ("soup_close", "arch", "soup", "meshlets", "boxes", "planes"):
+for name in ("soup_close", "arch", "soup", "meshlets", "boxes", "planes", "hairball_mini"):
     sc = small[name]
     cfg, inst, inst_cols, inst_rects = api.prepare_frame(sc)
     cw = np.frombuffer(bytes(cfg), np.uint32).copy()

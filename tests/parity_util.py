@@ -21,6 +21,8 @@ def small_scenes():
     out["hairball"] = scenes.hairball(num_strands=2_500, segments=48, width=480, height=270, ribbon_width=0.08)
     out["arch"] = scenes.architecture(num_small=30_000, num_large=60, width=960, height=540, atlas_opaque=256,
                                       atlas_trans=128, levels=5)
+    # small enough for the reference-source harness (32768 visible quads, tests/golden/make_ref_shader_golden.py): HIGH bins
+    out["hairball_mini"] = scenes.hairball(num_strands=600, segments=48, width=160, height=96, ribbon_width=0.5)
     out["boxes"] = scenes.boxes()  # the reference's '#boxes' (src/scene_setup.cpp:159-196), 1280x720
     return out
 
