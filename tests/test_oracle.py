@@ -26,7 +26,7 @@ def golden():
         return json.load(f)
 
 
-@pytest.mark.parametrize("name", ["soup", "soup_close", "planes", "meshlets", "hairball", "arch", "boxes"])
+@pytest.mark.parametrize("name", ["soup", "soup_close", "planes", "meshlets", "hairball", "arch", "boxes", "hairball_mini"])
 def test_oracle_matches_golden_and_invariants(name, small, golden):
     o = pu.run_oracle(small[name], threads=4)
     assert record(o) == golden[name]
