@@ -214,3 +214,24 @@ def test_public_headers_are_plain_c():
         res = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c", "-"],
                              input=f'#include "{hdr}"\n', capture_output=True, text=True)
         assert res.returncode == 0, hdr + ": " + res.stderr
+
+
+def test_bench_roofline_arithmetic():
+    """bench.algorithmic_bytes: SURVEY 8(d)'s byte formulas with this implementation's record sizes, and the
+    depth-complexity summary of the bench line's counters."""
+    import bench
+
+    stats = dict(input_quads=1000, visible_small=600, visible_large=40, bin_quads=900, bin_tris=300, low_bins=7, high_bins=3)
+    plain = bench.algorithmic_bytes(stats, {}, 1920, 1080)
+    n_vis, t_bin = 640, 2 * 900 + 300
+    assert plain["setup"] == 64 * 1000 + (4 + 192) * n_vis
+    assert plain["bin_count"] == 4 * n_vis + 64 * 40
+    assert plain["bin_dispatch"] == plain["bin_count"] + 4 * 1200
+    assert plain["raster"] == 4 * 1200 + 96 * t_bin + 4 * 10 * 1024
+    full = bench.algorithmic_bytes(stats, dict(colors=1, normals=1, uvs=1), 1920, 1080)
+    assert full["setup"] - plain["setup"] == 64 * n_vis and full["raster"] - plain["raster"] == 32 * t_bin
+    frag = np.zeros((4, 8), np.uint32)
+    frag[0, :4] = [1, 2, 3, 100]
+    d = bench.depth_complexity(frag)
+    assert d == {"covered_frac": 0.125, "median": 2.5, "p99": float(np.percentile([1, 2, 3, 100], 99)), "max": 100}
+    assert bench.depth_complexity(np.zeros((2, 2), np.uint32))["covered_frac"] == 0.0
