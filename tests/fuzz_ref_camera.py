@@ -42,5 +42,18 @@ for k in range(n):
         bad += 1
         if bad <= 3:
             print("differs:", kind, args, str(e)[:300])
-print("fuzz:", n, "cameras, outside the tolerances:", bad)
-sys.exit(1 if bad else 0)
+# material colour of uploadInstances: u32(IColor(FColor(diffuse, opacity))) (src/lucid_renderer.cpp:364-365), exact
+from lucid_b200 import api  # noqa: E402
+
+bad_colors = 0
+for k in range(n):
+    c = rng.uniform(-0.2, 1.3, 4) if k % 4 == 0 else rng.integers(0, 256, 4) / 255.0 + rng.choice([0.0, 1e-7, -1e-7])
+    c = [float(np.float32(v)) for v in c]
+    want = int(subprocess.run([BIN, "color"] + [repr(v) for v in c], check=True, capture_output=True, text=True).stdout.split()[1])
+    _, cols, _ = api.build_instances([(0, 1, 0, 0)], [((c[0], c[1], c[2]), c[3], (0.0, 0.0, 1.0, 1.0))])
+    if int(cols[0]) != want:
+        bad_colors += 1
+        if bad_colors <= 3:
+            print("colour differs:", c, hex(int(cols[0])), hex(want))
+print("fuzz:", n, "cameras, outside the tolerances:", bad, ";", n, "material colours, differing:", bad_colors)
+sys.exit(1 if bad or bad_colors else 0)
